@@ -1,0 +1,55 @@
+"""Build recipe for libapde.so (hand-written CUDA for sm_100a behind the C ABI of include/apde.h).
+
+In-tree build: the .so lands in apde_mvs_b200/_build/ and travels to the GPU box with the snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT_DIR, "libapde.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+SOURCES = ["apde_api.cu", "apde_kernels.cu", "apde_apd.cu", "apde_maps.cu", "apde_fusion.cu"]
+FLAGS = [
+    "-std=c++17", "-O3", "--use_fast_math", "-lineinfo",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-ccbin", "/usr/bin/g++",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+]
+
+
+def _newer(src, dst):
+    return not os.path.exists(dst) or os.path.getmtime(src) > os.path.getmtime(dst)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OUT_DIR, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(HERE, "..", "include", "apde.h"))
+    objs = []
+    procs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(OUT_DIR, s.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _newer(src, obj) or any(_newer(h, obj) for h in headers):
+            log = open(obj + ".log", "w")
+            procs.append((s, subprocess.Popen([NVCC] + FLAGS + ["-c", src, "-o", obj], stdout=log, stderr=subprocess.STDOUT), log))
+    failed = False
+    for s, p, log in procs:
+        rc = p.wait()
+        log.close()
+        if rc != 0 or verbose:
+            sys.stderr.write(open(os.path.join(OUT_DIR, s.replace(".cu", ".o")) + ".log").read())
+        failed |= rc != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    if procs or not os.path.exists(LIB):
+        subprocess.check_call([NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs + ["-lcudart"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

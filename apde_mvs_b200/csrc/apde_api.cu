@@ -1,0 +1,858 @@
+// apde_api.cu -- host driver behind the C ABI of include/apde.h: scene-resident images / cameras / maps, pyramid
+// levels as one layered texture, per-problem set-up (the reference's InuputInitialization + CudaSpaceInitialization,
+// APD.cpp:501-814, without any host round trip), the stage launcher and the multi-scale schedule of main.cpp:303-367.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/apde.h"
+#include "apde_kernels.h"
+#include "apde_fusion.h"
+
+using namespace apde;
+
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) return fail(APDE_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct ViewStore {
+    apde_camera cam;
+    std::vector<int> src;
+    uint8_t *d_gray = nullptr, *d_bgr = nullptr;
+    int mw = 0, mh = 0;  // size of the stored maps (0 = none yet)
+    float *d_normal = nullptr;
+    uint8_t *d_weak = nullptr, *d_conf = nullptr;
+    bool has_conf = false;
+};
+
+struct apde_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int V = 0, W = 0, H = 0;
+    bool committed = false;
+    std::vector<ViewStore> views;
+    float *d_depth_pool[2] = {nullptr, nullptr};  // [V][W*H] ; [1] only allocated in Jacobi mode
+    int cur = 0;
+    // pyramid level (one alive at a time)
+    int level_scale = 0, lw = 0, lh = 0;
+    cudaArray_t level_arr = nullptr;
+    cudaTextureObject_t level_tex = 0;
+    float *d_level_lin = nullptr;  // [V][lh*lw]
+    // problem working set (allocated once at full resolution)
+    bool ws_alloc = false;
+    float4 *d_planes = nullptr, *d_fit = nullptr;
+    float *d_costs = nullptr, *d_depthws = nullptr, *d_scratch_depth = nullptr, *d_scratch_normal = nullptr;
+    uint32_t *d_sel = nullptr;
+    uint4 *d_vw = nullptr;
+    uint8_t *d_weak = nullptr, *d_conf = nullptr, *d_reliable = nullptr;
+    short2 *d_nearest = nullptr, *d_anchors = nullptr;
+    unsigned long long *d_counters = nullptr;
+    uint64_t launches = 0;
+    // current problem
+    bool problem_active = false;
+    int ref_view = -1;
+    bool jacobi_write = false;
+    apde_params params;
+    std::vector<apde_camera> cams;
+    PassK K;
+    // fusion state
+    uint8_t *d_skip = nullptr;
+};
+
+extern "C" {
+
+const char *apde_last_error(void) { return g_err.c_str(); }
+const char *apde_version(void) { return "apde-b200 0.1 sm_100a"; }
+
+void apde_params_default(apde_params *p) {  // main.h:80-100
+    memset(p, 0, sizeof(*p));
+    p->max_iterations = 3;
+    p->num_images = 5;
+    p->top_k = 4;
+    p->depth_min = 0.0f;
+    p->depth_max = 1.0f;
+    p->geom_consistency = 0;
+    p->use_impetus = 1;
+    p->strong_radius = 5;
+    p->strong_increment = 2;
+    p->weak_radius = 5;
+    p->weak_increment = 5;
+    p->use_APD = 1;
+    p->use_sa = 1;
+    p->weak_peak_radius = 2;
+    p->rotate_time = 4;
+    p->ransac_threshold = 0.005f;
+    p->geom_factor = 0.2f;
+    p->state = APDE_FIRST_INIT;
+}
+
+void apde_schedule_default(apde_schedule *s) {
+    memset(s, 0, sizeof(*s));
+    s->rounds = 0;
+    s->geom_iterations = 3;
+    s->jacobi = 0;
+    s->use_impetus = 1;
+    s->geom_factor = 0.2f;
+    s->seed = 1;
+}
+
+int apde_create(int device, apde_context **out) {
+    if (!out) return fail(APDE_ERR_ARG, "apde_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(APDE_ERR_CUDA, "apde_create: no CUDA device (%s); libapde has no CPU fallback",
+                    e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(APDE_ERR_ARG, "apde_create: device %d out of range (%d devices)", device, n);
+    CU(cudaSetDevice(device));
+    apde_context *c = new apde_context();
+    c->device = device;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    CU(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long)));
+    *out = c;
+    return APDE_OK;
+}
+
+static void free_level(apde_context *c) {
+    if (c->level_tex) cudaDestroyTextureObject(c->level_tex);
+    if (c->level_arr) cudaFreeArray(c->level_arr);
+    if (c->d_level_lin) cudaFree(c->d_level_lin);
+    c->level_tex = 0; c->level_arr = nullptr; c->d_level_lin = nullptr; c->level_scale = 0;
+}
+static void free_scene(apde_context *c) {
+    for (auto &v : c->views) {
+        cudaFree(v.d_gray); cudaFree(v.d_bgr); cudaFree(v.d_normal); cudaFree(v.d_weak); cudaFree(v.d_conf);
+    }
+    c->views.clear();
+    cudaFree(c->d_depth_pool[0]); cudaFree(c->d_depth_pool[1]);
+    c->d_depth_pool[0] = c->d_depth_pool[1] = nullptr;
+    free_level(c);
+    if (c->ws_alloc) {
+        cudaFree(c->d_planes); cudaFree(c->d_fit); cudaFree(c->d_costs); cudaFree(c->d_depthws);
+        cudaFree(c->d_scratch_depth); cudaFree(c->d_scratch_normal); cudaFree(c->d_sel); cudaFree(c->d_vw);
+        cudaFree(c->d_weak); cudaFree(c->d_conf); cudaFree(c->d_reliable); cudaFree(c->d_nearest); cudaFree(c->d_anchors);
+        c->ws_alloc = false;
+    }
+    cudaFree(c->d_skip);
+    c->d_skip = nullptr;
+    c->committed = false;
+    c->problem_active = false;
+}
+
+void apde_destroy(apde_context *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_scene(c);
+    cudaFree(c->d_counters);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ------------------------------------------------------------------------------------------------ scene
+int apde_scene_begin(apde_context *c, int num_views, int width, int height) {
+    if (!c) return fail(APDE_ERR_ARG, "null context");
+    if (num_views <= 0 || width <= 0 || height <= 0) return fail(APDE_ERR_ARG, "scene_begin: bad dimensions");
+    if (width > 32768 || height > 32768 || num_views > 2048)
+        return fail(APDE_ERR_ARG, "scene_begin: %dx%d x %d views exceeds the layered-texture limits", width, height, num_views);
+    CU(cudaSetDevice(c->device));
+    free_scene(c);
+    c->V = num_views; c->W = width; c->H = height;
+    c->views.resize(num_views);
+    const size_t P = (size_t)width * height;
+    for (auto &v : c->views) {
+        CU(cudaMalloc(&v.d_gray, P));
+        CU(cudaMalloc(&v.d_normal, P * 3 * sizeof(float)));
+        CU(cudaMalloc(&v.d_weak, P));
+        CU(cudaMalloc(&v.d_conf, P));
+        memset(&v.cam, 0, sizeof(v.cam));
+    }
+    CU(cudaMalloc(&c->d_depth_pool[0], (size_t)num_views * P * sizeof(float)));
+    CU(cudaMemsetAsync(c->d_depth_pool[0], 0, (size_t)num_views * P * sizeof(float), c->stream));
+    c->cur = 0;
+    return APDE_OK;
+}
+
+int apde_scene_set_view(apde_context *c, int view, const uint8_t *gray, const uint8_t *bgr, const apde_camera *cam) {
+    if (!c || view < 0 || view >= c->V || !gray || !cam) return fail(APDE_ERR_ARG, "scene_set_view: bad argument");
+    CU(cudaSetDevice(c->device));
+    ViewStore &v = c->views[view];
+    const size_t P = (size_t)c->W * c->H;
+    CU(cudaMemcpyAsync(v.d_gray, gray, P, cudaMemcpyHostToDevice, c->stream));
+    if (bgr) {
+        if (!v.d_bgr) CU(cudaMalloc(&v.d_bgr, P * 3));
+        CU(cudaMemcpyAsync(v.d_bgr, bgr, P * 3, cudaMemcpyHostToDevice, c->stream));
+    }
+    v.cam = *cam;
+    v.cam.width = c->W;
+    v.cam.height = c->H;
+    CU(cudaStreamSynchronize(c->stream));
+    return APDE_OK;
+}
+
+int apde_scene_set_pairs(apde_context *c, int view, int num_src, const int32_t *src_views) {
+    if (!c || view < 0 || view >= c->V || num_src < 0 || (num_src > 0 && !src_views))
+        return fail(APDE_ERR_ARG, "scene_set_pairs: bad argument");
+    if (num_src > APDE_MAX_IMAGES - 1)
+        return fail(APDE_ERR_ARG, "Can't process so much images: %d", num_src + 1);  // APD.cpp:528-531
+    for (int i = 0; i < num_src; ++i)
+        if (src_views[i] < 0 || src_views[i] >= c->V) return fail(APDE_ERR_ARG, "scene_set_pairs: source %d out of range", src_views[i]);
+    c->views[view].src.assign(src_views, src_views + num_src);
+    return APDE_OK;
+}
+
+static int alloc_workspace(apde_context *c) {
+    if (c->ws_alloc) return APDE_OK;
+    const size_t P = (size_t)c->W * c->H;
+    CU(cudaMalloc(&c->d_planes, P * sizeof(float4)));
+    CU(cudaMalloc(&c->d_fit, P * sizeof(float4)));
+    CU(cudaMalloc(&c->d_costs, P * sizeof(float)));
+    CU(cudaMalloc(&c->d_depthws, P * sizeof(float) * APDE_MAX_IMAGES));
+    CU(cudaMalloc(&c->d_scratch_depth, P * sizeof(float)));
+    CU(cudaMalloc(&c->d_scratch_normal, P * 3 * sizeof(float)));
+    CU(cudaMalloc(&c->d_sel, P * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->d_vw, P * sizeof(uint4)));
+    CU(cudaMalloc(&c->d_weak, P));
+    CU(cudaMalloc(&c->d_conf, P));
+    CU(cudaMalloc(&c->d_reliable, P));
+    CU(cudaMalloc(&c->d_nearest, P * sizeof(short2)));
+    CU(cudaMalloc(&c->d_anchors, P * APDE_ANCHOR_NUM * sizeof(short2)));
+    CU(cudaMemsetAsync(c->d_vw, 0, P * sizeof(uint4), c->stream));
+    CU(cudaMemsetAsync(c->d_sel, 0, P * sizeof(uint32_t), c->stream));
+    c->ws_alloc = true;
+    return APDE_OK;
+}
+
+int apde_scene_commit(apde_context *c) {
+    if (!c || c->V <= 0) return fail(APDE_ERR_STATE, "scene_commit: no scene");
+    CU(cudaSetDevice(c->device));
+    int rc = alloc_workspace(c);
+    if (rc) return rc;
+    c->committed = true;
+    return APDE_OK;
+}
+
+// build the pyramid level for scale_size: INTER_LINEAR resize of every view (APD.cpp:564-588) into one layered texture
+static int ensure_level(apde_context *c, int scale) {
+    if (c->level_scale == scale) return APDE_OK;
+    free_level(c);
+    const float factor = 1.0f / (float)scale;
+    const int lw = (int)std::round(c->W * factor), lh = (int)std::round(c->H * factor);
+    if (lw < 16 || lh < 16) return fail(APDE_ERR_ARG, "pyramid level %dx%d too small", lw, lh);
+    const size_t P = (size_t)lw * lh;
+    CU(cudaMalloc(&c->d_level_lin, (size_t)c->V * P * sizeof(float)));
+    for (int v = 0; v < c->V; ++v)
+        CU(launch_resize_linear_u8(c->views[v].d_gray, c->W, c->H, c->d_level_lin + (size_t)v * P, lw, lh, c->stream));
+    c->launches += c->V;
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+    CU(cudaMalloc3DArray(&c->level_arr, &desc, make_cudaExtent(lw, lh, c->V), cudaArrayLayered));
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.srcPtr = make_cudaPitchedPtr(c->d_level_lin, (size_t)lw * sizeof(float), lw, lh);
+    cp.dstArray = c->level_arr;
+    cp.extent = make_cudaExtent(lw, lh, c->V);
+    cp.kind = cudaMemcpyDeviceToDevice;
+    CU(cudaMemcpy3DAsync(&cp, c->stream));
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = c->level_arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    // the reference asks for "wrap" with unnormalised coordinates, which CUDA serves as clamp (APD.cpp:701-705)
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    CU(cudaCreateTextureObject(&c->level_tex, &rd, &td, nullptr));
+    c->level_scale = scale; c->lw = lw; c->lh = lh;
+    return APDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ view maps
+int apde_view_download(apde_context *c, int view, float *depth, float *normal, uint8_t *weak, uint8_t *conf, int *width,
+                       int *height) {
+    if (!c || view < 0 || view >= c->V) return fail(APDE_ERR_ARG, "view_download: bad view");
+    CU(cudaSetDevice(c->device));
+    ViewStore &v = c->views[view];
+    if (width) *width = v.mw;
+    if (height) *height = v.mh;
+    const size_t P = (size_t)v.mw * v.mh, Pfull = (size_t)c->W * c->H;
+    if (P == 0) return APDE_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    if (depth) CU(cudaMemcpy(depth, c->d_depth_pool[c->cur] + (size_t)view * Pfull, P * sizeof(float), cudaMemcpyDeviceToHost));
+    if (normal) CU(cudaMemcpy(normal, v.d_normal, P * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (weak) CU(cudaMemcpy(weak, v.d_weak, P, cudaMemcpyDeviceToHost));
+    if (conf) CU(cudaMemcpy(conf, v.d_conf, P, cudaMemcpyDeviceToHost));
+    return APDE_OK;
+}
+
+int apde_view_upload(apde_context *c, int view, const float *depth, const float *normal, const uint8_t *weak,
+                     const uint8_t *conf, int width, int height) {
+    if (!c || view < 0 || view >= c->V || width <= 0 || height <= 0 || width > c->W || height > c->H)
+        return fail(APDE_ERR_ARG, "view_upload: bad argument");
+    CU(cudaSetDevice(c->device));
+    ViewStore &v = c->views[view];
+    const size_t P = (size_t)width * height, Pfull = (size_t)c->W * c->H;
+    CU(cudaStreamSynchronize(c->stream));
+    if (depth) CU(cudaMemcpy(c->d_depth_pool[c->cur] + (size_t)view * Pfull, depth, P * sizeof(float), cudaMemcpyHostToDevice));
+    if (normal) CU(cudaMemcpy(v.d_normal, normal, P * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    if (weak) CU(cudaMemcpy(v.d_weak, weak, P, cudaMemcpyHostToDevice));
+    if (conf) { CU(cudaMemcpy(v.d_conf, conf, P, cudaMemcpyHostToDevice)); v.has_conf = true; }
+    v.mw = width; v.mh = height;
+    return APDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ problem
+static void mat3_mul(const double *A, const double *B, double *C) {
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += A[3 * i + k] * B[3 * k + j];
+        C[3 * i + j] = s;
+    }
+}
+
+// camera-pair constants (double precision on the host).  Zero-skew pinhole K as the reference assumes (APD.cu:375-393).
+static void make_view_k(const apde_camera &rc, const apde_camera &sc, int layer, ViewK &vk) {
+    double Rr[9], Rs[9], Kr[9], Ks[9], Kri[9], Ksi[9];
+    for (int i = 0; i < 9; ++i) { Rr[i] = rc.R[i]; Rs[i] = sc.R[i]; Kr[i] = rc.K[i]; Ks[i] = sc.K[i]; }
+    auto kinv = [](const double *K, double *Ki) {
+        const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+        Ki[0] = 1.0 / fx; Ki[1] = 0; Ki[2] = -cx / fx;
+        Ki[3] = 0; Ki[4] = 1.0 / fy; Ki[5] = -cy / fy;
+        Ki[6] = 0; Ki[7] = 0; Ki[8] = 1.0;
+    };
+    auto kfwd = [](const double *K, double *Kf) {  // what ComputeHomography applies for the source: fx, fy, cx, cy, K[8]
+        Kf[0] = K[0]; Kf[1] = 0; Kf[2] = K[2];
+        Kf[3] = 0; Kf[4] = K[4]; Kf[5] = K[5];
+        Kf[6] = 0; Kf[7] = 0; Kf[8] = K[8];
+    };
+    double Krf[9], Ksf[9];
+    kfwd(Kr, Krf); kfwd(Ks, Ksf);
+    kinv(Kr, Kri); kinv(Ks, Ksi);
+    double Cr[3], Cs[3];
+    for (int j = 0; j < 3; ++j) {
+        Cr[j] = -(Rr[0 + j] * rc.t[0] + Rr[3 + j] * rc.t[1] + Rr[6 + j] * rc.t[2]);
+        Cs[j] = -(Rs[0 + j] * sc.t[0] + Rs[3 + j] * sc.t[1] + Rs[6 + j] * sc.t[2]);
+    }
+    double RrT[9], RsT[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { RrT[3 * i + j] = Rr[3 * j + i]; RsT[3 * i + j] = Rs[3 * j + i]; }
+    double Rrel[9], RrelT[9];
+    mat3_mul(Rs, RrT, Rrel);   // R_s R_r^T
+    mat3_mul(Rr, RsT, RrelT);  // R_r R_s^T
+    double dC[3] = {Cr[0] - Cs[0], Cr[1] - Cs[1], Cr[2] - Cs[2]};
+    double trel[3], treli[3];
+    for (int i = 0; i < 3; ++i) {
+        trel[i] = Rs[3 * i] * dC[0] + Rs[3 * i + 1] * dC[1] + Rs[3 * i + 2] * dC[2];
+        treli[i] = -(Rr[3 * i] * dC[0] + Rr[3 * i + 1] * dC[1] + Rr[3 * i + 2] * dC[2]);
+    }
+    double T[9], A[9], Ai[9];
+    mat3_mul(Ksf, Rrel, T); mat3_mul(T, Kri, A);
+    mat3_mul(Krf, RrelT, T); mat3_mul(T, Ksi, Ai);
+    for (int i = 0; i < 9; ++i) { vk.A[i] = (float)A[i]; vk.Ai[i] = (float)Ai[i]; }
+    for (int i = 0; i < 3; ++i) {
+        vk.b[i] = (float)(Ksf[3 * i] * trel[0] + Ksf[3 * i + 1] * trel[1] + Ksf[3 * i + 2] * trel[2]);
+        vk.bi[i] = (float)(Krf[3 * i] * treli[0] + Krf[3 * i + 1] * treli[1] + Krf[3 * i + 2] * treli[2]);
+    }
+    // baseline from the float camera centres as DepthToWeak computes it (APD.cu:2142-2147)
+    const float d0 = rc.c[0] - sc.c[0], d1 = rc.c[1] - sc.c[1], d2 = rc.c[2] - sc.c[2];
+    vk.baseline = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+    vk.layer = layer;
+}
+
+static void scale_camera(apde_camera &cam, int W, int H, int lw, int lh) {  // APD.cpp:570-585
+    if (lw == W && lh == H) { cam.width = W; cam.height = H; return; }
+    const float sx = lw / static_cast<float>(W), sy = lh / static_cast<float>(H);
+    cam.K[0] *= sx; cam.K[2] *= sx; cam.K[4] *= sy; cam.K[5] *= sy;
+    cam.width = lw; cam.height = lh;
+}
+
+int apde_problem_setup(apde_context *c, int ref_view, const apde_params *params, int scale_size, uint32_t seed) {
+    if (!c || !params) return fail(APDE_ERR_ARG, "problem_setup: null argument");
+    if (!c->committed) return fail(APDE_ERR_STATE, "problem_setup: scene not committed");
+    if (ref_view < 0 || ref_view >= c->V) return fail(APDE_ERR_ARG, "problem_setup: bad reference view %d", ref_view);
+    if (scale_size < 1) return fail(APDE_ERR_ARG, "problem_setup: bad scale_size");
+    if (params->strong_radius != 5 || params->strong_increment != 2 || params->weak_radius != 5 || params->weak_increment != 5)
+        return fail(APDE_ERR_ARG, "problem_setup: only the reference patch geometry (radius 5, increments 2/5) is supported");
+    CU(cudaSetDevice(c->device));
+    ViewStore &rv = c->views[ref_view];
+    const int N = (int)rv.src.size();
+    if (N < 1) return fail(APDE_ERR_ARG, "problem_setup: view %d has no source views", ref_view);
+    int rc = ensure_level(c, scale_size);
+    if (rc) return rc;
+    const int w = c->lw, h = c->lh;
+    const size_t P = (size_t)w * h, Pfull = (size_t)c->W * c->H;
+    cudaStream_t st = c->stream;
+
+    c->params = *params;
+    c->cams.resize(N + 1);
+    for (int i = 0; i <= N; ++i) {
+        const int vid = (i == 0) ? ref_view : rv.src[i - 1];
+        c->cams[i] = c->views[vid].cam;
+        scale_camera(c->cams[i], c->W, c->H, w, h);
+    }
+    c->params.depth_min = c->cams[0].depth_min * 0.6f;  // APD.cpp:554-556
+    c->params.depth_max = c->cams[0].depth_max * 1.2f;
+    c->params.num_images = N + 1;
+
+    PassK &K = c->K;
+    memset(&K, 0, sizeof(K));
+    K.W = w; K.H = h; K.N = N;
+    K.state = c->params.state; K.geom = c->params.geom_consistency; K.impetus = c->params.use_impetus;
+    K.use_apd = c->params.use_APD; K.top_k = c->params.top_k; K.weak_peak_radius = c->params.weak_peak_radius;
+    K.rotate_time = c->params.rotate_time; K.max_iterations = c->params.max_iterations;
+    K.depth_min = c->params.depth_min; K.depth_max = c->params.depth_max;
+    K.geom_factor = c->params.geom_factor; K.ransac_threshold = c->params.ransac_threshold;
+    K.fx = c->cams[0].K[0]; K.fy = c->cams[0].K[4]; K.cx = c->cams[0].K[2]; K.cy = c->cams[0].K[5];
+    for (int i = 0; i < 9; ++i) K.R[i] = c->cams[0].R[i];
+    K.ref_layer = ref_view;
+    K.seed = seed;
+    K.stream = (uint32_t)ref_view;
+    K.tex = c->level_tex;
+    K.planes = c->d_planes; K.costs = c->d_costs; K.sel = c->d_sel; K.vw = c->d_vw; K.weak = c->d_weak; K.conf = c->d_conf;
+    K.fit = c->d_fit; K.reliable = c->d_reliable; K.nearest = c->d_nearest; K.anchors = c->d_anchors;
+    K.depth = c->d_depthws; K.counters = c->d_counters;
+    for (int i = 0; i < N; ++i) make_view_k(c->cams[0], c->cams[i + 1], rv.src[i], K.v[i]);
+
+    const bool need_depth = c->params.geom_consistency || c->params.use_APD;
+    if (need_depth) {  // APD.cpp:592-610
+        for (int i = 0; i <= N; ++i) {
+            const int vid = (i == 0) ? ref_view : rv.src[i - 1];
+            const ViewStore &sv = c->views[vid];
+            if (sv.mw == 0) return fail(APDE_ERR_STATE, "problem_setup: view %d has no depth map yet", vid);
+            CU(launch_resize_nearest(c->d_depth_pool[c->cur] + (size_t)vid * Pfull, sv.mw, sv.mh, c->d_depthws + (size_t)i * P, w, h, 4, st));
+        }
+        c->launches += N + 1;
+    }
+    if (c->params.use_APD) {  // APD.cpp:614-626
+        if (rv.mw == 0 || !rv.has_conf) return fail(APDE_ERR_STATE, "problem_setup: use_APD needs weak/confidence maps of view %d", ref_view);
+        CU(launch_resize_nearest(rv.d_weak, rv.mw, rv.mh, c->d_weak, w, h, 1, st));
+        CU(launch_resize_nearest(rv.d_conf, rv.mw, rv.mh, c->d_conf, w, h, 1, st));
+        CU(cudaMemsetAsync(c->d_fit, 0, P * sizeof(float4), st));  // APD.cpp:771
+        c->launches += 2;
+    } else {  // APD.cpp:656-657
+        CU(launch_fill_u8(c->d_weak, APDE_STRONG, P, st));
+        CU(launch_fill_u8(c->d_conf, 1, P, st));
+    }
+    if (c->params.state != APDE_FIRST_INIT) {  // APD.cpp:662-683
+        if (rv.mw == 0) return fail(APDE_ERR_STATE, "problem_setup: view %d has no previous depth/normal", ref_view);
+        const float *dsrc = c->d_depth_pool[c->cur] + (size_t)ref_view * Pfull;
+        const float *nsrc = rv.d_normal;
+        if (rv.mw != w || rv.mh != h) {
+            CU(launch_resize_nearest(dsrc, rv.mw, rv.mh, c->d_scratch_depth, w, h, 4, st));
+            CU(launch_resize_nearest(nsrc, rv.mw, rv.mh, c->d_scratch_normal, w, h, 12, st));
+            dsrc = c->d_scratch_depth; nsrc = c->d_scratch_normal;
+            c->launches += 2;
+        }
+        CU(launch_planes_from_maps(dsrc, nsrc, c->d_planes, (int)P, st));
+        c->launches += 1;
+    } else {
+        CU(cudaMemsetAsync(c->d_planes, 0, P * sizeof(float4), st));
+    }
+    c->ref_view = ref_view;
+    c->problem_active = true;
+    return APDE_OK;
+}
+
+int apde_problem_dims(apde_context *c, int *width, int *height, int *num_images) {
+    if (!c || !c->problem_active) return fail(APDE_ERR_STATE, "no active problem");
+    if (width) *width = c->K.W;
+    if (height) *height = c->K.H;
+    if (num_images) *num_images = c->K.N + 1;
+    return APDE_OK;
+}
+
+int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
+    if (!c || !c->problem_active) return fail(APDE_ERR_STATE, "problem_stage: no active problem");
+    CU(cudaSetDevice(c->device));
+    CU(launch_stage(c->K, stage, iter, color, c->stream, nullptr));
+    c->launches++;
+    return APDE_OK;
+}
+
+// APD::RunPatchMatch, APD.cu:2663-2737
+int apde_problem_run(apde_context *c) {
+    if (!c || !c->problem_active) return fail(APDE_ERR_STATE, "problem_run: no active problem");
+    CU(cudaSetDevice(c->device));
+    const apde_params &p = c->params;
+    int rc;
+#define ST(stage, it, col) if ((rc = apde_problem_stage(c, stage, it, col))) return rc;
+    if (p.use_APD) { ST(APDE_STAGE_NEAREST_STRONG, 0, 0) ST(APDE_STAGE_GEN_ANCHORS, 0, 0) }
+    ST(APDE_STAGE_INIT, 0, 0)
+    for (int i = 0; i < p.max_iterations; ++i) {
+        ST(APDE_STAGE_PROP_STRONG, i, 0)
+        ST(APDE_STAGE_PROP_STRONG, i, 1)
+        if (p.use_APD) { ST(APDE_STAGE_RANSAC_FIT, i, 0) ST(APDE_STAGE_PROP_WEAK, i, 0) ST(APDE_STAGE_PROP_WEAK, i, 1) }
+    }
+    ST(APDE_STAGE_DEPTH_NORMAL, 0, 0)
+    ST(APDE_STAGE_MEDIAN, 0, 0)
+    ST(APDE_STAGE_MEDIAN, 0, 1)
+    ST(APDE_STAGE_DEPTH_TO_WEAK, 0, 0)
+    if (p.geom_consistency || p.use_APD) ST(APDE_STAGE_CONFIDENCE, 0, 0)
+    ST(APDE_STAGE_LOCAL_REFINE, 0, 0)
+#undef ST
+    return APDE_OK;
+}
+
+__global__ void k_unpack_vw(const uint4 *__restrict__ vw, uint8_t *__restrict__ out, int P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const uint4 w = vw[i];
+    for (int v = 0; v < 32; ++v) out[(size_t)i * 32 + v] = (uint8_t)vw_get(w, v);
+}
+__global__ void k_pack_vw(const uint8_t *__restrict__ in, uint4 *__restrict__ vw, int P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int v = 0; v < 32; ++v) w[v >> 3] |= (uint32_t)(in[(size_t)i * 32 + v] & 15u) << ((v & 7) * 4);
+    vw[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+static int field_ptr(apde_context *c, int field, void **ptr, size_t *bytes) {
+    const size_t P = (size_t)c->K.W * c->K.H;
+    switch (field) {
+        case APDE_FIELD_PLANES: *ptr = c->d_planes; *bytes = P * 16; break;
+        case APDE_FIELD_COSTS: *ptr = c->d_costs; *bytes = P * 4; break;
+        case APDE_FIELD_SELECTED_VIEWS: *ptr = c->d_sel; *bytes = P * 4; break;
+        case APDE_FIELD_WEAK_INFO: *ptr = c->d_weak; *bytes = P; break;
+        case APDE_FIELD_CONFIDENCE: *ptr = c->d_conf; *bytes = P; break;
+        case APDE_FIELD_FIT_PLANES: *ptr = c->d_fit; *bytes = P * 16; break;
+        case APDE_FIELD_WEAK_RELIABLE: *ptr = c->d_reliable; *bytes = P; break;
+        case APDE_FIELD_NEAREST_STRONG: *ptr = c->d_nearest; *bytes = P * 4; break;
+        case APDE_FIELD_ANCHORS: *ptr = c->d_anchors; *bytes = P * APDE_ANCHOR_NUM * 4; break;
+        case APDE_FIELD_SRC_DEPTH: *ptr = c->d_depthws; *bytes = P * 4 * (c->K.N + 1); break;
+        case APDE_FIELD_IMAGE: *ptr = c->d_level_lin + (size_t)c->ref_view * P; *bytes = P * 4; break;
+        default: return fail(APDE_ERR_ARG, "unknown field %d", field);
+    }
+    return APDE_OK;
+}
+
+int apde_problem_get(apde_context *c, int field, void *host, size_t bytes) {
+    if (!c || !c->problem_active || !host) return fail(APDE_ERR_STATE, "problem_get: no active problem");
+    CU(cudaSetDevice(c->device));
+    const size_t P = (size_t)c->K.W * c->K.H;
+    CU(cudaStreamSynchronize(c->stream));
+    if (field == APDE_FIELD_VIEW_WEIGHT) {
+        if (bytes != P * 32) return fail(APDE_ERR_ARG, "problem_get: view_weight needs %zu bytes", P * 32);
+        uint8_t *tmp;
+        CU(cudaMalloc(&tmp, P * 32));
+        k_unpack_vw<<<(unsigned)((P + 255) / 256), 256, 0, c->stream>>>(c->d_vw, tmp, (int)P);
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemcpy(host, tmp, P * 32, cudaMemcpyDeviceToHost));
+        cudaFree(tmp);
+        return APDE_OK;
+    }
+    void *ptr; size_t need;
+    int rc = field_ptr(c, field, &ptr, &need);
+    if (rc) return rc;
+    if (bytes != need) return fail(APDE_ERR_ARG, "problem_get: field %d needs %zu bytes, got %zu", field, need, bytes);
+    CU(cudaMemcpy(host, ptr, need, cudaMemcpyDeviceToHost));
+    return APDE_OK;
+}
+
+int apde_problem_set(apde_context *c, int field, const void *host, size_t bytes) {
+    if (!c || !c->problem_active || !host) return fail(APDE_ERR_STATE, "problem_set: no active problem");
+    CU(cudaSetDevice(c->device));
+    const size_t P = (size_t)c->K.W * c->K.H;
+    CU(cudaStreamSynchronize(c->stream));
+    if (field == APDE_FIELD_VIEW_WEIGHT) {
+        if (bytes != P * 32) return fail(APDE_ERR_ARG, "problem_set: view_weight needs %zu bytes", P * 32);
+        uint8_t *tmp;
+        CU(cudaMalloc(&tmp, P * 32));
+        CU(cudaMemcpy(tmp, host, P * 32, cudaMemcpyHostToDevice));
+        k_pack_vw<<<(unsigned)((P + 255) / 256), 256, 0, c->stream>>>(tmp, c->d_vw, (int)P);
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(tmp);
+        return APDE_OK;
+    }
+    if (field == APDE_FIELD_IMAGE) return fail(APDE_ERR_ARG, "problem_set: field is read only");
+    void *ptr; size_t need;
+    int rc = field_ptr(c, field, &ptr, &need);
+    if (rc) return rc;
+    if (bytes != need) return fail(APDE_ERR_ARG, "problem_set: field %d needs %zu bytes, got %zu", field, need, bytes);
+    CU(cudaMemcpy(ptr, host, need, cudaMemcpyHostToDevice));
+    return APDE_OK;
+}
+
+int apde_problem_get_image(apde_context *c, int idx, float *host, size_t bytes) {
+    if (!c || !c->problem_active || !host) return fail(APDE_ERR_STATE, "problem_get_image: no active problem");
+    if (idx < 0 || idx > c->K.N) return fail(APDE_ERR_ARG, "problem_get_image: bad index");
+    const size_t P = (size_t)c->K.W * c->K.H;
+    if (bytes != P * 4) return fail(APDE_ERR_ARG, "problem_get_image: needs %zu bytes", P * 4);
+    CU(cudaSetDevice(c->device));
+    const int vid = (idx == 0) ? c->ref_view : c->views[c->ref_view].src[idx - 1];
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(host, c->d_level_lin + (size_t)vid * P, P * 4, cudaMemcpyDeviceToHost));
+    return APDE_OK;
+}
+
+int apde_problem_get_cameras(apde_context *c, apde_camera *cams, apde_params *params) {
+    if (!c || !c->problem_active) return fail(APDE_ERR_STATE, "problem_get_cameras: no active problem");
+    if (cams) memcpy(cams, c->cams.data(), sizeof(apde_camera) * c->cams.size());
+    if (params) *params = c->params;
+    return APDE_OK;
+}
+
+static int problem_finish_impl(apde_context *c, bool jacobi) {
+    if (!c || !c->problem_active) return fail(APDE_ERR_STATE, "problem_finish: no active problem");
+    CU(cudaSetDevice(c->device));
+    ViewStore &rv = c->views[c->ref_view];
+    const size_t P = (size_t)c->K.W * c->K.H, Pfull = (size_t)c->W * c->H;
+    float *dpool = c->d_depth_pool[jacobi ? (c->cur ^ 1) : c->cur];
+    CU(launch_finish(c->d_planes, c->d_weak, dpool + (size_t)c->ref_view * Pfull, rv.d_normal, rv.d_weak, (int)P,
+                     c->params.depth_min, c->params.depth_max, c->stream));
+    c->launches++;
+    if (c->params.geom_consistency || c->params.use_APD) {  // main.cpp:187-190
+        CU(cudaMemcpyAsync(rv.d_conf, c->d_conf, P, cudaMemcpyDeviceToDevice, c->stream));
+        rv.has_conf = true;
+    }
+    rv.mw = c->K.W; rv.mh = c->K.H;
+    c->problem_active = false;
+    return APDE_OK;
+}
+
+int apde_problem_finish(apde_context *c) { return problem_finish_impl(c, false); }
+
+int apde_pass_run(apde_context *c, int ref_view, const apde_params *params, int scale_size, uint32_t seed) {
+    int rc = apde_problem_setup(c, ref_view, params, scale_size, seed);
+    if (rc) return rc;
+    if ((rc = apde_problem_run(c))) return rc;
+    return apde_problem_finish(c);
+}
+
+int apde_eval_costs(apde_context *c, int n, const int32_t *tuples, const float *planes, int mode, float *out) {
+    if (!c || !c->problem_active) return fail(APDE_ERR_STATE, "eval_costs: no active problem");
+    if (n <= 0 || !tuples || !planes || !out || mode < 0 || mode > 2) return fail(APDE_ERR_ARG, "eval_costs: bad argument");
+    for (int i = 0; i < n; ++i) {
+        const int x = tuples[3 * i], y = tuples[3 * i + 1], v = tuples[3 * i + 2];
+        if (x < 0 || x >= c->K.W || y < 0 || y >= c->K.H || v < 1 || v > c->K.N)
+            return fail(APDE_ERR_ARG, "eval_costs: tuple %d (%d, %d, %d) out of range", i, x, y, v);
+    }
+    CU(cudaSetDevice(c->device));
+    int *d_t; float4 *d_p; float *d_o;
+    CU(cudaMalloc(&d_t, (size_t)n * 12));
+    CU(cudaMalloc(&d_p, (size_t)n * 16));
+    CU(cudaMalloc(&d_o, (size_t)n * 4));
+    CU(cudaMemcpyAsync(d_t, tuples, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_p, planes, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    CU(launch_eval_costs(c->K, n, d_t, d_p, mode, d_o, c->stream));
+    c->launches++;
+    CU(cudaMemcpyAsync(out, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_t); cudaFree(d_p); cudaFree(d_o);
+    return APDE_OK;
+}
+
+int apde_get_counters(apde_context *c, uint64_t out[4], int reset) {
+    if (!c || !out) return fail(APDE_ERR_ARG, "get_counters: null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    unsigned long long h[4];
+    CU(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; out[3] = c->launches;
+    if (reset) { CU(cudaMemset(c->d_counters, 0, sizeof(h))); c->launches = 0; }
+    return APDE_OK;
+}
+
+int apde_depth_pool(apde_context *c, void **dev_ptr, size_t *bytes, size_t *bytes_per_view) {
+    if (!c || !c->d_depth_pool[0]) return fail(APDE_ERR_STATE, "depth_pool: no scene");
+    const size_t Pfull = (size_t)c->W * c->H;
+    if (dev_ptr) *dev_ptr = c->d_depth_pool[c->cur];
+    if (bytes) *bytes = (size_t)c->V * Pfull * sizeof(float);
+    if (bytes_per_view) *bytes_per_view = Pfull * sizeof(float);
+    return APDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ schedule
+static int compute_round_num(int W, int H) {  // main.cpp:129-146
+    int max_size = W > H ? W : H;
+    int r = 1;
+    while (max_size > 800) { max_size /= 2; r++; }
+    return r;
+}
+
+int apde_schedule_num_passes(apde_context *c, const apde_schedule *s) {
+    if (!c || !s || c->V <= 0) return fail(APDE_ERR_ARG, "schedule_num_passes: bad argument");
+    const int rounds = s->rounds > 0 ? s->rounds : compute_round_num(c->W, c->H);
+    return rounds * (1 + s->geom_iterations);
+}
+
+int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_index, apde_timing *out) {
+    if (!c || !s) return fail(APDE_ERR_ARG, "run_schedule_pass: null argument");
+    if (!c->committed) return fail(APDE_ERR_STATE, "run_schedule_pass: scene not committed");
+    CU(cudaSetDevice(c->device));
+    const int rounds = s->rounds > 0 ? s->rounds : compute_round_num(c->W, c->H);
+    const int per_round = 1 + s->geom_iterations;
+    if (pass_index < 0 || pass_index >= rounds * per_round) return fail(APDE_ERR_ARG, "run_schedule_pass: pass %d out of range", pass_index);
+    const int i = pass_index / per_round, j = pass_index % per_round - 1;  // j = -1: photometric pass
+    const size_t Pfull = (size_t)c->W * c->H;
+    if (s->jacobi && !c->d_depth_pool[1]) {
+        CU(cudaMalloc(&c->d_depth_pool[1], (size_t)c->V * Pfull * sizeof(float)));
+        CU(cudaMemsetAsync(c->d_depth_pool[1], 0, (size_t)c->V * Pfull * sizeof(float), c->stream));
+    }
+    apde_params p;
+    apde_params_default(&p);
+    p.geom_factor = s->geom_factor;
+    p.use_impetus = s->use_impetus;
+    p.max_iterations = 3;
+    if (i == 0) {
+        p.use_APD = 0;
+    } else {
+        p.use_APD = 1;
+        p.ransac_threshold = (float)(0.01 - i * 0.00125);                       // main.cpp:318
+        p.rotate_time = std::min(static_cast<int>(std::pow(2, i)), 4);           // main.cpp:319
+    }
+    if (j < 0) {  // main.cpp:309-331
+        p.state = (i == 0) ? APDE_FIRST_INIT : APDE_REFINE_INIT;
+        p.geom_consistency = 0;
+        p.weak_peak_radius = 6;
+    } else {  // main.cpp:333-365
+        p.state = APDE_REFINE_ITER;
+        p.geom_consistency = 1;
+        p.weak_peak_radius = std::max(4 - 2 * j, 2);
+    }
+    const int scale = static_cast<int>(std::pow(2, rounds - 1 - i));
+    const int first = (s->num_views_local > 0) ? s->first_view : 0;
+    const int count = (s->num_views_local > 0) ? s->num_views_local : c->V;
+    if (first < 0 || first + count > c->V) return fail(APDE_ERR_ARG, "run_schedule_pass: bad shard [%d, %d)", first, first + count);
+
+    uint64_t c0[4];
+    int rc = apde_get_counters(c, c0, 0);
+    if (rc) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    double pm_ms = 0.0;
+    for (int v = first; v < first + count; ++v) {
+        const uint32_t seed = s->seed * 0x9E3779B1u + (uint32_t)pass_index * 0x85EBCA77u;
+        if ((rc = apde_problem_setup(c, v, &p, scale, seed))) return rc;
+        CU(cudaEventRecord(c->ev0, c->stream));
+        if ((rc = apde_problem_run(c))) return rc;
+        CU(cudaEventRecord(c->ev1, c->stream));
+        if ((rc = problem_finish_impl(c, s->jacobi != 0))) return rc;
+        CU(cudaEventSynchronize(c->ev1));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        pm_ms += ms;
+    }
+    if (s->jacobi) {
+        // views outside this rank's shard keep their previous depth until the host-side exchange overwrites them
+        if (count < c->V) {
+            for (int v = 0; v < c->V; ++v) {
+                if (v >= first && v < first + count) continue;
+                CU(cudaMemcpyAsync(c->d_depth_pool[c->cur ^ 1] + (size_t)v * Pfull, c->d_depth_pool[c->cur] + (size_t)v * Pfull,
+                                   Pfull * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+            }
+        }
+        c->cur ^= 1;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    const auto t1 = std::chrono::steady_clock::now();
+    if (out) {
+        uint64_t c1[4];
+        if ((rc = apde_get_counters(c, c1, 0))) return rc;
+        out->patchmatch_ms += pm_ms;
+        out->total_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        out->evals_ncc_old += c1[0] - c0[0];
+        out->evals_ncc_new += c1[1] - c0[1];
+        out->evals_geom += c1[2] - c0[2];
+        out->kernel_launches += c1[3] - c0[3];
+        out->passes += 1;
+    }
+    return APDE_OK;
+}
+
+int apde_run_schedule(apde_context *c, const apde_schedule *s, apde_timing *out) {
+    const int n = apde_schedule_num_passes(c, s);
+    if (n < 0) return n;
+    if (out) memset(out, 0, sizeof(*out));
+    for (int p = 0; p < n; ++p) {
+        int rc = apde_run_schedule_pass(c, s, p, out);
+        if (rc) return rc;
+    }
+    return APDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fusion
+static int fusion_views(apde_context *c, std::vector<FusionView> &fv, int *mw, int *mh) {
+    const size_t Pfull = (size_t)c->W * c->H;
+    fv.resize(c->V);
+    *mw = c->views[0].mw; *mh = c->views[0].mh;
+    if (*mw == 0) return fail(APDE_ERR_STATE, "fusion: no depth maps yet");
+    for (int v = 0; v < c->V; ++v) {
+        const ViewStore &s = c->views[v];
+        if (s.mw != *mw || s.mh != *mh) return fail(APDE_ERR_STATE, "fusion: view %d has a different map size", v);
+        apde_camera cam = s.cam;
+        scale_camera(cam, c->W, c->H, *mw, *mh);  // RescaleImageAndCamera, APD.cpp:844-864
+        fv[v].cam = cam;
+        fv[v].depth = c->d_depth_pool[c->cur] + (size_t)v * Pfull;
+        fv[v].normal = s.d_normal;
+        fv[v].weak = s.d_weak;
+        fv[v].conf = s.d_conf;
+        fv[v].bgr = s.d_bgr;
+        fv[v].src = s.src;
+    }
+    return APDE_OK;
+}
+
+int apde_weak_vis_filter(apde_context *c, uint8_t *skip_weaks) {
+    if (!c || c->V <= 0) return fail(APDE_ERR_STATE, "weak_vis_filter: no scene");
+    CU(cudaSetDevice(c->device));
+    std::vector<FusionView> fv;
+    int mw, mh;
+    int rc = fusion_views(c, fv, &mw, &mh);
+    if (rc) return rc;
+    const size_t P = (size_t)mw * mh;
+    if (!c->d_skip) CU(cudaMalloc(&c->d_skip, (size_t)c->V * c->W * c->H));
+    CU(cudaMemsetAsync(c->d_skip, 0, (size_t)c->V * P, c->stream));
+    CU(fusion_weak_vis_filter(fv, mw, mh, c->W, c->H, c->d_skip, c->stream));
+    c->launches += c->V;
+    CU(cudaStreamSynchronize(c->stream));
+    if (skip_weaks) CU(cudaMemcpy(skip_weaks, c->d_skip, (size_t)c->V * P, cudaMemcpyDeviceToHost));
+    return APDE_OK;
+}
+
+int apde_fuse(apde_context *c, int use_weak_filter, float *xyz, float *bgr, int64_t max_points, int64_t *num_points) {
+    if (!c || c->V <= 0 || !num_points) return fail(APDE_ERR_STATE, "fuse: bad argument");
+    CU(cudaSetDevice(c->device));
+    std::vector<FusionView> fv;
+    int mw, mh;
+    int rc = fusion_views(c, fv, &mw, &mh);
+    if (rc) return rc;
+    const size_t P = (size_t)mw * mh;
+    if (!c->d_skip) CU(cudaMalloc(&c->d_skip, (size_t)c->V * c->W * c->H));
+    if (use_weak_filter) {
+        if ((rc = apde_weak_vis_filter(c, nullptr))) return rc;
+    } else {
+        CU(cudaMemsetAsync(c->d_skip, 0, (size_t)c->V * P, c->stream));
+    }
+    uint64_t launches = 0;
+    cudaError_t e = fusion_run(fv, mw, mh, c->d_skip, xyz, bgr, max_points, num_points, c->stream, &launches);
+    c->launches += launches;
+    if (e != cudaSuccess) return fail(APDE_ERR_CUDA, "fusion: %s", cudaGetErrorString(e));
+    return APDE_OK;
+}
+
+}  // extern "C"

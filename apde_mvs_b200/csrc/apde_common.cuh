@@ -1,0 +1,96 @@
+// apde_common.cuh -- device helpers shared by the pass kernels: pixel mappings, view-constant staging and the
+// multi-hypothesis joint view selection.
+#pragma once
+#include <cfloat>
+
+#include "apde_device.cuh"
+
+namespace apde {
+
+// -------------------------------------------------------------------------------------------- pixel mappings
+// checkerboard kernels: one warp = the 32 pixels of one colour inside an 8x8 tile (compact texture footprint).
+__device__ __forceinline__ bool half_pixel(const PassK &K, int color, int tiles_x, int ylimit, int &px, int &py) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    py = ty * 8 + (lane >> 2);
+    px = tx * 8 + 2 * (lane & 3) + ((py + color) & 1);
+    return px < K.W && py < ylimit;
+}
+// full kernels: one warp = an 8x4 tile
+__device__ __forceinline__ bool full_pixel(const PassK &K, int tiles_x, int &px, int &py) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    py = ty * 4 + (lane >> 3);
+    px = tx * 8 + (lane & 7);
+    return px < K.W && py < K.H;
+}
+
+// copy the per-view constants into shared memory (divergent per-lane view indices must not hit the constant bank)
+__device__ __forceinline__ ViewK *stage_views(const PassK &K, float *smem) {
+    const int words = K.N * (int)(sizeof(ViewK) / 4);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(K.v);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(smem);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    return reinterpret_cast<ViewK *>(smem);
+}
+__host__ __device__ inline int views_smem_floats(int N) { return ((N * (int)sizeof(ViewK) + 15) / 16) * 4; }
+
+// Multi-hypothesis joint view selection, APD.cu:1339-1386.  cost(h, v) = sc[(h * N + v) * stride]; prob scratch
+// sp[v * stride].  Returns the packed weights; *selmask = views with weight > 0, *wnorm = sum of weights.
+template <int NBR>
+__device__ __forceinline__ uint4 select_views(const PassK &K, const float *sc, float *sp, int stride,
+                                              const uint32_t (&nbr_sel)[NBR], unsigned nbr_valid, int iter, Rng &rng,
+                                              uint32_t *selmask, float *wnorm) {
+    const int N = K.N;
+    const float cost_threshold = (float)(0.8 * (double)__expf((float)(iter * iter) / (-90.0f)));
+    const float fallback = __expf(cost_threshold * cost_threshold / (-0.32f));
+    float psum = 0.0f;
+    for (int v = 0; v < N; ++v) {
+        float cnt = 0.0f, tmpw = 0.0f;
+        int cnt_false = 0;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const float c = sc[(h * N + v) * stride];
+            if (c < cost_threshold) { tmpw += __expf(c * c / (-0.18f)); cnt += 1.0f; }
+            if (c > 1.2f) cnt_false++;
+        }
+        float p = 0.0f;
+        if (cnt > 2.0f && cnt_false < 3) p = tmpw / cnt;
+        else if (cnt_false < 3) p = fallback;
+        float prior = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NBR; ++i)
+            if ((nbr_valid >> i) & 1u) prior += ((nbr_sel[i] >> v) & 1u) ? 0.9f : 0.1f;
+        p *= prior;
+        sp[v * stride] = p;
+        psum += p;
+    }
+    // TransformPDFToCDF, APD.cu:174-188
+    const float inv = 1.0f / psum;
+    float cum = 0.0f;
+    for (int v = 0; v < N; ++v) { cum += sp[v * stride] * inv; sp[v * stride] = cum; }
+    uint4 w = make_uint4(0, 0, 0, 0);
+    for (int s = 0; s < 15; ++s) {
+        const float r = rng.uniform() - FLT_EPSILON;
+        for (int v = 0; v < N; ++v) {
+            if (sp[v * stride] > r) { vw_inc(w, v); break; }
+        }
+    }
+    uint32_t mask = 0;
+    float wn = 0.0f;
+    for (int v = 0; v < N; ++v) {
+        const uint32_t wv = vw_get(w, v);
+        if (wv > 0) { mask |= 1u << v; wn += (float)wv; }
+    }
+    *selmask = mask;
+    *wnorm = wn;
+    return w;
+}
+
+
+static inline int half_rows_limit(int H) { return 32 * (((H / 2) + 15) / 16); }  // quirk 7, APD.cu:2676-2678
+
+}  // namespace apde

@@ -1,0 +1,354 @@
+// apde_device.cuh -- device-side types, counter RNG and per-hypothesis cost functions (sm_100a).
+//
+// Design: one thread per pixel; the 36 reference-patch texels and their sums are loaded ONCE per
+// pixel per kernel and stay in registers (the reference re-fetches them through the texture unit for every
+// evaluation, APD.cu:632); the camera-pair part of the homography is precomputed on the host per (ref, src) pair
+// (the reference recomputes it per evaluation, APD.cu:336-362), so that H = A - b m^T costs 9 FMAs; source texels
+// are gathered through ONE layered texture object (linear filter, clamp) holding every view of the pyramid level.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/apde.h"
+
+namespace apde {
+
+constexpr int kMaxSrc = APDE_MAX_IMAGES - 1;
+constexpr int kPatch = 36;  // (2*5/2+1)^2 samples: strong_radius 5, strong_increment 2 (main.h:87-88)
+
+// per (reference, source) pair constants, precomputed in double on the host
+struct ViewK {
+    float A[9];   // K_s R_rel K_r^-1                (homography:  H = A - b m^T,  m = n^T K_r^-1 / w)
+    float b[3];   // K_s t_rel,  t_rel = R_s (C_r - C_s)
+    float Ai[9];  // K_r R_rel^T K_s^-1              (backward reprojection)
+    float bi[3];  // K_r R_r (C_s - C_r)
+    float baseline;
+    int layer;    // layer of this source view in the level's texture
+};
+
+struct PassK {
+    int W, H, N;  // N = number of source views
+    int state, geom, impetus, use_apd, top_k, weak_peak_radius, rotate_time, max_iterations;
+    float depth_min, depth_max, geom_factor, ransac_threshold;
+    float fx, fy, cx, cy;  // reference intrinsics at this level
+    float R[9];            // reference rotation
+    int ref_layer;
+    uint32_t seed, stream;
+    cudaTextureObject_t tex;  // layered float32 images of the level (linear filter, clamp, unnormalised)
+    float4 *planes;
+    float *costs;
+    uint32_t *sel;
+    uint4 *vw;  // packed view weights: 4 bits per source view (0..15)
+    uint8_t *weak;
+    uint8_t *conf;
+    float4 *fit;
+    uint8_t *reliable;
+    short2 *nearest;
+    short2 *anchors;       // [P][9]
+    const float *depth;    // [N+1][P] working-resolution depth maps, 0 = ref
+    unsigned long long *counters;
+    ViewK v[kMaxSrc];
+};
+
+// ------------------------------------------------------------------------------------------------ RNG
+// Philox4x32-10, key = (seed, stream), counter = (pixel, site, block, 0).  Same spec as oracle/apd_oracle.cpp.
+enum Site : uint32_t { SITE_ANCHOR = 1, SITE_INIT = 2, SITE_STRONG = 16, SITE_FIT = 48, SITE_WEAK = 80 };
+
+__device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0,
+                                              uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+struct Rng {
+    uint32_t k0, k1, pixel, site, n;
+    uint32_t b0, b1, b2, b3;
+    __device__ __forceinline__ Rng(uint32_t seed, uint32_t stream, uint32_t pixel_, uint32_t site_)
+        : k0(seed), k1(stream), pixel(pixel_), site(site_), n(0), b0(0), b1(0), b2(0), b3(0) {}
+    __device__ __forceinline__ uint32_t next() {
+        const uint32_t lane = n & 3u;
+        if (lane == 0u) {
+            b0 = pixel; b1 = site; b2 = n >> 2; b3 = 0u;
+            philox4x32_10(b0, b1, b2, b3, k0, k1);
+        }
+        ++n;
+        return lane == 0u ? b0 : (lane == 1u ? b1 : (lane == 2u ? b2 : b3));
+    }
+    // (0,1], curand_uniform's mapping: x * 2^-32 + 2^-33
+    __device__ __forceinline__ float uniform() {
+        return __fmaf_rn(__uint2float_rn(next()), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+// single MUFU.RCP (what "x / z" compiles to under the reference's --use_fast_math, CMakeLists.txt:26)
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// reference-camera plane helpers (APD.cu:190-240), zero-skew pinhole
+__device__ __forceinline__ float depth_from_plane(const PassK &K, float4 pl, int px, int py) {
+    return -pl.w * K.fx / ((px - K.cx) * pl.x + (K.fx / K.fy) * (py - K.cy) * pl.y + K.fx * pl.z);
+}
+__device__ __forceinline__ float distance_to_origin(const PassK &K, int px, int py, float depth, float4 n) {
+    const float X0 = depth * (px - K.cx) / K.fx, X1 = depth * (py - K.cy) / K.fy;
+    return -(n.x * X0 + n.y * X1 + n.z * depth);
+}
+__device__ __forceinline__ float3 view_direction(const PassK &K, int px, int py, float depth) {
+    const float X0 = depth * (px - K.cx) / K.fx, X1 = depth * (py - K.cy) / K.fy, X2 = depth;
+    const float nrm = sqrtf(X0 * X0 + X1 * X1 + X2 * X2);
+    return make_float3(X0 / nrm, X1 / nrm, X2 / nrm);
+}
+__device__ __forceinline__ void normalize3(float4 &v) {
+    const float inv = rsqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+    v.x *= inv; v.y *= inv; v.z *= inv;
+}
+__device__ __forceinline__ float4 normal_to_world(const PassK &K, float4 p) {  // TransformNormal APD.cu:405
+    return make_float4(K.R[0] * p.x + K.R[3] * p.y + K.R[6] * p.z, K.R[1] * p.x + K.R[4] * p.y + K.R[7] * p.z,
+                       K.R[2] * p.x + K.R[5] * p.y + K.R[8] * p.z, p.w);
+}
+__device__ __forceinline__ float4 normal_to_refcam(const PassK &K, float4 p) {  // TransformNormal2RefCam APD.cu:415
+    return make_float4(K.R[0] * p.x + K.R[1] * p.y + K.R[2] * p.z, K.R[3] * p.x + K.R[4] * p.y + K.R[5] * p.z,
+                       K.R[6] * p.x + K.R[7] * p.y + K.R[8] * p.z, p.w);
+}
+
+__device__ __forceinline__ float4 random_normal(const PassK &K, int px, int py, Rng &rng, float depth) {  // APD.cu:242
+    float q1 = 1.0f, q2 = 1.0f, s = 2.0f;
+    while (s >= 1.0f) {
+        q1 = 2.0f * rng.uniform() - 1.0f;
+        q2 = 2.0f * rng.uniform() - 1.0f;
+        s = q1 * q1 + q2 * q2;
+    }
+    const float sq = sqrtf(1.0f - s);
+    float4 n = make_float4(2.0f * q1 * sq, 2.0f * q2 * sq, 1.0f - 2.0f * s, 0.0f);
+    const float3 vd = view_direction(K, px, py, depth);
+    if (n.x * vd.x + n.y * vd.y + n.z * vd.z > 0.0f) { n.x = -n.x; n.y = -n.y; n.z = -n.z; }
+    normalize3(n);
+    return n;
+}
+
+__device__ __forceinline__ float4 perturbed_normal(const PassK &K, int px, int py, float4 normal, Rng &rng,
+                                                   float perturbation) {  // APD.cu:270
+    const float3 vd = view_direction(K, px, py, 1.0f);
+    const float a1 = (rng.uniform() - 0.5f) * perturbation;
+    const float a2 = (rng.uniform() - 0.5f) * perturbation;
+    const float a3 = (rng.uniform() - 0.5f) * perturbation;
+    float s1, c1, s2, c2, s3, c3;
+    sincosf(a1, &s1, &c1); sincosf(a2, &s2, &c2); sincosf(a3, &s3, &c3);
+    const float r0 = c2 * c3, r1 = c3 * s1 * s2 - c1 * s3, r2 = s1 * s3 + c1 * c3 * s2;
+    const float r3 = c2 * s3, r4 = c1 * c3 + s1 * s2 * s3, r5 = c1 * s2 * s3 - c3 * s1;
+    const float r6 = -s2, r7 = c2 * s1, r8 = c1 * c2;
+    float4 np = make_float4(r0 * normal.x + r1 * normal.y + r2 * normal.z, r3 * normal.x + r4 * normal.y + r5 * normal.z,
+                            r6 * normal.x + r7 * normal.y + r8 * normal.z, 0.0f);
+    if (np.x * vd.x + np.y * vd.y + np.z * vd.z >= 0.0f) np = normal;
+    normalize3(np);
+    return np;
+}
+
+// ------------------------------------------------------------------------------------------------ costs
+// reference patch of one pixel: texels at (x+i, y+j), i outer, j inner, i,j in {-5,-3,...,5} (APD.cu:629-632).
+// A texel-centre fetch of the clamped linear texture returns the texel exactly.
+struct RefPatch {
+    float r[kPatch];
+    float mean, var;  // E[r], E[r^2]-E[r]^2 with the reference's accumulation order
+};
+
+__device__ __forceinline__ void load_ref_patch(const PassK &K, int px, int py, RefPatch &rp) {
+    float s = 0.0f, ss = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const float v = tex2DLayered<float>(K.tex, px + (2 * i - 5) + 0.5f, py + (2 * j - 5) + 0.5f, K.ref_layer);
+            rp.r[i * 6 + j] = v;
+            s += v;
+            ss += v * v;
+        }
+    }
+    const float inv = 1.0f / 36.0f;
+    s *= inv; ss *= inv;
+    rp.mean = s;
+    rp.var = ss - s * s;
+}
+
+// m = n^T K_r^-1 / w : the hypothesis-dependent row vector of H = A - b m^T
+__device__ __forceinline__ float3 plane_row(const PassK &K, float4 pl) {
+    const float iw = 1.0f / pl.w;
+    const float mx = pl.x / K.fx, my = pl.y / K.fy;
+    const float mz = pl.z - mx * K.cx - my * K.cy;
+    return make_float3(mx * iw, my * iw, mz * iw);
+}
+
+struct Homog { float h[9]; };
+
+__device__ __forceinline__ Homog make_homography(const ViewK &vk, float3 m) {
+    Homog Hm;
+    Hm.h[0] = fmaf(-vk.b[0], m.x, vk.A[0]); Hm.h[1] = fmaf(-vk.b[0], m.y, vk.A[1]); Hm.h[2] = fmaf(-vk.b[0], m.z, vk.A[2]);
+    Hm.h[3] = fmaf(-vk.b[1], m.x, vk.A[3]); Hm.h[4] = fmaf(-vk.b[1], m.y, vk.A[4]); Hm.h[5] = fmaf(-vk.b[1], m.z, vk.A[5]);
+    Hm.h[6] = fmaf(-vk.b[2], m.x, vk.A[6]); Hm.h[7] = fmaf(-vk.b[2], m.y, vk.A[7]); Hm.h[8] = fmaf(-vk.b[2], m.z, vk.A[8]);
+    return Hm;
+}
+
+// NCC of the warped 6x6 patch against the register-resident reference patch.  APD.cu:622-662.
+__device__ __forceinline__ float patch_ncc36(const PassK &K, const Homog &Hm, int layer, int px, int py,
+                                             const RefPatch &rp) {
+    const float *h = Hm.h;
+    // fold the +0.5 texel-centre offset into the numerators: (X + 0.5 Z) / Z
+    const float g0 = fmaf(0.5f, h[6], h[0]), g1 = fmaf(0.5f, h[7], h[1]), g2 = fmaf(0.5f, h[8], h[2]);
+    const float g3 = fmaf(0.5f, h[6], h[3]), g4 = fmaf(0.5f, h[7], h[4]), g5 = fmaf(0.5f, h[8], h[5]);
+    float sum_s = 0.0f, sum_ss = 0.0f, sum_rs = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float xi = (float)(px + 2 * i - 5);
+        const float bx = fmaf(g0, xi, g2), by = fmaf(g3, xi, g5), bz = fmaf(h[6], xi, h[8]);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const float yj = (float)(py + 2 * j - 5);
+            const float X = fmaf(g1, yj, bx), Y = fmaf(g4, yj, by), Z = fmaf(h[7], yj, bz);
+            const float iz = rcp_approx(Z);
+            const float s = tex2DLayered<float>(K.tex, X * iz, Y * iz, layer);
+            sum_s += s;
+            sum_ss = fmaf(s, s, sum_ss);
+            sum_rs = fmaf(rp.r[i * 6 + j], s, sum_rs);
+        }
+    }
+    const float inv = 1.0f / 36.0f;
+    sum_s *= inv; sum_ss *= inv; sum_rs *= inv;
+    const float var_s = sum_ss - sum_s * sum_s;
+    if (rp.var < 1e-5f || var_s < 1e-5f) return 2.0f;
+    const float covar = sum_rs - rp.mean * sum_s;
+    return fmaxf(0.0f, fminf(2.0f, 1.0f - covar * rsqrtf(rp.var * var_s)));
+}
+
+// ComputeBilateralNCCOld, APD.cu:596-663 (branch A).  Only the patch centre is bounds-checked (quirk 8).
+__device__ __forceinline__ float ncc_old(const PassK &K, const ViewK &vk, int px, int py, float3 m, const RefPatch &rp) {
+    const Homog Hm = make_homography(vk, m);
+    const float *h = Hm.h;
+    const float fxp = (float)px, fyp = (float)py;
+    const float Z = h[6] * fxp + h[7] * fyp + h[8];
+    const float iz = rcp_approx(Z);
+    const float ptx = (h[0] * fxp + h[1] * fyp + h[2]) * iz;
+    const float pty = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
+    if (ptx >= (float)K.W || ptx < 0.0f || pty >= (float)K.H || pty < 0.0f) return 2.0f;
+    return patch_ncc36(K, Hm, vk.layer, px, py, rp);
+}
+
+// 3x3 anchor patch (weak_radius 5, weak_increment 5) around (ax, ay), reference texels fetched on the fly
+__device__ __forceinline__ float patch_ncc9(const PassK &K, const Homog &Hm, int layer, int ax, int ay) {
+    const float *h = Hm.h;
+    float sr = 0.0f, srr = 0.0f, ss = 0.0f, sss = 0.0f, srs = 0.0f;
+#pragma unroll
+    for (int i = -5; i <= 5; i += 5) {
+#pragma unroll
+        for (int j = -5; j <= 5; j += 5) {
+            const float fxp = (float)(ax + i), fyp = (float)(ay + j);
+            const float r = tex2DLayered<float>(K.tex, fxp + 0.5f, fyp + 0.5f, K.ref_layer);
+            const float Z = h[6] * fxp + h[7] * fyp + h[8];
+            const float iz = rcp_approx(Z);
+            const float X = (h[0] * fxp + h[1] * fyp + h[2]) * iz, Y = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
+            const float s = tex2DLayered<float>(K.tex, X + 0.5f, Y + 0.5f, layer);
+            sr += r; srr = fmaf(r, r, srr); ss += s; sss = fmaf(s, s, sss); srs = fmaf(r, s, srs);
+        }
+    }
+    const float inv = 1.0f / 9.0f;
+    sr *= inv; srr *= inv; ss *= inv; sss *= inv; srs *= inv;
+    const float var_r = srr - sr * sr, var_s = sss - ss * ss;
+    if (var_r < 1e-5f || var_s < 1e-5f) return 2.0f;
+    const float covar = srs - sr * ss;
+    return fmaxf(0.0f, fminf(2.0f, 1.0f - covar * rsqrtf(var_r * var_s)));
+}
+
+// ComputeBilateralNCCNew, APD.cu:448-593 (sa_mask == 0): centre patch + focal-weighted anchor patches.
+__device__ __forceinline__ float ncc_new(const PassK &K, const ViewK &vk, int view_bit, int px, int py, float3 m,
+                                         const RefPatch &rp, const short2 *anc /* 9 anchors of this pixel */) {
+    const Homog Hm = make_homography(vk, m);
+    const float *h = Hm.h;
+    const float fW = (float)K.W, fH = (float)K.H;
+    {
+        const float fxp = (float)px, fyp = (float)py;
+        const float iz = rcp_approx(h[6] * fxp + h[7] * fyp + h[8]);
+        const float ptx = (h[0] * fxp + h[1] * fyp + h[2]) * iz, pty = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
+        if (ptx >= fW || ptx < 0.0f || pty >= fH || pty < 0.0f) return 2.0f;
+    }
+    // anchor 0 is the pixel itself (APD.cu:1887): its bounds test repeats the centre test above
+    const float center_cost = patch_ncc36(K, Hm, vk.layer, px, py, rp);
+    float sc[8];
+    int ns = 0;
+#pragma unroll
+    for (int k = 1; k < APDE_ANCHOR_NUM; ++k) {
+        const short2 a = anc[k];
+        if (a.x == -1 || a.y == -1) continue;
+        const float fxp = (float)a.x, fyp = (float)a.y;
+        const float iz = rcp_approx(h[6] * fxp + h[7] * fyp + h[8]);
+        const float ax = (h[0] * fxp + h[1] * fyp + h[2]) * iz, ay = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
+        if (ax < 0.0f || ay < 0.0f || ax >= fW || ay >= fH) {
+            if ((K.sel[a.x + a.y * K.W] >> view_bit) & 1u) sc[ns++] = 2.0f;
+            continue;
+        }
+        sc[ns++] = patch_ncc9(K, Hm, vk.layer, a.x, a.y);
+    }
+    if (ns == 0) return center_cost;
+    float mx = -1e10f;
+    for (int i = 0; i < ns; ++i) mx = fmaxf(mx, sc[i]);
+    float sum = 0.0f, acc = 0.0f;
+    float wts[8];
+    for (int i = 0; i < ns; ++i) { wts[i] = __expf(sc[i] - mx); sum += wts[i]; }
+    for (int i = 0; i < ns; ++i) acc += (wts[i] / sum) * sc[i];
+    acc = fminf(acc, 2.0f);
+    return 0.25f * center_cost + 0.75f * acc;
+}
+
+// ComputeGeomConsistencyCost, APD.cu:865-902, with the camera pair pre-composed:
+//   forward:  x_s ~ depth * A p~ + b ;  backward:  x_r ~ d_s * Ai s~ + bi
+__device__ __forceinline__ float geom_cost(const PassK &K, const ViewK &vk, int v /* 0-based source */, int px, int py,
+                                           float4 plane) {
+    const float depth = depth_from_plane(K, plane, px, py);
+    const float fxp = (float)px, fyp = (float)py;
+    const float qx = vk.A[0] * fxp + vk.A[1] * fyp + vk.A[2];
+    const float qy = vk.A[3] * fxp + vk.A[4] * fyp + vk.A[5];
+    const float qz = vk.A[6] * fxp + vk.A[7] * fyp + vk.A[8];
+    const float Z = fmaf(depth, qz, vk.b[2]);
+    const float sx = fmaf(depth, qx, vk.b[0]) / Z, sy = fmaf(depth, qy, vk.b[1]) / Z;
+    // "(int)src_pt.x + 0.5f" through a clamped texture == clamped truncation (cvt.rzi saturates, NaN -> 0)
+    const int ix = clampi(__float2int_rz(sx), 0, K.W - 1), iy = clampi(__float2int_rz(sy), 0, K.H - 1);
+    const float sd = K.depth[(size_t)(v + 1) * K.W * K.H + (size_t)iy * K.W + ix];
+    if (sd == 0.0f) return 3.0f;
+    const float rx = vk.Ai[0] * sx + vk.Ai[1] * sy + vk.Ai[2];
+    const float ry = vk.Ai[3] * sx + vk.Ai[4] * sy + vk.Ai[5];
+    const float rz = vk.Ai[6] * sx + vk.Ai[7] * sy + vk.Ai[8];
+    const float Zr = fmaf(sd, rz, vk.bi[2]);
+    const float bx = fmaf(sd, rx, vk.bi[0]) / Zr, by = fmaf(sd, ry, vk.bi[1]) / Zr;
+    const float dc = fxp - bx, dr = fyp - by;
+    return fminf(3.0f, sqrtf(dc * dc + dr * dr));
+}
+
+// packed view weights: 4 bits per view in a uint4
+__device__ __forceinline__ uint32_t vw_get(const uint4 &w, int v) {
+    const uint32_t word = (v < 8) ? w.x : (v < 16) ? w.y : (v < 24) ? w.z : w.w;
+    return (word >> ((v & 7) * 4)) & 15u;
+}
+__device__ __forceinline__ void vw_inc(uint4 &w, int v) {
+    const uint32_t inc = 1u << ((v & 7) * 4);
+    if (v < 8) w.x += inc; else if (v < 16) w.y += inc; else if (v < 24) w.z += inc; else w.w += inc;
+}
+
+__device__ __forceinline__ void count_evals(const PassK &K, unsigned n_old, unsigned n_new, unsigned n_geom) {
+    const unsigned m = __activemask();
+    const unsigned a = __reduce_add_sync(m, n_old), b = __reduce_add_sync(m, n_new), c = __reduce_add_sync(m, n_geom);
+    if ((int)(threadIdx.x & 31u) == __ffs(m) - 1) {
+        if (a) atomicAdd(&K.counters[0], (unsigned long long)a);
+        if (b) atomicAdd(&K.counters[1], (unsigned long long)b);
+        if (c) atomicAdd(&K.counters[2], (unsigned long long)c);
+    }
+}
+
+}  // namespace apde

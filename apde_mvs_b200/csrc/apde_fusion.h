@@ -1,0 +1,29 @@
+// apde_fusion.h -- GPU fusion: WeakVisFilter + RunFusion (APD.cpp:962-1227).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/apde.h"
+
+namespace apde {
+
+struct FusionView {
+    apde_camera cam;       // rescaled to the map size (RescaleImageAndCamera, APD.cpp:844-864)
+    const float *depth;    // [P]
+    const float *normal;   // [P][3]
+    const uint8_t *weak;   // [P]
+    const uint8_t *conf;   // [P]
+    const uint8_t *bgr;    // full-resolution colour image [Hfull][Wfull][3] or nullptr
+    std::vector<int> src;  // neighbour view indices
+};
+
+// skip: [V][P] device, zero-initialised by the caller
+cudaError_t fusion_weak_vis_filter(const std::vector<FusionView> &views, int w, int h, int Wfull, int Hfull, uint8_t *skip,
+                                   cudaStream_t st);
+// greedy fusion in the reference order; xyz / bgr are HOST buffers (may be null)
+cudaError_t fusion_run(const std::vector<FusionView> &views, int w, int h, const uint8_t *skip, float *xyz, float *bgr,
+                       int64_t max_points, int64_t *num_points, cudaStream_t st, uint64_t *launches);
+
+}  // namespace apde

@@ -1,0 +1,616 @@
+// apde_kernels.cu -- the PatchMatch pass kernels (sm_100a).  One thread per pixel; red/black half-sweeps update in
+// place because every neighbour read is of the opposite colour (same invariant as the reference).
+//
+// Each kernel cites the reference kernel it replaces.  Integer / scheduling artefacts (colouring, candidate index
+// sets, tie rules, zero-initialised cost rows of invalid neighbours) follow the reference bit for bit; see
+// SURVEY.md section 9 for the quirk list.
+#include "apde_device.cuh"
+#include "apde_kernels.h"
+#include "apde_common.cuh"
+
+#include <cfloat>
+
+namespace apde {
+
+// -------------------------------------------------------------------------------------------- K5 init
+// RandomInitialization + ComputeMultiViewInitialCostandSelectedViews, APD.cu:919-948, 723-774
+__global__ void __launch_bounds__(128) k_init(const __grid_constant__ PassK K, int tiles_x) {
+    int px, py;
+    if (!full_pixel(K, tiles_x, px, py)) return;
+    const int center = py * K.W + px;
+    float4 pl;
+    if (K.state == APDE_FIRST_INIT) {
+        Rng rng(K.seed, K.stream, (uint32_t)center, SITE_INIT);
+        const float depth = rng.uniform() * (K.depth_max - K.depth_min) + K.depth_min;
+        pl = random_normal(K, px, py, rng, depth);
+        pl.w = distance_to_origin(K, px, py, depth, pl);
+    } else {
+        pl = normal_to_refcam(K, K.planes[center]);
+        pl.w = distance_to_origin(K, px, py, pl.w, pl);
+    }
+    K.planes[center] = pl;
+
+    RefPatch rp;
+    load_ref_patch(K, px, py, rp);
+    const float3 m = plane_row(K, pl);
+    const bool weak = K.use_apd && K.weak[center] == APDE_WEAK;
+    float cv[kMaxSrc], cvc[kMaxSrc];
+    int num_valid = 0;
+    for (int v = 0; v < K.N; ++v) {
+        const float c = weak ? ncc_new(K, K.v[v], v, px, py, m, rp, K.anchors + (size_t)center * APDE_ANCHOR_NUM)
+                             : ncc_old(K, K.v[v], px, py, m, rp);
+        cv[v] = c; cvc[v] = c;
+        if (c < 2.0f) num_valid++;
+    }
+    // sort_small, APD.cu:3-12
+    for (int i = 1; i < K.N; i++) {
+        const float tmp = cv[i];
+        int j;
+        for (j = i; j >= 1 && tmp < cv[j - 1]; j--) cv[j] = cv[j - 1];
+        cv[j] = tmp;
+    }
+    uint32_t sel = 0;
+    float cost = 2.0f;
+    const int top_k = min(num_valid, K.top_k);
+    if (top_k > 0) {
+        float acc = 0.0f;
+        for (int i = 0; i < top_k; ++i) acc += cv[i];
+        const float thr = cv[top_k - 1];
+        for (int i = 0; i < K.N; ++i) if (cvc[i] <= thr) sel |= (1u << i);
+        cost = acc / top_k;
+    }
+    K.sel[center] = sel;
+    K.costs[center] = cost;
+    count_evals(K, weak ? 0 : K.N, weak ? K.N : 0, 0);
+}
+
+// -------------------------------------------------------------------------------------------- checkerboard candidates
+// APD.cu:1127-1314.  pos[k]: 0 up_near 1 up_far 2 down_near 3 down_far 4 left_near 5 left_far 6 right_near 7 right_far
+__device__ __forceinline__ unsigned checkerboard_candidates(const float *costs, int width, int height, int px,
+                                                            int py, int pos[8]) {
+    const int center = py * width + px;
+    unsigned flags = 0;
+    float cmin;
+    int cpt;
+    int up_far = center - 3 * width, down_far = center + 3 * width, left_far = center - 3, right_far = center + 3;
+    int up_near = center - width, down_near = center + width, left_near = center - 1, right_near = center + 1;
+#define APDE_TRY(cond, idx)                                      \
+    if (cond) {                                                  \
+        const int pt_ = (idx);                                   \
+        const float c_ = costs[pt_];                     \
+        if (c_ < cmin) { cmin = c_; cpt = pt_; }                 \
+    }
+    if (py > 2) {
+        flags |= 2u; cmin = costs[up_far]; cpt = up_far;
+#pragma unroll
+        for (int i = 1; i < 11; ++i) APDE_TRY(py > 2 + 2 * i, up_far - 2 * i * width)
+        up_far = cpt;
+    }
+    if (py < height - 3) {
+        flags |= 8u; cmin = costs[down_far]; cpt = down_far;
+#pragma unroll
+        for (int i = 1; i < 11; ++i) APDE_TRY(py < height - 3 - 2 * i, down_far + 2 * i * width)
+        down_far = cpt;
+    }
+    if (px > 2) {
+        flags |= 32u; cmin = costs[left_far]; cpt = left_far;
+#pragma unroll
+        for (int i = 1; i < 11; ++i) APDE_TRY(px > 2 + 2 * i, left_far - 2 * i)
+        left_far = cpt;
+    }
+    if (px < width - 3) {
+        flags |= 128u; cmin = costs[right_far]; cpt = right_far;
+#pragma unroll
+        for (int i = 1; i < 11; ++i) APDE_TRY(px < width - 3 - 2 * i, right_far + 2 * i)
+        right_far = cpt;
+    }
+    if (py > 0) {
+        flags |= 1u; cmin = costs[up_near]; cpt = up_near;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            APDE_TRY(py > 1 + i && px > i, up_near - (1 + i) * width - (i + 1))
+            APDE_TRY(py > 1 + i && px < width - 1 - i, up_near - (1 + i) * width + (i + 1))
+        }
+        up_near = cpt;
+    }
+    if (py < height - 1) {
+        flags |= 4u; cmin = costs[down_near]; cpt = down_near;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            APDE_TRY(py < height - 2 - i && px > i, down_near + (1 + i) * width - (i + 1))
+            APDE_TRY(py < height - 2 - i && px < width - 1 - i, down_near + (1 + i) * width + (i + 1))
+        }
+        down_near = cpt;
+    }
+    if (px > 0) {
+        flags |= 16u; cmin = costs[left_near]; cpt = left_near;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            APDE_TRY(px > 1 + i && py > i, left_near - (1 + i) - (i + 1) * width)
+            APDE_TRY(px > 1 + i && py < height - 1 - i, left_near - (1 + i) + (i + 1) * width)
+        }
+        left_near = cpt;
+    }
+    if (px < width - 1) {
+        flags |= 64u; cmin = costs[right_near]; cpt = right_near;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            APDE_TRY(px < width - 2 - i && py > i, right_near + (1 + i) - (i + 1) * width)
+            APDE_TRY(px < width - 2 - i && py < height - 1 - i, right_near + (1 + i) + (i + 1) * width)
+        }
+        right_near = cpt;
+    }
+#undef APDE_TRY
+    pos[0] = up_near; pos[1] = up_far; pos[2] = down_near; pos[3] = down_far;
+    pos[4] = left_near; pos[5] = left_far; pos[6] = right_near; pos[7] = right_far;
+    return flags;
+}
+
+// -------------------------------------------------------------------------------------------- K6 strong propagation
+// Black/RedPixelUpdateStrong -> CheckerboardPropagationStrong -> PlaneHypothesisRefinementStrong,
+// APD.cu:1654-1692, 1098-1440, 950-1006.
+//
+// phase 1: 8 candidates x N views (uniform view loop, costs parked in shared memory)
+// phase 2: joint view selection (15 Monte-Carlo draws from the CDF)
+// phase 3: current hypothesis + 5 refinement candidates, evaluated ONLY on views with non-zero weight -- zero-weight
+//          views contribute exactly 0 to the reference's weighted sums (costs are finite by construction), so
+//          skipping them is bit-identical and removes (N - S) of every N evaluations here.
+__global__ void __launch_bounds__(128) k_prop_strong(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
+                                                     int ylimit) {
+    extern __shared__ float smem[];
+    const ViewK *s_vk = stage_views(K, smem);
+    int px, py;
+    if (!half_pixel(K, color, tiles_x, ylimit, px, py)) return;
+    const int W = K.W, N = K.N;
+    const int center = py * W + px;
+    if (K.weak[center] == APDE_WEAK) return;
+    const int stride = blockDim.x;
+    float *sc = smem + views_smem_floats(N) + threadIdx.x;  // [8N][stride]
+    float *sp = sc + 8 * N * stride;                        // [N][stride]
+
+    RefPatch rp;
+    load_ref_patch(K, px, py, rp);
+    unsigned n_old = 0, n_geom = 0;
+
+    int pos[8];
+    const unsigned flags = checkerboard_candidates(K.costs, W, K.H, px, py, pos);
+#pragma unroll 1
+    for (int h = 0; h < 8; ++h) {
+        if ((flags >> h) & 1u) {
+            const float3 m = plane_row(K, K.planes[pos[h]]);
+#pragma unroll 1
+            for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_old(K, K.v[v], px, py, m, rp);
+            n_old += N;
+        } else {
+            // quirk 2: "float cost_array[8][32] = {2.0f}" leaves every entry 0 except [0][0]
+            for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = (h == 0 && v == 0) ? 2.0f : 0.0f;
+        }
+    }
+
+    uint32_t nbr_sel[4];
+    const unsigned nbr_valid = ((flags >> 0) & 1u) | (((flags >> 2) & 1u) << 1) | (((flags >> 4) & 1u) << 2) |
+                               (((flags >> 6) & 1u) << 3);
+    nbr_sel[0] = (nbr_valid & 1u) ? K.sel[center - W] : 0u;
+    nbr_sel[1] = (nbr_valid & 2u) ? K.sel[center + W] : 0u;
+    nbr_sel[2] = (nbr_valid & 4u) ? K.sel[center - 1] : 0u;
+    nbr_sel[3] = (nbr_valid & 8u) ? K.sel[center + 1] : 0u;
+
+    Rng rng(K.seed, K.stream, (uint32_t)center, SITE_STRONG + iter);
+    uint32_t wmask;
+    float wnorm;
+    const uint4 w = select_views<4>(K, sc, sp, stride, nbr_sel, nbr_valid, iter, rng, &wmask, &wnorm);
+    K.vw[center] = w;
+
+    float final_costs[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+        float acc = 0.0f;
+        for (uint32_t mk = wmask; mk; mk &= mk - 1) {
+            const int v = __ffs(mk) - 1;
+            acc += (float)vw_get(w, v) * sc[(h * N + v) * stride];
+        }
+        final_costs[h] = acc / wnorm;
+    }
+    int min_idx = 0;
+    {
+        float mc = final_costs[0];
+#pragma unroll
+        for (int h = 1; h < 8; ++h) if (final_costs[h] <= mc) { mc = final_costs[h]; min_idx = h; }  // ties -> last (quirk 3)
+    }
+    float fc_min = final_costs[0];
+#pragma unroll
+    for (int h = 1; h < 8; ++h) if (h == min_idx) fc_min = final_costs[h];
+
+    const bool use_geom = K.geom && K.impetus;
+    const float4 plane_c = K.planes[center];
+    float4 plane_now = plane_c;
+    float depth_now = 0.0f, cost_now = 0.0f, cost_written = 0.0f;
+    float4 cand_n[2];  // 0: random normal, 1: perturbed normal
+    float depth_rand = 0.0f, depth_pert = 0.0f;
+    const float dmin = K.depth_min, dmax = K.depth_max;
+
+    // current hypothesis on the selected views
+    {
+        const float3 m = plane_row(K, plane_c);
+        float acc = 0.0f;
+        for (uint32_t mk = wmask; mk; mk &= mk - 1) {
+            const int v = __ffs(mk) - 1;
+            float c = ncc_old(K, s_vk[v], px, py, m, rp);
+            n_old++;
+            if (use_geom) { c = c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, plane_c); n_geom++; }
+            acc += (float)vw_get(w, v) * c;
+        }
+        cost_now = acc / wnorm;
+    }
+    cost_written = cost_now;
+    depth_now = depth_from_plane(K, plane_c, px, py);
+    if ((flags >> min_idx) & 1u) {
+        const float4 cand = K.planes[pos[min_idx]];
+        const float db = depth_from_plane(K, cand, px, py);
+        if (db >= dmin && db <= dmax && fc_min < cost_now) {
+            depth_now = db; plane_now = cand; cost_now = fc_min;
+            K.sel[center] = wmask;
+        }
+    }
+    // PlaneHypothesisRefinementStrong: all five candidates are built from the state BEFORE the loop (APD.cu:968-980)
+    depth_rand = rng.uniform() * (dmax - dmin) + dmin;
+    cand_n[0] = random_normal(K, px, py, rng, depth_now);
+    {
+        const float lo = (1.0f - 0.02f) * depth_now, hi = (1.0f + 0.02f) * depth_now;
+        depth_pert = rng.uniform() * (hi - lo) + lo;  // the do-while can never repeat (quirk 6)
+    }
+    cand_n[1] = perturbed_normal(K, px, py, plane_now, rng, (float)(0.02 * 3.14159265358979323846));
+    const float4 base_n = plane_now;
+    const float base_d = depth_now;
+#pragma unroll 1
+    for (int i = 0; i < 5; ++i) {
+        float4 tp = (i == 0 || i == 4) ? base_n : (i == 3 ? cand_n[1] : cand_n[0]);
+        const float d = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : base_d);
+        tp.w = distance_to_origin(K, px, py, d, tp);
+        const float3 m = plane_row(K, tp);
+        float acc = 0.0f;
+        for (uint32_t mk = wmask; mk; mk &= mk - 1) {
+            const int v = __ffs(mk) - 1;
+            float c = ncc_old(K, s_vk[v], px, py, m, rp);
+            n_old++;
+            if (use_geom) { c = c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp); n_geom++; }
+            acc += (float)vw_get(w, v) * c;
+        }
+        const float tc = acc / wnorm;
+        const float db = depth_from_plane(K, tp, px, py);
+        if (db >= dmin && db <= dmax && tc < cost_now) { depth_now = db; plane_now = tp; cost_now = tc; }
+    }
+    if (K.state == APDE_REFINE_INIT) {
+        // costs[center] was overwritten with the recomputed current cost before this test (quirk 5)
+        if ((double)cost_now < (double)cost_written - 0.1) { K.costs[center] = cost_now; K.planes[center] = plane_now; }
+        else K.costs[center] = cost_written;
+    } else {
+        K.costs[center] = cost_now;
+        K.planes[center] = plane_now;
+    }
+    count_evals(K, n_old, 0, n_geom);
+}
+
+// -------------------------------------------------------------------------------------------- K9
+// GetDepthandNormal, APD.cu:1694-1709
+__global__ void __launch_bounds__(256) k_depth_normal(const __grid_constant__ PassK K) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K.W * K.H) return;
+    const int px = idx % K.W, py = idx / K.W;
+    float4 pl = K.planes[idx];
+    pl.w = depth_from_plane(K, pl, px, py);
+    K.planes[idx] = normal_to_world(K, pl);
+}
+
+// -------------------------------------------------------------------------------------------- K10 median
+// Black/RedPixelFilterStrong -> CheckerboardFilterStrong, APD.cu:1711-1855
+__global__ void __launch_bounds__(128) k_median(const __grid_constant__ PassK K, int color, int tiles_x, int ylimit) {
+    int px, py;
+    if (!half_pixel(K, color, tiles_x, ylimit, px, py)) return;
+    const int width = K.W, height = K.H;
+    const int center = py * width + px;
+    if (K.weak[center] == APDE_WEAK) return;
+    if (K.costs[center] < 0.001f) return;
+    float f[21];
+    int n = 0;
+    f[n++] = K.planes[center].w;
+    const int left = center - 1, leftleft = center - 3, up = center - width, upup = center - 3 * width;
+    const int down = center + width, downdown = center + 3 * width, right = center + 1, rightright = center + 3;
+#define APDE_TAP(cond, idx) if ((cond) && K.weak[(idx)] == APDE_STRONG) f[n++] = K.planes[(idx)].w;
+    APDE_TAP(py > 0, up)
+    APDE_TAP(py > 2, upup)
+    APDE_TAP(py > 4, upup - width * 2)
+    APDE_TAP(py < height - 1, down)
+    APDE_TAP(py < height - 3, downdown)
+    APDE_TAP(py < height - 5, downdown + width * 2)
+    APDE_TAP(px > 0, left)
+    APDE_TAP(px > 2, leftleft)
+    APDE_TAP(px > 4, leftleft - 2)
+    APDE_TAP(px < width - 1, right)
+    APDE_TAP(px < width - 3, rightright)
+    APDE_TAP(px < width - 5, rightright + 2)
+    APDE_TAP(py > 0 && px < width - 2, up + 2)
+    APDE_TAP(py < height - 1 && px < width - 2, down + 2)
+    APDE_TAP(py > 0 && px > 1, up - 2)
+    APDE_TAP(py < height - 1 && px > 1, down - 2)
+    APDE_TAP(px > 0 && py > 2, left - width * 2)
+    APDE_TAP(px < width - 1 && py > 2, right - width * 2)
+    APDE_TAP(px > 0 && py < height - 2, left + width * 2)
+    APDE_TAP(px < width - 1 && py < height - 2, right + width * 2)
+#undef APDE_TAP
+    for (int i = 1; i < n; i++) {
+        const float tmp = f[i];
+        int j;
+        for (j = i; j >= 1 && tmp < f[j - 1]; j--) f[j] = f[j - 1];
+        f[j] = tmp;
+    }
+    const int mi = n / 2;
+    K.planes[center].w = (n % 2 == 0) ? (f[mi - 1] + f[mi]) / 2 : f[mi];
+}
+
+// -------------------------------------------------------------------------------------------- K11 DepthToWeak
+// APD.cu:2103-2250: 61-sample disparity sweep of the view-weighted cost -> WEAK / STRONG / UNKNOWN
+__global__ void __launch_bounds__(128) k_depth_to_weak(const __grid_constant__ PassK K, int tiles_x, float *curve) {
+    extern __shared__ float smem[];
+    const ViewK *s_vk = stage_views(K, smem);
+    int px, py;
+    if (!full_pixel(K, tiles_x, px, py)) return;
+    const int W = K.W, H = K.H;
+    const int center = py * W + px;
+    const int min_margin = 6;
+    if (px < min_margin || py < min_margin || px >= W - min_margin || py >= H - min_margin) { K.weak[center] = APDE_UNKNOWN; return; }
+    float4 opl = normal_to_refcam(K, K.planes[center]);
+    const float origin_depth = opl.w;
+    if (origin_depth == 0.0f) { K.weak[center] = APDE_UNKNOWN; return; }
+    const uint32_t sel = K.sel[center];
+    const uint4 w = K.vw[center];
+    float base_line = 0.0f, weight_normal = 0.0f;
+    int valid_src = 0;
+    for (uint32_t mk = sel; mk; mk &= mk - 1) {
+        const int v = __ffs(mk) - 1;
+        weight_normal += (float)vw_get(w, v);
+        base_line += s_vk[v].baseline;
+        valid_src++;
+    }
+    if (valid_src == 0) { K.weak[center] = APDE_UNKNOWN; return; }
+    base_line /= valid_src;
+
+    RefPatch rp;
+    load_ref_patch(K, px, py, rp);
+    unsigned n_old = 0, n_geom = 0;
+    const float fb = K.fx * base_line;
+    const float disp = fb / origin_depth;
+    const int radius = 30, n = 61;
+    float pc[61];
+#pragma unroll 1
+    for (int pd = -radius; pd <= radius; ++pd) {
+        const float p_depth = fb / (disp + pd);
+        if (p_depth < K.depth_min || p_depth > K.depth_max) { pc[pd + radius] = 2.0f; continue; }
+        float4 tp = opl;
+        tp.w = distance_to_origin(K, px, py, p_depth, tp);
+        const float3 m = plane_row(K, tp);
+        float p_cost = 0.0f;
+        for (uint32_t mk = sel; mk; mk &= mk - 1) {
+            const int v = __ffs(mk) - 1;
+            float tc = ncc_old(K, s_vk[v], px, py, m, rp);
+            n_old++;
+            if (K.geom) { tc += K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp); n_geom++; }
+            p_cost += tc * (float)vw_get(w, v);
+        }
+        p_cost /= weight_normal;
+        pc[pd + radius] = (2.0f > p_cost) ? p_cost : 2.0f;  // OpenCV MIN(2.0f, p_cost): NaN -> 2
+    }
+    count_evals(K, n_old, 0, n_geom);
+    if (curve) for (int i = 0; i < n; ++i) curve[(size_t)center * n + i] = pc[i];
+
+    unsigned long long peaks = 0ull;
+    int peak_count = 0, min_peak = 0;
+    float min_cost = 2.0f;
+    for (int i = 2; i < n - 2; ++i) {
+        if (pc[i - 1] > pc[i] && pc[i + 1] > pc[i]) {
+            peaks |= 1ull << i;
+            peak_count++;
+            if (pc[i] < min_cost) { min_peak = i; min_cost = pc[i]; }
+        }
+    }
+    if (abs(min_peak - radius) > K.weak_peak_radius || pc[min_peak] > 0.5f) { K.weak[center] = APDE_WEAK; return; }
+    if (peak_count == 1) { K.weak[center] = (pc[min_peak] <= 0.15f) ? APDE_STRONG : APDE_WEAK; return; }
+    float var = 0.0f;
+    for (int i = 2; i < n - 2; ++i) {
+        if (((peaks >> i) & 1ull) && i != min_peak) { const float d = pc[i] - min_cost; var += d * d; }
+    }
+    var = sqrtf(var);
+    var /= (peak_count - 1);
+    K.weak[center] = (var > 0.2f) ? APDE_STRONG : APDE_WEAK;
+}
+
+// -------------------------------------------------------------------------------------------- K12 confidence
+// ConfidenceCompute, APD.cu:2282-2344
+__global__ void __launch_bounds__(128) k_confidence(const __grid_constant__ PassK K, int tiles_x) {
+    extern __shared__ float smem[];
+    const ViewK *s_vk = stage_views(K, smem);
+    int px, py;
+    if (!full_pixel(K, tiles_x, px, py)) return;
+    const int center = py * K.W + px;
+    K.conf[center] = 0;
+    const uint32_t sel = K.sel[center];
+    const float ref_depth = K.planes[center].w;
+    if (ref_depth <= 0.0f) { K.weak[center] = APDE_UNKNOWN; return; }
+    const float fxp = (float)px, fyp = (float)py;
+    int nc = 1;
+    for (uint32_t mk = sel; mk; mk &= mk - 1) {
+        const int v = __ffs(mk) - 1;
+        const ViewK &vk = s_vk[v];
+        const float qx = vk.A[0] * fxp + vk.A[1] * fyp + vk.A[2];
+        const float qy = vk.A[3] * fxp + vk.A[4] * fyp + vk.A[5];
+        const float qz = vk.A[6] * fxp + vk.A[7] * fyp + vk.A[8];
+        const float Z = fmaf(ref_depth, qz, vk.b[2]);
+        const float sx = fmaf(ref_depth, qx, vk.b[0]) / Z, sy = fmaf(ref_depth, qy, vk.b[1]) / Z;
+        const int ix = clampi(__float2int_rz(sx), 0, K.W - 1), iy = clampi(__float2int_rz(sy), 0, K.H - 1);
+        const float sd = K.depth[(size_t)(v + 1) * K.W * K.H + (size_t)iy * K.W + ix];
+        if (sd <= 0.0f) continue;
+        nc += 1;
+        const float rx = vk.Ai[0] * sx + vk.Ai[1] * sy + vk.Ai[2];
+        const float ry = vk.Ai[3] * sx + vk.Ai[4] * sy + vk.Ai[5];
+        const float rz = vk.Ai[6] * sx + vk.Ai[7] * sy + vk.Ai[8];
+        const float Zr = fmaf(sd, rz, vk.bi[2]);
+        const float bx = fmaf(sd, rx, vk.bi[0]) / Zr, by = fmaf(sd, ry, vk.bi[1]) / Zr;
+        const float dc = fxp - bx, dr = fyp - by;
+        if (sqrtf(dc * dc + dr * dr) <= 2.0f) nc += 2;
+        if (fabsf(ref_depth - Zr) / ref_depth <= 0.02f) nc += 2;
+    }
+    K.conf[center] = (uint8_t)min(nc, 255);
+}
+
+// -------------------------------------------------------------------------------------------- K13 local refine
+// LocalRefine, APD.cu:2346-2432
+__global__ void __launch_bounds__(128) k_local_refine(const __grid_constant__ PassK K, int tiles_x) {
+    extern __shared__ float smem[];
+    const ViewK *s_vk = stage_views(K, smem);
+    int px, py;
+    if (!full_pixel(K, tiles_x, px, py)) return;
+    const int center = py * K.W + px;
+    float4 opl = normal_to_refcam(K, K.planes[center]);
+    const float origin_depth = opl.w;
+    if (origin_depth == 0.0f) return;
+    const uint32_t sel = K.sel[center];
+    if (sel == 0u) return;
+    const uint4 w = K.vw[center];
+    RefPatch rp;
+    load_ref_patch(K, px, py, rp);
+    unsigned n_old = 0, n_geom = 0;
+    float cost_now = 0.0f, base_line = 0.0f, weight_normal = 0.0f;
+    int valid_src = 0;
+    {
+        float4 tp = opl;
+        tp.w = distance_to_origin(K, px, py, origin_depth, tp);
+        const float3 m = plane_row(K, tp);
+        for (uint32_t mk = sel; mk; mk &= mk - 1) {
+            const int v = __ffs(mk) - 1;
+            float tc = ncc_old(K, s_vk[v], px, py, m, rp);
+            n_old++;
+            if (K.geom) { tc += K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp); n_geom++; }
+            const float wv = (float)vw_get(w, v);
+            cost_now += tc * wv;
+            weight_normal += wv;
+            base_line += s_vk[v].baseline;
+            valid_src++;
+        }
+    }
+    if (weight_normal == 0.0f) { count_evals(K, n_old, 0, n_geom); return; }
+    cost_now /= weight_normal;
+    base_line /= valid_src;
+    const float fb = K.fx * base_line;
+    const float disp = fb / origin_depth;
+    float min_cost = 2.0f, best_depth = origin_depth;
+#pragma unroll 1
+    for (int pd = -5; pd <= 5; ++pd) {
+        const float p_depth = fb / (disp + pd);
+        if (p_depth < K.depth_min || p_depth > K.depth_max) continue;
+        float4 tp = opl;
+        tp.w = distance_to_origin(K, px, py, p_depth, tp);
+        const float3 m = plane_row(K, tp);
+        float tc = 0.0f;
+        for (uint32_t mk = sel; mk; mk &= mk - 1) {
+            const int v = __ffs(mk) - 1;
+            const float wv = (float)vw_get(w, v);
+            tc += ncc_old(K, s_vk[v], px, py, m, rp) * wv;
+            n_old++;
+            if (K.geom) { tc += K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp) * wv; n_geom++; }
+        }
+        tc /= weight_normal;
+        if (tc < min_cost) { min_cost = tc; best_depth = p_depth; }
+    }
+    if ((double)(cost_now - min_cost) > 0.1) K.planes[center].w = best_depth;
+    count_evals(K, n_old, 0, n_geom);
+}
+
+// -------------------------------------------------------------------------------------------- parity hook
+__global__ void __launch_bounds__(128) k_eval_costs(const __grid_constant__ PassK K, int n, const int *__restrict__ tuples,
+                                                    const float4 *__restrict__ planes, int mode, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int px = tuples[3 * i], py = tuples[3 * i + 1], v = tuples[3 * i + 2] - 1;
+    const float4 pl = planes[i];
+    float c;
+    if (mode == 2) {
+        c = geom_cost(K, K.v[v], v, px, py, pl);
+    } else {
+        RefPatch rp;
+        load_ref_patch(K, px, py, rp);
+        const float3 m = plane_row(K, pl);
+        c = (mode == 0) ? ncc_old(K, K.v[v], px, py, m, rp)
+                        : ncc_new(K, K.v[v], v, px, py, m, rp, K.anchors + (size_t)(py * K.W + px) * APDE_ANCHOR_NUM);
+    }
+    out[i] = c;
+}
+
+// -------------------------------------------------------------------------------------------- launchers
+static size_t prop_smem_bytes(int N, int threads) { return sizeof(float) * ((size_t)views_smem_floats(N) + (size_t)9 * N * threads); }
+int prop_block_threads(int N) {
+    if (prop_smem_bytes(N, 128) <= 56 * 1024) return 128;
+    if (prop_smem_bytes(N, 64) <= 64 * 1024) return 64;
+    return 32;
+}
+
+cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStream_t st, float *curve) {
+    const int W = K.W, H = K.H, N = K.N;
+    const int ylimit = min(H, half_rows_limit(H));
+    const int tiles8x = (W + 7) / 8;
+    const size_t vsm = sizeof(float) * views_smem_floats(N);
+    switch (stage) {
+        case APDE_STAGE_INIT: {
+            const int tiles = tiles8x * ((H + 3) / 4);
+            k_init<<<(tiles + 3) / 4, 128, 0, st>>>(K, tiles8x);
+            break;
+        }
+        case APDE_STAGE_PROP_STRONG: {
+            const int threads = prop_block_threads(N);
+            const size_t smem = prop_smem_bytes(N, threads);
+            static size_t configured = 0;
+            if (smem > configured) {
+                cudaError_t e = cudaFuncSetAttribute(k_prop_strong, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                configured = smem;
+            }
+            const int tiles = tiles8x * ((ylimit + 7) / 8);
+            const int wpb = threads / 32;
+            k_prop_strong<<<(tiles + wpb - 1) / wpb, threads, smem, st>>>(K, iter, color, tiles8x, ylimit);
+            break;
+        }
+        case APDE_STAGE_DEPTH_NORMAL:
+            k_depth_normal<<<(W * H + 255) / 256, 256, 0, st>>>(K);
+            break;
+        case APDE_STAGE_MEDIAN: {
+            const int tiles = tiles8x * ((ylimit + 7) / 8);
+            k_median<<<(tiles + 3) / 4, 128, 0, st>>>(K, color, tiles8x, ylimit);
+            break;
+        }
+        case APDE_STAGE_DEPTH_TO_WEAK: {
+            const int tiles = tiles8x * ((H + 3) / 4);
+            k_depth_to_weak<<<(tiles + 3) / 4, 128, vsm, st>>>(K, tiles8x, curve);
+            break;
+        }
+        case APDE_STAGE_CONFIDENCE: {
+            const int tiles = tiles8x * ((H + 3) / 4);
+            k_confidence<<<(tiles + 3) / 4, 128, vsm, st>>>(K, tiles8x);
+            break;
+        }
+        case APDE_STAGE_LOCAL_REFINE: {
+            const int tiles = tiles8x * ((H + 3) / 4);
+            k_local_refine<<<(tiles + 3) / 4, 128, vsm, st>>>(K, tiles8x);
+            break;
+        }
+        default:
+            return launch_stage_apd(K, stage, iter, color, st);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_eval_costs(const PassK &K, int n, const int *tuples, const float4 *planes, int mode, float *out,
+                              cudaStream_t st) {
+    k_eval_costs<<<(n + 127) / 128, 128, 0, st>>>(K, n, tuples, planes, mode, out);
+    return cudaGetLastError();
+}
+
+}  // namespace apde

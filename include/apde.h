@@ -1,0 +1,218 @@
+/*
+ * apde.h -- C ABI of libapde (B200-native APDe-MVS hot path: deformable-PatchMatch depth/normal estimation
+ * + depth/normal fusion).  Plain C types only: no C++, CUDA or torch types cross this boundary.
+ *
+ * Every entry point replaces a piece of the reference's driver interface (file:line into the reference tree):
+ *
+ *   apde_create / apde_destroy          <- cudaSetDevice(gpu_index)                      main.cpp:264
+ *   apde_scene_begin / _set_view / _set_pairs / _commit
+ *                                       <- GenerateSampleList + ReadImage + ReadCamera   main.cpp:44-102, APD.cpp:85-160
+ *                                          (images/cameras become scene-resident instead of MemoryCache, APD.cpp:3-16)
+ *   apde_problem_setup                  <- APD::APD + InuputInitialization + CudaSpaceInitialization
+ *                                          + SetDataPassHelperInCuda                     APD.cpp:458-814
+ *   apde_problem_stage / apde_problem_run
+ *                                       <- APD::RunPatchMatch (one kernel / all kernels) APD.cu:2663-2737
+ *   apde_problem_get / apde_problem_set <- GetPlaneHypothesis / GetPixelStates / GetConfidence   APD.cpp:816-826
+ *   apde_problem_finish                 <- ProcessProblem tail: depth range check + WriteBinMat  main.cpp:168-190
+ *   apde_pass_run                       <- ProcessProblem                                main.cpp:148-208
+ *   apde_run_schedule                   <- main()'s round x iteration x problem loops    main.cpp:303-367
+ *   apde_view_download / apde_view_upload
+ *                                       <- ReadBinMat / WriteBinMat of depths/normals/weak/confidence.bin  APD.cpp:18-83
+ *   apde_eval_costs                     <- ComputeBilateralNCCOld/New, ComputeGeomConsistencyCost (parity hook)
+ *                                                                                        APD.cu:448-721, 865-902
+ *   apde_weak_vis_filter / apde_fuse    <- WeakVisFilter, RunFusion                      APD.cpp:962-1227
+ *   apde_get_counters                   <- (none; the reference only prints wall-clock, main.cpp:157-161)
+ *   apde_last_error                     <- CudaSafeCall / CudaCheckError                 APD.cpp:417-450
+ *
+ * Conventions: every function returns 0 on success and a negative apde_status otherwise (the reference prints and
+ * exit()s; a library must not).  Host buffers are caller-owned; device state is owned by the context.  One context
+ * per GPU; calls on one context must be serialised by the caller.  There is NO CPU fallback: without a usable CUDA
+ * device apde_create fails with APDE_ERR_CUDA.
+ */
+#ifndef APDE_H_
+#define APDE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APDE_MAX_IMAGES 32 /* main.h:40 */
+#define APDE_ANCHOR_NUM 9  /* main.h:41 */
+
+typedef enum {
+    APDE_OK = 0,
+    APDE_ERR_ARG = -1,
+    APDE_ERR_CUDA = -2,
+    APDE_ERR_STATE = -3,
+    APDE_ERR_NOMEM = -4
+} apde_status;
+
+/* RunState, main.h:68-72 */
+enum { APDE_FIRST_INIT = 0, APDE_REFINE_INIT = 1, APDE_REFINE_ITER = 2 };
+/* PixelState, main.h:74-78 */
+enum { APDE_WEAK = 0, APDE_STRONG = 1, APDE_UNKNOWN = 2 };
+
+/* Camera, main.h:50-61 (identical layout, 120 bytes) */
+typedef struct {
+    float K[9];
+    float R[9];
+    float t[3];
+    float c[3];
+    int height;
+    int width;
+    float depth_min;
+    float depth_max;
+    float interval;
+    float depth_num;
+} apde_camera;
+
+/* PatchMatchParams, main.h:80-100 (bools widened to int) */
+typedef struct {
+    int max_iterations;
+    int num_images; /* filled by the library: N + 1 */
+    int top_k;
+    float depth_min; /* filled by the library: 0.6 * cam.depth_min, APD.cpp:554 */
+    float depth_max; /* filled by the library: 1.2 * cam.depth_max, APD.cpp:555 */
+    int geom_consistency;
+    int use_impetus;
+    int strong_radius;
+    int strong_increment;
+    int weak_radius;
+    int weak_increment;
+    int use_APD;
+    int use_sa; /* accepted, ignored: SAM masks are out of scope */
+    int weak_peak_radius;
+    int rotate_time;
+    float ransac_threshold;
+    float geom_factor;
+    int state;
+} apde_params;
+
+/* the reference defaults, main.h:80-100 */
+void apde_params_default(apde_params *p);
+
+typedef struct apde_context apde_context;
+
+int apde_create(int device, apde_context **out);
+void apde_destroy(apde_context *ctx);
+const char *apde_last_error(void);
+/* library build info: "sm_100a;..." */
+const char *apde_version(void);
+
+/* ---------------------------------------------------------------- scene (resident images + cameras + maps) */
+int apde_scene_begin(apde_context *ctx, int num_views, int width, int height);
+/* gray: H*W bytes (what cv::imread(GRAYSCALE) yields, APD.cpp:145) ; bgr may be NULL (only fusion colours need it) */
+int apde_scene_set_view(apde_context *ctx, int view, const uint8_t *gray, const uint8_t *bgr, const apde_camera *cam);
+/* neighbour list of a view = Problem::src_image_ids (main.h:104), at most APDE_MAX_IMAGES-1 entries */
+int apde_scene_set_pairs(apde_context *ctx, int view, int num_src, const int32_t *src_views);
+int apde_scene_commit(apde_context *ctx);
+
+/* maps of a view as the reference stores them in depths/normals/weak/confidence.bin.  normal = float[P][3].
+ * Any pointer may be NULL.  width/height report (download) or give (upload) the map size. */
+int apde_view_download(apde_context *ctx, int view, float *depth, float *normal, uint8_t *weak, uint8_t *conf,
+                       int *width, int *height);
+int apde_view_upload(apde_context *ctx, int view, const float *depth, const float *normal, const uint8_t *weak,
+                     const uint8_t *conf, int width, int height);
+
+/* ---------------------------------------------------------------- one problem = one reference view, one pass */
+int apde_problem_setup(apde_context *ctx, int ref_view, const apde_params *params, int scale_size, uint32_t seed);
+
+typedef enum {
+    APDE_STAGE_NEAREST_STRONG = 0, /* FindNearestStrongPoint   APD.cu:2434 */
+    APDE_STAGE_GEN_ANCHORS = 1,    /* GenAnchors + NeigbourUpdate APD.cu:1857, 2084 */
+    APDE_STAGE_INIT = 2,           /* RandomInitialization     APD.cu:919 */
+    APDE_STAGE_PROP_STRONG = 3,    /* Black/RedPixelUpdateStrong APD.cu:1654 */
+    APDE_STAGE_RANSAC_FIT = 4,     /* RANSACToGetFitPlane      APD.cu:2486 */
+    APDE_STAGE_PROP_WEAK = 5,      /* Black/RedPixelUpdateWeak APD.cu:1617 */
+    APDE_STAGE_DEPTH_NORMAL = 6,   /* GetDepthandNormal        APD.cu:1694 */
+    APDE_STAGE_MEDIAN = 7,         /* Black/RedPixelFilterStrong APD.cu:1823 */
+    APDE_STAGE_DEPTH_TO_WEAK = 8,  /* DepthToWeak              APD.cu:2103 */
+    APDE_STAGE_CONFIDENCE = 9,     /* ConfidenceCompute        APD.cu:2282 */
+    APDE_STAGE_LOCAL_REFINE = 10   /* LocalRefine              APD.cu:2346 */
+} apde_stage;
+
+/* run one kernel of RunPatchMatch; color 0 = black ((x+y) even), 1 = red */
+int apde_problem_stage(apde_context *ctx, int stage, int iter, int color);
+/* run all of RunPatchMatch in the reference order */
+int apde_problem_run(apde_context *ctx);
+
+typedef enum {
+    APDE_FIELD_PLANES = 0,         /* float4[P] */
+    APDE_FIELD_COSTS = 1,          /* float[P] */
+    APDE_FIELD_SELECTED_VIEWS = 2, /* uint32[P] */
+    APDE_FIELD_VIEW_WEIGHT = 3,    /* uint8[P][32] (reference layout; stored packed on the device) */
+    APDE_FIELD_WEAK_INFO = 4,      /* uint8[P] */
+    APDE_FIELD_CONFIDENCE = 5,     /* uint8[P] */
+    APDE_FIELD_FIT_PLANES = 6,     /* float4[P] */
+    APDE_FIELD_WEAK_RELIABLE = 7,  /* uint8[P] */
+    APDE_FIELD_NEAREST_STRONG = 8, /* short2[P] */
+    APDE_FIELD_ANCHORS = 9,        /* short2[P][9] */
+    APDE_FIELD_IMAGE = 10,         /* float[P], working-resolution reference image (read only) */
+    APDE_FIELD_SRC_DEPTH = 11      /* float[N+1][P], working-resolution depth maps, index 0 = ref (read only) */
+} apde_field;
+
+int apde_problem_get(apde_context *ctx, int field, void *host, size_t bytes);
+int apde_problem_set(apde_context *ctx, int field, const void *host, size_t bytes);
+int apde_problem_dims(apde_context *ctx, int *width, int *height, int *num_images);
+/* working-resolution image of source index idx (0 = ref) and the working cameras, for parity checks */
+int apde_problem_get_image(apde_context *ctx, int idx, float *host, size_t bytes);
+int apde_problem_get_cameras(apde_context *ctx, apde_camera *cams /* [N+1] */, apde_params *params);
+/* write depth/normal/weak/confidence back into the view store (depth range check of main.cpp:172-175) */
+int apde_problem_finish(apde_context *ctx);
+
+/* setup + run + finish */
+int apde_pass_run(apde_context *ctx, int ref_view, const apde_params *params, int scale_size, uint32_t seed);
+
+/* parity hook: per-hypothesis costs of the current problem.  tuples = int32[n][3] (x, y, src_idx>=1),
+ * planes = float[n][4] (camera-frame normal, plane distance).  mode 0 = NCC-Old, 1 = NCC-New, 2 = geometric. */
+int apde_eval_costs(apde_context *ctx, int n, const int32_t *tuples, const float *planes, int mode, float *out);
+
+/* ---------------------------------------------------------------- whole schedule (main.cpp:303-367) */
+typedef struct {
+    int rounds;          /* <= 0: ComputeRoundNum rule (halve max side until <= 800), main.cpp:129-146 */
+    int geom_iterations; /* reference: 3 */
+    int jacobi;          /* 0: reference order (Gauss-Seidel through fresh maps); 1: all views read previous-pass maps */
+    int use_impetus;
+    float geom_factor;   /* 0.2 (0.05 for TaT), main.cpp:294-298 */
+    uint32_t seed;
+    int first_view, num_views_local; /* this rank's shard of reference views (multi-GPU); 0,0 = all */
+} apde_schedule;
+
+void apde_schedule_default(apde_schedule *s);
+
+typedef struct {
+    double patchmatch_ms; /* device time of all RunPatchMatch stages (CUDA events) */
+    double total_ms;      /* including setup / finish of every problem */
+    uint64_t evals_ncc_old, evals_ncc_new, evals_geom;
+    uint64_t kernel_launches;
+    int passes;
+} apde_timing;
+
+int apde_run_schedule(apde_context *ctx, const apde_schedule *s, apde_timing *out);
+/* run one pass (all views of the shard) of the schedule; pass_index counts from 0 as main.cpp's iteration_index */
+int apde_run_schedule_pass(apde_context *ctx, const apde_schedule *s, int pass_index, apde_timing *out);
+int apde_schedule_num_passes(apde_context *ctx, const apde_schedule *s);
+
+/* cumulative device counters since the last reset: [0] NCC-Old evals, [1] NCC-New evals, [2] geom evals,
+ * [3] kernel launches */
+int apde_get_counters(apde_context *ctx, uint64_t out[4], int reset);
+
+/* device pointer + byte size of the replicated depth-map pool ([V][P] float at the current map size) so that a
+ * host-side collective (NCCL all-gather between passes) can exchange shards in place */
+int apde_depth_pool(apde_context *ctx, void **dev_ptr, size_t *bytes, size_t *bytes_per_view);
+
+/* ---------------------------------------------------------------- fusion (APD.cpp:962-1227) */
+/* skip_weaks: uint8[V][P] out (host) or NULL to keep it on the device only */
+int apde_weak_vis_filter(apde_context *ctx, uint8_t *skip_weaks);
+/* RunFusion: returns the number of fused points through *num_points; xyz float[max][3], bgr float[max][3]
+ * (either may be NULL to only count).  use_weak_filter mirrors the CLI flag (main.cpp:19). */
+int apde_fuse(apde_context *ctx, int use_weak_filter, float *xyz, float *bgr, int64_t max_points,
+              int64_t *num_points);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APDE_H_ */

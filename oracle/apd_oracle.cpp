@@ -1,0 +1,1617 @@
+/*
+ * apd_oracle.cpp -- CPU ORACLE (TEST INFRASTRUCTURE ONLY; see apd_oracle.h).
+ *
+ * Plain fp32 restatement of the reference algorithm, one function per reference function, each citing the
+ * reference file:line it follows.  Compiled with -ffp-contract=off so every operation rounds like the
+ * source says.  Nothing in the product (apde_mvs_b200/) links, imports or executes this file.
+ */
+#include "apd_oracle.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+struct F2 { float x, y; };
+struct F3 { float x, y, z; };
+struct F4 { float x, y, z, w; };
+struct S2 { int16_t x, y; };
+struct I2 { int x, y; };
+
+constexpr float kPi = 3.14159265358979323846f;
+constexpr double kPiD = 3.14159265358979323846;
+
+/* OpenCV's MIN/MAX macros as used by the reference (NaN behaviour matters, APD.cu:2185) */
+#define ORC_MIN(a, b) ((a) > (b) ? (b) : (a))
+#define ORC_MAX(a, b) ((a) < (b) ? (b) : (a))
+
+/* ------------------------------------------------------------------------------------------------
+ * RNG: Philox4x32-10, key = (seed, stream), counter = (pixel, site, block, 0).
+ * Replaces curand XORWOW (APD.cu:904-917); uniform() keeps curand_uniform's (0,1] mapping.
+ * ---------------------------------------------------------------------------------------------- */
+inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)M0 * c[0];
+        const uint64_t p1 = (uint64_t)M1 * c[2];
+        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        const uint32_t n0 = hi1 ^ c[1] ^ k0;
+        const uint32_t n1 = lo1;
+        const uint32_t n2 = hi0 ^ c[3] ^ k1;
+        const uint32_t n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += W0; k1 += W1;
+    }
+}
+
+enum Site : uint32_t {
+    SITE_ANCHOR = 1,
+    SITE_INIT = 2,
+    SITE_STRONG = 16,  /* + iter */
+    SITE_FIT = 48,     /* + iter */
+    SITE_WEAK = 80,    /* + iter */
+};
+
+struct Rng {
+    uint32_t k0, k1, pixel, site, n;
+    uint32_t buf[4];
+    Rng(uint32_t seed, uint32_t stream, uint32_t pixel_, uint32_t site_)
+        : k0(seed), k1(stream), pixel(pixel_), site(site_), n(0) {}
+    uint32_t next() {
+        if ((n & 3u) == 0u) {
+            buf[0] = pixel; buf[1] = site; buf[2] = n >> 2; buf[3] = 0u;
+            philox4x32_10(buf, k0, k1);
+        }
+        return buf[(n++) & 3u];
+    }
+    /* (0,1], like curand_uniform: x * 2^-32 + 2^-33 */
+    float uniform() { return std::fmaf((float)next(), 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * texture semantics (APD.cpp:699-706): float32, linear filter, unnormalised, "wrap" == clamp.
+ * tex_mode 1 emulates the texture unit's 1.8 fixed-point interpolation weights.
+ * ---------------------------------------------------------------------------------------------- */
+inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+inline float tex_linear(const float *T, int W, int H, float x, float y, int mode) {
+    float xB = x - 0.5f, yB = y - 0.5f;
+    if (!(xB == xB)) xB = 0.0f;
+    if (!(yB == yB)) yB = 0.0f;
+    xB = std::min(std::max(xB, -1.0f), (float)W);
+    yB = std::min(std::max(yB, -1.0f), (float)H);
+    const float fi = std::floor(xB), fj = std::floor(yB);
+    float a = xB - fi, b = yB - fj;
+    if (mode == 1) {
+        a = std::floor(a * 256.0f + 0.5f) * (1.0f / 256.0f);
+        b = std::floor(b * 256.0f + 0.5f) * (1.0f / 256.0f);
+    }
+    const int i0 = clampi((int)fi, 0, W - 1), i1 = clampi((int)fi + 1, 0, W - 1);
+    const int j0 = clampi((int)fj, 0, H - 1), j1 = clampi((int)fj + 1, 0, H - 1);
+    const double t00 = T[j0 * (size_t)W + i0], t10 = T[j0 * (size_t)W + i1];
+    const double t01 = T[j1 * (size_t)W + i0], t11 = T[j1 * (size_t)W + i1];
+    const double da = a, db = b;
+    return (float)((1.0 - da) * (1.0 - db) * t00 + da * (1.0 - db) * t10 + (1.0 - da) * db * t01 + da * db * t11);
+}
+
+/* texel-centre fetch (x+0.5, y+0.5): exact texel, clamped */
+inline float tex_point(const float *T, int W, int H, int x, int y) {
+    return T[clampi(y, 0, H - 1) * (size_t)W + clampi(x, 0, W - 1)];
+}
+
+/* float -> int with CUDA cvt.rzi semantics (saturating, NaN -> 0), used by "(int)src_pt.x" APD.cu:885 */
+inline int cuda_f2i(float v) {
+    if (!(v == v)) return 0;
+    if (v >= 2147483648.0f) return INT32_MAX;
+    if (v <= -2147483648.0f) return INT32_MIN;
+    return (int)v;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * small helpers (APD.cu:3-38, 60-86, 157-240)
+ * ---------------------------------------------------------------------------------------------- */
+inline void sort_small(float *d, int n) { /* APD.cu:3-12 */
+    int j;
+    for (int i = 1; i < n; i++) {
+        float tmp = d[i];
+        for (j = i; j >= 1 && tmp < d[j - 1]; j--) d[j] = d[j - 1];
+        d[j] = tmp;
+    }
+}
+
+inline int find_min_cost_index(const float *costs, int n) { /* APD.cu:60-71, ties -> last */
+    float min_cost = costs[0];
+    int idx_min = 0;
+    for (int idx = 1; idx < n; ++idx) {
+        if (costs[idx] <= min_cost) { min_cost = costs[idx]; idx_min = idx; }
+    }
+    return idx_min;
+}
+
+inline int is_set(uint32_t v, int n) { return (v >> n) & 1u; }
+
+inline void normalize3(F4 *v) { /* APD.cu:157-164 (rsqrtf) */
+    const float n2 = v->x * v->x + v->y * v->y + v->z * v->z;
+    const float inv = 1.0f / std::sqrt(n2);
+    v->x *= inv; v->y *= inv; v->z *= inv;
+}
+
+inline void normalize2(F2 *v) { /* APD.cu:166-172 */
+    const float n2 = v->x * v->x + v->y * v->y;
+    const float inv = 1.0f / std::sqrt(n2);
+    v->x *= inv; v->y *= inv;
+}
+
+inline void pdf_to_cdf(float *probs, int n) { /* APD.cu:174-188 */
+    float s = 0.0f;
+    for (int i = 0; i < n; ++i) s += probs[i];
+    const float inv = 1.0f / s;
+    float cum = 0.0f;
+    for (int i = 0; i < n; ++i) { const float p = probs[i] * inv; cum += p; probs[i] = cum; }
+}
+
+inline void get_3d_point(const orc_camera &cam, float px, float py, float depth, float *X) { /* APD.cu:190-202 */
+    X[0] = depth * (px - cam.K[2]) / cam.K[0];
+    X[1] = depth * (py - cam.K[5]) / cam.K[4];
+    X[2] = depth;
+}
+
+inline F4 view_direction(const orc_camera &cam, I2 p, float depth) { /* APD.cu:204-216 */
+    float X[3];
+    get_3d_point(cam, (float)p.x, (float)p.y, depth, X);
+    const float norm = std::sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2]);
+    return F4{X[0] / norm, X[1] / norm, X[2] / norm, 0.0f};
+}
+
+inline float distance_to_origin(const orc_camera &cam, I2 p, float depth, F4 n) { /* APD.cu:218-223 */
+    float X[3];
+    get_3d_point(cam, (float)p.x, (float)p.y, depth, X);
+    return -(n.x * X[0] + n.y * X[1] + n.z * X[2]);
+}
+
+inline float depth_from_plane(const orc_camera &cam, F4 pl, I2 p) { /* APD.cu:237-240 */
+    return -pl.w * cam.K[0] /
+           ((p.x - cam.K[2]) * pl.x + (cam.K[0] / cam.K[4]) * (p.y - cam.K[5]) * pl.y + cam.K[0] * pl.z);
+}
+
+inline F4 random_normal(const orc_camera &cam, I2 p, Rng &rng, float depth) { /* APD.cu:242-268 */
+    float q1 = 1.0f, q2 = 1.0f, s = 2.0f;
+    while (s >= 1.0f) {
+        q1 = 2.0f * rng.uniform() - 1.0f;
+        q2 = 2.0f * rng.uniform() - 1.0f;
+        s = q1 * q1 + q2 * q2;
+    }
+    const float sq = std::sqrt(1.0f - s);
+    F4 n{2.0f * q1 * sq, 2.0f * q2 * sq, 1.0f - 2.0f * s, 0.0f};
+    const F4 vd = view_direction(cam, p, depth);
+    const float dp = n.x * vd.x + n.y * vd.y + n.z * vd.z;
+    if (dp > 0.0f) { n.x = -n.x; n.y = -n.y; n.z = -n.z; }
+    normalize3(&n);
+    return n;
+}
+
+inline F4 perturbed_normal(const orc_camera &cam, I2 p, F4 normal, Rng &rng, float perturbation) { /* APD.cu:270-305 */
+    const F4 vd = view_direction(cam, p, 1.0f);
+    const float a1 = (rng.uniform() - 0.5f) * perturbation;
+    const float a2 = (rng.uniform() - 0.5f) * perturbation;
+    const float a3 = (rng.uniform() - 0.5f) * perturbation;
+    const float s1 = std::sin(a1), s2 = std::sin(a2), s3 = std::sin(a3);
+    const float c1 = std::cos(a1), c2 = std::cos(a2), c3 = std::cos(a3);
+    float R[9];
+    R[0] = c2 * c3;
+    R[1] = c3 * s1 * s2 - c1 * s3;
+    R[2] = s1 * s3 + c1 * c3 * s2;
+    R[3] = c2 * s3;
+    R[4] = c1 * c3 + s1 * s2 * s3;
+    R[5] = c1 * s2 * s3 - c3 * s1;
+    R[6] = -s2;
+    R[7] = c2 * s1;
+    R[8] = c1 * c2;
+    F4 np;
+    np.x = R[0] * normal.x + R[1] * normal.y + R[2] * normal.z;
+    np.y = R[3] * normal.x + R[4] * normal.y + R[5] * normal.z;
+    np.z = R[6] * normal.x + R[7] * normal.y + R[8] * normal.z;
+    np.w = 0.0f; /* Mat33DotVec3 leaves w untouched (uninitialised in the reference); callers overwrite it */
+    if (np.x * vd.x + np.y * vd.y + np.z * vd.z >= 0.0f) np = normal;
+    normalize3(&np);
+    return np;
+}
+
+inline F4 random_plane(const orc_camera &cam, I2 p, Rng &rng, float dmin, float dmax) { /* APD.cu:307-313 */
+    const float depth = rng.uniform() * (dmax - dmin) + dmin;
+    F4 pl = random_normal(cam, p, rng, depth);
+    pl.w = distance_to_origin(cam, p, depth, pl);
+    return pl;
+}
+
+inline F4 normal_to_world(const orc_camera &cam, F4 pl) { /* TransformNormal APD.cu:405-413 */
+    F4 r;
+    r.x = cam.R[0] * pl.x + cam.R[3] * pl.y + cam.R[6] * pl.z;
+    r.y = cam.R[1] * pl.x + cam.R[4] * pl.y + cam.R[7] * pl.z;
+    r.z = cam.R[2] * pl.x + cam.R[5] * pl.y + cam.R[8] * pl.z;
+    r.w = pl.w;
+    return r;
+}
+
+inline F4 normal_to_refcam(const orc_camera &cam, F4 pl) { /* TransformNormal2RefCam APD.cu:415-423 */
+    F4 r;
+    r.x = cam.R[0] * pl.x + cam.R[1] * pl.y + cam.R[2] * pl.z;
+    r.y = cam.R[3] * pl.x + cam.R[4] * pl.y + cam.R[5] * pl.z;
+    r.z = cam.R[6] * pl.x + cam.R[7] * pl.y + cam.R[8] * pl.z;
+    r.w = pl.w;
+    return r;
+}
+
+/* APD.cu:334-394 */
+void homography(const orc_camera &rc, const orc_camera &sc, F4 pl, float *H) {
+    float ref_C[3], src_C[3];
+    ref_C[0] = -(rc.R[0] * rc.t[0] + rc.R[3] * rc.t[1] + rc.R[6] * rc.t[2]);
+    ref_C[1] = -(rc.R[1] * rc.t[0] + rc.R[4] * rc.t[1] + rc.R[7] * rc.t[2]);
+    ref_C[2] = -(rc.R[2] * rc.t[0] + rc.R[5] * rc.t[1] + rc.R[8] * rc.t[2]);
+    src_C[0] = -(sc.R[0] * sc.t[0] + sc.R[3] * sc.t[1] + sc.R[6] * sc.t[2]);
+    src_C[1] = -(sc.R[1] * sc.t[0] + sc.R[4] * sc.t[1] + sc.R[7] * sc.t[2]);
+    src_C[2] = -(sc.R[2] * sc.t[0] + sc.R[5] * sc.t[1] + sc.R[8] * sc.t[2]);
+    float Rr[9], Cr[3], tr[3];
+    Rr[0] = sc.R[0] * rc.R[0] + sc.R[1] * rc.R[1] + sc.R[2] * rc.R[2];
+    Rr[1] = sc.R[0] * rc.R[3] + sc.R[1] * rc.R[4] + sc.R[2] * rc.R[5];
+    Rr[2] = sc.R[0] * rc.R[6] + sc.R[1] * rc.R[7] + sc.R[2] * rc.R[8];
+    Rr[3] = sc.R[3] * rc.R[0] + sc.R[4] * rc.R[1] + sc.R[5] * rc.R[2];
+    Rr[4] = sc.R[3] * rc.R[3] + sc.R[4] * rc.R[4] + sc.R[5] * rc.R[5];
+    Rr[5] = sc.R[3] * rc.R[6] + sc.R[4] * rc.R[7] + sc.R[5] * rc.R[8];
+    Rr[6] = sc.R[6] * rc.R[0] + sc.R[7] * rc.R[1] + sc.R[8] * rc.R[2];
+    Rr[7] = sc.R[6] * rc.R[3] + sc.R[7] * rc.R[4] + sc.R[8] * rc.R[5];
+    Rr[8] = sc.R[6] * rc.R[6] + sc.R[7] * rc.R[7] + sc.R[8] * rc.R[8];
+    Cr[0] = ref_C[0] - src_C[0];
+    Cr[1] = ref_C[1] - src_C[1];
+    Cr[2] = ref_C[2] - src_C[2];
+    tr[0] = sc.R[0] * Cr[0] + sc.R[1] * Cr[1] + sc.R[2] * Cr[2];
+    tr[1] = sc.R[3] * Cr[0] + sc.R[4] * Cr[1] + sc.R[5] * Cr[2];
+    tr[2] = sc.R[6] * Cr[0] + sc.R[7] * Cr[1] + sc.R[8] * Cr[2];
+
+    H[0] = Rr[0] - tr[0] * pl.x / pl.w;
+    H[1] = Rr[1] - tr[0] * pl.y / pl.w;
+    H[2] = Rr[2] - tr[0] * pl.z / pl.w;
+    H[3] = Rr[3] - tr[1] * pl.x / pl.w;
+    H[4] = Rr[4] - tr[1] * pl.y / pl.w;
+    H[5] = Rr[5] - tr[1] * pl.z / pl.w;
+    H[6] = Rr[6] - tr[2] * pl.x / pl.w;
+    H[7] = Rr[7] - tr[2] * pl.y / pl.w;
+    H[8] = Rr[8] - tr[2] * pl.z / pl.w;
+
+    float tmp[9];
+    tmp[0] = H[0] / rc.K[0];
+    tmp[1] = H[1] / rc.K[4];
+    tmp[2] = -H[0] * rc.K[2] / rc.K[0] - H[1] * rc.K[5] / rc.K[4] + H[2];
+    tmp[3] = H[3] / rc.K[0];
+    tmp[4] = H[4] / rc.K[4];
+    tmp[5] = -H[3] * rc.K[2] / rc.K[0] - H[4] * rc.K[5] / rc.K[4] + H[5];
+    tmp[6] = H[6] / rc.K[0];
+    tmp[7] = H[7] / rc.K[4];
+    tmp[8] = -H[6] * rc.K[2] / rc.K[0] - H[7] * rc.K[5] / rc.K[4] + H[8];
+
+    H[0] = sc.K[0] * tmp[0] + sc.K[2] * tmp[6];
+    H[1] = sc.K[0] * tmp[1] + sc.K[2] * tmp[7];
+    H[2] = sc.K[0] * tmp[2] + sc.K[2] * tmp[8];
+    H[3] = sc.K[4] * tmp[3] + sc.K[5] * tmp[6];
+    H[4] = sc.K[4] * tmp[4] + sc.K[5] * tmp[7];
+    H[5] = sc.K[4] * tmp[5] + sc.K[5] * tmp[8];
+    H[6] = sc.K[8] * tmp[6];
+    H[7] = sc.K[8] * tmp[7];
+    H[8] = sc.K[8] * tmp[8];
+}
+
+inline F2 corresponding_point(const float *H, int px, int py) { /* APD.cu:396-403 */
+    const float x = H[0] * px + H[1] * py + H[2];
+    const float y = H[3] * px + H[4] * py + H[5];
+    const float z = H[6] * px + H[7] * py + H[8];
+    return F2{x / z, y / z};
+}
+
+inline F4 load4(const float *p, size_t i) { return F4{p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]}; }
+inline void store4(float *p, size_t i, F4 v) { p[4 * i] = v.x; p[4 * i + 1] = v.y; p[4 * i + 2] = v.z; p[4 * i + 3] = v.w; }
+inline S2 load_s2(const int16_t *p, size_t i) { return S2{p[2 * i], p[2 * i + 1]}; }
+inline void store_s2(int16_t *p, size_t i, S2 v) { p[2 * i] = v.x; p[2 * i + 1] = v.y; }
+
+inline void count(orc_problem *pb, int which) {
+#pragma omp atomic
+    pb->counters[which]++;
+}
+
+/* NCC of one patch around (cx, cy) with the given radius/increment (shared by Old and New).  APD.cu:622-662 */
+inline float patch_ncc(const orc_problem *pb, const float *H, int src_idx, int cx, int cy, int radius, int increment) {
+    const int W = pb->width, Hh = pb->height;
+    const float *ref = pb->images[0];
+    const float *src = pb->images[src_idx];
+    float sum_ref = 0.0f, sum_ref_ref = 0.0f, sum_src = 0.0f, sum_src_src = 0.0f, sum_ref_src = 0.0f, wsum = 0.0f;
+    for (int i = -radius; i <= radius; i += increment) {
+        for (int j = -radius; j <= radius; j += increment) {
+            const int rx = cx + i, ry = cy + j;
+            const float ref_pix = tex_point(ref, W, Hh, rx, ry);
+            const F2 sp = corresponding_point(H, rx, ry);
+            const float src_pix = tex_linear(src, W, Hh, sp.x + 0.5f, sp.y + 0.5f, pb->tex_mode);
+            const float weight = 1.0f; /* quirk 1: "bilateral" weight == 1 (APD.cu:534,635) */
+            sum_ref += weight * ref_pix;
+            sum_ref_ref += weight * ref_pix * ref_pix;
+            sum_src += weight * src_pix;
+            sum_src_src += weight * src_pix * src_pix;
+            sum_ref_src += weight * ref_pix * src_pix;
+            wsum += weight;
+        }
+    }
+    if (wsum == 0.0f) return -1.0f; /* only reachable in NCC-New with SAM masks; never here */
+    const float inv = 1.0f / wsum;
+    sum_ref *= inv; sum_ref_ref *= inv; sum_src *= inv; sum_src_src *= inv; sum_ref_src *= inv;
+    const float var_ref = sum_ref_ref - sum_ref * sum_ref;
+    const float var_src = sum_src_src - sum_src * sum_src;
+    const float kMinVar = 1e-5f;
+    if (var_ref < kMinVar || var_src < kMinVar) return 2.0f;
+    const float covar = sum_ref_src - sum_ref * sum_src;
+    const float denom = std::sqrt(var_ref * var_src);
+    /* max(0, min(2, v)) with CUDA fminf/fmaxf NaN semantics (quirk 10): NaN -> 2 */
+    const float v = 1.0f - covar / denom;
+    return std::fmax(0.0f, std::fmin(2.0f, v));
+}
+
+/* APD.cu:596-663 (branch A only; sa_mask == 0) */
+float ncc_old(orc_problem *pb, I2 p, int src_idx, F4 plane) {
+    count(pb, 0);
+    const orc_camera &rc = pb->cameras[0];
+    const orc_camera &sc = pb->cameras[src_idx];
+    float H[9];
+    homography(rc, sc, plane, H);
+    const F2 pt = corresponding_point(H, p.x, p.y);
+    if (pt.x >= sc.width || pt.x < 0.0f || pt.y >= sc.height || pt.y < 0.0f) return 2.0f;
+    return patch_ncc(pb, H, src_idx, p.x, p.y, pb->params.strong_radius, pb->params.strong_increment);
+}
+
+inline void softmax(float *c, int n) { /* APD.cu:431-446 */
+    float mx = -1e10f;
+    for (int i = 0; i < n; i++) if (c[i] > mx) mx = c[i];
+    float sum = 0.0f;
+    for (int i = 0; i < n; i++) { c[i] = std::exp(c[i] - mx); sum += c[i]; }
+    for (int i = 0; i < n; i++) c[i] /= sum;
+}
+
+/* APD.cu:448-593 (sa_mask == 0) */
+float ncc_new(orc_problem *pb, I2 p, int src_idx, F4 plane) {
+    count(pb, 1);
+    const orc_camera &rc = pb->cameras[0];
+    const orc_camera &sc = pb->cameras[src_idx];
+    const int W = pb->width, Hh = pb->height;
+    const size_t center = p.x + (size_t)p.y * W;
+    const float cost_max = 2.0f;
+    float H[9];
+    homography(rc, sc, plane, H);
+    const F2 pt = corresponding_point(H, p.x, p.y);
+    if (pt.x >= sc.width || pt.x < 0.0f || pt.y >= sc.height || pt.y < 0.0f) return cost_max;
+    float cost = 0.0f;
+    float strong_costs[9];
+    int strong_num = 0;
+    if (pb->weak_info[center] != ORC_WEAK) return cost; /* reference prints "error" and returns 0 (APD.cu:590) */
+    float center_cost = 0.0f, strong_weight = 0.0f;
+    for (int k = 0; k < ORC_ANCHOR_NUM; ++k) {
+        const S2 a = load_s2(pb->anchors, center * ORC_ANCHOR_NUM + k);
+        if (a.x == -1 || a.y == -1) continue;
+        const F2 asp = corresponding_point(H, a.x, a.y);
+        if (asp.x < 0 || asp.y < 0 || asp.x >= W || asp.y >= Hh) {
+            if (k != 0) {
+                const uint32_t vi = pb->selected_views[a.x + (size_t)a.y * W];
+                if (is_set(vi, src_idx - 1)) { strong_costs[strong_num++] = cost_max; strong_weight += 1; }
+                continue;
+            } else {
+                return cost_max;
+            }
+        }
+        const int radius = (k == 0 ? pb->params.strong_radius : pb->params.weak_radius);
+        const int increment = (k == 0 ? pb->params.strong_increment : pb->params.weak_increment);
+        const float tc = patch_ncc(pb, H, src_idx, a.x, a.y, radius, increment);
+        if (k == 0) center_cost = tc;
+        else { strong_costs[strong_num++] = tc; strong_weight += 1; }
+    }
+    if (strong_weight <= 1e-6f) {
+        cost = center_cost;
+    } else {
+        float wts[9];
+        for (int i = 0; i < strong_num; ++i) wts[i] = strong_costs[i];
+        softmax(wts, strong_num);
+        float strong_cost = 0.0f;
+        for (int i = 0; i < strong_num; ++i) strong_cost += wts[i] * strong_costs[i];
+        strong_cost = ORC_MIN(strong_cost, cost_max);
+        cost = (float)(0.25 * (double)center_cost + 0.75 * (double)strong_cost); /* double literals, APD.cu:586 */
+    }
+    return cost;
+}
+
+inline F3 point_on_world(float x, float y, float depth, const orc_camera &cam) { /* APD.cu:831-851 */
+    F3 X, T;
+    X.x = depth * (x - cam.K[2]) / cam.K[0];
+    X.y = depth * (y - cam.K[5]) / cam.K[4];
+    X.z = depth;
+    T.x = cam.R[0] * X.x + cam.R[3] * X.y + cam.R[6] * X.z;
+    T.y = cam.R[1] * X.x + cam.R[4] * X.y + cam.R[7] * X.z;
+    T.z = cam.R[2] * X.x + cam.R[5] * X.y + cam.R[8] * X.z;
+    X.x = T.x + cam.c[0];
+    X.y = T.y + cam.c[1];
+    X.z = T.z + cam.c[2];
+    return X;
+}
+
+inline void project_on_camera(F3 P, const orc_camera &cam, F2 &pt, float &depth) { /* APD.cu:853-863 */
+    F3 t;
+    t.x = cam.R[0] * P.x + cam.R[1] * P.y + cam.R[2] * P.z + cam.t[0];
+    t.y = cam.R[3] * P.x + cam.R[4] * P.y + cam.R[5] * P.z + cam.t[1];
+    t.z = cam.R[6] * P.x + cam.R[7] * P.y + cam.R[8] * P.z + cam.t[2];
+    depth = cam.K[6] * t.x + cam.K[7] * t.y + cam.K[8] * t.z;
+    pt.x = (cam.K[0] * t.x + cam.K[1] * t.y + cam.K[2] * t.z) / depth;
+    pt.y = (cam.K[3] * t.x + cam.K[4] * t.y + cam.K[5] * t.z) / depth;
+}
+
+/* nearest-texel depth fetch "(int)x + 0.5f" through a clamped linear texture (APD.cu:885, 2319) */
+inline float depth_fetch(const orc_problem *pb, int idx, F2 pt) {
+    const int ix = clampi(cuda_f2i(pt.x), 0, pb->width - 1);
+    const int iy = clampi(cuda_f2i(pt.y), 0, pb->height - 1);
+    return pb->depths[idx][iy * (size_t)pb->width + ix];
+}
+
+/* APD.cu:865-902 */
+float geom_cost(orc_problem *pb, I2 p, int src_idx, F4 plane) {
+    count(pb, 2);
+    const orc_camera &rc = pb->cameras[0];
+    const orc_camera &sc = pb->cameras[src_idx];
+    const float max_cost = 3.0f;
+    const float depth = depth_from_plane(rc, plane, p);
+    const F3 fwd = point_on_world((float)p.x, (float)p.y, depth, rc);
+    F2 sp; float sd;
+    project_on_camera(fwd, sc, sp, sd);
+    const float src_depth = depth_fetch(pb, src_idx, sp);
+    if (src_depth == 0.0f) return max_cost;
+    const F3 s3 = point_on_world(sp.x, sp.y, src_depth, sc);
+    F2 bp; float rd;
+    project_on_camera(s3, rc, bp, rd);
+    const float dc = p.x - bp.x, dr = p.y - bp.y;
+    const float cc = std::sqrt(dc * dc + dr * dr);
+    return std::fmin(max_cost, cc);
+}
+
+/* APD.cu:723-774 */
+float initial_cost_and_views(orc_problem *pb, I2 p) {
+    const orc_params &prm = pb->params;
+    const size_t center = p.x + (size_t)p.y * pb->width;
+    const F4 plane = load4(pb->planes, center);
+    const float cost_max = 2.0f;
+    float cv[32] = {2.0f};
+    float cvc[32] = {2.0f};
+    int cost_count = 0, num_valid = 0;
+    for (int i = 1; i < prm.num_images; ++i) {
+        float c;
+        if (prm.use_APD && pb->weak_info[center] == ORC_WEAK) c = ncc_new(pb, p, i, plane);
+        else c = ncc_old(pb, p, i, plane);
+        cv[i - 1] = c; cvc[i - 1] = c;
+        cost_count++;
+        if (c < cost_max) num_valid++;
+    }
+    sort_small(cv, cost_count);
+    uint32_t sel = 0;
+    const int top_k = std::min(num_valid, prm.top_k);
+    float ret = cost_max;
+    if (top_k > 0) {
+        float cost = 0.0f;
+        for (int i = 0; i < top_k; ++i) cost += cv[i];
+        const float thr = cv[top_k - 1];
+        for (int i = 0; i < prm.num_images - 1; ++i) if (cvc[i] <= thr) sel |= (1u << i);
+        ret = cost / top_k;
+    }
+    pb->selected_views[center] = sel;
+    return ret;
+}
+
+/* rows a half-grid launch covers (quirk 7, APD.cu:2676-2678) */
+inline int half_rows_limit(int H) { return 32 * (((H / 2) + 15) / 16); }
+/* Black <=> (x+y) even (APD.cu:1619-1626, 1656-1663) */
+inline bool is_color(int x, int y, int color) { return ((x + y) & 1) == color; }
+
+/* APD.cu:1127-1314: the 8 adaptive-checkerboard candidates */
+void checkerboard_candidates(const float *costs, int width, int height, I2 p, int positions[8], bool flag[8]) {
+    const int center = p.y * width + p.x;
+    for (int i = 0; i < 8; ++i) flag[i] = false;
+    float costMin; int costMinPoint;
+    int left_near = center - 1, left_far = center - 3, right_near = center + 1, right_far = center + 3;
+    int up_near = center - width, up_far = center - 3 * width, down_near = center + width, down_far = center + 3 * width;
+    if (p.y > 2) {
+        flag[1] = true; costMin = costs[up_far]; costMinPoint = up_far;
+        for (int i = 1; i < 11; ++i) if (p.y > 2 + 2 * i) {
+            int pt = up_far - 2 * i * width;
+            if (costs[pt] < costMin) { costMin = costs[pt]; costMinPoint = pt; }
+        }
+        up_far = costMinPoint;
+    }
+    if (p.y < height - 3) {
+        flag[3] = true; costMin = costs[down_far]; costMinPoint = down_far;
+        for (int i = 1; i < 11; ++i) if (p.y < height - 3 - 2 * i) {
+            int pt = down_far + 2 * i * width;
+            if (costs[pt] < costMin) { costMin = costs[pt]; costMinPoint = pt; }
+        }
+        down_far = costMinPoint;
+    }
+    if (p.x > 2) {
+        flag[5] = true; costMin = costs[left_far]; costMinPoint = left_far;
+        for (int i = 1; i < 11; ++i) if (p.x > 2 + 2 * i) {
+            int pt = left_far - 2 * i;
+            if (costs[pt] < costMin) { costMin = costs[pt]; costMinPoint = pt; }
+        }
+        left_far = costMinPoint;
+    }
+    if (p.x < width - 3) {
+        flag[7] = true; costMin = costs[right_far]; costMinPoint = right_far;
+        for (int i = 1; i < 11; ++i) if (p.x < width - 3 - 2 * i) {
+            int pt = right_far + 2 * i;
+            if (costs[pt] < costMin) { costMin = costs[pt]; costMinPoint = pt; }
+        }
+        right_far = costMinPoint;
+    }
+    if (p.y > 0) {
+        flag[0] = true; costMin = costs[up_near]; costMinPoint = up_near;
+        for (int i = 0; i < 3; ++i) {
+            if (p.y > 1 + i && p.x > i) {
+                int pt = up_near - (1 + i) * width - (i + 1);
+                if (costs[pt] < costMin) { costMin = costs[pt]; costMinPoint = pt; }
+            }
+            if (p.y > 1 + i && p.x < width - 1 - i) {
+                int pt = up_near - (1 + i) * width + (i + 1);
+                if (costs[pt] < costMin) { costMin = costs[pt]; costMinPoint = pt; }
+            }
+        }
+        up_near = costMinPoint;
+    }
+    if (p.y < height - 1) {
+        flag[2] = true; costMin = costs[down_near]; costMinPoint = down_near;
+        for (int i = 0; i < 3; ++i) {
+            if (p.y < height - 2 - i && p.x > i) {
+                int pt = down_near + (1 + i) * width - (i + 1);
+                if (costs[pt] < costMin) { costMin = costs[pt]; costMinPoint = pt; }
+            }
+            if (p.y < height - 2 - i && p.x < width - 1 - i) {
+                int pt = down_near + (1 + i) * width + (i + 1);
+                if (costs[pt] < costMin) { costMin = costs[pt]; costMinPoint = pt; }
+            }
+        }
+        down_near = costMinPoint;
+    }
+    if (p.x > 0) {
+        flag[4] = true; costMin = costs[left_near]; costMinPoint = left_near;
+        for (int i = 0; i < 3; ++i) {
+            if (p.x > 1 + i && p.y > i) {
+                int pt = left_near - (1 + i) - (i + 1) * width;
+                if (costs[pt] < costMin) { costMin = costs[pt]; costMinPoint = pt; }
+            }
+            if (p.x > 1 + i && p.y < height - 1 - i) {
+                int pt = left_near - (1 + i) + (i + 1) * width;
+                if (costs[pt] < costMin) { costMin = costs[pt]; costMinPoint = pt; }
+            }
+        }
+        left_near = costMinPoint;
+    }
+    if (p.x < width - 1) {
+        flag[6] = true; costMin = costs[right_near]; costMinPoint = right_near;
+        for (int i = 0; i < 3; ++i) {
+            if (p.x < width - 2 - i && p.y > i) {
+                int pt = right_near + (1 + i) - (i + 1) * width;
+                if (costs[pt] < costMin) { costMin = costs[pt]; costMinPoint = pt; }
+            }
+            if (p.x < width - 2 - i && p.y < height - 1 - i) {
+                int pt = right_near + (1 + i) + (i + 1) * width;
+                if (costs[pt] < costMin) { costMin = costs[pt]; costMinPoint = pt; }
+            }
+        }
+        right_near = costMinPoint;
+    }
+    const int pos[8] = {up_near, up_far, down_near, down_far, left_near, left_far, right_near, right_far};
+    for (int i = 0; i < 8; ++i) positions[i] = pos[i];
+}
+
+/* joint view selection shared by strong/weak propagation (APD.cu:1339-1386, 1505-1552) */
+void select_views(const orc_problem *pb, float cost_array[8][32], const float *priors, int iter, Rng &rng,
+                  uint8_t *view_weights, uint32_t *temp_selected, float *weight_norm) {
+    const int nv = pb->params.num_images - 1;
+    float sampling_probs[32] = {0.0f};
+    const float cost_threshold = (float)(0.8 * (double)std::exp((float)(iter * iter) / (-90.0f)));
+    for (int i = 0; i < nv; i++) {
+        float cnt = 0; int cnt_false = 0; float tmpw = 0;
+        for (int j = 0; j < 8; j++) {
+            if (cost_array[j][i] < cost_threshold) {
+                tmpw += std::exp(cost_array[j][i] * cost_array[j][i] / (-0.18f));
+                cnt++;
+            }
+            if (cost_array[j][i] > 1.2f) cnt_false++;
+        }
+        if (cnt > 2 && cnt_false < 3) sampling_probs[i] = tmpw / cnt;
+        else if (cnt_false < 3) sampling_probs[i] = std::exp(cost_threshold * cost_threshold / (-0.32f));
+        sampling_probs[i] = sampling_probs[i] * priors[i];
+    }
+    pdf_to_cdf(sampling_probs, nv);
+    for (int s = 0; s < 15; ++s) {
+        const float r = rng.uniform() - FLT_EPSILON;
+        for (int v = 0; v < nv; ++v) {
+            if (sampling_probs[v] > r) { view_weights[v] += 1; break; }
+        }
+    }
+    uint32_t sel = 0; float wn = 0;
+    for (int i = 0; i < nv; ++i) if (view_weights[i] > 0) { sel |= (1u << i); wn += view_weights[i]; }
+    *temp_selected = sel; *weight_norm = wn;
+}
+
+/* APD.cu:950-1006 */
+void refine_strong(orc_problem *pb, F4 *plane, float *depth, float *cost, Rng &rng, const uint8_t *vw,
+                   float weight_norm, I2 p) {
+    const orc_camera &cam = pb->cameras[0];
+    const orc_params &prm = pb->params;
+    const float depth_perturbation = 0.02f, normal_perturbation = 0.02f;
+    const float dmin = prm.depth_min, dmax = prm.depth_max;
+    const float depth_rand = rng.uniform() * (dmax - dmin) + dmin;
+    const F4 n_rand = random_normal(cam, p, rng, *depth);
+    float depth_pert = *depth;
+    const float lo = (1 - depth_perturbation) * depth_pert, hi = (1 + depth_perturbation) * depth_pert;
+    depth_pert = rng.uniform() * (hi - lo) + lo; /* do-while can never repeat (quirk 6) */
+    const F4 n_pert = perturbed_normal(cam, p, *plane, rng, (float)((double)normal_perturbation * kPiD));
+    const float depths[5] = {depth_rand, *depth, depth_rand, *depth, depth_pert};
+    const F4 normals[5] = {*plane, n_rand, n_rand, n_pert, *plane};
+    for (int i = 0; i < 5; ++i) {
+        F4 tp = normals[i];
+        tp.w = distance_to_origin(cam, p, depths[i], tp);
+        float cvv[32] = {2.0f};
+        for (int v = 1; v < prm.num_images; ++v) cvv[v - 1] = ncc_old(pb, p, v, tp);
+        float tc = 0.0f;
+        for (int j = 0; j < prm.num_images - 1; ++j) {
+            if (prm.geom_consistency && prm.use_impetus)
+                tc += vw[j] * (cvv[j] + prm.geom_factor * geom_cost(pb, p, j + 1, tp));
+            else
+                tc += vw[j] * cvv[j];
+        }
+        tc /= weight_norm;
+        const float db = depth_from_plane(cam, tp, p);
+        if (db >= dmin && db <= dmax && tc < *cost) { *depth = db; *plane = tp; *cost = tc; }
+    }
+}
+
+/* APD.cu:1098-1440 */
+void propagate_strong_pixel(orc_problem *pb, I2 p, int iter) {
+    const int width = pb->width, height = pb->height;
+    const orc_params &prm = pb->params;
+    const orc_camera &cam = pb->cameras[0];
+    const int nv = prm.num_images - 1;
+    const int center = p.y * width + p.x;
+    float cost_array[8][32];
+    std::memset(cost_array, 0, sizeof(cost_array));
+    cost_array[0][0] = 2.0f; /* quirk 2: "= {2.0f}" sets only [0][0] */
+    bool flag[8]; int positions[8];
+    checkerboard_candidates(pb->costs, width, height, p, positions, flag);
+    /* evaluation order of the reference: 1,3,5,7,0,2,4,6 -- order is irrelevant for the values */
+    for (int k = 0; k < 8; ++k) if (flag[k]) {
+        const F4 pl = load4(pb->planes, positions[k]);
+        for (int v = 1; v < prm.num_images; ++v) cost_array[k][v - 1] = ncc_old(pb, p, v, pl);
+    }
+    uint8_t *vw = &pb->view_weight[(size_t)center * ORC_MAX_IMAGES];
+    for (int i = 0; i < ORC_MAX_IMAGES; ++i) vw[i] = 0;
+    float priors[32] = {0.0f};
+    const int nbr[4] = {center - width, center + width, center - 1, center + 1};
+    for (int i = 0; i < 4; ++i) if (flag[2 * i]) {
+        for (int j = 0; j < nv; ++j) {
+            if (is_set(pb->selected_views[nbr[i]], j) == 1) priors[j] += 0.9f;
+            else priors[j] += 0.1f;
+        }
+    }
+    Rng rng(pb->seed, pb->stream, (uint32_t)center, SITE_STRONG + iter);
+    uint32_t temp_sel; float weight_norm;
+    select_views(pb, cost_array, priors, iter, rng, vw, &temp_sel, &weight_norm);
+
+    float final_costs[8] = {0.0f};
+    for (int i = 0; i < 8; ++i) {
+        for (int j = 0; j < nv; ++j) if (vw[j] > 0) final_costs[i] += vw[j] * cost_array[i][j];
+        final_costs[i] /= weight_norm;
+    }
+    const int min_idx = find_min_cost_index(final_costs, 8);
+
+    const F4 plane_c = load4(pb->planes, center);
+    float cvn[32] = {2.0f};
+    for (int v = 1; v < prm.num_images; ++v) cvn[v - 1] = ncc_old(pb, p, v, plane_c);
+    float cost_now = 0.0f;
+    for (int i = 0; i < nv; ++i) {
+        if (prm.geom_consistency && prm.use_impetus)
+            cost_now += vw[i] * (cvn[i] + prm.geom_factor * geom_cost(pb, p, i + 1, plane_c));
+        else
+            cost_now += vw[i] * cvn[i];
+    }
+    cost_now /= weight_norm;
+    pb->costs[center] = cost_now;
+    float depth_now = depth_from_plane(cam, plane_c, p);
+    F4 plane_now = plane_c;
+    if (flag[min_idx]) {
+        const F4 cand = load4(pb->planes, positions[min_idx]);
+        const float db = depth_from_plane(cam, cand, p);
+        if (db >= prm.depth_min && db <= prm.depth_max && final_costs[min_idx] < cost_now) {
+            depth_now = db; plane_now = cand; cost_now = final_costs[min_idx];
+            pb->selected_views[center] = temp_sel;
+        }
+    }
+    refine_strong(pb, &plane_now, &depth_now, &cost_now, rng, vw, weight_norm, p);
+    if (prm.state == ORC_REFINE_INIT) {
+        if ((double)cost_now < (double)pb->costs[center] - 0.1) { /* double literal, APD.cu:1431 */
+            pb->costs[center] = cost_now; store4(pb->planes, center, plane_now);
+        }
+    } else {
+        pb->costs[center] = cost_now; store4(pb->planes, center, plane_now);
+    }
+}
+
+/* APD.cu:1008-1096 */
+void refine_weak(orc_problem *pb, F4 *plane, float *depth, float *cost, Rng &rng, const uint8_t *vw,
+                 float weight_norm, I2 p) {
+    const orc_camera &cam = pb->cameras[0];
+    const orc_params &prm = pb->params;
+    const float depth_perturbation = 0.02f, normal_perturbation = 0.02f;
+    const float dmin = prm.depth_min, dmax = prm.depth_max;
+    const size_t center = p.x + (size_t)p.y * pb->width;
+    {
+        const F4 fit = load4(pb->fit_planes, center);
+        if (fit.x == 0 && fit.y == 0 && fit.z == 0) return;
+        float cvv[32] = {2.0f};
+        for (int v = 1; v < prm.num_images; ++v) cvv[v - 1] = ncc_new(pb, p, v, fit);
+        float tc = 0.0f;
+        for (int j = 0; j < prm.num_images - 1; ++j) if (vw[j] > 0) {
+            if (prm.geom_consistency) tc += vw[j] * (cvv[j] + prm.geom_factor * geom_cost(pb, p, j + 1, fit));
+            else tc += vw[j] * cvv[j];
+        }
+        tc /= weight_norm;
+        const float db = depth_from_plane(cam, fit, p);
+        if (db >= dmin && db <= dmax && tc < *cost) { *depth = db; *plane = fit; *cost = tc; }
+    }
+    const float depth_rand = rng.uniform() * (dmax - dmin) + dmin;
+    const F4 n_rand = random_normal(cam, p, rng, *depth);
+    float depth_pert = *depth;
+    const float lo = (1 - depth_perturbation) * depth_pert, hi = (1 + depth_perturbation) * depth_pert;
+    depth_pert = rng.uniform() * (hi - lo) + lo;
+    const F4 n_pert = perturbed_normal(cam, p, *plane, rng, (float)((double)normal_perturbation * kPiD));
+    const float depths[5] = {depth_rand, *depth, depth_rand, *depth, depth_pert};
+    const F4 normals[5] = {*plane, n_rand, n_rand, n_pert, *plane};
+    for (int i = 0; i < 5; ++i) {
+        F4 tp = normals[i];
+        tp.w = distance_to_origin(cam, p, depths[i], tp);
+        float cvv[32] = {2.0f};
+        for (int v = 1; v < prm.num_images; ++v) cvv[v - 1] = ncc_new(pb, p, v, tp);
+        float tc = 0.0f;
+        for (int j = 0; j < prm.num_images - 1; ++j) if (vw[j] > 0) {
+            if (prm.geom_consistency) tc += vw[j] * (cvv[j] + prm.geom_factor * geom_cost(pb, p, j + 1, tp));
+            else tc += vw[j] * cvv[j];
+        }
+        tc /= weight_norm;
+        const float db = depth_from_plane(cam, tp, p);
+        if (db >= dmin && db <= dmax && tc < *cost) { *depth = db; *plane = tp; *cost = tc; }
+    }
+}
+
+/* APD.cu:1442-1615 */
+void propagate_weak_pixel(orc_problem *pb, I2 p, int iter) {
+    const int width = pb->width;
+    const orc_params &prm = pb->params;
+    const orc_camera &cam = pb->cameras[0];
+    const int nv = prm.num_images - 1;
+    const size_t center = p.y * (size_t)width + p.x;
+    float cost_array[8][32];
+    std::memset(cost_array, 0, sizeof(cost_array));
+    cost_array[0][0] = 2.0f;
+    bool flag[8]; size_t positions[8] = {0}; F4 new_planes[8];
+    for (int i = 0; i < 8; ++i) {
+        const S2 a = load_s2(pb->anchors, center * ORC_ANCHOR_NUM + i + 1);
+        if (a.x == -1 || a.y == -1 || pb->weak_info[a.x + (size_t)a.y * width] != ORC_STRONG) { flag[i] = false; continue; }
+        positions[i] = a.x + (size_t)a.y * width;
+        flag[i] = true;
+        new_planes[i] = load4(pb->planes, positions[i]);
+        for (int v = 1; v < prm.num_images; ++v) cost_array[i][v - 1] = ncc_new(pb, p, v, new_planes[i]);
+    }
+    uint8_t *vw = &pb->view_weight[center * ORC_MAX_IMAGES];
+    for (int i = 0; i < ORC_MAX_IMAGES; ++i) vw[i] = 0;
+    float priors[32] = {0.0f};
+    for (int i = 0; i < 8; ++i) {
+        const S2 a = load_s2(pb->anchors, center * ORC_ANCHOR_NUM + i + 1);
+        if (a.x == -1 || a.y == -1) continue;
+        for (int j = 0; j < nv; ++j) {
+            if (is_set(pb->selected_views[a.x + (size_t)a.y * width], j) == 1) priors[j] += 0.9f;
+            else priors[j] += 0.1f;
+        }
+    }
+    Rng rng(pb->seed, pb->stream, (uint32_t)center, SITE_WEAK + iter);
+    uint32_t temp_sel; float weight_norm;
+    select_views(pb, cost_array, priors, iter, rng, vw, &temp_sel, &weight_norm);
+
+    float final_costs[8] = {0.0f};
+    for (int i = 0; i < 8; ++i) {
+        for (int j = 0; j < nv; ++j) if (vw[j] > 0) {
+            if (prm.geom_consistency) {
+                if (flag[i]) final_costs[i] += vw[j] * (cost_array[i][j] + prm.geom_factor * geom_cost(pb, p, j + 1, load4(pb->planes, positions[i])));
+                else final_costs[i] += vw[j] * (cost_array[i][j] + prm.geom_factor * 3.0f);
+            } else {
+                final_costs[i] += vw[j] * cost_array[i][j];
+            }
+        }
+        final_costs[i] /= weight_norm;
+    }
+    const int min_idx = find_min_cost_index(final_costs, 8);
+    const F4 plane_c = load4(pb->planes, center);
+    float cvn[32] = {2.0f};
+    for (int v = 1; v < prm.num_images; ++v) cvn[v - 1] = ncc_new(pb, p, v, plane_c);
+    float cost_now = 0.0f;
+    for (int i = 0; i < nv; ++i) {
+        if (prm.geom_consistency) cost_now += vw[i] * (cvn[i] + prm.geom_factor * geom_cost(pb, p, i + 1, plane_c));
+        else cost_now += vw[i] * cvn[i];
+    }
+    cost_now /= weight_norm;
+    pb->costs[center] = cost_now;
+    float depth_now = depth_from_plane(cam, plane_c, p);
+    F4 plane_now = plane_c;
+    if (flag[min_idx]) {
+        const float db = depth_from_plane(cam, new_planes[min_idx], p);
+        if (db >= prm.depth_min && db <= prm.depth_max && final_costs[min_idx] < cost_now) {
+            depth_now = db; plane_now = new_planes[min_idx]; cost_now = final_costs[min_idx];
+            pb->selected_views[center] = temp_sel;
+        }
+    }
+    refine_weak(pb, &plane_now, &depth_now, &cost_now, rng, vw, weight_norm, p);
+    if (prm.state == ORC_REFINE_INIT) {
+        if ((double)cost_now < (double)pb->costs[center] - 0.1) { pb->costs[center] = cost_now; store4(pb->planes, center, plane_now); }
+    } else {
+        pb->costs[center] = cost_now; store4(pb->planes, center, plane_now);
+    }
+}
+
+/* APD.cu:1711-1821 */
+void median_pixel(orc_problem *pb, I2 p) {
+    const int width = pb->width, height = pb->height;
+    const int center = p.y * width + p.x;
+    float *pl = pb->planes;
+    const uint8_t *wk = pb->weak_info;
+    float filter[21]; int index = 0;
+    filter[index++] = pl[4 * center + 3];
+    const int left = center - 1, leftleft = center - 3, up = center - width, upup = center - 3 * width;
+    const int down = center + width, downdown = center + 3 * width, right = center + 1, rightright = center + 3;
+    if (pb->costs[center] < 0.001f) return;
+#define TAP(cond, idx) if ((cond) && wk[(idx)] == ORC_STRONG) filter[index++] = pl[4 * (idx) + 3];
+    TAP(p.y > 0, up)
+    TAP(p.y > 2, upup)
+    TAP(p.y > 4, upup - width * 2)
+    TAP(p.y < height - 1, down)
+    TAP(p.y < height - 3, downdown)
+    TAP(p.y < height - 5, downdown + width * 2)
+    TAP(p.x > 0, left)
+    TAP(p.x > 2, leftleft)
+    TAP(p.x > 4, leftleft - 2)
+    TAP(p.x < width - 1, right)
+    TAP(p.x < width - 3, rightright)
+    TAP(p.x < width - 5, rightright + 2)
+    TAP(p.y > 0 && p.x < width - 2, up + 2)
+    TAP(p.y < height - 1 && p.x < width - 2, down + 2)
+    TAP(p.y > 0 && p.x > 1, up - 2)
+    TAP(p.y < height - 1 && p.x > 1, down - 2)
+    TAP(p.x > 0 && p.y > 2, left - width * 2)
+    TAP(p.x < width - 1 && p.y > 2, right - width * 2)
+    TAP(p.x > 0 && p.y < height - 2, left + width * 2)
+    TAP(p.x < width - 1 && p.y < height - 2, right + width * 2)
+#undef TAP
+    sort_small(filter, index);
+    const int m = index / 2;
+    if (index % 2 == 0) pl[4 * center + 3] = (filter[m - 1] + filter[m]) / 2;
+    else pl[4 * center + 3] = filter[m];
+}
+
+inline float baseline_len(const orc_camera &a, const orc_camera &b) { /* APD.cu:2142-2147 */
+    const float d0 = a.c[0] - b.c[0], d1 = a.c[1] - b.c[1], d2 = a.c[2] - b.c[2];
+    const float t = d0 * d0 + d1 * d1 + d2 * d2;
+    return std::sqrt(t);
+}
+
+bool point_in_triangle(S2 A, S2 B, S2 C, I2 P) { /* APD.cu:122-143 */
+    const F2 AB{(float)(B.x - A.x), (float)(B.y - A.y)};
+    const F2 BC{(float)(C.x - B.x), (float)(C.y - B.y)};
+    const F2 CA{(float)(A.x - C.x), (float)(A.y - C.y)};
+    const float ab = std::sqrt(AB.x * AB.x + AB.y * AB.y);
+    const float bc = std::sqrt(BC.x * BC.x + BC.y * BC.y);
+    const float ca = std::sqrt(CA.x * CA.x + CA.y * CA.y);
+    if (ab <= 2 || bc <= 2 || ca <= 2) return false;
+    if (!(ab + bc > ca && bc + ca > ab && ab + ca > bc)) return false;
+    const F2 PA{(float)(A.x - P.x), (float)(A.y - P.y)};
+    const F2 PB{(float)(B.x - P.x), (float)(B.y - P.y)};
+    const F2 PC{(float)(C.x - P.x), (float)(C.y - P.y)};
+    const float t1 = PA.x * PB.y - PA.y * PB.x;
+    const float t2 = PB.x * PC.y - PB.y * PC.x;
+    const float t3 = PC.x * PA.y - PC.y * PA.x;
+    return t1 * t2 >= 0 && t1 * t3 >= 0;
+}
+
+void sort_small_weighted(S2 *pts, float *w, int n) { /* APD.cu:25-38 */
+    int j;
+    for (int i = 1; i < n; i++) {
+        S2 tmp = pts[i]; float tw = w[i];
+        for (j = i; j >= 1 && tw < w[j - 1]; j--) { pts[j] = pts[j - 1]; w[j] = w[j - 1]; }
+        pts[j] = tmp; w[j] = tw;
+    }
+}
+
+/* "(curand() % 2 == 0 ? 1 : -1) * curand() % shift_range" (APD.cu:1921): int * unsigned -> unsigned arithmetic */
+inline int rand_shift(Rng &rng, int shift_range) {
+    const int sgn = (rng.next() % 2 == 0 ? 1 : -1);
+    const uint32_t r = rng.next();
+    const uint32_t prod = (uint32_t)sgn * r;
+    return (int)(prod % (uint32_t)shift_range);
+}
+
+int set_threads(const orc_problem *pb) {
+    int n = pb->num_threads > 0 ? pb->num_threads : 1;
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#endif
+    return n;
+}
+
+}  // namespace
+
+/* ================================================================================================
+ * extern "C" API
+ * ============================================================================================== */
+extern "C" {
+
+void orc_philox(uint32_t seed, uint32_t stream, uint32_t pixel, uint32_t site, uint32_t block, uint32_t out[4]) {
+    out[0] = pixel; out[1] = site; out[2] = block; out[3] = 0;
+    philox4x32_10(out, seed, stream);
+}
+
+void orc_homography(const orc_camera *ref, const orc_camera *src, const float plane[4], float H[9]) {
+    homography(*ref, *src, F4{plane[0], plane[1], plane[2], plane[3]}, H);
+}
+
+float orc_tex2d(const float *img, int w, int h, float x, float y, int tex_mode) {
+    return tex_linear(img, w, h, x, y, tex_mode);
+}
+
+float orc_ncc_old(orc_problem *pb, int x, int y, int src_idx, const float plane[4]) {
+    return ncc_old(pb, I2{x, y}, src_idx, F4{plane[0], plane[1], plane[2], plane[3]});
+}
+float orc_ncc_new(orc_problem *pb, int x, int y, int src_idx, const float plane[4]) {
+    return ncc_new(pb, I2{x, y}, src_idx, F4{plane[0], plane[1], plane[2], plane[3]});
+}
+float orc_geom_cost(orc_problem *pb, int x, int y, int src_idx, const float plane[4]) {
+    return geom_cost(pb, I2{x, y}, src_idx, F4{plane[0], plane[1], plane[2], plane[3]});
+}
+
+void orc_eval_costs(orc_problem *pb, int n, const int32_t *tuples, const float *planes, int mode, float *out) {
+    set_threads(pb);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < n; ++i) {
+        const I2 p{tuples[3 * i], tuples[3 * i + 1]};
+        const int v = tuples[3 * i + 2];
+        const F4 pl = load4(planes, i);
+        out[i] = mode == 0 ? ncc_old(pb, p, v, pl) : (mode == 1 ? ncc_new(pb, p, v, pl) : geom_cost(pb, p, v, pl));
+    }
+}
+
+void orc_checkerboard_candidates(const float *costs, int w, int h, int x, int y, int32_t positions[8], uint8_t flags[8]) {
+    bool f[8]; int pos[8];
+    checkerboard_candidates(costs, w, h, I2{x, y}, pos, f);
+    for (int i = 0; i < 8; ++i) { positions[i] = pos[i]; flags[i] = f[i] ? 1 : 0; }
+}
+
+/* K5: APD.cu:919-948 */
+void orc_random_init(orc_problem *pb) {
+    set_threads(pb);
+    const int W = pb->width, H = pb->height;
+    const orc_camera &cam = pb->cameras[0];
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+        const I2 p{x, y};
+        const size_t center = (size_t)y * W + x;
+        if (pb->params.state == ORC_FIRST_INIT) {
+            Rng rng(pb->seed, pb->stream, (uint32_t)center, SITE_INIT);
+            store4(pb->planes, center, random_plane(cam, p, rng, pb->params.depth_min, pb->params.depth_max));
+        } else {
+            F4 pl = load4(pb->planes, center);
+            pl = normal_to_refcam(cam, pl);
+            const float depth = pl.w;
+            pl.w = distance_to_origin(cam, p, depth, pl);
+            store4(pb->planes, center, pl);
+        }
+        pb->costs[center] = initial_cost_and_views(pb, p);
+    }
+}
+
+/* K6: APD.cu:1654-1692 */
+void orc_propagate_strong(orc_problem *pb, int iter, int color) {
+    set_threads(pb);
+    const int W = pb->width, H = pb->height;
+    const int ylim = std::min(H, half_rows_limit(H));
+#pragma omp parallel for schedule(dynamic, 2)
+    for (int y = 0; y < ylim; ++y) for (int x = 0; x < W; ++x) {
+        if (!is_color(x, y, color)) continue;
+        if (pb->weak_info[(size_t)y * W + x] == ORC_WEAK) continue;
+        propagate_strong_pixel(pb, I2{x, y}, iter);
+    }
+}
+
+/* K8: APD.cu:1617-1652 */
+void orc_propagate_weak(orc_problem *pb, int iter, int color) {
+    set_threads(pb);
+    const int W = pb->width, H = pb->height;
+    const int ylim = std::min(H, half_rows_limit(H));
+#pragma omp parallel for schedule(dynamic, 2)
+    for (int y = 0; y < ylim; ++y) for (int x = 0; x < W; ++x) {
+        if (!is_color(x, y, color)) continue;
+        if (pb->weak_info[(size_t)y * W + x] != ORC_WEAK) continue;
+        propagate_weak_pixel(pb, I2{x, y}, iter);
+    }
+}
+
+/* K9: APD.cu:1694-1709 */
+void orc_depth_normal(orc_problem *pb) {
+    const int W = pb->width, H = pb->height;
+    const orc_camera &cam = pb->cameras[0];
+    for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+        const size_t c = (size_t)y * W + x;
+        F4 pl = load4(pb->planes, c);
+        pl.w = depth_from_plane(cam, pl, I2{x, y});
+        store4(pb->planes, c, normal_to_world(cam, pl));
+    }
+}
+
+/* K10: APD.cu:1823-1855 */
+void orc_median_filter(orc_problem *pb, int color) {
+    const int W = pb->width, H = pb->height;
+    const int ylim = std::min(H, half_rows_limit(H));
+    for (int y = 0; y < ylim; ++y) for (int x = 0; x < W; ++x) {
+        if (!is_color(x, y, color)) continue;
+        if (pb->weak_info[(size_t)y * W + x] != ORC_WEAK) median_pixel(pb, I2{x, y});
+    }
+}
+
+/* K11: APD.cu:2103-2250 */
+void orc_depth_to_weak(orc_problem *pb, float *curve) {
+    set_threads(pb);
+    const int W = pb->width, H = pb->height;
+    const orc_params &prm = pb->params;
+    const orc_camera *cams = pb->cameras;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+        const I2 pt{x, y};
+        const int min_margin = 6;
+        const size_t center = (size_t)y * W + x;
+        if (x < min_margin || y < min_margin || x >= W - min_margin || y >= H - min_margin) { pb->weak_info[center] = ORC_UNKNOWN; continue; }
+        const uint8_t *vw = &pb->view_weight[ORC_MAX_IMAGES * center];
+        F4 opl = normal_to_refcam(cams[0], load4(pb->planes, center));
+        const float origin_depth = opl.w;
+        if (origin_depth == 0) { pb->weak_info[center] = ORC_UNKNOWN; continue; }
+        float base_line = 0; int valid_src = 0; float weight_normal = 0.0f;
+        const uint32_t sel = pb->selected_views[center];
+        for (int s = 1; s < prm.num_images; ++s) if (is_set(sel, s - 1)) {
+            weight_normal += vw[s - 1];
+            base_line += baseline_len(cams[0], cams[s]);
+            valid_src++;
+        }
+        if (valid_src == 0) { pb->weak_info[center] = ORC_UNKNOWN; continue; }
+        base_line /= valid_src;
+        const float disp = cams[0].K[0] * base_line / origin_depth;
+        const int radius = 30, n = 2 * radius + 1;
+        float pc[61];
+        for (int pd = -radius; pd <= radius; ++pd) {
+            const float p_depth = cams[0].K[0] * base_line / (disp + pd);
+            if (p_depth < prm.depth_min || p_depth > prm.depth_max) { pc[pd + radius] = 2.0f; continue; }
+            F4 tp = opl;
+            tp.w = distance_to_origin(cams[0], pt, p_depth, tp);
+            float p_cost = 0.0f;
+            for (int s = 1; s < prm.num_images; ++s) {
+                float tc = 0.0f;
+                if (is_set(sel, s - 1)) {
+                    tc += ncc_old(pb, pt, s, tp);
+                    if (prm.geom_consistency) tc += prm.geom_factor * geom_cost(pb, pt, s, tp);
+                    p_cost += (tc * vw[s - 1]);
+                }
+            }
+            p_cost /= weight_normal;
+            pc[pd + radius] = ORC_MIN(2.0f, p_cost);
+        }
+        if (curve) for (int i = 0; i < n; ++i) curve[center * n + i] = pc[i];
+        bool is_peak[61];
+        for (int i = 0; i < n; ++i) is_peak[i] = false;
+        int peak_count = 0, min_peak = 0; float min_cost = 2.0f;
+        for (int i = 2; i < n - 2; ++i) {
+            if (pc[i - 1] > pc[i] && pc[i + 1] > pc[i]) {
+                is_peak[i] = true; peak_count++;
+                if (pc[i] < min_cost) { min_peak = i; min_cost = pc[i]; }
+            }
+        }
+        if (std::abs(min_peak - radius) > prm.weak_peak_radius || pc[min_peak] > 0.5f) { pb->weak_info[center] = ORC_WEAK; continue; }
+        if (peak_count == 1) { pb->weak_info[center] = (pc[min_peak] <= 0.15f) ? ORC_STRONG : ORC_WEAK; continue; }
+        float var = 0.0f;
+        for (int i = 2; i < n - 2; ++i) if (is_peak[i] && i != min_peak) { const float d = pc[i] - min_cost; var += d * d; }
+        var = std::sqrt(var);
+        var /= (peak_count - 1);
+        pb->weak_info[center] = (var > 0.2f) ? ORC_STRONG : ORC_WEAK;
+    }
+}
+
+/* K12: APD.cu:2282-2344 */
+void orc_confidence(orc_problem *pb) {
+    const int W = pb->width, H = pb->height;
+    const orc_camera &rc = pb->cameras[0];
+    for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+        const size_t center = (size_t)y * W + x;
+        pb->confidence[center] = 0;
+        const uint32_t sel = pb->selected_views[center];
+        const float ref_depth = pb->planes[4 * center + 3];
+        if (ref_depth <= 0.0f) { pb->weak_info[center] = ORC_UNKNOWN; continue; }
+        const F3 fwd = point_on_world((float)x, (float)y, ref_depth, rc);
+        int nc = 1;
+        for (int i = 0; i < pb->params.num_images - 1; ++i) {
+            if (!is_set(sel, i)) continue;
+            const int s = i + 1;
+            const orc_camera &sc = pb->cameras[s];
+            F2 sp; float sd;
+            project_on_camera(fwd, sc, sp, sd);
+            const float src_depth = depth_fetch(pb, s, sp);
+            if (src_depth <= 0.0f) continue;
+            nc += 1;
+            const F3 s3 = point_on_world(sp.x, sp.y, src_depth, sc);
+            F2 bp; float rd;
+            project_on_camera(s3, rc, bp, rd);
+            const float dc = x - bp.x, dr = y - bp.y;
+            const float pd = std::sqrt(dc * dc + dr * dr);
+            if (pd <= 2.0f) nc += 2;
+            const float rdd = std::fabs(ref_depth - rd) / ref_depth;
+            if (rdd <= 0.02f) nc += 2;
+        }
+        if (nc > 255) nc = 255;
+        pb->confidence[center] = (uint8_t)nc;
+    }
+}
+
+/* K13: APD.cu:2346-2432 */
+void orc_local_refine(orc_problem *pb) {
+    set_threads(pb);
+    const int W = pb->width, H = pb->height;
+    const orc_params &prm = pb->params;
+    const orc_camera *cams = pb->cameras;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+        const I2 pt{x, y};
+        const size_t center = (size_t)y * W + x;
+        const uint8_t *vw = &pb->view_weight[ORC_MAX_IMAGES * center];
+        F4 opl = normal_to_refcam(cams[0], load4(pb->planes, center));
+        const float origin_depth = opl.w;
+        if (origin_depth == 0) continue;
+        const uint32_t sel = pb->selected_views[center];
+        float cost_now = 0.0f, base_line = 0; int valid_src = 0; float weight_normal = 0.0f;
+        for (int s = 1; s < prm.num_images; ++s) if (is_set(sel, s - 1)) {
+            F4 tp = opl;
+            tp.w = distance_to_origin(cams[0], pt, origin_depth, tp);
+            float tc = ncc_old(pb, pt, s, tp);
+            if (prm.geom_consistency) tc += prm.geom_factor * geom_cost(pb, pt, s, tp);
+            cost_now += (tc * vw[s - 1]);
+            weight_normal += vw[s - 1];
+            base_line += baseline_len(cams[0], cams[s]);
+            valid_src++;
+        }
+        if (weight_normal == 0 || valid_src == 0) continue;
+        cost_now /= weight_normal;
+        base_line /= valid_src;
+        const float disp = cams[0].K[0] * base_line / origin_depth;
+        const int radius = 5;
+        float min_cost = 2.0f, best_depth = origin_depth;
+        for (int pd = -radius; pd <= radius; ++pd) {
+            const float p_depth = cams[0].K[0] * base_line / (disp + pd);
+            if (p_depth < prm.depth_min || p_depth > prm.depth_max) continue;
+            F4 tp = opl;
+            tp.w = distance_to_origin(cams[0], pt, p_depth, tp);
+            float tc = 0.0f;
+            for (int s = 1; s < prm.num_images; ++s) if (is_set(sel, s - 1)) {
+                tc += (ncc_old(pb, pt, s, tp) * vw[s - 1]);
+                if (prm.geom_consistency) tc += (prm.geom_factor * geom_cost(pb, pt, s, tp) * vw[s - 1]);
+            }
+            tc /= weight_normal;
+            if (tc < min_cost) { min_cost = tc; best_depth = p_depth; }
+        }
+        if ((double)(cost_now - min_cost) > 0.1) pb->planes[4 * center + 3] = best_depth;
+    }
+}
+
+/* K2: APD.cu:2434-2484 */
+void orc_nearest_strong(orc_problem *pb) {
+    set_threads(pb);
+    const int W = pb->width, H = pb->height;
+    const uint8_t *wk = pb->weak_info, *cf = pb->confidence;
+#pragma omp parallel for schedule(dynamic, 2)
+    for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+        const size_t center = (size_t)y * W + x;
+        S2 out{-1, -1};
+        const uint8_t cc = cf[center];
+        if (wk[center] == ORC_WEAK || wk[center] == ORC_UNKNOWN) {
+            uint8_t best_conf = 0; S2 best{-1, -1}; float min_dist = FLT_MAX;
+            const int radius = 100;
+            for (int dx = -radius; dx <= radius; ++dx) for (int dy = -radius; dy <= radius; ++dy) {
+                const int tx = x + dx, ty = y + dy;
+                if (tx < 0 || tx >= W || ty < 0 || ty >= H) continue;
+                const size_t tc = (size_t)ty * W + tx;
+                if (wk[tc] != ORC_STRONG) continue;
+                if (cf[tc] < cc) continue;
+                const float d = std::sqrt((float)(dx * dx + dy * dy));
+                if (d < min_dist) { min_dist = d; best = S2{(int16_t)tx, (int16_t)ty}; best_conf = cf[tc]; }
+                else if (d == min_dist) { if (cf[tc] > best_conf) { best = S2{(int16_t)tx, (int16_t)ty}; best_conf = cf[tc]; } }
+            }
+            out = best;
+        } else if (wk[center] == ORC_STRONG) {
+            out = S2{(int16_t)x, (int16_t)y};
+        }
+        store_s2(pb->nearest_strong, center, out);
+    }
+}
+
+/* K3: APD.cu:1857-2082 */
+void orc_gen_anchors(orc_problem *pb) {
+    set_threads(pb);
+    const int width = pb->width, height = pb->height;
+    const orc_params &prm = pb->params;
+    const orc_camera &camera = pb->cameras[0];
+#pragma omp parallel for schedule(dynamic, 2)
+    for (int y = 0; y < height; ++y) for (int x = 0; x < width; ++x) {
+        const I2 point{x, y};
+        const size_t center = (size_t)y * width + x;
+        if (pb->weak_info[center] != ORC_WEAK) continue;
+        const int min_margin = 6;
+        const float depth_diff = prm.depth_max - prm.depth_min;
+        Rng rng(pb->seed, pb->stream, (uint32_t)center, SITE_ANCHOR);
+        int16_t *anchors = &pb->anchors[center * ORC_ANCHOR_NUM * 2];
+        for (int i = 0; i < ORC_ANCHOR_NUM; ++i) { anchors[2 * i] = -1; anchors[2 * i + 1] = -1; }
+        anchors[0] = (int16_t)x; anchors[1] = (int16_t)y;
+        S2 strong_points[32]; bool dir_valid[32];
+        for (int i = 0; i < 32; ++i) { strong_points[i] = S2{-1, -1}; dir_valid[i] = false; }
+        int origin_direction_index = -1, strong_point_size = 0;
+        const int rotate_time = prm.rotate_time;
+        const float angle = 45.0f / rotate_time;
+        const float cos_angle = (float)std::cos((double)angle * kPiD / (double)180.f);
+        const float sin_angle = (float)std::sin((double)angle * kPiD / (double)180.f);
+        const float threshhold = (float)std::cos((double)(angle / 2.0f) * kPiD / 180.0);
+        const int shift_range = ORC_MAX((int)(std::tan((double)(angle / 2.0f) * kPiD / 180.0) * 20), 1);
+        const float ransac_threshold = prm.ransac_threshold;
+        for (int odx = -1; odx <= 1; ++odx) for (int ody = -1; ody <= 1; ++ody) {
+            if (odx == 0 && ody == 0) continue;
+            F2 od{(float)odx, (float)ody};
+            normalize2(&od);
+            origin_direction_index++;
+            for (int rot = 0; rot < rotate_time; ++rot) {
+                const int dir_index = origin_direction_index * 4 + rot;
+                for (int radius = 2; radius <= 4096; radius = ORC_MIN(radius * 2, radius + 25)) {
+                    const F2 test_pt{point.x + od.x * radius, point.y + od.y * radius};
+                    if (test_pt.x < 0 || test_pt.y < 0 || test_pt.x >= width || test_pt.y >= height) break;
+                    for (int ri = 0; ri < 4; ++ri) {
+                        const int rxs = rand_shift(rng, shift_range);
+                        const int rys = rand_shift(rng, shift_range);
+                        F2 dir{od.x * 20 + rxs, od.y * 20 + rys};
+                        normalize2(&dir);
+                        S2 ap{(int16_t)(int)(point.x + dir.x * radius), (int16_t)(int)(point.y + dir.y * radius)};
+                        if (ap.x < min_margin || ap.y < min_margin || ap.x >= width - min_margin || ap.y >= height - min_margin) continue;
+                        ap = load_s2(pb->nearest_strong, ap.x + (size_t)ap.y * width);
+                        if (ap.x == -1 || ap.y == -1) continue;
+                        F2 td{(float)(ap.x - point.x), (float)(ap.y - point.y)};
+                        normalize2(&td);
+                        const float ca = td.x * od.x + td.y * od.y;
+                        if (ca > threshhold) { strong_points[dir_index] = ap; dir_valid[dir_index] = true; strong_point_size++; break; }
+                    }
+                    if (dir_valid[dir_index]) break;
+                }
+                F2 rd{od.x * cos_angle - od.y * sin_angle, od.x * sin_angle + od.y * cos_angle};
+                normalize2(&rd);
+                od = rd;
+            }
+        }
+        if (strong_point_size <= 3) { pb->weak_reliable[center] = 0; continue; }
+        F4 best_plane{0, 0, 0, 0};
+        int ua = -1, ub = -1, uc = -1; bool has_valid = false;
+        S2 spv[32]; F3 spv3[32]; int valid_count = 0; float X[3];
+        get_3d_point(camera, (float)point.x, (float)point.y, pb->planes[4 * center + 3], X);
+        const F3 cpw{X[0], X[1], X[2]};
+        for (int i = 0; i < 32; ++i) {
+            spv[i] = S2{-1, -1};
+            if (dir_valid[i]) {
+                const S2 sp = strong_points[i];
+                const size_t spc = sp.x + (size_t)sp.y * width;
+                spv[valid_count] = sp;
+                get_3d_point(camera, (float)sp.x, (float)sp.y, pb->planes[4 * spc + 3], X);
+                spv3[valid_count] = F3{X[0], X[1], X[2]};
+                valid_count++;
+            }
+        }
+        {
+            int iteration = 50; float min_cost = FLT_MAX; int max_count = 3;
+            while (iteration--) {
+                const int a = rng.next() % valid_count, b = rng.next() % valid_count, c = rng.next() % valid_count;
+                if (a == b || b == c || a == c) continue;
+                if (!point_in_triangle(spv[a], spv[b], spv[c], point)) continue;
+                const F3 &A = spv3[a], &B = spv3[b], &C = spv3[c];
+                const F3 AC{A.x - C.x, A.y - C.y, A.z - C.z}, BC{B.x - C.x, B.y - C.y, B.z - C.z};
+                F4 cv;
+                cv.x = AC.y * BC.z - BC.y * AC.z;
+                cv.y = -(AC.x * BC.z - BC.x * AC.z);
+                cv.z = AC.x * BC.y - BC.x * AC.y;
+                cv.w = 0;
+                if ((cv.x == 0 && cv.y == 0 && cv.z == 0) || std::isnan(cv.x) || std::isnan(cv.y) || std::isnan(cv.z)) continue;
+                normalize3(&cv);
+                cv.w = -(cv.x * A.x + cv.y * A.y + cv.z * A.z);
+                int tcnt = 0; float sdist = 0.0f;
+                for (int si = 0; si < valid_count; ++si) {
+                    const F3 &tp = spv3[si];
+                    const float d = std::fabs(cv.x * tp.x + cv.y * tp.y + cv.z * tp.z + cv.w);
+                    if (d / depth_diff < ransac_threshold) { tcnt++; sdist += d; }
+                }
+                if (tcnt < 6) continue;
+                const float cd = std::fabs(cv.x * cpw.x + cv.y * cpw.y + cv.z * cpw.z + cv.w);
+                if (tcnt > max_count) {
+                    max_count = tcnt; min_cost = cd; best_plane = cv; has_valid = true; ua = a; ub = b; uc = c;
+                } else if (tcnt == max_count) {
+                    if (cd < min_cost) { max_count = tcnt; min_cost = cd; best_plane = cv; ua = a; ub = b; uc = c; }
+                }
+            }
+        }
+        if (!has_valid) { pb->weak_reliable[center] = 0; continue; }
+        float weight[32];
+        for (int i = 0; i < valid_count; ++i) {
+            const F3 &tp = spv3[i];
+            float d = std::fabs(best_plane.x * tp.x + best_plane.y * tp.y + best_plane.z * tp.z + best_plane.w);
+            if (d / depth_diff >= ransac_threshold) { spv[i] = S2{-1, -1}; weight[i] = FLT_MAX; continue; }
+            if (i == ua || i == ub || i == uc) d -= 1;
+            weight[i] = d;
+        }
+        sort_small_weighted(spv, weight, valid_count);
+        /* strong_points_valid has 32 initialised slots; anchors 1..8 <- slots 0..7 (APD.cu:2075-2080) */
+        for (int i = 1; i < ORC_ANCHOR_NUM; ++i) { anchors[2 * i] = spv[i - 1].x; anchors[2 * i + 1] = spv[i - 1].y; }
+        pb->weak_reliable[center] = 1;
+    }
+}
+
+/* K4: APD.cu:2084-2100 */
+void orc_neighbour_update(orc_problem *pb) {
+    const size_t P = (size_t)pb->width * pb->height;
+    for (size_t c = 0; c < P; ++c)
+        if (pb->weak_info[c] == ORC_WEAK && pb->weak_reliable[c] != 1) pb->weak_info[c] = ORC_UNKNOWN;
+}
+
+/* K7: APD.cu:2486-2598 */
+void orc_ransac_fit(orc_problem *pb, int iter) {
+    set_threads(pb);
+    const int width = pb->width, height = pb->height;
+    const orc_camera &camera = pb->cameras[0];
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < height; ++y) for (int x = 0; x < width; ++x) {
+        const I2 point{x, y};
+        const size_t center = (size_t)y * width + x;
+        if (pb->weak_info[center] != ORC_WEAK) { store4(pb->fit_planes, center, load4(pb->planes, center)); continue; }
+        Rng rng(pb->seed, pb->stream, (uint32_t)center, SITE_FIT + iter);
+        S2 sp[8]; F3 sp3[8]; int sc = 0; float X[3];
+        for (int i = 1; i < ORC_ANCHOR_NUM; ++i) {
+            const S2 tp = load_s2(pb->anchors, center * ORC_ANCHOR_NUM + i);
+            if (tp.x == -1 || tp.y == -1) continue;
+            sp[sc] = tp;
+            const size_t tc = tp.x + (size_t)tp.y * width;
+            const float depth = depth_from_plane(camera, load4(pb->planes, tc), I2{tp.x, tp.y});
+            get_3d_point(camera, (float)tp.x, (float)tp.y, depth, X);
+            sp3[sc] = F3{X[0], X[1], X[2]};
+            sc++;
+        }
+        if (sc < 3) { store4(pb->fit_planes, center, load4(pb->planes, center)); continue; }
+        int iteration = 50; float min_cost = FLT_MAX; F4 best{0, 0, 0, 0}; bool has_best = false;
+        while (iteration--) {
+            const int a = rng.next() % sc, b = rng.next() % sc, c = rng.next() % sc;
+            if (a == b || b == c || a == c) continue;
+            if (!point_in_triangle(sp[a], sp[b], sp[c], point)) continue;
+            const F3 &A = sp3[a], &B = sp3[b], &C = sp3[c];
+            const F3 AC{A.x - C.x, A.y - C.y, A.z - C.z}, BC{B.x - C.x, B.y - C.y, B.z - C.z};
+            F4 cv;
+            cv.x = AC.y * BC.z - BC.y * AC.z;
+            cv.y = -(AC.x * BC.z - BC.x * AC.z);
+            cv.z = AC.x * BC.y - BC.x * AC.y;
+            cv.w = 0;
+            if ((cv.x == 0 && cv.y == 0 && cv.z == 0) || std::isnan(cv.x) || std::isnan(cv.y) || std::isnan(cv.z)) continue;
+            normalize3(&cv);
+            cv.w = -(cv.x * A.x + cv.y * A.y + cv.z * A.z);
+            float tcst = 0.0f;
+            for (int si = 0; si < sc; ++si) {
+                if (si == a || si == b || si == c) continue;
+                const F3 &tp = sp3[si];
+                tcst += std::fabs(cv.x * tp.x + cv.y * tp.y + cv.z * tp.z + cv.w);
+            }
+            if (tcst < min_cost) { min_cost = tcst; best = cv; has_best = true; }
+            if (min_cost == 0) break;
+        }
+        if (has_best) {
+            const float depth = depth_from_plane(camera, load4(pb->planes, center), point);
+            const F4 vd = view_direction(camera, point, depth);
+            const float dp = best.x * vd.x + best.y * vd.y + best.z * vd.z;
+            if (dp > 0) { best.x = -best.x; best.y = -best.y; best.z = -best.z; best.w = -best.w; }
+            store4(pb->fit_planes, center, best);
+        } else {
+            store4(pb->fit_planes, center, F4{0, 0, 0, 0});
+        }
+    }
+}
+
+/* APD::RunPatchMatch, APD.cu:2663-2737 */
+void orc_run_pass(orc_problem *pb) {
+    const orc_params &prm = pb->params;
+    if (prm.use_APD) { orc_nearest_strong(pb); orc_gen_anchors(pb); orc_neighbour_update(pb); }
+    orc_random_init(pb);
+    for (int i = 0; i < prm.max_iterations; ++i) {
+        orc_propagate_strong(pb, i, 0);
+        orc_propagate_strong(pb, i, 1);
+        if (prm.use_APD) { orc_ransac_fit(pb, i); orc_propagate_weak(pb, i, 0); orc_propagate_weak(pb, i, 1); }
+    }
+    orc_depth_normal(pb);
+    orc_median_filter(pb, 0);
+    orc_median_filter(pb, 1);
+    orc_depth_to_weak(pb, nullptr);
+    if (prm.geom_consistency || prm.use_APD) orc_confidence(pb);
+    orc_local_refine(pb);
+}
+
+/* ================================================================================================
+ * fusion (APD.cpp:844-910, 962-1227)
+ * ============================================================================================== */
+namespace {
+F3 f_point_on_world(int x, int y, float depth, const orc_camera &cam) { /* APD.cpp:866-889 */
+    F3 X, T;
+    X.x = depth * (x - cam.K[2]) / cam.K[0];
+    X.y = depth * (y - cam.K[5]) / cam.K[4];
+    X.z = depth;
+    T.x = cam.R[0] * X.x + cam.R[3] * X.y + cam.R[6] * X.z;
+    T.y = cam.R[1] * X.x + cam.R[4] * X.y + cam.R[7] * X.z;
+    T.z = cam.R[2] * X.x + cam.R[5] * X.y + cam.R[8] * X.z;
+    F3 C;
+    C.x = -(cam.R[0] * cam.t[0] + cam.R[3] * cam.t[1] + cam.R[6] * cam.t[2]);
+    C.y = -(cam.R[1] * cam.t[0] + cam.R[4] * cam.t[1] + cam.R[7] * cam.t[2]);
+    C.z = -(cam.R[2] * cam.t[0] + cam.R[5] * cam.t[1] + cam.R[8] * cam.t[2]);
+    return F3{T.x + C.x, T.y + C.y, T.z + C.z};
+}
+float f_angle(const float *a, const float *b) { /* APD.cpp:902-910; cv::norm is double */
+    const float dot = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+    const double na = std::sqrt((double)a[0] * a[0] + (double)a[1] * a[1] + (double)a[2] * a[2]);
+    const double nb = std::sqrt((double)b[0] * b[0] + (double)b[1] * b[1] + (double)b[2] * b[2]);
+    const float ang = std::acos((float)(dot / (na * nb)));
+    if (ang != ang) return 0.0f;
+    return ang;
+}
+/* confidences[..].at<float>(r, c) on a CV_8UC1 map (quirk 14, APD.cpp:1010-1011): 4 raw bytes at r*W + 4c;
+ * bytes past the end of the map read as 0 (the reference reads out of bounds there). */
+float conf_as_float(const uint8_t *conf, size_t P, int W, int r, int c) {
+    uint8_t b[4] = {0, 0, 0, 0};
+    const size_t off = (size_t)r * W + 4 * (size_t)c;
+    for (int i = 0; i < 4; ++i) if (off + i < P) b[i] = conf[off + i];
+    float f; std::memcpy(&f, b, 4);
+    return f;
+}
+}  // namespace
+
+/* APD.cpp:962-1049 */
+void orc_weak_vis_filter(const orc_fusion_input *in, uint8_t *skip) {
+    const int V = in->num_views, W = in->width, H = in->height;
+    const size_t P = (size_t)W * H;
+#ifdef _OPENMP
+    omp_set_num_threads(in->num_threads > 0 ? in->num_threads : 1);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int ref = 0; ref < V; ++ref) {
+        const orc_camera &rc = in->cameras[ref];
+        for (int r = 0; r < H; ++r) for (int c = 0; c < W; ++c) {
+            if (in->weaks[ref * P + (size_t)r * W + c] != ORC_WEAK) continue;
+            const float ref_depth = in->depths[ref * P + (size_t)r * W + c];
+            const F3 X = f_point_on_world(c, r, ref_depth, rc);
+            int so = 0, wo = 0;
+            for (int s = 0; s < V; ++s) {
+                if (s == ref) continue;
+                const orc_camera &sc = in->cameras[s];
+                const float a[3] = {rc.c[0] - X.x, rc.c[1] - X.y, rc.c[2] - X.z};
+                const float b[3] = {sc.c[0] - X.x, sc.c[1] - X.y, sc.c[2] - X.z};
+                float ang = f_angle(a, b);
+                ang = (float)((double)(ang * 180.0f) / kPiD);
+                if (ang > 80.0f) continue;
+                F2 pt; float pd;
+                project_on_camera(X, sc, pt, pd);
+                if (pd <= 0.0f) continue;
+                const int sr = (int)(pt.y + 0.5f), scn = (int)(pt.x + 0.5f);
+                if (scn >= 0 && scn < W && sr >= 0 && sr < H) {
+                    const float sd = in->depths[s * P + (size_t)sr * W + scn];
+                    const uint8_t wk = in->weaks[s * P + (size_t)sr * W + scn];
+                    if (wk == ORC_STRONG) {
+                        if (pd < sd - 0.01f * sd) so++;
+                    } else if (wk == ORC_WEAK) {
+                        if (conf_as_float(in->confidences + s * P, P, W, sr, scn) < conf_as_float(in->confidences + ref * P, P, W, r, c)) {
+                            if (pd < sd - 0.01f * sd) wo++;
+                        }
+                    }
+                }
+            }
+            if (so >= 2 || wo >= 4) skip[ref * P + (size_t)r * W + c] = 1;
+        }
+    }
+}
+
+/* APD.cpp:1140-1224 (greedy, order dependent) */
+int64_t orc_fuse(const orc_fusion_input *in, const uint8_t *skip, float *pts, float *cols, int64_t max_points) {
+    const int V = in->num_views, W = in->width, H = in->height;
+    const size_t P = (size_t)W * H;
+    std::vector<uint8_t> masks((size_t)V * P, 0);
+    int64_t n = 0;
+    for (int ref = 0; ref < V; ++ref) {
+        const int nb0 = in->src_offsets[ref], nb1 = in->src_offsets[ref + 1];
+        const int num_ngb = nb1 - nb0;
+        std::vector<I2> used(num_ngb);
+        for (int r = 0; r < H; ++r) for (int c = 0; c < W; ++c) {
+            const size_t px = (size_t)r * W + c;
+            if (masks[ref * P + px] == 1) continue;
+            if (skip && skip[ref * P + px] == 1) continue;
+            const float ref_depth = in->depths[ref * P + px];
+            if (ref_depth <= 0.0) continue;
+            const float *rn = &in->normals[(ref * P + px) * 3];
+            const F3 X = f_point_on_world(c, r, ref_depth, in->cameras[ref]);
+            int num_consistent = 0; float dyn = 0.0f;
+            for (int j = 0; j < num_ngb; ++j) used[j] = I2{-1, -1};
+            for (int j = 0; j < num_ngb; ++j) {
+                const int s = in->src_ids[nb0 + j];
+                F2 pt; float pd;
+                project_on_camera(X, in->cameras[s], pt, pd);
+                const int sr = (int)(pt.y + 0.5f), sc = (int)(pt.x + 0.5f);
+                if (sc >= 0 && sc < W && sr >= 0 && sr < H) {
+                    const size_t spx = (size_t)sr * W + sc;
+                    if (masks[s * P + spx] == 1) continue;
+                    const float sd = in->depths[s * P + spx];
+                    if (sd <= 0.0) continue;
+                    const float *sn = &in->normals[(s * P + spx) * 3];
+                    const F3 tX = f_point_on_world(sc, sr, sd, in->cameras[s]);
+                    F2 tp;
+                    project_on_camera(tX, in->cameras[ref], tp, pd);
+                    const float re = (float)std::sqrt(std::pow((double)(c - tp.x), 2) + std::pow((double)(r - tp.y), 2));
+                    const float rdd = std::fabs(pd - ref_depth) / ref_depth;
+                    const float ang = f_angle(rn, sn);
+                    if (re < 2.0f && rdd < 0.01f && ang < 0.174533f) {
+                        used[j] = I2{sc, sr};
+                        const float ti = re + 200 * rdd + ang * 10;
+                        dyn += (float)std::exp((double)-ti);
+                        num_consistent++;
+                    }
+                }
+            }
+            const float factor = (in->weaks[ref * P + px] == ORC_WEAK ? 0.45f : 0.3f);
+            if (num_consistent >= 1 && (dyn > factor * num_consistent)) {
+                float col[3] = {0, 0, 0};
+                if (in->colors) for (int k = 0; k < 3; ++k) col[k] = (float)in->colors[(ref * P + px) * 3 + k];
+                for (int j = 0; j < num_ngb; ++j) {
+                    if (used[j].x == -1) continue;
+                    const int s = in->src_ids[nb0 + j];
+                    const size_t spx = (size_t)used[j].y * W + used[j].x;
+                    masks[s * P + spx] = 1;
+                    if (in->colors) for (int k = 0; k < 3; ++k) col[k] += in->colors[(s * P + spx) * 3 + k];
+                }
+                for (int k = 0; k < 3; ++k) col[k] /= (num_consistent + 1);
+                if (n < max_points) {
+                    pts[3 * n] = X.x; pts[3 * n + 1] = X.y; pts[3 * n + 2] = X.z;
+                    if (cols) { cols[3 * n] = col[0]; cols[3 * n + 1] = col[1]; cols[3 * n + 2] = col[2]; }
+                }
+                n++;
+            }
+        }
+    }
+    return n;
+}
+
+}  // extern "C"
