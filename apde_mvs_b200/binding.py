@@ -127,6 +127,7 @@ def load_library(path=None):
     lib.apde_problem_finish.argtypes = [P]
     lib.apde_pass_run.argtypes = [P, C.c_int, C.POINTER(Params), C.c_int, C.c_uint32]
     lib.apde_eval_costs.argtypes = [P, C.c_int, P, P, C.c_int, P]
+    lib.apde_debug_tex2d.argtypes = [P, C.c_int, C.c_int, P, P]
     lib.apde_run_schedule.argtypes = [P, C.POINTER(Schedule), C.POINTER(Timing)]
     lib.apde_run_schedule_pass.argtypes = [P, C.POINTER(Schedule), C.c_int, C.POINTER(Timing)]
     lib.apde_schedule_num_passes.argtypes = [P, C.POINTER(Schedule)]
@@ -292,6 +293,12 @@ class Context:
         assert len(tuples) == len(planes)
         out = np.zeros(len(tuples), np.float32)
         self._check(self.lib.apde_eval_costs(self._h, len(tuples), _ptr(tuples), _ptr(planes), mode, _ptr(out)))
+        return out
+
+    def debug_tex2d(self, idx, xy):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        out = np.zeros(len(xy), np.float32)
+        self._check(self.lib.apde_debug_tex2d(self._h, idx, len(xy), _ptr(xy), _ptr(out)))
         return out
 
     # ---- schedule

@@ -667,6 +667,28 @@ int apde_eval_costs(apde_context *c, int n, const int32_t *tuples, const float *
     return APDE_OK;
 }
 
+__global__ void k_debug_tex(cudaTextureObject_t tex, int layer, int n, const float2 *xy, float *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = tex2DLayered<float>(tex, xy[i].x, xy[i].y, layer);
+}
+
+int apde_debug_tex2d(apde_context *c, int idx, int n, const float *xy, float *out) {
+    if (!c || !c->problem_active) return fail(APDE_ERR_STATE, "debug_tex2d: no active problem");
+    if (idx < 0 || idx > c->K.N || n <= 0 || !xy || !out) return fail(APDE_ERR_ARG, "debug_tex2d: bad argument");
+    CU(cudaSetDevice(c->device));
+    const int layer = (idx == 0) ? c->ref_view : c->views[c->ref_view].src[idx - 1];
+    float2 *d_xy; float *d_o;
+    CU(cudaMalloc(&d_xy, (size_t)n * 8));
+    CU(cudaMalloc(&d_o, (size_t)n * 4));
+    CU(cudaMemcpyAsync(d_xy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    k_debug_tex<<<(n + 255) / 256, 256, 0, c->stream>>>(c->level_tex, layer, n, d_xy, d_o);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_xy); cudaFree(d_o);
+    return APDE_OK;
+}
+
 int apde_get_counters(apde_context *c, uint64_t out[4], int reset) {
     if (!c || !out) return fail(APDE_ERR_ARG, "get_counters: null argument");
     CU(cudaSetDevice(c->device));

@@ -170,6 +170,10 @@ int apde_pass_run(apde_context *ctx, int ref_view, const apde_params *params, in
  * planes = float[n][4] (camera-frame normal, plane distance).  mode 0 = NCC-Old, 1 = NCC-New, 2 = geometric. */
 int apde_eval_costs(apde_context *ctx, int n, const int32_t *tuples, const float *planes, int mode, float *out);
 
+/* parity hook: tex2D<float>(image of source index idx, x, y) exactly as the kernels sample it (linear filter, clamp,
+ * unnormalised; texture set-up of APD.cpp:699-706).  xy = float[n][2]. */
+int apde_debug_tex2d(apde_context *ctx, int idx, int n, const float *xy, float *out);
+
 /* ---------------------------------------------------------------- whole schedule (main.cpp:303-367) */
 typedef struct {
     int rounds;          /* <= 0: ComputeRoundNum rule (halve max side until <= 800), main.cpp:129-146 */

@@ -1,0 +1,95 @@
+"""ctypes binding of oracle/_ref/libapd_ref.so = the reference's own APD.cu compiled as-is (TEST INFRASTRUCTURE;
+needs a GPU; built by `make -C oracle ref` where /root/reference is mounted, shipped to the GPU box prebuilt)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "_ref", "libapd_ref.so")
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB)
+        L.ref_eval_costs.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_run_pass.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_double)]
+        assert L.ref_sizeof_camera() == 120
+        _lib = L
+    return _lib
+
+
+def _params(p):
+    ip = np.array([p.max_iterations, p.num_images, p.top_k, p.geom_consistency, p.use_impetus, p.strong_radius,
+                   p.strong_increment, p.weak_radius, p.weak_increment, p.use_APD, p.use_sa, p.weak_peak_radius,
+                   p.rotate_time, p.state], np.int32)
+    fp = np.array([p.depth_min, p.depth_max, p.ransac_threshold, p.geom_factor], np.float32)
+    return ip, fp
+
+
+def _ptr_array(arrs):
+    if arrs is None:
+        return None, None
+    keep = [np.ascontiguousarray(a, np.float32) for a in arrs]
+    pa = (C.c_void_p * len(keep))(*[a.ctypes.data for a in keep])
+    return pa, keep
+
+
+def _cams(cameras):
+    buf = (C.c_char * (120 * len(cameras)))()
+    for i, cam in enumerate(cameras):
+        C.memmove(C.addressof(buf) + 120 * i, C.byref(cam), 120)
+    return buf
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def eval_costs(images, cameras, params, tuples, planes, mode=0, depths=None, weak=None, selected_views=None, anchors=None):
+    h, w = images[0].shape
+    n = len(images)
+    pi, keep_i = _ptr_array(images)
+    pd, keep_d = _ptr_array(depths)
+    ip, fp = _params(params)
+    ip[1] = n
+    tuples = np.ascontiguousarray(tuples, np.int32).reshape(-1, 3)
+    planes = np.ascontiguousarray(planes, np.float32).reshape(-1, 4)
+    out = np.zeros(len(tuples), np.float32)
+    weak = None if weak is None else np.ascontiguousarray(weak, np.uint8)
+    sel = None if selected_views is None else np.ascontiguousarray(selected_views, np.uint32)
+    anc = None if anchors is None else np.ascontiguousarray(anchors, np.int16)
+    cams = _cams(cameras)
+    rc = lib().ref_eval_costs(w, h, n, C.cast(pi, C.c_void_p), C.cast(pd, C.c_void_p) if pd else None, C.cast(cams, C.c_void_p),
+                              _p(ip), _p(fp), _p(weak), _p(sel), _p(anc), len(tuples), _p(tuples), _p(planes), mode, _p(out))
+    if rc != 0:
+        raise RuntimeError("ref_eval_costs failed: %d" % rc)
+    return out
+
+
+def run_pass(images, cameras, params, planes=None, weak=None, conf=None, depths=None, seed=1):
+    """returns (planes [h,w,4] world normal + depth, weak, conf, RunPatchMatch ms)"""
+    h, w = images[0].shape
+    n = len(images)
+    pi, keep_i = _ptr_array(images)
+    pd, keep_d = _ptr_array(depths)
+    ip, fp = _params(params)
+    ip[1] = n
+    planes = np.zeros((h, w, 4), np.float32) if planes is None else np.ascontiguousarray(planes, np.float32).copy()
+    weak = np.ones((h, w), np.uint8) if weak is None else np.ascontiguousarray(weak, np.uint8).copy()
+    conf = np.ones((h, w), np.uint8) if conf is None else np.ascontiguousarray(conf, np.uint8).copy()
+    ms = C.c_double()
+    cams = _cams(cameras)
+    rc = lib().ref_run_pass(w, h, n, C.cast(pi, C.c_void_p), C.cast(pd, C.c_void_p) if pd else None, C.cast(cams, C.c_void_p),
+                            _p(ip), _p(fp), _p(planes), _p(weak), _p(conf), seed, C.byref(ms))
+    if rc != 0:
+        raise RuntimeError("ref_run_pass failed: %d" % rc)
+    return planes, weak, conf, ms.value

@@ -1,0 +1,253 @@
+// ref_wrapper.cu -- TEST INFRASTRUCTURE: C-ABI entry points around the REFERENCE's own device code.
+//
+// This translation unit #includes /root/reference/APD.cu verbatim (path given with -I by oracle/Makefile; nothing of
+// the reference is copied into this repository) and adds
+//   * ref_eval_costs : calls the reference's ComputeBilateralNCCOld / ComputeBilateralNCCNew /
+//                      ComputeGeomConsistencyCost on caller-supplied (pixel, view, plane) tuples -- the pin for the
+//                      CPU oracle and for the B200 kernels;
+//   * ref_run_pass   : builds the reference APD object's device state from caller arrays and runs the reference's own
+//                      APD::RunPatchMatch() -- the GPU baseline of bench.py --impl reference and of the whole-pass
+//                      parity test.
+// The only deviation from the reference binary: clock64() in InitRandomStates (APD.cu:916) reads a settable seed so that
+// runs are repeatable (SURVEY.md 7.1 step 0 allows exactly this patch; it is done with a macro, not an edit).
+// The output lives in oracle/_ref/ (git-ignored) and only runs on the GPU box.
+#define private public
+#include "APD.h"
+#undef private
+
+__device__ long long g_ref_seed = 0x1234567LL;
+#define clock64() (g_ref_seed)
+#include "APD.cu"
+#undef clock64
+
+#include <cstdio>
+
+// ---- host symbols the reference's APD.cu expects from APD.cpp (not compiled here: it needs the real OpenCV)
+void CudaSafeCall(const cudaError_t error, const std::string &file, const int line) {
+    if (error != cudaSuccess) {
+        fprintf(stderr, "reference CUDA error %s at %s:%d\n", cudaGetErrorString(error), file.c_str(), line);
+        exit(EXIT_FAILURE);
+    }
+}
+void CudaCheckError(const char *file, const int line) { CudaSafeCall(cudaGetLastError(), file, line); }
+bool WriteBinMat(const path &, const cv::Mat &, bool) { return true; }
+bool ShowNormalMap(const path &, const cv::Mat &) { return true; }
+APD::APD(const Problem &problem_) { params_host = problem_.params; this->problem = problem_; }
+APD::~APD() {}
+
+namespace {
+
+struct RefState {
+    int w = 0, h = 0, n = 0;
+    cudaArray *img_arr[MAX_IMAGES] = {nullptr};
+    cudaArray *dep_arr[MAX_IMAGES] = {nullptr};
+    cudaTextureObjects tex_img_host, tex_dep_host;
+    cudaTextureObjects *tex_img = nullptr, *tex_dep = nullptr;
+    Camera *cams = nullptr;
+    PatchMatchParams *params = nullptr;
+    float4 *planes = nullptr, *fit = nullptr;
+    float *costs = nullptr;
+    curandState *rand_states = nullptr;
+    unsigned *sel = nullptr;
+    uchar *vw = nullptr, *weak = nullptr, *conf = nullptr, *sa = nullptr, *reliable = nullptr;
+    short2 *nearest = nullptr, *anchors = nullptr;
+    int *anchors_map = nullptr;
+    DataPassHelper helper_host, *helper = nullptr;
+    bool has_depth = false;
+};
+
+cudaTextureObject_t make_tex(cudaArray *arr) {  // same descriptor as APD.cpp:695-706
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = cudaAddressModeWrap;
+    td.addressMode[1] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    cudaTextureObject_t t = 0;
+    cudaCreateTextureObject(&t, &rd, &td, NULL);
+    return t;
+}
+
+void free_state(RefState &s) {
+    for (int i = 0; i < s.n; ++i) {
+        if (s.img_arr[i]) { cudaDestroyTextureObject(s.tex_img_host.images[i]); cudaFreeArray(s.img_arr[i]); }
+        if (s.dep_arr[i]) { cudaDestroyTextureObject(s.tex_dep_host.images[i]); cudaFreeArray(s.dep_arr[i]); }
+    }
+    cudaFree(s.tex_img); cudaFree(s.tex_dep); cudaFree(s.cams); cudaFree(s.params); cudaFree(s.planes); cudaFree(s.fit);
+    cudaFree(s.costs); cudaFree(s.rand_states); cudaFree(s.sel); cudaFree(s.vw); cudaFree(s.weak); cudaFree(s.conf);
+    cudaFree(s.sa); cudaFree(s.reliable); cudaFree(s.nearest); cudaFree(s.anchors); cudaFree(s.anchors_map); cudaFree(s.helper);
+}
+
+// the device-side part of CudaSpaceInitialization + SetDataPassHelperInCuda (APD.cpp:687-814), from caller arrays
+void build_state(RefState &s, int w, int h, int n, const float *const *images, const float *const *depths, const Camera *cams,
+                 const PatchMatchParams *params, const float *planes, const uchar *weak, const uchar *conf,
+                 const short *anchors_dense /* [P][9][2] or null */) {
+    s.w = w; s.h = h; s.n = n;
+    const size_t P = (size_t)w * h;
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+    for (int i = 0; i < n; ++i) {
+        cudaMallocArray(&s.img_arr[i], &cd, w, h);
+        cudaMemcpy2DToArray(s.img_arr[i], 0, 0, images[i], w * sizeof(float), w * sizeof(float), h, cudaMemcpyHostToDevice);
+        s.tex_img_host.images[i] = make_tex(s.img_arr[i]);
+    }
+    cudaMalloc(&s.tex_img, sizeof(cudaTextureObjects));
+    cudaMemcpy(s.tex_img, &s.tex_img_host, sizeof(cudaTextureObjects), cudaMemcpyHostToDevice);
+    s.has_depth = depths != nullptr;
+    if (depths) {
+        for (int i = 0; i < n; ++i) {
+            cudaMallocArray(&s.dep_arr[i], &cd, w, h);
+            cudaMemcpy2DToArray(s.dep_arr[i], 0, 0, depths[i], w * sizeof(float), w * sizeof(float), h, cudaMemcpyHostToDevice);
+            s.tex_dep_host.images[i] = make_tex(s.dep_arr[i]);
+        }
+        cudaMalloc(&s.tex_dep, sizeof(cudaTextureObjects));
+        cudaMemcpy(s.tex_dep, &s.tex_dep_host, sizeof(cudaTextureObjects), cudaMemcpyHostToDevice);
+    }
+    cudaMalloc(&s.cams, sizeof(Camera) * n);
+    cudaMemcpy(s.cams, cams, sizeof(Camera) * n, cudaMemcpyHostToDevice);
+    cudaMalloc(&s.params, sizeof(PatchMatchParams));
+    cudaMemcpy(s.params, params, sizeof(PatchMatchParams), cudaMemcpyHostToDevice);
+    cudaMalloc(&s.costs, P * sizeof(float));
+    cudaMalloc(&s.rand_states, P * sizeof(curandState));
+    cudaMalloc(&s.sel, P * sizeof(unsigned));
+    cudaMemset(s.sel, 0, P * sizeof(unsigned));
+    cudaMalloc(&s.vw, P * MAX_IMAGES);
+    cudaMemset(s.vw, 0, P * MAX_IMAGES);
+    cudaMalloc(&s.planes, P * sizeof(float4));
+    if (planes) cudaMemcpy(s.planes, planes, P * sizeof(float4), cudaMemcpyHostToDevice);
+    else cudaMemset(s.planes, 0, P * sizeof(float4));
+    cudaMalloc(&s.weak, P);
+    if (weak) cudaMemcpy(s.weak, weak, P, cudaMemcpyHostToDevice); else cudaMemset(s.weak, STRONG, P);
+    cudaMalloc(&s.conf, P);
+    if (conf) cudaMemcpy(s.conf, conf, P, cudaMemcpyHostToDevice); else cudaMemset(s.conf, 1, P);
+    cudaMalloc(&s.sa, P);
+    cudaMemset(s.sa, 0, P);  // SAM off: sa_mask_host = zeros (APD.cpp:613)
+    cudaMalloc(&s.fit, P * sizeof(float4));
+    cudaMemset(s.fit, 0, P * sizeof(float4));
+    cudaMalloc(&s.reliable, P);
+    cudaMemset(s.reliable, 0, P);
+    cudaMalloc(&s.nearest, P * sizeof(short2));
+    // anchors_map: running index of WEAK pixels (APD.cpp:627-640)
+    std::vector<int> amap(P, -1);
+    int weak_count = 0;
+    if (weak) for (size_t i = 0; i < P; ++i) if (weak[i] == WEAK) amap[i] = weak_count++;
+    cudaMalloc(&s.anchors_map, P * sizeof(int));
+    cudaMemcpy(s.anchors_map, amap.data(), P * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMalloc(&s.anchors, (size_t)(weak_count > 0 ? weak_count : 1) * ANCHOR_NUM * sizeof(short2));
+    if (anchors_dense && weak_count > 0) {
+        std::vector<short2> comp((size_t)weak_count * ANCHOR_NUM);
+        for (size_t i = 0; i < P; ++i) if (amap[i] >= 0)
+            for (int k = 0; k < ANCHOR_NUM; ++k)
+                comp[(size_t)amap[i] * ANCHOR_NUM + k] = make_short2(anchors_dense[(i * ANCHOR_NUM + k) * 2], anchors_dense[(i * ANCHOR_NUM + k) * 2 + 1]);
+        cudaMemcpy(s.anchors, comp.data(), comp.size() * sizeof(short2), cudaMemcpyHostToDevice);
+    }
+    DataPassHelper &hp = s.helper_host;
+    memset(&hp, 0, sizeof(hp));
+    hp.width = w; hp.height = h; hp.ref_index = 0;
+    hp.texture_objects_cuda = s.tex_img; hp.texture_depths_cuda = s.tex_dep; hp.cameras_cuda = s.cams;
+    hp.plane_hypotheses_cuda = s.planes; hp.rand_states_cuda = s.rand_states; hp.selected_views_cuda = s.sel;
+    hp.anchors_cuda = s.anchors; hp.anchors_map_cuda = s.anchors_map; hp.weak_info_cuda = s.weak;
+    hp.confidence_cuda = s.conf; hp.sa_mask_cuda = s.sa; hp.costs_cuda = s.costs; hp.params = s.params;
+    hp.debug_point = make_int2(DEBUG_POINT_X, DEBUG_POINT_Y);
+    hp.fit_plane_hypotheses_cuda = s.fit; hp.weak_reliable_cuda = s.reliable; hp.view_weight_cuda = s.vw;
+    hp.weak_nearest_strong = s.nearest;
+    cudaMalloc(&s.helper, sizeof(DataPassHelper));
+    cudaMemcpy(s.helper, &hp, sizeof(DataPassHelper), cudaMemcpyHostToDevice);
+}
+
+__global__ void ref_eval_kernel(DataPassHelper *helper, int n, const int *tuples, const float4 *planes, int mode, float *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 p = make_int2(tuples[3 * i], tuples[3 * i + 1]);
+    const int v = tuples[3 * i + 2];
+    float c;
+    if (mode == 0) c = ComputeBilateralNCCOld(p, v, planes[i], helper);
+    else if (mode == 1) c = ComputeBilateralNCCNew(p, v, planes[i], helper);
+    else c = ComputeGeomConsistencyCost(p, v, planes[i], helper);
+    out[i] = c;
+}
+
+PatchMatchParams to_ref_params(const int *ip, const float *fp) {
+    // ip: max_iterations, num_images, top_k, geom, impetus, strong_radius, strong_inc, weak_radius, weak_inc, use_APD,
+    //     use_sa, weak_peak_radius, rotate_time, state ; fp: depth_min, depth_max, ransac_threshold, geom_factor
+    PatchMatchParams p;
+    p.max_iterations = ip[0]; p.num_images = ip[1]; p.top_k = ip[2]; p.geom_consistency = ip[3] != 0; p.use_impetus = ip[4] != 0;
+    p.strong_radius = ip[5]; p.strong_increment = ip[6]; p.weak_radius = ip[7]; p.weak_increment = ip[8];
+    p.use_APD = ip[9] != 0; p.use_sa = ip[10] != 0; p.weak_peak_radius = ip[11]; p.rotate_time = ip[12]; p.state = (RunState)ip[13];
+    p.depth_min = fp[0]; p.depth_max = fp[1]; p.ransac_threshold = fp[2]; p.geom_factor = fp[3];
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ref_sizeof_camera() { return (int)sizeof(Camera); }
+
+// images / depths: arrays of n host pointers (depths may be null).  cams: n reference Camera structs (120 B each).
+int ref_eval_costs(int w, int h, int n_images, const float *const *images, const float *const *depths, const void *cams,
+                   const int *iparams, const float *fparams, const unsigned char *weak, const unsigned *selected_views,
+                   const short *anchors_dense, int n, const int *tuples, const float *planes, int mode, float *out) {
+    RefState s;
+    PatchMatchParams prm = to_ref_params(iparams, fparams);
+    build_state(s, w, h, n_images, images, depths, (const Camera *)cams, &prm, nullptr, weak, nullptr, anchors_dense);
+    if (selected_views) cudaMemcpy(s.sel, selected_views, (size_t)w * h * sizeof(unsigned), cudaMemcpyHostToDevice);
+    int *d_t; float4 *d_p; float *d_o;
+    cudaMalloc(&d_t, (size_t)n * 12); cudaMalloc(&d_p, (size_t)n * 16); cudaMalloc(&d_o, (size_t)n * 4);
+    cudaMemcpy(d_t, tuples, (size_t)n * 12, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_p, planes, (size_t)n * 16, cudaMemcpyHostToDevice);
+    ref_eval_kernel<<<(n + 127) / 128, 128>>>(s.helper, n, d_t, d_p, mode, d_o);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(out, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_t); cudaFree(d_p); cudaFree(d_o);
+    free_state(s);
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
+// One reference pass through the reference's own APD::RunPatchMatch().  planes: in (state != FIRST_INIT) / out float4[P]
+// as on disk (world normal, depth).  weak / conf: in (use_APD) / out.  kernel_ms: wall time of RunPatchMatch() exactly as
+// main.cpp:157-161 measures it (kernels + the final device->host copies).
+int ref_run_pass(int w, int h, int n_images, const float *const *images, const float *const *depths, const void *cams,
+                 const int *iparams, const float *fparams, float *planes, unsigned char *weak, unsigned char *conf,
+                 long long seed, double *kernel_ms) {
+    const size_t P = (size_t)w * h;
+    PatchMatchParams prm = to_ref_params(iparams, fparams);
+    Problem problem;
+    problem.ref_image_id = 0;
+    problem.params = prm;
+    problem.show_medium_result = false;
+    problem.export_anchor = false;
+    problem.export_reliable_curve = false;
+    problem.iteration = 0;
+    problem.used_time = 0;
+    APD apd(problem);
+    RefState s;
+    build_state(s, w, h, n_images, images, depths, (const Camera *)cams, &prm, planes, prm.use_APD ? weak : nullptr,
+                prm.use_APD ? conf : nullptr, nullptr);
+    cudaMemcpyToSymbol(g_ref_seed, &seed, sizeof(seed));
+    apd.num_images = n_images; apd.width = w; apd.height = h;
+    apd.params_host = prm;
+    apd.helper_cuda = s.helper;
+    apd.plane_hypotheses_cuda = s.planes; apd.weak_info_cuda = s.weak; apd.confidence_cuda = s.conf;
+    apd.plane_hypotheses_host.reset(new float4[P]);
+    apd.weak_info_host = cv::Mat(h, w, CV_8UC1);
+    apd.confidence_host = cv::Mat(h, w, CV_8UC1);
+    apd.weak_count = 0;
+    cudaDeviceSynchronize();
+    auto t0 = std::chrono::steady_clock::now();
+    apd.RunPatchMatch();
+    auto t1 = std::chrono::steady_clock::now();
+    if (kernel_ms) *kernel_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    cudaError_t e = cudaGetLastError();
+    memcpy(planes, apd.plane_hypotheses_host.get(), P * sizeof(float4));
+    if (weak) memcpy(weak, apd.weak_info_host.ptr<uchar>(0), P);
+    if (conf && (prm.geom_consistency || prm.use_APD)) memcpy(conf, apd.confidence_host.ptr<uchar>(0), P);
+    free_state(s);
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
+}  // extern "C"
