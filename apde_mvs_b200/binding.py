@@ -71,7 +71,7 @@ class Schedule(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [
-        ("patchmatch_ms", C.c_double), ("total_ms", C.c_double),
+        ("patchmatch_ms", C.c_double), ("device_ms", C.c_double), ("total_ms", C.c_double),
         ("evals_ncc_old", C.c_uint64), ("evals_ncc_new", C.c_uint64), ("evals_geom", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("passes", C.c_int),
     ]
@@ -132,6 +132,9 @@ def load_library(path=None):
     lib.apde_run_schedule_pass.argtypes = [P, C.POINTER(Schedule), C.c_int, C.POINTER(Timing)]
     lib.apde_schedule_num_passes.argtypes = [P, C.POINTER(Schedule)]
     lib.apde_get_counters.argtypes = [P, C.POINTER(C.c_uint64), C.c_int]
+    lib.apde_set_profiling.argtypes = [P, C.c_int]
+    lib.apde_get_stage_stats.argtypes = [P, P, P, P, C.c_int]
+    lib.apde_microbench.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.apde_depth_pool.argtypes = [P, C.POINTER(P), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.apde_weak_vis_filter.argtypes = [P, P]
     lib.apde_fuse.argtypes = [P, C.c_int, P, P, C.c_int64, C.POINTER(C.c_int64)]
@@ -322,6 +325,21 @@ class Context:
         out = (C.c_uint64 * 4)()
         self._check(self.lib.apde_get_counters(self._h, out, 1 if reset else 0))
         return [int(x) for x in out]
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.apde_set_profiling(self._h, int(on)))
+
+    def stage_stats(self, reset=False):
+        ms = np.zeros(11, np.float64)
+        launches = np.zeros(11, np.uint64)
+        evals = np.zeros((11, 3), np.uint64)
+        self._check(self.lib.apde_get_stage_stats(self._h, _ptr(ms), _ptr(launches), _ptr(evals), int(reset)))
+        return ms, launches, evals
+
+    def microbench(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.apde_microbench(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def depth_pool(self):
         p, nbytes, per_view = C.c_void_p(), C.c_size_t(), C.c_size_t()

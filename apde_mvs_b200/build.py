@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libapde.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["apde_api.cu", "apde_kernels.cu", "apde_apd.cu", "apde_maps.cu", "apde_fusion.cu"]
+SOURCES = ["apde_api.cu", "apde_kernels.cu", "apde_apd.cu", "apde_maps.cu", "apde_fusion.cu", "apde_microbench.cu"]
 FLAGS = [
     "-std=c++17", "-O3", "--use_fast_math", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

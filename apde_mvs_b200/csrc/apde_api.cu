@@ -17,6 +17,8 @@
 
 using namespace apde;
 
+static const int kStages = 11;
+static const int kCounterWords = (kStages + 1) * 4;
 static thread_local std::string g_err;
 static int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -65,8 +67,14 @@ struct apde_context {
     uint4 *d_vw = nullptr;
     uint8_t *d_weak = nullptr, *d_conf = nullptr, *d_reliable = nullptr;
     short2 *d_nearest = nullptr, *d_anchors = nullptr;
-    unsigned long long *d_counters = nullptr;
+    unsigned long long *d_counters = nullptr;  // [kStages + 1][4]: per-stage NCC-Old / NCC-New / geom evaluation counts
     uint64_t launches = 0;
+    // per-stage profiling (CUDA events on the launching stream)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_stage;
+    double stage_ms[16] = {0};
+    uint64_t stage_launches[16] = {0};
     // current problem
     bool problem_active = false;
     int ref_view = -1;
@@ -130,8 +138,8 @@ int apde_create(int device, apde_context **out) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
-    CU(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
-    CU(cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->d_counters, kCounterWords * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_counters, 0, kCounterWords * sizeof(unsigned long long)));
     *out = c;
     return APDE_OK;
 }
@@ -168,6 +176,7 @@ void apde_destroy(apde_context *c) {
     cudaStreamSynchronize(c->stream);
     free_scene(c);
     cudaFree(c->d_counters);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -180,6 +189,16 @@ int apde_scene_begin(apde_context *c, int num_views, int width, int height) {
     if (width > 32768 || height > 32768 || num_views > 2048)
         return fail(APDE_ERR_ARG, "scene_begin: %dx%d x %d views exceeds the layered-texture limits", width, height, num_views);
     CU(cudaSetDevice(c->device));
+    if (c->committed && c->V == num_views && c->W == width && c->H == height) {
+        // same shape as the resident scene: keep every allocation, only forget the maps and the pyramid level
+        CU(cudaStreamSynchronize(c->stream));
+        for (auto &v : c->views) { v.mw = v.mh = 0; v.has_conf = false; v.src.clear(); }
+        free_level(c);
+        c->problem_active = false;
+        c->committed = false;
+        c->cur = 0;
+        return APDE_OK;
+    }
     free_scene(c);
     c->V = num_views; c->W = width; c->H = height;
     c->views.resize(num_views);
@@ -435,7 +454,7 @@ int apde_problem_setup(apde_context *c, int ref_view, const apde_params *params,
     K.tex = c->level_tex;
     K.planes = c->d_planes; K.costs = c->d_costs; K.sel = c->d_sel; K.vw = c->d_vw; K.weak = c->d_weak; K.conf = c->d_conf;
     K.fit = c->d_fit; K.reliable = c->d_reliable; K.nearest = c->d_nearest; K.anchors = c->d_anchors;
-    K.depth = c->d_depthws; K.counters = c->d_counters;
+    K.depth = c->d_depthws; K.counters = c->d_counters + 4 * kStages;
     for (int i = 0; i < N; ++i) make_view_k(c->cams[0], c->cams[i + 1], rv.src[i], K.v[i]);
 
     const bool need_depth = c->params.geom_consistency || c->params.use_APD;
@@ -488,9 +507,66 @@ int apde_problem_dims(apde_context *c, int *width, int *height, int *num_images)
 
 int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
     if (!c || !c->problem_active) return fail(APDE_ERR_STATE, "problem_stage: no active problem");
+    if (stage < 0 || stage >= kStages) return fail(APDE_ERR_ARG, "problem_stage: unknown stage %d", stage);
     CU(cudaSetDevice(c->device));
-    CU(launch_stage(c->K, stage, iter, color, c->stream, nullptr));
+    PassK Kl = c->K;
+    Kl.counters = c->d_counters + 4 * stage;
+    if (c->profiling) {
+        const size_t k = c->ev_stage.size();
+        while (c->ev_pool.size() < 2 * (k + 1)) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            c->ev_pool.push_back(e);
+        }
+        CU(cudaEventRecord(c->ev_pool[2 * k], c->stream));
+        CU(launch_stage(Kl, stage, iter, color, c->stream, nullptr));
+        CU(cudaEventRecord(c->ev_pool[2 * k + 1], c->stream));
+        c->ev_stage.push_back(stage);
+    } else {
+        CU(launch_stage(Kl, stage, iter, color, c->stream, nullptr));
+    }
     c->launches++;
+    c->stage_launches[stage]++;
+    return APDE_OK;
+}
+
+static int collect_stage_events(apde_context *c) {
+    if (c->ev_stage.empty()) return APDE_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t k = 0; k < c->ev_stage.size(); ++k) {
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, c->ev_pool[2 * k], c->ev_pool[2 * k + 1]));
+        c->stage_ms[c->ev_stage[k]] += ms;
+    }
+    c->ev_stage.clear();
+    return APDE_OK;
+}
+
+int apde_set_profiling(apde_context *c, int on) {
+    if (!c) return fail(APDE_ERR_ARG, "set_profiling: null context");
+    int rc = collect_stage_events(c);
+    if (rc) return rc;
+    c->profiling = on != 0;
+    return APDE_OK;
+}
+
+int apde_get_stage_stats(apde_context *c, double *ms, uint64_t *launches, uint64_t *evals, int reset) {
+    if (!c) return fail(APDE_ERR_ARG, "get_stage_stats: null context");
+    CU(cudaSetDevice(c->device));
+    int rc = collect_stage_events(c);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    unsigned long long h[kCounterWords];
+    CU(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int s = 0; s < kStages; ++s) {
+        if (ms) ms[s] = c->stage_ms[s];
+        if (launches) launches[s] = c->stage_launches[s];
+        if (evals) for (int k = 0; k < 3; ++k) evals[3 * s + k] = h[4 * s + k];
+    }
+    if (reset) {
+        CU(cudaMemset(c->d_counters, 0, sizeof(h)));
+        for (int s = 0; s < 16; ++s) { c->stage_ms[s] = 0; c->stage_launches[s] = 0; }
+    }
     return APDE_OK;
 }
 
@@ -515,6 +591,7 @@ int apde_problem_run(apde_context *c) {
     if (p.geom_consistency || p.use_APD) ST(APDE_STAGE_CONFIDENCE, 0, 0)
     ST(APDE_STAGE_LOCAL_REFINE, 0, 0)
 #undef ST
+    if (c->profiling && c->ev_stage.size() > 512) return collect_stage_events(c);
     return APDE_OK;
 }
 
@@ -689,13 +766,26 @@ int apde_debug_tex2d(apde_context *c, int idx, int n, const float *xy, float *ou
     return APDE_OK;
 }
 
+int apde_microbench(apde_context *c, double *fp32_tflops, double *tex_gsamples) {
+    if (!c) return fail(APDE_ERR_ARG, "microbench: null context");
+    CU(cudaSetDevice(c->device));
+    if (fp32_tflops) CU(microbench_fp32(fp32_tflops, c->stream));
+    if (tex_gsamples) {
+        if (!c->level_tex) return fail(APDE_ERR_STATE, "microbench: no pyramid level built yet");
+        CU(microbench_tex(c->level_tex, 0, c->lw, c->lh, tex_gsamples, c->stream));
+    }
+    return APDE_OK;
+}
+
 int apde_get_counters(apde_context *c, uint64_t out[4], int reset) {
     if (!c || !out) return fail(APDE_ERR_ARG, "get_counters: null argument");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
-    unsigned long long h[4];
+    unsigned long long h[kCounterWords];
     CU(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
-    out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; out[3] = c->launches;
+    out[0] = out[1] = out[2] = 0;
+    for (int s = 0; s <= kStages; ++s) { out[0] += h[4 * s]; out[1] += h[4 * s + 1]; out[2] += h[4 * s + 2]; }
+    out[3] = c->launches;
     if (reset) { CU(cudaMemset(c->d_counters, 0, sizeof(h))); c->launches = 0; }
     return APDE_OK;
 }
@@ -767,6 +857,10 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
     if (rc) return rc;
     const auto t0 = std::chrono::steady_clock::now();
     double pm_ms = 0.0;
+    cudaEvent_t evp0, evp1;
+    CU(cudaEventCreate(&evp0));
+    CU(cudaEventCreate(&evp1));
+    CU(cudaEventRecord(evp0, c->stream));
     for (int v = first; v < first + count; ++v) {
         const uint32_t seed = s->seed * 0x9E3779B1u + (uint32_t)pass_index * 0x85EBCA77u;
         if ((rc = apde_problem_setup(c, v, &p, scale, seed))) return rc;
@@ -779,6 +873,7 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
         CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         pm_ms += ms;
     }
+    CU(cudaEventRecord(evp1, c->stream));
     if (s->jacobi) {
         // views outside this rank's shard keep their previous depth until the host-side exchange overwrites them
         if (count < c->V) {
@@ -786,16 +881,22 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
                 if (v >= first && v < first + count) continue;
                 CU(cudaMemcpyAsync(c->d_depth_pool[c->cur ^ 1] + (size_t)v * Pfull, c->d_depth_pool[c->cur] + (size_t)v * Pfull,
                                    Pfull * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+                // the host-side exchange fills these at the pass resolution before the next pass reads them
+                c->views[v].mw = c->lw; c->views[v].mh = c->lh;
             }
         }
         c->cur ^= 1;
     }
     CU(cudaStreamSynchronize(c->stream));
+    float dev_ms = 0.0f;
+    CU(cudaEventElapsedTime(&dev_ms, evp0, evp1));
+    cudaEventDestroy(evp0); cudaEventDestroy(evp1);
     const auto t1 = std::chrono::steady_clock::now();
     if (out) {
         uint64_t c1[4];
         if ((rc = apde_get_counters(c, c1, 0))) return rc;
         out->patchmatch_ms += pm_ms;
+        out->device_ms += dev_ms;
         out->total_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
         out->evals_ncc_old += c1[0] - c0[0];
         out->evals_ncc_new += c1[1] - c0[1];

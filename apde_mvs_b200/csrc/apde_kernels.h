@@ -26,4 +26,8 @@ cudaError_t launch_fill_u8(uint8_t *dst, uint8_t v, size_t n, cudaStream_t st);
 cudaError_t launch_finish(const float4 *planes, uint8_t *weak, float *depth, float *normal, uint8_t *weak_out, int P,
                           float dmin, float dmax, cudaStream_t st);
 
+// roofline denominators measured in-process (apde_microbench.cu)
+cudaError_t microbench_fp32(double *tflops, cudaStream_t st);
+cudaError_t microbench_tex(cudaTextureObject_t tex, int layer, int W, int H, double *gsamples, cudaStream_t st);
+
 }  // namespace apde

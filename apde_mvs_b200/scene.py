@@ -132,12 +132,12 @@ class Scene:
                 f.write("%d\n%d %s\n" % (i, len(src), " ".join("%d 1.0" % s for s in src)))
 
 
-def _finish(scene, facets, K, poses, num_src, depth_range, with_color=False):
+def _finish(scene, facets, K, poses, num_src, depth_range, with_color=False, prerendered=None):
     W, H = scene.width, scene.height
     scene.K = K
     centers = []
-    for R, t in poses:
-        gray, depth = render_view(facets, K, R, t, W, H)
+    for i, (R, t) in enumerate(poses):
+        gray, depth = prerendered[i] if prerendered is not None else render_view(facets, K, R, t, W, H)
         scene.images.append(gray)
         scene.gt_depth.append(depth)
         scene.Rs.append(R)
@@ -186,7 +186,8 @@ def _room_facets(seed, weak=0.0):
     return fac
 
 
-def make_office_scene(width=1550, height=1030, num_views=26, num_src=10, seed=2, weak=0.0, arc_deg=60.0, with_color=False):
+def make_office_scene(width=1550, height=1030, num_views=26, num_src=10, seed=2, weak=0.0, arc_deg=60.0, with_color=False,
+                      prerendered=None):
     """C2 / C3 / C4 / C5 shaped: floor + two walls + three boxes, cameras on an arc looking at the room centre.
     weak > 0 adds weak-texture blobs (amplitude <= 1 grey level) covering roughly that fraction of every surface."""
     f = 0.85 * width
@@ -199,7 +200,7 @@ def make_office_scene(width=1550, height=1030, num_views=26, num_src=10, seed=2,
         a = np.deg2rad(-arc_deg / 2 + arc_deg * i / max(1, num_views - 1))
         eye = target + radius * np.array([np.sin(a), -0.25 + 0.1 * np.sin(3 * a), -np.cos(a)])
         poses.append(look_at(eye, target))
-    return _finish(Scene(width, height), facets, K, poses, num_src, (2.0, 12.0), with_color)
+    return _finish(Scene(width, height), facets, K, poses, num_src, (2.0, 12.0), with_color, prerendered)
 
 
 def depth_accuracy(depth, gt, rel=0.01):

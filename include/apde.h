@@ -188,8 +188,9 @@ typedef struct {
 void apde_schedule_default(apde_schedule *s);
 
 typedef struct {
-    double patchmatch_ms; /* device time of all RunPatchMatch stages (CUDA events) */
-    double total_ms;      /* including setup / finish of every problem */
+    double patchmatch_ms; /* device time of all RunPatchMatch stages (CUDA events; == the reference's "RunPatchMatch time") */
+    double device_ms;     /* device time of the whole pass incl. set-up / finish kernels (CUDA events on the stream) */
+    double total_ms;      /* host wall clock of the same region, stream synchronised on both sides */
     uint64_t evals_ncc_old, evals_ncc_new, evals_geom;
     uint64_t kernel_launches;
     int passes;
@@ -203,6 +204,15 @@ int apde_schedule_num_passes(apde_context *ctx, const apde_schedule *s);
 /* cumulative device counters since the last reset: [0] NCC-Old evals, [1] NCC-New evals, [2] geom evals,
  * [3] kernel launches */
 int apde_get_counters(apde_context *ctx, uint64_t out[4], int reset);
+
+/* per-kernel profile of the pass: when enabled, every stage launch is bracketed by CUDA events on the launching stream.
+ * ms[11], launches[11], evals[11][3] are indexed by apde_stage. */
+int apde_set_profiling(apde_context *ctx, int on);
+int apde_get_stage_stats(apde_context *ctx, double *ms, uint64_t *launches, uint64_t *evals, int reset);
+
+/* roofline denominators measured on this GPU, in this process: FP32 FMA rate (TFLOP/s) and texture-unit bilinear gather
+ * rate (10^9 filtered samples/s) on the current pyramid level.  Either pointer may be NULL. */
+int apde_microbench(apde_context *ctx, double *fp32_tflops, double *tex_gsamples);
 
 /* device pointer + byte size of the replicated depth-map pool ([V][P] float at the current map size) so that a
  * host-side collective (NCCL all-gather between passes) can exchange shards in place */
