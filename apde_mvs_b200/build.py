@@ -12,8 +12,11 @@ OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libapde.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["apde_api.cu", "apde_kernels.cu", "apde_apd.cu", "apde_maps.cu", "apde_fusion.cu", "apde_microbench.cu"]
+# the fusion kernels restate HOST code of the reference (IEEE arithmetic, no FMA contraction): no fast-math there
+PRECISE = {"apde_fusion.cu": ["-fmad=false"]}
+FAST = ["--use_fast_math"]
 FLAGS = [
-    "-std=c++17", "-O3", "--use_fast_math", "-lineinfo",
+    "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-ccbin", "/usr/bin/g++",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
@@ -36,7 +39,7 @@ def build(force=False, verbose=False):
         objs.append(obj)
         if force or _newer(src, obj) or any(_newer(h, obj) for h in headers):
             log = open(obj + ".log", "w")
-            procs.append((s, subprocess.Popen([NVCC] + FLAGS + ["-c", src, "-o", obj], stdout=log, stderr=subprocess.STDOUT), log))
+            procs.append((s, subprocess.Popen([NVCC] + FLAGS + PRECISE.get(s, FAST) + ["-c", src, "-o", obj], stdout=log, stderr=subprocess.STDOUT), log))
     failed = False
     for s, p, log in procs:
         rc = p.wait()

@@ -934,7 +934,7 @@ static int fusion_views(apde_context *c, std::vector<FusionView> &fv, int *mw, i
         fv[v].normal = s.d_normal;
         fv[v].weak = s.d_weak;
         fv[v].conf = s.d_conf;
-        fv[v].bgr = s.d_bgr;
+        fv[v].bgr = (*mw == c->W && *mh == c->H) ? s.d_bgr : nullptr;  // colours only at full resolution
         fv[v].src = s.src;
     }
     return APDE_OK;

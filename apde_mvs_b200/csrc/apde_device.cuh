@@ -171,13 +171,13 @@ __device__ __forceinline__ void load_ref_patch(const PassK &K, int px, int py, R
             const float v = tex2DLayered<float>(K.tex, px + (2 * i - 5) + 0.5f, py + (2 * j - 5) + 0.5f, K.ref_layer);
             rp.r[i * 6 + j] = v;
             s += v;
-            ss += v * v;
+            ss = fmaf(v, v, ss);
         }
     }
+    // epilogue arithmetic exactly as the reference build's SASS: mean = inv * sum; var = FFMA(inv, sum_xx, -(mean * mean))
     const float inv = 1.0f / 36.0f;
-    s *= inv; ss *= inv;
-    rp.mean = s;
-    rp.var = ss - s * s;
+    rp.mean = inv * s;
+    rp.var = fmaf(inv, ss, -__fmul_rn(rp.mean, rp.mean));
 }
 
 // m = n^T K_r^-1 / w : the hypothesis-dependent row vector of H = A - b m^T
@@ -222,11 +222,11 @@ __device__ __forceinline__ float patch_ncc36(const PassK &K, const Homog &Hm, in
         }
     }
     const float inv = 1.0f / 36.0f;
-    sum_s *= inv; sum_ss *= inv; sum_rs *= inv;
-    const float var_s = sum_ss - sum_s * sum_s;
+    const float mean_s = inv * sum_s, e_rs = inv * sum_rs;
+    const float var_s = fmaf(inv, sum_ss, -__fmul_rn(mean_s, mean_s));
     if (rp.var < 1e-5f || var_s < 1e-5f) return 2.0f;
-    const float covar = sum_rs - rp.mean * sum_s;
-    return fmaxf(0.0f, fminf(2.0f, 1.0f - covar * rsqrtf(rp.var * var_s)));
+    const float covar = fmaf(-rp.mean, mean_s, e_rs);
+    return fmaxf(0.0f, fminf(2.0f, fmaf(-covar, rsqrtf(rp.var * var_s), 1.0f)));
 }
 
 // ComputeBilateralNCCOld, APD.cu:596-663 (branch A).  Only the patch centre is bounds-checked (quirk 8).
@@ -260,11 +260,11 @@ __device__ __forceinline__ float patch_ncc9(const PassK &K, const Homog &Hm, int
         }
     }
     const float inv = 1.0f / 9.0f;
-    sr *= inv; srr *= inv; ss *= inv; sss *= inv; srs *= inv;
-    const float var_r = srr - sr * sr, var_s = sss - ss * ss;
+    const float mean_r = inv * sr, mean_s = inv * ss, e_rs = inv * srs;
+    const float var_r = fmaf(inv, srr, -__fmul_rn(mean_r, mean_r)), var_s = fmaf(inv, sss, -__fmul_rn(mean_s, mean_s));
     if (var_r < 1e-5f || var_s < 1e-5f) return 2.0f;
-    const float covar = srs - sr * ss;
-    return fmaxf(0.0f, fminf(2.0f, 1.0f - covar * rsqrtf(var_r * var_s)));
+    const float covar = fmaf(-mean_r, mean_s, e_rs);
+    return fmaxf(0.0f, fminf(2.0f, fmaf(-covar, rsqrtf(var_r * var_s), 1.0f)));
 }
 
 // ComputeBilateralNCCNew, APD.cu:448-593 (sa_mask == 0): centre patch + focal-weighted anchor patches.

@@ -1,6 +1,341 @@
-// apde_fusion.cu -- placeholder until the fusion kernels land (filled in next commit)
+// apde_fusion.cu -- GPU fusion: WeakVisFilter (APD.cpp:962-1049) and RunFusion (APD.cpp:1051-1227).  sm_100a.
+//
+// Compiled WITHOUT --use_fast_math and with -fmad=false: the reference fusion is host code (IEEE arithmetic, no FMA
+// contraction), and its accept / reject tests must come out the same.
+//
+// RunFusion is greedy and order dependent (views in order, pixels row-major; an accepted point masks the source pixels it
+// used, APD.cpp:1149,1176,1209).  The GPU version reproduces that order exactly without a serial sweep:
+//   phase A (parallel): every (pixel, neighbour) reprojection test that does not depend on masks written during this view;
+//   phase B (parallel fixed point): "pixel p uses neighbour pixel q unless an accepted pixel p' < p already used q".
+//     claim[q] = min accepted user of q.  The decision of p depends only on decisions of smaller pixels, so the system is
+//     triangular and has exactly one solution -- the serial result -- which Jacobi iteration reaches in (max dependency
+//     chain length) sweeps, a handful in practice;
+//   phase C: commit masks, ordered compaction of the accepted points (prefix sum keeps the reference's point order).
 #include "apde_fusion.h"
+
+#include <cub/cub.cuh>
+
+#include <climits>
+
 namespace apde {
-cudaError_t fusion_weak_vis_filter(const std::vector<FusionView> &, int, int, int, int, uint8_t *, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t fusion_run(const std::vector<FusionView> &, int, int, const uint8_t *, float *, float *, int64_t, int64_t *, cudaStream_t, uint64_t *) { return cudaErrorNotSupported; }
+
+struct FCam {
+    float K[9], R[9], t[3], c[3];
+    const float *depth;
+    const float *normal;
+    const uint8_t *weak;
+    const uint8_t *conf;
+    const uint8_t *bgr;
+};
+
+// Get3DPointonWorld, APD.cpp:866-889 (camera centre recomputed in float)
+__device__ __forceinline__ float3 point_on_world(int x, int y, float depth, const FCam &cam) {
+    const float px = depth * (x - cam.K[2]) / cam.K[0];
+    const float py = depth * (y - cam.K[5]) / cam.K[4];
+    const float pz = depth;
+    const float tx = cam.R[0] * px + cam.R[3] * py + cam.R[6] * pz;
+    const float ty = cam.R[1] * px + cam.R[4] * py + cam.R[7] * pz;
+    const float tz = cam.R[2] * px + cam.R[5] * py + cam.R[8] * pz;
+    const float cx = -(cam.R[0] * cam.t[0] + cam.R[3] * cam.t[1] + cam.R[6] * cam.t[2]);
+    const float cy = -(cam.R[1] * cam.t[0] + cam.R[4] * cam.t[1] + cam.R[7] * cam.t[2]);
+    const float cz = -(cam.R[2] * cam.t[0] + cam.R[5] * cam.t[1] + cam.R[8] * cam.t[2]);
+    return make_float3(tx + cx, ty + cy, tz + cz);
 }
+// ProjectCamera, APD.cpp:891-900
+__device__ __forceinline__ void project_camera(float3 X, const FCam &cam, float2 &pt, float &depth) {
+    const float tx = cam.R[0] * X.x + cam.R[1] * X.y + cam.R[2] * X.z + cam.t[0];
+    const float ty = cam.R[3] * X.x + cam.R[4] * X.y + cam.R[5] * X.z + cam.t[1];
+    const float tz = cam.R[6] * X.x + cam.R[7] * X.y + cam.R[8] * X.z + cam.t[2];
+    depth = cam.K[6] * tx + cam.K[7] * ty + cam.K[8] * tz;
+    pt.x = (cam.K[0] * tx + cam.K[1] * ty + cam.K[2] * tz) / depth;
+    pt.y = (cam.K[3] * tx + cam.K[4] * ty + cam.K[5] * tz) / depth;
+}
+// GetAngle, APD.cpp:902-910 (cv::norm is double)
+__device__ __forceinline__ float get_angle(float ax, float ay, float az, float bx, float by, float bz) {
+    const float dot = ax * bx + ay * by + az * bz;
+    const double na = sqrt((double)ax * ax + (double)ay * ay + (double)az * az);
+    const double nb = sqrt((double)bx * bx + (double)by * by + (double)bz * bz);
+    const float ang = acosf((float)(dot / (na * nb)));
+    return (ang != ang) ? 0.0f : ang;
+}
+// confidences[..].at<float>(r, c) on a CV_8UC1 map (APD.cpp:1010-1011): four raw bytes at r*W + 4c, zero past the end
+__device__ __forceinline__ float conf_as_float(const uint8_t *conf, int P, int W, int r, int c) {
+    const int off = r * W + 4 * c;
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (off + i < P) bits |= (uint32_t)conf[off + i] << (8 * i);
+    return __uint_as_float(bits);
+}
+
+__global__ void __launch_bounds__(128) k_weak_vis(const FCam *__restrict__ cams, int V, int ref, int W, int H,
+                                                  uint8_t *__restrict__ skip) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int P = W * H;
+    if (idx >= P) return;
+    const FCam &rc = cams[ref];
+    if (rc.weak[idx] != APDE_WEAK) return;
+    const int r = idx / W, c = idx % W;
+    const float ref_depth = rc.depth[idx];
+    const float3 X = point_on_world(c, r, ref_depth, rc);
+    int so = 0, wo = 0;
+    for (int s = 0; s < V; ++s) {
+        if (s == ref) continue;
+        const FCam &sc = cams[s];
+        float ang = get_angle(rc.c[0] - X.x, rc.c[1] - X.y, rc.c[2] - X.z, sc.c[0] - X.x, sc.c[1] - X.y, sc.c[2] - X.z);
+        ang = (float)((double)(ang * 180.0f) / 3.14159265358979323846);
+        if (ang > 80.0f) continue;
+        float2 pt;
+        float pd;
+        project_camera(X, sc, pt, pd);
+        if (pd <= 0.0f) continue;
+        const int sr = (int)(pt.y + 0.5f), scn = (int)(pt.x + 0.5f);
+        if (scn >= 0 && scn < W && sr >= 0 && sr < H) {
+            const float sd = sc.depth[sr * W + scn];
+            const uint8_t wk = sc.weak[sr * W + scn];
+            if (wk == APDE_STRONG) {
+                if (pd < sd - 0.01f * sd) so++;
+            } else if (wk == APDE_WEAK) {
+                if (conf_as_float(sc.conf, P, W, sr, scn) < conf_as_float(rc.conf, P, W, r, c)) {
+                    if (pd < sd - 0.01f * sd) wo++;
+                }
+            }
+        }
+    }
+    if (so >= 2 || wo >= 4) skip[(size_t)ref * P + idx] = 1;
+}
+
+// phase A: mask-independent tests of pixel idx of view `ref` against its neighbours
+__global__ void __launch_bounds__(128) k_fuse_candidates(const FCam *__restrict__ cams, const int *__restrict__ nbr, int N,
+                                                         int ref, int W, int H, const uint8_t *__restrict__ masks,
+                                                         const uint8_t *__restrict__ skip, int *__restrict__ cq,
+                                                         float *__restrict__ ce, uint8_t *__restrict__ active) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int P = W * H;
+    if (idx >= P) return;
+    const FCam &rc = cams[ref];
+    uint8_t act = 0;
+    const float ref_depth = rc.depth[idx];
+    if (masks[(size_t)ref * P + idx] != 1 && skip[(size_t)ref * P + idx] != 1 && !(ref_depth <= 0.0f)) {
+        act = 1;
+        const int r = idx / W, c = idx % W;
+        const float3 X = point_on_world(c, r, ref_depth, rc);
+        const float nx = rc.normal[3 * idx], ny = rc.normal[3 * idx + 1], nz = rc.normal[3 * idx + 2];
+        for (int j = 0; j < N; ++j) {
+            const int s = nbr[j];
+            const FCam &sc = cams[s];
+            int q = -1;
+            float e = 0.0f;
+            float2 pt;
+            float pd;
+            project_camera(X, sc, pt, pd);
+            const int sr = (int)(pt.y + 0.5f), scn = (int)(pt.x + 0.5f);
+            if (scn >= 0 && scn < W && sr >= 0 && sr < H) {
+                const int sp = sr * W + scn;
+                const float sd = sc.depth[sp];
+                if (masks[(size_t)s * P + sp] != 1 && !(sd <= 0.0f)) {
+                    const float3 tX = point_on_world(scn, sr, sd, sc);
+                    float2 tp;
+                    project_camera(tX, rc, tp, pd);
+                    const float re = (float)sqrt(pow((double)(c - tp.x), 2.0) + pow((double)(r - tp.y), 2.0));
+                    const float rdd = fabsf(pd - ref_depth) / ref_depth;
+                    const float ang = get_angle(nx, ny, nz, sc.normal[3 * sp], sc.normal[3 * sp + 1], sc.normal[3 * sp + 2]);
+                    if (re < 2.0f && rdd < 0.01f && ang < 0.174533f) {
+                        q = sp;
+                        e = (float)exp((double)-(re + 200 * rdd + ang * 10));
+                    }
+                }
+            }
+            cq[(size_t)j * P + idx] = q;
+            ce[(size_t)j * P + idx] = e;
+        }
+    }
+    active[idx] = act;
+}
+
+// phase B: one Jacobi sweep.  used[p] = bit mask of neighbours consumed by an accepted p (0 = rejected).
+__global__ void __launch_bounds__(128) k_fuse_sweep(const int *__restrict__ slot, int N, int P, const uint8_t *__restrict__ active,
+                                                    const uint8_t *__restrict__ weak, const int *__restrict__ cq,
+                                                    const float *__restrict__ ce, const int *__restrict__ claim_prev,
+                                                    int *__restrict__ claim_next, uint32_t *__restrict__ used,
+                                                    int *__restrict__ changed) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P || !active[idx]) return;
+    int num = 0;
+    float dyn = 0.0f;
+    uint32_t bits = 0;
+    for (int j = 0; j < N; ++j) {
+        const int q = cq[(size_t)j * P + idx];
+        if (q < 0) continue;
+        if (claim_prev[(size_t)slot[j] * P + q] < idx) continue;  // masked by an earlier accepted pixel of this view
+        bits |= 1u << j;
+        dyn += ce[(size_t)j * P + idx];
+        num++;
+    }
+    const float factor = (weak[idx] == APDE_WEAK) ? 0.45f : 0.3f;
+    if (!(num >= 1 && dyn > factor * num)) bits = 0;
+    if (bits != used[idx]) { used[idx] = bits; *changed = 1; }
+    for (int j = 0; j < N; ++j)
+        if ((bits >> j) & 1u) atomicMin(&claim_next[(size_t)slot[j] * P + cq[(size_t)j * P + idx]], idx);
+}
+
+// phase C: commit masks, flag accepted pixels
+__global__ void __launch_bounds__(128) k_fuse_commit(const int *__restrict__ nbr, int N, int P, const int *__restrict__ cq,
+                                                     const uint32_t *__restrict__ used, uint8_t *__restrict__ masks,
+                                                     int *__restrict__ flags) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const uint32_t bits = used[idx];
+    flags[idx] = bits ? 1 : 0;
+    for (int j = 0; j < N; ++j)
+        if ((bits >> j) & 1u) masks[(size_t)nbr[j] * P + cq[(size_t)j * P + idx]] = 1;
+}
+
+__global__ void __launch_bounds__(128) k_fuse_emit(const FCam *__restrict__ cams, const int *__restrict__ nbr, int N, int ref,
+                                                   int W, int H, const int *__restrict__ cq, const uint32_t *__restrict__ used,
+                                                   const int *__restrict__ offs, float *__restrict__ xyz,
+                                                   float *__restrict__ bgr) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int P = W * H;
+    if (idx >= P) return;
+    const uint32_t bits = used[idx];
+    if (!bits) return;
+    const FCam &rc = cams[ref];
+    const int o = offs[idx];
+    const float3 X = point_on_world(idx % W, idx / W, rc.depth[idx], rc);
+    xyz[3 * o] = X.x; xyz[3 * o + 1] = X.y; xyz[3 * o + 2] = X.z;
+    float col[3] = {0.0f, 0.0f, 0.0f};
+    int n = 0;
+    if (rc.bgr) {
+        for (int k = 0; k < 3; ++k) col[k] = (float)rc.bgr[3 * idx + k];
+        for (int j = 0; j < N; ++j) {
+            if (!((bits >> j) & 1u)) continue;
+            const uint8_t *sb = cams[nbr[j]].bgr;
+            const int q = cq[(size_t)j * P + idx];
+            if (sb) for (int k = 0; k < 3; ++k) col[k] += (float)sb[3 * q + k];
+            n++;
+        }
+        for (int k = 0; k < 3; ++k) col[k] /= (n + 1);
+    }
+    bgr[3 * o] = col[0]; bgr[3 * o + 1] = col[1]; bgr[3 * o + 2] = col[2];
+}
+
+__global__ void k_fill_int(int *p, int v, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+static cudaError_t upload_cams(const std::vector<FusionView> &views, FCam **d_cams) {
+    std::vector<FCam> hc(views.size());
+    for (size_t v = 0; v < views.size(); ++v) {
+        const apde_camera &c = views[v].cam;
+        for (int i = 0; i < 9; ++i) { hc[v].K[i] = c.K[i]; hc[v].R[i] = c.R[i]; }
+        for (int i = 0; i < 3; ++i) { hc[v].t[i] = c.t[i]; hc[v].c[i] = c.c[i]; }
+        hc[v].depth = views[v].depth; hc[v].normal = views[v].normal; hc[v].weak = views[v].weak; hc[v].conf = views[v].conf;
+        hc[v].bgr = views[v].bgr;  // the caller passes colours only when they have the maps' resolution
+    }
+    cudaError_t e = cudaMalloc(d_cams, hc.size() * sizeof(FCam));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d_cams, hc.data(), hc.size() * sizeof(FCam), cudaMemcpyHostToDevice);
+}
+
+cudaError_t fusion_weak_vis_filter(const std::vector<FusionView> &views, int w, int h, int Wfull, int Hfull, uint8_t *skip,
+                                   cudaStream_t st) {
+    FCam *d_cams = nullptr;
+    (void)Wfull; (void)Hfull;
+    cudaError_t e = upload_cams(views, &d_cams);
+    if (e != cudaSuccess) return e;
+    const int V = (int)views.size(), P = w * h;
+    for (int ref = 0; ref < V; ++ref) k_weak_vis<<<(P + 127) / 128, 128, 0, st>>>(d_cams, V, ref, w, h, skip);
+    e = cudaStreamSynchronize(st);
+    cudaFree(d_cams);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+#define FCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = e_; goto done; } } while (0)
+
+cudaError_t fusion_run(const std::vector<FusionView> &views, int w, int h, const uint8_t *skip, float *xyz, float *bgr,
+                       int64_t max_points, int64_t *num_points, cudaStream_t st, uint64_t *launches) {
+    const int V = (int)views.size(), P = w * h;
+    cudaError_t err = cudaSuccess;
+    FCam *d_cams = nullptr;
+    uint8_t *d_masks = nullptr, *d_active = nullptr;
+    int *d_nbr = nullptr, *d_slot = nullptr, *d_cq = nullptr, *d_claim[2] = {nullptr, nullptr}, *d_flags = nullptr, *d_offs = nullptr,
+        *d_changed = nullptr;
+    float *d_ce = nullptr, *d_xyz = nullptr, *d_bgr = nullptr;
+    uint32_t *d_used = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int64_t total = 0;
+    int maxN = 1;
+    for (auto &v : views) maxN = std::max(maxN, (int)v.src.size());
+    const int blocks = (P + 127) / 128;
+    FCU(upload_cams(views, &d_cams));
+    FCU(cudaMalloc(&d_masks, (size_t)V * P));
+    FCU(cudaMemsetAsync(d_masks, 0, (size_t)V * P, st));
+    FCU(cudaMalloc(&d_active, P));
+    FCU(cudaMalloc(&d_nbr, maxN * sizeof(int)));
+    FCU(cudaMalloc(&d_slot, maxN * sizeof(int)));
+    FCU(cudaMalloc(&d_cq, (size_t)maxN * P * sizeof(int)));
+    FCU(cudaMalloc(&d_ce, (size_t)maxN * P * sizeof(float)));
+    FCU(cudaMalloc(&d_claim[0], (size_t)maxN * P * sizeof(int)));
+    FCU(cudaMalloc(&d_claim[1], (size_t)maxN * P * sizeof(int)));
+    FCU(cudaMalloc(&d_used, (size_t)P * sizeof(uint32_t)));
+    FCU(cudaMalloc(&d_flags, (size_t)P * sizeof(int)));
+    FCU(cudaMalloc(&d_offs, (size_t)P * sizeof(int)));
+    FCU(cudaMalloc(&d_changed, sizeof(int)));
+    FCU(cudaMalloc(&d_xyz, (size_t)P * 3 * sizeof(float)));
+    FCU(cudaMalloc(&d_bgr, (size_t)P * 3 * sizeof(float)));
+    FCU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_flags, d_offs, P, st));
+    FCU(cudaMalloc(&d_tmp, tmp_bytes));
+
+    for (int ref = 0; ref < V; ++ref) {
+        const int N = (int)views[ref].src.size();
+        if (N == 0) continue;
+        std::vector<int> slot(N);
+        for (int j = 0; j < N; ++j) {  // duplicate neighbour ids share one claim plane, as they share masks[src] in the reference
+            slot[j] = j;
+            for (int k = 0; k < j; ++k) if (views[ref].src[k] == views[ref].src[j]) { slot[j] = k; break; }
+        }
+        FCU(cudaMemcpyAsync(d_nbr, views[ref].src.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
+        FCU(cudaMemcpyAsync(d_slot, slot.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
+        k_fuse_candidates<<<blocks, 128, 0, st>>>(d_cams, d_nbr, N, ref, w, h, d_masks, skip, d_cq, d_ce, d_active);
+        FCU(cudaMemsetAsync(d_used, 0, (size_t)P * sizeof(uint32_t), st));
+        const size_t nclaim = (size_t)N * P;
+        k_fill_int<<<(unsigned)((nclaim + 255) / 256), 256, 0, st>>>(d_claim[0], INT_MAX, nclaim);
+        if (launches) *launches += 2;
+        int cur = 0;
+        for (int sweep = 0; sweep < 100000; ++sweep) {
+            k_fill_int<<<(unsigned)((nclaim + 255) / 256), 256, 0, st>>>(d_claim[cur ^ 1], INT_MAX, nclaim);
+            FCU(cudaMemsetAsync(d_changed, 0, sizeof(int), st));
+            k_fuse_sweep<<<blocks, 128, 0, st>>>(d_slot, N, P, d_active, views[ref].weak, d_cq, d_ce, d_claim[cur], d_claim[cur ^ 1],
+                                                 d_used, d_changed);
+            if (launches) *launches += 2;
+            int changed = 0;
+            FCU(cudaMemcpyAsync(&changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, st));
+            FCU(cudaStreamSynchronize(st));
+            cur ^= 1;
+            if (!changed) break;
+        }
+        k_fuse_commit<<<blocks, 128, 0, st>>>(d_nbr, N, P, d_cq, d_used, d_masks, d_flags);
+        FCU(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_flags, d_offs, P, st));
+        k_fuse_emit<<<blocks, 128, 0, st>>>(d_cams, d_nbr, N, ref, w, h, d_cq, d_used, d_offs, d_xyz, d_bgr);
+        if (launches) *launches += 3;
+        int last_off = 0, last_flag = 0;
+        FCU(cudaMemcpyAsync(&last_off, d_offs + P - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FCU(cudaMemcpyAsync(&last_flag, d_flags + P - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FCU(cudaStreamSynchronize(st));
+        const int64_t n = (int64_t)last_off + last_flag;
+        const int64_t room = std::max<int64_t>(0, std::min<int64_t>(n, max_points - total));
+        if (room > 0 && xyz) FCU(cudaMemcpy(xyz + 3 * total, d_xyz, (size_t)room * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        if (room > 0 && bgr) FCU(cudaMemcpy(bgr + 3 * total, d_bgr, (size_t)room * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        total += n;
+    }
+    *num_points = total;
+done:
+    cudaFree(d_cams); cudaFree(d_masks); cudaFree(d_active); cudaFree(d_nbr); cudaFree(d_slot); cudaFree(d_cq); cudaFree(d_ce);
+    cudaFree(d_claim[0]); cudaFree(d_claim[1]); cudaFree(d_used); cudaFree(d_flags); cudaFree(d_offs); cudaFree(d_changed);
+    cudaFree(d_xyz); cudaFree(d_bgr); cudaFree(d_tmp);
+    return err;
+}
+
+}  // namespace apde

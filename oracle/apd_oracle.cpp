@@ -344,25 +344,31 @@ inline float patch_ncc(const orc_problem *pb, const float *H, int src_idx, int c
             const F2 sp = corresponding_point(H, rx, ry);
             const float src_pix = tex_linear(src, W, Hh, sp.x + 0.5f, sp.y + 0.5f, pb->tex_mode);
             const float weight = 1.0f; /* quirk 1: "bilateral" weight == 1 (APD.cu:534,635) */
+            /* nvcc (-fmad=true, the reference's build) folds weight == 1 and contracts every "sum += a * b" into one
+             * FMA.  This matters: on weak texture var = E[x^2] - E[x]^2 is a difference of two ~16384 numbers whose
+             * fp32 rounding noise (~2e-3) dwarfs the 1e-5 variance floor, so the contraction pattern decides costs. */
             sum_ref += weight * ref_pix;
-            sum_ref_ref += weight * ref_pix * ref_pix;
+            sum_ref_ref = std::fmaf(ref_pix, ref_pix, sum_ref_ref);
             sum_src += weight * src_pix;
-            sum_src_src += weight * src_pix * src_pix;
-            sum_ref_src += weight * ref_pix * src_pix;
+            sum_src_src = std::fmaf(src_pix, src_pix, sum_src_src);
+            sum_ref_src = std::fmaf(ref_pix, src_pix, sum_ref_src);
             wsum += weight;
         }
     }
     if (wsum == 0.0f) return -1.0f; /* only reachable in NCC-New with SAM masks; never here */
+    /* Epilogue exactly as nvcc compiles APD.cu:644-661 for sm_100 with the reference flags (SASS of the reference build:
+     * MUFU.RCP; 3x FMUL; FMUL mean^2; FFMA(inv, sum_xx, -mean^2); FFMA(-mean_r, mean_s, E_rs); FFMA(-covar, 1/sqrt, 1)).
+     * MUFU.RCP(36) and MUFU.RCP(9) return the correctly rounded reciprocal (tools/probe_mufu.cu). */
     const float inv = 1.0f / wsum;
-    sum_ref *= inv; sum_ref_ref *= inv; sum_src *= inv; sum_src_src *= inv; sum_ref_src *= inv;
-    const float var_ref = sum_ref_ref - sum_ref * sum_ref;
-    const float var_src = sum_src_src - sum_src * sum_src;
+    const float mean_ref = inv * sum_ref, mean_src = inv * sum_src, e_rs = inv * sum_ref_src;
+    const float var_ref = std::fmaf(inv, sum_ref_ref, -(mean_ref * mean_ref));
+    const float var_src = std::fmaf(inv, sum_src_src, -(mean_src * mean_src));
     const float kMinVar = 1e-5f;
     if (var_ref < kMinVar || var_src < kMinVar) return 2.0f;
-    const float covar = sum_ref_src - sum_ref * sum_src;
+    const float covar = std::fmaf(-mean_ref, mean_src, e_rs);
     const float denom = std::sqrt(var_ref * var_src);
     /* max(0, min(2, v)) with CUDA fminf/fmaxf NaN semantics (quirk 10): NaN -> 2 */
-    const float v = 1.0f - covar / denom;
+    const float v = std::fmaf(-covar, 1.0f / denom, 1.0f);
     return std::fmax(0.0f, std::fmin(2.0f, v));
 }
 
