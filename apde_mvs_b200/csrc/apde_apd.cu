@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(128) k_prop_weak(const __grid_constant__ PassK
 
     RefPatch rp;
     load_ref_patch(K, px, py, rp);
+    AnchorRef ar;
+    load_anchor_ref(K, anc, ar);
     unsigned n_new = 0, n_geom = 0;
 
     unsigned flags = 0, anchor_valid = 0;
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(128) k_prop_weak(const __grid_constant__ PassK
         if (ok) {
             const float3 m = plane_row(K, K.planes[pos[h]]);
 #pragma unroll 1
-            for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_new(K, K.v[v], v, px, py, m, rp, anc);
+            for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_new(K, K.v[v], v, px, py, m, rp, ar);
             n_new += N;
         } else {
             for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = (h == 0 && v == 0) ? 2.0f : 0.0f;
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(128) k_prop_weak(const __grid_constant__ PassK
         float acc = 0.0f;
         for (uint32_t mk = wmask; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            float c = ncc_new(K, s_vk[v], v, px, py, m, rp, anc);
+            float c = ncc_new(K, s_vk[v], v, px, py, m, rp, ar);
             n_new++;
             if (use_geom) { c = c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, plane_c); n_geom++; }
             acc += (float)vw_get(w, v) * c;
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(128) k_prop_weak(const __grid_constant__ PassK
             float acc = 0.0f;
             for (uint32_t mk = wmask; mk; mk &= mk - 1) {
                 const int v = __ffs(mk) - 1;
-                float c = ncc_new(K, s_vk[v], v, px, py, m, rp, anc);
+                float c = ncc_new(K, s_vk[v], v, px, py, m, rp, ar);
                 n_new++;
                 if (use_geom) { c = c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp); n_geom++; }
                 acc += (float)vw_get(w, v) * c;

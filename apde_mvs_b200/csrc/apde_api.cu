@@ -777,6 +777,13 @@ int apde_microbench(apde_context *c, double *fp32_tflops, double *tex_gsamples) 
     return APDE_OK;
 }
 
+int apde_microbench_pattern(apde_context *c, int mode, float spread, double *tex_gsamples) {
+    if (!c || !tex_gsamples || !c->level_tex) return fail(APDE_ERR_STATE, "microbench_pattern: no pyramid level built yet");
+    CU(cudaSetDevice(c->device));
+    CU(microbench_tex_pattern(c->level_tex, 0, c->lw, c->lh, mode, spread, tex_gsamples, c->stream));
+    return APDE_OK;
+}
+
 int apde_get_counters(apde_context *c, uint64_t out[4], int reset) {
     if (!c || !out) return fail(APDE_ERR_ARG, "get_counters: null argument");
     CU(cudaSetDevice(c->device));

@@ -242,26 +242,60 @@ __device__ __forceinline__ float ncc_old(const PassK &K, const ViewK &vk, int px
     return patch_ncc36(K, Hm, vk.layer, px, py, rp);
 }
 
-// 3x3 anchor patch (weak_radius 5, weak_increment 5) around (ax, ay), reference texels fetched on the fly
-__device__ __forceinline__ float patch_ncc9(const PassK &K, const Homog &Hm, int layer, int ax, int ay) {
+// Reference side of the (up to) 8 anchor patches of a WEAK pixel: 3x3 taps (weak_radius 5, weak_increment 5) and their
+// statistics.  They depend on the pixel only, so they are gathered once per pixel per kernel (the reference re-fetches
+// them for every evaluation, APD.cu:531) -- per evaluation only the 9 SOURCE samples per anchor remain.
+struct AnchorRef {
+    float r[8 * 9];
+    float mean[8], var[8];
+    short2 a[8];  // x == -1: no anchor in this slot
+};
+
+__device__ __forceinline__ void load_anchor_ref(const PassK &K, const short2 *anc, AnchorRef &ar) {
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        const short2 a = anc[k + 1];
+        ar.a[k] = a;
+        if (a.x == -1 || a.y == -1) { ar.a[k].x = -1; continue; }
+        float sr = 0.0f, srr = 0.0f;
+        int t = 0;
+#pragma unroll
+        for (int i = -5; i <= 5; i += 5) {
+#pragma unroll
+            for (int j = -5; j <= 5; j += 5) {
+                const float r = tex2DLayered<float>(K.tex, (float)(a.x + i) + 0.5f, (float)(a.y + j) + 0.5f, K.ref_layer);
+                ar.r[k * 9 + t++] = r;
+                sr += r;
+                srr = fmaf(r, r, srr);
+            }
+        }
+        const float inv = 1.0f / 9.0f;
+        ar.mean[k] = inv * sr;
+        ar.var[k] = fmaf(inv, srr, -__fmul_rn(ar.mean[k], ar.mean[k]));
+    }
+}
+
+// NCC of one 3x3 anchor patch: only the source samples are gathered here
+__device__ __forceinline__ float patch_ncc9(const PassK &K, const Homog &Hm, int layer, int ax, int ay, const float *r9,
+                                            float mean_r, float var_r) {
     const float *h = Hm.h;
-    float sr = 0.0f, srr = 0.0f, ss = 0.0f, sss = 0.0f, srs = 0.0f;
+    float ss = 0.0f, sss = 0.0f, srs = 0.0f;
+    int t = 0;
 #pragma unroll
     for (int i = -5; i <= 5; i += 5) {
 #pragma unroll
         for (int j = -5; j <= 5; j += 5) {
             const float fxp = (float)(ax + i), fyp = (float)(ay + j);
-            const float r = tex2DLayered<float>(K.tex, fxp + 0.5f, fyp + 0.5f, K.ref_layer);
             const float Z = h[6] * fxp + h[7] * fyp + h[8];
             const float iz = rcp_approx(Z);
             const float X = (h[0] * fxp + h[1] * fyp + h[2]) * iz, Y = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
             const float s = tex2DLayered<float>(K.tex, X + 0.5f, Y + 0.5f, layer);
-            sr += r; srr = fmaf(r, r, srr); ss += s; sss = fmaf(s, s, sss); srs = fmaf(r, s, srs);
+            ss += s; sss = fmaf(s, s, sss); srs = fmaf(r9[t++], s, srs);
         }
     }
     const float inv = 1.0f / 9.0f;
-    const float mean_r = inv * sr, mean_s = inv * ss, e_rs = inv * srs;
-    const float var_r = fmaf(inv, srr, -__fmul_rn(mean_r, mean_r)), var_s = fmaf(inv, sss, -__fmul_rn(mean_s, mean_s));
+    const float mean_s = inv * ss, e_rs = inv * srs;
+    const float var_s = fmaf(inv, sss, -__fmul_rn(mean_s, mean_s));
     if (var_r < 1e-5f || var_s < 1e-5f) return 2.0f;
     const float covar = fmaf(-mean_r, mean_s, e_rs);
     return fmaxf(0.0f, fminf(2.0f, fmaf(-covar, rsqrtf(var_r * var_s), 1.0f)));
@@ -269,7 +303,7 @@ __device__ __forceinline__ float patch_ncc9(const PassK &K, const Homog &Hm, int
 
 // ComputeBilateralNCCNew, APD.cu:448-593 (sa_mask == 0): centre patch + focal-weighted anchor patches.
 __device__ __forceinline__ float ncc_new(const PassK &K, const ViewK &vk, int view_bit, int px, int py, float3 m,
-                                         const RefPatch &rp, const short2 *anc /* 9 anchors of this pixel */) {
+                                         const RefPatch &rp, const AnchorRef &ar) {
     const Homog Hm = make_homography(vk, m);
     const float *h = Hm.h;
     const float fW = (float)K.W, fH = (float)K.H;
@@ -283,10 +317,10 @@ __device__ __forceinline__ float ncc_new(const PassK &K, const ViewK &vk, int vi
     const float center_cost = patch_ncc36(K, Hm, vk.layer, px, py, rp);
     float sc[8];
     int ns = 0;
-#pragma unroll
-    for (int k = 1; k < APDE_ANCHOR_NUM; ++k) {
-        const short2 a = anc[k];
-        if (a.x == -1 || a.y == -1) continue;
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        const short2 a = ar.a[k];
+        if (a.x == -1) continue;
         const float fxp = (float)a.x, fyp = (float)a.y;
         const float iz = rcp_approx(h[6] * fxp + h[7] * fyp + h[8]);
         const float ax = (h[0] * fxp + h[1] * fyp + h[2]) * iz, ay = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
@@ -294,7 +328,7 @@ __device__ __forceinline__ float ncc_new(const PassK &K, const ViewK &vk, int vi
             if ((K.sel[a.x + a.y * K.W] >> view_bit) & 1u) sc[ns++] = 2.0f;
             continue;
         }
-        sc[ns++] = patch_ncc9(K, Hm, vk.layer, a.x, a.y);
+        sc[ns++] = patch_ncc9(K, Hm, vk.layer, a.x, a.y, &ar.r[k * 9], ar.mean[k], ar.var[k]);
     }
     if (ns == 0) return center_cost;
     float mx = -1e10f;

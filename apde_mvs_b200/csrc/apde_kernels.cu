@@ -36,9 +36,10 @@ __global__ void __launch_bounds__(128) k_init(const __grid_constant__ PassK K, i
     const bool weak = K.use_apd && K.weak[center] == APDE_WEAK;
     float cv[kMaxSrc], cvc[kMaxSrc];
     int num_valid = 0;
+    AnchorRef ar;
+    if (weak) load_anchor_ref(K, K.anchors + (size_t)center * APDE_ANCHOR_NUM, ar);
     for (int v = 0; v < K.N; ++v) {
-        const float c = weak ? ncc_new(K, K.v[v], v, px, py, m, rp, K.anchors + (size_t)center * APDE_ANCHOR_NUM)
-                             : ncc_old(K, K.v[v], px, py, m, rp);
+        const float c = weak ? ncc_new(K, K.v[v], v, px, py, m, rp, ar) : ncc_old(K, K.v[v], px, py, m, rp);
         cv[v] = c; cvc[v] = c;
         if (c < 2.0f) num_valid++;
     }
@@ -539,8 +540,13 @@ __global__ void __launch_bounds__(128) k_eval_costs(const __grid_constant__ Pass
         RefPatch rp;
         load_ref_patch(K, px, py, rp);
         const float3 m = plane_row(K, pl);
-        c = (mode == 0) ? ncc_old(K, K.v[v], px, py, m, rp)
-                        : ncc_new(K, K.v[v], v, px, py, m, rp, K.anchors + (size_t)(py * K.W + px) * APDE_ANCHOR_NUM);
+        if (mode == 0) {
+            c = ncc_old(K, K.v[v], px, py, m, rp);
+        } else {
+            AnchorRef ar;
+            load_anchor_ref(K, K.anchors + (size_t)(py * K.W + px) * APDE_ANCHOR_NUM, ar);
+            c = ncc_new(K, K.v[v], v, px, py, m, rp, ar);
+        }
     }
     out[i] = c;
 }

@@ -29,5 +29,7 @@ cudaError_t launch_finish(const float4 *planes, uint8_t *weak, float *depth, flo
 // roofline denominators measured in-process (apde_microbench.cu)
 cudaError_t microbench_fp32(double *tflops, cudaStream_t st);
 cudaError_t microbench_tex(cudaTextureObject_t tex, int layer, int W, int H, double *gsamples, cudaStream_t st);
+cudaError_t microbench_tex_pattern(cudaTextureObject_t tex, int layer, int W, int H, int mode, float spread, double *gsamples,
+                                   cudaStream_t st);
 
 }  // namespace apde

@@ -213,6 +213,8 @@ int apde_get_stage_stats(apde_context *ctx, double *ms, uint64_t *launches, uint
 /* roofline denominators measured on this GPU, in this process: FP32 FMA rate (TFLOP/s) and texture-unit bilinear gather
  * rate (10^9 filtered samples/s) on the current pyramid level.  Either pointer may be NULL. */
 int apde_microbench(apde_context *ctx, double *fp32_tflops, double *tex_gsamples);
+/* access-pattern study (thread-per-evaluation vs quad-per-evaluation, scattered hypotheses): 10^9 samples/s */
+int apde_microbench_pattern(apde_context *ctx, int mode, float spread, double *tex_gsamples);
 
 /* device pointer + byte size of the replicated depth-map pool ([V][P] float at the current map size) so that a
  * host-side collective (NCCL all-gather between passes) can exchange shards in place */
