@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(128) k_prop_weak(const __grid_constant__ PassK
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
     int px, py;
-    if (!half_pixel(K, color, tiles_x, ylimit, px, py)) return;
+    if (!half_pixel_or_list(K, color, tiles_x, ylimit, px, py)) return;
     const int W = K.W, N = K.N;
     const int center = py * W + px;
     if (K.weak[center] != APDE_WEAK) return;

@@ -55,7 +55,16 @@ struct apde_context {
     float *d_depth_pool[2] = {nullptr, nullptr};  // [V][W*H] ; [1] only allocated in Jacobi mode
     int cur = 0;
     // pyramid level (one alive at a time)
-    int level_scale = 0, lw = 0, lh = 0;
+    // pyramid levels: built on first use, kept for the whole scene (images are immutable after commit)
+    struct Level {
+        int scale = 0, w = 0, h = 0;
+        cudaArray_t arr = nullptr;
+        cudaTextureObject_t tex = 0;
+        float *lin = nullptr;  // [V][h*w]
+        bool stale = true;     // contents must be re-derived from the views' images
+    };
+    std::vector<Level> levels;
+    int level_scale = 0, lw = 0, lh = 0;  // the level of the current problem
     cudaArray_t level_arr = nullptr;
     cudaTextureObject_t level_tex = 0;
     float *d_level_lin = nullptr;  // [V][lh*lw]
@@ -67,11 +76,14 @@ struct apde_context {
     uint4 *d_vw = nullptr;
     uint8_t *d_weak = nullptr, *d_conf = nullptr, *d_reliable = nullptr;
     short2 *d_nearest = nullptr, *d_anchors = nullptr;
+    int *d_lists = nullptr, *d_list_counts = nullptr;  // compacted checkerboard pixel lists (4 x list_cap)
+    int list_cap = 0;
+    bool lists_dirty = true;
     unsigned long long *d_counters = nullptr;  // [kStages + 1][4]: per-stage NCC-Old / NCC-New / geom evaluation counts
     uint64_t launches = 0;
     // per-stage profiling (CUDA events on the launching stream)
     bool profiling = false;
-    std::vector<cudaEvent_t> ev_pool;
+    std::vector<cudaEvent_t> ev_pool, pm_events;
     std::vector<int> ev_stage;
     double stage_ms[16] = {0};
     uint64_t stage_launches[16] = {0};
@@ -145,9 +157,12 @@ int apde_create(int device, apde_context **out) {
 }
 
 static void free_level(apde_context *c) {
-    if (c->level_tex) cudaDestroyTextureObject(c->level_tex);
-    if (c->level_arr) cudaFreeArray(c->level_arr);
-    if (c->d_level_lin) cudaFree(c->d_level_lin);
+    for (auto &L : c->levels) {
+        if (L.tex) cudaDestroyTextureObject(L.tex);
+        if (L.arr) cudaFreeArray(L.arr);
+        if (L.lin) cudaFree(L.lin);
+    }
+    c->levels.clear();
     c->level_tex = 0; c->level_arr = nullptr; c->d_level_lin = nullptr; c->level_scale = 0;
 }
 static void free_scene(apde_context *c) {
@@ -162,6 +177,7 @@ static void free_scene(apde_context *c) {
         cudaFree(c->d_planes); cudaFree(c->d_fit); cudaFree(c->d_costs); cudaFree(c->d_depthws);
         cudaFree(c->d_scratch_depth); cudaFree(c->d_scratch_normal); cudaFree(c->d_sel); cudaFree(c->d_vw);
         cudaFree(c->d_weak); cudaFree(c->d_conf); cudaFree(c->d_reliable); cudaFree(c->d_nearest); cudaFree(c->d_anchors);
+        cudaFree(c->d_lists); cudaFree(c->d_list_counts);
         c->ws_alloc = false;
     }
     cudaFree(c->d_skip);
@@ -177,6 +193,7 @@ void apde_destroy(apde_context *c) {
     free_scene(c);
     cudaFree(c->d_counters);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
+    for (auto e : c->pm_events) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -193,7 +210,8 @@ int apde_scene_begin(apde_context *c, int num_views, int width, int height) {
         // same shape as the resident scene: keep every allocation, only forget the maps and the pyramid level
         CU(cudaStreamSynchronize(c->stream));
         for (auto &v : c->views) { v.mw = v.mh = 0; v.has_conf = false; v.src.clear(); }
-        free_level(c);
+        for (auto &L : c->levels) L.stale = true;
+        c->level_scale = 0;
         c->problem_active = false;
         c->committed = false;
         c->cur = 0;
@@ -260,6 +278,9 @@ static int alloc_workspace(apde_context *c) {
     CU(cudaMalloc(&c->d_reliable, P));
     CU(cudaMalloc(&c->d_nearest, P * sizeof(short2)));
     CU(cudaMalloc(&c->d_anchors, P * APDE_ANCHOR_NUM * sizeof(short2)));
+    c->list_cap = (int)(P / 2 + 64);
+    CU(cudaMalloc(&c->d_lists, (size_t)4 * c->list_cap * sizeof(int)));
+    CU(cudaMalloc(&c->d_list_counts, 4 * sizeof(int)));
     CU(cudaMemsetAsync(c->d_vw, 0, P * sizeof(uint4), c->stream));
     CU(cudaMemsetAsync(c->d_sel, 0, P * sizeof(uint32_t), c->stream));
     c->ws_alloc = true;
@@ -278,37 +299,49 @@ int apde_scene_commit(apde_context *c) {
 // build the pyramid level for scale_size: INTER_LINEAR resize of every view (APD.cpp:564-588) into one layered texture
 static int ensure_level(apde_context *c, int scale) {
     if (c->level_scale == scale) return APDE_OK;
-    free_level(c);
-    const float factor = 1.0f / (float)scale;
-    const int lw = (int)std::round(c->W * factor), lh = (int)std::round(c->H * factor);
-    if (lw < 16 || lh < 16) return fail(APDE_ERR_ARG, "pyramid level %dx%d too small", lw, lh);
-    const size_t P = (size_t)lw * lh;
-    CU(cudaMalloc(&c->d_level_lin, (size_t)c->V * P * sizeof(float)));
-    for (int v = 0; v < c->V; ++v)
-        CU(launch_resize_linear_u8(c->views[v].d_gray, c->W, c->H, c->d_level_lin + (size_t)v * P, lw, lh, c->stream));
-    c->launches += c->V;
-    cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
-    CU(cudaMalloc3DArray(&c->level_arr, &desc, make_cudaExtent(lw, lh, c->V), cudaArrayLayered));
-    cudaMemcpy3DParms cp;
-    memset(&cp, 0, sizeof(cp));
-    cp.srcPtr = make_cudaPitchedPtr(c->d_level_lin, (size_t)lw * sizeof(float), lw, lh);
-    cp.dstArray = c->level_arr;
-    cp.extent = make_cudaExtent(lw, lh, c->V);
-    cp.kind = cudaMemcpyDeviceToDevice;
-    CU(cudaMemcpy3DAsync(&cp, c->stream));
-    cudaResourceDesc rd;
-    memset(&rd, 0, sizeof(rd));
-    rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = c->level_arr;
-    cudaTextureDesc td;
-    memset(&td, 0, sizeof(td));
-    // the reference asks for "wrap" with unnormalised coordinates, which CUDA serves as clamp (APD.cpp:701-705)
-    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
-    td.filterMode = cudaFilterModeLinear;
-    td.readMode = cudaReadModeElementType;
-    td.normalizedCoords = 0;
-    CU(cudaCreateTextureObject(&c->level_tex, &rd, &td, nullptr));
-    c->level_scale = scale; c->lw = lw; c->lh = lh;
+    apde_context::Level *L = nullptr;
+    for (auto &l : c->levels) if (l.scale == scale) L = &l;
+    if (!L) {
+        const float factor = 1.0f / (float)scale;
+        const int lw = (int)std::round(c->W * factor), lh = (int)std::round(c->H * factor);
+        if (lw < 16 || lh < 16) return fail(APDE_ERR_ARG, "pyramid level %dx%d too small", lw, lh);
+        apde_context::Level nl;
+        nl.scale = scale; nl.w = lw; nl.h = lh;
+        const size_t P = (size_t)lw * lh;
+        CU(cudaMalloc(&nl.lin, (size_t)c->V * P * sizeof(float)));
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+        CU(cudaMalloc3DArray(&nl.arr, &desc, make_cudaExtent(lw, lh, c->V), cudaArrayLayered));
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = nl.arr;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        // the reference asks for "wrap" with unnormalised coordinates, which CUDA serves as clamp (APD.cpp:701-705)
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        CU(cudaCreateTextureObject(&nl.tex, &rd, &td, nullptr));
+        c->levels.push_back(nl);
+        L = &c->levels.back();
+    }
+    if (L->stale) {
+        const size_t P = (size_t)L->w * L->h;
+        for (int v = 0; v < c->V; ++v)
+            CU(launch_resize_linear_u8(c->views[v].d_gray, c->W, c->H, L->lin + (size_t)v * P, L->w, L->h, c->stream));
+        c->launches += c->V;
+        cudaMemcpy3DParms cp;
+        memset(&cp, 0, sizeof(cp));
+        cp.srcPtr = make_cudaPitchedPtr(L->lin, (size_t)L->w * sizeof(float), L->w, L->h);
+        cp.dstArray = L->arr;
+        cp.extent = make_cudaExtent(L->w, L->h, c->V);
+        cp.kind = cudaMemcpyDeviceToDevice;
+        CU(cudaMemcpy3DAsync(&cp, c->stream));
+        L->stale = false;
+    }
+    c->level_scale = scale; c->lw = L->w; c->lh = L->h;
+    c->level_arr = L->arr; c->level_tex = L->tex; c->d_level_lin = L->lin;
     return APDE_OK;
 }
 
@@ -494,6 +527,7 @@ int apde_problem_setup(apde_context *c, int ref_view, const apde_params *params,
     }
     c->ref_view = ref_view;
     c->problem_active = true;
+    c->lists_dirty = true;
     return APDE_OK;
 }
 
@@ -511,6 +545,18 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
     CU(cudaSetDevice(c->device));
     PassK Kl = c->K;
     Kl.counters = c->d_counters + 4 * stage;
+    if (stage == APDE_STAGE_GEN_ANCHORS) c->lists_dirty = true;  // NeigbourUpdate turns unreliable WEAK pixels into UNKNOWN
+    if ((stage == APDE_STAGE_PROP_STRONG || stage == APDE_STAGE_PROP_WEAK) && c->params.use_APD) {
+        // rounds with WEAK pixels: walk compacted (colour, class) lists so that no lane idles on the other class
+        if (c->lists_dirty) {
+            CU(launch_build_lists(c->K, c->d_lists, c->d_list_counts, c->list_cap, c->stream));
+            c->launches++;
+            c->lists_dirty = false;
+        }
+        const int cls = (color << 1) | (stage == APDE_STAGE_PROP_WEAK ? 1 : 0);
+        Kl.list = c->d_lists + (size_t)cls * c->list_cap;
+        Kl.list_count = c->d_list_counts + cls;
+    }
     if (c->profiling) {
         const size_t k = c->ev_stage.size();
         while (c->ev_pool.size() < 2 * (k + 1)) {
@@ -667,6 +713,7 @@ int apde_problem_set(apde_context *c, int field, const void *host, size_t bytes)
         return APDE_OK;
     }
     if (field == APDE_FIELD_IMAGE) return fail(APDE_ERR_ARG, "problem_set: field is read only");
+    if (field == APDE_FIELD_WEAK_INFO) c->lists_dirty = true;
     void *ptr; size_t need;
     int rc = field_ptr(c, field, &ptr, &need);
     if (rc) return rc;
@@ -868,19 +915,26 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
     CU(cudaEventCreate(&evp0));
     CU(cudaEventCreate(&evp1));
     CU(cudaEventRecord(evp0, c->stream));
+    while ((int)c->pm_events.size() < 2 * count) {
+        cudaEvent_t ev;
+        CU(cudaEventCreate(&ev));
+        c->pm_events.push_back(ev);
+    }
     for (int v = first; v < first + count; ++v) {
         const uint32_t seed = s->seed * 0x9E3779B1u + (uint32_t)pass_index * 0x85EBCA77u;
         if ((rc = apde_problem_setup(c, v, &p, scale, seed))) return rc;
-        CU(cudaEventRecord(c->ev0, c->stream));
+        CU(cudaEventRecord(c->pm_events[2 * (v - first)], c->stream));
         if ((rc = apde_problem_run(c))) return rc;
-        CU(cudaEventRecord(c->ev1, c->stream));
-        if ((rc = problem_finish_impl(c, s->jacobi != 0))) return rc;
-        CU(cudaEventSynchronize(c->ev1));
-        float ms = 0.0f;
-        CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-        pm_ms += ms;
+        CU(cudaEventRecord(c->pm_events[2 * (v - first) + 1], c->stream));
+        if ((rc = problem_finish_impl(c, s->jacobi != 0))) return rc;  // no host sync: the host runs ahead of the stream
     }
     CU(cudaEventRecord(evp1, c->stream));
+    CU(cudaEventSynchronize(evp1));
+    for (int k = 0; k < count; ++k) {
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, c->pm_events[2 * k], c->pm_events[2 * k + 1]));
+        pm_ms += ms;
+    }
     if (s->jacobi) {
         // views outside this rank's shard keep their previous depth until the host-side exchange overwrites them
         if (count < c->V) {

@@ -17,6 +17,17 @@ __device__ __forceinline__ bool half_pixel(const PassK &K, int color, int tiles_
     px = tx * 8 + 2 * (lane & 3) + ((py + color) & 1);
     return px < K.W && py < ylimit;
 }
+// checkerboard kernels in rounds that have WEAK pixels: threads walk a compacted pixel list (no idle lanes on the
+// other class); without a list the implicit tile mapping above is used
+__device__ __forceinline__ bool half_pixel_or_list(const PassK &K, int color, int tiles_x, int ylimit, int &px, int &py) {
+    if (K.list == nullptr) return half_pixel(K, color, tiles_x, ylimit, px, py);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= *K.list_count) return false;
+    const int center = K.list[idx];
+    px = center % K.W;
+    py = center / K.W;
+    return true;
+}
 // full kernels: one warp = an 8x4 tile
 __device__ __forceinline__ bool full_pixel(const PassK &K, int tiles_x, int &px, int &py) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -88,6 +99,89 @@ __device__ __forceinline__ uint4 select_views(const PassK &K, const float *sc, f
     *selmask = mask;
     *wnorm = wn;
     return w;
+}
+
+
+// -------------------------------------------------------------------------------------------- checkerboard candidates
+// APD.cu:1127-1314.  pos[k]: 0 up_near 1 up_far 2 down_near 3 down_far 4 left_near 5 left_far 6 right_near 7 right_far
+__device__ __forceinline__ unsigned checkerboard_candidates(const float *costs, int width, int height, int px,
+                                                            int py, int pos[8]) {
+    const int center = py * width + px;
+    unsigned flags = 0;
+    float cmin;
+    int cpt;
+    int up_far = center - 3 * width, down_far = center + 3 * width, left_far = center - 3, right_far = center + 3;
+    int up_near = center - width, down_near = center + width, left_near = center - 1, right_near = center + 1;
+#define APDE_TRY(cond, idx)                                      \
+    if (cond) {                                                  \
+        const int pt_ = (idx);                                   \
+        const float c_ = costs[pt_];                     \
+        if (c_ < cmin) { cmin = c_; cpt = pt_; }                 \
+    }
+    if (py > 2) {
+        flags |= 2u; cmin = costs[up_far]; cpt = up_far;
+#pragma unroll
+        for (int i = 1; i < 11; ++i) APDE_TRY(py > 2 + 2 * i, up_far - 2 * i * width)
+        up_far = cpt;
+    }
+    if (py < height - 3) {
+        flags |= 8u; cmin = costs[down_far]; cpt = down_far;
+#pragma unroll
+        for (int i = 1; i < 11; ++i) APDE_TRY(py < height - 3 - 2 * i, down_far + 2 * i * width)
+        down_far = cpt;
+    }
+    if (px > 2) {
+        flags |= 32u; cmin = costs[left_far]; cpt = left_far;
+#pragma unroll
+        for (int i = 1; i < 11; ++i) APDE_TRY(px > 2 + 2 * i, left_far - 2 * i)
+        left_far = cpt;
+    }
+    if (px < width - 3) {
+        flags |= 128u; cmin = costs[right_far]; cpt = right_far;
+#pragma unroll
+        for (int i = 1; i < 11; ++i) APDE_TRY(px < width - 3 - 2 * i, right_far + 2 * i)
+        right_far = cpt;
+    }
+    if (py > 0) {
+        flags |= 1u; cmin = costs[up_near]; cpt = up_near;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            APDE_TRY(py > 1 + i && px > i, up_near - (1 + i) * width - (i + 1))
+            APDE_TRY(py > 1 + i && px < width - 1 - i, up_near - (1 + i) * width + (i + 1))
+        }
+        up_near = cpt;
+    }
+    if (py < height - 1) {
+        flags |= 4u; cmin = costs[down_near]; cpt = down_near;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            APDE_TRY(py < height - 2 - i && px > i, down_near + (1 + i) * width - (i + 1))
+            APDE_TRY(py < height - 2 - i && px < width - 1 - i, down_near + (1 + i) * width + (i + 1))
+        }
+        down_near = cpt;
+    }
+    if (px > 0) {
+        flags |= 16u; cmin = costs[left_near]; cpt = left_near;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            APDE_TRY(px > 1 + i && py > i, left_near - (1 + i) - (i + 1) * width)
+            APDE_TRY(px > 1 + i && py < height - 1 - i, left_near - (1 + i) + (i + 1) * width)
+        }
+        left_near = cpt;
+    }
+    if (px < width - 1) {
+        flags |= 64u; cmin = costs[right_near]; cpt = right_near;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            APDE_TRY(px < width - 2 - i && py > i, right_near + (1 + i) - (i + 1) * width)
+            APDE_TRY(px < width - 2 - i && py < height - 1 - i, right_near + (1 + i) + (i + 1) * width)
+        }
+        right_near = cpt;
+    }
+#undef APDE_TRY
+    pos[0] = up_near; pos[1] = up_far; pos[2] = down_near; pos[3] = down_far;
+    pos[4] = left_near; pos[5] = left_far; pos[6] = right_near; pos[7] = right_far;
+    return flags;
 }
 
 

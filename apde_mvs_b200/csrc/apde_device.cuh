@@ -24,6 +24,7 @@ struct ViewK {
     float bi[3];  // K_r R_r (C_s - C_r)
     float baseline;
     int layer;    // layer of this source view in the level's texture
+    int pad_[2];  // 112 bytes: 16-byte aligned rows in shared memory
 };
 
 struct PassK {
@@ -47,6 +48,9 @@ struct PassK {
     short2 *anchors;       // [P][9]
     const float *depth;    // [N+1][P] working-resolution depth maps, 0 = ref
     unsigned long long *counters;
+    // compacted pixel lists of the checkerboard kernels (rounds with WEAK pixels): [colour][strong | weak], see k_build_lists
+    const int *list;  // nullptr: implicit 8x8-tile mapping
+    const int *list_count;
     ViewK v[kMaxSrc];
 };
 

@@ -9,6 +9,7 @@
 #include "apde_common.cuh"
 
 #include <cfloat>
+#include <cstdlib>
 
 namespace apde {
 
@@ -65,88 +66,6 @@ __global__ void __launch_bounds__(128) k_init(const __grid_constant__ PassK K, i
     count_evals(K, weak ? 0 : K.N, weak ? K.N : 0, 0);
 }
 
-// -------------------------------------------------------------------------------------------- checkerboard candidates
-// APD.cu:1127-1314.  pos[k]: 0 up_near 1 up_far 2 down_near 3 down_far 4 left_near 5 left_far 6 right_near 7 right_far
-__device__ __forceinline__ unsigned checkerboard_candidates(const float *costs, int width, int height, int px,
-                                                            int py, int pos[8]) {
-    const int center = py * width + px;
-    unsigned flags = 0;
-    float cmin;
-    int cpt;
-    int up_far = center - 3 * width, down_far = center + 3 * width, left_far = center - 3, right_far = center + 3;
-    int up_near = center - width, down_near = center + width, left_near = center - 1, right_near = center + 1;
-#define APDE_TRY(cond, idx)                                      \
-    if (cond) {                                                  \
-        const int pt_ = (idx);                                   \
-        const float c_ = costs[pt_];                     \
-        if (c_ < cmin) { cmin = c_; cpt = pt_; }                 \
-    }
-    if (py > 2) {
-        flags |= 2u; cmin = costs[up_far]; cpt = up_far;
-#pragma unroll
-        for (int i = 1; i < 11; ++i) APDE_TRY(py > 2 + 2 * i, up_far - 2 * i * width)
-        up_far = cpt;
-    }
-    if (py < height - 3) {
-        flags |= 8u; cmin = costs[down_far]; cpt = down_far;
-#pragma unroll
-        for (int i = 1; i < 11; ++i) APDE_TRY(py < height - 3 - 2 * i, down_far + 2 * i * width)
-        down_far = cpt;
-    }
-    if (px > 2) {
-        flags |= 32u; cmin = costs[left_far]; cpt = left_far;
-#pragma unroll
-        for (int i = 1; i < 11; ++i) APDE_TRY(px > 2 + 2 * i, left_far - 2 * i)
-        left_far = cpt;
-    }
-    if (px < width - 3) {
-        flags |= 128u; cmin = costs[right_far]; cpt = right_far;
-#pragma unroll
-        for (int i = 1; i < 11; ++i) APDE_TRY(px < width - 3 - 2 * i, right_far + 2 * i)
-        right_far = cpt;
-    }
-    if (py > 0) {
-        flags |= 1u; cmin = costs[up_near]; cpt = up_near;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            APDE_TRY(py > 1 + i && px > i, up_near - (1 + i) * width - (i + 1))
-            APDE_TRY(py > 1 + i && px < width - 1 - i, up_near - (1 + i) * width + (i + 1))
-        }
-        up_near = cpt;
-    }
-    if (py < height - 1) {
-        flags |= 4u; cmin = costs[down_near]; cpt = down_near;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            APDE_TRY(py < height - 2 - i && px > i, down_near + (1 + i) * width - (i + 1))
-            APDE_TRY(py < height - 2 - i && px < width - 1 - i, down_near + (1 + i) * width + (i + 1))
-        }
-        down_near = cpt;
-    }
-    if (px > 0) {
-        flags |= 16u; cmin = costs[left_near]; cpt = left_near;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            APDE_TRY(px > 1 + i && py > i, left_near - (1 + i) - (i + 1) * width)
-            APDE_TRY(px > 1 + i && py < height - 1 - i, left_near - (1 + i) + (i + 1) * width)
-        }
-        left_near = cpt;
-    }
-    if (px < width - 1) {
-        flags |= 64u; cmin = costs[right_near]; cpt = right_near;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            APDE_TRY(px < width - 2 - i && py > i, right_near + (1 + i) - (i + 1) * width)
-            APDE_TRY(px < width - 2 - i && py < height - 1 - i, right_near + (1 + i) + (i + 1) * width)
-        }
-        right_near = cpt;
-    }
-#undef APDE_TRY
-    pos[0] = up_near; pos[1] = up_far; pos[2] = down_near; pos[3] = down_far;
-    pos[4] = left_near; pos[5] = left_far; pos[6] = right_near; pos[7] = right_far;
-    return flags;
-}
-
 // -------------------------------------------------------------------------------------------- K6 strong propagation
 // Black/RedPixelUpdateStrong -> CheckerboardPropagationStrong -> PlaneHypothesisRefinementStrong,
 // APD.cu:1654-1692, 1098-1440, 950-1006.
@@ -161,7 +80,7 @@ __global__ void __launch_bounds__(128) k_prop_strong(const __grid_constant__ Pas
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
     int px, py;
-    if (!half_pixel(K, color, tiles_x, ylimit, px, py)) return;
+    if (!half_pixel_or_list(K, color, tiles_x, ylimit, px, py)) return;
     const int W = K.W, N = K.N;
     const int center = py * W + px;
     if (K.weak[center] == APDE_WEAK) return;
@@ -526,6 +445,44 @@ __global__ void __launch_bounds__(128) k_local_refine(const __grid_constant__ Pa
     count_evals(K, n_old, 0, n_geom);
 }
 
+// -------------------------------------------------------------------------------------------- pixel lists
+// One pass over the 8x8 tiles: every pixel the red/black kernels would visit is appended to the list of its
+// (colour, strong | weak) class.  Warp-aggregated appends keep tile-local order, so a warp of the propagation kernels
+// still works on spatially close pixels.  lists: 4 arrays of `cap` ints; counts: 4 ints (zeroed by the caller).
+__global__ void __launch_bounds__(128) k_build_lists(const __grid_constant__ PassK K, int tiles_x, int ylimit, int *lists,
+                                                     int *counts, int cap) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int l = lane + 32 * half;
+        const int px = tx * 8 + (l & 7), py = ty * 8 + (l >> 3);
+        const bool in = px < K.W && py < ylimit;
+        const int center = py * K.W + px;
+        const int cls = in ? ((((px + py) & 1) << 1) | (K.weak[center] == APDE_WEAK ? 1 : 0)) : -1;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+            if (m == 0) continue;
+            int base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(&counts[c], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (cls == c) lists[(size_t)c * cap + base + __popc(m & ((1u << lane) - 1))] = center;
+        }
+    }
+}
+
+cudaError_t launch_build_lists(const PassK &K, int *lists, int *counts, int cap, cudaStream_t st) {
+    const int ylimit = min(K.H, half_rows_limit(K.H));
+    const int tiles8x = (K.W + 7) / 8;
+    const int tiles = tiles8x * ((ylimit + 7) / 8);
+    cudaError_t e = cudaMemsetAsync(counts, 0, 4 * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    k_build_lists<<<(tiles + 3) / 4, 128, 0, st>>>(K, tiles8x, ylimit, lists, counts, cap);
+    return cudaGetLastError();
+}
+
 // -------------------------------------------------------------------------------------------- parity hook
 __global__ void __launch_bounds__(128) k_eval_costs(const __grid_constant__ PassK K, int n, const int *__restrict__ tuples,
                                                     const float4 *__restrict__ planes, int mode, float *__restrict__ out) {
@@ -559,8 +516,22 @@ int prop_block_threads(int N) {
     return 32;
 }
 
+// APDE_QUAD_KERNELS=1 selects the experimental quad-cooperative kernels (apde_quad.cu).  Measured on B200 (r01): they
+// hold the texture rate under scattered hypotheses but need 2.7x the issue slots per evaluation (exact-order shuffle
+// chain), and lose to the thread-per-evaluation kernels of this file on the real, mostly coherent workload.
+static bool use_thread_kernels() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("APDE_QUAD_KERNELS"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+
 cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStream_t st, float *curve) {
     const int W = K.W, H = K.H, N = K.N;
+    if (!use_thread_kernels()) {
+        bool handled = false;
+        cudaError_t e = launch_stage_quad(K, stage, iter, color, st, curve, &handled);
+        if (handled || e != cudaSuccess) return e;
+    }
     const int ylimit = min(H, half_rows_limit(H));
     const int tiles8x = (W + 7) / 8;
     const size_t vsm = sizeof(float) * views_smem_floats(N);
@@ -579,7 +550,7 @@ cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStr
                 if (e != cudaSuccess) return e;
                 configured = smem;
             }
-            const int tiles = tiles8x * ((ylimit + 7) / 8);
+            const int tiles = tiles8x * ((ylimit + 7) / 8);  // 32 same-colour pixels per tile == worst-case list length / 32
             const int wpb = threads / 32;
             k_prop_strong<<<(tiles + wpb - 1) / wpb, threads, smem, st>>>(K, iter, color, tiles8x, ylimit);
             break;

@@ -8,11 +8,15 @@ namespace apde {
 
 // run one kernel of the pass (stage ids of include/apde.h).  curve: optional [P][61] export of DepthToWeak.
 cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStream_t st, float *curve);
+// quad-cooperative versions of the heavy stages (apde_quad.cu); *handled = false when the stage has none
+cudaError_t launch_stage_quad(const PassK &K, int stage, int iter, int color, cudaStream_t st, float *curve, bool *handled);
 // weak-texture (APD) stages: nearest strong, anchors, RANSAC fit, deformable propagation
 cudaError_t launch_stage_apd(const PassK &K, int stage, int iter, int color, cudaStream_t st);
 cudaError_t launch_eval_costs(const PassK &K, int n, const int *tuples, const float4 *planes, int mode, float *out,
                               cudaStream_t st);
 int prop_block_threads(int N);
+// compacted (colour, strong | weak) pixel lists for the checkerboard kernels: lists = 4 x cap ints, counts = 4 ints
+cudaError_t launch_build_lists(const PassK &K, int *lists, int *counts, int cap, cudaStream_t st);
 
 // scene / map kernels (apde_maps.cu)
 // OpenCV INTER_LINEAR resize of a u8 image to float (APD.cpp:574): dst[h][w] from src[H][W]
