@@ -3,11 +3,13 @@
 // APD.cpp:501-814, without any host round trip), the stage launcher and the multi-scale schedule of main.cpp:303-367.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -94,6 +96,8 @@ struct apde_context {
     apde_params params;
     std::vector<apde_camera> cams;
     PassK K;
+    SweepWorkspace sweep;  // DepthToWeak / LocalRefine column costs
+    PropWorkspace prop;    // propagation pipeline buffers
     // fusion state
     uint8_t *d_skip = nullptr;
 };
@@ -182,6 +186,8 @@ static void free_scene(apde_context *c) {
     }
     cudaFree(c->d_skip);
     c->d_skip = nullptr;
+    c->sweep.release();
+    c->prop.release();
     c->committed = false;
     c->problem_active = false;
 }
@@ -528,6 +534,7 @@ int apde_problem_setup(apde_context *c, int ref_view, const apde_params *params,
     c->ref_view = ref_view;
     c->problem_active = true;
     c->lists_dirty = true;
+    c->sweep.valid = false;
     return APDE_OK;
 }
 
@@ -546,8 +553,15 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
     PassK Kl = c->K;
     Kl.counters = c->d_counters + 4 * stage;
     if (stage == APDE_STAGE_GEN_ANCHORS) c->lists_dirty = true;  // NeigbourUpdate turns unreliable WEAK pixels into UNKNOWN
-    if ((stage == APDE_STAGE_PROP_STRONG || stage == APDE_STAGE_PROP_WEAK) && c->params.use_APD) {
-        // rounds with WEAK pixels: walk compacted (colour, class) lists so that no lane idles on the other class
+    static const bool legacy_prop = [] { const char *e = getenv("APDE_LEGACY_PROP"); return e && e[0] == '1'; }();
+    const bool prop_stage = stage == APDE_STAGE_PROP_STRONG || stage == APDE_STAGE_PROP_WEAK;
+    // measured on B200 (r01, 960x540, 5 src): the column pipeline wins for the sparse WEAK class (81 vs 116 ms per step:
+    // N x more parallelism for few pixels); for the dense strong class the fused one-thread-per-pixel kernel is faster (165 vs
+    // 179 ms: no intermediate buffers, no second pass over the reference patch).  APDE_PIPELINE_STRONG=1 forces the pipeline.
+    static const bool pipe_strong = [] { const char *e = getenv("APDE_PIPELINE_STRONG"); return e && e[0] == '1'; }();
+    const bool pipeline = prop_stage && !legacy_prop && !getenv("APDE_QUAD_KERNELS") && (stage == APDE_STAGE_PROP_WEAK || pipe_strong);
+    if (prop_stage && (c->params.use_APD || pipeline)) {
+        // compacted (colour, class) pixel lists: no lane idles on the other class, and the column kernels index by list slot
         if (c->lists_dirty) {
             CU(launch_build_lists(c->K, c->d_lists, c->d_list_counts, c->list_cap, c->stream));
             c->launches++;
@@ -557,6 +571,36 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
         Kl.list = c->d_lists + (size_t)cls * c->list_cap;
         Kl.list_count = c->d_list_counts + cls;
     }
+    auto run_stage = [&](const PassK &Kq) -> cudaError_t {
+        static const bool legacy = [] { const char *e = getenv("APDE_LEGACY_SWEEP"); return e && e[0] == '1'; }();
+        if (pipeline) {
+            cudaError_t e = c->prop.reserve(c->list_cap, Kq.N);
+            if (e != cudaSuccess) return e;
+            const int ylimit = std::min(Kq.H, 32 * (((Kq.H / 2) + 15) / 16));
+            const int max_pixels = (Kq.W * ylimit + 1) / 2 + 1;
+            return prop_half_sweep(Kq, c->prop, stage == APDE_STAGE_PROP_WEAK, Kq.list, Kq.list_count, max_pixels, iter, c->stream,
+                                   &c->launches);
+        }
+        if (!legacy && !getenv("APDE_QUAD_KERNELS")) {
+            if (stage == APDE_STAGE_DEPTH_TO_WEAK) {
+                cudaError_t e = sweep_build(Kq, c->sweep, 1, c->stream, &c->launches);
+                if (e != cudaSuccess) return e;
+                c->sweep.valid = true;
+                return sweep_classify(Kq, c->sweep, nullptr, c->stream);
+            }
+            if (stage == APDE_STAGE_LOCAL_REFINE) {
+                if (!c->sweep.valid) {
+                    cudaError_t e = sweep_build(Kq, c->sweep, 0, c->stream, &c->launches);
+                    if (e != cudaSuccess) return e;
+                }
+                c->sweep.valid = false;
+                return sweep_refine(Kq, c->sweep, c->stream);
+            }
+        }
+        return launch_stage(Kq, stage, iter, color, c->stream, nullptr);
+    };
+    // the stored column costs stay valid only across ConfidenceCompute (it touches neither planes nor view weights)
+    if (stage != APDE_STAGE_DEPTH_TO_WEAK && stage != APDE_STAGE_LOCAL_REFINE && stage != APDE_STAGE_CONFIDENCE) c->sweep.valid = false;
     if (c->profiling) {
         const size_t k = c->ev_stage.size();
         while (c->ev_pool.size() < 2 * (k + 1)) {
@@ -565,11 +609,11 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
             c->ev_pool.push_back(e);
         }
         CU(cudaEventRecord(c->ev_pool[2 * k], c->stream));
-        CU(launch_stage(Kl, stage, iter, color, c->stream, nullptr));
+        CU(run_stage(Kl));
         CU(cudaEventRecord(c->ev_pool[2 * k + 1], c->stream));
         c->ev_stage.push_back(stage);
     } else {
-        CU(launch_stage(Kl, stage, iter, color, c->stream, nullptr));
+        CU(run_stage(Kl));
     }
     c->launches++;
     c->stage_launches[stage]++;
@@ -714,6 +758,7 @@ int apde_problem_set(apde_context *c, int field, const void *host, size_t bytes)
     }
     if (field == APDE_FIELD_IMAGE) return fail(APDE_ERR_ARG, "problem_set: field is read only");
     if (field == APDE_FIELD_WEAK_INFO) c->lists_dirty = true;
+    c->sweep.valid = false;
     void *ptr; size_t need;
     int rc = field_ptr(c, field, &ptr, &need);
     if (rc) return rc;

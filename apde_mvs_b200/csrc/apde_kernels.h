@@ -18,6 +18,57 @@ int prop_block_threads(int N);
 // compacted (colour, strong | weak) pixel lists for the checkerboard kernels: lists = 4 x cap ints, counts = 4 ints
 cudaError_t launch_build_lists(const PassK &K, int *lists, int *counts, int cap, cudaStream_t st);
 
+// red/black propagation as a pipeline of balanced column kernels (apde_prop.cu)
+struct PropK {  // device view of the workspace, passed by value
+    const int *list;      // compacted pixel list of the (colour, class) being swept
+    const int *count;
+    int cap;              // row stride of every per-pixel array below
+    int *cand_pos;        // [8][cap]
+    uint32_t *cand_flags; // [cap]  bits 0-7: candidate usable, bits 8-15: anchor present (weak)
+    float *cost1;         // [9][N][cap] phase-1 costs (8 candidates + current plane)
+    float4 *plane_now;    // [cap] state after the candidate choice
+    float *depth_now, *cost_now, *cost_written, *wnorm;
+    uint32_t *wmask;
+    uint8_t *nh;          // [cap] number of refinement hypotheses (0 / 5 / 11)
+    float4 *hyp;          // [11][cap]
+    float *refpatch;      // [38][cap] reference patch texels + mean + variance
+    int *flags3, *colidx3, *colmap3;  // (pixel, selected view) columns: flags [N][cap], their prefix sum, column -> flat
+    float *cost3;         // [11][N * cap]
+};
+struct PropWorkspace {
+    int cap = 0, views = 0;
+    int *cand_pos = nullptr, *flags3 = nullptr, *colidx3 = nullptr, *colmap3 = nullptr;
+    uint32_t *cand_flags = nullptr, *wmask = nullptr;
+    float *cost1 = nullptr, *depth_now = nullptr, *cost_now = nullptr, *cost_written = nullptr, *wnorm = nullptr, *cost3 = nullptr;
+    float4 *plane_now = nullptr, *hyp = nullptr;
+    float *refpatch = nullptr;
+    uint8_t *nh = nullptr;
+    void *scan_tmp = nullptr;
+    size_t scan_bytes = 0;
+    cudaError_t reserve(int cap, int N);
+    void release();
+};
+cudaError_t prop_half_sweep(const PassK &K, PropWorkspace &ws, bool weak, const int *list, const int *count, int max_pixels, int iter,
+                            cudaStream_t st, uint64_t *launches);
+
+// DepthToWeak + LocalRefine as a balanced (pixel, view) column workload (apde_sweep.cu)
+struct SweepWorkspace {
+    int *flags = nullptr, *colidx = nullptr;  // [N][P] view-major column flags and their exclusive prefix sum
+    int *colmap = nullptr;                     // [ncols] column -> flat (view, pixel)
+    size_t map_cap = 0;
+    void *scan_tmp = nullptr;
+    size_t scan_bytes = 0, flag_cap = 0, col_cap = 0, geo_cap = 0;
+    float *ncc = nullptr, *geo = nullptr;      // [62][ncols] column costs (slot 61 = the current depth)
+    int ncols = 0;
+    bool valid = false;                        // columns match the problem state (set by DepthToWeak, used by LocalRefine)
+    cudaError_t reserve_flags(size_t n);
+    cudaError_t reserve_columns(size_t ncols, bool geom);
+    void release();
+};
+cudaError_t sweep_build(const PassK &K, SweepWorkspace &ws, int dtw, cudaStream_t st, uint64_t *launches);
+cudaError_t sweep_classify(const PassK &K, SweepWorkspace &ws, float *curve, cudaStream_t st);
+cudaError_t sweep_refine(const PassK &K, SweepWorkspace &ws, cudaStream_t st);
+
 // scene / map kernels (apde_maps.cu)
 // OpenCV INTER_LINEAR resize of a u8 image to float (APD.cpp:574): dst[h][w] from src[H][W]
 cudaError_t launch_resize_linear_u8(const uint8_t *src, int W, int H, float *dst, int w, int h, cudaStream_t st);

@@ -1,0 +1,479 @@
+// apde_prop.cu -- red/black propagation (strong AND weak pixels) as a pipeline of balanced kernels.  sm_100a.
+//
+// The reference runs CheckerboardPropagation{Strong,Weak} + PlaneHypothesisRefinement{Strong,Weak} (APD.cu:1098-1615,
+// 950-1096) as one fat thread per pixel: 8N + N + 5N sequential cost evaluations, 1.7-2 KB of local arrays, and (measured
+// on B200, r01) two problems for a one-thread-per-pixel port: warps wait for their pixel with the most selected views,
+// and the weak kernel has so few pixels that a launch is a handful of long serial threads (4 % of the texture roofline).
+// Here a half-sweep is
+//   P0  k_prop_candidates   per pixel : the 8 candidate positions (adaptive checkerboard / anchors)
+//   P1  k_prop_eval1        per (pixel, view) COLUMN, all N views: 8 candidate costs + the current plane's cost
+//   P2  k_prop_select       per pixel : joint view selection, candidate choice, refinement hypotheses (counter RNG)
+//       prefix sum + scatter: number the (pixel, selected view) columns view-major
+//   P3  k_prop_eval3        per (pixel, SELECTED view) column: the refinement hypotheses (+ geometric term)
+//   P4  k_prop_final        per pixel : weighted sums in the reference order, accept / write back
+// Every evaluation kernel has one thread per column: all lanes of a warp work on the SAME source view, on neighbouring
+// pixels, with identical trip counts; the parallelism is N x larger than one thread per pixel.  Sums over views are formed
+// per pixel in ascending view order, so results are identical to the per-pixel formulation (zero-weight views contribute
+// exactly 0 in the reference's sums: costs are finite by construction).
+#include <cub/cub.cuh>
+
+#include <cfloat>
+
+#include "apde_common.cuh"
+#include "apde_kernels.h"
+
+namespace apde {
+
+constexpr int kH1 = 9;  // phase-1 hypotheses per column: 8 candidates + the current plane
+
+__device__ __forceinline__ bool prop_pixel(const PassK &K, const PropK &B, int pix, int &px, int &py, int &center) {
+    if (pix >= *B.count) return false;
+    center = B.list[pix];
+    px = center % K.W;
+    py = center / K.W;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ P0 candidates
+template <bool WEAK>
+__global__ void __launch_bounds__(128) k_prop_candidates(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    int px, py, center;
+    if (!prop_pixel(K, B, pix, px, py, center)) return;
+    int pos[8];
+    unsigned flags = 0, valid = 0;
+    if (!WEAK) {
+        flags = checkerboard_candidates(K.costs, K.W, K.H, px, py, pos);
+    } else {
+        // candidates = the planes of the 8 anchors that are still STRONG (APD.cu:1471-1482)
+        const short2 *anc = K.anchors + (size_t)center * APDE_ANCHOR_NUM;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const short2 a = anc[h + 1];
+            pos[h] = 0;
+            if (!(a.x == -1 || a.y == -1)) {
+                valid |= 1u << h;
+                pos[h] = a.x + a.y * K.W;
+                if (K.weak[pos[h]] == APDE_STRONG) flags |= 1u << h;
+            }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 8; ++h) B.cand_pos[(size_t)h * B.cap + pix] = pos[h];
+    B.cand_flags[pix] = flags | (valid << 8);
+    // the reference patch is gathered ONCE per pixel and half-sweep; the column kernels re-load it with coalesced LDGs
+    // (one column per thread would otherwise spend 36 texture fetches per column on it)
+    RefPatch rp;
+    load_ref_patch(K, px, py, rp);
+#pragma unroll
+    for (int k = 0; k < kPatch; ++k) B.refpatch[(size_t)k * B.cap + pix] = rp.r[k];
+    B.refpatch[(size_t)kPatch * B.cap + pix] = rp.mean;
+    B.refpatch[(size_t)(kPatch + 1) * B.cap + pix] = rp.var;
+}
+
+__device__ __forceinline__ void load_ref_patch_g(const PropK &B, int pix, RefPatch &rp) {
+#pragma unroll
+    for (int k = 0; k < kPatch; ++k) rp.r[k] = B.refpatch[(size_t)k * B.cap + pix];
+    rp.mean = B.refpatch[(size_t)kPatch * B.cap + pix];
+    rp.var = B.refpatch[(size_t)(kPatch + 1) * B.cap + pix];
+}
+
+// ------------------------------------------------------------------------------------------------ P1 phase-1 columns
+template <bool WEAK>
+__global__ void __launch_bounds__(128) k_prop_eval1(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    int px, py, center;
+    if (!prop_pixel(K, B, pix, px, py, center)) return;
+    const int N = K.N;
+    const ViewK &vk = K.v[v];  // warp-uniform: served from the constant bank
+    RefPatch rp;
+    load_ref_patch_g(B, pix, rp);
+    AnchorRef ar;
+    if (WEAK) load_anchor_ref(K, K.anchors + (size_t)center * APDE_ANCHOR_NUM, ar);
+    const unsigned flags = B.cand_flags[pix] & 0xffu;
+    unsigned n_eval = 0;
+#pragma unroll 1
+    for (int h = 0; h < kH1; ++h) {
+        float c;
+        if (h == 8 || ((flags >> h) & 1u)) {
+            const float4 pl = (h == 8) ? K.planes[center] : K.planes[B.cand_pos[(size_t)h * B.cap + pix]];
+            const float3 m = plane_row(K, pl);
+            c = WEAK ? ncc_new(K, vk, v, px, py, m, rp, ar) : ncc_old(K, vk, px, py, m, rp);
+            n_eval++;
+        } else {
+            c = (h == 0 && v == 0) ? 2.0f : 0.0f;  // quirk 2: "cost_array[8][32] = {2.0f}" zero-fills all but [0][0]
+        }
+        B.cost1[((size_t)h * N + v) * B.cap + pix] = c;
+    }
+    count_evals(K, WEAK ? 0 : n_eval, WEAK ? n_eval : 0, 0);
+}
+
+// ------------------------------------------------------------------------------------------------ P2 selection
+// joint view selection (APD.cu:1339-1386 / 1505-1552) on the stored phase-1 costs
+template <int NBR>
+__device__ __forceinline__ uint4 select_views_g(const PassK &K, const float *sc, size_t stride, const uint32_t (&nbr_sel)[NBR],
+                                                unsigned nbr_valid, int iter, Rng &rng, uint32_t *selmask, float *wnorm) {
+    const int N = K.N;
+    const float cost_threshold = (float)(0.8 * (double)__expf((float)(iter * iter) / (-90.0f)));
+    const float fallback = __expf(cost_threshold * cost_threshold / (-0.32f));
+    float sp[kMaxSrc];
+    float psum = 0.0f;
+    for (int v = 0; v < N; ++v) {
+        float cnt = 0.0f, tmpw = 0.0f;
+        int cnt_false = 0;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const float c = sc[((size_t)h * N + v) * stride];
+            if (c < cost_threshold) { tmpw += __expf(c * c / (-0.18f)); cnt += 1.0f; }
+            if (c > 1.2f) cnt_false++;
+        }
+        float p = 0.0f;
+        if (cnt > 2.0f && cnt_false < 3) p = tmpw / cnt;
+        else if (cnt_false < 3) p = fallback;
+        float prior = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NBR; ++i)
+            if ((nbr_valid >> i) & 1u) prior += ((nbr_sel[i] >> v) & 1u) ? 0.9f : 0.1f;
+        p *= prior;
+        sp[v] = p;
+        psum += p;
+    }
+    const float inv = 1.0f / psum;  // TransformPDFToCDF, APD.cu:174-188
+    float cum = 0.0f;
+    for (int v = 0; v < N; ++v) { cum += sp[v] * inv; sp[v] = cum; }
+    uint4 w = make_uint4(0, 0, 0, 0);
+    for (int s = 0; s < 15; ++s) {
+        const float r = rng.uniform() - FLT_EPSILON;
+        for (int v = 0; v < N; ++v) {
+            if (sp[v] > r) { vw_inc(w, v); break; }
+        }
+    }
+    uint32_t mask = 0;
+    float wn = 0.0f;
+    for (int v = 0; v < N; ++v) {
+        const uint32_t wv = vw_get(w, v);
+        if (wv > 0) { mask |= 1u << v; wn += (float)wv; }
+    }
+    *selmask = mask;
+    *wnorm = wn;
+    return w;
+}
+
+// the five random refinement hypotheses built from (plane_now, depth_now); draws come from the caller (APD.cu:968-980)
+__device__ __forceinline__ void refinement_set(const PassK &K, int px, int py, float4 plane_now, float depth_now, float depth_rand,
+                                               float4 n_rand, float u_pert, float u1, float u2, float u3, float4 *out /* [5] */) {
+    const float lo = (1.0f - 0.02f) * depth_now, hi = (1.0f + 0.02f) * depth_now;
+    const float depth_pert = u_pert * (hi - lo) + lo;  // the do-while can never repeat (quirk 6)
+    // GeneratePerturbedNormal (APD.cu:270-305) with the three uniforms already drawn
+    const float perturbation = (float)(0.02 * 3.14159265358979323846);
+    const float3 vd = view_direction(K, px, py, 1.0f);
+    const float a1 = (u1 - 0.5f) * perturbation, a2 = (u2 - 0.5f) * perturbation, a3 = (u3 - 0.5f) * perturbation;
+    float s1, c1, s2, c2, s3, c3;
+    sincosf(a1, &s1, &c1); sincosf(a2, &s2, &c2); sincosf(a3, &s3, &c3);
+    const float r0 = c2 * c3, r1 = c3 * s1 * s2 - c1 * s3, r2 = s1 * s3 + c1 * c3 * s2;
+    const float r3 = c2 * s3, r4 = c1 * c3 + s1 * s2 * s3, r5 = c1 * s2 * s3 - c3 * s1;
+    const float r6 = -s2, r7 = c2 * s1, r8 = c1 * c2;
+    float4 n_pert = make_float4(r0 * plane_now.x + r1 * plane_now.y + r2 * plane_now.z, r3 * plane_now.x + r4 * plane_now.y + r5 * plane_now.z,
+                                r6 * plane_now.x + r7 * plane_now.y + r8 * plane_now.z, 0.0f);
+    if (n_pert.x * vd.x + n_pert.y * vd.y + n_pert.z * vd.z >= 0.0f) n_pert = plane_now;
+    normalize3(n_pert);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        float4 tp = (i == 0 || i == 4) ? plane_now : (i == 3 ? n_pert : n_rand);
+        const float d = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : depth_now);
+        tp.w = distance_to_origin(K, px, py, d, tp);
+        out[i] = tp;
+    }
+}
+
+template <bool WEAK>
+__global__ void __launch_bounds__(128) k_prop_select(const __grid_constant__ PassK K, const __grid_constant__ PropK B, int iter) {
+    extern __shared__ float smem[];
+    const ViewK *s_vk = stage_views(K, smem);
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    int px, py, center;
+    if (!prop_pixel(K, B, pix, px, py, center)) return;
+    const int W = K.W, N = K.N;
+    const size_t cap = B.cap;
+    const float *sc = B.cost1 + pix;
+    const unsigned cf = B.cand_flags[pix];
+    const unsigned flags = cf & 0xffu;
+    unsigned n_geom = 0;
+
+    Rng rng(K.seed, K.stream, (uint32_t)center, (WEAK ? SITE_WEAK : SITE_STRONG) + iter);
+    uint32_t wmask;
+    float wnorm;
+    uint4 w;
+    if (!WEAK) {
+        uint32_t nbr_sel[4];
+        const unsigned nbr_valid = ((flags >> 0) & 1u) | (((flags >> 2) & 1u) << 1) | (((flags >> 4) & 1u) << 2) |
+                                   (((flags >> 6) & 1u) << 3);
+        nbr_sel[0] = (nbr_valid & 1u) ? K.sel[center - W] : 0u;
+        nbr_sel[1] = (nbr_valid & 2u) ? K.sel[center + W] : 0u;
+        nbr_sel[2] = (nbr_valid & 4u) ? K.sel[center - 1] : 0u;
+        nbr_sel[3] = (nbr_valid & 8u) ? K.sel[center + 1] : 0u;
+        w = select_views_g<4>(K, sc, cap, nbr_sel, nbr_valid, iter, rng, &wmask, &wnorm);
+    } else {
+        uint32_t nbr_sel[8];
+        const unsigned anchor_valid = (cf >> 8) & 0xffu;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) nbr_sel[h] = ((anchor_valid >> h) & 1u) ? K.sel[B.cand_pos[(size_t)h * cap + pix]] : 0u;
+        w = select_views_g<8>(K, sc, cap, nbr_sel, anchor_valid, iter, rng, &wmask, &wnorm);
+    }
+    K.vw[center] = w;
+    for (int v = 0; v < N; ++v) B.flags3[(size_t)v * cap + pix] = (wmask >> v) & 1u;
+
+    // weighted candidate costs; weak candidates carry the geometric term whenever geom_consistency (quirk 4)
+    const bool geom_cand = WEAK && K.geom;
+    const bool geom_now = WEAK ? (K.geom != 0) : (K.geom && K.impetus);
+    float fc_min = 0.0f;
+    int min_idx = 0;
+#pragma unroll 1
+    for (int h = 0; h < 8; ++h) {
+        const bool fl = (flags >> h) & 1u;
+        float4 pl = make_float4(0, 0, 0, 0);
+        if (geom_cand && fl) pl = K.planes[B.cand_pos[(size_t)h * cap + pix]];
+        float acc = 0.0f;
+        for (uint32_t mk = wmask; mk; mk &= mk - 1) {
+            const int v = __ffs(mk) - 1;
+            const float c = sc[((size_t)h * N + v) * cap];
+            const float wv = (float)vw_get(w, v);
+            if (geom_cand) {
+                if (fl) { acc += wv * (c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, pl)); n_geom++; }
+                else acc += wv * (c + K.geom_factor * 3.0f);
+            } else {
+                acc += wv * c;
+            }
+        }
+        const float fc = acc / wnorm;
+        if (h == 0 || fc <= fc_min) { fc_min = fc; min_idx = h; }  // FindMinCostIndex: ties -> last (quirk 3)
+    }
+    // current hypothesis on the selected views (its costs were evaluated as hypothesis 8 of phase 1)
+    const float4 plane_c = K.planes[center];
+    float cost_now;
+    {
+        float acc = 0.0f;
+        for (uint32_t mk = wmask; mk; mk &= mk - 1) {
+            const int v = __ffs(mk) - 1;
+            float c = sc[((size_t)8 * N + v) * cap];
+            if (geom_now) { c = c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, plane_c); n_geom++; }
+            acc += (float)vw_get(w, v) * c;
+        }
+        cost_now = acc / wnorm;
+    }
+    const float cost_written = cost_now;  // costs[center] is overwritten before the REFINE_INIT test (quirk 5)
+    float4 plane_now = plane_c;
+    float depth_now = depth_from_plane(K, plane_c, px, py);
+    if ((flags >> min_idx) & 1u) {
+        const float4 cand = K.planes[B.cand_pos[(size_t)min_idx * cap + pix]];
+        const float db = depth_from_plane(K, cand, px, py);
+        if (db >= K.depth_min && db <= K.depth_max && fc_min < cost_now) {
+            depth_now = db; plane_now = cand; cost_now = fc_min;
+            K.sel[center] = wmask;
+        }
+    }
+    B.plane_now[pix] = plane_now;
+    B.depth_now[pix] = depth_now;
+    B.cost_now[pix] = cost_now;
+    B.cost_written[pix] = cost_written;
+    B.wnorm[pix] = wnorm;
+    B.wmask[pix] = wmask;
+
+    // refinement hypotheses.  All draws happen here so that the counter RNG stream of (pixel, site) stays sequential.
+    int nh = 5;
+    float4 fitp = make_float4(0, 0, 0, 0);
+    if (WEAK) {
+        fitp = K.fit[center];
+        if (fitp.x == 0 && fitp.y == 0 && fitp.z == 0) nh = 0;  // a zero fit plane skips the random refinement too (APD.cu:1028)
+        else nh = 11;
+    }
+    B.nh[pix] = (uint8_t)nh;
+    if (nh == 0) {
+        for (int v = 0; v < N; ++v) B.flags3[(size_t)v * cap + pix] = 0;  // no phase-3 columns for this pixel
+    } else {
+        const float depth_rand = rng.uniform() * (K.depth_max - K.depth_min) + K.depth_min;
+        const float4 n_rand = random_normal(K, px, py, rng, depth_now);  // direction only: independent of the depth's value
+        const float u_pert = rng.uniform();
+        const float u1 = rng.uniform(), u2 = rng.uniform(), u3 = rng.uniform();
+        float4 hyp[5];
+        if (!WEAK) {
+            refinement_set(K, px, py, plane_now, depth_now, depth_rand, n_rand, u_pert, u1, u2, u3, hyp);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) B.hyp[(size_t)i * cap + pix] = hyp[i];
+        } else {
+            // the five random hypotheses depend on whether the fit plane gets accepted first (APD.cu:1046-1067): both
+            // variants are evaluated, P4 picks the set that matches the outcome of the fit test
+            B.hyp[pix] = fitp;
+            refinement_set(K, px, py, plane_now, depth_now, depth_rand, n_rand, u_pert, u1, u2, u3, hyp);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) B.hyp[(size_t)(1 + i) * cap + pix] = hyp[i];
+            const float dfit = depth_from_plane(K, fitp, px, py);
+            refinement_set(K, px, py, fitp, dfit, depth_rand, n_rand, u_pert, u1, u2, u3, hyp);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) B.hyp[(size_t)(6 + i) * cap + pix] = hyp[i];
+        }
+    }
+    count_evals(K, 0, 0, n_geom);
+}
+
+// column number -> flat (view, pixel) index
+__global__ void __launch_bounds__(256) k_prop_scatter(const int *__restrict__ flags, const int *__restrict__ colidx, size_t nflat,
+                                                      int *__restrict__ colmap) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nflat && flags[i]) colmap[colidx[i]] = (int)i;
+}
+
+// ------------------------------------------------------------------------------------------------ P3 phase-3 columns
+template <bool WEAK>
+__global__ void __launch_bounds__(128) k_prop_eval3(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
+    extern __shared__ float smem[];
+    const ViewK *s_vk = stage_views(K, smem);
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t cap = B.cap;
+    const size_t nflat = (size_t)K.N * cap;
+    if (col >= B.colidx3[nflat]) return;  // total number of columns = the scan's last element
+    const int flat = B.colmap3[col];
+    const int v = flat / (int)cap, pix = flat % (int)cap;
+    const int center = B.list[pix];
+    const int px = center % K.W, py = center / K.W;
+    const ViewK &vk = s_vk[v];
+    RefPatch rp;
+    load_ref_patch_g(B, pix, rp);
+    AnchorRef ar;
+    if (WEAK) load_anchor_ref(K, K.anchors + (size_t)center * APDE_ANCHOR_NUM, ar);
+    const bool geom = WEAK ? (K.geom != 0) : (K.geom && K.impetus);
+    const int nh = WEAK ? 11 : 5;
+    unsigned n_eval = 0, n_geom = 0;
+#pragma unroll 1
+    for (int i = 0; i < nh; ++i) {
+        const float4 tp = B.hyp[(size_t)i * cap + pix];
+        const float3 m = plane_row(K, tp);
+        float c = WEAK ? ncc_new(K, vk, v, px, py, m, rp, ar) : ncc_old(K, vk, px, py, m, rp);
+        n_eval++;
+        if (geom) { c = c + K.geom_factor * geom_cost(K, vk, v, px, py, tp); n_geom++; }
+        B.cost3[(size_t)i * nflat + col] = c;
+    }
+    count_evals(K, WEAK ? 0 : n_eval, WEAK ? n_eval : 0, n_geom);
+}
+
+// ------------------------------------------------------------------------------------------------ P4 final decision
+template <bool WEAK>
+__global__ void __launch_bounds__(128) k_prop_final(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    int px, py, center;
+    if (!prop_pixel(K, B, pix, px, py, center)) return;
+    const size_t cap = B.cap;
+    const size_t nflat = (size_t)K.N * cap;
+    float4 plane_now = B.plane_now[pix];
+    float depth_now = B.depth_now[pix], cost_now = B.cost_now[pix];
+    const float cost_written = B.cost_written[pix], wnorm = B.wnorm[pix];
+    const uint32_t wmask = B.wmask[pix];
+    const uint4 w = K.vw[center];
+    const float dmin = K.depth_min, dmax = K.depth_max;
+    const int nh = B.nh[pix];
+    auto weighted = [&](int i) {
+        float acc = 0.0f;
+        for (uint32_t mk = wmask; mk; mk &= mk - 1) {
+            const int v = __ffs(mk) - 1;
+            acc += (float)vw_get(w, v) * B.cost3[(size_t)i * nflat + B.colidx3[(size_t)v * cap + pix]];
+        }
+        return acc / wnorm;
+    };
+    auto try_hyp = [&](int i) {
+        const float4 tp = B.hyp[(size_t)i * cap + pix];
+        const float tc = weighted(i);
+        const float db = depth_from_plane(K, tp, px, py);
+        if (db >= dmin && db <= dmax && tc < cost_now) { depth_now = db; plane_now = tp; cost_now = tc; return true; }
+        return false;
+    };
+    if (!WEAK) {
+        for (int i = 0; i < 5; ++i) try_hyp(i);
+    } else if (nh > 0) {
+        const bool fit_taken = try_hyp(0);
+        const int base = fit_taken ? 6 : 1;
+        for (int i = 0; i < 5; ++i) try_hyp(base + i);
+    }
+    if (K.state == APDE_REFINE_INIT) {
+        if ((double)cost_now < (double)cost_written - 0.1) { K.costs[center] = cost_now; K.planes[center] = plane_now; }
+        else K.costs[center] = cost_written;
+    } else {
+        K.costs[center] = cost_now;
+        K.planes[center] = plane_now;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+#define PCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
+
+cudaError_t PropWorkspace::reserve(int cap_, int N) {
+    if (cap_ <= cap && N <= views) return cudaSuccess;
+    release();
+    cap = cap_; views = N;
+    const size_t c = (size_t)cap, nflat = (size_t)N * c;
+    PCU(cudaMalloc(&cand_pos, 8 * c * sizeof(int)));
+    PCU(cudaMalloc(&cand_flags, c * sizeof(uint32_t)));
+    PCU(cudaMalloc(&cost1, (size_t)kH1 * nflat * sizeof(float)));
+    PCU(cudaMalloc(&plane_now, c * sizeof(float4)));
+    PCU(cudaMalloc(&depth_now, c * sizeof(float)));
+    PCU(cudaMalloc(&cost_now, c * sizeof(float)));
+    PCU(cudaMalloc(&cost_written, c * sizeof(float)));
+    PCU(cudaMalloc(&wnorm, c * sizeof(float)));
+    PCU(cudaMalloc(&wmask, c * sizeof(uint32_t)));
+    PCU(cudaMalloc(&nh, c));
+    PCU(cudaMalloc(&hyp, 11 * c * sizeof(float4)));
+    PCU(cudaMalloc(&refpatch, (size_t)(kPatch + 2) * c * sizeof(float)));
+    PCU(cudaMalloc(&flags3, (nflat + 1) * sizeof(int)));
+    PCU(cudaMalloc(&colidx3, (nflat + 1) * sizeof(int)));
+    PCU(cudaMalloc(&colmap3, nflat * sizeof(int)));
+    PCU(cudaMalloc(&cost3, 11 * nflat * sizeof(float)));
+    scan_bytes = 0;
+    PCU(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, flags3, colidx3, (int)(nflat + 1)));
+    PCU(cudaMalloc(&scan_tmp, scan_bytes));
+    PCU(cudaMemset(flags3, 0, (nflat + 1) * sizeof(int)));
+    return cudaSuccess;
+}
+void PropWorkspace::release() {
+    cudaFree(cand_pos); cudaFree(cand_flags); cudaFree(cost1); cudaFree(plane_now); cudaFree(depth_now); cudaFree(cost_now);
+    cudaFree(cost_written); cudaFree(wnorm); cudaFree(wmask); cudaFree(nh); cudaFree(hyp); cudaFree(flags3); cudaFree(colidx3);
+    cudaFree(colmap3); cudaFree(cost3); cudaFree(scan_tmp); cudaFree(refpatch);
+    refpatch = nullptr;
+    cand_pos = flags3 = colidx3 = colmap3 = nullptr; cand_flags = wmask = nullptr; cost1 = depth_now = cost_now = cost_written = wnorm = cost3 = nullptr;
+    plane_now = hyp = nullptr; nh = nullptr; scan_tmp = nullptr; cap = 0; views = 0;
+}
+
+template <bool WEAK>
+static cudaError_t run_half_sweep(const PassK &K, PropWorkspace &ws, const int *list, const int *count, int max_pixels, int iter,
+                                  cudaStream_t st, uint64_t *launches) {
+    PropK B;
+    B.list = list; B.count = count; B.cap = ws.cap;
+    B.cand_pos = ws.cand_pos; B.cand_flags = ws.cand_flags; B.cost1 = ws.cost1; B.plane_now = ws.plane_now;
+    B.depth_now = ws.depth_now; B.cost_now = ws.cost_now; B.cost_written = ws.cost_written; B.wnorm = ws.wnorm; B.wmask = ws.wmask;
+    B.nh = ws.nh; B.hyp = ws.hyp; B.refpatch = ws.refpatch; B.flags3 = ws.flags3; B.colidx3 = ws.colidx3; B.colmap3 = ws.colmap3; B.cost3 = ws.cost3;
+    const int N = K.N;
+    const size_t nflat = (size_t)N * ws.cap;
+    const unsigned pb = (unsigned)((max_pixels + 127) / 128);
+    const size_t vsm = sizeof(float) * views_smem_floats(N);
+    if (pb == 0) return cudaSuccess;
+    k_prop_candidates<WEAK><<<pb, 128, 0, st>>>(K, B);
+    k_prop_eval1<WEAK><<<dim3(pb, N), 128, 0, st>>>(K, B);
+    // flags3 of pixels beyond the list (previous, longer half-sweeps) must not create columns
+    PCU(cudaMemsetAsync(ws.flags3, 0, (nflat + 1) * sizeof(int), st));
+    k_prop_select<WEAK><<<pb, 128, vsm, st>>>(K, B, iter);
+    PCU(cub::DeviceScan::ExclusiveSum(ws.scan_tmp, ws.scan_bytes, ws.flags3, ws.colidx3, (int)(nflat + 1), st));
+    k_prop_scatter<<<(unsigned)((nflat + 255) / 256), 256, 0, st>>>(ws.flags3, ws.colidx3, nflat, ws.colmap3);
+    // worst case: every (pixel, view) is a column; threads beyond the device-side count exit at once
+    const size_t max_cols = (size_t)max_pixels * N;
+    k_prop_eval3<WEAK><<<(unsigned)((max_cols + 127) / 128), 128, vsm, st>>>(K, B);
+    k_prop_final<WEAK><<<pb, 128, 0, st>>>(K, B);
+    if (launches) *launches += 8;
+    return cudaGetLastError();
+}
+
+cudaError_t prop_half_sweep(const PassK &K, PropWorkspace &ws, bool weak, const int *list, const int *count, int max_pixels, int iter,
+                            cudaStream_t st, uint64_t *launches) {
+    return weak ? run_half_sweep<true>(K, ws, list, count, max_pixels, iter, st, launches)
+                : run_half_sweep<false>(K, ws, list, count, max_pixels, iter, st, launches);
+}
+
+}  // namespace apde

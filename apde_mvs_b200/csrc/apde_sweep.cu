@@ -1,0 +1,293 @@
+// apde_sweep.cu -- DepthToWeak (APD.cu:2103-2250) and LocalRefine (APD.cu:2346-2432) as a balanced column workload.
+//
+// Both kernels of the reference sweep the depth of a pixel along the viewing ray (disparity steps of one pixel, +-30 and
+// +-5) and sum, over the pixel's SELECTED views in ascending order, view-weighted NCC (+ geometric) costs.  One thread
+// per pixel makes every warp wait for its pixel with the most selected views and mixes source views inside a warp.  Here
+//   1. k_sweep_prepare   marks (pixel, view) columns;                         a prefix sum numbers them VIEW-MAJOR;
+//   2. k_sweep_columns   one thread = one column: 61 sweep evaluations + the evaluation at the current depth;
+//                        a warp holds 32 neighbouring pixels of the SAME source view, every lane does the same work;
+//   3. k_sweep_classify  (DepthToWeak) / k_sweep_refine (LocalRefine): one thread per pixel adds its columns in the
+//                        reference order and applies the reference's decision logic.
+// LocalRefine's 11 sweep samples are a subset of DepthToWeak's 61 (same plane, same views, same weights; only
+// ConfidenceCompute runs in between and it touches neither), so the second stage re-uses the stored column costs and
+// only the evaluation at the current depth is new: 12 S evaluations per pixel become 0 extra.
+#include <cub/cub.cuh>
+
+#include "apde_common.cuh"
+#include "apde_kernels.h"
+
+namespace apde {
+
+constexpr int kSweepR = 30, kSweepN = 61, kSlots = 62;  // slot 61 = the hypothesis at the current depth (LocalRefine's cost_now)
+
+// class of a pixel for the sweep: 0 = none, 1 = LocalRefine only (+-5), 2 = DepthToWeak + LocalRefine (+-30)
+__device__ __forceinline__ int sweep_class(const PassK &K, int px, int py, int center, bool dtw) {
+    const float w = K.planes[center].w;  // rotating the normal does not touch w (APD.cu:2127-2129)
+    if (w == 0.0f || K.sel[center] == 0u) return 0;
+    const int m = 6;
+    const bool border = px < m || py < m || px >= K.W - m || py >= K.H - m;
+    return (dtw && !border) ? 2 : 1;
+}
+
+__global__ void __launch_bounds__(256) k_sweep_prepare(const __grid_constant__ PassK K, int dtw, int *__restrict__ flags) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int P = K.W * K.H;
+    if (idx >= P) return;
+    const int px = idx % K.W, py = idx / K.W;
+    const int cls = sweep_class(K, px, py, idx, dtw != 0);
+    if (dtw && cls != 2) K.weak[idx] = APDE_UNKNOWN;  // border / zero depth / no selected view (APD.cu:2114-2153)
+    const uint32_t sel = cls ? K.sel[idx] : 0u;
+    for (int v = 0; v < K.N; ++v) flags[(size_t)v * P + idx] = (sel >> v) & 1u;
+}
+
+// column number -> flat (view, pixel) index
+__global__ void __launch_bounds__(256) k_sweep_scatter(const int *__restrict__ flags, const int *__restrict__ colidx, size_t nflat,
+                                                       int *__restrict__ colmap) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nflat && flags[i]) colmap[colidx[i]] = (int)i;
+}
+
+__global__ void __launch_bounds__(128) k_sweep_columns(const __grid_constant__ PassK K, int dtw, const int *__restrict__ colmap,
+                                                       int ncols, float *__restrict__ ncc, float *__restrict__ geo) {
+    extern __shared__ float smem[];
+    const ViewK *s_vk = stage_views(K, smem);
+    const int P = K.W * K.H;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    const int flat = colmap[col];
+    const int v = flat / P, center = flat % P;
+    const int px = center % K.W, py = center / K.W;
+    const int cls = sweep_class(K, px, py, center, dtw != 0);
+    const ViewK &vk = s_vk[v];
+    const float4 opl = normal_to_refcam(K, K.planes[center]);
+    const float origin_depth = opl.w;
+    // mean baseline over the selected views, ascending (APD.cu:2138-2155)
+    const uint32_t sel = K.sel[center];
+    float base_line = 0.0f;
+    int valid_src = 0;
+    for (uint32_t mk = sel; mk; mk &= mk - 1) { base_line += s_vk[__ffs(mk) - 1].baseline; valid_src++; }
+    base_line /= valid_src;
+    RefPatch rp;
+    load_ref_patch(K, px, py, rp);
+    unsigned n_old = 0, n_geom = 0;
+    const float fb = K.fx * base_line;
+    const float disp = fb / origin_depth;
+    const int r = (cls == 2) ? kSweepR : 5;
+#pragma unroll 1
+    for (int pd = -r; pd <= r; ++pd) {
+        const float p_depth = fb / (disp + pd);
+        if (p_depth < K.depth_min || p_depth > K.depth_max) continue;
+        float4 tp = opl;
+        tp.w = distance_to_origin(K, px, py, p_depth, tp);
+        const float3 m = plane_row(K, tp);
+        ncc[(size_t)(pd + kSweepR) * ncols + col] = ncc_old(K, vk, px, py, m, rp);
+        n_old++;
+        if (K.geom) { geo[(size_t)(pd + kSweepR) * ncols + col] = geom_cost(K, vk, v, px, py, tp); n_geom++; }
+    }
+    {
+        float4 tp = opl;
+        tp.w = distance_to_origin(K, px, py, origin_depth, tp);
+        const float3 m = plane_row(K, tp);
+        ncc[(size_t)kSweepN * ncols + col] = ncc_old(K, vk, px, py, m, rp);
+        n_old++;
+        if (K.geom) { geo[(size_t)kSweepN * ncols + col] = geom_cost(K, vk, v, px, py, tp); n_geom++; }
+    }
+    count_evals(K, n_old, 0, n_geom);
+}
+
+// DepthToWeak decision logic, APD.cu:2157-2249
+__global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ PassK K, const int *__restrict__ colidx, int ncols,
+                                                        const float *__restrict__ ncc, const float *__restrict__ geo,
+                                                        float *curve) {
+    extern __shared__ float smem[];
+    const ViewK *s_vk = stage_views(K, smem);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int P = K.W * K.H;
+    if (idx >= P) return;
+    const int px = idx % K.W, py = idx / K.W;
+    if (sweep_class(K, px, py, idx, true) != 2) return;
+    const float origin_depth = K.planes[idx].w;
+    const uint32_t sel = K.sel[idx];
+    const uint4 w = K.vw[idx];
+    float base_line = 0.0f, weight_normal = 0.0f;
+    int valid_src = 0;
+    for (uint32_t mk = sel; mk; mk &= mk - 1) {
+        const int v = __ffs(mk) - 1;
+        weight_normal += (float)vw_get(w, v);
+        base_line += s_vk[v].baseline;
+        valid_src++;
+    }
+    base_line /= valid_src;
+    const float fb = K.fx * base_line;
+    const float disp = fb / origin_depth;
+    const int radius = kSweepR, n = kSweepN;
+    float pc[kSweepN];
+#pragma unroll 1
+    for (int pd = -radius; pd <= radius; ++pd) {
+        const float p_depth = fb / (disp + pd);
+        if (p_depth < K.depth_min || p_depth > K.depth_max) { pc[pd + radius] = 2.0f; continue; }
+        float p_cost = 0.0f;
+        for (uint32_t mk = sel; mk; mk &= mk - 1) {
+            const int v = __ffs(mk) - 1;
+            const size_t o = (size_t)(pd + radius) * ncols + colidx[(size_t)v * P + idx];
+            float tc = ncc[o];
+            if (K.geom) tc += K.geom_factor * geo[o];
+            p_cost += tc * (float)vw_get(w, v);
+        }
+        p_cost /= weight_normal;
+        pc[pd + radius] = (2.0f > p_cost) ? p_cost : 2.0f;  // OpenCV MIN(2.0f, p_cost): NaN -> 2
+    }
+    if (curve) for (int i = 0; i < n; ++i) curve[(size_t)idx * n + i] = pc[i];
+    unsigned long long peaks = 0ull;
+    int peak_count = 0, min_peak = 0;
+    float min_cost = 2.0f;
+    for (int i = 2; i < n - 2; ++i) {
+        if (pc[i - 1] > pc[i] && pc[i + 1] > pc[i]) {
+            peaks |= 1ull << i;
+            peak_count++;
+            if (pc[i] < min_cost) { min_peak = i; min_cost = pc[i]; }
+        }
+    }
+    if (abs(min_peak - radius) > K.weak_peak_radius || pc[min_peak] > 0.5f) { K.weak[idx] = APDE_WEAK; return; }
+    if (peak_count == 1) { K.weak[idx] = (pc[min_peak] <= 0.15f) ? APDE_STRONG : APDE_WEAK; return; }
+    float var = 0.0f;
+    for (int i = 2; i < n - 2; ++i)
+        if (((peaks >> i) & 1ull) && i != min_peak) { const float d = pc[i] - min_cost; var += d * d; }
+    var = sqrtf(var);
+    var /= (peak_count - 1);
+    K.weak[idx] = (var > 0.2f) ? APDE_STRONG : APDE_WEAK;
+}
+
+// LocalRefine decision logic, APD.cu:2368-2431
+__global__ void __launch_bounds__(128) k_sweep_refine(const __grid_constant__ PassK K, const int *__restrict__ colidx, int ncols,
+                                                      const float *__restrict__ ncc, const float *__restrict__ geo) {
+    extern __shared__ float smem[];
+    const ViewK *s_vk = stage_views(K, smem);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int P = K.W * K.H;
+    if (idx >= P) return;
+    const int px = idx % K.W, py = idx / K.W;
+    if (sweep_class(K, px, py, idx, false) == 0) return;
+    const float origin_depth = K.planes[idx].w;
+    const uint32_t sel = K.sel[idx];
+    const uint4 w = K.vw[idx];
+    float cost_now = 0.0f, base_line = 0.0f, weight_normal = 0.0f;
+    int valid_src = 0;
+    for (uint32_t mk = sel; mk; mk &= mk - 1) {
+        const int v = __ffs(mk) - 1;
+        const size_t o = (size_t)kSweepN * ncols + colidx[(size_t)v * P + idx];
+        float tc = ncc[o];
+        if (K.geom) tc += K.geom_factor * geo[o];
+        const float wv = (float)vw_get(w, v);
+        cost_now += tc * wv;
+        weight_normal += wv;
+        base_line += s_vk[v].baseline;
+        valid_src++;
+    }
+    if (weight_normal == 0.0f) return;
+    cost_now /= weight_normal;
+    base_line /= valid_src;
+    const float fb = K.fx * base_line;
+    const float disp = fb / origin_depth;
+    float min_cost = 2.0f, best_depth = origin_depth;
+#pragma unroll 1
+    for (int pd = -5; pd <= 5; ++pd) {
+        const float p_depth = fb / (disp + pd);
+        if (p_depth < K.depth_min || p_depth > K.depth_max) continue;
+        float tc = 0.0f;
+        for (uint32_t mk = sel; mk; mk &= mk - 1) {
+            const int v = __ffs(mk) - 1;
+            const size_t o = (size_t)(pd + kSweepR) * ncols + colidx[(size_t)v * P + idx];
+            const float wv = (float)vw_get(w, v);
+            tc += ncc[o] * wv;
+            if (K.geom) tc += K.geom_factor * geo[o] * wv;
+        }
+        tc /= weight_normal;
+        if (tc < min_cost) { min_cost = tc; best_depth = p_depth; }
+    }
+    if ((double)(cost_now - min_cost) > 0.1) K.planes[idx].w = best_depth;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+cudaError_t SweepWorkspace::reserve_flags(size_t n) {
+    if (n <= flag_cap) return cudaSuccess;
+    cudaFree(flags); cudaFree(colidx); cudaFree(scan_tmp);
+    flags = colidx = nullptr; scan_tmp = nullptr;
+    cudaError_t e = cudaMalloc(&flags, (n + 1) * sizeof(int));
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMalloc(&colidx, (n + 1) * sizeof(int))) != cudaSuccess) return e;
+    scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, flags, colidx, (int)(n + 1));
+    if ((e = cudaMalloc(&scan_tmp, scan_bytes)) != cudaSuccess) return e;
+    flag_cap = n;
+    return cudaSuccess;
+}
+cudaError_t SweepWorkspace::reserve_columns(size_t ncols_, bool geom) {
+    const size_t need = ncols_ * kSlots;
+    if (ncols_ > map_cap) {
+        cudaFree(colmap);
+        colmap = nullptr;
+        cudaError_t e = cudaMalloc(&colmap, (ncols_ + ncols_ / 8) * sizeof(int));
+        if (e != cudaSuccess) return e;
+        map_cap = ncols_ + ncols_ / 8;
+    }
+    if (need > col_cap) {
+        cudaFree(ncc); cudaFree(geo);
+        ncc = geo = nullptr; geo_cap = 0;
+        const size_t cap = need + need / 8;
+        cudaError_t e = cudaMalloc(&ncc, cap * sizeof(float));
+        if (e != cudaSuccess) return e;
+        col_cap = cap;
+    }
+    if (geom && geo_cap < col_cap) {
+        cudaFree(geo);
+        cudaError_t e = cudaMalloc(&geo, col_cap * sizeof(float));
+        if (e != cudaSuccess) return e;
+        geo_cap = col_cap;
+    }
+    return cudaSuccess;
+}
+void SweepWorkspace::release() {
+    cudaFree(flags); cudaFree(colidx); cudaFree(scan_tmp); cudaFree(ncc); cudaFree(geo); cudaFree(colmap);
+    flags = colidx = colmap = nullptr; scan_tmp = nullptr; ncc = geo = nullptr;
+    flag_cap = col_cap = geo_cap = map_cap = 0; valid = false;
+}
+
+// columns for the current problem state; dtw = 1: DepthToWeak (+-30 for interior pixels), 0: LocalRefine only (+-5)
+cudaError_t sweep_build(const PassK &K, SweepWorkspace &ws, int dtw, cudaStream_t st, uint64_t *launches) {
+    const int P = K.W * K.H;
+    const size_t nflat = (size_t)K.N * P;
+    cudaError_t e = ws.reserve_flags(nflat);
+    if (e != cudaSuccess) return e;
+    k_sweep_prepare<<<(P + 255) / 256, 256, 0, st>>>(K, dtw, ws.flags);
+    if ((e = cudaMemsetAsync(ws.flags + nflat, 0, sizeof(int), st)) != cudaSuccess) return e;
+    if ((e = cub::DeviceScan::ExclusiveSum(ws.scan_tmp, ws.scan_bytes, ws.flags, ws.colidx, (int)(nflat + 1), st)) != cudaSuccess) return e;
+    int ncols = 0;
+    if ((e = cudaMemcpyAsync(&ncols, ws.colidx + nflat, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    ws.ncols = ncols;
+    if (launches) *launches += 2;
+    if (ncols > 0) {
+        if ((e = ws.reserve_columns((size_t)ncols, K.geom != 0)) != cudaSuccess) return e;
+        const size_t vsm = sizeof(float) * views_smem_floats(K.N);
+        k_sweep_scatter<<<(unsigned)((nflat + 255) / 256), 256, 0, st>>>(ws.flags, ws.colidx, nflat, ws.colmap);
+        k_sweep_columns<<<(ncols + 127) / 128, 128, vsm, st>>>(K, dtw, ws.colmap, ncols, ws.ncc, ws.geo);
+        if (launches) *launches += 2;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t sweep_classify(const PassK &K, SweepWorkspace &ws, float *curve, cudaStream_t st) {
+    if (ws.ncols == 0) return cudaSuccess;
+    const int P = K.W * K.H;
+    k_sweep_classify<<<(P + 127) / 128, 128, sizeof(float) * views_smem_floats(K.N), st>>>(K, ws.colidx, ws.ncols, ws.ncc, ws.geo, curve);
+    return cudaGetLastError();
+}
+cudaError_t sweep_refine(const PassK &K, SweepWorkspace &ws, cudaStream_t st) {
+    if (ws.ncols == 0) return cudaSuccess;
+    const int P = K.W * K.H;
+    k_sweep_refine<<<(P + 127) / 128, 128, sizeof(float) * views_smem_floats(K.N), st>>>(K, ws.colidx, ws.ncols, ws.ncc, ws.geo);
+    return cudaGetLastError();
+}
+
+}  // namespace apde

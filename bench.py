@@ -260,6 +260,11 @@ def run_ours(args, rank, world, local_rank):
         "evals_per_launch": k_ev_per_launch, "ms_per_launch": k_ms,
         "peak_source": "measured in-process (apde_microbench): FMA chain / 6x6 bilinear gather",
         "stage_ms": {STAGE_NAMES[i]: float(st_ms[i]) for i in range(11) if st_launch[i]},
+        # per heavy stage: fraction of the measured texture-gather peak (36 samples per NCC-Old evaluation; NCC-New
+        # evaluations gather 36 + 9 per valid anchor, counted here at 36, so prop_weak is under-stated)
+        "stage_tex_frac": {STAGE_NAMES[i]: float((st_evals[i, 0] + st_evals[i, 1]) * SAMPLES_PER_EVAL / (st_ms[i] * 1e-3) / 1e9 / tex_peak)
+                           for i in range(11) if st_launch[i] and st_ms[i] > 0 and (st_evals[i, 0] + st_evals[i, 1]) > 0},
+        "stage_gevals": {STAGE_NAMES[i]: float((st_evals[i, 0] + st_evals[i, 1]) / 1e9) for i in range(11) if st_launch[i]},
     }
     out = {
         "metric": "ref-views/s at %dx%d, %d src views" % (args.width, args.height, args.src),
