@@ -54,5 +54,26 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST_DIR = os.path.join(CSRC, "host")
+APD_BIN = os.path.join(OUT_DIR, "apd")
+APD_TEST_BIN = os.path.join(OUT_DIR, "test_apd_class")
+
+
+def build_host():
+    """C++17 host side of the drop-in surface: the APD class, the I/O layer and the `apd` CLI, linked against libapde.so"""
+    lib = build()
+    common = [os.path.join(HOST_DIR, f) for f in ("apd_io.cpp", "APD.cpp")]
+    hdrs = [os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR)]
+    for out, main_src in ((APD_BIN, "main.cpp"), (APD_TEST_BIN, "test_apd_class.cpp"), (os.path.join(OUT_DIR, "test_io"), "test_io.cpp")):
+        srcs = common + [os.path.join(HOST_DIR, main_src)]
+        if os.path.exists(out) and all(os.path.getmtime(h) < os.path.getmtime(out) for h in hdrs + [lib]):
+            continue
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-o", out] + srcs +
+                              ["-L" + OUT_DIR, "-lapde", "-lz", "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64", "-lcudart",
+                               "-Wl,-rpath,/usr/local/cuda/lib64"])
+    return APD_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host())

@@ -1,0 +1,146 @@
+#include "APD.h"
+
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <stdexcept>
+
+namespace apd {
+
+static void check(int rc, const char *what) {
+    if (rc != 0) throw std::runtime_error(std::string(what) + ": " + apde_last_error());
+}
+
+static std::map<std::string, std::shared_ptr<SceneSession>> g_sessions;
+
+std::shared_ptr<SceneSession> SceneSession::get(const path &dense_folder, int gpu_index) {
+    const std::string key = std::filesystem::weakly_canonical(dense_folder).string();
+    auto it = g_sessions.find(key);
+    if (it != g_sessions.end()) return it->second;
+    std::shared_ptr<SceneSession> s(new SceneSession());
+    std::string err;
+    if (!GenerateSampleList(dense_folder, s->problems, &err)) throw std::runtime_error(err);
+    if (s->problems.empty()) throw std::runtime_error("no problems in " + (dense_folder / "pair.txt").string());
+    check(apde_create(gpu_index, &s->ctx), "apde_create");
+    int max_id = 0;
+    for (auto &p : s->problems) max_id = std::max(max_id, p.ref_image_id);
+    s->id_to_view.assign(max_id + 1, -1);
+    for (size_t i = 0; i < s->problems.size(); ++i) s->id_to_view[s->problems[i].ref_image_id] = (int)i;
+    bool begun = false;
+    for (size_t i = 0; i < s->problems.size(); ++i) {
+        const auto &p = s->problems[i];
+        Mat gray, bgr;
+        const path img = dense_folder / "images" / (ToFormatIndex(p.ref_image_id) + p.img_ext);
+        if (!ReadImage(img, gray)) throw std::runtime_error("Images may error, check it!");
+        ReadImageColor(img, bgr);
+        if (!begun) {
+            s->width = gray.cols; s->height = gray.rows;
+            check(apde_scene_begin(s->ctx, (int)s->problems.size(), s->width, s->height), "apde_scene_begin");
+            begun = true;
+        } else if (gray.cols != s->width || gray.rows != s->height) {
+            throw std::runtime_error("Images may error, check it!");  // CheckImages, main.cpp:104-127
+        }
+        Camera cam;
+        if (!ReadCamera(dense_folder / "cams" / (ToFormatIndex(p.ref_image_id) + "_cam.txt"), cam)) throw std::runtime_error("can not read camera of image " + ToFormatIndex(p.ref_image_id));
+        cam.width = s->width; cam.height = s->height;
+        s->cameras.push_back(cam);
+        check(apde_scene_set_view(s->ctx, (int)i, gray.data(), bgr.empty() ? nullptr : bgr.data(), &cam), "apde_scene_set_view");
+        s->has_color = !bgr.empty();
+    }
+    for (size_t i = 0; i < s->problems.size(); ++i) {
+        std::vector<int32_t> src;
+        for (int id : s->problems[i].src_image_ids) {
+            const int v = s->view_of(id);
+            if (v < 0) throw std::runtime_error("pair.txt names image " + std::to_string(id) + " that is not a reference view");
+            src.push_back(v);
+        }
+        check(apde_scene_set_pairs(s->ctx, (int)i, (int)src.size(), src.data()), "apde_scene_set_pairs");
+    }
+    check(apde_scene_commit(s->ctx), "apde_scene_commit");
+    g_sessions[key] = s;
+    return s;
+}
+
+void SceneSession::release_all() { g_sessions.clear(); }
+SceneSession::~SceneSession() { if (ctx) apde_destroy(ctx); }
+int SceneSession::view_of(int image_id) const { return (image_id >= 0 && image_id < (int)id_to_view.size()) ? id_to_view[image_id] : -1; }
+
+APD::APD(const Problem &problem_) : problem(problem_) {
+    apde_params_default(&params_c);
+    const PatchMatchParams &p = problem.params;
+    params_c.max_iterations = p.max_iterations; params_c.top_k = p.top_k;
+    params_c.geom_consistency = p.geom_consistency; params_c.use_impetus = p.use_impetus;
+    params_c.strong_radius = p.strong_radius; params_c.strong_increment = p.strong_increment;
+    params_c.weak_radius = p.weak_radius; params_c.weak_increment = p.weak_increment;
+    params_c.use_APD = p.use_APD; params_c.use_sa = p.use_sa; params_c.weak_peak_radius = p.weak_peak_radius;
+    params_c.rotate_time = p.rotate_time; params_c.ransac_threshold = p.ransac_threshold; params_c.geom_factor = p.geom_factor;
+    params_c.state = (int)p.state;
+}
+APD::~APD() {}
+
+void APD::InuputInitialization() {  // APD.cpp:501-685: everything it loads is already resident
+    session = SceneSession::get(problem.dense_folder);
+    if (session->view_of(problem.ref_image_id) < 0) throw std::runtime_error("unknown reference image id");
+    std::cout << "Num images: " << problem.src_image_ids.size() + 1 << std::endl;
+}
+void APD::CudaSpaceInitialization() {  // APD.cpp:687-788
+    if (!session) InuputInitialization();
+    const uint32_t seed = 0x9E3779B1u + (uint32_t)problem.iteration * 0x85EBCA77u;
+    check(apde_problem_setup(session->ctx, session->view_of(problem.ref_image_id), &params_c, problem.scale_size, seed), "apde_problem_setup");
+    int n = 0;
+    check(apde_problem_dims(session->ctx, &width, &height, &n), "apde_problem_dims");
+    apde_params filled;
+    check(apde_problem_get_cameras(session->ctx, nullptr, &filled), "apde_problem_get_cameras");
+    params_c = filled;
+    std::cout << "Depth range: " << params_c.depth_min << " " << params_c.depth_max << std::endl;
+    std::cout << "Image size: " << width << " * " << height << std::endl;
+    set_up = true;
+}
+void APD::SetDataPassHelperInCuda() {}  // APD.cpp:790-814: kernel arguments are passed by value at launch
+void APD::RunPatchMatch() {             // APD.cu:2663-2737
+    if (!set_up) CudaSpaceInitialization();
+    check(apde_problem_run(session->ctx), "apde_problem_run");
+    ran = true;
+}
+void APD::download() {
+    if (downloaded) return;
+    if (!ran) throw std::runtime_error("RunPatchMatch has not run");
+    const size_t P = (size_t)width * height;
+    planes.resize(P);
+    weak.create(height, width, CV_8UC1);
+    conf.create(height, width, CV_8UC1);
+    check(apde_problem_get(session->ctx, APDE_FIELD_PLANES, planes.data(), P * 16), "planes");
+    check(apde_problem_get(session->ctx, APDE_FIELD_WEAK_INFO, weak.data(), P), "weak");
+    check(apde_problem_get(session->ctx, APDE_FIELD_CONFIDENCE, conf.data(), P), "confidence");
+    downloaded = true;
+}
+float4_ APD::GetPlaneHypothesis(int r, int c) { download(); return planes[(size_t)c + (size_t)r * width]; }
+Mat APD::GetPixelStates() { download(); return weak; }
+Mat APD::GetConfidence() { download(); return conf; }
+int APD::GetWidth() { return width; }
+int APD::GetHeight() { return height; }
+float APD::GetDepthMin() { return params_c.depth_min; }
+float APD::GetDepthMax() { return params_c.depth_max; }
+void APD::Commit() {
+    if (committed || !ran) return;
+    check(apde_problem_finish(session->ctx), "apde_problem_finish");
+    committed = true;
+}
+
+void RunFusion(const path &dense_folder, const std::vector<Problem> &, const std::string &name, bool weak_filter, bool export_color) {
+    auto s = SceneSession::get(dense_folder);
+    int64_t n = 0;
+    check(apde_fuse(s->ctx, weak_filter ? 1 : 0, nullptr, nullptr, 0, &n), "apde_fuse(count)");
+    std::vector<float> xyz((size_t)n * 3), bgr((size_t)n * 3);
+    int64_t n2 = 0;
+    check(apde_fuse(s->ctx, weak_filter ? 1 : 0, xyz.data(), bgr.data(), n, &n2), "apde_fuse");
+    std::vector<PointList> pc((size_t)std::min(n, n2));
+    for (size_t i = 0; i < pc.size(); ++i) {
+        pc[i].coord = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        pc[i].color = {bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2]};
+    }
+    ExportPointCloud(dense_folder / "APD" / name, pc, export_color && s->has_color);
+    std::cout << "Fused " << pc.size() << " points" << std::endl;
+}
+
+}  // namespace apd

@@ -1,0 +1,62 @@
+// apd_io.h -- host data plane of the drop-in surface: the reference's file formats without OpenCV / Boost.
+//   ReadBinMat / WriteBinMat   ".bin" maps ("dmb": int32 version=1, rows, cols, cv type + raw rows)  APD.cpp:18-83
+//   ReadCamera                 MVSNet *_cam.txt                                                     APD.cpp:85-135
+//   ReadImage / ReadImageColor PNG (zlib inflate) / PGM / PPM; grey = OpenCV's BGR2GRAY fixed point   APD.cpp:137-160
+//   ExportPointCloud           binary little-endian PLY, float xyz + uchar blue green red             APD.cpp:316-356
+//   GenerateSampleList         pair.txt -> Problem list                                              main.cpp:44-102
+#pragma once
+#include <cstdint>
+#include <filesystem>
+#include <string>
+#include <vector>
+
+#include "../../../include/apde.h"
+
+namespace apd {
+
+using path = std::filesystem::path;
+typedef apde_camera Camera;  // identical layout to the reference Camera (main.h:50-61)
+
+// OpenCV type codes used by the reference's maps
+enum { CV_8UC1 = 0, CV_8UC3 = 16, CV_32SC1 = 4, CV_32FC1 = 5, CV_32FC3 = 21 };
+
+struct Mat {  // the subset of cv::Mat the driver interface touches
+    int rows = 0, cols = 0, type_ = 0;
+    std::vector<uint8_t> buf;
+    Mat() {}
+    Mat(int r, int c, int type) { create(r, c, type); }
+    void create(int r, int c, int type);
+    int type() const { return type_; }
+    bool empty() const { return buf.empty(); }
+    size_t elem_size() const;
+    size_t step() const { return (size_t)cols * elem_size(); }
+    uint8_t *data() { return buf.data(); }
+    const uint8_t *data() const { return buf.data(); }
+    template <typename T> T &at(int r, int c) { return *reinterpret_cast<T *>(buf.data() + r * step() + c * sizeof(T)); }
+    template <typename T> const T &at(int r, int c) const { return *reinterpret_cast<const T *>(buf.data() + r * step() + c * sizeof(T)); }
+    template <typename T> T *ptr(int r = 0) { return reinterpret_cast<T *>(buf.data() + r * step()); }
+    template <typename T> const T *ptr(int r = 0) const { return reinterpret_cast<const T *>(buf.data() + r * step()); }
+};
+
+struct float3_ { float x, y, z; };
+struct PointList { float3_ coord; float3_ color; };  // main.h:63-66
+
+bool ReadBinMat(const path &mat_path, Mat &mat);
+bool WriteBinMat(const path &mat_path, const Mat &mat);
+bool ReadCamera(const path &cam_path, Camera &cam);
+bool ReadImage(const path &img_path, Mat &gray_u8);         // CV_8UC1 (the library converts to float on the device)
+bool ReadImageColor(const path &img_path, Mat &bgr_u8);     // CV_8UC3, BGR order as cv::imread(IMREAD_COLOR)
+bool WritePGM(const path &p, const Mat &gray_u8);
+bool ExportPointCloud(const path &ply_path, const std::vector<PointList> &pc, bool export_color = true);
+std::string ToFormatIndex(int index);
+
+struct ProblemDesc {  // main.h:102-115 (the fields the schedule needs)
+    int ref_image_id = 0;
+    std::vector<int> src_image_ids;
+    path dense_folder, result_folder;
+    std::string img_ext;
+};
+// pair.txt parser with the reference's rules: score <= 0 entries dropped, result folder APD/<id>/ created
+bool GenerateSampleList(const path &dense_folder, std::vector<ProblemDesc> &problems, std::string *err);
+
+}  // namespace apd

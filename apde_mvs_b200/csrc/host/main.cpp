@@ -1,0 +1,142 @@
+// main.cpp -- the reference's CLI (main.cpp:7-41, 210-411) on the B200 library: same flag spellings (booleans take a value),
+// same round x iteration x problem schedule, same output files (APD/%08d/{depths,normals,weak,confidence}.bin, APD/APD.ply).
+#include <chrono>
+#include <cstring>
+#include <iostream>
+#include <map>
+
+#include "APD.h"
+
+using namespace apd;
+
+struct Args {
+    std::string dense_folder, dataset = "DTU";
+    int gpu_index = 0;
+    bool only_fuse = false, no_fuse = false, memory_cache = true, use_sa = true, use_impetus = true, weak_filter = true, flush = false,
+         export_anchor = false, export_curve = false, export_color = true;
+};
+
+static void usage() {
+    std::cout << "Allowed options:\n  -d [ --dense_folder ] arg  path to dense folder\n  -g [ --gpu_index ] arg (=0)\n"
+                 "  -D [ --dataset ] arg (=DTU)  DTU, ETH3D, TaT_a, TaT_i, General\n  -f [ --only_fuse ] arg (=0)\n  -F [ --no_fuse ] arg (=0)\n"
+                 "  -m [ --memory_cache ] arg (=1)\n  -s [ --use_sa ] arg (=1)\n  -i [ --use_impetus ] arg (=1)\n  -w [ --weak_filter ] arg (=1)\n"
+                 "  --flush arg (=0)\n  -n [ --export_anchor ] arg (=0)\n  -r [ --export_curve ] arg (=0)\n  -c [ --export_color ] arg (=1)\n  -h [ --help ]\n";
+}
+static bool to_bool(const std::string &v) { return v == "1" || v == "true" || v == "True" || v == "yes" || v == "on"; }
+
+static Args parse(int argc, char **argv) {
+    Args a;
+    std::map<std::string, std::string> alias = {{"-d", "--dense_folder"}, {"-g", "--gpu_index"}, {"-D", "--dataset"}, {"-f", "--only_fuse"},
+        {"-F", "--no_fuse"}, {"-m", "--memory_cache"}, {"-s", "--use_sa"}, {"-i", "--use_impetus"}, {"-w", "--weak_filter"},
+        {"-n", "--export_anchor"}, {"-r", "--export_curve"}, {"-c", "--export_color"}, {"-h", "--help"}};
+    for (int i = 1; i < argc; ++i) {
+        std::string k = argv[i], v;
+        const size_t eq = k.find('=');
+        if (eq != std::string::npos) { v = k.substr(eq + 1); k = k.substr(0, eq); }
+        if (alias.count(k)) k = alias[k];
+        if (k == "--help") { usage(); exit(0); }
+        if (v.empty()) {
+            if (i + 1 >= argc) { std::cout << "Error: the required argument for option '" << k << "' is missing\n"; usage(); exit(-1); }
+            v = argv[++i];
+        }
+        if (k == "--dense_folder") a.dense_folder = v;
+        else if (k == "--gpu_index") a.gpu_index = atoi(v.c_str());
+        else if (k == "--dataset") a.dataset = v;
+        else if (k == "--only_fuse") a.only_fuse = to_bool(v);
+        else if (k == "--no_fuse") a.no_fuse = to_bool(v);
+        else if (k == "--memory_cache") a.memory_cache = to_bool(v);
+        else if (k == "--use_sa") a.use_sa = to_bool(v);
+        else if (k == "--use_impetus") a.use_impetus = to_bool(v);
+        else if (k == "--weak_filter") a.weak_filter = to_bool(v);
+        else if (k == "--flush") a.flush = to_bool(v);
+        else if (k == "--export_anchor") a.export_anchor = to_bool(v);
+        else if (k == "--export_curve") a.export_curve = to_bool(v);
+        else if (k == "--export_color") a.export_color = to_bool(v);
+        else { std::cout << "Error: unrecognised option '" << k << "'\n"; usage(); exit(-1); }
+    }
+    if (a.dense_folder.empty()) { std::cout << "Error: the option '--dense_folder' is required but missing\n"; usage(); exit(-1); }
+    return a;
+}
+
+static void write_maps(SceneSession &s) {
+    for (size_t i = 0; i < s.problems.size(); ++i) {
+        int w = 0, h = 0;
+        apde_view_download(s.ctx, (int)i, nullptr, nullptr, nullptr, nullptr, &w, &h);
+        if (w == 0) continue;
+        Mat depth(h, w, CV_32FC1), normal(h, w, CV_32FC3), weak(h, w, CV_8UC1), conf(h, w, CV_8UC1);
+        apde_view_download(s.ctx, (int)i, depth.ptr<float>(), normal.ptr<float>(), weak.data(), conf.data(), &w, &h);
+        const path dir = s.problems[i].result_folder;
+        WriteBinMat(dir / "depths.bin", depth);
+        WriteBinMat(dir / "normals.bin", normal);
+        WriteBinMat(dir / "weak.bin", weak);
+        WriteBinMat(dir / "confidence.bin", conf);
+    }
+}
+
+static bool read_maps(SceneSession &s) {  // --only_fuse: depth maps come from a previous run
+    for (size_t i = 0; i < s.problems.size(); ++i) {
+        const path dir = s.problems[i].result_folder;
+        Mat depth, normal, weak, conf;
+        if (!ReadBinMat(dir / "depths.bin", depth) || !ReadBinMat(dir / "normals.bin", normal) || !ReadBinMat(dir / "weak.bin", weak) ||
+            !ReadBinMat(dir / "confidence.bin", conf)) return false;
+        if (apde_view_upload(s.ctx, (int)i, depth.ptr<float>(), normal.ptr<float>(), weak.data(), conf.data(), depth.cols, depth.rows)) return false;
+    }
+    return true;
+}
+
+int main(int argc, char **argv) {
+    Args a = parse(argc, argv);
+    if (a.only_fuse) a.memory_cache = false;
+    if (a.no_fuse) a.flush = true;
+    std::cout << "========================== Config ==========================" << std::endl;
+    std::cout << "dense_folder : " << a.dense_folder << "\ngpu_index    : " << a.gpu_index << "\ndataset      : " << a.dataset
+              << "\nonly_fuse    : " << a.only_fuse << "\nno_fuse      : " << a.no_fuse << "\nmemory_cache : " << a.memory_cache
+              << "\nuse_sa       : " << a.use_sa << " (ignored: SAM masks are out of scope)\nuse_impetus  : " << a.use_impetus
+              << "\nweak_filter  : " << a.weak_filter << "\nflush        : " << a.flush << "\nexport_anchor: " << a.export_anchor
+              << "\nexport_curve : " << a.export_curve << "\nexport_color : " << a.export_color << std::endl;
+    std::cout << "============================================================" << std::endl;
+    try {
+        std::filesystem::create_directories(path(a.dense_folder) / "APD");
+        auto s = SceneSession::get(a.dense_folder, a.gpu_index);
+        std::cout << "There are " << s->problems.size() << " problems needed to be processed!" << std::endl;
+        if (a.dataset == "TaT_a" || a.dataset == "TaT_i")
+            std::cout << "note: the TaT fusion variants (APD.cpp:1229-1608) are not implemented yet; using RunFusion" << std::endl;
+        if (a.only_fuse) {
+            if (!read_maps(*s)) { std::cout << "Error: can not read the depth maps of a previous run" << std::endl; return EXIT_FAILURE; }
+            RunFusion(a.dense_folder, {}, "APD.ply", a.weak_filter, a.export_color);
+            printf("Fusion done!\n");
+            return EXIT_SUCCESS;
+        }
+        apde_schedule sched;
+        apde_schedule_default(&sched);
+        sched.use_impetus = a.use_impetus;
+        sched.geom_factor = (a.dataset == "TaT_a" || a.dataset == "TaT_i") ? 0.05f : 0.2f;  // main.cpp:294-298
+        const int npass = apde_schedule_num_passes(s->ctx, &sched);
+        std::cout << "Round nums: " << npass / (1 + sched.geom_iterations) << std::endl;
+        apde_timing t;
+        memset(&t, 0, sizeof(t));
+        const auto start = std::chrono::steady_clock::now();
+        for (int p = 0; p < npass; ++p) {
+            if (p % (1 + sched.geom_iterations) == 0)
+                std::cout << "========================== Round " << p / (1 + sched.geom_iterations) << " ==========================" << std::endl;
+            std::cout << "======== iteration " << p << "========" << std::endl;
+            const double before = t.patchmatch_ms;
+            if (apde_run_schedule_pass(s->ctx, &sched, p, &t)) { std::cout << "Error: " << apde_last_error() << std::endl; return EXIT_FAILURE; }
+            printf("RunPatchMatch time: %d ms (all %zu views)\n", (int)(t.patchmatch_ms - before), s->problems.size());
+        }
+        const auto end = std::chrono::steady_clock::now();
+        std::cout << "Cost time: " << std::chrono::duration_cast<std::chrono::milliseconds>(end - start).count() << " ms" << std::endl;
+        std::cout << "Average used time: " << (int)(t.patchmatch_ms / s->problems.size()) << " ms" << std::endl;
+        std::cout << "Cost evaluations: " << t.evals_ncc_old << " NCC, " << t.evals_ncc_new << " deformable NCC, " << t.evals_geom << " geometric" << std::endl;
+        write_maps(*s);  // the reference writes after every pass; nothing reads them in between when maps stay resident
+        if (a.no_fuse) { printf("Skip fusion, all done!\n"); return EXIT_SUCCESS; }
+        std::cout << "Run fusion\n";
+        RunFusion(a.dense_folder, {}, "APD.ply", a.weak_filter, a.export_color);
+        std::cout << "All done\n";
+    } catch (const std::exception &e) {
+        std::cout << "Error: " << e.what() << std::endl;
+        return EXIT_FAILURE;
+    }
+    SceneSession::release_all();
+    return EXIT_SUCCESS;
+}

@@ -1,0 +1,49 @@
+// test_io.cpp -- CPU-only exerciser of the host I/O layer for tests/test_host_io.py (no GPU calls; links libapde only for symbols)
+#include <cstdio>
+#include <iostream>
+
+#include "apd_io.h"
+using namespace apd;
+
+int main(int argc, char **argv) {
+    if (argc < 3) return 2;
+    const std::string cmd = argv[1];
+    if (cmd == "gray") {  // gray <image> <out.pgm>
+        Mat g;
+        if (!ReadImage(argv[2], g)) return 1;
+        return WritePGM(argv[3], g) ? 0 : 1;
+    }
+    if (cmd == "color") {  // color <image> <out.bin>  (CV_8UC3 BGR)
+        Mat c;
+        if (!ReadImageColor(argv[2], c)) return 1;
+        return WriteBinMat(argv[3], c) ? 0 : 1;
+    }
+    if (cmd == "cam") {  // cam <cam.txt>
+        Camera cam;
+        if (!ReadCamera(argv[2], cam)) return 1;
+        for (int i = 0; i < 9; ++i) printf("%.9g ", cam.K[i]);
+        for (int i = 0; i < 9; ++i) printf("%.9g ", cam.R[i]);
+        for (int i = 0; i < 3; ++i) printf("%.9g ", cam.t[i]);
+        for (int i = 0; i < 3; ++i) printf("%.9g ", cam.c[i]);
+        printf("%.9g %.9g %.9g %.9g\n", cam.depth_min, cam.depth_max, cam.interval, cam.depth_num);
+        return 0;
+    }
+    if (cmd == "bin") {  // bin <in.bin> <out.bin>: round trip
+        Mat m;
+        if (!ReadBinMat(argv[2], m)) return 1;
+        printf("%d %d %d\n", m.rows, m.cols, m.type());
+        return WriteBinMat(argv[3], m) ? 0 : 1;
+    }
+    if (cmd == "pairs") {  // pairs <dense_folder>
+        std::vector<ProblemDesc> pr;
+        std::string err;
+        if (!GenerateSampleList(argv[2], pr, &err)) { std::cout << err << std::endl; return 1; }
+        for (auto &p : pr) { printf("%d %s:", p.ref_image_id, p.img_ext.c_str()); for (int s : p.src_image_ids) printf(" %d", s); printf("\n"); }
+        return 0;
+    }
+    if (cmd == "ply") {  // ply <out.ply>
+        std::vector<PointList> pc = {{{1.5f, -2.0f, 3.25f}, {10, 20, 30}}, {{0.0f, 1.0f, 2.0f}, {255, 0, 128}}};
+        return ExportPointCloud(argv[2], pc, true) ? 0 : 1;
+    }
+    return 2;
+}
