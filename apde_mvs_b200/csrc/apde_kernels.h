@@ -77,6 +77,7 @@ cudaError_t launch_resize_nearest(const void *src, int W, int H, void *dst, int 
 // planes <- (normal, depth) maps (APD.cpp:674-682); weak/conf defaults (APD.cpp:656-657)
 cudaError_t launch_planes_from_maps(const float *depth, const float *normal, float4 *planes, int P, cudaStream_t st);
 cudaError_t launch_fill_u8(uint8_t *dst, uint8_t v, size_t n, cudaStream_t st);
+cudaError_t launch_float_to_half(const float *src, void *dst, size_t n, cudaStream_t st);
 // ProcessProblem tail (main.cpp:168-178): depth range check, normals, states
 cudaError_t launch_finish(const float4 *planes, uint8_t *weak, float *depth, float *normal, uint8_t *weak_out, int P,
                           float dmin, float dmax, cudaStream_t st);

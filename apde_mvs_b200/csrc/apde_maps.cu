@@ -1,5 +1,7 @@
 // apde_maps.cu -- pyramid / map kernels either side of the pass: OpenCV-compatible INTER_LINEAR image resize,
 // INTER_NEAREST map up-sampling, state import / export.  All HBM-bound streaming kernels.
+#include <cuda_fp16.h>
+
 #include "apde_kernels.h"
 
 namespace apde {
@@ -68,6 +70,15 @@ __global__ void __launch_bounds__(256) k_planes_from_maps(const float *__restric
 }
 cudaError_t launch_planes_from_maps(const float *depth, const float *normal, float4 *planes, int P, cudaStream_t st) {
     k_planes_from_maps<<<(P + 255) / 256, 256, 0, st>>>(depth, normal, planes, P);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) k_float_to_half(const float *__restrict__ src, __half *__restrict__ dst, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+cudaError_t launch_float_to_half(const float *src, void *dst, size_t n, cudaStream_t st) {
+    k_float_to_half<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, (__half *)dst, n);
     return cudaGetLastError();
 }
 

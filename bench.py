@@ -122,11 +122,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_pinned = set()
+
+
 def pin(arr):
     """cudaHostRegister a numpy buffer so the C ABI's host->device copies come from pinned memory"""
+    if arr.ctypes.data in _pinned:
+        return arr
     try:
         rt = C.CDLL("libcudart.so.12")
         rt.cudaHostRegister(C.c_void_p(arr.ctypes.data), C.c_size_t(arr.nbytes), 0)
+        rt.cudaGetLastError()  # a failed registration must not linger as the runtime's sticky last error
+        _pinned.add(arr.ctypes.data)
     except Exception:
         pass
     return arr
