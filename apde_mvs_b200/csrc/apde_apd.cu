@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(128) k_ransac_fit(const __grid_constant__ Pass
 // -------------------------------------------------------------------------------------------- K8 weak propagation
 // Black/RedPixelUpdateWeak -> CheckerboardPropagationWeak -> PlaneHypothesisRefinementWeak,
 // APD.cu:1617-1652, 1442-1615, 1008-1096
-__global__ void __launch_bounds__(128) k_prop_weak(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
+template <bool U>
+__device__ __forceinline__ void k_prop_weak_body(const PassK &K, int iter, int color, int tiles_x,
                                                    int ylimit) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
@@ -272,9 +273,9 @@ __global__ void __launch_bounds__(128) k_prop_weak(const __grid_constant__ PassK
     const short2 *anc = K.anchors + (size_t)center * APDE_ANCHOR_NUM;
 
     RefPatch rp;
-    load_ref_patch(K, px, py, rp);
+    load_ref_patch<U>(K, px, py, rp);
     AnchorRef ar;
-    load_anchor_ref(K, anc, ar);
+    load_anchor_ref<U>(K, anc, ar);
     unsigned n_new = 0, n_geom = 0;
 
     unsigned flags = 0, anchor_valid = 0;
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(128) k_prop_weak(const __grid_constant__ PassK
         if (ok) {
             const float3 m = plane_row(K, K.planes[pos[h]]);
 #pragma unroll 1
-            for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_new(K, K.v[v], v, px, py, m, rp, ar);
+            for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_new<U>(K, K.v[v], v, px, py, m, rp, ar);
             n_new += N;
         } else {
             for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = (h == 0 && v == 0) ? 2.0f : 0.0f;
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(128) k_prop_weak(const __grid_constant__ PassK
         float acc = 0.0f;
         for (uint32_t mk = wmask; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            float c = ncc_new(K, s_vk[v], v, px, py, m, rp, ar);
+            float c = ncc_new<U>(K, s_vk[v], v, px, py, m, rp, ar);
             n_new++;
             if (use_geom) { c = c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, plane_c); n_geom++; }
             acc += (float)vw_get(w, v) * c;
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(128) k_prop_weak(const __grid_constant__ PassK
             float acc = 0.0f;
             for (uint32_t mk = wmask; mk; mk &= mk - 1) {
                 const int v = __ffs(mk) - 1;
-                float c = ncc_new(K, s_vk[v], v, px, py, m, rp, ar);
+                float c = ncc_new<U>(K, s_vk[v], v, px, py, m, rp, ar);
                 n_new++;
                 if (use_geom) { c = c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp); n_geom++; }
                 acc += (float)vw_get(w, v) * c;
@@ -407,6 +408,12 @@ __global__ void __launch_bounds__(128) k_prop_weak(const __grid_constant__ PassK
     }
     count_evals(K, 0, n_new, n_geom);
 }
+__global__ void __launch_bounds__(128) k_prop_weak(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
+                                                   int ylimit) {
+    if (K.tex_unorm > 0.0f) k_prop_weak_body<true>(K, iter, color, tiles_x, ylimit);
+    else k_prop_weak_body<false>(K, iter, color, tiles_x, ylimit);
+}
+
 
 cudaError_t launch_stage_apd(const PassK &K, int stage, int iter, int color, cudaStream_t st) {
     const int W = K.W, H = K.H, N = K.N;

@@ -65,10 +65,13 @@ struct apde_context {
         float *lin = nullptr;  // [V][h*w]
         void *half = nullptr;  // [V][h*w] __half staging when the texture is stored as fp16
         bool fp16 = false;
+        bool u8 = false;       // 8-bit UNORM texels (scale 1 only: the images are 8-bit integers)
+        bool u16 = false;      // 16-bit UNORM texels holding 4 x value (power-of-two scales of divisible sizes: 2x2 means)
         bool stale = true;     // contents must be re-derived from the views' images
     };
     std::vector<Level> levels;
     int level_scale = 0, lw = 0, lh = 0;  // the level of the current problem
+    float level_unorm = 0.0f, level_inv = 1.0f;
     cudaArray_t level_arr = nullptr;
     cudaTextureObject_t level_tex = 0;
     float *d_level_lin = nullptr;  // [V][lh*lw]
@@ -324,7 +327,17 @@ static int ensure_level(apde_context *c, int scale) {
         // max 0.0625 grey levels off, 10 % bit-identical) -> costs move by ~1e-3: outside the 1e-4 parity bar, so not used.
         static const bool want16 = [] { const char *e = getenv("APDE_TEX_FP16"); return e && e[0] == '1'; }();
         nl.fp16 = want16 && (scale == 1 || (scale == 2 && c->W % 2 == 0 && c->H % 2 == 0));
-        cudaChannelFormatDesc desc = nl.fp16 ? cudaCreateChannelDescHalf() : cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+        // 8-bit UNORM texels at full resolution: exact (see fetch() in apde_device.cuh); APDE_TEX_U8=0 keeps float32
+        static const bool want8 = [] { const char *e = getenv("APDE_TEX_U8"); return !(e && e[0] == '0'); }();
+        nl.u8 = want8 && !nl.fp16 && scale == 1;
+        // 16-bit UNORM texels (4 x value) for the coarser levels were measured NOT exact: the unit filters them at fp16
+        // precision (max 0.125 grey levels off, tools/diag_u8.py), so coarse levels keep float32 texels.  APDE_TEX_U16=1 forces it.
+        static const bool want16u = [] { const char *e = getenv("APDE_TEX_U16"); return e && e[0] == '1'; }();
+        nl.u16 = want16u && !nl.fp16 && scale > 1 && (scale & (scale - 1)) == 0 && c->W % scale == 0 && c->H % scale == 0;
+        cudaChannelFormatDesc desc = nl.u8 ? cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned)
+                                     : nl.u16 ? cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned)
+                                     : nl.fp16 ? cudaCreateChannelDescHalf() : cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+        if (nl.u16) CU(cudaMalloc(&nl.half, (size_t)c->V * P * 2));
         if (nl.fp16) CU(cudaMalloc(&nl.half, (size_t)c->V * P * 2));
         CU(cudaMalloc3DArray(&nl.arr, &desc, make_cudaExtent(lw, lh, c->V), cudaArrayLayered));
         cudaResourceDesc rd;
@@ -336,7 +349,7 @@ static int ensure_level(apde_context *c, int scale) {
         // the reference asks for "wrap" with unnormalised coordinates, which CUDA serves as clamp (APD.cpp:701-705)
         td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
         td.filterMode = cudaFilterModeLinear;
-        td.readMode = cudaReadModeElementType;
+        td.readMode = (nl.u8 || nl.u16) ? cudaReadModeNormalizedFloat : cudaReadModeElementType;
         td.normalizedCoords = 0;
         CU(cudaCreateTextureObject(&nl.tex, &rd, &td, nullptr));
         c->levels.push_back(nl);
@@ -349,7 +362,21 @@ static int ensure_level(apde_context *c, int scale) {
         c->launches += c->V;
         cudaMemcpy3DParms cp;
         memset(&cp, 0, sizeof(cp));
-        if (L->fp16) {
+        if (L->u8) {
+            for (int v = 0; v < c->V; ++v) {  // the 8-bit images are the texels; one layer per view
+                cudaMemcpy3DParms cv;
+                memset(&cv, 0, sizeof(cv));
+                cv.srcPtr = make_cudaPitchedPtr(c->views[v].d_gray, (size_t)L->w, L->w, L->h);
+                cv.dstArray = L->arr;
+                cv.dstPos = make_cudaPos(0, 0, v);
+                cv.extent = make_cudaExtent(L->w, L->h, 1);
+                cv.kind = cudaMemcpyDeviceToDevice;
+                CU(cudaMemcpy3DAsync(&cv, c->stream));
+            }
+        } else if (L->u16) {
+            CU(launch_float_to_u16x4(L->lin, L->half, (size_t)c->V * P, c->stream));
+            cp.srcPtr = make_cudaPitchedPtr(L->half, (size_t)L->w * 2, L->w, L->h);
+        } else if (L->fp16) {
             CU(launch_float_to_half(L->lin, L->half, (size_t)c->V * P, c->stream));
             cp.srcPtr = make_cudaPitchedPtr(L->half, (size_t)L->w * 2, L->w, L->h);
         } else {
@@ -358,11 +385,13 @@ static int ensure_level(apde_context *c, int scale) {
         cp.dstArray = L->arr;
         cp.extent = make_cudaExtent(L->w, L->h, c->V);
         cp.kind = cudaMemcpyDeviceToDevice;
-        CU(cudaMemcpy3DAsync(&cp, c->stream));
+        if (!L->u8) CU(cudaMemcpy3DAsync(&cp, c->stream));
         L->stale = false;
     }
     c->level_scale = scale; c->lw = L->w; c->lh = L->h;
     c->level_arr = L->arr; c->level_tex = L->tex; c->d_level_lin = L->lin;
+    c->level_unorm = L->u8 ? 255.0f * 256.0f : (L->u16 ? 65535.0f * 256.0f : 0.0f);
+    c->level_inv = L->u8 ? 1.0f / 256.0f : 1.0f / 1024.0f;
     return APDE_OK;
 }
 
@@ -506,6 +535,8 @@ int apde_problem_setup(apde_context *c, int ref_view, const apde_params *params,
     K.seed = seed;
     K.stream = (uint32_t)ref_view;
     K.tex = c->level_tex;
+    K.tex_unorm = c->level_unorm;
+    K.tex_inv = c->level_inv;
     K.planes = c->d_planes; K.costs = c->d_costs; K.sel = c->d_sel; K.vw = c->d_vw; K.weak = c->d_weak; K.conf = c->d_conf;
     K.fit = c->d_fit; K.reliable = c->d_reliable; K.nearest = c->d_nearest; K.anchors = c->d_anchors;
     K.depth = c->d_depthws; K.counters = c->d_counters + 4 * kStages;
@@ -851,9 +882,9 @@ int apde_eval_costs(apde_context *c, int n, const int32_t *tuples, const float *
     return APDE_OK;
 }
 
-__global__ void k_debug_tex(cudaTextureObject_t tex, int layer, int n, const float2 *xy, float *out) {
+__global__ void k_debug_tex(const __grid_constant__ PassK K, int layer, int n, const float2 *xy, float *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = tex2DLayered<float>(tex, xy[i].x, xy[i].y, layer);
+    if (i < n) out[i] = K.tex_unorm > 0.0f ? fetch<true>(K, xy[i].x, xy[i].y, layer) : fetch<false>(K, xy[i].x, xy[i].y, layer);
 }
 
 int apde_debug_tex2d(apde_context *c, int idx, int n, const float *xy, float *out) {
@@ -865,7 +896,7 @@ int apde_debug_tex2d(apde_context *c, int idx, int n, const float *xy, float *ou
     CU(cudaMalloc(&d_xy, (size_t)n * 8));
     CU(cudaMalloc(&d_o, (size_t)n * 4));
     CU(cudaMemcpyAsync(d_xy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-    k_debug_tex<<<(n + 255) / 256, 256, 0, c->stream>>>(c->level_tex, layer, n, d_xy, d_o);
+    k_debug_tex<<<(n + 255) / 256, 256, 0, c->stream>>>(c->K, layer, n, d_xy, d_o);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

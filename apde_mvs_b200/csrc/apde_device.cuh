@@ -35,7 +35,8 @@ struct PassK {
     float R[9];            // reference rotation
     int ref_layer;
     uint32_t seed, stream;
-    cudaTextureObject_t tex;  // layered float32 images of the level (linear filter, clamp, unnormalised)
+    cudaTextureObject_t tex;  // layered images of the level (linear filter, clamp, unnormalised coordinates)
+    float tex_unorm, tex_inv; // 0: float32 texels.  > 0: integer texels read as normalised float; sample = rint(t * tex_unorm) * tex_inv
     float4 *planes;
     float *costs;
     uint32_t *sel;
@@ -158,6 +159,21 @@ __device__ __forceinline__ float4 perturbed_normal(const PassK &K, int px, int p
     return np;
 }
 
+// One filtered sample of the level.  With integer-valued texels the exact filtered value is a multiple of 1/256 (the
+// texture unit's four weights are integers that sum to 256, profiles/r01_texture_filter_model.md), so a level stored as
+// 8-bit UNORM texels -- a quarter of the bytes behind every gather, and the L1TEX data pipe is the binding unit -- gives
+// back exactly the float32 texture's sample after one multiply and one round: rint(t * 255 * 256) / 256.  Coarser pyramid
+// levels of even sizes are 2x2 means (multiples of 1/4): stored x4 as 16-bit UNORM, sample = rint(t * 65535 * 256) / 1024.
+// U (compile time) = the level holds UNORM texels.  Decode = 2 FMA-pipe instructions: y = fma(t, 255*256, 1.5*2^23) is
+// 1.5*2^23 + n with n = rint(t*255*256) exactly, and fma(y, 2^-8, -1.5*2^15) = n / 256 exactly.
+template <bool U>
+__device__ __forceinline__ float fetch(const PassK &K, float x, float y, int layer) {
+    const float t = tex2DLayered<float>(K.tex, x, y, layer);
+    if (!U) return t;
+    const float y2 = fmaf(t, K.tex_unorm, 12582912.0f);
+    return fmaf(y2, K.tex_inv, -12582912.0f * K.tex_inv);
+}
+
 // ------------------------------------------------------------------------------------------------ costs
 // reference patch of one pixel: texels at (x+i, y+j), i outer, j inner, i,j in {-5,-3,...,5} (APD.cu:629-632).
 // A texel-centre fetch of the clamped linear texture returns the texel exactly.
@@ -166,13 +182,14 @@ struct RefPatch {
     float mean, var;  // E[r], E[r^2]-E[r]^2 with the reference's accumulation order
 };
 
+template <bool U>
 __device__ __forceinline__ void load_ref_patch(const PassK &K, int px, int py, RefPatch &rp) {
     float s = 0.0f, ss = 0.0f;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            const float v = tex2DLayered<float>(K.tex, px + (2 * i - 5) + 0.5f, py + (2 * j - 5) + 0.5f, K.ref_layer);
+            const float v = fetch<U>(K, px + (2 * i - 5) + 0.5f, py + (2 * j - 5) + 0.5f, K.ref_layer);
             rp.r[i * 6 + j] = v;
             s += v;
             ss = fmaf(v, v, ss);
@@ -203,6 +220,7 @@ __device__ __forceinline__ Homog make_homography(const ViewK &vk, float3 m) {
 }
 
 // NCC of the warped 6x6 patch against the register-resident reference patch.  APD.cu:622-662.
+template <bool U>
 __device__ __forceinline__ float patch_ncc36(const PassK &K, const Homog &Hm, int layer, int px, int py,
                                              const RefPatch &rp) {
     const float *h = Hm.h;
@@ -219,7 +237,7 @@ __device__ __forceinline__ float patch_ncc36(const PassK &K, const Homog &Hm, in
             const float yj = (float)(py + 2 * j - 5);
             const float X = fmaf(g1, yj, bx), Y = fmaf(g4, yj, by), Z = fmaf(h[7], yj, bz);
             const float iz = rcp_approx(Z);
-            const float s = tex2DLayered<float>(K.tex, X * iz, Y * iz, layer);
+            const float s = fetch<U>(K, X * iz, Y * iz, layer);
             sum_s += s;
             sum_ss = fmaf(s, s, sum_ss);
             sum_rs = fmaf(rp.r[i * 6 + j], s, sum_rs);
@@ -234,6 +252,7 @@ __device__ __forceinline__ float patch_ncc36(const PassK &K, const Homog &Hm, in
 }
 
 // ComputeBilateralNCCOld, APD.cu:596-663 (branch A).  Only the patch centre is bounds-checked (quirk 8).
+template <bool U>
 __device__ __forceinline__ float ncc_old(const PassK &K, const ViewK &vk, int px, int py, float3 m, const RefPatch &rp) {
     const Homog Hm = make_homography(vk, m);
     const float *h = Hm.h;
@@ -243,7 +262,7 @@ __device__ __forceinline__ float ncc_old(const PassK &K, const ViewK &vk, int px
     const float ptx = (h[0] * fxp + h[1] * fyp + h[2]) * iz;
     const float pty = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
     if (ptx >= (float)K.W || ptx < 0.0f || pty >= (float)K.H || pty < 0.0f) return 2.0f;
-    return patch_ncc36(K, Hm, vk.layer, px, py, rp);
+    return patch_ncc36<U>(K, Hm, vk.layer, px, py, rp);
 }
 
 // Reference side of the (up to) 8 anchor patches of a WEAK pixel: 3x3 taps (weak_radius 5, weak_increment 5) and their
@@ -255,6 +274,7 @@ struct AnchorRef {
     short2 a[8];  // x == -1: no anchor in this slot
 };
 
+template <bool U>
 __device__ __forceinline__ void load_anchor_ref(const PassK &K, const short2 *anc, AnchorRef &ar) {
 #pragma unroll 1
     for (int k = 0; k < 8; ++k) {
@@ -267,7 +287,7 @@ __device__ __forceinline__ void load_anchor_ref(const PassK &K, const short2 *an
         for (int i = -5; i <= 5; i += 5) {
 #pragma unroll
             for (int j = -5; j <= 5; j += 5) {
-                const float r = tex2DLayered<float>(K.tex, (float)(a.x + i) + 0.5f, (float)(a.y + j) + 0.5f, K.ref_layer);
+                const float r = fetch<U>(K, (float)(a.x + i) + 0.5f, (float)(a.y + j) + 0.5f, K.ref_layer);
                 ar.r[k * 9 + t++] = r;
                 sr += r;
                 srr = fmaf(r, r, srr);
@@ -280,6 +300,7 @@ __device__ __forceinline__ void load_anchor_ref(const PassK &K, const short2 *an
 }
 
 // NCC of one 3x3 anchor patch: only the source samples are gathered here
+template <bool U>
 __device__ __forceinline__ float patch_ncc9(const PassK &K, const Homog &Hm, int layer, int ax, int ay, const float *r9,
                                             float mean_r, float var_r) {
     const float *h = Hm.h;
@@ -293,7 +314,7 @@ __device__ __forceinline__ float patch_ncc9(const PassK &K, const Homog &Hm, int
             const float Z = h[6] * fxp + h[7] * fyp + h[8];
             const float iz = rcp_approx(Z);
             const float X = (h[0] * fxp + h[1] * fyp + h[2]) * iz, Y = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
-            const float s = tex2DLayered<float>(K.tex, X + 0.5f, Y + 0.5f, layer);
+            const float s = fetch<U>(K, X + 0.5f, Y + 0.5f, layer);
             ss += s; sss = fmaf(s, s, sss); srs = fmaf(r9[t++], s, srs);
         }
     }
@@ -306,6 +327,7 @@ __device__ __forceinline__ float patch_ncc9(const PassK &K, const Homog &Hm, int
 }
 
 // ComputeBilateralNCCNew, APD.cu:448-593 (sa_mask == 0): centre patch + focal-weighted anchor patches.
+template <bool U>
 __device__ __forceinline__ float ncc_new(const PassK &K, const ViewK &vk, int view_bit, int px, int py, float3 m,
                                          const RefPatch &rp, const AnchorRef &ar) {
     const Homog Hm = make_homography(vk, m);
@@ -318,7 +340,7 @@ __device__ __forceinline__ float ncc_new(const PassK &K, const ViewK &vk, int vi
         if (ptx >= fW || ptx < 0.0f || pty >= fH || pty < 0.0f) return 2.0f;
     }
     // anchor 0 is the pixel itself (APD.cu:1887): its bounds test repeats the centre test above
-    const float center_cost = patch_ncc36(K, Hm, vk.layer, px, py, rp);
+    const float center_cost = patch_ncc36<U>(K, Hm, vk.layer, px, py, rp);
     float sc[8];
     int ns = 0;
 #pragma unroll 1
@@ -332,7 +354,7 @@ __device__ __forceinline__ float ncc_new(const PassK &K, const ViewK &vk, int vi
             if ((K.sel[a.x + a.y * K.W] >> view_bit) & 1u) sc[ns++] = 2.0f;
             continue;
         }
-        sc[ns++] = patch_ncc9(K, Hm, vk.layer, a.x, a.y, &ar.r[k * 9], ar.mean[k], ar.var[k]);
+        sc[ns++] = patch_ncc9<U>(K, Hm, vk.layer, a.x, a.y, &ar.r[k * 9], ar.mean[k], ar.var[k]);
     }
     if (ns == 0) return center_cost;
     float mx = -1e10f;

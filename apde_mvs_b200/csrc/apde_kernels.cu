@@ -15,7 +15,8 @@ namespace apde {
 
 // -------------------------------------------------------------------------------------------- K5 init
 // RandomInitialization + ComputeMultiViewInitialCostandSelectedViews, APD.cu:919-948, 723-774
-__global__ void __launch_bounds__(128) k_init(const __grid_constant__ PassK K, int tiles_x) {
+template <bool U>
+__device__ __forceinline__ void k_init_body(const PassK &K, int tiles_x) {
     int px, py;
     if (!full_pixel(K, tiles_x, px, py)) return;
     const int center = py * K.W + px;
@@ -32,15 +33,15 @@ __global__ void __launch_bounds__(128) k_init(const __grid_constant__ PassK K, i
     K.planes[center] = pl;
 
     RefPatch rp;
-    load_ref_patch(K, px, py, rp);
+    load_ref_patch<U>(K, px, py, rp);
     const float3 m = plane_row(K, pl);
     const bool weak = K.use_apd && K.weak[center] == APDE_WEAK;
     float cv[kMaxSrc], cvc[kMaxSrc];
     int num_valid = 0;
     AnchorRef ar;
-    if (weak) load_anchor_ref(K, K.anchors + (size_t)center * APDE_ANCHOR_NUM, ar);
+    if (weak) load_anchor_ref<U>(K, K.anchors + (size_t)center * APDE_ANCHOR_NUM, ar);
     for (int v = 0; v < K.N; ++v) {
-        const float c = weak ? ncc_new(K, K.v[v], v, px, py, m, rp, ar) : ncc_old(K, K.v[v], px, py, m, rp);
+        const float c = weak ? ncc_new<U>(K, K.v[v], v, px, py, m, rp, ar) : ncc_old<U>(K, K.v[v], px, py, m, rp);
         cv[v] = c; cvc[v] = c;
         if (c < 2.0f) num_valid++;
     }
@@ -65,6 +66,11 @@ __global__ void __launch_bounds__(128) k_init(const __grid_constant__ PassK K, i
     K.costs[center] = cost;
     count_evals(K, weak ? 0 : K.N, weak ? K.N : 0, 0);
 }
+__global__ void __launch_bounds__(128) k_init(const __grid_constant__ PassK K, int tiles_x) {
+    if (K.tex_unorm > 0.0f) k_init_body<true>(K, tiles_x);
+    else k_init_body<false>(K, tiles_x);
+}
+
 
 // -------------------------------------------------------------------------------------------- K6 strong propagation
 // Black/RedPixelUpdateStrong -> CheckerboardPropagationStrong -> PlaneHypothesisRefinementStrong,
@@ -75,7 +81,8 @@ __global__ void __launch_bounds__(128) k_init(const __grid_constant__ PassK K, i
 // phase 3: current hypothesis + 5 refinement candidates, evaluated ONLY on views with non-zero weight -- zero-weight
 //          views contribute exactly 0 to the reference's weighted sums (costs are finite by construction), so
 //          skipping them is bit-identical and removes (N - S) of every N evaluations here.
-__global__ void __launch_bounds__(128) k_prop_strong(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
+template <bool U>
+__device__ __forceinline__ void k_prop_strong_body(const PassK &K, int iter, int color, int tiles_x,
                                                      int ylimit) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
@@ -89,7 +96,7 @@ __global__ void __launch_bounds__(128) k_prop_strong(const __grid_constant__ Pas
     float *sp = sc + 8 * N * stride;                        // [N][stride]
 
     RefPatch rp;
-    load_ref_patch(K, px, py, rp);
+    load_ref_patch<U>(K, px, py, rp);
     unsigned n_old = 0, n_geom = 0;
 
     int pos[8];
@@ -99,7 +106,7 @@ __global__ void __launch_bounds__(128) k_prop_strong(const __grid_constant__ Pas
         if ((flags >> h) & 1u) {
             const float3 m = plane_row(K, K.planes[pos[h]]);
 #pragma unroll 1
-            for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_old(K, K.v[v], px, py, m, rp);
+            for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_old<U>(K, K.v[v], px, py, m, rp);
             n_old += N;
         } else {
             // quirk 2: "float cost_array[8][32] = {2.0f}" leaves every entry 0 except [0][0]
@@ -155,7 +162,7 @@ __global__ void __launch_bounds__(128) k_prop_strong(const __grid_constant__ Pas
         float acc = 0.0f;
         for (uint32_t mk = wmask; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            float c = ncc_old(K, s_vk[v], px, py, m, rp);
+            float c = ncc_old<U>(K, s_vk[v], px, py, m, rp);
             n_old++;
             if (use_geom) { c = c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, plane_c); n_geom++; }
             acc += (float)vw_get(w, v) * c;
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(128) k_prop_strong(const __grid_constant__ Pas
         float acc = 0.0f;
         for (uint32_t mk = wmask; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            float c = ncc_old(K, s_vk[v], px, py, m, rp);
+            float c = ncc_old<U>(K, s_vk[v], px, py, m, rp);
             n_old++;
             if (use_geom) { c = c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp); n_geom++; }
             acc += (float)vw_get(w, v) * c;
@@ -210,6 +217,12 @@ __global__ void __launch_bounds__(128) k_prop_strong(const __grid_constant__ Pas
     }
     count_evals(K, n_old, 0, n_geom);
 }
+__global__ void __launch_bounds__(128) k_prop_strong(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
+                                                     int ylimit) {
+    if (K.tex_unorm > 0.0f) k_prop_strong_body<true>(K, iter, color, tiles_x, ylimit);
+    else k_prop_strong_body<false>(K, iter, color, tiles_x, ylimit);
+}
+
 
 // -------------------------------------------------------------------------------------------- K9
 // GetDepthandNormal, APD.cu:1694-1709
@@ -270,7 +283,8 @@ __global__ void __launch_bounds__(128) k_median(const __grid_constant__ PassK K,
 
 // -------------------------------------------------------------------------------------------- K11 DepthToWeak
 // APD.cu:2103-2250: 61-sample disparity sweep of the view-weighted cost -> WEAK / STRONG / UNKNOWN
-__global__ void __launch_bounds__(128) k_depth_to_weak(const __grid_constant__ PassK K, int tiles_x, float *curve) {
+template <bool U>
+__device__ __forceinline__ void k_depth_to_weak_body(const PassK &K, int tiles_x, float *curve) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
     int px, py;
@@ -296,7 +310,7 @@ __global__ void __launch_bounds__(128) k_depth_to_weak(const __grid_constant__ P
     base_line /= valid_src;
 
     RefPatch rp;
-    load_ref_patch(K, px, py, rp);
+    load_ref_patch<U>(K, px, py, rp);
     unsigned n_old = 0, n_geom = 0;
     const float fb = K.fx * base_line;
     const float disp = fb / origin_depth;
@@ -312,7 +326,7 @@ __global__ void __launch_bounds__(128) k_depth_to_weak(const __grid_constant__ P
         float p_cost = 0.0f;
         for (uint32_t mk = sel; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            float tc = ncc_old(K, s_vk[v], px, py, m, rp);
+            float tc = ncc_old<U>(K, s_vk[v], px, py, m, rp);
             n_old++;
             if (K.geom) { tc += K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp); n_geom++; }
             p_cost += tc * (float)vw_get(w, v);
@@ -343,6 +357,11 @@ __global__ void __launch_bounds__(128) k_depth_to_weak(const __grid_constant__ P
     var /= (peak_count - 1);
     K.weak[center] = (var > 0.2f) ? APDE_STRONG : APDE_WEAK;
 }
+__global__ void __launch_bounds__(128) k_depth_to_weak(const __grid_constant__ PassK K, int tiles_x, float *curve) {
+    if (K.tex_unorm > 0.0f) k_depth_to_weak_body<true>(K, tiles_x, curve);
+    else k_depth_to_weak_body<false>(K, tiles_x, curve);
+}
+
 
 // -------------------------------------------------------------------------------------------- K12 confidence
 // ConfidenceCompute, APD.cu:2282-2344
@@ -384,7 +403,8 @@ __global__ void __launch_bounds__(128) k_confidence(const __grid_constant__ Pass
 
 // -------------------------------------------------------------------------------------------- K13 local refine
 // LocalRefine, APD.cu:2346-2432
-__global__ void __launch_bounds__(128) k_local_refine(const __grid_constant__ PassK K, int tiles_x) {
+template <bool U>
+__device__ __forceinline__ void k_local_refine_body(const PassK &K, int tiles_x) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
     int px, py;
@@ -397,7 +417,7 @@ __global__ void __launch_bounds__(128) k_local_refine(const __grid_constant__ Pa
     if (sel == 0u) return;
     const uint4 w = K.vw[center];
     RefPatch rp;
-    load_ref_patch(K, px, py, rp);
+    load_ref_patch<U>(K, px, py, rp);
     unsigned n_old = 0, n_geom = 0;
     float cost_now = 0.0f, base_line = 0.0f, weight_normal = 0.0f;
     int valid_src = 0;
@@ -407,7 +427,7 @@ __global__ void __launch_bounds__(128) k_local_refine(const __grid_constant__ Pa
         const float3 m = plane_row(K, tp);
         for (uint32_t mk = sel; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            float tc = ncc_old(K, s_vk[v], px, py, m, rp);
+            float tc = ncc_old<U>(K, s_vk[v], px, py, m, rp);
             n_old++;
             if (K.geom) { tc += K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp); n_geom++; }
             const float wv = (float)vw_get(w, v);
@@ -434,7 +454,7 @@ __global__ void __launch_bounds__(128) k_local_refine(const __grid_constant__ Pa
         for (uint32_t mk = sel; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
             const float wv = (float)vw_get(w, v);
-            tc += ncc_old(K, s_vk[v], px, py, m, rp) * wv;
+            tc += ncc_old<U>(K, s_vk[v], px, py, m, rp) * wv;
             n_old++;
             if (K.geom) { tc += K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp) * wv; n_geom++; }
         }
@@ -444,6 +464,11 @@ __global__ void __launch_bounds__(128) k_local_refine(const __grid_constant__ Pa
     if ((double)(cost_now - min_cost) > 0.1) K.planes[center].w = best_depth;
     count_evals(K, n_old, 0, n_geom);
 }
+__global__ void __launch_bounds__(128) k_local_refine(const __grid_constant__ PassK K, int tiles_x) {
+    if (K.tex_unorm > 0.0f) k_local_refine_body<true>(K, tiles_x);
+    else k_local_refine_body<false>(K, tiles_x);
+}
+
 
 // -------------------------------------------------------------------------------------------- pixel lists
 // One pass over the 8x8 tiles: every pixel the red/black kernels would visit is appended to the list of its
@@ -484,7 +509,8 @@ cudaError_t launch_build_lists(const PassK &K, int *lists, int *counts, int cap,
 }
 
 // -------------------------------------------------------------------------------------------- parity hook
-__global__ void __launch_bounds__(128) k_eval_costs(const __grid_constant__ PassK K, int n, const int *__restrict__ tuples,
+template <bool U>
+__device__ __forceinline__ void k_eval_costs_body(const PassK &K, int n, const int *__restrict__ tuples,
                                                     const float4 *__restrict__ planes, int mode, float *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -495,18 +521,24 @@ __global__ void __launch_bounds__(128) k_eval_costs(const __grid_constant__ Pass
         c = geom_cost(K, K.v[v], v, px, py, pl);
     } else {
         RefPatch rp;
-        load_ref_patch(K, px, py, rp);
+        load_ref_patch<U>(K, px, py, rp);
         const float3 m = plane_row(K, pl);
         if (mode == 0) {
-            c = ncc_old(K, K.v[v], px, py, m, rp);
+            c = ncc_old<U>(K, K.v[v], px, py, m, rp);
         } else {
             AnchorRef ar;
-            load_anchor_ref(K, K.anchors + (size_t)(py * K.W + px) * APDE_ANCHOR_NUM, ar);
-            c = ncc_new(K, K.v[v], v, px, py, m, rp, ar);
+            load_anchor_ref<U>(K, K.anchors + (size_t)(py * K.W + px) * APDE_ANCHOR_NUM, ar);
+            c = ncc_new<U>(K, K.v[v], v, px, py, m, rp, ar);
         }
     }
     out[i] = c;
 }
+__global__ void __launch_bounds__(128) k_eval_costs(const __grid_constant__ PassK K, int n, const int *__restrict__ tuples,
+                                                    const float4 *__restrict__ planes, int mode, float *__restrict__ out) {
+    if (K.tex_unorm > 0.0f) k_eval_costs_body<true>(K, n, tuples, planes, mode, out);
+    else k_eval_costs_body<false>(K, n, tuples, planes, mode, out);
+}
+
 
 // -------------------------------------------------------------------------------------------- launchers
 static size_t prop_smem_bytes(int N, int threads) { return sizeof(float) * ((size_t)views_smem_floats(N) + (size_t)9 * N * threads); }

@@ -78,6 +78,7 @@ cudaError_t launch_resize_nearest(const void *src, int W, int H, void *dst, int 
 cudaError_t launch_planes_from_maps(const float *depth, const float *normal, float4 *planes, int P, cudaStream_t st);
 cudaError_t launch_fill_u8(uint8_t *dst, uint8_t v, size_t n, cudaStream_t st);
 cudaError_t launch_float_to_half(const float *src, void *dst, size_t n, cudaStream_t st);
+cudaError_t launch_float_to_u16x4(const float *src, void *dst, size_t n, cudaStream_t st);
 // ProcessProblem tail (main.cpp:168-178): depth range check, normals, states
 cudaError_t launch_finish(const float4 *planes, uint8_t *weak, float *depth, float *normal, uint8_t *weak_out, int P,
                           float dmin, float dmax, cudaStream_t st);

@@ -82,6 +82,16 @@ cudaError_t launch_float_to_half(const float *src, void *dst, size_t n, cudaStre
     return cudaGetLastError();
 }
 
+// pyramid levels that are exact 2x2 means of 8-bit pixels: 4 x value is an integer <= 1020
+__global__ void __launch_bounds__(256) k_float_to_u16x4(const float *__restrict__ src, unsigned short *__restrict__ dst, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (unsigned short)__float2int_rn(src[i] * 4.0f);
+}
+cudaError_t launch_float_to_u16x4(const float *src, void *dst, size_t n, cudaStream_t st) {
+    k_float_to_u16x4<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, (unsigned short *)dst, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fill_u8(uint8_t *dst, uint8_t v, size_t n, cudaStream_t st) { return cudaMemsetAsync(dst, v, n, st); }
 
 // ProcessProblem tail, main.cpp:168-178

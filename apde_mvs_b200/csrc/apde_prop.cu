@@ -35,8 +35,8 @@ __device__ __forceinline__ bool prop_pixel(const PassK &K, const PropK &B, int p
 }
 
 // ------------------------------------------------------------------------------------------------ P0 candidates
-template <bool WEAK>
-__global__ void __launch_bounds__(128) k_prop_candidates(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
+template <bool WEAK, bool U>
+__device__ __forceinline__ void k_prop_candidates_body(const PassK &K, const PropK &B) {
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     int px, py, center;
     if (!prop_pixel(K, B, pix, px, py, center)) return;
@@ -64,12 +64,18 @@ __global__ void __launch_bounds__(128) k_prop_candidates(const __grid_constant__
     // the reference patch is gathered ONCE per pixel and half-sweep; the column kernels re-load it with coalesced LDGs
     // (one column per thread would otherwise spend 36 texture fetches per column on it)
     RefPatch rp;
-    load_ref_patch(K, px, py, rp);
+    load_ref_patch<U>(K, px, py, rp);
 #pragma unroll
     for (int k = 0; k < kPatch; ++k) B.refpatch[(size_t)k * B.cap + pix] = rp.r[k];
     B.refpatch[(size_t)kPatch * B.cap + pix] = rp.mean;
     B.refpatch[(size_t)(kPatch + 1) * B.cap + pix] = rp.var;
 }
+template <bool WEAK>
+__global__ void __launch_bounds__(128) k_prop_candidates(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
+    if (K.tex_unorm > 0.0f) k_prop_candidates_body<WEAK, true>(K, B);
+    else k_prop_candidates_body<WEAK, false>(K, B);
+}
+
 
 __device__ __forceinline__ void load_ref_patch_g(const PropK &B, int pix, RefPatch &rp) {
 #pragma unroll
@@ -79,8 +85,8 @@ __device__ __forceinline__ void load_ref_patch_g(const PropK &B, int pix, RefPat
 }
 
 // ------------------------------------------------------------------------------------------------ P1 phase-1 columns
-template <bool WEAK>
-__global__ void __launch_bounds__(128) k_prop_eval1(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
+template <bool WEAK, bool U>
+__device__ __forceinline__ void k_prop_eval1_body(const PassK &K, const PropK &B) {
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y;
     int px, py, center;
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(128) k_prop_eval1(const __grid_constant__ Pass
     RefPatch rp;
     load_ref_patch_g(B, pix, rp);
     AnchorRef ar;
-    if (WEAK) load_anchor_ref(K, K.anchors + (size_t)center * APDE_ANCHOR_NUM, ar);
+    if (WEAK) load_anchor_ref<U>(K, K.anchors + (size_t)center * APDE_ANCHOR_NUM, ar);
     const unsigned flags = B.cand_flags[pix] & 0xffu;
     unsigned n_eval = 0;
 #pragma unroll 1
@@ -99,7 +105,7 @@ __global__ void __launch_bounds__(128) k_prop_eval1(const __grid_constant__ Pass
         if (h == 8 || ((flags >> h) & 1u)) {
             const float4 pl = (h == 8) ? K.planes[center] : K.planes[B.cand_pos[(size_t)h * B.cap + pix]];
             const float3 m = plane_row(K, pl);
-            c = WEAK ? ncc_new(K, vk, v, px, py, m, rp, ar) : ncc_old(K, vk, px, py, m, rp);
+            c = WEAK ? ncc_new<U>(K, vk, v, px, py, m, rp, ar) : ncc_old<U>(K, vk, px, py, m, rp);
             n_eval++;
         } else {
             c = (h == 0 && v == 0) ? 2.0f : 0.0f;  // quirk 2: "cost_array[8][32] = {2.0f}" zero-fills all but [0][0]
@@ -108,6 +114,12 @@ __global__ void __launch_bounds__(128) k_prop_eval1(const __grid_constant__ Pass
     }
     count_evals(K, WEAK ? 0 : n_eval, WEAK ? n_eval : 0, 0);
 }
+template <bool WEAK>
+__global__ void __launch_bounds__(128) k_prop_eval1(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
+    if (K.tex_unorm > 0.0f) k_prop_eval1_body<WEAK, true>(K, B);
+    else k_prop_eval1_body<WEAK, false>(K, B);
+}
+
 
 // ------------------------------------------------------------------------------------------------ P2 selection
 // joint view selection (APD.cu:1339-1386 / 1505-1552) on the stored phase-1 costs
@@ -325,8 +337,8 @@ __global__ void __launch_bounds__(256) k_prop_scatter(const int *__restrict__ fl
 }
 
 // ------------------------------------------------------------------------------------------------ P3 phase-3 columns
-template <bool WEAK>
-__global__ void __launch_bounds__(128) k_prop_eval3(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
+template <bool WEAK, bool U>
+__device__ __forceinline__ void k_prop_eval3_body(const PassK &K, const PropK &B) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -341,7 +353,7 @@ __global__ void __launch_bounds__(128) k_prop_eval3(const __grid_constant__ Pass
     RefPatch rp;
     load_ref_patch_g(B, pix, rp);
     AnchorRef ar;
-    if (WEAK) load_anchor_ref(K, K.anchors + (size_t)center * APDE_ANCHOR_NUM, ar);
+    if (WEAK) load_anchor_ref<U>(K, K.anchors + (size_t)center * APDE_ANCHOR_NUM, ar);
     const bool geom = WEAK ? (K.geom != 0) : (K.geom && K.impetus);
     const int nh = WEAK ? 11 : 5;
     unsigned n_eval = 0, n_geom = 0;
@@ -349,13 +361,19 @@ __global__ void __launch_bounds__(128) k_prop_eval3(const __grid_constant__ Pass
     for (int i = 0; i < nh; ++i) {
         const float4 tp = B.hyp[(size_t)i * cap + pix];
         const float3 m = plane_row(K, tp);
-        float c = WEAK ? ncc_new(K, vk, v, px, py, m, rp, ar) : ncc_old(K, vk, px, py, m, rp);
+        float c = WEAK ? ncc_new<U>(K, vk, v, px, py, m, rp, ar) : ncc_old<U>(K, vk, px, py, m, rp);
         n_eval++;
         if (geom) { c = c + K.geom_factor * geom_cost(K, vk, v, px, py, tp); n_geom++; }
         B.cost3[(size_t)i * nflat + col] = c;
     }
     count_evals(K, WEAK ? 0 : n_eval, WEAK ? n_eval : 0, n_geom);
 }
+template <bool WEAK>
+__global__ void __launch_bounds__(128) k_prop_eval3(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
+    if (K.tex_unorm > 0.0f) k_prop_eval3_body<WEAK, true>(K, B);
+    else k_prop_eval3_body<WEAK, false>(K, B);
+}
+
 
 // ------------------------------------------------------------------------------------------------ P4 final decision
 template <bool WEAK>

@@ -36,7 +36,7 @@ __device__ __forceinline__ void q_load_ref(const PassK &K, int px, int py, QRef 
     for (int i = 0; i < 6; ++i) {
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            const float v = tex2DLayered<float>(K.tex, px + (2 * i - 5) + 0.5f, py + (2 * j - 5) + 0.5f, K.ref_layer);
+            const float v = K.tex_unorm > 0.0f ? fetch<true>(K, px + (2 * i - 5) + 0.5f, py + (2 * j - 5) + 0.5f, K.ref_layer) : fetch<false>(K, px + (2 * i - 5) + 0.5f, py + (2 * j - 5) + 0.5f, K.ref_layer);
             rp.r[i * 6 + j] = v;
             s += v;
             ss = fmaf(v, v, ss);
@@ -72,7 +72,7 @@ __device__ __forceinline__ float q_ncc_old(const PassK &K, const ViewK &vk, int 
         const float bx = fmaf(g0, xi, g2), by = fmaf(g3, xi, g5), bz = fmaf(h[6], xi, h[8]);
         const float X = fmaf(g1, yj, bx), Y = fmaf(g4, yj, by), Z = fmaf(h[7], yj, bz);
         const float iz = rcp_approx(Z);
-        s[t] = tex2DLayered<float>(K.tex, X * iz, Y * iz, layer);
+        s[t] = K.tex_unorm > 0.0f ? fetch<true>(K, X * iz, Y * iz, layer) : fetch<false>(K, X * iz, Y * iz, layer);
     }
     float sum_s = 0.0f, sum_ss = 0.0f, sum_rs = 0.0f;
 #pragma unroll

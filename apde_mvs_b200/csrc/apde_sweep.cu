@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256) k_sweep_scatter(const int *__restrict__ f
     if (i < nflat && flags[i]) colmap[colidx[i]] = (int)i;
 }
 
-__global__ void __launch_bounds__(128) k_sweep_columns(const __grid_constant__ PassK K, int dtw, const int *__restrict__ colmap,
+template <bool U>
+__device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, const int *__restrict__ colmap,
                                                        int ncols, float *__restrict__ ncc, float *__restrict__ geo) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(128) k_sweep_columns(const __grid_constant__ P
     for (uint32_t mk = sel; mk; mk &= mk - 1) { base_line += s_vk[__ffs(mk) - 1].baseline; valid_src++; }
     base_line /= valid_src;
     RefPatch rp;
-    load_ref_patch(K, px, py, rp);
+    load_ref_patch<U>(K, px, py, rp);
     unsigned n_old = 0, n_geom = 0;
     const float fb = K.fx * base_line;
     const float disp = fb / origin_depth;
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(128) k_sweep_columns(const __grid_constant__ P
         float4 tp = opl;
         tp.w = distance_to_origin(K, px, py, p_depth, tp);
         const float3 m = plane_row(K, tp);
-        ncc[(size_t)(pd + kSweepR) * ncols + col] = ncc_old(K, vk, px, py, m, rp);
+        ncc[(size_t)(pd + kSweepR) * ncols + col] = ncc_old<U>(K, vk, px, py, m, rp);
         n_old++;
         if (K.geom) { geo[(size_t)(pd + kSweepR) * ncols + col] = geom_cost(K, vk, v, px, py, tp); n_geom++; }
     }
@@ -88,12 +89,18 @@ __global__ void __launch_bounds__(128) k_sweep_columns(const __grid_constant__ P
         float4 tp = opl;
         tp.w = distance_to_origin(K, px, py, origin_depth, tp);
         const float3 m = plane_row(K, tp);
-        ncc[(size_t)kSweepN * ncols + col] = ncc_old(K, vk, px, py, m, rp);
+        ncc[(size_t)kSweepN * ncols + col] = ncc_old<U>(K, vk, px, py, m, rp);
         n_old++;
         if (K.geom) { geo[(size_t)kSweepN * ncols + col] = geom_cost(K, vk, v, px, py, tp); n_geom++; }
     }
     count_evals(K, n_old, 0, n_geom);
 }
+__global__ void __launch_bounds__(128) k_sweep_columns(const __grid_constant__ PassK K, int dtw, const int *__restrict__ colmap,
+                                                       int ncols, float *__restrict__ ncc, float *__restrict__ geo) {
+    if (K.tex_unorm > 0.0f) k_sweep_columns_body<true>(K, dtw, colmap, ncols, ncc, geo);
+    else k_sweep_columns_body<false>(K, dtw, colmap, ncols, ncc, geo);
+}
+
 
 // DepthToWeak decision logic, APD.cu:2157-2249
 __global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ PassK K, const int *__restrict__ colidx, int ncols,
