@@ -133,11 +133,13 @@ def load_library(path=None):
     lib.apde_schedule_num_passes.argtypes = [P, C.POINTER(Schedule)]
     lib.apde_get_counters.argtypes = [P, C.POINTER(C.c_uint64), C.c_int]
     lib.apde_set_profiling.argtypes = [P, C.c_int]
+    lib.apde_set_sweep_budget_mb.argtypes = [P, C.c_size_t]
     lib.apde_get_stage_stats.argtypes = [P, P, P, P, C.c_int]
     lib.apde_microbench.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.apde_depth_pool.argtypes = [P, C.POINTER(P), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.apde_weak_vis_filter.argtypes = [P, P]
     lib.apde_fuse.argtypes = [P, C.c_int, P, P, C.c_int64, C.POINTER(C.c_int64)]
+    lib.apde_fuse_variant.argtypes = [P, C.c_int, C.c_int, P, P, C.c_int64, C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 
@@ -326,6 +328,9 @@ class Context:
         self._check(self.lib.apde_get_counters(self._h, out, 1 if reset else 0))
         return [int(x) for x in out]
 
+    def set_sweep_budget_mb(self, mb):
+        self._check(self.lib.apde_set_sweep_budget_mb(self._h, C.c_size_t(mb)))
+
     def set_profiling(self, on=True):
         self._check(self.lib.apde_set_profiling(self._h, int(on)))
 
@@ -353,13 +358,15 @@ class Context:
         self._check(self.lib.apde_weak_vis_filter(self._h, _ptr(skip)))
         return skip
 
-    def fuse(self, use_weak_filter=True, max_points=None):
+    def fuse(self, use_weak_filter=True, max_points=None, variant=0):
+        """variant 0 = RunFusion, 1 = RunFusion_TAT_I, 2 = RunFusion_TAT_A (main.cpp:277-283)"""
         n = C.c_int64()
         if max_points is None:
-            self._check(self.lib.apde_fuse(self._h, int(use_weak_filter), None, None, 0, C.byref(n)))
+            self._check(self.lib.apde_fuse_variant(self._h, variant, int(use_weak_filter), None, None, 0, C.byref(n)))
             max_points = n.value
         xyz = np.zeros((max_points, 3), np.float32)
         bgr = np.zeros((max_points, 3), np.float32)
-        self._check(self.lib.apde_fuse(self._h, int(use_weak_filter), _ptr(xyz), _ptr(bgr), max_points, C.byref(n)))
+        self._check(self.lib.apde_fuse_variant(self._h, variant, int(use_weak_filter), _ptr(xyz), _ptr(bgr), max_points,
+                                               C.byref(n)))
         k = min(n.value, max_points)
         return xyz[:k], bgr[:k]

@@ -221,7 +221,10 @@ int apde_scene_begin(apde_context *c, int num_views, int width, int height) {
     if (c->committed && c->V == num_views && c->W == width && c->H == height) {
         // same shape as the resident scene: keep every allocation, only forget the maps and the pyramid level
         CU(cudaStreamSynchronize(c->stream));
-        for (auto &v : c->views) { v.mw = v.mh = 0; v.has_conf = false; v.src.clear(); }
+        for (auto &v : c->views) {
+            v.mw = v.mh = 0; v.has_conf = false; v.src.clear();
+            CU(cudaMemsetAsync(v.d_conf, 0, (size_t)c->W * c->H, c->stream));
+        }
         for (auto &L : c->levels) L.stale = true;
         c->level_scale = 0;
         c->problem_active = false;
@@ -238,6 +241,7 @@ int apde_scene_begin(apde_context *c, int num_views, int width, int height) {
         CU(cudaMalloc(&v.d_normal, P * 3 * sizeof(float)));
         CU(cudaMalloc(&v.d_weak, P));
         CU(cudaMalloc(&v.d_conf, P));
+        CU(cudaMemset(v.d_conf, 0, P));  // no confidence map exists before the first geometric / APD pass (main.cpp:187-190)
         memset(&v.cam, 0, sizeof(v.cam));
     }
     CU(cudaMalloc(&c->d_depth_pool[0], (size_t)num_views * P * sizeof(float)));
@@ -628,20 +632,9 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
                                    &c->launches);
         }
         if (!legacy && !getenv("APDE_QUAD_KERNELS")) {
-            if (stage == APDE_STAGE_DEPTH_TO_WEAK) {
-                cudaError_t e = sweep_build(Kq, c->sweep, 1, c->stream, &c->launches);
-                if (e != cudaSuccess) return e;
-                c->sweep.valid = true;
-                return sweep_classify(Kq, c->sweep, nullptr, c->stream);
-            }
-            if (stage == APDE_STAGE_LOCAL_REFINE) {
-                if (!c->sweep.valid) {
-                    cudaError_t e = sweep_build(Kq, c->sweep, 0, c->stream, &c->launches);
-                    if (e != cudaSuccess) return e;
-                }
-                c->sweep.valid = false;
-                return sweep_refine(Kq, c->sweep, c->stream);
-            }
+            // (the sweep functions count every launch but the last one; the generic count below adds that)
+            if (stage == APDE_STAGE_DEPTH_TO_WEAK) return sweep_depth_to_weak(Kq, c->sweep, nullptr, c->stream, &c->launches);
+            if (stage == APDE_STAGE_LOCAL_REFINE) return sweep_local_refine(Kq, c->sweep, c->stream, &c->launches);
         }
         return launch_stage(Kq, stage, iter, color, c->stream, nullptr);
     };
@@ -661,8 +654,9 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
     } else {
         CU(run_stage(Kl));
     }
-    c->launches++;
-    c->stage_launches[stage]++;
+    const int nl = (stage == APDE_STAGE_INIT && Kl.use_apd) ? 2 : 1;  // two-phase init (see k_init)
+    c->launches += nl;
+    c->stage_launches[stage] += nl;
     return APDE_OK;
 }
 
@@ -675,6 +669,13 @@ static int collect_stage_events(apde_context *c) {
         c->stage_ms[c->ev_stage[k]] += ms;
     }
     c->ev_stage.clear();
+    return APDE_OK;
+}
+
+int apde_set_sweep_budget_mb(apde_context *c, size_t megabytes) {
+    if (!c) return fail(APDE_ERR_ARG, "set_sweep_budget_mb: no context");
+    c->sweep.budget_mb = megabytes;
+    c->sweep.valid = false;
     return APDE_OK;
 }
 
@@ -1110,7 +1111,13 @@ int apde_weak_vis_filter(apde_context *c, uint8_t *skip_weaks) {
 }
 
 int apde_fuse(apde_context *c, int use_weak_filter, float *xyz, float *bgr, int64_t max_points, int64_t *num_points) {
+    return apde_fuse_variant(c, APDE_FUSE_DEFAULT, use_weak_filter, xyz, bgr, max_points, num_points);
+}
+
+int apde_fuse_variant(apde_context *c, int variant, int use_weak_filter, float *xyz, float *bgr, int64_t max_points,
+                      int64_t *num_points) {
     if (!c || c->V <= 0 || !num_points) return fail(APDE_ERR_STATE, "fuse: bad argument");
+    if (variant < APDE_FUSE_DEFAULT || variant > APDE_FUSE_TAT_A) return fail(APDE_ERR_ARG, "fuse: unknown variant %d", variant);
     CU(cudaSetDevice(c->device));
     std::vector<FusionView> fv;
     int mw, mh;
@@ -1124,7 +1131,9 @@ int apde_fuse(apde_context *c, int use_weak_filter, float *xyz, float *bgr, int6
         CU(cudaMemsetAsync(c->d_skip, 0, (size_t)c->V * P, c->stream));
     }
     uint64_t launches = 0;
-    cudaError_t e = fusion_run(fv, mw, mh, c->d_skip, xyz, bgr, max_points, num_points, c->stream, &launches);
+    cudaError_t e = variant == APDE_FUSE_DEFAULT
+                        ? fusion_run(fv, mw, mh, c->d_skip, xyz, bgr, max_points, num_points, c->stream, &launches)
+                        : fusion_run_tat(fv, mw, mh, variant, c->d_skip, xyz, bgr, max_points, num_points, c->stream, &launches);
     c->launches += launches;
     if (e != cudaSuccess) return fail(APDE_ERR_CUDA, "fusion: %s", cudaGetErrorString(e));
     return APDE_OK;

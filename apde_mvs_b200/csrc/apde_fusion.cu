@@ -338,4 +338,188 @@ done:
     return err;
 }
 
+// ------------------------------------------------------------------------------------------------ Tanks-and-Temples variants
+// RunFusion_TAT_I (variant 1, APD.cpp:1229-1431) and RunFusion_TAT_A (variant 2, APD.cpp:1433-1608).  masks[] of a view
+// are written only while that view is the reference and read only through its neighbours, so one view's pixels are
+// independent -- except for the reference's per-VIEW diff[] array: a neighbour that is out of bounds / masked / without
+// depth at pixel p keeps the measurements of the last pixel q < p (row-major) that did update it.  That carry-over is a
+// forward fill: last_j(p) = max{q <= p : neighbour j measured at q}, computed for every neighbour with one inclusive
+// max-scan over the pixel axis; the decision kernel then reads its measurements at last_j(p).
+struct TatMeasure { float dist, depth, angle; int q; };
+
+__global__ void __launch_bounds__(128) k_tat_measure(const FCam *__restrict__ cams, const int *__restrict__ nbr, int N, int ref,
+                                                     int W, int H, const uint8_t *__restrict__ masks,
+                                                     const uint8_t *__restrict__ skip, TatMeasure *__restrict__ meas,
+                                                     int *__restrict__ last, uint8_t *__restrict__ active) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int P = W * H;
+    if (idx >= P) return;
+    const FCam &rc = cams[ref];
+    const float ref_depth = rc.depth[idx];
+    const bool act = skip[(size_t)ref * P + idx] != 1 && !(ref_depth <= 0.0f);
+    active[idx] = act ? 1 : 0;
+    const int r = idx / W, c = idx % W;
+    float3 X = make_float3(0.f, 0.f, 0.f);
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    if (act) {
+        X = point_on_world(c, r, ref_depth, rc);
+        nx = rc.normal[3 * idx]; ny = rc.normal[3 * idx + 1]; nz = rc.normal[3 * idx + 2];
+    }
+    for (int j = 0; j < N; ++j) {
+        int l = -1;
+        if (act) {
+            const FCam &sc = cams[nbr[j]];
+            float2 pt;
+            float pd;
+            project_camera(X, sc, pt, pd);
+            const int sr = (int)(pt.y + 0.5f), scn = (int)(pt.x + 0.5f);
+            if (scn >= 0 && scn < W && sr >= 0 && sr < H) {
+                const int sp = sr * W + scn;
+                const float sd = sc.depth[sp];
+                if (masks[(size_t)nbr[j] * P + sp] != 1 && !(sd <= 0.0f)) {
+                    const float3 tX = point_on_world(scn, sr, sd, sc);
+                    float2 tp;
+                    project_camera(tX, rc, tp, pd);
+                    TatMeasure m;
+                    m.dist = (float)sqrt(pow((double)(c - tp.x), 2.0) + pow((double)(r - tp.y), 2.0));
+                    m.depth = fabsf(pd - ref_depth) / ref_depth;
+                    m.angle = get_angle(nx, ny, nz, sc.normal[3 * sp], sc.normal[3 * sp + 1], sc.normal[3 * sp + 2]);
+                    m.q = sp;
+                    meas[(size_t)j * P + idx] = m;
+                    l = idx;
+                }
+            }
+        }
+        last[(size_t)j * P + idx] = l;
+    }
+}
+
+struct MaxInt {
+    __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; }
+};
+
+__global__ void __launch_bounds__(128) k_tat_decide(int N, int P, int variant, const uint8_t *__restrict__ active,
+                                                    const TatMeasure *__restrict__ meas, const int *__restrict__ last,
+                                                    uint32_t *__restrict__ used, int *__restrict__ flags,
+                                                    uint8_t *__restrict__ mask_ref) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    uint32_t bits = 0;
+    int ok = 0;
+    if (active[idx]) {
+        const float dist_base = 0.25f;
+        const float depth_base = variant == 1 ? 1.0f / 3500.0f : 1.0f / 3000.0f;
+        const float angle_base = 0.06981317007977318f, angle_grad = 0.05235987755982988f;
+        for (int k = 2; k <= N && !ok; ++k) {
+            int count = 0;
+            bits = 0;
+            for (int j = 0; j < N; ++j) {
+                const int l = last[(size_t)j * P + idx];
+                if (l < 0) continue;  // CostData() defaults: FLT_MAX never passes
+                const TatMeasure m = meas[(size_t)j * P + l];
+                bool pass = m.dist < k * dist_base && m.depth < k * depth_base;
+                if (variant == 1) pass = pass && m.angle < (k * angle_grad + angle_base);
+                if (pass) { count++; bits |= 1u << j; }
+            }
+            if (count >= k) ok = 1;
+        }
+    }
+    used[idx] = ok ? bits : 0u;
+    flags[idx] = ok;
+    if (ok) mask_ref[idx] = 1;
+}
+
+__global__ void __launch_bounds__(128) k_tat_emit(const FCam *__restrict__ cams, const int *__restrict__ nbr, int N, int ref,
+                                                  int W, int H, int variant, const TatMeasure *__restrict__ meas,
+                                                  const int *__restrict__ last, const uint32_t *__restrict__ used,
+                                                  const int *__restrict__ flags, const int *__restrict__ offs,
+                                                  float *__restrict__ xyz, float *__restrict__ bgr) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int P = W * H;
+    if (idx >= P || !flags[idx]) return;
+    const FCam &rc = cams[ref];
+    const int o = offs[idx];
+    const float3 X = point_on_world(idx % W, idx / W, rc.depth[idx], rc);
+    xyz[3 * o] = X.x; xyz[3 * o + 1] = X.y; xyz[3 * o + 2] = X.z;
+    float col[3] = {0.0f, 0.0f, 0.0f};
+    if (rc.bgr) {
+        for (int k = 0; k < 3; ++k) col[k] = (float)rc.bgr[3 * idx + k];
+        if (variant == 1) {
+            const uint32_t bits = used[idx];
+            int n = 0;
+            for (int j = 0; j < N; ++j) {
+                if (!((bits >> j) & 1u)) continue;
+                const uint8_t *sb = cams[nbr[j]].bgr;
+                const int q = meas[(size_t)j * P + last[(size_t)j * P + idx]].q;  // possibly another pixel's coordinates (quirk)
+                if (sb) for (int k = 0; k < 3; ++k) col[k] += (float)sb[3 * q + k];
+                n++;
+            }
+            for (int k = 0; k < 3; ++k) col[k] /= (n + 1.0f);
+        }
+    }
+    bgr[3 * o] = col[0]; bgr[3 * o + 1] = col[1]; bgr[3 * o + 2] = col[2];
+}
+
+cudaError_t fusion_run_tat(const std::vector<FusionView> &views, int w, int h, int variant, const uint8_t *skip, float *xyz,
+                           float *bgr, int64_t max_points, int64_t *num_points, cudaStream_t st, uint64_t *launches) {
+    const int V = (int)views.size(), P = w * h;
+    cudaError_t err = cudaSuccess;
+    FCam *d_cams = nullptr;
+    uint8_t *d_masks = nullptr, *d_active = nullptr;
+    int *d_nbr = nullptr, *d_last = nullptr, *d_flags = nullptr, *d_offs = nullptr;
+    TatMeasure *d_meas = nullptr;
+    float *d_xyz = nullptr, *d_bgr = nullptr;
+    uint32_t *d_used = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_a = 0, tmp_b = 0;
+    int64_t total = 0;
+    int maxN = 1;
+    for (auto &v : views) maxN = std::max(maxN, (int)v.src.size());
+    const int blocks = (P + 127) / 128;
+    FCU(upload_cams(views, &d_cams));
+    FCU(cudaMalloc(&d_masks, (size_t)V * P));
+    FCU(cudaMemsetAsync(d_masks, 0, (size_t)V * P, st));
+    FCU(cudaMalloc(&d_active, P));
+    FCU(cudaMalloc(&d_nbr, maxN * sizeof(int)));
+    FCU(cudaMalloc(&d_last, (size_t)maxN * P * sizeof(int)));
+    FCU(cudaMalloc(&d_meas, (size_t)maxN * P * sizeof(TatMeasure)));
+    FCU(cudaMalloc(&d_used, (size_t)P * sizeof(uint32_t)));
+    FCU(cudaMalloc(&d_flags, (size_t)P * sizeof(int)));
+    FCU(cudaMalloc(&d_offs, (size_t)P * sizeof(int)));
+    FCU(cudaMalloc(&d_xyz, (size_t)P * 3 * sizeof(float)));
+    FCU(cudaMalloc(&d_bgr, (size_t)P * 3 * sizeof(float)));
+    FCU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_a, d_flags, d_offs, P, st));
+    FCU(cub::DeviceScan::InclusiveScan(nullptr, tmp_b, d_last, d_last, MaxInt(), P, st));
+    FCU(cudaMalloc(&d_tmp, std::max(tmp_a, tmp_b)));
+    tmp_a = tmp_b = std::max(tmp_a, tmp_b);
+
+    for (int ref = 0; ref < V; ++ref) {
+        const int N = (int)views[ref].src.size();
+        if (N < 2) continue;  // the k loop starts at 2 (APD.cpp:1382)
+        FCU(cudaMemcpyAsync(d_nbr, views[ref].src.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
+        k_tat_measure<<<blocks, 128, 0, st>>>(d_cams, d_nbr, N, ref, w, h, d_masks, skip, d_meas, d_last, d_active);
+        for (int j = 0; j < N; ++j)
+            FCU(cub::DeviceScan::InclusiveScan(d_tmp, tmp_b, d_last + (size_t)j * P, d_last + (size_t)j * P, MaxInt(), P, st));
+        k_tat_decide<<<blocks, 128, 0, st>>>(N, P, variant, d_active, d_meas, d_last, d_used, d_flags, d_masks + (size_t)ref * P);
+        FCU(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_a, d_flags, d_offs, P, st));
+        k_tat_emit<<<blocks, 128, 0, st>>>(d_cams, d_nbr, N, ref, w, h, variant, d_meas, d_last, d_used, d_flags, d_offs, d_xyz,
+                                           d_bgr);
+        if (launches) *launches += 4 + N;
+        int last_off = 0, last_flag = 0;
+        FCU(cudaMemcpyAsync(&last_off, d_offs + P - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FCU(cudaMemcpyAsync(&last_flag, d_flags + P - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FCU(cudaStreamSynchronize(st));
+        const int64_t n = (int64_t)last_off + last_flag;
+        const int64_t room = std::max<int64_t>(0, std::min<int64_t>(n, max_points - total));
+        if (room > 0 && xyz) FCU(cudaMemcpy(xyz + 3 * total, d_xyz, (size_t)room * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        if (room > 0 && bgr) FCU(cudaMemcpy(bgr + 3 * total, d_bgr, (size_t)room * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        total += n;
+    }
+    *num_points = total;
+done:
+    cudaFree(d_cams); cudaFree(d_masks); cudaFree(d_active); cudaFree(d_nbr); cudaFree(d_last); cudaFree(d_meas); cudaFree(d_used);
+    cudaFree(d_flags); cudaFree(d_offs); cudaFree(d_xyz); cudaFree(d_bgr); cudaFree(d_tmp);
+    return err;
+}
+
 }  // namespace apde

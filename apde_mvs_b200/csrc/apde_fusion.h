@@ -26,4 +26,8 @@ cudaError_t fusion_weak_vis_filter(const std::vector<FusionView> &views, int w, 
 cudaError_t fusion_run(const std::vector<FusionView> &views, int w, int h, const uint8_t *skip, float *xyz, float *bgr,
                        int64_t max_points, int64_t *num_points, cudaStream_t st, uint64_t *launches);
 
+// Tanks-and-Temples variants: 1 = RunFusion_TAT_I (APD.cpp:1229-1431), 2 = RunFusion_TAT_A (APD.cpp:1433-1608)
+cudaError_t fusion_run_tat(const std::vector<FusionView> &views, int w, int h, int variant, const uint8_t *skip, float *xyz,
+                           float *bgr, int64_t max_points, int64_t *num_points, cudaStream_t st, uint64_t *launches);
+
 }  // namespace apde

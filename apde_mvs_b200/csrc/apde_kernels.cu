@@ -15,11 +15,17 @@ namespace apde {
 
 // -------------------------------------------------------------------------------------------- K5 init
 // RandomInitialization + ComputeMultiViewInitialCostandSelectedViews, APD.cu:919-948, 723-774
+//
+// The deformable cost of a WEAK pixel reads selected_views of its (STRONG) anchors (APD.cu:502-503) -- in the reference
+// while the same kernel is still writing them, a data race.  Here the kernel runs in two phases when use_APD is set:
+// phase 0 = every pixel that is not WEAK, phase 1 = the WEAK pixels, which then see their anchors' final masks.  This is
+// one of the serialisations the reference's race allows, and it makes the pass deterministic.  phase < 0 = all pixels.
 template <bool U>
-__device__ __forceinline__ void k_init_body(const PassK &K, int tiles_x) {
+__device__ __forceinline__ void k_init_body(const PassK &K, int tiles_x, int phase) {
     int px, py;
     if (!full_pixel(K, tiles_x, px, py)) return;
     const int center = py * K.W + px;
+    if (phase >= 0 && (int)(K.weak[center] == APDE_WEAK) != phase) return;
     float4 pl;
     if (K.state == APDE_FIRST_INIT) {
         Rng rng(K.seed, K.stream, (uint32_t)center, SITE_INIT);
@@ -66,9 +72,9 @@ __device__ __forceinline__ void k_init_body(const PassK &K, int tiles_x) {
     K.costs[center] = cost;
     count_evals(K, weak ? 0 : K.N, weak ? K.N : 0, 0);
 }
-__global__ void __launch_bounds__(128) k_init(const __grid_constant__ PassK K, int tiles_x) {
-    if (K.tex_unorm > 0.0f) k_init_body<true>(K, tiles_x);
-    else k_init_body<false>(K, tiles_x);
+__global__ void __launch_bounds__(128) k_init(const __grid_constant__ PassK K, int tiles_x, int phase) {
+    if (K.tex_unorm > 0.0f) k_init_body<true>(K, tiles_x, phase);
+    else k_init_body<false>(K, tiles_x, phase);
 }
 
 
@@ -570,7 +576,12 @@ cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStr
     switch (stage) {
         case APDE_STAGE_INIT: {
             const int tiles = tiles8x * ((H + 3) / 4);
-            k_init<<<(tiles + 3) / 4, 128, 0, st>>>(K, tiles8x);
+            if (K.use_apd) {
+                k_init<<<(tiles + 3) / 4, 128, 0, st>>>(K, tiles8x, 0);
+                k_init<<<(tiles + 3) / 4, 128, 0, st>>>(K, tiles8x, 1);
+            } else {
+                k_init<<<(tiles + 3) / 4, 128, 0, st>>>(K, tiles8x, -1);
+            }
             break;
         }
         case APDE_STAGE_PROP_STRONG: {

@@ -60,14 +60,15 @@ struct SweepWorkspace {
     size_t scan_bytes = 0, flag_cap = 0, col_cap = 0, geo_cap = 0;
     float *ncc = nullptr, *geo = nullptr;      // [62][ncols] column costs (slot 61 = the current depth)
     int ncols = 0;
-    bool valid = false;                        // columns match the problem state (set by DepthToWeak, used by LocalRefine)
+    int p0 = 0, Pb = 0;                        // the band of pixels the stored columns cover
+    size_t budget_mb = 0;                      // column storage budget (0 = APDE_SWEEP_BUDGET_MB or 48 GB)
+    bool valid = false;                        // columns cover the whole image and match the problem state (set by DepthToWeak, used by LocalRefine)
     cudaError_t reserve_flags(size_t n);
     cudaError_t reserve_columns(size_t ncols, bool geom);
     void release();
 };
-cudaError_t sweep_build(const PassK &K, SweepWorkspace &ws, int dtw, cudaStream_t st, uint64_t *launches);
-cudaError_t sweep_classify(const PassK &K, SweepWorkspace &ws, float *curve, cudaStream_t st);
-cudaError_t sweep_refine(const PassK &K, SweepWorkspace &ws, cudaStream_t st);
+cudaError_t sweep_depth_to_weak(const PassK &K, SweepWorkspace &ws, float *curve, cudaStream_t st, uint64_t *launches);
+cudaError_t sweep_local_refine(const PassK &K, SweepWorkspace &ws, cudaStream_t st, uint64_t *launches);
 
 // scene / map kernels (apde_maps.cu)
 // OpenCV INTER_LINEAR resize of a u8 image to float (APD.cpp:574): dst[h][w] from src[H][W]

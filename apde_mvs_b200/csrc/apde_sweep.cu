@@ -29,15 +29,17 @@ __device__ __forceinline__ int sweep_class(const PassK &K, int px, int py, int c
     return (dtw && !border) ? 2 : 1;
 }
 
-__global__ void __launch_bounds__(256) k_sweep_prepare(const __grid_constant__ PassK K, int dtw, int *__restrict__ flags) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int P = K.W * K.H;
-    if (idx >= P) return;
+// All sweep kernels work on a BAND of whole rows: pixels [p0, p0 + Pb).  flags / colidx are [N][Pb] for the band.
+__global__ void __launch_bounds__(256) k_sweep_prepare(const __grid_constant__ PassK K, int dtw, int p0, int Pb,
+                                                       int *__restrict__ flags) {
+    const int loc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (loc >= Pb) return;
+    const int idx = p0 + loc;
     const int px = idx % K.W, py = idx / K.W;
     const int cls = sweep_class(K, px, py, idx, dtw != 0);
     if (dtw && cls != 2) K.weak[idx] = APDE_UNKNOWN;  // border / zero depth / no selected view (APD.cu:2114-2153)
     const uint32_t sel = cls ? K.sel[idx] : 0u;
-    for (int v = 0; v < K.N; ++v) flags[(size_t)v * P + idx] = (sel >> v) & 1u;
+    for (int v = 0; v < K.N; ++v) flags[(size_t)v * Pb + loc] = (sel >> v) & 1u;
 }
 
 // column number -> flat (view, pixel) index
@@ -48,15 +50,14 @@ __global__ void __launch_bounds__(256) k_sweep_scatter(const int *__restrict__ f
 }
 
 template <bool U>
-__device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, const int *__restrict__ colmap,
+__device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, int p0, int Pb, const int *__restrict__ colmap,
                                                        int ncols, float *__restrict__ ncc, float *__restrict__ geo) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
-    const int P = K.W * K.H;
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= ncols) return;
     const int flat = colmap[col];
-    const int v = flat / P, center = flat % P;
+    const int v = flat / Pb, center = p0 + flat % Pb;
     const int px = center % K.W, py = center / K.W;
     const int cls = sweep_class(K, px, py, center, dtw != 0);
     const ViewK &vk = s_vk[v];
@@ -95,22 +96,24 @@ __device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, co
     }
     count_evals(K, n_old, 0, n_geom);
 }
-__global__ void __launch_bounds__(128) k_sweep_columns(const __grid_constant__ PassK K, int dtw, const int *__restrict__ colmap,
-                                                       int ncols, float *__restrict__ ncc, float *__restrict__ geo) {
-    if (K.tex_unorm > 0.0f) k_sweep_columns_body<true>(K, dtw, colmap, ncols, ncc, geo);
-    else k_sweep_columns_body<false>(K, dtw, colmap, ncols, ncc, geo);
+__global__ void __launch_bounds__(128) k_sweep_columns(const __grid_constant__ PassK K, int dtw, int p0, int Pb,
+                                                       const int *__restrict__ colmap, int ncols, float *__restrict__ ncc,
+                                                       float *__restrict__ geo) {
+    if (K.tex_unorm > 0.0f) k_sweep_columns_body<true>(K, dtw, p0, Pb, colmap, ncols, ncc, geo);
+    else k_sweep_columns_body<false>(K, dtw, p0, Pb, colmap, ncols, ncc, geo);
 }
 
 
 // DepthToWeak decision logic, APD.cu:2157-2249
-__global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ PassK K, const int *__restrict__ colidx, int ncols,
+__global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ PassK K, int p0, int Pb,
+                                                        const int *__restrict__ colidx, int ncols,
                                                         const float *__restrict__ ncc, const float *__restrict__ geo,
                                                         float *curve) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int P = K.W * K.H;
-    if (idx >= P) return;
+    const int loc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (loc >= Pb) return;
+    const int idx = p0 + loc;
     const int px = idx % K.W, py = idx / K.W;
     if (sweep_class(K, px, py, idx, true) != 2) return;
     const float origin_depth = K.planes[idx].w;
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ 
         float p_cost = 0.0f;
         for (uint32_t mk = sel; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            const size_t o = (size_t)(pd + radius) * ncols + colidx[(size_t)v * P + idx];
+            const size_t o = (size_t)(pd + radius) * ncols + colidx[(size_t)v * Pb + loc];
             float tc = ncc[o];
             if (K.geom) tc += K.geom_factor * geo[o];
             p_cost += tc * (float)vw_get(w, v);
@@ -166,13 +169,14 @@ __global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ 
 }
 
 // LocalRefine decision logic, APD.cu:2368-2431
-__global__ void __launch_bounds__(128) k_sweep_refine(const __grid_constant__ PassK K, const int *__restrict__ colidx, int ncols,
+__global__ void __launch_bounds__(128) k_sweep_refine(const __grid_constant__ PassK K, int p0, int Pb,
+                                                      const int *__restrict__ colidx, int ncols,
                                                       const float *__restrict__ ncc, const float *__restrict__ geo) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int P = K.W * K.H;
-    if (idx >= P) return;
+    const int loc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (loc >= Pb) return;
+    const int idx = p0 + loc;
     const int px = idx % K.W, py = idx / K.W;
     if (sweep_class(K, px, py, idx, false) == 0) return;
     const float origin_depth = K.planes[idx].w;
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(128) k_sweep_refine(const __grid_constant__ Pa
     int valid_src = 0;
     for (uint32_t mk = sel; mk; mk &= mk - 1) {
         const int v = __ffs(mk) - 1;
-        const size_t o = (size_t)kSweepN * ncols + colidx[(size_t)v * P + idx];
+        const size_t o = (size_t)kSweepN * ncols + colidx[(size_t)v * Pb + loc];
         float tc = ncc[o];
         if (K.geom) tc += K.geom_factor * geo[o];
         const float wv = (float)vw_get(w, v);
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(128) k_sweep_refine(const __grid_constant__ Pa
         float tc = 0.0f;
         for (uint32_t mk = sel; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            const size_t o = (size_t)(pd + kSweepR) * ncols + colidx[(size_t)v * P + idx];
+            const size_t o = (size_t)(pd + kSweepR) * ncols + colidx[(size_t)v * Pb + loc];
             const float wv = (float)vw_get(w, v);
             tc += ncc[o] * wv;
             if (K.geom) tc += K.geom_factor * geo[o] * wv;
@@ -260,41 +264,86 @@ void SweepWorkspace::release() {
     flag_cap = col_cap = geo_cap = map_cap = 0; valid = false;
 }
 
-// columns for the current problem state; dtw = 1: DepthToWeak (+-30 for interior pixels), 0: LocalRefine only (+-5)
-cudaError_t sweep_build(const PassK &K, SweepWorkspace &ws, int dtw, cudaStream_t st, uint64_t *launches) {
-    const int P = K.W * K.H;
-    const size_t nflat = (size_t)K.N * P;
+// Rows per band so that the WORST-CASE column storage of a band (every view selected at every pixel) stays under the
+// budget: N * Pb * 62 floats (* 2 with the geometric term).  1920x1080 x 10 views fits one band (10.3 GB); 6048x4032 x 10
+// views would need 121 GB in one piece and is processed in 3 bands.  APDE_SWEEP_BUDGET_MB overrides the 48 GB default.
+static int band_rows(const PassK &K, const SweepWorkspace &ws) {
+    static const size_t env_mb = [] {
+        const char *e = getenv("APDE_SWEEP_BUDGET_MB");
+        return e ? (size_t)atoll(e) : (size_t)0;
+    }();
+    const size_t mb = ws.budget_mb ? ws.budget_mb : (env_mb ? env_mb : (size_t)49152);
+    const size_t budget = mb << 20;
+    const size_t per_row = (size_t)K.N * K.W * kSlots * sizeof(float) * (K.geom ? 2 : 1);
+    const size_t rows = budget / (per_row ? per_row : 1);
+    return (int)std::max<size_t>(1, std::min<size_t>(rows, (size_t)K.H));
+}
+
+// columns of the band [p0, p0 + Pb) for the current problem state; dtw = 1: DepthToWeak (+-30 for interior pixels), 0: LocalRefine only
+static cudaError_t sweep_build_band(const PassK &K, SweepWorkspace &ws, int dtw, int p0, int Pb, cudaStream_t st, uint64_t *launches) {
+    const size_t nflat = (size_t)K.N * Pb;
     cudaError_t e = ws.reserve_flags(nflat);
     if (e != cudaSuccess) return e;
-    k_sweep_prepare<<<(P + 255) / 256, 256, 0, st>>>(K, dtw, ws.flags);
+    k_sweep_prepare<<<(Pb + 255) / 256, 256, 0, st>>>(K, dtw, p0, Pb, ws.flags);
     if ((e = cudaMemsetAsync(ws.flags + nflat, 0, sizeof(int), st)) != cudaSuccess) return e;
     if ((e = cub::DeviceScan::ExclusiveSum(ws.scan_tmp, ws.scan_bytes, ws.flags, ws.colidx, (int)(nflat + 1), st)) != cudaSuccess) return e;
     int ncols = 0;
     if ((e = cudaMemcpyAsync(&ncols, ws.colidx + nflat, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
     ws.ncols = ncols;
+    ws.p0 = p0; ws.Pb = Pb;
     if (launches) *launches += 2;
     if (ncols > 0) {
         if ((e = ws.reserve_columns((size_t)ncols, K.geom != 0)) != cudaSuccess) return e;
         const size_t vsm = sizeof(float) * views_smem_floats(K.N);
         k_sweep_scatter<<<(unsigned)((nflat + 255) / 256), 256, 0, st>>>(ws.flags, ws.colidx, nflat, ws.colmap);
-        k_sweep_columns<<<(ncols + 127) / 128, 128, vsm, st>>>(K, dtw, ws.colmap, ncols, ws.ncc, ws.geo);
+        k_sweep_columns<<<(ncols + 127) / 128, 128, vsm, st>>>(K, dtw, p0, Pb, ws.colmap, ncols, ws.ncc, ws.geo);
         if (launches) *launches += 2;
     }
     return cudaGetLastError();
 }
-
-cudaError_t sweep_classify(const PassK &K, SweepWorkspace &ws, float *curve, cudaStream_t st) {
+static cudaError_t sweep_classify_band(const PassK &K, SweepWorkspace &ws, float *curve, cudaStream_t st) {
     if (ws.ncols == 0) return cudaSuccess;
-    const int P = K.W * K.H;
-    k_sweep_classify<<<(P + 127) / 128, 128, sizeof(float) * views_smem_floats(K.N), st>>>(K, ws.colidx, ws.ncols, ws.ncc, ws.geo, curve);
+    k_sweep_classify<<<(ws.Pb + 127) / 128, 128, sizeof(float) * views_smem_floats(K.N), st>>>(K, ws.p0, ws.Pb, ws.colidx, ws.ncols, ws.ncc,
+                                                                                              ws.geo, curve);
     return cudaGetLastError();
 }
-cudaError_t sweep_refine(const PassK &K, SweepWorkspace &ws, cudaStream_t st) {
+static cudaError_t sweep_refine_band(const PassK &K, SweepWorkspace &ws, cudaStream_t st) {
     if (ws.ncols == 0) return cudaSuccess;
-    const int P = K.W * K.H;
-    k_sweep_refine<<<(P + 127) / 128, 128, sizeof(float) * views_smem_floats(K.N), st>>>(K, ws.colidx, ws.ncols, ws.ncc, ws.geo);
+    k_sweep_refine<<<(ws.Pb + 127) / 128, 128, sizeof(float) * views_smem_floats(K.N), st>>>(K, ws.p0, ws.Pb, ws.colidx, ws.ncols, ws.ncc,
+                                                                                            ws.geo);
     return cudaGetLastError();
+}
+
+// DepthToWeak.  With one band the columns stay valid for LocalRefine (ws.valid); with several bands they do not.
+cudaError_t sweep_depth_to_weak(const PassK &K, SweepWorkspace &ws, float *curve, cudaStream_t st, uint64_t *launches) {
+    const int rows = band_rows(K, ws);
+    ws.valid = false;
+    for (int y0 = 0; y0 < K.H; y0 += rows) {
+        const int nr = std::min(rows, K.H - y0);
+        cudaError_t e = sweep_build_band(K, ws, 1, y0 * K.W, nr * K.W, st, launches);
+        if (e != cudaSuccess) return e;
+        if ((e = sweep_classify_band(K, ws, curve, st)) != cudaSuccess) return e;
+        if (launches && y0 + nr < K.H) *launches += 1;
+    }
+    ws.valid = rows >= K.H;
+    return cudaSuccess;
+}
+// LocalRefine: re-uses DepthToWeak's columns when they are still valid, otherwise builds the +-5 columns band by band.
+cudaError_t sweep_local_refine(const PassK &K, SweepWorkspace &ws, cudaStream_t st, uint64_t *launches) {
+    if (ws.valid) {
+        ws.valid = false;
+        return sweep_refine_band(K, ws, st);
+    }
+    const int rows = band_rows(K, ws);
+    for (int y0 = 0; y0 < K.H; y0 += rows) {
+        const int nr = std::min(rows, K.H - y0);
+        cudaError_t e = sweep_build_band(K, ws, 0, y0 * K.W, nr * K.W, st, launches);
+        if (e != cudaSuccess) return e;
+        if ((e = sweep_refine_band(K, ws, st)) != cudaSuccess) return e;
+        if (launches && y0 + nr < K.H) *launches += 1;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace apde

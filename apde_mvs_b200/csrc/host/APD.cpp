@@ -127,13 +127,13 @@ void APD::Commit() {
     committed = true;
 }
 
-void RunFusion(const path &dense_folder, const std::vector<Problem> &, const std::string &name, bool weak_filter, bool export_color) {
+static void run_fusion_variant(int variant, const path &dense_folder, const std::string &name, bool weak_filter, bool export_color) {
     auto s = SceneSession::get(dense_folder);
     int64_t n = 0;
-    check(apde_fuse(s->ctx, weak_filter ? 1 : 0, nullptr, nullptr, 0, &n), "apde_fuse(count)");
+    check(apde_fuse_variant(s->ctx, variant, weak_filter ? 1 : 0, nullptr, nullptr, 0, &n), "apde_fuse(count)");
     std::vector<float> xyz((size_t)n * 3), bgr((size_t)n * 3);
     int64_t n2 = 0;
-    check(apde_fuse(s->ctx, weak_filter ? 1 : 0, xyz.data(), bgr.data(), n, &n2), "apde_fuse");
+    check(apde_fuse_variant(s->ctx, variant, weak_filter ? 1 : 0, xyz.data(), bgr.data(), n, &n2), "apde_fuse");
     std::vector<PointList> pc((size_t)std::min(n, n2));
     for (size_t i = 0; i < pc.size(); ++i) {
         pc[i].coord = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
@@ -141,6 +141,16 @@ void RunFusion(const path &dense_folder, const std::vector<Problem> &, const std
     }
     ExportPointCloud(dense_folder / "APD" / name, pc, export_color && s->has_color);
     std::cout << "Fused " << pc.size() << " points" << std::endl;
+}
+
+void RunFusion(const path &dense_folder, const std::vector<Problem> &, const std::string &name, bool weak_filter, bool export_color) {
+    run_fusion_variant(APDE_FUSE_DEFAULT, dense_folder, name, weak_filter, export_color);
+}
+void RunFusion_TAT_I(const path &dense_folder, const std::vector<Problem> &, const std::string &name, bool weak_filter, bool export_color) {
+    run_fusion_variant(APDE_FUSE_TAT_I, dense_folder, name, weak_filter, export_color);
+}
+void RunFusion_TAT_A(const path &dense_folder, const std::vector<Problem> &, const std::string &name, bool weak_filter, bool export_color) {
+    run_fusion_variant(APDE_FUSE_TAT_A, dense_folder, name, weak_filter, export_color);
 }
 
 }  // namespace apd

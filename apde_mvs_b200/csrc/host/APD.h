@@ -105,5 +105,10 @@ private:
 // RunFusion (APD.cpp:1051-1227): WeakVisFilter + greedy fusion on the GPU, PLY written by ExportPointCloud
 void RunFusion(const path &dense_folder, const std::vector<Problem> &problems, const std::string &name = "APD.ply",
                bool weak_filter = true, bool export_color = true);
+// Tanks-and-Temples variants (APD.cpp:1229-1431 intermediate set, 1433-1608 advanced set), dispatched by main.cpp:277-283
+void RunFusion_TAT_I(const path &dense_folder, const std::vector<Problem> &problems, const std::string &name = "APD.ply",
+                     bool weak_filter = true, bool export_color = true);
+void RunFusion_TAT_A(const path &dense_folder, const std::vector<Problem> &problems, const std::string &name = "APD.ply",
+                     bool weak_filter = true, bool export_color = true);
 
 }  // namespace apd

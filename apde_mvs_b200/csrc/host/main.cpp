@@ -99,11 +99,14 @@ int main(int argc, char **argv) {
         std::filesystem::create_directories(path(a.dense_folder) / "APD");
         auto s = SceneSession::get(a.dense_folder, a.gpu_index);
         std::cout << "There are " << s->problems.size() << " problems needed to be processed!" << std::endl;
-        if (a.dataset == "TaT_a" || a.dataset == "TaT_i")
-            std::cout << "note: the TaT fusion variants (APD.cpp:1229-1608) are not implemented yet; using RunFusion" << std::endl;
+        auto fuse = [&]() {  // main.cpp:277-283 / 402-408
+            if (a.dataset == "TaT_a") RunFusion_TAT_A(a.dense_folder, {}, "APD.ply", a.weak_filter, a.export_color);
+            else if (a.dataset == "TaT_i") RunFusion_TAT_I(a.dense_folder, {}, "APD.ply", a.weak_filter, a.export_color);
+            else RunFusion(a.dense_folder, {}, "APD.ply", a.weak_filter, a.export_color);
+        };
         if (a.only_fuse) {
             if (!read_maps(*s)) { std::cout << "Error: can not read the depth maps of a previous run" << std::endl; return EXIT_FAILURE; }
-            RunFusion(a.dense_folder, {}, "APD.ply", a.weak_filter, a.export_color);
+            fuse();
             printf("Fusion done!\n");
             return EXIT_SUCCESS;
         }
@@ -131,7 +134,7 @@ int main(int argc, char **argv) {
         write_maps(*s);  // the reference writes after every pass; nothing reads them in between when maps stay resident
         if (a.no_fuse) { printf("Skip fusion, all done!\n"); return EXIT_SUCCESS; }
         std::cout << "Run fusion\n";
-        RunFusion(a.dense_folder, {}, "APD.ply", a.weak_filter, a.export_color);
+        fuse();
         std::cout << "All done\n";
     } catch (const std::exception &e) {
         std::cout << "Error: " << e.what() << std::endl;

@@ -21,6 +21,7 @@
  *   apde_eval_costs                     <- ComputeBilateralNCCOld/New, ComputeGeomConsistencyCost (parity hook)
  *                                                                                        APD.cu:448-721, 865-902
  *   apde_weak_vis_filter / apde_fuse    <- WeakVisFilter, RunFusion                      APD.cpp:962-1227
+ *   apde_fuse_variant                   <- RunFusion_TAT_I / RunFusion_TAT_A             APD.cpp:1229-1608
  *   apde_get_counters                   <- (none; the reference only prints wall-clock, main.cpp:157-161)
  *   apde_last_error                     <- CudaSafeCall / CudaCheckError                 APD.cpp:417-450
  *
@@ -208,6 +209,9 @@ int apde_get_counters(apde_context *ctx, uint64_t out[4], int reset);
 /* per-kernel profile of the pass: when enabled, every stage launch is bracketed by CUDA events on the launching stream.
  * ms[11], launches[11], evals[11][3] are indexed by apde_stage. */
 int apde_set_profiling(apde_context *ctx, int on);
+/* DepthToWeak / LocalRefine keep 62 cost slots per (pixel, selected view) column in HBM; images whose worst case exceeds
+ * this budget are processed in bands of rows (results are identical).  0 = default (48 GB, or APDE_SWEEP_BUDGET_MB). */
+int apde_set_sweep_budget_mb(apde_context *ctx, size_t megabytes);
 int apde_get_stage_stats(apde_context *ctx, double *ms, uint64_t *launches, uint64_t *evals, int reset);
 
 /* roofline denominators measured on this GPU, in this process: FP32 FMA rate (TFLOP/s) and texture-unit bilinear gather
@@ -227,6 +231,11 @@ int apde_weak_vis_filter(apde_context *ctx, uint8_t *skip_weaks);
  * (either may be NULL to only count).  use_weak_filter mirrors the CLI flag (main.cpp:19). */
 int apde_fuse(apde_context *ctx, int use_weak_filter, float *xyz, float *bgr, int64_t max_points,
               int64_t *num_points);
+/* The dataset-specific variants main.cpp:277-283 dispatches to: RunFusion (ETH3D and others), RunFusion_TAT_I
+ * (APD.cpp:1229-1431) and RunFusion_TAT_A (APD.cpp:1433-1608). */
+enum apde_fuse_kind { APDE_FUSE_DEFAULT = 0, APDE_FUSE_TAT_I = 1, APDE_FUSE_TAT_A = 2 };
+int apde_fuse_variant(apde_context *ctx, int variant, int use_weak_filter, float *xyz, float *bgr, int64_t max_points,
+                      int64_t *num_points);
 
 #ifdef __cplusplus
 }

@@ -1023,10 +1023,15 @@ void orc_random_init(orc_problem *pb) {
     set_threads(pb);
     const int W = pb->width, H = pb->height;
     const orc_camera &cam = pb->cameras[0];
+    /* The deformable cost of a WEAK pixel reads selected_views of its STRONG anchors (APD.cu:502-503) while the reference's
+     * kernel is still writing them (a race).  Serialisation chosen here and in the CUDA product: all non-WEAK pixels first,
+     * then the WEAK ones. */
+    for (int phase = 0; phase < (pb->params.use_APD ? 2 : 1); ++phase)
 #pragma omp parallel for schedule(dynamic, 4)
     for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
         const I2 p{x, y};
         const size_t center = (size_t)y * W + x;
+        if (pb->params.use_APD && (int)(pb->weak_info[center] == ORC_WEAK) != phase) continue;
         if (pb->params.state == ORC_FIRST_INIT) {
             Rng rng(pb->seed, pb->stream, (uint32_t)center, SITE_INIT);
             store4(pb->planes, center, random_plane(cam, p, rng, pb->params.depth_min, pb->params.depth_max));
@@ -1625,3 +1630,83 @@ int64_t orc_fuse(const orc_fusion_input *in, const uint8_t *skip, float *pts, fl
 }
 
 }  // extern "C"
+
+/* ================================================================================================
+ * Tanks-and-Temples fusion variants (APD.cpp:1229-1431 RunFusion_TAT_I, 1433-1608 RunFusion_TAT_A)
+ *   variant 1 = TAT_I (distance + depth + angle thresholds growing with k, colours averaged over the used neighbours)
+ *   variant 2 = TAT_A (distance + depth thresholds, reference colour only)
+ * Quirk 14: diff[] is declared per VIEW, not per pixel, so a neighbour that is skipped (out of bounds, masked, invalid
+ * depth) keeps the values -- and the source coordinates -- of the last pixel that did update it.
+ * ============================================================================================== */
+extern "C" int64_t orc_fuse_tat(const orc_fusion_input *in, const uint8_t *skip, int variant, float *pts, float *cols,
+                                int64_t max_points) {
+    const int V = in->num_views, W = in->width, H = in->height;
+    const size_t P = (size_t)W * H;
+    const float dist_base = 0.25f;
+    const float depth_base = variant == 1 ? 1.0f / 3500.0f : 1.0f / 3000.0f;
+    const float angle_base = 0.06981317007977318f, angle_grad = 0.05235987755982988f;
+    std::vector<uint8_t> masks((size_t)V * P, 0);
+    struct CostData { float dist = FLT_MAX, depth = FLT_MAX, angle = FLT_MAX; int src_r = 0, src_c = 0; bool use = false; };
+    int64_t n = 0;
+    for (int ref = 0; ref < V; ++ref) {
+        const int nb0 = in->src_offsets[ref], num_ngb = in->src_offsets[ref + 1] - nb0;
+        std::vector<CostData> diff(num_ngb);
+        for (int r = 0; r < H; ++r) for (int c = 0; c < W; ++c) {
+            const size_t px = (size_t)r * W + c;
+            if (skip && skip[ref * P + px] == 1) continue;
+            const float ref_depth = in->depths[ref * P + px];
+            if (ref_depth <= 0.0) continue;
+            const float *rn = &in->normals[(ref * P + px) * 3];
+            const F3 X = f_point_on_world(c, r, ref_depth, in->cameras[ref]);
+            for (int j = 0; j < num_ngb; ++j) {
+                const int s = in->src_ids[nb0 + j];
+                F2 pt; float pd;
+                project_on_camera(X, in->cameras[s], pt, pd);
+                const int sr = (int)(pt.y + 0.5f), sc = (int)(pt.x + 0.5f);
+                if (sc >= 0 && sc < W && sr >= 0 && sr < H) {
+                    const size_t spx = (size_t)sr * W + sc;
+                    if (masks[s * P + spx] == 1) continue;
+                    const float sd = in->depths[s * P + spx];
+                    if (sd <= 0.0) continue;
+                    const float *sn = &in->normals[(s * P + spx) * 3];
+                    const F3 tX = f_point_on_world(sc, sr, sd, in->cameras[s]);
+                    F2 tp;
+                    project_on_camera(tX, in->cameras[ref], tp, pd);
+                    diff[j].dist = (float)std::sqrt(std::pow((double)(c - tp.x), 2) + std::pow((double)(r - tp.y), 2));
+                    diff[j].depth = std::fabs(pd - ref_depth) / ref_depth;
+                    diff[j].angle = f_angle(rn, sn);
+                    diff[j].src_r = sr; diff[j].src_c = sc;
+                }
+            }
+            for (int k = 2; k <= num_ngb; ++k) {
+                int count = 0;
+                for (int j = 0; j < num_ngb; ++j) {
+                    diff[j].use = false;
+                    bool ok = diff[j].dist < k * dist_base && diff[j].depth < k * depth_base;
+                    if (variant == 1) ok = ok && diff[j].angle < (k * angle_grad + angle_base);
+                    if (ok) { count++; diff[j].use = true; }
+                }
+                if (count >= k) {
+                    float col[3] = {0, 0, 0};
+                    if (in->colors) for (int q = 0; q < 3; ++q) col[q] = (float)in->colors[(ref * P + px) * 3 + q];
+                    if (variant == 1 && in->colors) {
+                        for (int j = 0; j < num_ngb; ++j) if (diff[j].use) {
+                            const int s = in->src_ids[nb0 + j];
+                            const size_t spx = (size_t)diff[j].src_r * W + diff[j].src_c;
+                            for (int q = 0; q < 3; ++q) col[q] += (float)in->colors[(s * P + spx) * 3 + q];
+                        }
+                        for (int q = 0; q < 3; ++q) col[q] /= (count + 1.0f);
+                    }
+                    if (n < max_points) {
+                        pts[3 * n] = X.x; pts[3 * n + 1] = X.y; pts[3 * n + 2] = X.z;
+                        if (cols) { cols[3 * n] = col[0]; cols[3 * n + 1] = col[1]; cols[3 * n + 2] = col[2]; }
+                    }
+                    n++;
+                    masks[ref * P + px] = 1;
+                    break;
+                }
+            }
+        }
+    }
+    return n;
+}

@@ -144,6 +144,10 @@ void orc_weak_vis_filter(const orc_fusion_input *in, uint8_t *skip_weaks /* [V][
 int64_t orc_fuse(const orc_fusion_input *in, const uint8_t *skip_weaks, float *points_xyz, float *points_bgr,
                  int64_t max_points);
 
+/* RunFusion_TAT_I (variant 1, APD.cpp:1229-1431) / RunFusion_TAT_A (variant 2, APD.cpp:1433-1608) */
+int64_t orc_fuse_tat(const orc_fusion_input *in, const uint8_t *skip_weaks, int variant, float *points_xyz, float *points_bgr,
+                     int64_t max_points);
+
 #ifdef __cplusplus
 }
 #endif

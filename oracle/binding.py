@@ -81,6 +81,8 @@ def lib():
         L.orc_weak_vis_filter.argtypes = [C.POINTER(OFusionInput), C.c_void_p]
         L.orc_fuse.restype = C.c_int64
         L.orc_fuse.argtypes = [C.POINTER(OFusionInput), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.orc_fuse_tat.restype = C.c_int64
+        L.orc_fuse_tat.argtypes = [C.POINTER(OFusionInput), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
         _lib = L
     return _lib
 
@@ -160,8 +162,8 @@ def checkerboard_candidates(costs, x, y):
     return pos, flags
 
 
-def fusion(cameras, depths, normals, weaks, confs, pairs, colors=None, weak_filter=True, num_threads=8):
-    """returns (points xyz, colours bgr, skip_weaks)"""
+def fusion(cameras, depths, normals, weaks, confs, pairs, colors=None, weak_filter=True, num_threads=8, variant=0):
+    """returns (points xyz, colours bgr, skip_weaks); variant 0 = RunFusion, 1 = RunFusion_TAT_I, 2 = RunFusion_TAT_A"""
     L = lib()
     V, h, w = depths.shape
     cams = (OCamera * V)()
@@ -188,8 +190,12 @@ def fusion(cameras, depths, normals, weaks, confs, pairs, colors=None, weak_filt
     skip = np.zeros((V, h, w), np.uint8)
     if weak_filter:
         L.orc_weak_vis_filter(C.byref(fi), skip.ctypes.data)
-    n = L.orc_fuse(C.byref(fi), skip.ctypes.data, None, None, 0)
+    def run(p, c, m):
+        if variant == 0:
+            return L.orc_fuse(C.byref(fi), skip.ctypes.data, p, c, m)
+        return L.orc_fuse_tat(C.byref(fi), skip.ctypes.data, variant, p, c, m)
+    n = run(None, None, 0)
     xyz = np.zeros((n, 3), np.float32)
     bgr = np.zeros((n, 3), np.float32)
-    L.orc_fuse(C.byref(fi), skip.ctypes.data, xyz.ctypes.data, bgr.ctypes.data, n)
+    run(xyz.ctypes.data, bgr.ctypes.data, n)
     return xyz, bgr, skip

@@ -72,3 +72,64 @@ def test_whole_pass_matches_oracle_on_odd_shapes(ctx, size, views, src):
     ctx.problem_finish()
     d, n, wk, cf = ctx.view_download(1)
     assert d.shape == (h, w) and n.shape == (h, w, 3)
+
+
+def test_fusion_variants_on_uploaded_maps_with_holes():
+    """all three fusion variants on uploaded maps with holes, noise and mixed WEAK/STRONG labels == the oracle, point for
+    point and in the reference's order (APD.cpp:1051-1608); holes exercise the diff[] carry-over of the TaT variants"""
+    from apde_mvs_b200.binding import Context
+    from apde_mvs_b200.scene import make_plane_scene
+    from oracle import binding as orc
+    W, H, V = 160, 120, 5
+    scene = make_plane_scene(W, H, num_views=V, num_src=4, seed=9, with_color=True)
+    rng = np.random.default_rng(3)
+    depths = np.stack(scene.gt_depth).astype(np.float32)
+    depths *= (1 + rng.normal(0, 2e-4, depths.shape)).astype(np.float32)  # noise around the TaT depth thresholds (1/3500)
+    holes = rng.random(depths.shape) < 0.15
+    depths[holes] = 0
+    depths[:, 40:60, 30:90] = 0  # a block hole: long carry-over runs
+    n_w = np.array([-0.15, 0.1, 1.0]); n_w /= -np.linalg.norm(n_w)
+    normals = np.tile(n_w.astype(np.float32), (V, H, W, 1))
+    normals += rng.normal(0, 0.03, normals.shape).astype(np.float32)
+    weaks = (rng.random((V, H, W)) < 0.7).astype(np.uint8)
+    confs = rng.integers(0, 255, (V, H, W)).astype(np.uint8)
+    ctx = Context(0)
+    ctx.load_scene(scene)
+    for v in range(V):
+        ctx.view_upload(v, depths[v], normals[v], weaks[v], confs[v])
+    cols = np.stack(scene.colors)
+    for variant in (0, 1, 2):
+        for wf in (True, False):
+            xyz_o, bgr_o, _ = orc.fusion(scene.cameras, depths, normals, weaks, confs, scene.pairs, cols, weak_filter=wf,
+                                         variant=variant)
+            xyz_g, bgr_g = ctx.fuse(wf, variant=variant)
+            print("variant %d weak_filter %d: gpu %d oracle %d points" % (variant, wf, len(xyz_g), len(xyz_o)))
+            assert len(xyz_o) > 500
+            assert len(xyz_g) == len(xyz_o)
+            assert np.allclose(xyz_g, xyz_o, rtol=1e-5, atol=1e-5)
+            assert np.abs(bgr_g - bgr_o).max() <= 1e-3
+    ctx.close()
+
+
+def test_banded_sweep_is_identical():
+    """DepthToWeak / LocalRefine column storage processed in bands of rows (large images, apde_set_sweep_budget_mb) gives
+    bit-identical maps to the single-band path, in photometric, geometric and use_APD passes"""
+    from apde_mvs_b200.binding import Context, default_schedule
+    from apde_mvs_b200.scene import make_office_scene
+    scene = make_office_scene(320, 240, num_views=4, num_src=3, seed=3, weak=0.3)
+    sched = default_schedule()
+    sched.rounds, sched.geom_iterations, sched.seed = 2, 1, 9
+    out = []
+    for mb in (0, 1):  # 1 MB: 320 x 3 views x 62 slots x 4 B (x 2 geometric) = 238 / 476 KB per row -> 4 / 2 rows per band
+        ctx = Context(0)
+        ctx.set_sweep_budget_mb(mb)
+        ctx.load_scene(scene)
+        t = ctx.run_schedule(sched)
+        out.append(([ctx.view_download(v) for v in range(4)], t))
+        ctx.close()
+    (a, ta), (b, tb) = out
+    assert tb.kernel_launches > ta.kernel_launches  # the banded run really took the banded path
+    assert (ta.evals_ncc_old, ta.evals_ncc_new) != (0, 0)
+    for v in range(4):
+        for k in range(4):
+            assert np.array_equal(a[v][k], b[v][k]), "view %d map %d differs between banded and single-band sweeps" % (v, k)

@@ -1,0 +1,171 @@
+"""The BASELINE.json configurations at their FULL image sizes (view counts reduced so that the suite stays in minutes).
+
+The oracle cannot finish these sizes in seconds, so apart from C1 the checks are size-independent properties of the
+path: analytic ground truth of the synthetic scenes, bit-exact determinism under a fixed seed, the pyramid rule
+(ComputeRoundNum, main.cpp:129-146), the analytic bound on cost evaluations per pixel, and fused
+points lying on the known surfaces."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _download(ctx, V):
+    return [ctx.view_download(v) for v in range(V)]
+
+
+def _interior(a, m=16):
+    return a[m:-m, m:-m]
+
+
+def _strong_accuracy(maps, scene, rel=0.01):
+    accs, shares = [], []
+    for v, (d, _, wk, _) in enumerate(maps):
+        gt = scene.gt_depth[v]
+        sel = _interior((wk == 1) & (gt > 0))
+        ok = _interior(np.abs(d - gt) <= rel * gt)
+        accs.append(float(ok[sel].mean()))
+        shares.append(float(sel.mean()))
+    return accs, shares
+
+
+def test_c1_config(ctx):
+    """configs[0]: 5 views 640x480, 4 sources, 1 photometric pass, slanted textured plane z = 4 + 0.15x - 0.1y; whole
+    pass of one view against the oracle's whole pass (same counter RNG), all views against ground truth, fusion == oracle"""
+    from apde_mvs_b200.binding import default_schedule
+    from apde_mvs_b200.scene import make_plane_scene
+    from helpers import oracle_from_ctx
+    from oracle import binding as orc
+    from apde_mvs_b200.binding import default_params
+    scene = make_plane_scene(640, 480, num_views=5, num_src=4, seed=1, with_color=True)
+    ctx.load_scene(scene)
+    sched = default_schedule()
+    sched.rounds, sched.geom_iterations, sched.seed = 1, 0, 11
+    assert ctx.num_passes(sched) == 1
+    t = ctx.run_schedule(sched)
+    assert t.passes == 1 and t.evals_ncc_old > 0 and t.evals_ncc_new == 0 and t.evals_geom == 0
+    maps = _download(ctx, 5)
+    for v, (d, nrm, wk, cf) in enumerate(maps):
+        gt = scene.gt_depth[v]
+        ok = _interior(np.abs(d - gt) <= 0.01 * gt)
+        print("C1 view %d: within 1%% of ground truth %.5f, strong share %.4f" % (v, ok.mean(), (wk == 1).mean()))
+        assert ok.mean() >= 0.99
+        assert np.abs(np.linalg.norm(nrm, axis=-1)[d > 0] - 1).max() < 1e-3
+    # one view against the oracle's whole pass from the same seed / stream
+    p = default_params()
+    p.use_APD, p.state = 0, 0
+    ctx.problem_setup(2, p, 1, 11)
+    pb = oracle_from_ctx(ctx, 11, 2)
+    ctx.problem_run()
+    ctx.problem_finish()
+    dg = ctx.view_download(2)[0]
+    pb.stage("run_pass")
+    do = pb.planes[..., 3]
+    with np.errstate(all="ignore"):
+        same = _interior(np.abs(dg - do) <= 0.01 * np.abs(do))
+    print("C1 view 2: GPU pass within 1%% of the oracle pass on %.5f of pixels" % same.mean())
+    assert same.mean() >= 0.99
+    # fusion of the GPU maps: GPU == oracle, point for point
+    depths, normals, weaks, confs = (np.stack([m[i] for m in _download(ctx, 5)]) for i in range(4))
+    xyz_o, bgr_o, _ = orc.fusion(scene.cameras, depths, normals, weaks, confs, scene.pairs, np.stack(scene.colors))
+    xyz_g, bgr_g = ctx.fuse(True)
+    print("C1 fusion: gpu %d points, oracle %d" % (len(xyz_g), len(xyz_o)))
+    assert len(xyz_g) == len(xyz_o) and len(xyz_g) > 100000
+    assert np.allclose(xyz_g, xyz_o, rtol=1e-5, atol=1e-5)
+    res = np.abs(4 + 0.15 * xyz_g[:, 0] - 0.1 * xyz_g[:, 1] - xyz_g[:, 2])
+    assert np.quantile(res, 0.99) < 0.03
+
+
+def test_c2_shape_properties(ctx):
+    """configs[1] shape: 1550x1030 office, 10 sources (6 of the 26 views), photometric + 2 geometric iterations per
+    round, two rounds by the reference's pyramid rule"""
+    from apde_mvs_b200.binding import default_schedule
+    from apde_mvs_b200.scene import make_office_scene
+    V, N = 6, 5
+    scene = make_office_scene(1550, 1030, num_views=V, num_src=N, seed=2, arc_deg=20.0, with_color=True)
+    ctx.load_scene(scene)
+    sched = default_schedule()
+    sched.geom_iterations, sched.seed = 2, 21
+    assert ctx.num_passes(sched) == 2 * 3  # ComputeRoundNum: 1550 -> 775 <= 800 => 2 rounds
+    ctx.counters(reset=True)
+    t = ctx.run_schedule(sched)
+    maps = _download(ctx, V)
+    accs, shares = _strong_accuracy(maps, scene)
+    print("C2 shape: strong-pixel accuracy %s, strong share %s, %.1f ms patchmatch" % (np.round(accs, 4), np.round(shares, 3), t.patchmatch_ms))
+    assert min(accs) >= 0.97 and min(shares) > 0.5
+    # evaluation counts against the analytic bound of SURVEY 8d: <= 43N + 73S NCC evaluations per pixel per pass (S <= N)
+    P_full, P_half = 1550 * 1030, 775 * 515
+    bound = V * 3 * (P_full + P_half) * (43 * N + 73 * N + 16 * N)
+    assert 0.2 * bound < t.evals_ncc_old + t.evals_ncc_new < bound
+    assert t.evals_geom > 0
+    # determinism: the same seed gives the same maps bit for bit, a different seed does not
+    ctx.load_scene(scene)
+    ctx.run_schedule(sched)
+    maps2 = _download(ctx, V)
+    for a, b in zip(maps, maps2):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    sched.seed = 22
+    ctx.load_scene(scene)
+    ctx.run_schedule(sched)
+    maps3 = _download(ctx, V)
+    assert not np.array_equal(maps[0][0], maps3[0][0])
+    accs3, _ = _strong_accuracy(maps3, scene)
+    assert abs(np.mean(accs3) - np.mean(accs)) < 0.01
+    # fused cloud lies on the surfaces: every fused point re-projects onto view 0's ground-truth depth where visible
+    xyz, _ = ctx.fuse(True)
+    assert len(xyz) > 0.3 * P_full
+    R, tt, K = scene.Rs[0], scene.ts[0], scene.K
+    Xc = xyz.astype(np.float64) @ R.T + tt
+    uv = Xc @ K.T
+    u, v = uv[:, 0] / uv[:, 2], uv[:, 1] / uv[:, 2]
+    inside = (Xc[:, 2] > 0) & (u >= 0) & (u < 1549) & (v >= 0) & (v < 1029)
+    gt = scene.gt_depth[0][np.round(v[inside]).astype(int), np.round(u[inside]).astype(int)]
+    rel = np.abs(Xc[inside, 2] - gt) / gt
+    print("C2 shape fusion: %d points, %.4f within 1%% of view 0's ground truth (occlusions included)" % (len(xyz), (rel < 0.01).mean()))
+    assert (rel < 0.01).mean() > 0.9
+
+
+def test_c4_shape_three_levels(ctx):
+    """configs[3] shape: 1920x1056 => three pyramid levels (480x264, 960x528, 1920x1056), 4 * 3 passes per view"""
+    from apde_mvs_b200.binding import default_schedule
+    from apde_mvs_b200.scene import make_office_scene
+    V = 4
+    scene = make_office_scene(1920, 1056, num_views=V, num_src=3, seed=4, arc_deg=12.0)
+    ctx.load_scene(scene)
+    sched = default_schedule()
+    sched.seed = 41
+    assert ctx.num_passes(sched) == 12
+    t = ctx.run_schedule(sched)
+    assert t.passes == 12
+    maps = _download(ctx, V)
+    assert maps[0][0].shape == (1056, 1920)
+    accs, shares = _strong_accuracy(maps, scene)
+    print("C4 shape: strong-pixel accuracy %s, strong share %s" % (np.round(accs, 4), np.round(shares, 3)))
+    assert min(accs) >= 0.97
+
+
+def test_c5_shape_four_levels(ctx):
+    """configs[4] shape: 6048x4032 => four pyramid levels, 16 passes per view; 3 views / 2 sources of the slanted plane"""
+    from apde_mvs_b200.binding import default_schedule
+    from apde_mvs_b200.scene import make_plane_scene
+    V = 3
+    scene = make_plane_scene(6048, 4032, num_views=V, num_src=2, seed=5)
+    ctx.load_scene(scene)
+    sched = default_schedule()
+    sched.seed = 51
+    assert ctx.num_passes(sched) == 16
+    t = ctx.run_schedule(sched)
+    maps = _download(ctx, V)
+    assert maps[0][0].shape == (4032, 6048)
+    for v, (d, _, wk, _) in enumerate(maps):
+        gt = scene.gt_depth[v]
+        ok = _interior(np.abs(d - gt) <= 0.01 * gt, 64)
+        strong, weak = _interior((gt > 0) & (wk == 1), 64), _interior((gt > 0) & (wk == 0), 64)
+        print("C5 shape view %d: within 1%% of ground truth: STRONG %.5f (share %.4f), WEAK %.5f (share %.4f), UNKNOWN share %.4f; "
+              "%.0f ms patchmatch total" % (v, ok[strong].mean(), strong.mean(), ok[weak].mean() if weak.any() else 1.0, weak.mean(),
+                                           (wk == 2).mean(), t.patchmatch_ms))
+        assert ok[strong].mean() >= 0.99 and strong.mean() > 0.8
+    xyz, _ = ctx.fuse(True)
+    res = np.abs(4 + 0.15 * xyz[:, 0] - 0.1 * xyz[:, 1] - xyz[:, 2])
+    print("C5 shape fusion: %d points, plane residual q99 %.4f" % (len(xyz), np.quantile(res, 0.99)))
+    assert len(xyz) > 6048 * 4032 * 0.3 and np.quantile(res, 0.99) < 0.03

@@ -225,6 +225,16 @@ def test_schedule_and_fusion(ctx, office):
     assert abs(len(xyz_g2) - len(xyz_o2)) <= max(3, 0.001 * len(xyz_o2))
     # fused points lie on the synthetic surfaces: median distance to ground truth small
     assert len(xyz_g) > 1000
+    # Tanks-and-Temples variants (APD.cpp:1229-1608), including the per-view carry-over of diff[] (quirk 14)
+    for variant in (1, 2):
+        xyz_t, bgr_t = ctx.fuse(True, variant=variant)
+        xyz_ot, bgr_ot, _ = orc.fusion(scene.cameras, depths, normals, weaks, confs, scene.pairs, np.stack(scene.colors),
+                                       variant=variant)
+        print("fusion TaT variant %d: gpu %d points, oracle %d points" % (variant, len(xyz_t), len(xyz_ot)))
+        assert abs(len(xyz_t) - len(xyz_ot)) <= max(3, 0.001 * len(xyz_ot)) and len(xyz_t) > 1000
+        if len(xyz_t) == len(xyz_ot):
+            assert np.allclose(xyz_t, xyz_ot, rtol=1e-5, atol=1e-5)
+            assert np.abs(bgr_t - bgr_ot).max() <= 1e-3
 
 
 def test_resize_matches_opencv(ctx):

@@ -197,6 +197,39 @@ def test_fusion_oracle_on_ground_truth_maps():
     assert len(xyz0) == 0
 
 
+def test_fusion_oracle_tat_variants():
+    """RunFusion_TAT_I / _A (APD.cpp:1229-1608): k-of-N consistency with thresholds growing in k; diff[] carries over
+    between pixels of a view (quirk 14), so a pixel whose neighbours all fall outside can still be accepted"""
+    from apde_mvs_b200.scene import make_plane_scene
+    scene = make_plane_scene(96, 72, num_views=4, num_src=3, seed=5, with_color=True)
+    V = 4
+    depths = np.stack(scene.gt_depth).astype(np.float32)
+    n_w = np.array([-0.15, 0.1, 1.0]); n_w /= -np.linalg.norm(n_w)
+    normals = np.tile(n_w.astype(np.float32), (V, 72, 96, 1))
+    weaks = np.ones((V, 72, 96), np.uint8)
+    confs = np.ones((V, 72, 96), np.uint8)
+    cols = np.stack(scene.colors)
+    counts = {}
+    for variant in (1, 2):
+        xyz, bgr, _ = orc.fusion(scene.cameras, depths, normals, weaks, confs, scene.pairs, cols, variant=variant)
+        counts[variant] = len(xyz)
+        assert len(xyz) > 0.5 * 96 * 72
+        res = np.abs(4 + 0.15 * xyz[:, 0] - 0.1 * xyz[:, 1] - xyz[:, 2])
+        assert np.quantile(res, 0.99) < 1e-2
+        assert bgr.min() >= 0 and bgr.max() <= 255
+    # TAT_A has the looser depth threshold and no angle test: it accepts at least as many points on clean maps
+    assert counts[2] >= counts[1]
+    # carry-over: blank the neighbours' depth everywhere except one early row -> later pixels of view 0 reuse the
+    # measurements of that row and are still accepted (a per-pixel diff[] would reject them all)
+    d2 = depths.copy()
+    d2[1:, 8:, :] = 0
+    xyz, _, _ = orc.fusion(scene.cameras, d2, normals, weaks, confs, scene.pairs, cols, variant=2)
+    assert len(xyz) > 96 * 20, "stale diff[] must keep accepting pixels of view 0 (got %d)" % len(xyz)
+    # a view with fewer than two neighbours never fuses anything (k starts at 2)
+    xyz1, _, _ = orc.fusion(scene.cameras, depths, normals, weaks, confs, [p[:1] for p in scene.pairs], cols, variant=1)
+    assert len(xyz1) == 0
+
+
 # ------------------------------------------------------------------------------------------------ C ABI
 def test_c_abi_exports_every_declared_symbol(apde_lib):
     hdr = open(os.path.join(ROOT, "include", "apde.h")).read()
