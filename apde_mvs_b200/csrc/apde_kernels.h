@@ -60,7 +60,7 @@ struct SweepWorkspace {
     size_t scan_bytes = 0, flag_cap = 0, col_cap = 0, geo_cap = 0;
     float *ncc = nullptr, *geo = nullptr;      // [62][ncols] column costs (slot 61 = the current depth)
     int ncols = 0;
-    int p0 = 0, Pb = 0;                        // the band of pixels the stored columns cover
+    int y0 = 0, rows = 0, Pb = 0;              // the band of rows the stored columns cover; Pb = slots (8x4 tiles, padded)
     size_t budget_mb = 0;                      // column storage budget (0 = APDE_SWEEP_BUDGET_MB or 48 GB)
     bool valid = false;                        // columns cover the whole image and match the problem state (set by DepthToWeak, used by LocalRefine)
     cudaError_t reserve_flags(size_t n);

@@ -29,16 +29,27 @@ __device__ __forceinline__ int sweep_class(const PassK &K, int px, int py, int c
     return (dtw && !border) ? 2 : 1;
 }
 
-// All sweep kernels work on a BAND of whole rows: pixels [p0, p0 + Pb).  flags / colidx are [N][Pb] for the band.
-__global__ void __launch_bounds__(256) k_sweep_prepare(const __grid_constant__ PassK K, int dtw, int p0, int Pb,
+// All sweep kernels work on a BAND of whole rows starting at row y0; slots of the band are its pixels in row-major order,
+// Pb = rows * W of them, and flags / colidx are [N][Pb].  (Measured on B200, r01: numbering the slots in 8x4 tiles instead
+// made DepthToWeak 3 % slower -- with 8-bit texels a 32 B sector is a 32x1 strip, which a row-major warp covers best.)
+__device__ __forceinline__ bool slot_pixel(const PassK &K, int y0, int rows, int loc, int &px, int &py) {
+    px = loc % K.W;
+    py = y0 + loc / K.W;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_sweep_prepare(const __grid_constant__ PassK K, int dtw, int y0, int rows, int Pb,
                                                        int *__restrict__ flags) {
     const int loc = blockIdx.x * blockDim.x + threadIdx.x;
     if (loc >= Pb) return;
-    const int idx = p0 + loc;
-    const int px = idx % K.W, py = idx / K.W;
-    const int cls = sweep_class(K, px, py, idx, dtw != 0);
-    if (dtw && cls != 2) K.weak[idx] = APDE_UNKNOWN;  // border / zero depth / no selected view (APD.cu:2114-2153)
-    const uint32_t sel = cls ? K.sel[idx] : 0u;
+    int px, py;
+    uint32_t sel = 0u;
+    if (slot_pixel(K, y0, rows, loc, px, py)) {
+        const int idx = py * K.W + px;
+        const int cls = sweep_class(K, px, py, idx, dtw != 0);
+        if (dtw && cls != 2) K.weak[idx] = APDE_UNKNOWN;  // border / zero depth / no selected view (APD.cu:2114-2153)
+        if (cls) sel = K.sel[idx];
+    }
     for (int v = 0; v < K.N; ++v) flags[(size_t)v * Pb + loc] = (sel >> v) & 1u;
 }
 
@@ -50,15 +61,18 @@ __global__ void __launch_bounds__(256) k_sweep_scatter(const int *__restrict__ f
 }
 
 template <bool U>
-__device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, int p0, int Pb, const int *__restrict__ colmap,
-                                                       int ncols, float *__restrict__ ncc, float *__restrict__ geo) {
+__device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, int y0, int rows, int Pb,
+                                                       const int *__restrict__ colmap, int ncols, float *__restrict__ ncc,
+                                                       float *__restrict__ geo) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= ncols) return;
     const int flat = colmap[col];
-    const int v = flat / Pb, center = p0 + flat % Pb;
-    const int px = center % K.W, py = center / K.W;
+    const int v = flat / Pb;
+    int px, py;
+    slot_pixel(K, y0, rows, flat % Pb, px, py);
+    const int center = py * K.W + px;
     const int cls = sweep_class(K, px, py, center, dtw != 0);
     const ViewK &vk = s_vk[v];
     const float4 opl = normal_to_refcam(K, K.planes[center]);
@@ -96,25 +110,25 @@ __device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, in
     }
     count_evals(K, n_old, 0, n_geom);
 }
-__global__ void __launch_bounds__(128) k_sweep_columns(const __grid_constant__ PassK K, int dtw, int p0, int Pb,
+__global__ void __launch_bounds__(128) k_sweep_columns(const __grid_constant__ PassK K, int dtw, int y0, int rows, int Pb,
                                                        const int *__restrict__ colmap, int ncols, float *__restrict__ ncc,
                                                        float *__restrict__ geo) {
-    if (K.tex_unorm > 0.0f) k_sweep_columns_body<true>(K, dtw, p0, Pb, colmap, ncols, ncc, geo);
-    else k_sweep_columns_body<false>(K, dtw, p0, Pb, colmap, ncols, ncc, geo);
+    if (K.tex_unorm > 0.0f) k_sweep_columns_body<true>(K, dtw, y0, rows, Pb, colmap, ncols, ncc, geo);
+    else k_sweep_columns_body<false>(K, dtw, y0, rows, Pb, colmap, ncols, ncc, geo);
 }
 
 
 // DepthToWeak decision logic, APD.cu:2157-2249
-__global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ PassK K, int p0, int Pb,
+__global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ PassK K, int y0, int rows, int Pb,
                                                         const int *__restrict__ colidx, int ncols,
                                                         const float *__restrict__ ncc, const float *__restrict__ geo,
                                                         float *curve) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
     const int loc = blockIdx.x * blockDim.x + threadIdx.x;
-    if (loc >= Pb) return;
-    const int idx = p0 + loc;
-    const int px = idx % K.W, py = idx / K.W;
+    int px, py;
+    if (loc >= Pb || !slot_pixel(K, y0, rows, loc, px, py)) return;
+    const int idx = py * K.W + px;
     if (sweep_class(K, px, py, idx, true) != 2) return;
     const float origin_depth = K.planes[idx].w;
     const uint32_t sel = K.sel[idx];
@@ -169,15 +183,15 @@ __global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ 
 }
 
 // LocalRefine decision logic, APD.cu:2368-2431
-__global__ void __launch_bounds__(128) k_sweep_refine(const __grid_constant__ PassK K, int p0, int Pb,
+__global__ void __launch_bounds__(128) k_sweep_refine(const __grid_constant__ PassK K, int y0, int rows, int Pb,
                                                       const int *__restrict__ colidx, int ncols,
                                                       const float *__restrict__ ncc, const float *__restrict__ geo) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
     const int loc = blockIdx.x * blockDim.x + threadIdx.x;
-    if (loc >= Pb) return;
-    const int idx = p0 + loc;
-    const int px = idx % K.W, py = idx / K.W;
+    int px, py;
+    if (loc >= Pb || !slot_pixel(K, y0, rows, loc, px, py)) return;
+    const int idx = py * K.W + px;
     if (sweep_class(K, px, py, idx, false) == 0) return;
     const float origin_depth = K.planes[idx].w;
     const uint32_t sel = K.sel[idx];
@@ -279,38 +293,39 @@ static int band_rows(const PassK &K, const SweepWorkspace &ws) {
     return (int)std::max<size_t>(1, std::min<size_t>(rows, (size_t)K.H));
 }
 
-// columns of the band [p0, p0 + Pb) for the current problem state; dtw = 1: DepthToWeak (+-30 for interior pixels), 0: LocalRefine only
-static cudaError_t sweep_build_band(const PassK &K, SweepWorkspace &ws, int dtw, int p0, int Pb, cudaStream_t st, uint64_t *launches) {
+// columns of the band of rows [y0, y0 + rows) for the current problem state; dtw = 1: DepthToWeak (+-30 for interior pixels), 0: LocalRefine only
+static cudaError_t sweep_build_band(const PassK &K, SweepWorkspace &ws, int dtw, int y0, int rows, cudaStream_t st, uint64_t *launches) {
+    const int Pb = K.W * rows;
     const size_t nflat = (size_t)K.N * Pb;
     cudaError_t e = ws.reserve_flags(nflat);
     if (e != cudaSuccess) return e;
-    k_sweep_prepare<<<(Pb + 255) / 256, 256, 0, st>>>(K, dtw, p0, Pb, ws.flags);
+    k_sweep_prepare<<<(Pb + 255) / 256, 256, 0, st>>>(K, dtw, y0, rows, Pb, ws.flags);
     if ((e = cudaMemsetAsync(ws.flags + nflat, 0, sizeof(int), st)) != cudaSuccess) return e;
     if ((e = cub::DeviceScan::ExclusiveSum(ws.scan_tmp, ws.scan_bytes, ws.flags, ws.colidx, (int)(nflat + 1), st)) != cudaSuccess) return e;
     int ncols = 0;
     if ((e = cudaMemcpyAsync(&ncols, ws.colidx + nflat, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
     ws.ncols = ncols;
-    ws.p0 = p0; ws.Pb = Pb;
+    ws.y0 = y0; ws.rows = rows; ws.Pb = Pb;
     if (launches) *launches += 2;
     if (ncols > 0) {
         if ((e = ws.reserve_columns((size_t)ncols, K.geom != 0)) != cudaSuccess) return e;
         const size_t vsm = sizeof(float) * views_smem_floats(K.N);
         k_sweep_scatter<<<(unsigned)((nflat + 255) / 256), 256, 0, st>>>(ws.flags, ws.colidx, nflat, ws.colmap);
-        k_sweep_columns<<<(ncols + 127) / 128, 128, vsm, st>>>(K, dtw, p0, Pb, ws.colmap, ncols, ws.ncc, ws.geo);
+        k_sweep_columns<<<(ncols + 127) / 128, 128, vsm, st>>>(K, dtw, y0, rows, Pb, ws.colmap, ncols, ws.ncc, ws.geo);
         if (launches) *launches += 2;
     }
     return cudaGetLastError();
 }
 static cudaError_t sweep_classify_band(const PassK &K, SweepWorkspace &ws, float *curve, cudaStream_t st) {
     if (ws.ncols == 0) return cudaSuccess;
-    k_sweep_classify<<<(ws.Pb + 127) / 128, 128, sizeof(float) * views_smem_floats(K.N), st>>>(K, ws.p0, ws.Pb, ws.colidx, ws.ncols, ws.ncc,
+    k_sweep_classify<<<(ws.Pb + 127) / 128, 128, sizeof(float) * views_smem_floats(K.N), st>>>(K, ws.y0, ws.rows, ws.Pb, ws.colidx, ws.ncols, ws.ncc,
                                                                                               ws.geo, curve);
     return cudaGetLastError();
 }
 static cudaError_t sweep_refine_band(const PassK &K, SweepWorkspace &ws, cudaStream_t st) {
     if (ws.ncols == 0) return cudaSuccess;
-    k_sweep_refine<<<(ws.Pb + 127) / 128, 128, sizeof(float) * views_smem_floats(K.N), st>>>(K, ws.p0, ws.Pb, ws.colidx, ws.ncols, ws.ncc,
+    k_sweep_refine<<<(ws.Pb + 127) / 128, 128, sizeof(float) * views_smem_floats(K.N), st>>>(K, ws.y0, ws.rows, ws.Pb, ws.colidx, ws.ncols, ws.ncc,
                                                                                             ws.geo);
     return cudaGetLastError();
 }
@@ -321,7 +336,7 @@ cudaError_t sweep_depth_to_weak(const PassK &K, SweepWorkspace &ws, float *curve
     ws.valid = false;
     for (int y0 = 0; y0 < K.H; y0 += rows) {
         const int nr = std::min(rows, K.H - y0);
-        cudaError_t e = sweep_build_band(K, ws, 1, y0 * K.W, nr * K.W, st, launches);
+        cudaError_t e = sweep_build_band(K, ws, 1, y0, nr, st, launches);
         if (e != cudaSuccess) return e;
         if ((e = sweep_classify_band(K, ws, curve, st)) != cudaSuccess) return e;
         if (launches && y0 + nr < K.H) *launches += 1;
@@ -338,7 +353,7 @@ cudaError_t sweep_local_refine(const PassK &K, SweepWorkspace &ws, cudaStream_t 
     const int rows = band_rows(K, ws);
     for (int y0 = 0; y0 < K.H; y0 += rows) {
         const int nr = std::min(rows, K.H - y0);
-        cudaError_t e = sweep_build_band(K, ws, 0, y0 * K.W, nr * K.W, st, launches);
+        cudaError_t e = sweep_build_band(K, ws, 0, y0, nr, st, launches);
         if (e != cudaSuccess) return e;
         if ((e = sweep_refine_band(K, ws, st)) != cudaSuccess) return e;
         if (launches && y0 + nr < K.H) *launches += 1;
