@@ -82,6 +82,10 @@ class STAGE:
         CONFIDENCE, LOCAL_REFINE = range(11)
 
 
+class POOL:
+    DEPTH, NORMAL, WEAK, CONFIDENCE, SKIP = range(5)
+
+
 class FIELD:
     PLANES, COSTS, SELECTED_VIEWS, VIEW_WEIGHT, WEAK_INFO, CONFIDENCE, FIT_PLANES, WEAK_RELIABLE, NEAREST_STRONG, \
         ANCHORS, IMAGE, SRC_DEPTH = range(12)
@@ -140,6 +144,9 @@ def load_library(path=None):
     lib.apde_weak_vis_filter.argtypes = [P, P]
     lib.apde_fuse.argtypes = [P, C.c_int, P, P, C.c_int64, C.POINTER(C.c_int64)]
     lib.apde_fuse_variant.argtypes = [P, C.c_int, C.c_int, P, P, C.c_int64, C.POINTER(C.c_int64)]
+    lib.apde_weak_vis_filter_range.argtypes = [P, C.c_int, C.c_int, P]
+    lib.apde_map_pool.argtypes = [P, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.apde_views_mark_maps.argtypes = [P, C.c_int, C.c_int]
     _lib = lib
     return lib
 
@@ -178,6 +185,7 @@ class Context:
         self._h = None
         self._check(self.lib.apde_create(device, C.byref(h)))
         self._h = h
+        self.device = device
 
     def _check(self, rc):
         if rc != 0:
@@ -234,6 +242,12 @@ class Context:
             self._check(self.lib.apde_view_download(self._h, view, _ptr(depth), _ptr(normal), _ptr(weak), _ptr(conf),
                                                     C.byref(w), C.byref(h)))
         return depth, normal, weak, conf
+
+    def view_dims(self, view):
+        """(width, height) of the maps stored for a view, (0, 0) if none yet"""
+        w, h = C.c_int(), C.c_int()
+        self._check(self.lib.apde_view_download(self._h, view, None, None, None, None, C.byref(w), C.byref(h)))
+        return w.value, h.value
 
     def view_upload(self, view, depth=None, normal=None, weak=None, conf=None):
         ref = next(a for a in (depth, normal, weak, conf) if a is not None)
@@ -357,6 +371,19 @@ class Context:
         skip = np.zeros((self.V,) + d.shape, np.uint8)
         self._check(self.lib.apde_weak_vis_filter(self._h, _ptr(skip)))
         return skip
+
+    def weak_vis_filter_range(self, first_view, num_views):
+        """WeakVisFilter for a shard of reference views; the skip maps stay in the device pool (POOL.SKIP)"""
+        self._check(self.lib.apde_weak_vis_filter_range(self._h, first_view, num_views, None))
+
+    def map_pool(self, which):
+        """(device pointer, total bytes, bytes per view) of the [V][...] pool of one map field"""
+        ptr, total, per = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        self._check(self.lib.apde_map_pool(self._h, which, C.byref(ptr), C.byref(total), C.byref(per)))
+        return ptr.value, total.value, per.value
+
+    def views_mark_maps(self, width, height):
+        self._check(self.lib.apde_views_mark_maps(self._h, width, height))
 
     def fuse(self, use_weak_filter=True, max_points=None, variant=0):
         """variant 0 = RunFusion, 1 = RunFusion_TAT_I, 2 = RunFusion_TAT_A (main.cpp:277-283)"""

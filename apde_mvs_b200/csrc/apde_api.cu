@@ -42,6 +42,8 @@ struct ViewStore {
     std::vector<int> src;
     uint8_t *d_gray = nullptr, *d_bgr = nullptr;
     int mw = 0, mh = 0;  // size of the stored maps (0 = none yet)
+    int dw = 0, dh = 0;  // size of this view's depth map in the READABLE pool d_depth_pool[cur]: equal to mw x mh, except in
+                         // Jacobi mode between a view's finish and the end of the pass (the new map went to the other pool)
     float *d_normal = nullptr;
     uint8_t *d_weak = nullptr, *d_conf = nullptr;
     bool has_conf = false;
@@ -55,6 +57,10 @@ struct apde_context {
     bool committed = false;
     std::vector<ViewStore> views;
     float *d_depth_pool[2] = {nullptr, nullptr};  // [V][W*H] ; [1] only allocated in Jacobi mode
+    // normal / weak / confidence maps of all views, contiguous per field so that a multi-GPU job can all-gather them in
+    // place before fusion (apde_map_pool); ViewStore::d_normal / d_weak / d_conf point into these
+    float *d_normal_pool = nullptr;               // [V][W*H*3]
+    uint8_t *d_weak_pool = nullptr, *d_conf_pool = nullptr;  // [V][W*H]
     int cur = 0;
     // pyramid level (one alive at a time)
     // pyramid levels: built on first use, kept for the whole scene (images are immutable after commit)
@@ -177,9 +183,11 @@ static void free_level(apde_context *c) {
 }
 static void free_scene(apde_context *c) {
     for (auto &v : c->views) {
-        cudaFree(v.d_gray); cudaFree(v.d_bgr); cudaFree(v.d_normal); cudaFree(v.d_weak); cudaFree(v.d_conf);
+        cudaFree(v.d_gray); cudaFree(v.d_bgr);
     }
     c->views.clear();
+    cudaFree(c->d_normal_pool); cudaFree(c->d_weak_pool); cudaFree(c->d_conf_pool);
+    c->d_normal_pool = nullptr; c->d_weak_pool = c->d_conf_pool = nullptr;
     cudaFree(c->d_depth_pool[0]); cudaFree(c->d_depth_pool[1]);
     c->d_depth_pool[0] = c->d_depth_pool[1] = nullptr;
     free_level(c);
@@ -222,7 +230,7 @@ int apde_scene_begin(apde_context *c, int num_views, int width, int height) {
         // same shape as the resident scene: keep every allocation, only forget the maps and the pyramid level
         CU(cudaStreamSynchronize(c->stream));
         for (auto &v : c->views) {
-            v.mw = v.mh = 0; v.has_conf = false; v.src.clear();
+            v.mw = v.mh = v.dw = v.dh = 0; v.has_conf = false; v.src.clear();
             CU(cudaMemsetAsync(v.d_conf, 0, (size_t)c->W * c->H, c->stream));
         }
         for (auto &L : c->levels) L.stale = true;
@@ -236,12 +244,16 @@ int apde_scene_begin(apde_context *c, int num_views, int width, int height) {
     c->V = num_views; c->W = width; c->H = height;
     c->views.resize(num_views);
     const size_t P = (size_t)width * height;
-    for (auto &v : c->views) {
+    CU(cudaMalloc(&c->d_normal_pool, (size_t)num_views * P * 3 * sizeof(float)));
+    CU(cudaMalloc(&c->d_weak_pool, (size_t)num_views * P));
+    CU(cudaMalloc(&c->d_conf_pool, (size_t)num_views * P));
+    CU(cudaMemset(c->d_conf_pool, 0, (size_t)num_views * P));  // no confidence map exists before the first geometric / APD pass (main.cpp:187-190)
+    for (int i = 0; i < num_views; ++i) {
+        ViewStore &v = c->views[i];
         CU(cudaMalloc(&v.d_gray, P));
-        CU(cudaMalloc(&v.d_normal, P * 3 * sizeof(float)));
-        CU(cudaMalloc(&v.d_weak, P));
-        CU(cudaMalloc(&v.d_conf, P));
-        CU(cudaMemset(v.d_conf, 0, P));  // no confidence map exists before the first geometric / APD pass (main.cpp:187-190)
+        v.d_normal = c->d_normal_pool + (size_t)i * P * 3;
+        v.d_weak = c->d_weak_pool + (size_t)i * P;
+        v.d_conf = c->d_conf_pool + (size_t)i * P;
         memset(&v.cam, 0, sizeof(v.cam));
     }
     CU(cudaMalloc(&c->d_depth_pool[0], (size_t)num_views * P * sizeof(float)));
@@ -430,6 +442,7 @@ int apde_view_upload(apde_context *c, int view, const float *depth, const float 
     if (weak) CU(cudaMemcpy(v.d_weak, weak, P, cudaMemcpyHostToDevice));
     if (conf) { CU(cudaMemcpy(v.d_conf, conf, P, cudaMemcpyHostToDevice)); v.has_conf = true; }
     v.mw = width; v.mh = height;
+    if (depth) { v.dw = width; v.dh = height; }
     return APDE_OK;
 }
 
@@ -551,8 +564,8 @@ int apde_problem_setup(apde_context *c, int ref_view, const apde_params *params,
         for (int i = 0; i <= N; ++i) {
             const int vid = (i == 0) ? ref_view : rv.src[i - 1];
             const ViewStore &sv = c->views[vid];
-            if (sv.mw == 0) return fail(APDE_ERR_STATE, "problem_setup: view %d has no depth map yet", vid);
-            CU(launch_resize_nearest(c->d_depth_pool[c->cur] + (size_t)vid * Pfull, sv.mw, sv.mh, c->d_depthws + (size_t)i * P, w, h, 4, st));
+            if (sv.dw == 0) return fail(APDE_ERR_STATE, "problem_setup: view %d has no depth map yet", vid);
+            CU(launch_resize_nearest(c->d_depth_pool[c->cur] + (size_t)vid * Pfull, sv.dw, sv.dh, c->d_depthws + (size_t)i * P, w, h, 4, st));
         }
         c->launches += N + 1;
     }
@@ -571,7 +584,7 @@ int apde_problem_setup(apde_context *c, int ref_view, const apde_params *params,
         const float *dsrc = c->d_depth_pool[c->cur] + (size_t)ref_view * Pfull;
         const float *nsrc = rv.d_normal;
         if (rv.mw != w || rv.mh != h) {
-            CU(launch_resize_nearest(dsrc, rv.mw, rv.mh, c->d_scratch_depth, w, h, 4, st));
+            CU(launch_resize_nearest(dsrc, rv.dw, rv.dh, c->d_scratch_depth, w, h, 4, st));
             CU(launch_resize_nearest(nsrc, rv.mw, rv.mh, c->d_scratch_normal, w, h, 12, st));
             dsrc = c->d_scratch_depth; nsrc = c->d_scratch_normal;
             c->launches += 2;
@@ -847,6 +860,7 @@ static int problem_finish_impl(apde_context *c, bool jacobi) {
         rv.has_conf = true;
     }
     rv.mw = c->K.W; rv.mh = c->K.H;
+    if (!jacobi) { rv.dw = rv.mw; rv.dh = rv.mh; }
     c->problem_active = false;
     return APDE_OK;
 }
@@ -1039,6 +1053,7 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
             }
         }
         c->cur ^= 1;
+        for (auto &v : c->views) { v.dw = v.mw; v.dh = v.mh; }
     }
     CU(cudaStreamSynchronize(c->stream));
     float dev_ms = 0.0f;
@@ -1093,8 +1108,42 @@ static int fusion_views(apde_context *c, std::vector<FusionView> &fv, int *mw, i
     return APDE_OK;
 }
 
-int apde_weak_vis_filter(apde_context *c, uint8_t *skip_weaks) {
+int apde_map_pool(apde_context *c, int which, void **device_ptr, size_t *bytes_total, size_t *bytes_per_view) {
+    if (!c || c->V <= 0 || !device_ptr) return fail(APDE_ERR_STATE, "map_pool: no scene");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    const size_t P = (size_t)c->W * c->H;
+    size_t per = 0;
+    switch (which) {
+        case APDE_POOL_DEPTH: *device_ptr = c->d_depth_pool[c->cur]; per = P * sizeof(float); break;
+        case APDE_POOL_NORMAL: *device_ptr = c->d_normal_pool; per = P * 3 * sizeof(float); break;
+        case APDE_POOL_WEAK: *device_ptr = c->d_weak_pool; per = P; break;
+        case APDE_POOL_CONFIDENCE: *device_ptr = c->d_conf_pool; per = P; break;
+        case APDE_POOL_SKIP:
+            if (!c->d_skip) {
+                CU(cudaMalloc(&c->d_skip, (size_t)c->V * P));
+                CU(cudaMemset(c->d_skip, 0, (size_t)c->V * P));
+            }
+            *device_ptr = c->d_skip;
+            per = c->views[0].mw ? (size_t)c->views[0].mw * c->views[0].mh : P;  // rows are strided by the MAP size
+            break;
+        default: return fail(APDE_ERR_ARG, "map_pool: unknown pool %d", which);
+    }
+    if (bytes_total) *bytes_total = per * c->V;
+    if (bytes_per_view) *bytes_per_view = per;
+    return APDE_OK;
+}
+
+int apde_views_mark_maps(apde_context *c, int width, int height) {
+    if (!c || c->V <= 0) return fail(APDE_ERR_STATE, "views_mark_maps: no scene");
+    if (width <= 0 || height <= 0 || width > c->W || height > c->H) return fail(APDE_ERR_ARG, "views_mark_maps: bad size");
+    for (auto &v : c->views) { v.mw = v.dw = width; v.mh = v.dh = height; v.has_conf = true; }
+    return APDE_OK;
+}
+
+int apde_weak_vis_filter_range(apde_context *c, int first_view, int num_views, uint8_t *skip_weaks) {
     if (!c || c->V <= 0) return fail(APDE_ERR_STATE, "weak_vis_filter: no scene");
+    if (first_view < 0 || num_views < 0 || first_view + num_views > c->V) return fail(APDE_ERR_ARG, "weak_vis_filter: bad view range");
     CU(cudaSetDevice(c->device));
     std::vector<FusionView> fv;
     int mw, mh;
@@ -1102,12 +1151,17 @@ int apde_weak_vis_filter(apde_context *c, uint8_t *skip_weaks) {
     if (rc) return rc;
     const size_t P = (size_t)mw * mh;
     if (!c->d_skip) CU(cudaMalloc(&c->d_skip, (size_t)c->V * c->W * c->H));
-    CU(cudaMemsetAsync(c->d_skip, 0, (size_t)c->V * P, c->stream));
-    CU(fusion_weak_vis_filter(fv, mw, mh, c->W, c->H, c->d_skip, c->stream));
-    c->launches += c->V;
+    CU(cudaMemsetAsync(c->d_skip + (size_t)first_view * P, 0, (size_t)num_views * P, c->stream));
+    CU(fusion_weak_vis_filter(fv, mw, mh, first_view, num_views, c->d_skip, c->stream));
+    c->launches += num_views;
     CU(cudaStreamSynchronize(c->stream));
-    if (skip_weaks) CU(cudaMemcpy(skip_weaks, c->d_skip, (size_t)c->V * P, cudaMemcpyDeviceToHost));
+    if (skip_weaks) CU(cudaMemcpy(skip_weaks, c->d_skip + (size_t)first_view * P, (size_t)num_views * P, cudaMemcpyDeviceToHost));
     return APDE_OK;
+}
+
+int apde_weak_vis_filter(apde_context *c, uint8_t *skip_weaks) {
+    if (!c || c->V <= 0) return fail(APDE_ERR_STATE, "weak_vis_filter: no scene");
+    return apde_weak_vis_filter_range(c, 0, c->V, skip_weaks);
 }
 
 int apde_fuse(apde_context *c, int use_weak_filter, float *xyz, float *bgr, int64_t max_points, int64_t *num_points) {
@@ -1125,7 +1179,9 @@ int apde_fuse_variant(apde_context *c, int variant, int use_weak_filter, float *
     if (rc) return rc;
     const size_t P = (size_t)mw * mh;
     if (!c->d_skip) CU(cudaMalloc(&c->d_skip, (size_t)c->V * c->W * c->H));
-    if (use_weak_filter) {
+    if (use_weak_filter == APDE_WEAK_FILTER_KEEP) {
+        // skip maps already in the pool (filled by apde_weak_vis_filter_range on this or on peer GPUs)
+    } else if (use_weak_filter) {
         if ((rc = apde_weak_vis_filter(c, nullptr))) return rc;
     } else {
         CU(cudaMemsetAsync(c->d_skip, 0, (size_t)c->V * P, c->stream));

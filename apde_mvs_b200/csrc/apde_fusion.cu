@@ -238,14 +238,13 @@ static cudaError_t upload_cams(const std::vector<FusionView> &views, FCam **d_ca
     return cudaMemcpy(*d_cams, hc.data(), hc.size() * sizeof(FCam), cudaMemcpyHostToDevice);
 }
 
-cudaError_t fusion_weak_vis_filter(const std::vector<FusionView> &views, int w, int h, int Wfull, int Hfull, uint8_t *skip,
+cudaError_t fusion_weak_vis_filter(const std::vector<FusionView> &views, int w, int h, int first_view, int num_views, uint8_t *skip,
                                    cudaStream_t st) {
     FCam *d_cams = nullptr;
-    (void)Wfull; (void)Hfull;
     cudaError_t e = upload_cams(views, &d_cams);
     if (e != cudaSuccess) return e;
     const int V = (int)views.size(), P = w * h;
-    for (int ref = 0; ref < V; ++ref) k_weak_vis<<<(P + 127) / 128, 128, 0, st>>>(d_cams, V, ref, w, h, skip);
+    for (int ref = first_view; ref < first_view + num_views; ++ref) k_weak_vis<<<(P + 127) / 128, 128, 0, st>>>(d_cams, V, ref, w, h, skip);
     e = cudaStreamSynchronize(st);
     cudaFree(d_cams);
     return e != cudaSuccess ? e : cudaGetLastError();

@@ -19,8 +19,8 @@ struct FusionView {
     std::vector<int> src;  // neighbour view indices
 };
 
-// skip: [V][P] device, zero-initialised by the caller
-cudaError_t fusion_weak_vis_filter(const std::vector<FusionView> &views, int w, int h, int Wfull, int Hfull, uint8_t *skip,
+// skip: [V][P] device, rows [first_view, first_view + num_views) zero-initialised by the caller and filled here
+cudaError_t fusion_weak_vis_filter(const std::vector<FusionView> &views, int w, int h, int first_view, int num_views, uint8_t *skip,
                                    cudaStream_t st);
 // greedy fusion in the reference order; xyz / bgr are HOST buffers (may be null)
 cudaError_t fusion_run(const std::vector<FusionView> &views, int w, int h, const uint8_t *skip, float *xyz, float *bgr,

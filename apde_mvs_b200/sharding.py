@@ -10,8 +10,8 @@ def shard(num_views, world, rank):
     return first, base + (1 if rank < rem else 0)
 
 
-def exchange_depth_maps(dist, pool, num_views, world):
-    """pool: [V, P] tensor replicated on every rank, each rank has fresh rows for its own shard only.
+def exchange_rows(dist, pool, num_views, world):
+    """pool: [V, X] tensor (any dtype) replicated on every rank, each rank has fresh rows for its own shard only.
     Equal shards use one in-place all_gather_into_tensor; ragged shards fall back to per-rank broadcasts."""
     base, rem = divmod(num_views, world)
     rank = dist.get_rank()
@@ -26,3 +26,8 @@ def exchange_depth_maps(dist, pool, num_views, world):
         first, count = shard(num_views, world, r)
         if count:
             dist.broadcast(pool[first:first + count], src=r)
+
+
+def exchange_depth_maps(dist, pool, num_views, world):
+    """the per-pass exchange of the replicated depth pool (kept under its first name)"""
+    exchange_rows(dist, pool, num_views, world)

@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--rounds", type=int, default=0, help="0 = reference rule (ComputeRoundNum)")
     ap.add_argument("--geom-iters", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fusion", action="store_true", help="skip the fusion report (outside the timed metric)")
     ap.add_argument("--ref-views", type=int, default=0, help="reference arm: reference views processed per step (0 = all)")
     return ap.parse_args()
 
@@ -293,10 +294,51 @@ def run_ours(args, rank, world, local_rank):
     }
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, scene, evals_total / args.steps / V)
+    if world == 1 and not args.no_fusion:
+        out["fusion"] = fusion_report(args, ctx, scene, cpu=not args.no_cpu_baseline)
     print(json.dumps(out))
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------- fusion (outside the metric)
+def fusion_report(args, ctx, scene, cpu=True):
+    """WeakVisFilter + RunFusion of the maps the timed steps left on the device: GPU wall time for the whole scene, and the
+    reference's host-side fusion (APD.cpp:962-1227, restated in the oracle, one thread as in the reference's main loop) on a
+    bounded sample -- the first 4 views with their neighbours among those -- timed beside the GPU on the same sample."""
+    from apde_mvs_b200.binding import Context
+    from apde_mvs_b200.scene import Scene
+    V = len(scene.images)
+    t0 = time.perf_counter()
+    xyz, _ = ctx.fuse(True)
+    rep = {"gpu_ms_scene": (time.perf_counter() - t0) * 1e3, "points_scene": int(len(xyz)), "views_scene": V}
+    nv = min(4, V)
+    if nv < 3:
+        return rep
+    sub = Scene(scene.width, scene.height)
+    sub.K = scene.K
+    sub.images, sub.cameras = scene.images[:nv], scene.cameras[:nv]
+    sub.pairs = [[q for q in range(nv) if q != v] for v in range(nv)]
+    maps = [ctx.view_download(v) for v in range(nv)]
+    c2 = Context(ctx.device)
+    c2.load_scene(sub)
+    for v in range(nv):
+        c2.view_upload(v, *maps[v])
+    c2.fuse(True)  # warm-up (allocations)
+    t0 = time.perf_counter()
+    gx, _ = c2.fuse(True)
+    rep.update({"sample": "views 0..%d, %d neighbours each, %dx%d" % (nv - 1, nv - 1, scene.width, scene.height),
+                "gpu_ms_sample": (time.perf_counter() - t0) * 1e3, "points_sample": int(len(gx))})
+    c2.close()
+    if cpu:
+        from oracle import binding as orc
+        depths, normals, weaks, confs = (np.stack([m[i] for m in maps]) for i in range(4))
+        t0 = time.perf_counter()
+        ox, _, _ = orc.fusion(sub.cameras, depths, normals, weaks, confs, sub.pairs, None, num_threads=os.cpu_count() or 1)
+        rep.update({"cpu_ms_sample": (time.perf_counter() - t0) * 1e3, "cpu_kind": "port", "cpu_threads_weak_vis_filter": os.cpu_count() or 1,
+                    "cpu_threads_fusion": 1, "identical_to_cpu": bool(len(ox) == len(gx) and np.allclose(ox, gx, rtol=1e-5, atol=1e-5))})
+    return rep
 
 
 # ----------------------------------------------------------------------------------------------- CPU baseline (oracle port)

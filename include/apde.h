@@ -231,6 +231,23 @@ int apde_weak_vis_filter(apde_context *ctx, uint8_t *skip_weaks);
  * (either may be NULL to only count).  use_weak_filter mirrors the CLI flag (main.cpp:19). */
 int apde_fuse(apde_context *ctx, int use_weak_filter, float *xyz, float *bgr, int64_t max_points,
               int64_t *num_points);
+/* WeakVisFilter for reference views [first_view, first_view + num_views) only: the per-view work items of the reference's
+ * thread pool (APD.cpp:1040-1047) sharded over GPUs.  skip_weaks: uint8[num_views][P] out (host) or NULL. */
+int apde_weak_vis_filter_range(apde_context *ctx, int first_view, int num_views, uint8_t *skip_weaks);
+/* use_weak_filter value for apde_fuse*: keep the skip maps that are already in the APDE_POOL_SKIP pool */
+#define APDE_WEAK_FILTER_KEEP 2
+
+/* Multi-GPU fusion: the maps of all views live in one contiguous device pool per field, [V][bytes_per_view]
+ * (maps smaller than the full resolution are packed at the start of their slot).  A job with one process per GPU
+ * all-gathers the rows of its own views in place (NCCL over NVLink), calls apde_views_mark_maps on every rank, shards
+ * WeakVisFilter with apde_weak_vis_filter_range, all-gathers APDE_POOL_SKIP and lets one rank run apde_fuse_variant with
+ * APDE_WEAK_FILTER_KEEP.  The pointer stays valid until the next apde_scene_begin with a different shape; for
+ * APDE_POOL_DEPTH it is the pool the next pass reads (same as apde_depth_pool). */
+enum apde_pool { APDE_POOL_DEPTH = 0, APDE_POOL_NORMAL = 1, APDE_POOL_WEAK = 2, APDE_POOL_CONFIDENCE = 3, APDE_POOL_SKIP = 4 };
+int apde_map_pool(apde_context *ctx, int which, void **device_ptr, size_t *bytes_total, size_t *bytes_per_view);
+/* declare that every view's slot in the pools now holds maps of width x height (after an all-gather of peer maps) */
+int apde_views_mark_maps(apde_context *ctx, int width, int height);
+
 /* The dataset-specific variants main.cpp:277-283 dispatches to: RunFusion (ETH3D and others), RunFusion_TAT_I
  * (APD.cpp:1229-1431) and RunFusion_TAT_A (APD.cpp:1433-1608). */
 enum apde_fuse_kind { APDE_FUSE_DEFAULT = 0, APDE_FUSE_TAT_I = 1, APDE_FUSE_TAT_A = 2 };

@@ -310,3 +310,93 @@ def test_depth_map_exchange_gloo_world2(V):
     for p in procs:
         p.join(60)
     assert all(ok for _, ok in res), res
+
+
+def _gloo_fusion_worker(rank, world, port, V, q):
+    """DistributedScene host logic on CPU tensors: a fake context whose 'kernels' write recognisable values"""
+    import torch
+    import torch.distributed as dist
+    from apde_mvs_b200.binding import POOL
+    from apde_mvs_b200.distributed import DistributedScene
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P = 48
+
+    class FakeCtx:
+        def __init__(self):
+            self.V = V
+            self.pools = {POOL.DEPTH: torch.zeros(V, P), POOL.NORMAL: torch.zeros(V, 3 * P), POOL.WEAK: torch.zeros(V, P, dtype=torch.uint8),
+                          POOL.CONFIDENCE: torch.zeros(V, P, dtype=torch.uint8), POOL.SKIP: torch.zeros(V, P, dtype=torch.uint8)}
+            self.log = []
+
+        def num_passes(self, sched):
+            return 3
+
+        def run_schedule_pass(self, sched, p, t):
+            assert sched.jacobi == 1
+            for v in range(sched.first_view, sched.first_view + sched.num_views_local):
+                # a pass may only read depth maps of the PREVIOUS pass from other views: they must all be there
+                if p > 0:
+                    assert torch.all(self.pools[POOL.DEPTH][:, 0] == torch.arange(V) + 100.0 * (p - 1) + 1), (p, self.pools[POOL.DEPTH][:, 0])
+            for v in range(sched.first_view, sched.first_view + sched.num_views_local):
+                self.pools[POOL.DEPTH][v] = v + 100.0 * p + 1
+                self.pools[POOL.NORMAL][v] = -(v + 1.0)
+                self.pools[POOL.WEAK][v] = v + 1
+                self.pools[POOL.CONFIDENCE][v] = 2 * v + 1
+            self.log.append("pass%d" % p)
+
+        def view_dims(self, v):
+            return (8, 6)
+
+        def views_mark_maps(self, w, h):
+            self.log.append("mark%dx%d" % (w, h))
+
+        def weak_vis_filter_range(self, first, count):
+            # needs every view's maps
+            assert torch.all(self.pools[POOL.WEAK][:, 0] == torch.arange(V, dtype=torch.uint8) + 1)
+            for v in range(first, first + count):
+                self.pools[POOL.SKIP][v] = 10 + v
+            self.log.append("filter%d+%d" % (first, count))
+
+        def fuse(self, use_weak_filter, variant=0):
+            assert use_weak_filter == 2  # keep the gathered skip maps
+            assert torch.all(self.pools[POOL.SKIP][:, 0] == torch.arange(V, dtype=torch.uint8) + 10)
+            assert torch.all(self.pools[POOL.NORMAL][:, 0] == -(torch.arange(V) + 1.0))
+            assert torch.all(self.pools[POOL.CONFIDENCE][:, 0] == 2 * torch.arange(V, dtype=torch.uint8) + 1)
+            self.log.append("fuse")
+            return "xyz", "bgr"
+
+    class CpuScene(DistributedScene):
+        def pool_tensor(self, which):
+            return self.ctx.pools[which]
+
+    from apde_mvs_b200.binding import Schedule
+    ctx = FakeCtx()
+    ds = CpuScene(ctx, dist, "cpu")
+    try:
+        ds.run_schedule(Schedule())
+        xyz, bgr = ds.fuse(True)
+        ok = (xyz == "xyz") if rank == 0 else (xyz is None)
+        ok = ok and ctx.log[:3] == ["pass0", "pass1", "pass2"] and ctx.log[3] == "mark8x6" and ctx.log[4].startswith("filter")
+        ok = ok and (("fuse" in ctx.log) == (rank == 0))
+    except AssertionError as e:  # report instead of hanging the peer
+        ok = False
+        print("rank %d: %r" % (rank, e))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("V", [6, 5])
+def test_distributed_fusion_host_logic_gloo_world2(V):
+    """per-pass depth exchange, then normal/weak/confidence gather, sharded WeakVisFilter, skip gather, rank-0 fusion"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + V
+    procs = [ctx.Process(target=_gloo_fusion_worker, args=(r, 2, port, V, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(ok for _, ok in res), res

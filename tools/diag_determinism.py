@@ -11,6 +11,8 @@ scene = make_office_scene(W, H, num_views=V, num_src=N, seed=2, arc_deg=15.0, we
 ctx = Context(0)
 sched = default_schedule()
 sched.seed = 21
+sched.jacobi = int(os.environ.get("JACOBI", "0"))
+if os.environ.get("ROUNDS"): sched.rounds = int(os.environ["ROUNDS"])
 runs = []
 for rep in range(2):
     ctx.load_scene(scene)
