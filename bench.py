@@ -350,7 +350,7 @@ def cpu_baseline(args, scene, evals_per_view):
     from helpers import ref_params
     from oracle import binding as orc
     cores = os.cpu_count() or 1
-    w, h = max(64, scene.width // 8), max(48, scene.height // 8)
+    w, h = max(64, scene.width // 4), max(48, scene.height // 4)  # ~10 s of CPU work at 1920x1080 x 10 views on 16 cores
     ids = [0] + list(scene.pairs[0])
     imgs, cams = [], []
     for i in ids:
