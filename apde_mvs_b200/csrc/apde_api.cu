@@ -1,6 +1,7 @@
 // apde_api.cu -- host driver behind the C ABI of include/apde.h: scene-resident images / cameras / maps, pyramid
 // levels as one layered texture, per-problem set-up (the reference's InuputInitialization + CudaSpaceInitialization,
 // APD.cpp:501-814, without any host round trip), the stage launcher and the multi-scale schedule of main.cpp:303-367.
+#include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -1012,6 +1013,14 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
     const int count = (s->num_views_local > 0) ? s->num_views_local : c->V;
     if (first < 0 || first + count > c->V) return fail(APDE_ERR_ARG, "run_schedule_pass: bad shard [%d, %d)", first, first + count);
 
+    // APDE_PROFILE_PASS=<pass>[:<occurrence>]: bracket that pass with cudaProfilerStart/Stop, for
+    // `ncu --profile-from-start off` captures of one pass deep inside a run (profiles/README)
+    static const int prof_pass = [] { const char *e = getenv("APDE_PROFILE_PASS"); return e ? atoi(e) : -1; }();
+    static const int prof_occ = [] { const char *e = getenv("APDE_PROFILE_PASS"); const char *q = e ? strchr(e, ':') : nullptr; return q ? atoi(q + 1) : 1; }();
+    static int prof_seen = 0;
+    const bool prof_now = pass_index == prof_pass && ++prof_seen == prof_occ;
+    if (prof_now) cudaProfilerStart();
+
     uint64_t c0[4];
     int rc = apde_get_counters(c, c0, 0);
     if (rc) return rc;
@@ -1056,6 +1065,7 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
         for (auto &v : c->views) { v.dw = v.mw; v.dh = v.mh; }
     }
     CU(cudaStreamSynchronize(c->stream));
+    if (prof_now) cudaProfilerStop();
     float dev_ms = 0.0f;
     CU(cudaEventElapsedTime(&dev_ms, evp0, evp1));
     cudaEventDestroy(evp0); cudaEventDestroy(evp1);
