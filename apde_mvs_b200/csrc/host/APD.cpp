@@ -130,10 +130,24 @@ void APD::Commit() {
 static void run_fusion_variant(int variant, const path &dense_folder, const std::string &name, bool weak_filter, bool export_color) {
     auto s = SceneSession::get(dense_folder);
     int64_t n = 0;
-    check(apde_fuse_variant(s->ctx, variant, weak_filter ? 1 : 0, nullptr, nullptr, 0, &n), "apde_fuse(count)");
+    int filter_mode = 0;
+    if (weak_filter) {  // WeakVisFilter once; its masks also go to <dense>/APD/<id>/skip.png as in the reference (APD.cpp:1026-1036)
+        int mw = 0, mh = 0;
+        check(apde_view_download(s->ctx, 0, nullptr, nullptr, nullptr, nullptr, &mw, &mh), "apde_view_download(dims)");
+        const size_t P = (size_t)mw * mh;
+        std::vector<uint8_t> skip(P * s->problems.size());
+        check(apde_weak_vis_filter(s->ctx, skip.data()), "apde_weak_vis_filter");
+        for (size_t v = 0; v < s->problems.size(); ++v) {
+            Mat img(mh, mw, CV_8UC1);
+            for (size_t i = 0; i < P; ++i) img.data()[i] = skip[v * P + i] == 1 ? 255 : 0;
+            WritePNG(s->problems[v].result_folder / "skip.png", img);
+        }
+        filter_mode = APDE_WEAK_FILTER_KEEP;
+    }
+    check(apde_fuse_variant(s->ctx, variant, filter_mode, nullptr, nullptr, 0, &n), "apde_fuse(count)");
     std::vector<float> xyz((size_t)n * 3), bgr((size_t)n * 3);
     int64_t n2 = 0;
-    check(apde_fuse_variant(s->ctx, variant, weak_filter ? 1 : 0, xyz.data(), bgr.data(), n, &n2), "apde_fuse");
+    check(apde_fuse_variant(s->ctx, variant, filter_mode, xyz.data(), bgr.data(), n, &n2), "apde_fuse");
     std::vector<PointList> pc((size_t)std::min(n, n2));
     for (size_t i = 0; i < pc.size(); ++i) {
         pc[i].coord = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};

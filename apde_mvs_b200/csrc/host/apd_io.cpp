@@ -148,18 +148,20 @@ static bool decode_pnm(const std::vector<uint8_t> &f, int &w, int &h, int &chann
     return true;
 }
 
-static bool decode_any(const path &p, int &w, int &h, int &ch, std::vector<uint8_t> &pix) {
+bool decode_jpeg(const std::vector<uint8_t> &f, bool want_color, int &w, int &h, int &channels, std::vector<uint8_t> &pix);  // apd_jpeg.cpp
+
+static bool decode_any(const path &p, bool want_color, int &w, int &h, int &ch, std::vector<uint8_t> &pix) {
     std::vector<uint8_t> f;
     if (!read_file(p, f)) { std::cout << "Error opening file: " << p << std::endl; return false; }
-    if (decode_png(f, w, h, ch, pix) || decode_pnm(f, w, h, ch, pix)) return true;
-    std::cout << "Error: unsupported image format (PNG / PGM / PPM, 8 bit) " << p << std::endl;  // JPEG: SURVEY.md 8(f)-3
+    if (decode_png(f, w, h, ch, pix) || decode_pnm(f, w, h, ch, pix) || decode_jpeg(f, want_color, w, h, ch, pix)) return true;
+    std::cout << "Error: unsupported image format (8-bit PNG / PGM / PPM / Huffman JPEG) " << p << std::endl;
     return false;
 }
 
 bool ReadImage(const path &img_path, Mat &gray) {
     int w, h, ch;
     std::vector<uint8_t> pix;
-    if (!decode_any(img_path, w, h, ch, pix)) return false;
+    if (!decode_any(img_path, false, w, h, ch, pix)) return false;
     gray.create(h, w, CV_8UC1);
     if (ch == 1) memcpy(gray.data(), pix.data(), pix.size());
     else  // cv::imread(IMREAD_GRAYSCALE) of a colour PNG goes through libpng's png_set_rgb_to_gray(0.299, 0.587): 15-bit
@@ -172,7 +174,7 @@ bool ReadImage(const path &img_path, Mat &gray) {
 bool ReadImageColor(const path &img_path, Mat &bgr) {
     int w, h, ch;
     std::vector<uint8_t> pix;
-    if (!decode_any(img_path, w, h, ch, pix)) return false;
+    if (!decode_any(img_path, true, w, h, ch, pix)) return false;
     bgr.create(h, w, CV_8UC3);
     for (size_t i = 0; i < (size_t)w * h; ++i) {
         if (ch == 1) { bgr.data()[3 * i] = bgr.data()[3 * i + 1] = bgr.data()[3 * i + 2] = pix[i]; }
@@ -186,6 +188,44 @@ bool WritePGM(const path &p, const Mat &g) {
     if (!out) return false;
     out << "P5\n" << g.cols << " " << g.rows << "\n255\n";
     out.write((const char *)g.data(), (std::streamsize)g.buf.size());
+    return (bool)out;
+}
+
+// 8-bit grey or BGR image as a non-interlaced PNG (filter 0, zlib), the format of the reference's skip.png (APD.cpp:1035)
+bool WritePNG(const path &p, const Mat &img) {
+    const int ch = img.type() == CV_8UC3 ? 3 : img.type() == CV_8UC1 ? 1 : 0;
+    if (!ch || img.empty()) return false;
+    const size_t stride = (size_t)img.cols * ch;
+    std::vector<uint8_t> raw((stride + 1) * img.rows);
+    for (int y = 0; y < img.rows; ++y) {
+        uint8_t *o = &raw[(stride + 1) * y];
+        *o++ = 0;
+        const uint8_t *s = img.data() + stride * y;
+        if (ch == 1) memcpy(o, s, stride);
+        else for (int x = 0; x < img.cols; ++x) { o[3 * x] = s[3 * x + 2]; o[3 * x + 1] = s[3 * x + 1]; o[3 * x + 2] = s[3 * x]; }
+    }
+    uLongf clen = compressBound((uLong)raw.size());
+    std::vector<uint8_t> comp(clen);
+    if (compress2(comp.data(), &clen, raw.data(), (uLong)raw.size(), 6) != Z_OK) return false;
+    std::ofstream out(p, std::ios::binary);
+    if (!out) return false;
+    auto chunk = [&](const char *tag, const uint8_t *d, uint32_t len) {
+        uint8_t hdr[8] = {(uint8_t)(len >> 24), (uint8_t)(len >> 16), (uint8_t)(len >> 8), (uint8_t)len, (uint8_t)tag[0], (uint8_t)tag[1], (uint8_t)tag[2], (uint8_t)tag[3]};
+        out.write((const char *)hdr, 8);
+        if (len) out.write((const char *)d, len);
+        uLong crc = crc32(0L, hdr + 4, 4);
+        if (len) crc = crc32(crc, d, len);
+        const uint8_t c[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
+        out.write((const char *)c, 4);
+    };
+    static const uint8_t sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
+    out.write((const char *)sig, 8);
+    const uint32_t w = (uint32_t)img.cols, h = (uint32_t)img.rows;
+    const uint8_t ihdr[13] = {(uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w, (uint8_t)(h >> 24), (uint8_t)(h >> 16), (uint8_t)(h >> 8), (uint8_t)h,
+                              8, (uint8_t)(ch == 3 ? 2 : 0), 0, 0, 0};
+    chunk("IHDR", ihdr, 13);
+    chunk("IDAT", comp.data(), (uint32_t)clen);
+    chunk("IEND", nullptr, 0);
     return (bool)out;
 }
 

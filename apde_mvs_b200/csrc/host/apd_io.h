@@ -1,7 +1,7 @@
 // apd_io.h -- host data plane of the drop-in surface: the reference's file formats without OpenCV / Boost.
 //   ReadBinMat / WriteBinMat   ".bin" maps ("dmb": int32 version=1, rows, cols, cv type + raw rows)  APD.cpp:18-83
 //   ReadCamera                 MVSNet *_cam.txt                                                     APD.cpp:85-135
-//   ReadImage / ReadImageColor PNG (zlib inflate) / PGM / PPM; grey = OpenCV's BGR2GRAY fixed point   APD.cpp:137-160
+//   ReadImage / ReadImageColor PNG (zlib inflate) / JPEG (apd_jpeg.cpp) / PGM / PPM, pixel-identical to cv::imread   APD.cpp:137-160
 //   ExportPointCloud           binary little-endian PLY, float xyz + uchar blue green red             APD.cpp:316-356
 //   GenerateSampleList         pair.txt -> Problem list                                              main.cpp:44-102
 #pragma once
@@ -47,6 +47,7 @@ bool ReadCamera(const path &cam_path, Camera &cam);
 bool ReadImage(const path &img_path, Mat &gray_u8);         // CV_8UC1 (the library converts to float on the device)
 bool ReadImageColor(const path &img_path, Mat &bgr_u8);     // CV_8UC3, BGR order as cv::imread(IMREAD_COLOR)
 bool WritePGM(const path &p, const Mat &gray_u8);
+bool WritePNG(const path &p, const Mat &img_u8);             // CV_8UC1 or CV_8UC3 (BGR), what cv::imwrite("*.png") stores
 bool ExportPointCloud(const path &ply_path, const std::vector<PointList> &pc, bool export_color = true);
 std::string ToFormatIndex(int index);
 

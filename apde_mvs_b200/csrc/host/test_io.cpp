@@ -18,6 +18,16 @@ int main(int argc, char **argv) {
         if (!ReadImageColor(argv[2], c)) return 1;
         return WriteBinMat(argv[3], c) ? 0 : 1;
     }
+    if (cmd == "png") {  // png <image> <out.png>: colour round trip through WritePNG
+        Mat c;
+        if (!ReadImageColor(argv[2], c)) return 1;
+        return WritePNG(argv[3], c) ? 0 : 1;
+    }
+    if (cmd == "graypng") {  // graypng <image> <out.png>
+        Mat g;
+        if (!ReadImage(argv[2], g)) return 1;
+        return WritePNG(argv[3], g) ? 0 : 1;
+    }
     if (cmd == "cam") {  // cam <cam.txt>
         Camera cam;
         if (!ReadCamera(argv[2], cam)) return 1;

@@ -49,6 +49,9 @@ def test_apd_cli_end_to_end(dense):
         acc = depth_accuracy(depth[12:-12, 12:-12], scene.gt_depth[v][12:-12, 12:-12])
         assert acc >= 0.99, (v, acc)
         assert conf.max() > 1  # geometric passes ran
+        import cv2
+        skip = cv2.imread(str(d / "APD" / ("%08d" % v) / "skip.png"), cv2.IMREAD_UNCHANGED)  # WeakVisFilter mask, APD.cpp:1035
+        assert skip is not None and skip.shape == (192, 256) and set(np.unique(skip)) <= {0, 255}
     raw = open(d / "APD" / "APD.ply", "rb").read()
     head, body = raw.split(b"end_header\n")
     n = int(head.split(b"element vertex ")[1].split(b"\n")[0])
@@ -70,3 +73,35 @@ def test_apd_class_facade(dense):
     d, _ = dense
     out = subprocess.check_output([os.path.join(ROOT, "apde_mvs_b200", "_build", "test_apd_class"), str(d)], text=True)
     assert out.strip().endswith("OK"), out[-1500:]
+
+
+def test_apd_cli_jpeg_inputs_and_tat_fusion(dense, tmp_path):
+    """JPEG images (the reference datasets' format, decoded as cv::imread does) and the Tanks-and-Temples fusion variants
+    selected by --dataset (main.cpp:277-283, 294-298)"""
+    import cv2
+    import shutil
+    from apde_mvs_b200.scene import depth_accuracy
+    d, scene = dense
+    apd = os.path.join(ROOT, "apde_mvs_b200", "_build", "apd")
+    counts = {}
+    for dataset in ("TaT_i", "TaT_a"):
+        j = tmp_path / ("jpg_" + dataset)
+        os.makedirs(j / "images")
+        shutil.copytree(d / "cams", j / "cams")
+        shutil.copy(d / "pair.txt", j / "pair.txt")
+        for v in range(5):
+            cv2.imwrite(str(j / "images" / ("%08d.jpg" % v)), scene.images[v], [cv2.IMWRITE_JPEG_QUALITY, 95])
+        out = subprocess.run([apd, "-d", str(j), "--dataset", dataset], capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout[-2000:]
+        depth = _read_bin(j / "APD" / "00000002" / "depths.bin")
+        acc = depth_accuracy(depth[12:-12, 12:-12], scene.gt_depth[2][12:-12, 12:-12])
+        assert acc >= 0.98, acc
+        raw = open(j / "APD" / "APD.ply", "rb").read()
+        head, body = raw.split(b"end_header\n")
+        n = int(head.split(b"element vertex ")[1].split(b"\n")[0])
+        xyz = np.frombuffer(body, np.dtype([("p", "<f4", 3), ("c", "u1", 3)]))["p"]
+        res = np.abs(4 + 0.15 * xyz[:, 0] - 0.1 * xyz[:, 1] - xyz[:, 2])
+        print("%s: %d points, plane residual q99 %.4f, view 2 accuracy %.4f" % (dataset, n, np.quantile(res, 0.99), acc))
+        assert n > 20000 and np.quantile(res, 0.99) < 0.05
+        counts[dataset] = n
+    assert counts["TaT_a"] != counts["TaT_i"]  # different thresholds, different clouds

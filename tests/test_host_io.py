@@ -48,6 +48,60 @@ def test_png_decode_matches_opencv(tool, tmp_path):
     subprocess.check_call([tool, "color", str(tmp_path / "c.png"), str(tmp_path / "c.bin")])
     got, typ = _read_bin(tmp_path / "c.bin")
     assert typ == 16 and np.array_equal(got, cv2.imread(str(tmp_path / "c.png"), cv2.IMREAD_COLOR))
+    # WritePNG (skip.png, APD.cpp:1035) is readable by OpenCV and lossless
+    subprocess.check_call([tool, "png", str(tmp_path / "c.png"), str(tmp_path / "c2.png")])
+    assert np.array_equal(cv2.imread(str(tmp_path / "c2.png"), cv2.IMREAD_COLOR), color)
+    subprocess.check_call([tool, "graypng", str(tmp_path / "g.png"), str(tmp_path / "g2.png")])
+    assert np.array_equal(cv2.imread(str(tmp_path / "g2.png"), cv2.IMREAD_UNCHANGED), gray)
+
+
+def _natural(w, h, rng):
+    y, x = np.mgrid[0:h, 0:w]
+    img = np.stack([128 + 80 * np.sin(x / 17.0 + c) * np.cos(y / 23.0 - c) + 30 * np.sin((x + y) / 5.0) for c in range(3)], -1)
+    return np.clip(img + rng.normal(0, 6, img.shape), 0, 255).astype(np.uint8)
+
+
+def test_jpeg_decode_matches_opencv(tool, tmp_path):
+    """ReadImage / ReadImageColor on JPEG == cv::imread (libjpeg-turbo defaults: islow IDCT, luma plane for
+    IMREAD_GRAYSCALE, fancy chroma up-sampling, fixed-point YCbCr->RGB), bit for bit (APD.cpp:145, 1092)"""
+    import cv2
+    rng = np.random.default_rng(0)
+    S = cv2.IMWRITE_JPEG_SAMPLING_FACTOR
+    variants = {"q90": [cv2.IMWRITE_JPEG_QUALITY, 90], "q35": [cv2.IMWRITE_JPEG_QUALITY, 35], "progressive": [cv2.IMWRITE_JPEG_PROGRESSIVE, 1],
+                "restart": [cv2.IMWRITE_JPEG_RST_INTERVAL, 3], "optimized": [cv2.IMWRITE_JPEG_OPTIMIZE, 1],
+                "444": [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444], "422": [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422],
+                "420": [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420], "440": [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440], "grey": None}
+    for (w, h) in ((64, 48), (131, 97), (17, 9), (5, 3)):
+        for name, params in variants.items():
+            img = _natural(w, h, rng)
+            p = str(tmp_path / ("%dx%d_%s.jpg" % (w, h, name)))
+            if params is None:
+                cv2.imwrite(p, cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+            else:
+                cv2.imwrite(p, img, params)
+            subprocess.check_call([tool, "gray", p, str(tmp_path / "g.pgm")])
+            subprocess.check_call([tool, "color", p, str(tmp_path / "c.bin")])
+            assert np.array_equal(_read_pgm(tmp_path / "g.pgm"), cv2.imread(p, cv2.IMREAD_GRAYSCALE)), (w, h, name, "grey")
+            assert np.array_equal(_read_bin(tmp_path / "c.bin")[0], cv2.imread(p, cv2.IMREAD_COLOR)), (w, h, name, "colour")
+    # EXIF orientation: cv::imread turns the image upright
+    cv2.imwrite(str(tmp_path / "base.jpg"), _natural(96, 64, rng), [cv2.IMWRITE_JPEG_QUALITY, 92])
+    raw = open(tmp_path / "base.jpg", "rb").read()
+    for o in range(1, 9):
+        for e in "<>":
+            tiff = (b"II*\x00" if e == "<" else b"MM\x00*") + struct.pack(e + "I", 8) + struct.pack(e + "H", 1) + \
+                struct.pack(e + "HHIHH", 0x0112, 3, 1, o, 0) + struct.pack(e + "I", 0)
+            app1 = b"Exif\x00\x00" + tiff
+            p = str(tmp_path / ("exif%d.jpg" % o))
+            open(p, "wb").write(raw[:2] + b"\xff\xe1" + struct.pack(">H", len(app1) + 2) + app1 + raw[2:])
+            subprocess.check_call([tool, "gray", p, str(tmp_path / "g.pgm")])
+            subprocess.check_call([tool, "color", p, str(tmp_path / "c.bin")])
+            assert np.array_equal(_read_pgm(tmp_path / "g.pgm"), cv2.imread(p, cv2.IMREAD_GRAYSCALE)), ("exif", o, e)
+            assert np.array_equal(_read_bin(tmp_path / "c.bin")[0], cv2.imread(p, cv2.IMREAD_COLOR)), ("exif", o, e)
+    # truncated / non-JPEG data is an error, not a crash
+    open(tmp_path / "bad.jpg", "wb").write(raw[:200])
+    assert subprocess.run([tool, "gray", str(tmp_path / "bad.jpg"), str(tmp_path / "g.pgm")], capture_output=True).returncode in (0, 1)
+    open(tmp_path / "bad2.jpg", "wb").write(b"not an image")
+    assert subprocess.run([tool, "gray", str(tmp_path / "bad2.jpg"), str(tmp_path / "g.pgm")], capture_output=True).returncode == 1
 
 
 def test_bin_mat_format_roundtrip(tool, tmp_path):
