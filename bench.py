@@ -385,11 +385,8 @@ def run_reference(args, rank, world):
     schedule as main.cpp:303-367; host-side stages of InuputInitialization / ProcessProblem are emulated with cv2/numpy."""
     if rank != 0:
         return
-    import cv2
-    from apde_mvs_b200.binding import Camera
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from helpers import ref_params
     from oracle import ref_binding as ref
+    from oracle.ref_schedule import compute_round_num, run_reference_schedule
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libapd_ref.so not built (needs /root/reference at build time)"}))
         return
@@ -397,69 +394,10 @@ def run_reference(args, rank, world):
     V = len(scene.images)
     nviews = args.ref_views if args.ref_views > 0 else V
     W, H = scene.width, scene.height
-    rounds = args.rounds
-    if rounds <= 0:
-        rounds, m = 1, max(W, H)
-        while m > 800:
-            m //= 2
-            rounds += 1
-    fimgs = [im.astype(np.float32) for im in scene.images]
+    rounds = args.rounds if args.rounds > 0 else compute_round_num(W, H)
 
     def one_step():
-        maps = [dict() for _ in range(V)]
-        pm_ms = 0.0
-        it = 0
-        for i in range(rounds):
-            scale = 2 ** (rounds - 1 - i)
-            w, h = int(round(W / scale)), int(round(H / scale))
-            lv_imgs = fimgs if scale == 1 else [cv2.resize(im, (w, h), interpolation=cv2.INTER_LINEAR) for im in fimgs]
-            for j in range(-1, args.geom_iters):
-                p = ref_params()
-                p.use_APD = 0 if i == 0 else 1
-                if i > 0:
-                    p.ransac_threshold = 0.01 - i * 0.00125
-                    p.rotate_time = min(2 ** i, 4)
-                if j < 0:
-                    p.state, p.geom_consistency, p.weak_peak_radius = (0 if i == 0 else 1), 0, 6
-                else:
-                    p.state, p.geom_consistency, p.weak_peak_radius = 2, 1, max(4 - 2 * j, 2)
-                for v in range(nviews if (i, j) != (0, -1) else V):  # every view needs a depth map after the first pass
-                    ids = [v] + list(scene.pairs[v])
-                    cams = []
-                    for k in ids:
-                        cam = Camera()
-                        C.memmove(C.byref(cam), C.byref(scene.cameras[k]), C.sizeof(cam))
-                        if scale != 1:
-                            sx, sy = w / float(W), h / float(H)
-                            cam.K[0] *= sx; cam.K[2] *= sx; cam.K[4] *= sy; cam.K[5] *= sy
-                        cam.width, cam.height = w, h
-                        cams.append(cam)
-                    p.depth_min, p.depth_max = cams[0].depth_min * 0.6, cams[0].depth_max * 1.2
-
-                    def rs(a):
-                        return a if a.shape[:2] == (h, w) else cv2.resize(a, (w, h), interpolation=cv2.INTER_NEAREST)
-                    depths = None
-                    if p.geom_consistency or p.use_APD:
-                        depths = [rs(maps[k]["depth"]) for k in ids]
-                    planes = weak = conf = None
-                    if p.state != 0:
-                        planes = np.concatenate([rs(maps[v]["normal"]), rs(maps[v]["depth"])[..., None]], -1)
-                    if p.use_APD:
-                        weak, conf = rs(maps[v]["weak"]), rs(maps[v]["conf"])
-                    pl, wk, cf, ms = ref.run_pass([lv_imgs[k] for k in ids], cams, p, planes, weak, conf, depths, seed=1000 * it + v)
-                    if v < nviews:
-                        pm_ms += ms
-                    depth = pl[..., 3].copy()
-                    bad = (depth < p.depth_min) | (depth > p.depth_max)
-                    depth[bad] = 0
-                    wk[bad] = 2
-                    maps[v].update(depth=depth, normal=np.ascontiguousarray(pl[..., :3]), weak=wk)
-                    if p.geom_consistency or p.use_APD:
-                        maps[v]["conf"] = cf
-                    elif "conf" not in maps[v]:
-                        maps[v]["conf"] = np.ones((h, w), np.uint8)
-                it += 1
-        return pm_ms
+        return run_reference_schedule(scene, rounds, args.geom_iters, nviews)[1]
 
     for _ in range(min(args.warmup, 1)):
         one_step()
