@@ -101,8 +101,12 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 // reference-camera plane helpers (APD.cu:190-240), zero-skew pinhole
+// (explicit intrinsics, see plane_row: the same plane must give the same depth in every kernel it is inlined into)
 __device__ __forceinline__ float depth_from_plane(const PassK &K, float4 pl, int px, int py) {
-    return -pl.w * K.fx / ((px - K.cx) * pl.x + (K.fx / K.fy) * (py - K.cy) * pl.y + K.fx * pl.z);
+    const float a = __fmul_rn(__fsub_rn((float)px, K.cx), pl.x);
+    const float b = __fmul_rn(__fdividef(K.fx, K.fy), __fsub_rn((float)py, K.cy));
+    const float den = __fmaf_rn(K.fx, pl.z, __fmaf_rn(b, pl.y, a));
+    return __fdividef(__fmul_rn(-pl.w, K.fx), den);
 }
 __device__ __forceinline__ float distance_to_origin(const PassK &K, int px, int py, float depth, float4 n) {
     const float X0 = depth * (px - K.cx) / K.fx, X1 = depth * (py - K.cy) / K.fy;
@@ -202,11 +206,14 @@ __device__ __forceinline__ void load_ref_patch(const PassK &K, int px, int py, R
 }
 
 // m = n^T K_r^-1 / w : the hypothesis-dependent row vector of H = A - b m^T
+// Explicit intrinsics: every kernel that evaluates a hypothesis must produce the SAME row vector from the same plane, whatever
+// the compiler would contract around an inlined copy (a 1-ulp difference moves sample coordinates across the texture unit's
+// 1/256 weight buckets and shows up as 1e-4-level cost differences between kernel variants).
 __device__ __forceinline__ float3 plane_row(const PassK &K, float4 pl) {
-    const float iw = 1.0f / pl.w;
-    const float mx = pl.x / K.fx, my = pl.y / K.fy;
-    const float mz = pl.z - mx * K.cx - my * K.cy;
-    return make_float3(mx * iw, my * iw, mz * iw);
+    const float iw = rcp_approx(pl.w);
+    const float mx = __fdividef(pl.x, K.fx), my = __fdividef(pl.y, K.fy);
+    const float mz = __fmaf_rn(-my, K.cy, __fmaf_rn(-mx, K.cx, pl.z));
+    return make_float3(__fmul_rn(mx, iw), __fmul_rn(my, iw), __fmul_rn(mz, iw));
 }
 
 struct Homog { float h[9]; };
@@ -257,10 +264,10 @@ __device__ __forceinline__ float ncc_old(const PassK &K, const ViewK &vk, int px
     const Homog Hm = make_homography(vk, m);
     const float *h = Hm.h;
     const float fxp = (float)px, fyp = (float)py;
-    const float Z = h[6] * fxp + h[7] * fyp + h[8];
+    const float Z = __fadd_rn(__fmaf_rn(h[7], fyp, __fmul_rn(h[6], fxp)), h[8]);
     const float iz = rcp_approx(Z);
-    const float ptx = (h[0] * fxp + h[1] * fyp + h[2]) * iz;
-    const float pty = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
+    const float ptx = __fmul_rn(__fadd_rn(__fmaf_rn(h[1], fyp, __fmul_rn(h[0], fxp)), h[2]), iz);
+    const float pty = __fmul_rn(__fadd_rn(__fmaf_rn(h[4], fyp, __fmul_rn(h[3], fxp)), h[5]), iz);
     if (ptx >= (float)K.W || ptx < 0.0f || pty >= (float)K.H || pty < 0.0f) return 2.0f;
     return patch_ncc36<U>(K, Hm, vk.layer, px, py, rp);
 }
@@ -373,22 +380,23 @@ __device__ __forceinline__ float geom_cost(const PassK &K, const ViewK &vk, int 
                                            float4 plane) {
     const float depth = depth_from_plane(K, plane, px, py);
     const float fxp = (float)px, fyp = (float)py;
-    const float qx = vk.A[0] * fxp + vk.A[1] * fyp + vk.A[2];
-    const float qy = vk.A[3] * fxp + vk.A[4] * fyp + vk.A[5];
-    const float qz = vk.A[6] * fxp + vk.A[7] * fyp + vk.A[8];
-    const float Z = fmaf(depth, qz, vk.b[2]);
-    const float sx = fmaf(depth, qx, vk.b[0]) / Z, sy = fmaf(depth, qy, vk.b[1]) / Z;
+    // explicit intrinsics throughout: the truncation below turns a 1-ulp difference into another depth texel
+    const float qx = __fadd_rn(__fmaf_rn(vk.A[1], fyp, __fmul_rn(vk.A[0], fxp)), vk.A[2]);
+    const float qy = __fadd_rn(__fmaf_rn(vk.A[4], fyp, __fmul_rn(vk.A[3], fxp)), vk.A[5]);
+    const float qz = __fadd_rn(__fmaf_rn(vk.A[7], fyp, __fmul_rn(vk.A[6], fxp)), vk.A[8]);
+    const float Z = __fmaf_rn(depth, qz, vk.b[2]);
+    const float sx = __fdividef(__fmaf_rn(depth, qx, vk.b[0]), Z), sy = __fdividef(__fmaf_rn(depth, qy, vk.b[1]), Z);
     // "(int)src_pt.x + 0.5f" through a clamped texture == clamped truncation (cvt.rzi saturates, NaN -> 0)
     const int ix = clampi(__float2int_rz(sx), 0, K.W - 1), iy = clampi(__float2int_rz(sy), 0, K.H - 1);
     const float sd = K.depth[(size_t)(v + 1) * K.W * K.H + (size_t)iy * K.W + ix];
     if (sd == 0.0f) return 3.0f;
-    const float rx = vk.Ai[0] * sx + vk.Ai[1] * sy + vk.Ai[2];
-    const float ry = vk.Ai[3] * sx + vk.Ai[4] * sy + vk.Ai[5];
-    const float rz = vk.Ai[6] * sx + vk.Ai[7] * sy + vk.Ai[8];
-    const float Zr = fmaf(sd, rz, vk.bi[2]);
-    const float bx = fmaf(sd, rx, vk.bi[0]) / Zr, by = fmaf(sd, ry, vk.bi[1]) / Zr;
-    const float dc = fxp - bx, dr = fyp - by;
-    return fminf(3.0f, sqrtf(dc * dc + dr * dr));
+    const float rx = __fadd_rn(__fmaf_rn(vk.Ai[1], sy, __fmul_rn(vk.Ai[0], sx)), vk.Ai[2]);
+    const float ry = __fadd_rn(__fmaf_rn(vk.Ai[4], sy, __fmul_rn(vk.Ai[3], sx)), vk.Ai[5]);
+    const float rz = __fadd_rn(__fmaf_rn(vk.Ai[7], sy, __fmul_rn(vk.Ai[6], sx)), vk.Ai[8]);
+    const float Zr = __fmaf_rn(sd, rz, vk.bi[2]);
+    const float bx = __fdividef(__fmaf_rn(sd, rx, vk.bi[0]), Zr), by = __fdividef(__fmaf_rn(sd, ry, vk.bi[1]), Zr);
+    const float dc = __fsub_rn(fxp, bx), dr = __fsub_rn(fyp, by);
+    return fminf(3.0f, sqrtf(__fmaf_rn(dr, dr, __fmul_rn(dc, dc))));
 }
 
 // packed view weights: 4 bits per view in a uint4

@@ -170,7 +170,7 @@ __device__ __forceinline__ void k_prop_strong_body(const PassK &K, int iter, int
             const int v = __ffs(mk) - 1;
             float c = ncc_old<U>(K, s_vk[v], px, py, m, rp);
             n_old++;
-            if (use_geom) { c = c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, plane_c); n_geom++; }
+            if (use_geom) { c = __fmaf_rn(K.geom_factor, geom_cost(K, s_vk[v], v, px, py, plane_c), c); n_geom++; }
             acc += (float)vw_get(w, v) * c;
         }
         cost_now = acc / wnorm;
@@ -206,7 +206,7 @@ __device__ __forceinline__ void k_prop_strong_body(const PassK &K, int iter, int
             const int v = __ffs(mk) - 1;
             float c = ncc_old<U>(K, s_vk[v], px, py, m, rp);
             n_old++;
-            if (use_geom) { c = c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp); n_geom++; }
+            if (use_geom) { c = __fmaf_rn(K.geom_factor, geom_cost(K, s_vk[v], v, px, py, tp), c); n_geom++; }
             acc += (float)vw_get(w, v) * c;
         }
         const float tc = acc / wnorm;
@@ -223,10 +223,219 @@ __device__ __forceinline__ void k_prop_strong_body(const PassK &K, int iter, int
     }
     count_evals(K, n_old, 0, n_geom);
 }
-__global__ void __launch_bounds__(128) k_prop_strong(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
-                                                     int ylimit) {
+__global__ void __launch_bounds__(128) k_prop_strong_v1(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
+                                                        int ylimit) {
     if (K.tex_unorm > 0.0f) k_prop_strong_body<true>(K, iter, color, tiles_x, ylimit);
     else k_prop_strong_body<false>(K, iter, color, tiles_x, ylimit);
+}
+
+// The same half-sweep with the refinement evaluations WARP-COMPACTED.
+//
+// In the kernel above every lane walks its OWN selected views in phase 3: at one instant the 32 lanes of a warp sample up
+// to N different source views (different layers of the texture array -> no cache locality) and the warp runs as long as
+// its lane with the most selected views.  Here the (pixel, selected view) pairs of a warp are listed VIEW-MAJOR in shared
+// memory and dealt out 32 at a time: a warp-wide texture fetch then covers neighbouring pixels of ONE view, all lanes carry
+// work, and every pair evaluates the five refinement hypotheses back to back.  The owner lane parks its reference patch and
+// its five hypotheses in shared memory (the phase-1 cost columns are dead by then), any lane may evaluate them, and the owner
+// gathers the costs afterwards and forms the weighted sums in ascending view order -- the arithmetic per cost and per sum
+// is unchanged, so the results are bit-identical to the kernel above (tests/test_gpu_parity.py runs both).
+//
+// per-thread shared-memory column (slot * blockDim + thread):  phase 1-2: [8N] candidate costs, [N] view priors
+//                                                              phase 3  : [38] ref patch, [20] 5 planes, [5N] costs
+constexpr int kStrongRefSlot = 0, kStrongPlaneSlot = kPatch + 2, kStrongCostSlot = kPatch + 2 + 20;
+__host__ __device__ inline int strong_column_floats(int N) { return max(9 * N, kStrongCostSlot + 5 * N); }
+
+template <bool U>
+__device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int iter, int color, int tiles_x, int ylimit) {
+    extern __shared__ float smem[];
+    const ViewK *s_vk = stage_views(K, smem);
+    const int W = K.W, N = K.N;
+    const int stride = blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *col0 = smem + views_smem_floats(N);                 // columns of all threads
+    float *sc = col0 + threadIdx.x;                            // this thread's column
+    float *sp = sc + 8 * N * stride;
+    unsigned short *items = reinterpret_cast<unsigned short *>(col0 + (size_t)strong_column_floats(N) * stride) + (size_t)warp * 32 * N;
+
+    int px = 0, py = 0;
+    bool active = half_pixel_or_list(K, color, tiles_x, ylimit, px, py);
+    const int center = py * W + px;
+    if (active && K.weak[center] == APDE_WEAK) active = false;
+
+    unsigned n_old = 0, n_geom = 0;
+    uint32_t wmask = 0;
+    uint4 w = make_uint4(0, 0, 0, 0);
+    float wnorm = 1.0f, cost_now = 0.0f, cost_written = 0.0f, depth_now = 0.0f;
+    float4 plane_now = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool use_geom = K.geom && K.impetus;
+    const float dmin = K.depth_min, dmax = K.depth_max;
+
+    if (active) {
+        RefPatch rp;
+        load_ref_patch<U>(K, px, py, rp);
+        int pos[8];
+        const unsigned flags = checkerboard_candidates(K.costs, W, K.H, px, py, pos);
+#pragma unroll 1
+        for (int h = 0; h < 8; ++h) {
+            if ((flags >> h) & 1u) {
+                const float3 m = plane_row(K, K.planes[pos[h]]);
+#pragma unroll 1
+                for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_old<U>(K, K.v[v], px, py, m, rp);
+                n_old += N;
+            } else {
+                // quirk 2: "float cost_array[8][32] = {2.0f}" leaves every entry 0 except [0][0]
+                for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = (h == 0 && v == 0) ? 2.0f : 0.0f;
+            }
+        }
+        uint32_t nbr_sel[4];
+        const unsigned nbr_valid = ((flags >> 0) & 1u) | (((flags >> 2) & 1u) << 1) | (((flags >> 4) & 1u) << 2) |
+                                   (((flags >> 6) & 1u) << 3);
+        nbr_sel[0] = (nbr_valid & 1u) ? K.sel[center - W] : 0u;
+        nbr_sel[1] = (nbr_valid & 2u) ? K.sel[center + W] : 0u;
+        nbr_sel[2] = (nbr_valid & 4u) ? K.sel[center - 1] : 0u;
+        nbr_sel[3] = (nbr_valid & 8u) ? K.sel[center + 1] : 0u;
+
+        Rng rng(K.seed, K.stream, (uint32_t)center, SITE_STRONG + iter);
+        w = select_views<4>(K, sc, sp, stride, nbr_sel, nbr_valid, iter, rng, &wmask, &wnorm);
+        K.vw[center] = w;
+
+        float final_costs[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            float acc = 0.0f;
+            for (uint32_t mk = wmask; mk; mk &= mk - 1) {
+                const int v = __ffs(mk) - 1;
+                acc += (float)vw_get(w, v) * sc[(h * N + v) * stride];
+            }
+            final_costs[h] = acc / wnorm;
+        }
+        int min_idx = 0;
+        {
+            float mc = final_costs[0];
+#pragma unroll
+            for (int h = 1; h < 8; ++h) if (final_costs[h] <= mc) { mc = final_costs[h]; min_idx = h; }  // ties -> last (quirk 3)
+        }
+        float fc_min = final_costs[0];
+#pragma unroll
+        for (int h = 1; h < 8; ++h) if (h == min_idx) fc_min = final_costs[h];
+
+        const float4 plane_c = K.planes[center];
+        plane_now = plane_c;
+        // current hypothesis on the selected views (one evaluation per pair: stays with the owner lane)
+        {
+            const float3 m = plane_row(K, plane_c);
+            float acc = 0.0f;
+            for (uint32_t mk = wmask; mk; mk &= mk - 1) {
+                const int v = __ffs(mk) - 1;
+                float c = ncc_old<U>(K, s_vk[v], px, py, m, rp);
+                n_old++;
+                if (use_geom) { c = __fmaf_rn(K.geom_factor, geom_cost(K, s_vk[v], v, px, py, plane_c), c); n_geom++; }
+                acc += (float)vw_get(w, v) * c;
+            }
+            cost_now = acc / wnorm;
+        }
+        cost_written = cost_now;
+        depth_now = depth_from_plane(K, plane_c, px, py);
+        if ((flags >> min_idx) & 1u) {
+            const float4 cand = K.planes[pos[min_idx]];
+            const float db = depth_from_plane(K, cand, px, py);
+            if (db >= dmin && db <= dmax && fc_min < cost_now) {
+                depth_now = db; plane_now = cand; cost_now = fc_min;
+                K.sel[center] = wmask;
+            }
+        }
+        // PlaneHypothesisRefinementStrong: all five candidates are built from the state BEFORE the loop (APD.cu:968-980)
+        const float depth_rand = rng.uniform() * (dmax - dmin) + dmin;
+        float4 cand_n[2];
+        cand_n[0] = random_normal(K, px, py, rng, depth_now);
+        const float lo = (1.0f - 0.02f) * depth_now, hi = (1.0f + 0.02f) * depth_now;
+        const float depth_pert = rng.uniform() * (hi - lo) + lo;  // the do-while can never repeat (quirk 6)
+        cand_n[1] = perturbed_normal(K, px, py, plane_now, rng, (float)(0.02 * 3.14159265358979323846));
+        // park the reference patch and the five hypotheses in this thread's column (phase-1 costs are dead now)
+#pragma unroll
+        for (int k = 0; k < kPatch; ++k) sc[(kStrongRefSlot + k) * stride] = rp.r[k];
+        sc[(kStrongRefSlot + kPatch) * stride] = rp.mean;
+        sc[(kStrongRefSlot + kPatch + 1) * stride] = rp.var;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            float4 tp = (i == 0 || i == 4) ? plane_now : (i == 3 ? cand_n[1] : cand_n[0]);
+            const float d = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : depth_now);
+            tp.w = distance_to_origin(K, px, py, d, tp);
+            sc[(kStrongPlaneSlot + 4 * i + 0) * stride] = tp.x;
+            sc[(kStrongPlaneSlot + 4 * i + 1) * stride] = tp.y;
+            sc[(kStrongPlaneSlot + 4 * i + 2) * stride] = tp.z;
+            sc[(kStrongPlaneSlot + 4 * i + 3) * stride] = tp.w;
+        }
+    }
+    __syncwarp();
+
+    // (pixel, selected view) pairs of this warp, view-major
+    int total = 0;
+    for (int v = 0; v < N; ++v) {
+        const unsigned m = __ballot_sync(0xffffffffu, active && ((wmask >> v) & 1u));
+        if (active && ((wmask >> v) & 1u)) items[total + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(lane | (v << 8));
+        total += __popc(m);
+    }
+    __syncwarp();
+    const int pxy = (px << 16) | py;
+#pragma unroll 1
+    for (int base = 0; base < total; base += 32) {
+        const bool has = base + lane < total;
+        const unsigned short it = has ? items[base + lane] : (unsigned short)0;
+        const int src = it & 31, v = it >> 8;
+        const int sxy = __shfl_sync(0xffffffffu, pxy, src);
+        if (has) {
+            const int spx = sxy >> 16, spy = sxy & 0xffff;
+            const float *scol = col0 + (warp * 32 + src);
+            RefPatch rp;
+#pragma unroll
+            for (int k = 0; k < kPatch; ++k) rp.r[k] = scol[(kStrongRefSlot + k) * stride];
+            rp.mean = scol[(kStrongRefSlot + kPatch) * stride];
+            rp.var = scol[(kStrongRefSlot + kPatch + 1) * stride];
+            const ViewK &vk = s_vk[v];
+#pragma unroll 1
+            for (int i = 0; i < 5; ++i) {
+                const float4 tp = make_float4(scol[(kStrongPlaneSlot + 4 * i + 0) * stride], scol[(kStrongPlaneSlot + 4 * i + 1) * stride],
+                                              scol[(kStrongPlaneSlot + 4 * i + 2) * stride], scol[(kStrongPlaneSlot + 4 * i + 3) * stride]);
+                const float3 m = plane_row(K, tp);
+                float c = ncc_old<U>(K, vk, spx, spy, m, rp);
+                n_old++;
+                if (use_geom) { c = __fmaf_rn(K.geom_factor, geom_cost(K, vk, v, spx, spy, tp), c); n_geom++; }
+                const_cast<float *>(scol)[(kStrongCostSlot + i * N + v) * stride] = c;
+            }
+        }
+    }
+    __syncwarp();
+
+    if (active) {
+#pragma unroll 1
+        for (int i = 0; i < 5; ++i) {
+            const float4 tp = make_float4(sc[(kStrongPlaneSlot + 4 * i + 0) * stride], sc[(kStrongPlaneSlot + 4 * i + 1) * stride],
+                                          sc[(kStrongPlaneSlot + 4 * i + 2) * stride], sc[(kStrongPlaneSlot + 4 * i + 3) * stride]);
+            float acc = 0.0f;
+            for (uint32_t mk = wmask; mk; mk &= mk - 1) {
+                const int v = __ffs(mk) - 1;
+                acc += (float)vw_get(w, v) * sc[(kStrongCostSlot + i * N + v) * stride];
+            }
+            const float tc = acc / wnorm;
+            const float db = depth_from_plane(K, tp, px, py);
+            if (db >= dmin && db <= dmax && tc < cost_now) { depth_now = db; plane_now = tp; cost_now = tc; }
+        }
+        if (K.state == APDE_REFINE_INIT) {
+            // costs[center] was overwritten with the recomputed current cost before this test (quirk 5)
+            if ((double)cost_now < (double)cost_written - 0.1) { K.costs[center] = cost_now; K.planes[center] = plane_now; }
+            else K.costs[center] = cost_written;
+        } else {
+            K.costs[center] = cost_now;
+            K.planes[center] = plane_now;
+        }
+    }
+    count_evals(K, n_old, 0, n_geom);
+}
+__global__ void __launch_bounds__(128) k_prop_strong(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
+                                                     int ylimit) {
+    if (K.tex_unorm > 0.0f) k_prop_strong_compact_body<true>(K, iter, color, tiles_x, ylimit);
+    else k_prop_strong_compact_body<false>(K, iter, color, tiles_x, ylimit);
 }
 
 
@@ -588,15 +797,32 @@ cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStr
             break;
         }
         case APDE_STAGE_PROP_STRONG: {
-            const int threads = prop_block_threads(N);
-            const size_t smem = prop_smem_bytes(N, threads);
+            const char *v1env = getenv("APDE_STRONG_V1");  // read per launch: tests toggle it inside one process
+            const bool v1 = v1env && v1env[0] == '1';
+            const int tiles = tiles8x * ((ylimit + 7) / 8);  // 32 same-colour pixels per tile == worst-case list length / 32
+            if (v1) {  // per-lane refinement loop (kept for A/B measurements and as the parity twin of the compacted kernel)
+                const int threads = prop_block_threads(N);
+                const size_t smem = prop_smem_bytes(N, threads);
+                static size_t configured = 0;
+                if (smem > configured) {
+                    cudaError_t e = cudaFuncSetAttribute(k_prop_strong_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e != cudaSuccess) return e;
+                    configured = smem;
+                }
+                const int wpb = threads / 32;
+                k_prop_strong_v1<<<(tiles + wpb - 1) / wpb, threads, smem, st>>>(K, iter, color, tiles8x, ylimit);
+                break;
+            }
+            // column floats + the warp's pair list (N shorts per thread)
+            auto bytes = [&](int threads) { return sizeof(float) * ((size_t)views_smem_floats(N) + (size_t)(strong_column_floats(N) + (N + 1) / 2) * threads); };
+            const int threads = bytes(128) <= 72 * 1024 ? 128 : (bytes(64) <= 100 * 1024 ? 64 : 32);
+            const size_t smem = bytes(threads);
             static size_t configured = 0;
             if (smem > configured) {
                 cudaError_t e = cudaFuncSetAttribute(k_prop_strong, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
                 configured = smem;
             }
-            const int tiles = tiles8x * ((ylimit + 7) / 8);  // 32 same-colour pixels per tile == worst-case list length / 32
             const int wpb = threads / 32;
             k_prop_strong<<<(tiles + wpb - 1) / wpb, threads, smem, st>>>(K, iter, color, tiles8x, ylimit);
             break;

@@ -133,3 +133,23 @@ def test_banded_sweep_is_identical():
     for v in range(4):
         for k in range(4):
             assert np.array_equal(a[v][k], b[v][k]), "view %d map %d differs between banded and single-band sweeps" % (v, k)
+
+
+def test_strong_propagation_kernel_variants_identical(tmp_path):
+    """the warp-compacted refinement of k_prop_strong (pairs of (pixel, selected view) dealt out view-major across the
+    warp) and the per-lane twin k_prop_strong_v1 give bit-identical maps over a whole two-round schedule"""
+    import os
+    import subprocess
+    import sys
+    from helpers import ROOT
+    outs = []
+    for v1 in ("0", "1"):
+        out = str(tmp_path / ("maps_v1_%s.npz" % v1))
+        env = dict(os.environ, APDE_STRONG_V1=v1)
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "dump_maps.py"), out, "320", "240", "5", "4", "0.25", "2"], env=env,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        outs.append(np.load(out))
+    a, b = outs
+    assert sorted(a.files) == sorted(b.files) and len(a.files) == 20
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), "map %s differs between the compacted and the per-lane kernel" % k
