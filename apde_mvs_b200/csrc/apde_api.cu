@@ -90,6 +90,7 @@ struct apde_context {
     uint4 *d_vw = nullptr;
     uint8_t *d_weak = nullptr, *d_conf = nullptr, *d_reliable = nullptr;
     short2 *d_nearest = nullptr, *d_anchors = nullptr;
+    uint16_t *d_ns_tiles = nullptr;
     int *d_lists = nullptr, *d_list_counts = nullptr;  // compacted checkerboard pixel lists (4 x list_cap)
     int list_cap = 0;
     bool lists_dirty = true;
@@ -195,7 +196,7 @@ static void free_scene(apde_context *c) {
     if (c->ws_alloc) {
         cudaFree(c->d_planes); cudaFree(c->d_fit); cudaFree(c->d_costs); cudaFree(c->d_depthws);
         cudaFree(c->d_scratch_depth); cudaFree(c->d_scratch_normal); cudaFree(c->d_sel); cudaFree(c->d_vw);
-        cudaFree(c->d_weak); cudaFree(c->d_conf); cudaFree(c->d_reliable); cudaFree(c->d_nearest); cudaFree(c->d_anchors);
+        cudaFree(c->d_weak); cudaFree(c->d_conf); cudaFree(c->d_reliable); cudaFree(c->d_nearest); cudaFree(c->d_anchors); cudaFree(c->d_ns_tiles);
         cudaFree(c->d_lists); cudaFree(c->d_list_counts);
         c->ws_alloc = false;
     }
@@ -306,6 +307,7 @@ static int alloc_workspace(apde_context *c) {
     CU(cudaMalloc(&c->d_conf, P));
     CU(cudaMalloc(&c->d_reliable, P));
     CU(cudaMalloc(&c->d_nearest, P * sizeof(short2)));
+    CU(cudaMalloc(&c->d_ns_tiles, (size_t)((c->W + 7) / 8) * ((c->H + 7) / 8) * sizeof(uint16_t)));
     CU(cudaMalloc(&c->d_anchors, P * APDE_ANCHOR_NUM * sizeof(short2)));
     c->list_cap = (int)(P / 2 + 64);
     CU(cudaMalloc(&c->d_lists, (size_t)4 * c->list_cap * sizeof(int)));
@@ -556,7 +558,7 @@ int apde_problem_setup(apde_context *c, int ref_view, const apde_params *params,
     K.tex_unorm = c->level_unorm;
     K.tex_inv = c->level_inv;
     K.planes = c->d_planes; K.costs = c->d_costs; K.sel = c->d_sel; K.vw = c->d_vw; K.weak = c->d_weak; K.conf = c->d_conf;
-    K.fit = c->d_fit; K.reliable = c->d_reliable; K.nearest = c->d_nearest; K.anchors = c->d_anchors;
+    K.fit = c->d_fit; K.reliable = c->d_reliable; K.nearest = c->d_nearest; K.ns_tiles = c->d_ns_tiles; K.anchors = c->d_anchors;
     K.depth = c->d_depthws; K.counters = c->d_counters + 4 * kStages;
     for (int i = 0; i < N; ++i) make_view_k(c->cams[0], c->cams[i + 1], rv.src[i], K.v[i]);
 
@@ -668,7 +670,7 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
     } else {
         CU(run_stage(Kl));
     }
-    const int nl = (stage == APDE_STAGE_INIT && Kl.use_apd) ? 2 : 1;  // two-phase init (see k_init)
+    const int nl = ((stage == APDE_STAGE_INIT && Kl.use_apd) || stage == APDE_STAGE_NEAREST_STRONG) ? 2 : 1;  // two-phase init (see k_init); tile summary + search
     c->launches += nl;
     c->stage_launches[stage] += nl;
     return APDE_OK;

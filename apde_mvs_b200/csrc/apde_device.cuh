@@ -46,6 +46,7 @@ struct PassK {
     float4 *fit;
     uint8_t *reliable;
     short2 *nearest;
+    uint16_t *ns_tiles;    // [ceil(H/8)][ceil(W/8)] nearest-strong pruning summary: 0 = no STRONG pixel in the 8x8 tile, else 1 + max confidence
     short2 *anchors;       // [P][9]
     const float *depth;    // [N+1][P] working-resolution depth maps, 0 = ref
     unsigned long long *counters;
