@@ -28,10 +28,11 @@ ALG_FLOP_PER_EVAL = 1340.0  # SURVEY.md 8(d) / BASELINE.md 2.4
 ALG_L1_BYTES_PER_EVAL = 720.0
 SAMPLES_PER_EVAL = 36.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-resolution k_prop_strong launch at the default workload
-# (1920x1080, 10 source views), from the `ncu --set full` capture summarised in profiles/r01_ncu_1080p_raw_summary.txt:
-# 188-205 MB read + 36-39 MB written.  The algorithmic minimum of that launch is ~115 MB (11 u8 images, plane / cost / mask
-# reads of the frame, writes of the half frame): the kernel is texture-pipe bound, not HBM bound.
-NCU_DRAM_BYTES_PROP_STRONG_1080P = 2.3e8
+# (1920x1080, 10 source views), from the `ncu --set full` capture summarised in
+# profiles/r01_ncu_full_prop_strong_compacted.md: 193-209 MB read + 55-61 MB written.  The algorithmic minimum of that
+# launch is ~115 MB (11 u8 images, plane / cost / mask reads of the frame, writes of the half frame): the kernel is bound by
+# the texture data pipe (88-89 % of its wavefront peak), not by HBM (0.7 % of DRAM throughput).
+NCU_DRAM_BYTES_PROP_STRONG_1080P = 2.6e8
 STAGE_NAMES = ["nearest_strong", "gen_anchors", "init", "prop_strong", "ransac_fit", "prop_weak", "depth_normal", "median",
                "depth_to_weak", "confidence", "local_refine"]
 
@@ -267,7 +268,7 @@ def run_ours(args, rank, world, local_rank):
         "unit": "Gsample/s" if frac_tex >= frac_fp32 else "TFLOP/s",
         "frac": max(frac_tex, frac_fp32),
         "traffic": NCU_DRAM_BYTES_PROP_STRONG_1080P if (args.width, args.height, args.src) == (1920, 1080, 10) else None,
-        "traffic_unit": "DRAM bytes per full-resolution launch (ncu --set full, profiles/r01_ncu_1080p_raw_summary.txt)",
+        "traffic_unit": "DRAM bytes per full-resolution launch (ncu --set full, profiles/r01_ncu_full_prop_strong_compacted.md)",
         "fp32": {"achieved_tflops": fp32_ach, "peak_tflops": fp32_peak, "frac": frac_fp32, "flop_per_eval": ALG_FLOP_PER_EVAL},
         "l1tex": {"achieved_gsamples": tex_ach, "peak_gsamples": tex_peak, "frac": frac_tex, "samples_per_eval": SAMPLES_PER_EVAL,
                   "achieved_GBps": tex_ach * ALG_L1_BYTES_PER_EVAL / SAMPLES_PER_EVAL},
