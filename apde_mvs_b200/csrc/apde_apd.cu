@@ -122,10 +122,22 @@ __device__ __forceinline__ int rand_shift(Rng &rng, int shift_range) {
     return (int)(((uint32_t)sgn * r) % (uint32_t)shift_range);
 }
 
+// The WEAK-only kernels below walk the compacted (colour, weak) pixel lists when the caller provides one (K.list): WEAK
+// pixels are a few per cent of the frame, and a full-grid launch would leave most lanes of most warps idle.
+__device__ __forceinline__ bool full_pixel_or_list(const PassK &K, int tiles_x, int &px, int &py) {
+    if (K.list == nullptr) return full_pixel(K, tiles_x, px, py);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= *K.list_count) return false;
+    const int center = K.list[idx];
+    px = center % K.W;
+    py = center / K.W;
+    return true;
+}
+
 // GenAnchors + NeigbourUpdate, APD.cu:1857-2100 (NeigbourUpdate only touches the pixel's own state, so it is fused)
 __global__ void __launch_bounds__(128) k_gen_anchors(const __grid_constant__ PassK K, int tiles_x) {
     int px, py;
-    if (!full_pixel(K, tiles_x, px, py)) return;
+    if (!full_pixel_or_list(K, tiles_x, px, py)) return;
     const int width = K.W, height = K.H;
     const int center = py * width + px;
     if (K.weak[center] != APDE_WEAK) return;
@@ -240,9 +252,16 @@ __global__ void __launch_bounds__(128) k_gen_anchors(const __grid_constant__ Pas
 
 // -------------------------------------------------------------------------------------------- K7 RANSAC fit
 // RANSACToGetFitPlane, APD.cu:2486-2598
+// fit = current plane for every pixel that is not WEAK (APD.cu:2497-2500): the streaming half of RANSACToGetFitPlane when the
+// WEAK pixels are processed from their lists
+__global__ void __launch_bounds__(256) k_fit_copy_nonweak(const __grid_constant__ PassK K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K.W * K.H && K.weak[i] != APDE_WEAK) K.fit[i] = K.planes[i];
+}
+
 __global__ void __launch_bounds__(128) k_ransac_fit(const __grid_constant__ PassK K, int iter, int tiles_x) {
     int px, py;
-    if (!full_pixel(K, tiles_x, px, py)) return;
+    if (!full_pixel_or_list(K, tiles_x, px, py)) return;
     const int width = K.W;
     const int center = py * width + px;
     if (K.weak[center] != APDE_WEAK) { K.fit[center] = K.planes[center]; return; }
@@ -456,16 +475,23 @@ cudaError_t launch_stage_apd(const PassK &K, int stage, int iter, int color, cud
     const int W = K.W, H = K.H, N = K.N;
     const int tiles8x = (W + 7) / 8;
     const int tiles_full = tiles8x * ((H + 3) / 4);
+    const int list_blocks = (W * min(H, half_rows_limit(H)) + 1) / 2 / 128 + 1;  // worst-case list length / 128
     switch (stage) {
         case APDE_STAGE_NEAREST_STRONG:
             k_ns_tiles<<<tiles8x * ((H + 7) / 8), 64, 0, st>>>(K, tiles8x);
             k_nearest_strong<<<(tiles_full + 3) / 4, 128, 0, st>>>(K, tiles8x);
             break;
         case APDE_STAGE_GEN_ANCHORS:
-            k_gen_anchors<<<(tiles_full + 3) / 4, 128, 0, st>>>(K, tiles8x);
+            if (K.list) k_gen_anchors<<<list_blocks, 128, 0, st>>>(K, tiles8x);
+            else k_gen_anchors<<<(tiles_full + 3) / 4, 128, 0, st>>>(K, tiles8x);
             break;
         case APDE_STAGE_RANSAC_FIT:
-            k_ransac_fit<<<(tiles_full + 3) / 4, 128, 0, st>>>(K, iter, tiles8x);
+            if (K.list) {
+                if (color == 0) k_fit_copy_nonweak<<<(W * H + 255) / 256, 256, 0, st>>>(K);
+                k_ransac_fit<<<list_blocks, 128, 0, st>>>(K, iter, tiles8x);
+            } else {
+                k_ransac_fit<<<(tiles_full + 3) / 4, 128, 0, st>>>(K, iter, tiles8x);
+            }
             break;
         case APDE_STAGE_PROP_WEAK: {
             const int ylimit = min(H, half_rows_limit(H));

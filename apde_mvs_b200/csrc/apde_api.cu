@@ -637,8 +637,29 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
         Kl.list = c->d_lists + (size_t)cls * c->list_cap;
         Kl.list_count = c->d_list_counts + cls;
     }
+    // WEAK-only full-frame stages (GenAnchors, RANSAC plane fit) walk the two (colour, weak) lists instead of the whole grid.
+    // The lists hold rows [0, half_rows_limit): only usable when that covers the frame (quirk 7 shapes fall back).
+    const bool weak_lists = (stage == APDE_STAGE_GEN_ANCHORS || stage == APDE_STAGE_RANSAC_FIT) && c->params.use_APD &&
+                            !getenv("APDE_QUAD_KERNELS") && !getenv("APDE_NO_WEAK_LISTS") && 32 * (((c->K.H / 2) + 15) / 16) >= c->K.H;
+    if (weak_lists && c->lists_dirty) {
+        CU(launch_build_lists(c->K, c->d_lists, c->d_list_counts, c->list_cap, c->stream));
+        c->launches++;
+        c->lists_dirty = false;
+    }
     auto run_stage = [&](const PassK &Kq) -> cudaError_t {
         static const bool legacy = [] { const char *e = getenv("APDE_LEGACY_SWEEP"); return e && e[0] == '1'; }();
+        if (weak_lists) {
+            for (int col = 0; col < 2; ++col) {
+                PassK Kw = Kq;
+                const int cls = (col << 1) | 1;
+                Kw.list = c->d_lists + (size_t)cls * c->list_cap;
+                Kw.list_count = c->d_list_counts + cls;
+                cudaError_t e = launch_stage(Kw, stage, iter, col, c->stream, nullptr);
+                if (e != cudaSuccess) return e;
+            }
+            c->launches += (stage == APDE_STAGE_RANSAC_FIT) ? 2 : 1;  // (+1 counted below)
+            return cudaSuccess;
+        }
         if (pipeline) {
             cudaError_t e = c->prop.reserve(c->list_cap, Kq.N);
             if (e != cudaSuccess) return e;
@@ -673,6 +694,7 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
     const int nl = ((stage == APDE_STAGE_INIT && Kl.use_apd) || stage == APDE_STAGE_NEAREST_STRONG) ? 2 : 1;  // two-phase init (see k_init); tile summary + search
     c->launches += nl;
     c->stage_launches[stage] += nl;
+    if (stage == APDE_STAGE_GEN_ANCHORS) c->lists_dirty = true;  // NeigbourUpdate turned unreliable WEAK pixels into UNKNOWN
     return APDE_OK;
 }
 
