@@ -32,6 +32,9 @@ struct PropK {  // device view of the workspace, passed by value
     uint8_t *nh;          // [cap] number of refinement hypotheses (0 / 5 / 11)
     float4 *hyp;          // [11][cap]
     float *refpatch;      // [38][cap] reference patch texels + mean + variance
+    float *anchorref;     // [88][cap] weak pixels: reference side of the 8 anchor patches (72 texels, 8 means, 8 variances)
+    int *anchor_xy;       // [8][cap]  anchor coordinates packed (x & 0xffff) | (y << 16); x == -1: empty slot
+    uint8_t *base3;       // [cap] weak pixels: first refinement slot after the fit-plane test (1 or 6)
     int *flags3, *colidx3, *colmap3;  // (pixel, selected view) columns: flags [N][cap], their prefix sum, column -> flat
     float *cost3;         // [11][N * cap]
 };
@@ -41,8 +44,9 @@ struct PropWorkspace {
     uint32_t *cand_flags = nullptr, *wmask = nullptr;
     float *cost1 = nullptr, *depth_now = nullptr, *cost_now = nullptr, *cost_written = nullptr, *wnorm = nullptr, *cost3 = nullptr;
     float4 *plane_now = nullptr, *hyp = nullptr;
-    float *refpatch = nullptr;
-    uint8_t *nh = nullptr;
+    float *refpatch = nullptr, *anchorref = nullptr;
+    int *anchor_xy = nullptr;
+    uint8_t *nh = nullptr, *base3 = nullptr;
     void *scan_tmp = nullptr;
     size_t scan_bytes = 0;
     cudaError_t reserve(int cap, int N);

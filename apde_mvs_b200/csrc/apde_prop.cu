@@ -69,6 +69,20 @@ __device__ __forceinline__ void k_prop_candidates_body(const PassK &K, const Pro
     for (int k = 0; k < kPatch; ++k) B.refpatch[(size_t)k * B.cap + pix] = rp.r[k];
     B.refpatch[(size_t)kPatch * B.cap + pix] = rp.mean;
     B.refpatch[(size_t)(kPatch + 1) * B.cap + pix] = rp.var;
+    if (WEAK) {
+        // the reference side of the anchor patches depends on the pixel only: gathered once here (72 texture fetches), re-loaded
+        // with coalesced LDGs by every (pixel, view) column of P1 and P3 instead of 72 fetches per column
+        AnchorRef ar;
+        load_anchor_ref<U>(K, K.anchors + (size_t)center * APDE_ANCHOR_NUM, ar);
+#pragma unroll
+        for (int k = 0; k < 72; ++k) B.anchorref[(size_t)k * B.cap + pix] = ar.r[k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            B.anchorref[(size_t)(72 + k) * B.cap + pix] = ar.mean[k];
+            B.anchorref[(size_t)(80 + k) * B.cap + pix] = ar.var[k];
+            B.anchor_xy[(size_t)k * B.cap + pix] = ((int)ar.a[k].x & 0xffff) | ((int)ar.a[k].y << 16);
+        }
+    }
 }
 template <bool WEAK>
 __global__ void __launch_bounds__(128) k_prop_candidates(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
@@ -84,6 +98,18 @@ __device__ __forceinline__ void load_ref_patch_g(const PropK &B, int pix, RefPat
     rp.var = B.refpatch[(size_t)(kPatch + 1) * B.cap + pix];
 }
 
+__device__ __forceinline__ void load_anchor_ref_g(const PropK &B, int pix, AnchorRef &ar) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int xy = B.anchor_xy[(size_t)k * B.cap + pix];
+        ar.a[k] = make_short2((short)(xy & 0xffff), (short)(xy >> 16));
+        ar.mean[k] = B.anchorref[(size_t)(72 + k) * B.cap + pix];
+        ar.var[k] = B.anchorref[(size_t)(80 + k) * B.cap + pix];
+    }
+#pragma unroll
+    for (int k = 0; k < 72; ++k) ar.r[k] = B.anchorref[(size_t)k * B.cap + pix];
+}
+
 // ------------------------------------------------------------------------------------------------ P1 phase-1 columns
 template <bool WEAK, bool U>
 __device__ __forceinline__ void k_prop_eval1_body(const PassK &K, const PropK &B) {
@@ -96,7 +122,7 @@ __device__ __forceinline__ void k_prop_eval1_body(const PassK &K, const PropK &B
     RefPatch rp;
     load_ref_patch_g(B, pix, rp);
     AnchorRef ar;
-    if (WEAK) load_anchor_ref<U>(K, K.anchors + (size_t)center * APDE_ANCHOR_NUM, ar);
+    if (WEAK) load_anchor_ref_g(B, pix, ar);
     const unsigned flags = B.cand_flags[pix] & 0xffu;
     unsigned n_eval = 0;
 #pragma unroll 1
@@ -337,8 +363,10 @@ __global__ void __launch_bounds__(256) k_prop_scatter(const int *__restrict__ fl
 }
 
 // ------------------------------------------------------------------------------------------------ P3 phase-3 columns
+// mode (weak only): 0 = all hypotheses in one launch (slot 8 duplicates slot 3 and is skipped); 1 = the fit plane only
+// (slot 0); 2 = the five random hypotheses that follow the outcome of the fit test (slots base3 .. base3 + 4)
 template <bool WEAK, bool U>
-__device__ __forceinline__ void k_prop_eval3_body(const PassK &K, const PropK &B) {
+__device__ __forceinline__ void k_prop_eval3_body(const PassK &K, const PropK &B, int mode) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -353,12 +381,15 @@ __device__ __forceinline__ void k_prop_eval3_body(const PassK &K, const PropK &B
     RefPatch rp;
     load_ref_patch_g(B, pix, rp);
     AnchorRef ar;
-    if (WEAK) load_anchor_ref<U>(K, K.anchors + (size_t)center * APDE_ANCHOR_NUM, ar);
+    if (WEAK) load_anchor_ref_g(B, pix, ar);
     const bool geom = WEAK ? (K.geom != 0) : (K.geom && K.impetus);
-    const int nh = WEAK ? 11 : 5;
+    int i0 = 0, nh = WEAK ? 11 : 5;
+    if (WEAK && mode == 1) nh = 1;
+    if (WEAK && mode == 2) { i0 = B.base3[pix]; nh = i0 + 5; }
     unsigned n_eval = 0, n_geom = 0;
 #pragma unroll 1
-    for (int i = 0; i < nh; ++i) {
+    for (int i = i0; i < nh; ++i) {
+        if (WEAK && mode == 0 && i == 8) continue;  // (random depth, random normal): the same plane as slot 3
         const float4 tp = B.hyp[(size_t)i * cap + pix];
         const float3 m = plane_row(K, tp);
         float c = WEAK ? ncc_new<U>(K, vk, v, px, py, m, rp, ar) : ncc_old<U>(K, vk, px, py, m, rp);
@@ -369,15 +400,36 @@ __device__ __forceinline__ void k_prop_eval3_body(const PassK &K, const PropK &B
     count_evals(K, WEAK ? 0 : n_eval, WEAK ? n_eval : 0, n_geom);
 }
 template <bool WEAK>
-__global__ void __launch_bounds__(128) k_prop_eval3(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
-    if (K.tex_unorm > 0.0f) k_prop_eval3_body<WEAK, true>(K, B);
-    else k_prop_eval3_body<WEAK, false>(K, B);
+__global__ void __launch_bounds__(128) k_prop_eval3(const __grid_constant__ PassK K, const __grid_constant__ PropK B, int mode) {
+    if (K.tex_unorm > 0.0f) k_prop_eval3_body<WEAK, true>(K, B, mode);
+    else k_prop_eval3_body<WEAK, false>(K, B, mode);
+}
+
+// weak pixels, between the two refinement rounds: does the fit plane get accepted (APD.cu:1046-1052)?  The answer selects
+// which set of five random hypotheses is evaluated; k_prop_final repeats the same test on the same numbers.
+__global__ void __launch_bounds__(128) k_prop_fit_test(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    int px, py, center;
+    if (!prop_pixel(K, B, pix, px, py, center)) return;
+    if (B.nh[pix] == 0) { B.base3[pix] = 1; return; }
+    const size_t cap = B.cap, nflat = (size_t)K.N * cap;
+    const uint32_t wmask = B.wmask[pix];
+    const uint4 w = K.vw[center];
+    float acc = 0.0f;
+    for (uint32_t mk = wmask; mk; mk &= mk - 1) {
+        const int v = __ffs(mk) - 1;
+        acc = __fmaf_rn((float)vw_get(w, v), B.cost3[B.colidx3[(size_t)v * cap + pix]], acc);  // == weighted(0) of k_prop_final
+    }
+    const float tc = __fdividef(acc, B.wnorm[pix]);
+    const float db = depth_from_plane(K, B.hyp[pix], px, py);
+    B.base3[pix] = (db >= K.depth_min && db <= K.depth_max && tc < B.cost_now[pix]) ? 6 : 1;
+    (void)nflat;
 }
 
 
 // ------------------------------------------------------------------------------------------------ P4 final decision
 template <bool WEAK>
-__global__ void __launch_bounds__(128) k_prop_final(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
+__global__ void __launch_bounds__(128) k_prop_final(const __grid_constant__ PassK K, const __grid_constant__ PropK B, int one_round) {
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     int px, py, center;
     if (!prop_pixel(K, B, pix, px, py, center)) return;
@@ -391,12 +443,13 @@ __global__ void __launch_bounds__(128) k_prop_final(const __grid_constant__ Pass
     const float dmin = K.depth_min, dmax = K.depth_max;
     const int nh = B.nh[pix];
     auto weighted = [&](int i) {
+        const int slot = (WEAK && one_round && i == 8) ? 3 : i;  // slot 8 is the same plane as slot 3 and is not evaluated twice
         float acc = 0.0f;
         for (uint32_t mk = wmask; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            acc += (float)vw_get(w, v) * B.cost3[(size_t)i * nflat + B.colidx3[(size_t)v * cap + pix]];
+            acc = __fmaf_rn((float)vw_get(w, v), B.cost3[(size_t)slot * nflat + B.colidx3[(size_t)v * cap + pix]], acc);
         }
-        return acc / wnorm;
+        return __fdividef(acc, wnorm);
     };
     auto try_hyp = [&](int i) {
         const float4 tp = B.hyp[(size_t)i * cap + pix];
@@ -441,6 +494,7 @@ cudaError_t PropWorkspace::reserve(int cap_, int N) {
     PCU(cudaMalloc(&nh, c));
     PCU(cudaMalloc(&hyp, 11 * c * sizeof(float4)));
     PCU(cudaMalloc(&refpatch, (size_t)(kPatch + 2) * c * sizeof(float)));
+    PCU(cudaMalloc(&base3, c));
     PCU(cudaMalloc(&flags3, (nflat + 1) * sizeof(int)));
     PCU(cudaMalloc(&colidx3, (nflat + 1) * sizeof(int)));
     PCU(cudaMalloc(&colmap3, nflat * sizeof(int)));
@@ -454,8 +508,8 @@ cudaError_t PropWorkspace::reserve(int cap_, int N) {
 void PropWorkspace::release() {
     cudaFree(cand_pos); cudaFree(cand_flags); cudaFree(cost1); cudaFree(plane_now); cudaFree(depth_now); cudaFree(cost_now);
     cudaFree(cost_written); cudaFree(wnorm); cudaFree(wmask); cudaFree(nh); cudaFree(hyp); cudaFree(flags3); cudaFree(colidx3);
-    cudaFree(colmap3); cudaFree(cost3); cudaFree(scan_tmp); cudaFree(refpatch);
-    refpatch = nullptr;
+    cudaFree(colmap3); cudaFree(cost3); cudaFree(scan_tmp); cudaFree(refpatch); cudaFree(anchorref); cudaFree(anchor_xy); cudaFree(base3);
+    refpatch = anchorref = nullptr; anchor_xy = nullptr; base3 = nullptr;
     cand_pos = flags3 = colidx3 = colmap3 = nullptr; cand_flags = wmask = nullptr; cost1 = depth_now = cost_now = cost_written = wnorm = cost3 = nullptr;
     plane_now = hyp = nullptr; nh = nullptr; scan_tmp = nullptr; cap = 0; views = 0;
 }
@@ -468,6 +522,11 @@ static cudaError_t run_half_sweep(const PassK &K, PropWorkspace &ws, const int *
     B.cand_pos = ws.cand_pos; B.cand_flags = ws.cand_flags; B.cost1 = ws.cost1; B.plane_now = ws.plane_now;
     B.depth_now = ws.depth_now; B.cost_now = ws.cost_now; B.cost_written = ws.cost_written; B.wnorm = ws.wnorm; B.wmask = ws.wmask;
     B.nh = ws.nh; B.hyp = ws.hyp; B.refpatch = ws.refpatch; B.flags3 = ws.flags3; B.colidx3 = ws.colidx3; B.colmap3 = ws.colmap3; B.cost3 = ws.cost3;
+    if (WEAK && !ws.anchorref) {  // only the weak class needs the anchor cache (384 B per list slot)
+        PCU(cudaMalloc(&ws.anchorref, (size_t)88 * ws.cap * sizeof(float)));
+        PCU(cudaMalloc(&ws.anchor_xy, (size_t)8 * ws.cap * sizeof(int)));
+    }
+    B.anchorref = ws.anchorref; B.anchor_xy = ws.anchor_xy; B.base3 = ws.base3;
     const int N = K.N;
     const size_t nflat = (size_t)N * ws.cap;
     const unsigned pb = (unsigned)((max_pixels + 127) / 128);
@@ -482,9 +541,21 @@ static cudaError_t run_half_sweep(const PassK &K, PropWorkspace &ws, const int *
     k_prop_scatter<<<(unsigned)((nflat + 255) / 256), 256, 0, st>>>(ws.flags3, ws.colidx3, nflat, ws.colmap3);
     // worst case: every (pixel, view) is a column; threads beyond the device-side count exit at once
     const size_t max_cols = (size_t)max_pixels * N;
-    k_prop_eval3<WEAK><<<(unsigned)((max_cols + 127) / 128), 128, vsm, st>>>(K, B);
-    k_prop_final<WEAK><<<pb, 128, 0, st>>>(K, B);
-    if (launches) *launches += 8;
+    const unsigned cb = (unsigned)((max_cols + 127) / 128);
+    const char *one = getenv("APDE_WEAK_ONE_ROUND");  // A/B switch: all 10 distinct hypotheses in one launch
+    const int one_round = (!WEAK || (one && one[0] == '1')) ? 1 : 0;
+    if (one_round) {
+        k_prop_eval3<WEAK><<<cb, 128, vsm, st>>>(K, B, 0);
+        if (launches) *launches += 8;
+    } else {
+        // the five random hypotheses of a weak pixel depend on whether its fit plane is accepted (APD.cu:1046-1067): evaluate
+        // the fit plane, decide, then evaluate only the set that applies -- 6 deformable evaluations per column instead of 10
+        k_prop_eval3<WEAK><<<cb, 128, vsm, st>>>(K, B, 1);
+        k_prop_fit_test<<<pb, 128, 0, st>>>(K, B);
+        k_prop_eval3<WEAK><<<cb, 128, vsm, st>>>(K, B, 2);
+        if (launches) *launches += 10;
+    }
+    k_prop_final<WEAK><<<pb, 128, 0, st>>>(K, B, one_round);
     return cudaGetLastError();
 }
 

@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--src", type=int, default=10)
     ap.add_argument("--rounds", type=int, default=0, help="0 = reference rule (ComputeRoundNum)")
     ap.add_argument("--geom-iters", type=int, default=3)
+    ap.add_argument("--weak", type=float, default=0.0, help="share of every surface covered by weak-texture blobs (C3-like workloads; 0 = headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fusion", action="store_true", help="skip the fusion report (outside the timed metric)")
     ap.add_argument("--ref-views", type=int, default=0, help="reference arm: reference views processed per step (0 = all)")
@@ -59,7 +60,7 @@ def parse_args():
 def build_scene(args, world):
     """base group of views_per_gpu views, replicated `world` times as independent groups (identical work per GPU)"""
     from apde_mvs_b200.scene import Scene, make_office_scene
-    cache = "/tmp/apde_bench_scene_%dx%d_%d_%d.npz" % (args.width, args.height, args.views_per_gpu, args.src)
+    cache = "/tmp/apde_bench_scene_%dx%d_%d_%d_%g.npz" % (args.width, args.height, args.views_per_gpu, args.src, args.weak)
     pre = None
     if os.path.exists(cache):
         try:
@@ -67,7 +68,7 @@ def build_scene(args, world):
             pre = list(zip(z["images"], z["gt"]))
         except Exception:
             pre = None
-    base = make_office_scene(args.width, args.height, args.views_per_gpu, args.src, seed=2, prerendered=pre)
+    base = make_office_scene(args.width, args.height, args.views_per_gpu, args.src, seed=2, weak=args.weak, prerendered=pre)
     if pre is None:
         try:
             np.savez(cache + ".tmp.npz", images=np.stack(base.images), gt=np.stack(base.gt_depth))
@@ -290,6 +291,7 @@ def run_ours(args, rank, world, local_rank):
                                "(rounds x (1 photometric + %d geometric))" % (vpg, args.width, args.height, args.src, npass, args.geom_iters),
                    "views_total": V, "passes_per_view": npass, "l2": "inputs larger than L2 (%.0f MB of images + maps per step)"
                    % (V * args.width * args.height * 26 / 1e6),
+                   "weak_texture_share": args.weak,
                    "ordering": "reference (Gauss-Seidel)" if world == 1 else "Jacobi + NCCL all-gather of depth maps per pass"},
         "cost_evals_per_s": evals_total / step_s, "cost_evals_per_step": evals_total / args.steps,
         "patchmatch_ms_per_view_pass": tm.patchmatch_ms / (args.steps * npass * vpg),
