@@ -10,7 +10,8 @@ ANCHOR_NUM = 9
 
 
 def lib_path():
-    return os.path.join(_HERE, "_build", "libapde.so")
+    # APDE_LIB: an alternative build of the same ABI (A/B comparisons of library versions, tools/ab_prev.sh)
+    return os.environ.get("APDE_LIB") or os.path.join(_HERE, "_build", "libapde.so")
 
 
 class ApdeError(RuntimeError):

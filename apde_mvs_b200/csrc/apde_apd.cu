@@ -127,8 +127,9 @@ __device__ __forceinline__ int rand_shift(Rng &rng, int shift_range) {
 __device__ __forceinline__ bool full_pixel_or_list(const PassK &K, int tiles_x, int &px, int &py) {
     if (K.list == nullptr) return full_pixel(K, tiles_x, px, py);
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= *K.list_count) return false;
-    const int center = K.list[idx];
+    const int *lst = K.list + (size_t)blockIdx.y * K.list_pair_stride;
+    if (idx >= K.list_count[2 * blockIdx.y]) return false;
+    const int center = lst[idx];
     px = center % K.W;
     py = center / K.W;
     return true;
@@ -475,20 +476,21 @@ cudaError_t launch_stage_apd(const PassK &K, int stage, int iter, int color, cud
     const int W = K.W, H = K.H, N = K.N;
     const int tiles8x = (W + 7) / 8;
     const int tiles_full = tiles8x * ((H + 3) / 4);
-    const int list_blocks = (W * min(H, half_rows_limit(H)) + 1) / 2 / 128 + 1;  // worst-case list length / 128
+    // list launches: color carries the host-side length of the longer of the two weak lists; blockIdx.y = colour
+    const dim3 list_grid((unsigned)((max(color, 1) + 127) / 128), 2);
     switch (stage) {
         case APDE_STAGE_NEAREST_STRONG:
             k_ns_tiles<<<tiles8x * ((H + 7) / 8), 64, 0, st>>>(K, tiles8x);
             k_nearest_strong<<<(tiles_full + 3) / 4, 128, 0, st>>>(K, tiles8x);
             break;
         case APDE_STAGE_GEN_ANCHORS:
-            if (K.list) k_gen_anchors<<<list_blocks, 128, 0, st>>>(K, tiles8x);
+            if (K.list) k_gen_anchors<<<list_grid, 128, 0, st>>>(K, tiles8x);
             else k_gen_anchors<<<(tiles_full + 3) / 4, 128, 0, st>>>(K, tiles8x);
             break;
         case APDE_STAGE_RANSAC_FIT:
             if (K.list) {
-                if (color == 0) k_fit_copy_nonweak<<<(W * H + 255) / 256, 256, 0, st>>>(K);
-                k_ransac_fit<<<list_blocks, 128, 0, st>>>(K, iter, tiles8x);
+                k_fit_copy_nonweak<<<(W * H + 255) / 256, 256, 0, st>>>(K);
+                k_ransac_fit<<<list_grid, 128, 0, st>>>(K, iter, tiles8x);
             } else {
                 k_ransac_fit<<<(tiles_full + 3) / 4, 128, 0, st>>>(K, iter, tiles8x);
             }

@@ -93,6 +93,7 @@ struct apde_context {
     uint16_t *d_ns_tiles = nullptr;
     int *d_lists = nullptr, *d_list_counts = nullptr;  // compacted checkerboard pixel lists (4 x list_cap)
     int list_cap = 0;
+    int h_list_counts[4] = {0, 0, 0, 0};  // host copy of the list lengths: sizes (or skips) the list-driven launches
     bool lists_dirty = true;
     unsigned long long *d_counters = nullptr;  // [kStages + 1][4]: per-stage NCC-Old / NCC-New / geom evaluation counts
     uint64_t launches = 0;
@@ -612,6 +613,18 @@ int apde_problem_dims(apde_context *c, int *width, int *height, int *num_images)
     return APDE_OK;
 }
 
+// (re)build the four (colour, class) pixel lists and fetch their lengths.  The 16-byte read-back costs one stream sync per
+// build (twice per pass), and saves launching worst-case grids for the sparse WEAK class: the column pipeline of a weak
+// half-sweep is ~10 launches over [N][capacity] arrays, ~1 ms each time even when the frame holds no WEAK pixel at all.
+static int build_lists(apde_context *c) {
+    CU(launch_build_lists(c->K, c->d_lists, c->d_list_counts, c->list_cap, c->stream));
+    CU(cudaMemcpyAsync(c->h_list_counts, c->d_list_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->launches++;
+    c->lists_dirty = false;
+    return APDE_OK;
+}
+
 int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
     if (!c || !c->problem_active) return fail(APDE_ERR_STATE, "problem_stage: no active problem");
     if (stage < 0 || stage >= kStages) return fail(APDE_ERR_ARG, "problem_stage: unknown stage %d", stage);
@@ -628,11 +641,7 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
     const bool pipeline = prop_stage && !legacy_prop && !getenv("APDE_QUAD_KERNELS") && (stage == APDE_STAGE_PROP_WEAK || pipe_strong);
     if (prop_stage && (c->params.use_APD || pipeline)) {
         // compacted (colour, class) pixel lists: no lane idles on the other class, and the column kernels index by list slot
-        if (c->lists_dirty) {
-            CU(launch_build_lists(c->K, c->d_lists, c->d_list_counts, c->list_cap, c->stream));
-            c->launches++;
-            c->lists_dirty = false;
-        }
+        if (c->lists_dirty) { const int rc = build_lists(c); if (rc) return rc; }
         const int cls = (color << 1) | (stage == APDE_STAGE_PROP_WEAK ? 1 : 0);
         Kl.list = c->d_lists + (size_t)cls * c->list_cap;
         Kl.list_count = c->d_list_counts + cls;
@@ -641,31 +650,26 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
     // The lists hold rows [0, half_rows_limit): only usable when that covers the frame (quirk 7 shapes fall back).
     const bool weak_lists = (stage == APDE_STAGE_GEN_ANCHORS || stage == APDE_STAGE_RANSAC_FIT) && c->params.use_APD &&
                             !getenv("APDE_QUAD_KERNELS") && !getenv("APDE_NO_WEAK_LISTS") && 32 * (((c->K.H / 2) + 15) / 16) >= c->K.H;
-    if (weak_lists && c->lists_dirty) {
-        CU(launch_build_lists(c->K, c->d_lists, c->d_list_counts, c->list_cap, c->stream));
-        c->launches++;
-        c->lists_dirty = false;
-    }
+    if (weak_lists && c->lists_dirty) { const int rc = build_lists(c); if (rc) return rc; }
     auto run_stage = [&](const PassK &Kq) -> cudaError_t {
         static const bool legacy = [] { const char *e = getenv("APDE_LEGACY_SWEEP"); return e && e[0] == '1'; }();
         if (weak_lists) {
-            for (int col = 0; col < 2; ++col) {
-                PassK Kw = Kq;
-                const int cls = (col << 1) | 1;
-                Kw.list = c->d_lists + (size_t)cls * c->list_cap;
-                Kw.list_count = c->d_list_counts + cls;
-                cudaError_t e = launch_stage(Kw, stage, iter, col, c->stream, nullptr);
-                if (e != cudaSuccess) return e;
-            }
-            c->launches += (stage == APDE_STAGE_RANSAC_FIT) ? 2 : 1;  // (+1 counted below)
-            return cudaSuccess;
+            // both weak lists (black = class 1, red = class 3) in ONE launch, blockIdx.y = colour: the few long-running threads
+            // of a sparse class overlap instead of serialising two launch tails
+            PassK Kw = Kq;
+            Kw.list = c->d_lists + (size_t)1 * c->list_cap;
+            Kw.list_count = c->d_list_counts + 1;
+            Kw.list_pair_stride = 2 * c->list_cap;
+            const int longest = std::max(c->h_list_counts[1], c->h_list_counts[3]);
+            if (longest == 0 && stage == APDE_STAGE_GEN_ANCHORS) return cudaSuccess;  // no WEAK pixel: nothing to do
+            if (stage == APDE_STAGE_RANSAC_FIT) c->launches += 1;  // fit copy + fit (+1 counted below)
+            return launch_stage(Kw, stage, iter, longest, c->stream, nullptr);  // `color` carries the list length here
         }
         if (pipeline) {
             cudaError_t e = c->prop.reserve(c->list_cap, Kq.N);
             if (e != cudaSuccess) return e;
-            const int ylimit = std::min(Kq.H, 32 * (((Kq.H / 2) + 15) / 16));
-            const int max_pixels = (Kq.W * ylimit + 1) / 2 + 1;
-            return prop_half_sweep(Kq, c->prop, stage == APDE_STAGE_PROP_WEAK, Kq.list, Kq.list_count, max_pixels, iter, c->stream,
+            const int cls = (color << 1) | (stage == APDE_STAGE_PROP_WEAK ? 1 : 0);
+            return prop_half_sweep(Kq, c->prop, stage == APDE_STAGE_PROP_WEAK, Kq.list, Kq.list_count, c->h_list_counts[cls], iter, c->stream,
                                    &c->launches);
         }
         if (!legacy && !getenv("APDE_QUAD_KERNELS")) {

@@ -53,6 +53,7 @@ struct PassK {
     // compacted pixel lists of the checkerboard kernels (rounds with WEAK pixels): [colour][strong | weak], see k_build_lists
     const int *list;  // nullptr: implicit 8x8-tile mapping
     const int *list_count;
+    int list_pair_stride;  // > 0: blockIdx.y = colour selects list + y * stride, count[2 * y] (both weak lists in one launch)
     ViewK v[kMaxSrc];
 };
 

@@ -517,18 +517,22 @@ void PropWorkspace::release() {
 template <bool WEAK>
 static cudaError_t run_half_sweep(const PassK &K, PropWorkspace &ws, const int *list, const int *count, int max_pixels, int iter,
                                   cudaStream_t st, uint64_t *launches) {
+    if (max_pixels <= 0) return cudaSuccess;  // empty class: no launches at all
     PropK B;
-    B.list = list; B.count = count; B.cap = ws.cap;
+    // row stride of every per-pixel array = the list length rounded up, not the capacity: the [N][stride] flag / scan / scatter
+    // passes then touch what the half-sweep really holds
+    B.list = list; B.count = count; B.cap = std::min(ws.cap, (max_pixels + 127) / 128 * 128);
     B.cand_pos = ws.cand_pos; B.cand_flags = ws.cand_flags; B.cost1 = ws.cost1; B.plane_now = ws.plane_now;
     B.depth_now = ws.depth_now; B.cost_now = ws.cost_now; B.cost_written = ws.cost_written; B.wnorm = ws.wnorm; B.wmask = ws.wmask;
     B.nh = ws.nh; B.hyp = ws.hyp; B.refpatch = ws.refpatch; B.flags3 = ws.flags3; B.colidx3 = ws.colidx3; B.colmap3 = ws.colmap3; B.cost3 = ws.cost3;
     if (WEAK && !ws.anchorref) {  // only the weak class needs the anchor cache (384 B per list slot)
         PCU(cudaMalloc(&ws.anchorref, (size_t)88 * ws.cap * sizeof(float)));
         PCU(cudaMalloc(&ws.anchor_xy, (size_t)8 * ws.cap * sizeof(int)));
+        (void)max_pixels;
     }
     B.anchorref = ws.anchorref; B.anchor_xy = ws.anchor_xy; B.base3 = ws.base3;
     const int N = K.N;
-    const size_t nflat = (size_t)N * ws.cap;
+    const size_t nflat = (size_t)N * B.cap;
     const unsigned pb = (unsigned)((max_pixels + 127) / 128);
     const size_t vsm = sizeof(float) * views_smem_floats(N);
     if (pb == 0) return cudaSuccess;
