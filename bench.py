@@ -319,6 +319,7 @@ def fusion_report(args, ctx, scene, cpu=True):
     from apde_mvs_b200.binding import Context
     from apde_mvs_b200.scene import Scene
     V = len(scene.images)
+    ctx.fuse(True)  # warm-up: the first call allocates the skip / claim / candidate buffers
     t0 = time.perf_counter()
     xyz, _ = ctx.fuse(True)
     rep = {"gpu_ms_scene": (time.perf_counter() - t0) * 1e3, "points_scene": int(len(xyz)), "views_scene": V}
