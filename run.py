@@ -4,8 +4,9 @@
     python run.py --data_dir <root> --scans scan1 scan2 --gpu_num 8 --work_num 1 [--only_fuse] [--no_fuse] ...
 
 One `apd` process per scan, pinned to a GPU slot exactly like the reference's worker table (run.py:72-82, 104-138).
-Differences: --no_sam is implied (the SAM plug-in is out of scope, tools/run_SAM.py is never imported), the image layout
-helpers of scripts/dataset_loader.py are reduced to "images/ must exist", and --APD_path defaults to the in-tree build.
+Differences: --no_sam is implied (the SAM plug-in is out of scope, tools/run_SAM.py is never imported) and --APD_path
+defaults to the in-tree build.  The image-layout helper (scripts/dataset_loader.py:54-140: first existing candidate
+directory, symlinked to <scan>/images) is restated in resolve_images_dir().
 """
 import argparse
 import multiprocessing as mp
@@ -40,7 +41,56 @@ def parse_args(argv=None):
     p.add_argument('--export_anchor', action='store_true', default=False)
     p.add_argument('--export_curve', action='store_true', default=False)
     p.add_argument('--review', action='store_true', default=False)
+    p.add_argument('--reservation', type=str, default=None, help='sleep before starting, e.g. 3h30m10s (run.py:167-170)')
+    p.add_argument('--backup_code', action='store_true', default=False, help='copy the sources next to the results (run.py:139)')
+    p.add_argument('--image_dir_name', type=str, nargs='+', default=['images', 'undist/images'],
+                   help='candidate image directories below the scan folder, first hit wins')
+    p.add_argument('--image_suffixes', type=str, nargs='+', default=['.jpg', '.jpeg', '.png'],
+                   help='image file extensions that count (with or without the dot, any case)')
+    p.add_argument('--no_image_symlink', action='store_true', default=False,
+                   help='do not symlink the resolved candidate to <scan>/images')
     return p.parse_args(argv)
+
+
+def resolve_images_dir(scan_dir, candidates, create_symlink=True):
+    """scripts/dataset_loader.py:75-140: the first existing candidate is the source; <scan>/images is what the binary reads, so
+    a different source is symlinked there unless told otherwise.  Returns the directory to count images in."""
+    source = None
+    for cand in candidates:
+        path = os.path.join(scan_dir, *[x for x in cand.replace('\\', '/').split('/') if x])
+        if os.path.isdir(path):
+            source = path
+            break
+    if source is None:
+        raise FileNotFoundError('no image directory among %s below %s' % (candidates, scan_dir))
+    canonical = os.path.join(scan_dir, 'images')
+    if os.path.isdir(canonical):
+        return canonical
+    if os.path.exists(canonical):
+        raise FileExistsError('%s exists but is not a directory' % canonical)
+    if not create_symlink:
+        return source
+    os.symlink(os.path.relpath(source, scan_dir), canonical)
+    return canonical
+
+
+def count_images(image_dir, suffixes):
+    sfx = tuple(('.' + x.lstrip('.')).lower() for x in suffixes)
+    return sum(1 for f in os.listdir(image_dir) if f.lower().endswith(sfx))
+
+
+def parse_reservation(text):
+    """'3h30m10s' -> seconds (the reference hands the string to sleep(1))"""
+    import re
+    total, pos = 0.0, 0
+    for m in re.finditer(r'(\d+(?:\.\d+)?)([smhd]?)', text):
+        if m.start() != pos or not m.group(0):
+            break
+        total += float(m.group(1)) * {'': 1, 's': 1, 'm': 60, 'h': 3600, 'd': 86400}[m.group(2)]
+        pos = m.end()
+    if pos != len(text):
+        raise ValueError('bad reservation %r' % text)
+    return total
 
 
 def dataset_tag(data_dir, scan):
@@ -69,8 +119,13 @@ def _init(pp, ll, aa):
 
 def worker(scan):
     scan_dir = os.path.join(args.data_dir, scan)
+    try:
+        resolve_images_dir(scan_dir, args.image_dir_name, not args.no_image_symlink)
+    except (FileNotFoundError, FileExistsError) as exc:
+        print('[{}] cannot prepare the image directory: {}'.format(scan, exc))
+        return 1
     if not os.path.isdir(os.path.join(scan_dir, 'images')):
-        print('{} has no images/ folder'.format(scan_dir))
+        print('{} has no images/ folder (and --no_image_symlink was given)'.format(scan_dir))
         return 1
     with lock:
         pos_index = 0
@@ -100,12 +155,38 @@ def worker(scan):
 
 def main(argv=None):
     a = parse_args(argv)
+    if a.reservation is not None:
+        import time
+        print('sleep for reservation: {}'.format(a.reservation))
+        time.sleep(parse_reservation(a.reservation))
     scans = a.scans or sorted(d for d in os.listdir(a.data_dir) if os.path.isdir(os.path.join(a.data_dir, d)))
-    # most images first, like run.py:214
-    def nimg(s):
-        d = os.path.join(a.data_dir, s, 'images')
-        return len(os.listdir(d)) if os.path.isdir(d) else 0
-    scans.sort(key=nimg, reverse=True)
+    if a.backup_code and not (a.review or a.dry_run):
+        import shutil
+        import time
+        dst = os.path.join(a.data_dir, 'code_backup_' + time.strftime('%Y%m%d_%H%M%S'))
+        os.makedirs(dst, exist_ok=True)
+        for item in ('run.py', 'include', 'apde_mvs_b200'):
+            src = os.path.join(ROOT, item)
+            if os.path.isdir(src):
+                shutil.copytree(src, os.path.join(dst, item), ignore=shutil.ignore_patterns('_build', '__pycache__', '*.so', '*.o'))
+            else:
+                shutil.copy(src, dst)
+    # scans whose images cannot be found are skipped; most images first, like run.py:186-214
+    counted = []
+    for s in scans:
+        scan_dir = os.path.join(a.data_dir, s)
+        if not os.path.isdir(scan_dir):
+            print('{} is not a dir'.format(scan_dir))
+            continue
+        try:
+            counted.append((count_images(resolve_images_dir(scan_dir, a.image_dir_name, not a.no_image_symlink), a.image_suffixes), s))
+        except (FileNotFoundError, FileExistsError) as exc:
+            print('skipping {}: {}'.format(scan_dir, exc))
+    if not counted:
+        print('No valid scans found.')
+        return 0
+    counted.sort(key=lambda x: -x[0])
+    scans = [s for _, s in counted]
     total = a.gpu_num * a.work_num
     positions = mp.Array('i', [0] * total)
     lock = mp.Lock()
