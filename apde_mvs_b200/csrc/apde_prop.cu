@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(128) k_prop_fit_test(const __grid_constant__ P
     int px, py, center;
     if (!prop_pixel(K, B, pix, px, py, center)) return;
     if (B.nh[pix] == 0) { B.base3[pix] = 1; return; }
-    const size_t cap = B.cap, nflat = (size_t)K.N * cap;
+    const size_t cap = B.cap;
     const uint32_t wmask = B.wmask[pix];
     const uint4 w = K.vw[center];
     float acc = 0.0f;
@@ -423,7 +423,6 @@ __global__ void __launch_bounds__(128) k_prop_fit_test(const __grid_constant__ P
     const float tc = __fdividef(acc, B.wnorm[pix]);
     const float db = depth_from_plane(K, B.hyp[pix], px, py);
     B.base3[pix] = (db >= K.depth_min && db <= K.depth_max && tc < B.cost_now[pix]) ? 6 : 1;
-    (void)nflat;
 }
 
 
@@ -528,7 +527,6 @@ static cudaError_t run_half_sweep(const PassK &K, PropWorkspace &ws, const int *
     if (WEAK && !ws.anchorref) {  // only the weak class needs the anchor cache (384 B per list slot)
         PCU(cudaMalloc(&ws.anchorref, (size_t)88 * ws.cap * sizeof(float)));
         PCU(cudaMalloc(&ws.anchor_xy, (size_t)8 * ws.cap * sizeof(int)));
-        (void)max_pixels;
     }
     B.anchorref = ws.anchorref; B.anchor_xy = ws.anchor_xy; B.base3 = ws.base3;
     const int N = K.N;
