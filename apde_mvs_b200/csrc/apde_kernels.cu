@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(128) k_prop_strong_v1(const __grid_constant__ 
     else k_prop_strong_body<false>(K, iter, color, tiles_x, ylimit);
 }
 
-// The same half-sweep with the refinement evaluations WARP-COMPACTED.
+// The same half-sweep with the phase-3 evaluations (current hypothesis, then the five refinement hypotheses) WARP-COMPACTED.
 //
 // In the kernel above every lane walks its OWN selected views in phase 3: at one instant the 32 lanes of a warp sample up
 // to N different source views (different layers of the texture array -> no cache locality) and the warp runs as long as
@@ -265,11 +265,14 @@ __device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int i
     unsigned n_old = 0, n_geom = 0;
     uint32_t wmask = 0;
     uint4 w = make_uint4(0, 0, 0, 0);
-    float wnorm = 1.0f, cost_now = 0.0f, cost_written = 0.0f, depth_now = 0.0f;
-    float4 plane_now = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wnorm = 1.0f, cost_now = 0.0f, cost_written = 0.0f, depth_now = 0.0f, fc_min = 0.0f;
+    float4 plane_now = make_float4(0.f, 0.f, 0.f, 0.f), plane_c = plane_now;
+    int cand_center = -1;  // pixel whose plane won the candidate vote (-1: the winner was an invalid slot, quirk 2)
     const bool use_geom = K.geom && K.impetus;
     const float dmin = K.depth_min, dmax = K.depth_max;
+    Rng rng(K.seed, K.stream, (uint32_t)center, SITE_STRONG + iter);
 
+    // ---- phase 1 + 2 (owner lane): 8 candidates x N views, joint view selection, candidate vote
     if (active) {
         RefPatch rp;
         load_ref_patch<U>(K, px, py, rp);
@@ -295,7 +298,6 @@ __device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int i
         nbr_sel[2] = (nbr_valid & 4u) ? K.sel[center - 1] : 0u;
         nbr_sel[3] = (nbr_valid & 8u) ? K.sel[center + 1] : 0u;
 
-        Rng rng(K.seed, K.stream, (uint32_t)center, SITE_STRONG + iter);
         w = select_views<4>(K, sc, sp, stride, nbr_sel, nbr_valid, iter, rng, &wmask, &wnorm);
         K.vw[center] = w;
 
@@ -315,29 +317,80 @@ __device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int i
 #pragma unroll
             for (int h = 1; h < 8; ++h) if (final_costs[h] <= mc) { mc = final_costs[h]; min_idx = h; }  // ties -> last (quirk 3)
         }
-        float fc_min = final_costs[0];
+        fc_min = final_costs[0];
 #pragma unroll
         for (int h = 1; h < 8; ++h) if (h == min_idx) fc_min = final_costs[h];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) if (h == min_idx && ((flags >> h) & 1u)) cand_center = pos[h];
 
-        const float4 plane_c = K.planes[center];
-        plane_now = plane_c;
-        // current hypothesis on the selected views (one evaluation per pair: stays with the owner lane)
-        {
-            const float3 m = plane_row(K, plane_c);
-            float acc = 0.0f;
-            for (uint32_t mk = wmask; mk; mk &= mk - 1) {
-                const int v = __ffs(mk) - 1;
-                float c = ncc_old<U>(K, s_vk[v], px, py, m, rp);
-                n_old++;
-                if (use_geom) { c = __fmaf_rn(K.geom_factor, geom_cost(K, s_vk[v], v, px, py, plane_c), c); n_geom++; }
-                acc += (float)vw_get(w, v) * c;
+        plane_c = K.planes[center];
+        // park the reference patch and the current plane in this thread's column (the phase-1 costs are dead now)
+#pragma unroll
+        for (int k = 0; k < kPatch; ++k) sc[(kStrongRefSlot + k) * stride] = rp.r[k];
+        sc[(kStrongRefSlot + kPatch) * stride] = rp.mean;
+        sc[(kStrongRefSlot + kPatch + 1) * stride] = rp.var;
+        sc[(kStrongPlaneSlot + 0) * stride] = plane_c.x;
+        sc[(kStrongPlaneSlot + 1) * stride] = plane_c.y;
+        sc[(kStrongPlaneSlot + 2) * stride] = plane_c.z;
+        sc[(kStrongPlaneSlot + 3) * stride] = plane_c.w;
+    }
+    __syncwarp();
+
+    // ---- (pixel, selected view) pairs of this warp, view-major
+    int total = 0;
+    for (int v = 0; v < N; ++v) {
+        const unsigned m = __ballot_sync(0xffffffffu, active && ((wmask >> v) & 1u));
+        if (active && ((wmask >> v) & 1u)) items[total + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(lane | (v << 8));
+        total += __popc(m);
+    }
+    __syncwarp();
+    const int pxy = (px << 16) | py;
+    // every pair evaluates the nh planes parked in plane slots 0 .. nh-1 of its owner's column and leaves the costs in cost slot [i][v]
+    auto evaluate_pairs = [&](int nh) {
+#pragma unroll 1
+        for (int base = 0; base < total; base += 32) {
+            const bool has = base + lane < total;
+            const unsigned short it = has ? items[base + lane] : (unsigned short)0;
+            const int src = it & 31, v = it >> 8;
+            const int sxy = __shfl_sync(0xffffffffu, pxy, src);
+            if (has) {
+                const int spx = sxy >> 16, spy = sxy & 0xffff;
+                float *scol = col0 + (warp * 32 + src);
+                RefPatch rp;
+#pragma unroll
+                for (int k = 0; k < kPatch; ++k) rp.r[k] = scol[(kStrongRefSlot + k) * stride];
+                rp.mean = scol[(kStrongRefSlot + kPatch) * stride];
+                rp.var = scol[(kStrongRefSlot + kPatch + 1) * stride];
+                const ViewK &vk = s_vk[v];
+#pragma unroll 1
+                for (int i = 0; i < nh; ++i) {
+                    const float4 tp = make_float4(scol[(kStrongPlaneSlot + 4 * i + 0) * stride], scol[(kStrongPlaneSlot + 4 * i + 1) * stride],
+                                                  scol[(kStrongPlaneSlot + 4 * i + 2) * stride], scol[(kStrongPlaneSlot + 4 * i + 3) * stride]);
+                    const float3 m = plane_row(K, tp);
+                    float c = ncc_old<U>(K, vk, spx, spy, m, rp);
+                    n_old++;
+                    if (use_geom) { c = __fmaf_rn(K.geom_factor, geom_cost(K, vk, v, spx, spy, tp), c); n_geom++; }
+                    scol[(kStrongCostSlot + i * N + v) * stride] = c;
+                }
             }
-            cost_now = acc / wnorm;
         }
+        __syncwarp();
+    };
+
+    // ---- the current hypothesis on the selected views
+    evaluate_pairs(1);
+    if (active) {
+        float acc = 0.0f;
+        for (uint32_t mk = wmask; mk; mk &= mk - 1) {
+            const int v = __ffs(mk) - 1;
+            acc += (float)vw_get(w, v) * sc[(kStrongCostSlot + v) * stride];
+        }
+        cost_now = acc / wnorm;
         cost_written = cost_now;
+        plane_now = plane_c;
         depth_now = depth_from_plane(K, plane_c, px, py);
-        if ((flags >> min_idx) & 1u) {
-            const float4 cand = K.planes[pos[min_idx]];
+        if (cand_center >= 0) {
+            const float4 cand = K.planes[cand_center];
             const float db = depth_from_plane(K, cand, px, py);
             if (db >= dmin && db <= dmax && fc_min < cost_now) {
                 depth_now = db; plane_now = cand; cost_now = fc_min;
@@ -351,11 +404,6 @@ __device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int i
         const float lo = (1.0f - 0.02f) * depth_now, hi = (1.0f + 0.02f) * depth_now;
         const float depth_pert = rng.uniform() * (hi - lo) + lo;  // the do-while can never repeat (quirk 6)
         cand_n[1] = perturbed_normal(K, px, py, plane_now, rng, (float)(0.02 * 3.14159265358979323846));
-        // park the reference patch and the five hypotheses in this thread's column (phase-1 costs are dead now)
-#pragma unroll
-        for (int k = 0; k < kPatch; ++k) sc[(kStrongRefSlot + k) * stride] = rp.r[k];
-        sc[(kStrongRefSlot + kPatch) * stride] = rp.mean;
-        sc[(kStrongRefSlot + kPatch + 1) * stride] = rp.var;
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
             float4 tp = (i == 0 || i == 4) ? plane_now : (i == 3 ? cand_n[1] : cand_n[0]);
@@ -369,44 +417,8 @@ __device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int i
     }
     __syncwarp();
 
-    // (pixel, selected view) pairs of this warp, view-major
-    int total = 0;
-    for (int v = 0; v < N; ++v) {
-        const unsigned m = __ballot_sync(0xffffffffu, active && ((wmask >> v) & 1u));
-        if (active && ((wmask >> v) & 1u)) items[total + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(lane | (v << 8));
-        total += __popc(m);
-    }
-    __syncwarp();
-    const int pxy = (px << 16) | py;
-#pragma unroll 1
-    for (int base = 0; base < total; base += 32) {
-        const bool has = base + lane < total;
-        const unsigned short it = has ? items[base + lane] : (unsigned short)0;
-        const int src = it & 31, v = it >> 8;
-        const int sxy = __shfl_sync(0xffffffffu, pxy, src);
-        if (has) {
-            const int spx = sxy >> 16, spy = sxy & 0xffff;
-            const float *scol = col0 + (warp * 32 + src);
-            RefPatch rp;
-#pragma unroll
-            for (int k = 0; k < kPatch; ++k) rp.r[k] = scol[(kStrongRefSlot + k) * stride];
-            rp.mean = scol[(kStrongRefSlot + kPatch) * stride];
-            rp.var = scol[(kStrongRefSlot + kPatch + 1) * stride];
-            const ViewK &vk = s_vk[v];
-#pragma unroll 1
-            for (int i = 0; i < 5; ++i) {
-                const float4 tp = make_float4(scol[(kStrongPlaneSlot + 4 * i + 0) * stride], scol[(kStrongPlaneSlot + 4 * i + 1) * stride],
-                                              scol[(kStrongPlaneSlot + 4 * i + 2) * stride], scol[(kStrongPlaneSlot + 4 * i + 3) * stride]);
-                const float3 m = plane_row(K, tp);
-                float c = ncc_old<U>(K, vk, spx, spy, m, rp);
-                n_old++;
-                if (use_geom) { c = __fmaf_rn(K.geom_factor, geom_cost(K, vk, v, spx, spy, tp), c); n_geom++; }
-                const_cast<float *>(scol)[(kStrongCostSlot + i * N + v) * stride] = c;
-            }
-        }
-    }
-    __syncwarp();
-
+    // ---- the five refinement hypotheses
+    evaluate_pairs(5);
     if (active) {
 #pragma unroll 1
         for (int i = 0; i < 5; ++i) {
