@@ -33,6 +33,11 @@ SAMPLES_PER_EVAL = 36.0
 # launch is ~115 MB (11 u8 images, plane / cost / mask reads of the frame, writes of the half frame): the kernel is bound by
 # the texture data pipe (88-89 % of its wavefront peak), not by HBM (0.7 % of DRAM throughput).
 NCU_DRAM_BYTES_PROP_STRONG_1080P = 2.6e8
+# k_sweep_columns (DepthToWeak), same workload, profiles/r01_ncu_1080p_raw_summary.txt: 0.56 GB read + 2.99 GB written per
+# full-resolution launch -- the [62][columns] cost arrays (algorithmic: columns x 62 x 4 B x 2 with the geometric term).
+NCU_DRAM_BYTES_SWEEP_COLUMNS_1080P = 3.55e9
+NCU_TRAFFIC = {"prop_strong": (NCU_DRAM_BYTES_PROP_STRONG_1080P, "k_prop_strong", "profiles/r01_ncu_full_prop_strong_compacted.md"),
+               "depth_to_weak": (NCU_DRAM_BYTES_SWEEP_COLUMNS_1080P, "k_sweep_columns", "profiles/r01_ncu_1080p_raw_summary.txt")}
 STAGE_NAMES = ["nearest_strong", "gen_anchors", "init", "prop_strong", "ransac_fit", "prop_weak", "depth_normal", "median",
                "depth_to_weak", "confidence", "local_refine"]
 
@@ -262,14 +267,15 @@ def run_ours(args, rank, world, local_rank):
     tex_ach = k_ev_per_launch * SAMPLES_PER_EVAL / (k_ms * 1e-3) / 1e9
     frac_fp32, frac_tex = fp32_ach / fp32_peak, tex_ach / tex_peak
     roofline = {
-        "kernel": "k_" + STAGE_NAMES[k], "share_of_step": float(st_ms[k] / st_ms.sum()),
+        "kernel": NCU_TRAFFIC.get(STAGE_NAMES[k], (None, "k_" + STAGE_NAMES[k], ""))[1], "stage": STAGE_NAMES[k],
+        "share_of_step": float(st_ms[k] / st_ms.sum()),
         "bound": "l1tex" if frac_tex >= frac_fp32 else "fp32",
         "achieved": tex_ach if frac_tex >= frac_fp32 else fp32_ach,
         "peak": tex_peak if frac_tex >= frac_fp32 else fp32_peak,
         "unit": "Gsample/s" if frac_tex >= frac_fp32 else "TFLOP/s",
         "frac": max(frac_tex, frac_fp32),
-        "traffic": NCU_DRAM_BYTES_PROP_STRONG_1080P if (args.width, args.height, args.src) == (1920, 1080, 10) else None,
-        "traffic_unit": "DRAM bytes per full-resolution launch (ncu --set full, profiles/r01_ncu_full_prop_strong_compacted.md)",
+        "traffic": NCU_TRAFFIC[STAGE_NAMES[k]][0] if (args.width, args.height, args.src) == (1920, 1080, 10) and STAGE_NAMES[k] in NCU_TRAFFIC else None,
+        "traffic_unit": "DRAM bytes per full-resolution launch (ncu --set full, %s)" % NCU_TRAFFIC.get(STAGE_NAMES[k], (0, "", "n/a"))[2],
         "fp32": {"achieved_tflops": fp32_ach, "peak_tflops": fp32_peak, "frac": frac_fp32, "flop_per_eval": ALG_FLOP_PER_EVAL},
         "l1tex": {"achieved_gsamples": tex_ach, "peak_gsamples": tex_peak, "frac": frac_tex, "samples_per_eval": SAMPLES_PER_EVAL,
                   "achieved_GBps": tex_ach * ALG_L1_BYTES_PER_EVAL / SAMPLES_PER_EVAL},
