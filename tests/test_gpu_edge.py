@@ -44,10 +44,11 @@ def test_error_behaviour(apde_lib):
     c.close()
 
 
-@pytest.mark.parametrize("size,views,src", [((131, 97), 4, 3), ((48, 33), 3, 2), ((96, 64), 3, 1), ((80, 64), 15, 13)])
+@pytest.mark.parametrize("size,views,src", [((131, 97), 4, 3), ((48, 33), 3, 2), ((96, 64), 3, 1), ((80, 64), 15, 13),
+                                            ((64, 48), 32, 31)])
 def test_whole_pass_matches_oracle_on_odd_shapes(ctx, size, views, src):
     """odd widths / heights (incl. H = 33: the last row is never visited by the red/black kernels, quirk 7), a single
-    source view, and N = 13 (the shared-memory sizing switches to 64-thread blocks)"""
+    source view, N = 13 (the shared-memory sizing switches to 64-thread blocks) and N = 31, the MAX_IMAGES limit (main.h:40)"""
     from apde_mvs_b200.scene import make_plane_scene
     w, h = size
     scene = make_plane_scene(w, h, num_views=views, num_src=src, seed=5)
