@@ -834,6 +834,9 @@ cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStr
                 cudaError_t e = cudaFuncSetAttribute(k_prop_strong, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
                 configured = smem;
+                // experiment knob: shared-memory carve-out in per cent (less shared memory = fewer resident CTAs, more L1/TEX cache)
+                if (const char *co = getenv("APDE_STRONG_CARVEOUT"))
+                    cudaFuncSetAttribute(k_prop_strong, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
             }
             const int wpb = threads / 32;
             k_prop_strong<<<(tiles + wpb - 1) / wpb, threads, smem, st>>>(K, iter, color, tiles8x, ylimit);
