@@ -8,7 +8,10 @@
  * PARITY PIN: the reference ships no tests / golden vectors, so this oracle is
  * pinned against outputs of the reference's own device functions, produced on a B200 by
  * oracle/ref_wrapper.cu (which #includes /root/reference/APD.cu unmodified) and committed as
- * tests/golden/ref_*.npz together with the generating script (tests/golden/make_ref_golden.py).
+ * tests/golden/ref_*.npz together with the generating script (tests/golden/make_ref_golden.py).  The HOST half (ReadCamera,
+ * the .bin map format, WeakVisFilter, RunFusion, RunFusion_TAT_I / _TAT_A, PLY export) is pinned against the reference's own
+ * APD.cpp, compiled unmodified into oracle/_ref/libapd_ref_host.so (oracle/ref_host_wrapper.cpp) and run on the CPU by
+ * tests/test_ref_host.py: identical skip maps, points, order and colours.
  *
  * Deviations from the reference that are deliberate and shared with the CUDA product:
  *   - RNG: Philox4x32-10 counter RNG keyed by (seed, stream), counter = (pixel, site, block) instead

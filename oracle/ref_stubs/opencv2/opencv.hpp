@@ -1,10 +1,15 @@
-// Minimal stand-in for the OpenCV C++ API surface that /root/reference/APD.h and APD.cu touch (OpenCV C++ headers are
-// not installable in this image).  TEST INFRASTRUCTURE: lets nvcc compile the reference's own APD.cu unmodified.
+// Minimal stand-in for the OpenCV C++ API surface that /root/reference/APD.h, APD.cu and APD.cpp touch (OpenCV C++ headers
+// are not installable in this image).  TEST INFRASTRUCTURE: lets nvcc compile the reference's own APD.cu and APD.cpp
+// unmodified.  Only what the fusion path needs behaves like OpenCV (Mat, at<>, clone, zeros, imread of binary PGM / PPM,
+// nearest resize, norm); imwrite stores 8-bit single-channel images as PGM; applyColorMap and flip are no-ops.
 #ifndef APDE_STUB_OPENCV_HPP_
 #define APDE_STUB_OPENCV_HPP_
 #include <cfloat>
+#include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -34,17 +39,43 @@ struct Vec {
 };
 typedef Vec<float, 3> Vec3f;
 typedef Vec<uchar, 3> Vec3b;
+inline Vec3f operator/(const Vec3f &a, float d) { return Vec3f(a[0] / d, a[1] / d, a[2] / d); }
+inline double norm(const Vec3f &a) { return std::sqrt((double)a[0] * a[0] + (double)a[1] * a[1] + (double)a[2] * a[2]); }  // cv::norm: double accumulation
 struct Size { int width, height; Size(int w = 0, int h = 0) : width(w), height(h) {} };
-struct Scalar { double v[4]; Scalar(double a = 0) { v[0] = a; v[1] = v[2] = v[3] = 0; } };
+struct Scalar { double v[4]; Scalar(double a = 0, double b = 0, double c = 0, double d = 0) { v[0] = a; v[1] = b; v[2] = c; v[3] = d; } };
+struct MatStep {  // cv::MatStep: usable as a size_t and as step[0]
+    size_t v = 0;
+    MatStep() {}
+    MatStep(size_t s) : v(s) {}
+    operator size_t() const { return v; }
+    size_t operator[](int) const { return v; }
+};
+enum { IMREAD_GRAYSCALE = 0, IMREAD_COLOR = 1, INTER_NEAREST = 0, INTER_LINEAR = 1, COLORMAP_JET = 2 };
 
 class Mat {
 public:
     int rows = 0, cols = 0;
     uchar *data = nullptr;
-    size_t step = 0;
+    MatStep step;
     Mat() {}
     Mat(int r, int c, int type) { create(r, c, type); }
     Mat(int r, int c, int type, const Scalar &s) { create(r, c, type); std::memset(data, (int)s.v[0], step * rows); }
+    Mat(Size sz, int type) { create(sz.height, sz.width, type); }
+    Mat(Size sz, int type, const Scalar &s) { create(sz.height, sz.width, type); std::memset(data, (int)s.v[0], step * rows); }
+    int channels() const { return (type_ >> 3) + 1; }
+    size_t elemSize() const { static const int e[] = {1, 1, 2, 2, 4, 4, 8, 2}; return (size_t)e[type_ & 7] * channels(); }
+    // 8U -> 32F (ReadImage, APD.cpp:150) and 32F -> 8U with scale / offset (ShowNormalMap), saturating
+    void convertTo(Mat &dst, int rtype, double alpha = 1.0, double beta = 0.0) const {
+        Mat out(rows, cols, rtype);
+        const int n = cols * channels();
+        for (int r = 0; r < rows; ++r)
+            for (int i = 0; i < n; ++i) {
+                const double v = ((type_ & 7) == 0 ? (double)ptr<uchar>(r)[i] : (double)ptr<float>(r)[i]) * alpha + beta;
+                if ((rtype & 7) == 0) out.ptr<uchar>(r)[i] = (uchar)(v < 0 ? 0 : v > 255 ? 255 : std::lrint(v));
+                else out.ptr<float>(r)[i] = (float)v;
+            }
+        dst = out;
+    }
     static Mat zeros(int r, int c, int type) { Mat m(r, c, type); std::memset(m.data, 0, m.step * m.rows); return m; }
     static Mat zeros(Size s, int type) { return zeros(s.height, s.width, type); }
     static Mat ones(int r, int c, int type) { Mat m(r, c, type); std::memset(m.data, 1, m.step * m.rows); return m; }
@@ -68,7 +99,59 @@ private:
     int type_ = 0;
     std::shared_ptr<uchar[]> store_;
 };
-template <typename T> class Mat_ : public Mat {};
-inline bool imwrite(const std::string &, const Mat &) { return true; }
+template <typename T> class Mat_ : public Mat {
+public:
+    Mat_() {}
+    Mat_(const Mat &m) : Mat(m) {}
+};
+// single-channel 8-bit images are stored as binary PGM whatever the extension says (the tests read WeakVisFilter's skip.png
+// that way); everything else is dropped
+inline bool imwrite(const std::string &path, const Mat &m) {
+    if (m.type() != CV_8UC1 || m.empty()) return true;
+    FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) return false;
+    std::fprintf(f, "P5\n%d %d\n255\n", m.cols, m.rows);
+    for (int r = 0; r < m.rows; ++r) std::fwrite(m.ptr<uchar>(r), 1, (size_t)m.cols, f);
+    std::fclose(f);
+    return true;
+}
+inline void applyColorMap(const Mat &, Mat &, int) {}
+inline void flip(const Mat &, Mat &, int) {}
+// binary PGM (P5) / PPM (P6), 8 bit.  IMREAD_COLOR returns BGR like OpenCV; IMREAD_GRAYSCALE of a colour file is not needed here
+inline Mat imread(const std::string &path, int flag) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) return Mat();
+    char magic[3] = {0, 0, 0};
+    int w = 0, h = 0, maxv = 0;
+    if (std::fscanf(f, "%2s %d %d %d", magic, &w, &h, &maxv) != 4 || maxv != 255 || (magic[1] != '5' && magic[1] != '6')) { std::fclose(f); return Mat(); }
+    std::fgetc(f);
+    const int ch = magic[1] == '6' ? 3 : 1;
+    std::vector<uchar> buf((size_t)w * h * ch);
+    const size_t got = std::fread(buf.data(), 1, buf.size(), f);
+    std::fclose(f);
+    if (got != buf.size()) return Mat();
+    Mat out(h, w, flag == IMREAD_COLOR ? CV_8UC3 : CV_8UC1);
+    for (int r = 0; r < h; ++r)
+        for (int c = 0; c < w; ++c) {
+            const uchar *p = &buf[((size_t)r * w + c) * ch];
+            if (flag == IMREAD_COLOR) { uchar *o = out.ptr<uchar>(r) + 3 * c; o[0] = p[ch - 1]; o[1] = p[ch == 3 ? 1 : 0]; o[2] = p[0]; }
+            else out.ptr<uchar>(r)[c] = ch == 1 ? p[0] : (uchar)((p[0] * 9797 + p[1] * 19234 + p[2] * 3737) >> 15);
+        }
+    return out;
+}
+// INTER_NEAREST as OpenCV (sx = min(floor(dx / scale), W - 1)); INTER_LINEAR falls back to it (no test resizes images here)
+inline void resize(const Mat &src, Mat &dst, Size sz, double = 0, double = 0, int = INTER_NEAREST) {
+    Mat out(sz.height, sz.width, src.type());
+    const size_t es = src.elemSize();
+    const double ifx = 1.0 / ((double)sz.width / src.cols), ify = 1.0 / ((double)sz.height / src.rows);
+    for (int r = 0; r < sz.height; ++r) {
+        const int sy = std::min((int)std::floor(r * ify), src.rows - 1);
+        for (int c = 0; c < sz.width; ++c) {
+            const int sx = std::min((int)std::floor(c * ifx), src.cols - 1);
+            std::memcpy(out.data + r * out.step + c * es, src.data + sy * src.step + sx * es, es);
+        }
+    }
+    dst = out;
+}
 }  // namespace cv
 #endif
