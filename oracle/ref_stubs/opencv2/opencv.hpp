@@ -139,16 +139,48 @@ inline Mat imread(const std::string &path, int flag) {
         }
     return out;
 }
-// INTER_NEAREST as OpenCV (sx = min(floor(dx / scale), W - 1)); INTER_LINEAR falls back to it (no test resizes images here)
-inline void resize(const Mat &src, Mat &dst, Size sz, double = 0, double = 0, int = INTER_NEAREST) {
+// cv::resize.  INTER_NEAREST: sx = min(floor(dx / scale), W - 1).  INTER_LINEAR: OpenCV's float path -- fx = (float)((dx + 0.5) *
+// scale - 0.5), taps clamped with zero weight at the borders, horizontal then vertical pass in float (the formula the CUDA
+// product's pyramid kernel is tested against cv2 with); 8-bit results are rounded.
+inline void resize(const Mat &src, Mat &dst, Size sz, double = 0, double = 0, int interp = INTER_LINEAR) {
     Mat out(sz.height, sz.width, src.type());
     const size_t es = src.elemSize();
     const double ifx = 1.0 / ((double)sz.width / src.cols), ify = 1.0 / ((double)sz.height / src.rows);
+    if (interp == INTER_NEAREST) {
+        for (int r = 0; r < sz.height; ++r) {
+            const int sy = std::min((int)std::floor(r * ify), src.rows - 1);
+            for (int c = 0; c < sz.width; ++c) {
+                const int sx = std::min((int)std::floor(c * ifx), src.cols - 1);
+                std::memcpy(out.data + r * out.step + c * es, src.data + sy * src.step + sx * es, es);
+            }
+        }
+        dst = out;
+        return;
+    }
+    const int cn = src.channels();
+    const bool f32 = (src.type() & 7) == 5;
+    auto get = [&](int y, int x, int k) -> float { return f32 ? src.ptr<float>(y)[x * cn + k] : (float)src.ptr<uchar>(y)[x * cn + k]; };
     for (int r = 0; r < sz.height; ++r) {
-        const int sy = std::min((int)std::floor(r * ify), src.rows - 1);
+        float fy = (float)((r + 0.5) * ify - 0.5);
+        int sy = (int)std::floor(fy);
+        fy -= sy;
+        if (sy < 0) { fy = 0.0f; sy = 0; }
+        if (sy >= src.rows - 1) { fy = 0.0f; sy = src.rows - 1; }
+        const int sy1 = std::min(sy + 1, src.rows - 1);
         for (int c = 0; c < sz.width; ++c) {
-            const int sx = std::min((int)std::floor(c * ifx), src.cols - 1);
-            std::memcpy(out.data + r * out.step + c * es, src.data + sy * src.step + sx * es, es);
+            float fx = (float)((c + 0.5) * ifx - 0.5);
+            int sx = (int)std::floor(fx);
+            fx -= sx;
+            if (sx < 0) { fx = 0.0f; sx = 0; }
+            if (sx >= src.cols - 1) { fx = 0.0f; sx = src.cols - 1; }
+            const int sx1 = std::min(sx + 1, src.cols - 1);
+            for (int k = 0; k < cn; ++k) {
+                const float r0 = get(sy, sx, k) * (1.0f - fx) + get(sy, sx1, k) * fx;
+                const float r1 = get(sy1, sx, k) * (1.0f - fx) + get(sy1, sx1, k) * fx;
+                const float v = r0 * (1.0f - fy) + r1 * fy;
+                if (f32) out.ptr<float>(r)[c * cn + k] = v;
+                else out.ptr<uchar>(r)[c * cn + k] = (uchar)std::lrint(v < 0 ? 0 : v > 255 ? 255 : v);
+            }
         }
     }
     dst = out;

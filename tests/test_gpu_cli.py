@@ -105,3 +105,79 @@ def test_apd_cli_jpeg_inputs_and_tat_fusion(dense, tmp_path):
         assert n > 20000 and np.quantile(res, 0.99) < 0.05
         counts[dataset] = n
     assert counts["TaT_a"] != counts["TaT_i"]  # different thresholds, different clouds
+
+
+def test_cli_against_the_reference_main(tmp_path):
+    """the product's `apd` against the REFERENCE's own main() (APD.cu + APD.cpp + main.cpp compiled unmodified into
+    oracle/_ref/libapd_ref_full.so) on the same dense folder: same files written, final depth maps agreeing on STRONG
+    pixels as well as two runs of the reference agree with each other, equal state shares, fused clouds of equal size"""
+    import shutil
+    sys.path.insert(0, ROOT)
+    from oracle import ref_main_runner as runner
+    if not runner.available():
+        pytest.skip("oracle/_ref/libapd_ref_full.so not built (needs /root/reference at build time)")
+    from apde_mvs_b200 import build as b
+    from apde_mvs_b200.scene import make_office_scene
+    b.build_host()
+    V, W, H = 5, 320, 240
+    scene = make_office_scene(W, H, num_views=V, num_src=4, seed=8, arc_deg=25.0, with_color=True)
+    ours = tmp_path / "ours"
+    scene.write_dense_folder(str(ours))  # PNG images
+    import cv2
+    for v in range(V):
+        cv2.imwrite(str(ours / "images" / ("%08d.png" % v)), scene.colors[v])  # colour inputs: grey conversion is part of the path
+
+    def ref_folder(name):
+        d = tmp_path / name
+        shutil.copytree(ours / "cams", d / "cams")
+        shutil.copy(ours / "pair.txt", d / "pair.txt")
+        os.makedirs(d / "images")
+        for v in range(V):  # PPM content under the .png name the reference looks for (stub cv::imread decodes by magic)
+            with open(d / "images" / ("%08d.png" % v), "wb") as f:
+                f.write(b"P6\n%d %d\n255\n" % (W, H))
+                f.write(np.ascontiguousarray(scene.colors[v][..., ::-1]).tobytes())
+        return d
+
+    def run_ref(d, seed):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_main_runner.py"), str(seed), "--dense_folder", str(d),
+                              "--use_sa", "false", "--memory_cache", "true", "--flush", "true"], capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+        return out.stdout
+
+    ra, rb = ref_folder("ref_a"), ref_folder("ref_b")
+    log_a = run_ref(ra, 1111)
+    run_ref(rb, 2222)
+    apd = os.path.join(ROOT, "apde_mvs_b200", "_build", "apd")
+    out = subprocess.run([apd, "-d", str(ours), "--use_sa", "false"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-1500:]
+    assert "Round nums: 1" in out.stdout and "Round nums: 1" in log_a
+    agree, self_agree, dshare = [], [], []
+    for v in range(V):
+        m = {}
+        for tag, d in (("o", ours), ("a", ra), ("b", rb)):
+            r = d / "APD" / ("%08d" % v)
+            for name in ("depths", "normals", "weak", "confidence"):
+                assert (r / (name + ".bin")).exists(), (tag, name)
+            m[tag] = (_read_bin(r / "depths.bin"), _read_bin(r / "weak.bin"), _read_bin(r / "normals.bin"))
+            assert m[tag][0].shape == (H, W) and m[tag][2].shape == (H, W, 3)
+        gt = scene.gt_depth[v]
+        inner = np.zeros((H, W), bool)
+        inner[12:-12, 12:-12] = True
+        with np.errstate(all="ignore"):
+            sel = inner & (gt > 0) & (m["o"][1] == 1) & (m["a"][1] == 1)
+            agree.append((np.abs(m["o"][0] - m["a"][0]) <= 0.01 * m["a"][0])[sel].mean())
+            sel2 = inner & (gt > 0) & (m["b"][1] == 1) & (m["a"][1] == 1)
+            self_agree.append((np.abs(m["b"][0] - m["a"][0]) <= 0.01 * m["a"][0])[sel2].mean())
+        ho = np.bincount(m["o"][1][inner], minlength=3) / inner.sum()
+        ha = np.bincount(m["a"][1][inner], minlength=3) / inner.sum()
+        dshare.append(np.abs(ho - ha).max())
+
+    def ply_count(p):
+        head = open(p, "rb").read(400)
+        return int(head.split(b"element vertex ")[1].split(b"\n")[0])
+    n_o, n_a, n_b = ply_count(ours / "APD" / "APD.ply"), ply_count(ra / "APD" / "APD.ply"), ply_count(rb / "APD" / "APD.ply")
+    print("apd vs reference main(): depth within 1%% per view %s (reference vs itself %s); state-share difference %.3f; fused points "
+          "ours %d, reference %d / %d" % (np.round(agree, 4), np.round(self_agree, 4), max(dshare), n_o, n_a, n_b))
+    assert min(agree) >= min(0.99, min(self_agree) - 0.01)
+    assert max(dshare) < 0.05
+    assert abs(n_o - n_a) <= max(0.03 * n_a, 3 * abs(n_a - n_b))
