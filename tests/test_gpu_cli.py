@@ -107,10 +107,13 @@ def test_apd_cli_jpeg_inputs_and_tat_fusion(dense, tmp_path):
     assert counts["TaT_a"] != counts["TaT_i"]  # different thresholds, different clouds
 
 
-def test_cli_against_the_reference_main(tmp_path):
+@pytest.mark.parametrize("dataset,W,H,weak,rounds", [("General", 320, 240, 0.0, 1), ("TaT_i", 960, 720, 0.25, 2)])
+def test_cli_against_the_reference_main(tmp_path, dataset, W, H, weak, rounds):
     """the product's `apd` against the REFERENCE's own main() (APD.cu + APD.cpp + main.cpp compiled unmodified into
     oracle/_ref/libapd_ref_full.so) on the same dense folder: same files written, final depth maps agreeing on STRONG
-    pixels as well as two runs of the reference agree with each other, equal state shares, fused clouds of equal size"""
+    pixels as well as two runs of the reference agree with each other, equal state shares, fused clouds of equal size.
+    Second case: two pyramid rounds (use_APD, map hand-over between levels in the reference's own host code), weak-texture
+    blobs, and the Tanks-and-Temples settings (geom_factor 0.05, RunFusion_TAT_I)."""
     import shutil
     sys.path.insert(0, ROOT)
     from oracle import ref_main_runner as runner
@@ -119,8 +122,8 @@ def test_cli_against_the_reference_main(tmp_path):
     from apde_mvs_b200 import build as b
     from apde_mvs_b200.scene import make_office_scene
     b.build_host()
-    V, W, H = 5, 320, 240
-    scene = make_office_scene(W, H, num_views=V, num_src=4, seed=8, arc_deg=25.0, with_color=True)
+    V = 5
+    scene = make_office_scene(W, H, num_views=V, num_src=4, seed=8, arc_deg=25.0, weak=weak, with_color=True)
     ours = tmp_path / "ours"
     scene.write_dense_folder(str(ours))  # PNG images
     import cv2
@@ -140,7 +143,7 @@ def test_cli_against_the_reference_main(tmp_path):
 
     def run_ref(d, seed):
         out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_main_runner.py"), str(seed), "--dense_folder", str(d),
-                              "--use_sa", "false", "--memory_cache", "true", "--flush", "true"], capture_output=True, text=True)
+                              "--use_sa", "false", "--memory_cache", "true", "--flush", "true", "--dataset", dataset], capture_output=True, text=True)
         assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
         return out.stdout
 
@@ -148,9 +151,9 @@ def test_cli_against_the_reference_main(tmp_path):
     log_a = run_ref(ra, 1111)
     run_ref(rb, 2222)
     apd = os.path.join(ROOT, "apde_mvs_b200", "_build", "apd")
-    out = subprocess.run([apd, "-d", str(ours), "--use_sa", "false"], capture_output=True, text=True)
+    out = subprocess.run([apd, "-d", str(ours), "--use_sa", "false", "--dataset", dataset], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout[-1500:]
-    assert "Round nums: 1" in out.stdout and "Round nums: 1" in log_a
+    assert "Round nums: %d" % rounds in out.stdout and "Round nums: %d" % rounds in log_a
     agree, self_agree, dshare = [], [], []
     for v in range(V):
         m = {}
@@ -176,7 +179,7 @@ def test_cli_against_the_reference_main(tmp_path):
         head = open(p, "rb").read(400)
         return int(head.split(b"element vertex ")[1].split(b"\n")[0])
     n_o, n_a, n_b = ply_count(ours / "APD" / "APD.ply"), ply_count(ra / "APD" / "APD.ply"), ply_count(rb / "APD" / "APD.ply")
-    print("apd vs reference main(): depth within 1%% per view %s (reference vs itself %s); state-share difference %.3f; fused points "
+    print(dataset, "apd vs reference main(): depth within 1%% per view %s (reference vs itself %s); state-share difference %.3f; fused points "
           "ours %d, reference %d / %d" % (np.round(agree, 4), np.round(self_agree, 4), max(dshare), n_o, n_a, n_b))
     assert min(agree) >= min(0.99, min(self_agree) - 0.01)
     assert max(dshare) < 0.05
