@@ -21,8 +21,26 @@ def lib():
         L.ref_read_camera.argtypes = [C.c_char_p, C.c_void_p]
         L.ref_copy_bin_mat.argtypes = [C.c_char_p, C.c_char_p]
         L.ref_run_fusion.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p]
+        L.ref_generate_sample_list.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
+        L.ref_compute_round_num.argtypes = [C.c_char_p]
         _lib = L
     return _lib
+
+
+def generate_sample_list(dense_folder, max_views=4096, max_src=1 << 20):
+    """the reference's GenerateSampleList -> (ref ids, list of source-id lists, image extension)"""
+    ids = np.zeros(max_views, np.int32)
+    offs = np.zeros(max_views + 1, np.int32)
+    src = np.zeros(max_src, np.int32)
+    ext = C.create_string_buffer(16)
+    n = lib().ref_generate_sample_list(str(dense_folder).encode(), max_views, max_src, ids.ctypes.data, offs.ctypes.data, src.ctypes.data, ext)
+    if n < 0:
+        raise RuntimeError("reference GenerateSampleList: buffer too small")
+    return ids[:n].tolist(), [src[offs[i]:offs[i + 1]].tolist() for i in range(n)], ext.value.decode()
+
+
+def compute_round_num(dense_folder):
+    return lib().ref_compute_round_num(str(dense_folder).encode())
 
 
 def read_camera(path):

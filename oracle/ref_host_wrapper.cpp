@@ -5,7 +5,37 @@
 // because the same file defines the APD class; none of it is called here).
 #include "APD.cpp"
 
+// main.cpp rides along for GenerateSampleList / ComputeRoundNum; its ProcessProblem refers to the one APD method that lives
+// in APD.cu, which this CPU-only library does not contain and never calls
+void APD::RunPatchMatch() {}
+#define main reference_main
+#include "main.cpp"
+#undef main
+
 extern "C" {
+
+// the reference's GenerateSampleList (main.cpp:44-102): ref ids, CSR source ids (score <= 0 dropped), image extension of view 0
+int ref_generate_sample_list(const char *dense_folder, int max_views, int max_src, int *ref_ids, int *src_offsets, int *src_ids, char *ext16) {
+    std::vector<Problem> problems;
+    GenerateSampleList(path(dense_folder), problems);
+    if ((int)problems.size() > max_views) return -1;
+    int k = 0;
+    src_offsets[0] = 0;
+    for (size_t i = 0; i < problems.size(); ++i) {
+        ref_ids[i] = problems[i].ref_image_id;
+        for (int s : problems[i].src_image_ids) { if (k >= max_src) return -2; src_ids[k++] = s; }
+        src_offsets[i + 1] = k;
+    }
+    if (!problems.empty()) { strncpy(ext16, problems[0].img_ext.c_str(), 15); ext16[15] = 0; }
+    return (int)problems.size();
+}
+
+// the reference's ComputeRoundNum (main.cpp:129-146) on the folder's first image
+int ref_compute_round_num(const char *dense_folder) {
+    std::vector<Problem> problems;
+    GenerateSampleList(path(dense_folder), problems);
+    return ComputeRoundNum(problems);
+}
 
 // the reference's ReadCamera (APD.cpp:85-135): out = K[9] R[9] t[3] c[3] height width depth_min depth_max interval depth_num
 int ref_read_camera(const char *cam_path, float *out) {

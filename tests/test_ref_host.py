@@ -75,6 +75,29 @@ def test_read_camera_and_bin_format_match_the_reference(tmp_path):
         assert int(out[2]) == typ and open(tmp_path / "copy2.bin", "rb").read() == open(src, "rb").read()
 
 
+def test_sample_list_and_round_rule_match_the_reference(tmp_path):
+    """pair.txt parsing (score <= 0 dropped, extension probing) and ComputeRoundNum: the product's C++ host side and the
+    schedule's round rule against the reference's own GenerateSampleList / ComputeRoundNum (main.cpp:44-146)"""
+    from apde_mvs_b200 import build as b
+    b.build_host()
+    tool = os.path.join(ROOT, "apde_mvs_b200", "_build", "test_io")
+    from oracle.ref_schedule import compute_round_num
+    for (w, h), want in (((640, 480), 1), ((801, 600), 2), ((1600, 1200), 2), ((1920, 1056), 3), ((400, 3300), 4)):
+        d = tmp_path / ("s_%dx%d" % (w, h))
+        os.makedirs(d / "images"); os.makedirs(d / "cams"); os.makedirs(d / "APD")  # main() creates APD/ before the list (main.cpp:262)
+        for v in range(3):
+            with open(d / "images" / ("%08d.png" % v), "wb") as f:   # PGM content under the name the reference probes for
+                f.write(b"P5\n%d %d\n255\n" % (w, h)); f.write(bytes(w * h))
+        with open(d / "pair.txt", "w") as f:
+            f.write("3\n0\n3 1 10.5 2 0.0 1 -1\n1\n2 0 1 2 3.5\n2\n0\n")
+        ids, src, ext = refh.generate_sample_list(d)
+        assert ids == [0, 1, 2] and src == [[1], [0, 2], []] and ext == ".png"
+        assert refh.compute_round_num(d) == want == compute_round_num(w, h)
+        out = subprocess.check_output([tool, "pairs", str(d)], text=True).strip().splitlines()
+        mine = [(int(l.split()[0]), [int(x) for x in l.split(":")[1].split()]) for l in out]
+        assert [m[0] for m in mine] == ids and [m[1] for m in mine] == src and out[0].split()[1].rstrip(":") == ext
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2])
 def test_fusion_oracle_matches_the_reference_code(tmp_path, variant):
     """WeakVisFilter + RunFusion / RunFusion_TAT_I / RunFusion_TAT_A: the oracle reproduces the reference's point cloud
