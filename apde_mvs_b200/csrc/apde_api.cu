@@ -203,6 +203,7 @@ static void free_scene(apde_context *c) {
     }
     cudaFree(c->d_skip);
     c->d_skip = nullptr;
+    fusion_release_cache();
     c->sweep.release();
     c->prop.release();
     c->committed = false;

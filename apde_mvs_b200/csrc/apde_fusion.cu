@@ -17,7 +17,42 @@
 
 #include <climits>
 
+#include <map>
+
 namespace apde {
+
+// Fusion runs once per scene but allocates ~1 GB of scratch each time; cudaMalloc / cudaFree of that size cost more than the
+// kernels.  Blocks are therefore recycled through a small exact-size pool (per device), emptied by fusion_release_cache().
+static std::multimap<std::pair<int, size_t>, void *> g_pool;
+static std::map<void *, std::pair<int, size_t>> g_live;
+template <typename T>
+static cudaError_t pool_malloc(T **p, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const auto key = std::make_pair(dev, bytes);
+    auto it = g_pool.find(key);
+    if (it != g_pool.end()) {
+        *p = static_cast<T *>(it->second);
+        g_pool.erase(it);
+        g_live[*p] = key;
+        return cudaSuccess;
+    }
+    void *q = nullptr;
+    const cudaError_t e = cudaMalloc(&q, bytes);
+    if (e == cudaSuccess) { *p = static_cast<T *>(q); g_live[q] = key; }
+    return e;
+}
+static void pool_free(void *p) {
+    if (!p) return;
+    auto it = g_live.find(p);
+    if (it == g_live.end()) { cudaFree(p); return; }
+    g_pool.emplace(it->second, p);
+    g_live.erase(it);
+}
+void fusion_release_cache() {
+    for (auto &kv : g_pool) cudaFree(kv.second);
+    g_pool.clear();
+}
 
 struct FCam {
     float K[9], R[9], t[3], c[3];
@@ -233,7 +268,7 @@ static cudaError_t upload_cams(const std::vector<FusionView> &views, FCam **d_ca
         hc[v].depth = views[v].depth; hc[v].normal = views[v].normal; hc[v].weak = views[v].weak; hc[v].conf = views[v].conf;
         hc[v].bgr = views[v].bgr;  // the caller passes colours only when they have the maps' resolution
     }
-    cudaError_t e = cudaMalloc(d_cams, hc.size() * sizeof(FCam));
+    cudaError_t e = pool_malloc(d_cams, hc.size() * sizeof(FCam));
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*d_cams, hc.data(), hc.size() * sizeof(FCam), cudaMemcpyHostToDevice);
 }
@@ -246,7 +281,7 @@ cudaError_t fusion_weak_vis_filter(const std::vector<FusionView> &views, int w, 
     const int V = (int)views.size(), P = w * h;
     for (int ref = first_view; ref < first_view + num_views; ++ref) k_weak_vis<<<(P + 127) / 128, 128, 0, st>>>(d_cams, V, ref, w, h, skip);
     e = cudaStreamSynchronize(st);
-    cudaFree(d_cams);
+    pool_free(d_cams);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
@@ -269,23 +304,23 @@ cudaError_t fusion_run(const std::vector<FusionView> &views, int w, int h, const
     for (auto &v : views) maxN = std::max(maxN, (int)v.src.size());
     const int blocks = (P + 127) / 128;
     FCU(upload_cams(views, &d_cams));
-    FCU(cudaMalloc(&d_masks, (size_t)V * P));
+    FCU(pool_malloc(&d_masks, (size_t)V * P));
     FCU(cudaMemsetAsync(d_masks, 0, (size_t)V * P, st));
-    FCU(cudaMalloc(&d_active, P));
-    FCU(cudaMalloc(&d_nbr, maxN * sizeof(int)));
-    FCU(cudaMalloc(&d_slot, maxN * sizeof(int)));
-    FCU(cudaMalloc(&d_cq, (size_t)maxN * P * sizeof(int)));
-    FCU(cudaMalloc(&d_ce, (size_t)maxN * P * sizeof(float)));
-    FCU(cudaMalloc(&d_claim[0], (size_t)maxN * P * sizeof(int)));
-    FCU(cudaMalloc(&d_claim[1], (size_t)maxN * P * sizeof(int)));
-    FCU(cudaMalloc(&d_used, (size_t)P * sizeof(uint32_t)));
-    FCU(cudaMalloc(&d_flags, (size_t)P * sizeof(int)));
-    FCU(cudaMalloc(&d_offs, (size_t)P * sizeof(int)));
-    FCU(cudaMalloc(&d_changed, sizeof(int)));
-    FCU(cudaMalloc(&d_xyz, (size_t)P * 3 * sizeof(float)));
-    FCU(cudaMalloc(&d_bgr, (size_t)P * 3 * sizeof(float)));
+    FCU(pool_malloc(&d_active, P));
+    FCU(pool_malloc(&d_nbr, maxN * sizeof(int)));
+    FCU(pool_malloc(&d_slot, maxN * sizeof(int)));
+    FCU(pool_malloc(&d_cq, (size_t)maxN * P * sizeof(int)));
+    FCU(pool_malloc(&d_ce, (size_t)maxN * P * sizeof(float)));
+    FCU(pool_malloc(&d_claim[0], (size_t)maxN * P * sizeof(int)));
+    FCU(pool_malloc(&d_claim[1], (size_t)maxN * P * sizeof(int)));
+    FCU(pool_malloc(&d_used, (size_t)P * sizeof(uint32_t)));
+    FCU(pool_malloc(&d_flags, (size_t)P * sizeof(int)));
+    FCU(pool_malloc(&d_offs, (size_t)P * sizeof(int)));
+    FCU(pool_malloc(&d_changed, sizeof(int)));
+    FCU(pool_malloc(&d_xyz, (size_t)P * 3 * sizeof(float)));
+    FCU(pool_malloc(&d_bgr, (size_t)P * 3 * sizeof(float)));
     FCU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_flags, d_offs, P, st));
-    FCU(cudaMalloc(&d_tmp, tmp_bytes));
+    FCU(pool_malloc(&d_tmp, tmp_bytes));
 
     for (int ref = 0; ref < V; ++ref) {
         const int N = (int)views[ref].src.size();
@@ -331,9 +366,9 @@ cudaError_t fusion_run(const std::vector<FusionView> &views, int w, int h, const
     }
     *num_points = total;
 done:
-    cudaFree(d_cams); cudaFree(d_masks); cudaFree(d_active); cudaFree(d_nbr); cudaFree(d_slot); cudaFree(d_cq); cudaFree(d_ce);
-    cudaFree(d_claim[0]); cudaFree(d_claim[1]); cudaFree(d_used); cudaFree(d_flags); cudaFree(d_offs); cudaFree(d_changed);
-    cudaFree(d_xyz); cudaFree(d_bgr); cudaFree(d_tmp);
+    pool_free(d_cams); pool_free(d_masks); pool_free(d_active); pool_free(d_nbr); pool_free(d_slot); pool_free(d_cq); pool_free(d_ce);
+    pool_free(d_claim[0]); pool_free(d_claim[1]); pool_free(d_used); pool_free(d_flags); pool_free(d_offs); pool_free(d_changed);
+    pool_free(d_xyz); pool_free(d_bgr); pool_free(d_tmp);
     return err;
 }
 
@@ -476,20 +511,20 @@ cudaError_t fusion_run_tat(const std::vector<FusionView> &views, int w, int h, i
     for (auto &v : views) maxN = std::max(maxN, (int)v.src.size());
     const int blocks = (P + 127) / 128;
     FCU(upload_cams(views, &d_cams));
-    FCU(cudaMalloc(&d_masks, (size_t)V * P));
+    FCU(pool_malloc(&d_masks, (size_t)V * P));
     FCU(cudaMemsetAsync(d_masks, 0, (size_t)V * P, st));
-    FCU(cudaMalloc(&d_active, P));
-    FCU(cudaMalloc(&d_nbr, maxN * sizeof(int)));
-    FCU(cudaMalloc(&d_last, (size_t)maxN * P * sizeof(int)));
-    FCU(cudaMalloc(&d_meas, (size_t)maxN * P * sizeof(TatMeasure)));
-    FCU(cudaMalloc(&d_used, (size_t)P * sizeof(uint32_t)));
-    FCU(cudaMalloc(&d_flags, (size_t)P * sizeof(int)));
-    FCU(cudaMalloc(&d_offs, (size_t)P * sizeof(int)));
-    FCU(cudaMalloc(&d_xyz, (size_t)P * 3 * sizeof(float)));
-    FCU(cudaMalloc(&d_bgr, (size_t)P * 3 * sizeof(float)));
+    FCU(pool_malloc(&d_active, P));
+    FCU(pool_malloc(&d_nbr, maxN * sizeof(int)));
+    FCU(pool_malloc(&d_last, (size_t)maxN * P * sizeof(int)));
+    FCU(pool_malloc(&d_meas, (size_t)maxN * P * sizeof(TatMeasure)));
+    FCU(pool_malloc(&d_used, (size_t)P * sizeof(uint32_t)));
+    FCU(pool_malloc(&d_flags, (size_t)P * sizeof(int)));
+    FCU(pool_malloc(&d_offs, (size_t)P * sizeof(int)));
+    FCU(pool_malloc(&d_xyz, (size_t)P * 3 * sizeof(float)));
+    FCU(pool_malloc(&d_bgr, (size_t)P * 3 * sizeof(float)));
     FCU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_a, d_flags, d_offs, P, st));
     FCU(cub::DeviceScan::InclusiveScan(nullptr, tmp_b, d_last, d_last, MaxInt(), P, st));
-    FCU(cudaMalloc(&d_tmp, std::max(tmp_a, tmp_b)));
+    FCU(pool_malloc(&d_tmp, std::max(tmp_a, tmp_b)));
     tmp_a = tmp_b = std::max(tmp_a, tmp_b);
 
     for (int ref = 0; ref < V; ++ref) {
@@ -516,8 +551,8 @@ cudaError_t fusion_run_tat(const std::vector<FusionView> &views, int w, int h, i
     }
     *num_points = total;
 done:
-    cudaFree(d_cams); cudaFree(d_masks); cudaFree(d_active); cudaFree(d_nbr); cudaFree(d_last); cudaFree(d_meas); cudaFree(d_used);
-    cudaFree(d_flags); cudaFree(d_offs); cudaFree(d_xyz); cudaFree(d_bgr); cudaFree(d_tmp);
+    pool_free(d_cams); pool_free(d_masks); pool_free(d_active); pool_free(d_nbr); pool_free(d_last); pool_free(d_meas); pool_free(d_used);
+    pool_free(d_flags); pool_free(d_offs); pool_free(d_xyz); pool_free(d_bgr); pool_free(d_tmp);
     return err;
 }
 

@@ -30,4 +30,7 @@ cudaError_t fusion_run(const std::vector<FusionView> &views, int w, int h, const
 cudaError_t fusion_run_tat(const std::vector<FusionView> &views, int w, int h, int variant, const uint8_t *skip, float *xyz,
                            float *bgr, int64_t max_points, int64_t *num_points, cudaStream_t st, uint64_t *launches);
 
+// frees the scratch blocks the fusion entry points keep for re-use
+void fusion_release_cache();
+
 }  // namespace apde
