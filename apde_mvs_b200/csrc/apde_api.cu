@@ -91,6 +91,9 @@ struct apde_context {
     uint8_t *d_weak = nullptr, *d_conf = nullptr, *d_reliable = nullptr;
     short2 *d_nearest = nullptr, *d_anchors = nullptr;
     uint16_t *d_ns_tiles = nullptr;
+    float *d_curve = nullptr;   // [P][61] DepthToWeak cost curves while capture_curve is on
+    size_t curve_cap = 0;
+    bool capture_curve = false;
     int *d_lists = nullptr, *d_list_counts = nullptr;  // compacted checkerboard pixel lists (4 x list_cap)
     int list_cap = 0;
     int h_list_counts[4] = {0, 0, 0, 0};  // host copy of the list lengths: sizes (or skips) the list-driven launches
@@ -197,7 +200,7 @@ static void free_scene(apde_context *c) {
     if (c->ws_alloc) {
         cudaFree(c->d_planes); cudaFree(c->d_fit); cudaFree(c->d_costs); cudaFree(c->d_depthws);
         cudaFree(c->d_scratch_depth); cudaFree(c->d_scratch_normal); cudaFree(c->d_sel); cudaFree(c->d_vw);
-        cudaFree(c->d_weak); cudaFree(c->d_conf); cudaFree(c->d_reliable); cudaFree(c->d_nearest); cudaFree(c->d_anchors); cudaFree(c->d_ns_tiles);
+        cudaFree(c->d_weak); cudaFree(c->d_conf); cudaFree(c->d_reliable); cudaFree(c->d_nearest); cudaFree(c->d_anchors); cudaFree(c->d_ns_tiles); cudaFree(c->d_curve); c->d_curve = nullptr; c->curve_cap = 0;
         cudaFree(c->d_lists); cudaFree(c->d_list_counts);
         c->ws_alloc = false;
     }
@@ -675,7 +678,23 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
         }
         if (!legacy && !getenv("APDE_QUAD_KERNELS")) {
             // (the sweep functions count every launch but the last one; the generic count below adds that)
-            if (stage == APDE_STAGE_DEPTH_TO_WEAK) return sweep_depth_to_weak(Kq, c->sweep, nullptr, c->stream, &c->launches);
+            if (stage == APDE_STAGE_DEPTH_TO_WEAK) {
+                float *curve = nullptr;
+                if (c->capture_curve) {
+                    const size_t need = (size_t)Kq.W * Kq.H * 61;
+                    if (need > c->curve_cap) {
+                        cudaFree(c->d_curve);
+                        c->d_curve = nullptr; c->curve_cap = 0;
+                        cudaError_t e = cudaMalloc(&c->d_curve, need * sizeof(float));
+                        if (e != cudaSuccess) return e;
+                        c->curve_cap = need;
+                    }
+                    cudaError_t e = cudaMemsetAsync(c->d_curve, 0, need * sizeof(float), c->stream);
+                    if (e != cudaSuccess) return e;
+                    curve = c->d_curve;
+                }
+                return sweep_depth_to_weak(Kq, c->sweep, curve, c->stream, &c->launches);
+            }
             if (stage == APDE_STAGE_LOCAL_REFINE) return sweep_local_refine(Kq, c->sweep, c->stream, &c->launches);
         }
         return launch_stage(Kq, stage, iter, color, c->stream, nullptr);
@@ -712,6 +731,13 @@ static int collect_stage_events(apde_context *c) {
         c->stage_ms[c->ev_stage[k]] += ms;
     }
     c->ev_stage.clear();
+    return APDE_OK;
+}
+
+int apde_problem_capture_curve(apde_context *c, int on) {
+    if (!c) return fail(APDE_ERR_ARG, "capture_curve: no context");
+    c->capture_curve = on != 0;
+    if (!on) { CU(cudaSetDevice(c->device)); cudaFree(c->d_curve); c->d_curve = nullptr; c->curve_cap = 0; }
     return APDE_OK;
 }
 
@@ -803,6 +829,9 @@ static int field_ptr(apde_context *c, int field, void **ptr, size_t *bytes) {
         case APDE_FIELD_ANCHORS: *ptr = c->d_anchors; *bytes = P * APDE_ANCHOR_NUM * 4; break;
         case APDE_FIELD_SRC_DEPTH: *ptr = c->d_depthws; *bytes = P * 4 * (c->K.N + 1); break;
         case APDE_FIELD_IMAGE: *ptr = c->d_level_lin + (size_t)c->ref_view * P; *bytes = P * 4; break;
+        case APDE_FIELD_RELIABLE_CURVE:
+            if (!c->capture_curve || c->curve_cap < P * 61) return fail(APDE_ERR_STATE, "no reliable curve captured (apde_problem_capture_curve)");
+            *ptr = c->d_curve; *bytes = P * 61 * 4; break;
         default: return fail(APDE_ERR_ARG, "unknown field %d", field);
     }
     return APDE_OK;
@@ -1003,19 +1032,13 @@ int apde_schedule_num_passes(apde_context *c, const apde_schedule *s) {
     return rounds * (1 + s->geom_iterations);
 }
 
-int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_index, apde_timing *out) {
-    if (!c || !s) return fail(APDE_ERR_ARG, "run_schedule_pass: null argument");
-    if (!c->committed) return fail(APDE_ERR_STATE, "run_schedule_pass: scene not committed");
-    CU(cudaSetDevice(c->device));
+int apde_schedule_pass_params(apde_context *c, const apde_schedule *s, int pass_index, apde_params *params, int *scale_size,
+                              uint32_t *seed) {
+    if (!c || !s || !params) return fail(APDE_ERR_ARG, "schedule_pass_params: null argument");
     const int rounds = s->rounds > 0 ? s->rounds : compute_round_num(c->W, c->H);
     const int per_round = 1 + s->geom_iterations;
-    if (pass_index < 0 || pass_index >= rounds * per_round) return fail(APDE_ERR_ARG, "run_schedule_pass: pass %d out of range", pass_index);
+    if (pass_index < 0 || pass_index >= rounds * per_round) return fail(APDE_ERR_ARG, "schedule_pass_params: pass %d out of range", pass_index);
     const int i = pass_index / per_round, j = pass_index % per_round - 1;  // j = -1: photometric pass
-    const size_t Pfull = (size_t)c->W * c->H;
-    if (s->jacobi && !c->d_depth_pool[1]) {
-        CU(cudaMalloc(&c->d_depth_pool[1], (size_t)c->V * Pfull * sizeof(float)));
-        CU(cudaMemsetAsync(c->d_depth_pool[1], 0, (size_t)c->V * Pfull * sizeof(float), c->stream));
-    }
     apde_params p;
     apde_params_default(&p);
     p.geom_factor = s->geom_factor;
@@ -1037,7 +1060,32 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
         p.geom_consistency = 1;
         p.weak_peak_radius = std::max(4 - 2 * j, 2);
     }
-    const int scale = static_cast<int>(std::pow(2, rounds - 1 - i));
+    *params = p;
+    if (scale_size) *scale_size = static_cast<int>(std::pow(2, rounds - 1 - i));
+    if (seed) *seed = s->seed * 0x9E3779B1u + (uint32_t)pass_index * 0x85EBCA77u;
+    return APDE_OK;
+}
+
+int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_index, apde_timing *out) {
+    if (!c || !s) return fail(APDE_ERR_ARG, "run_schedule_pass: null argument");
+    if (!c->committed) return fail(APDE_ERR_STATE, "run_schedule_pass: scene not committed");
+    CU(cudaSetDevice(c->device));
+    const int rounds = s->rounds > 0 ? s->rounds : compute_round_num(c->W, c->H);
+    const int per_round = 1 + s->geom_iterations;
+    if (pass_index < 0 || pass_index >= rounds * per_round) return fail(APDE_ERR_ARG, "run_schedule_pass: pass %d out of range", pass_index);
+    const int i = pass_index / per_round, j = pass_index % per_round - 1;  // j = -1: photometric pass
+    const size_t Pfull = (size_t)c->W * c->H;
+    if (s->jacobi && !c->d_depth_pool[1]) {
+        CU(cudaMalloc(&c->d_depth_pool[1], (size_t)c->V * Pfull * sizeof(float)));
+        CU(cudaMemsetAsync(c->d_depth_pool[1], 0, (size_t)c->V * Pfull * sizeof(float), c->stream));
+    }
+    apde_params p;
+    int scale = 1;
+    uint32_t seed = 0;
+    {
+        const int prc = apde_schedule_pass_params(c, s, pass_index, &p, &scale, &seed);
+        if (prc) return prc;
+    }
     const int first = (s->num_views_local > 0) ? s->first_view : 0;
     const int count = (s->num_views_local > 0) ? s->num_views_local : c->V;
     if (first < 0 || first + count > c->V) return fail(APDE_ERR_ARG, "run_schedule_pass: bad shard [%d, %d)", first, first + count);
@@ -1065,7 +1113,6 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
         c->pm_events.push_back(ev);
     }
     for (int v = first; v < first + count; ++v) {
-        const uint32_t seed = s->seed * 0x9E3779B1u + (uint32_t)pass_index * 0x85EBCA77u;
         if ((rc = apde_problem_setup(c, v, &p, scale, seed))) return rc;
         CU(cudaEventRecord(c->pm_events[2 * (v - first)], c->stream));
         if ((rc = apde_problem_run(c))) return rc;

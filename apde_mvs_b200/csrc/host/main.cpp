@@ -2,6 +2,7 @@
 // same round x iteration x problem schedule, same output files (APD/%08d/{depths,normals,weak,confidence}.bin, APD/APD.ply).
 #include <chrono>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <map>
 
@@ -73,6 +74,62 @@ static void write_maps(SceneSession &s) {
     }
 }
 
+// The last iteration with --export_anchor / --export_curve, view by view (main.cpp:353-358, APD.cu:2614-2627, 2651-2661, 2692-2723):
+//   anchors_map.bin  CV_32SC1: running index of the pixels that were WEAK when the pass started, -1 elsewhere (APD.cpp:627-640)
+//   anchors.bin      int weak_count, int 9, short2[weak_count][9] (x, y; -1 = empty slot)
+//   reliable_curve.bin  int width, int height, int 61, float[height * width][61]: DepthToWeak's cost curve
+static bool run_pass_with_exports(SceneSession &s, const apde_schedule &sched, int pass, bool export_anchor, bool export_curve) {
+    apde_params prm;
+    int scale = 1;
+    uint32_t seed = 0;
+    if (apde_schedule_pass_params(s.ctx, &sched, pass, &prm, &scale, &seed)) return false;
+    if (export_curve && apde_problem_capture_curve(s.ctx, 1)) return false;
+    for (size_t i = 0; i < s.problems.size(); ++i) {
+        int mw = 0, mh = 0;
+        apde_view_download(s.ctx, (int)i, nullptr, nullptr, nullptr, nullptr, &mw, &mh);
+        Mat weak_in(mh, mw, CV_8UC1);
+        if (mw) apde_view_download(s.ctx, (int)i, nullptr, nullptr, weak_in.data(), nullptr, &mw, &mh);
+        if (apde_problem_setup(s.ctx, (int)i, &prm, scale, seed) || apde_problem_run(s.ctx)) return false;
+        int w = 0, h = 0, n = 0;
+        apde_problem_dims(s.ctx, &w, &h, &n);
+        const path dir = s.problems[i].result_folder;
+        if (export_anchor && prm.use_APD && mw == w && mh == h) {
+            std::vector<int16_t> dense((size_t)w * h * 9 * 2);
+            if (apde_problem_get(s.ctx, APDE_FIELD_ANCHORS, dense.data(), dense.size() * sizeof(int16_t))) return false;
+            Mat amap(h, w, CV_32SC1);
+            std::vector<int16_t> packed;
+            int weak_count = 0;
+            for (int px = 0; px < w * h; ++px) {
+                if (weak_in.data()[px] == APDE_WEAK) {
+                    amap.ptr<int>()[px] = weak_count++;
+                    packed.insert(packed.end(), dense.begin() + (size_t)px * 18, dense.begin() + (size_t)(px + 1) * 18);
+                } else {
+                    amap.ptr<int>()[px] = -1;
+                }
+            }
+            WriteBinMat(dir / "anchors_map.bin", amap);
+            std::ofstream out(dir / "anchors.bin", std::ios::binary);
+            const int num = 9;
+            out.write((const char *)&weak_count, sizeof(int));
+            out.write((const char *)&num, sizeof(int));
+            out.write((const char *)packed.data(), (std::streamsize)(packed.size() * sizeof(int16_t)));
+        }
+        if (export_curve) {
+            std::vector<float> curve((size_t)w * h * 61);
+            if (apde_problem_get(s.ctx, APDE_FIELD_RELIABLE_CURVE, curve.data(), curve.size() * sizeof(float))) return false;
+            std::ofstream out(dir / "reliable_curve.bin", std::ios::binary);
+            const int num = 61;
+            out.write((const char *)&w, sizeof(int));
+            out.write((const char *)&h, sizeof(int));
+            out.write((const char *)&num, sizeof(int));
+            out.write((const char *)curve.data(), (std::streamsize)(curve.size() * sizeof(float)));
+        }
+        if (apde_problem_finish(s.ctx)) return false;
+    }
+    if (export_curve) apde_problem_capture_curve(s.ctx, 0);
+    return true;
+}
+
 static bool read_maps(SceneSession &s) {  // --only_fuse: depth maps come from a previous run
     for (size_t i = 0; i < s.problems.size(); ++i) {
         const path dir = s.problems[i].result_folder;
@@ -124,6 +181,10 @@ int main(int argc, char **argv) {
                 std::cout << "========================== Round " << p / (1 + sched.geom_iterations) << " ==========================" << std::endl;
             std::cout << "======== iteration " << p << "========" << std::endl;
             const double before = t.patchmatch_ms;
+            if (p == npass - 1 && (a.export_anchor || a.export_curve)) {  // is_last_iteration, main.cpp:335
+                if (!run_pass_with_exports(*s, sched, p, a.export_anchor, a.export_curve)) { std::cout << "Error: " << apde_last_error() << std::endl; return EXIT_FAILURE; }
+                continue;
+            }
             if (apde_run_schedule_pass(s->ctx, &sched, p, &t)) { std::cout << "Error: " << apde_last_error() << std::endl; return EXIT_FAILURE; }
             printf("RunPatchMatch time: %d ms (all %zu views)\n", (int)(t.patchmatch_ms - before), s->problems.size());
         }

@@ -152,7 +152,8 @@ typedef enum {
     APDE_FIELD_NEAREST_STRONG = 8, /* short2[P] */
     APDE_FIELD_ANCHORS = 9,        /* short2[P][9] */
     APDE_FIELD_IMAGE = 10,         /* float[P], working-resolution reference image (read only) */
-    APDE_FIELD_SRC_DEPTH = 11      /* float[N+1][P], working-resolution depth maps, index 0 = ref (read only) */
+    APDE_FIELD_SRC_DEPTH = 11,     /* float[N+1][P], working-resolution depth maps, index 0 = ref (read only) */
+    APDE_FIELD_RELIABLE_CURVE = 12 /* float[P][61], DepthToWeak's cost curve (read only; needs apde_problem_capture_curve) */
 } apde_field;
 
 int apde_problem_get(apde_context *ctx, int field, void *host, size_t bytes);
@@ -163,6 +164,10 @@ int apde_problem_get_image(apde_context *ctx, int idx, float *host, size_t bytes
 int apde_problem_get_cameras(apde_context *ctx, apde_camera *cams /* [N+1] */, apde_params *params);
 /* write depth/normal/weak/confidence back into the view store (depth range check of main.cpp:172-175) */
 int apde_problem_finish(apde_context *ctx);
+
+/* Keep DepthToWeak's 61-sample cost curve of the following problems (reliable_curve.bin, APD.cu:2714-2723, 2651-2661);
+ * costs P * 61 floats of device memory while on.  Pixels DepthToWeak does not sweep hold zeros. */
+int apde_problem_capture_curve(apde_context *ctx, int on);
 
 /* setup + run + finish */
 int apde_pass_run(apde_context *ctx, int ref_view, const apde_params *params, int scale_size, uint32_t seed);
@@ -187,6 +192,11 @@ typedef struct {
 } apde_schedule;
 
 void apde_schedule_default(apde_schedule *s);
+/* the PatchMatchParams, scale and seed that pass `pass_index` of the schedule uses for every view (main.cpp:309-365), for
+ * drivers that need to step through a pass view by view (apde_problem_setup / run / get / finish), e.g. to export the
+ * anchors and the reliable curve of the last iteration as the reference does (main.cpp:353-358) */
+int apde_schedule_pass_params(apde_context *ctx, const apde_schedule *s, int pass_index, apde_params *params, int *scale_size,
+                              uint32_t *seed);
 
 typedef struct {
     double patchmatch_ms; /* device time of all RunPatchMatch stages (CUDA events; == the reference's "RunPatchMatch time") */

@@ -184,3 +184,46 @@ def test_cli_against_the_reference_main(tmp_path, dataset, W, H, weak, rounds):
     assert min(agree) >= min(0.99, min(self_agree) - 0.01)
     assert max(dshare) < 0.05
     assert abs(n_o - n_a) <= max(0.03 * n_a, 3 * abs(n_a - n_b))
+
+
+def test_apd_cli_export_anchor_and_curve(tmp_path):
+    """--export_anchor / --export_curve (main.cpp:353-358): anchors_map.bin, anchors.bin and reliable_curve.bin of the last
+    iteration in the reference's layouts (APD.cu:2614-2627, 2651-2661), and the same maps as a run without the exports"""
+    import shutil
+    from apde_mvs_b200 import build as b
+    from apde_mvs_b200.scene import make_office_scene
+    b.build_host()
+    V, W, H = 3, 960, 720
+    scene = make_office_scene(W, H, num_views=V, num_src=2, seed=8, arc_deg=12.0, weak=0.3)
+    d0, d1 = tmp_path / "plain", tmp_path / "export"
+    scene.write_dense_folder(str(d0))
+    shutil.copytree(d0, d1)
+    apd = os.path.join(ROOT, "apde_mvs_b200", "_build", "apd")
+    for d, extra in ((d0, []), (d1, ["--export_anchor", "true", "--export_curve", "true"])):
+        out = subprocess.run([apd, "-d", str(d), "--no_fuse", "true"] + extra, capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout[-1500:]
+    for v in range(V):
+        r0, r1 = d0 / "APD" / ("%08d" % v), d1 / "APD" / ("%08d" % v)
+        for name in ("depths.bin", "normals.bin", "weak.bin", "confidence.bin"):
+            assert open(r0 / name, "rb").read() == open(r1 / name, "rb").read(), (v, name)  # the export path changes nothing
+        with open(r1 / "anchors_map.bin", "rb") as f:
+            version, rows, cols, typ = struct.unpack("<4i", f.read(16))
+            amap = np.frombuffer(f.read(), np.int32).reshape(rows, cols)
+        assert (version, rows, cols, typ) == (1, H, W, 4)
+        raw = open(r1 / "anchors.bin", "rb").read()
+        weak_count, num = struct.unpack("<2i", raw[:8])
+        anchors = np.frombuffer(raw[8:], np.int16).reshape(weak_count, num, 2)
+        assert num == 9 and weak_count == (amap >= 0).sum() and weak_count > 1000
+        ys, xs = np.nonzero(amap >= 0)
+        assert np.array_equal(amap[ys, xs], np.arange(weak_count))           # running index in row-major order
+        assert np.array_equal(anchors[:, 0, 0], xs) and np.array_equal(anchors[:, 0, 1], ys)  # anchor 0 = the pixel itself
+        rest = anchors[:, 1:]
+        ok = ((rest[..., 0] == -1) & (rest[..., 1] == -1)) | ((rest[..., 0] >= 0) & (rest[..., 0] < W) & (rest[..., 1] >= 0) & (rest[..., 1] < H))
+        assert ok.all() and (rest[..., 0] >= 0).mean() > 0.3
+        raw = open(r1 / "reliable_curve.bin", "rb").read()
+        cw, ch, cn = struct.unpack("<3i", raw[:12])
+        curve = np.frombuffer(raw[12:], np.float32).reshape(ch, cw, cn)
+        assert (cw, ch, cn) == (W, H, 61)
+        inner = curve[6:-6, 6:-6]
+        assert np.isfinite(inner).all() and inner.min() >= 0.0 and inner.max() <= 2.0 and (inner > 0).mean() > 0.5
+        assert not curve[:6].any()  # the 6-pixel border is never swept (APD.cu:2114)
