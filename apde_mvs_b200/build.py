@@ -62,7 +62,7 @@ APD_TEST_BIN = os.path.join(OUT_DIR, "test_apd_class")
 def build_host():
     """C++17 host side of the drop-in surface: the APD class, the I/O layer and the `apd` CLI, linked against libapde.so"""
     lib = build()
-    common = [os.path.join(HOST_DIR, f) for f in ("apd_io.cpp", "apd_jpeg.cpp", "APD.cpp")]
+    common = [os.path.join(HOST_DIR, f) for f in ("apd_io.cpp", "apd_jpeg.cpp", "apd_show.cpp", "APD.cpp")]
     hdrs = [os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR)]
     for out, main_src in ((APD_BIN, "main.cpp"), (APD_TEST_BIN, "test_apd_class.cpp"), (os.path.join(OUT_DIR, "test_io"), "test_io.cpp")):
         srcs = common + [os.path.join(HOST_DIR, main_src)]

@@ -2,6 +2,7 @@
 //   ReadBinMat / WriteBinMat   ".bin" maps ("dmb": int32 version=1, rows, cols, cv type + raw rows)  APD.cpp:18-83
 //   ReadCamera                 MVSNet *_cam.txt                                                     APD.cpp:85-135
 //   ReadImage / ReadImageColor PNG (zlib inflate) / JPEG (apd_jpeg.cpp) / PGM / PPM, pixel-identical to cv::imread   APD.cpp:137-160
+//   Show*                      depth_k.jpg / normal_k.jpg / weak_k.png / confidence_k.png (apd_show.cpp)         APD.cpp:162-314
 //   ExportPointCloud           binary little-endian PLY, float xyz + uchar blue green red             APD.cpp:316-356
 //   GenerateSampleList         pair.txt -> Problem list                                              main.cpp:44-102
 #pragma once
@@ -48,6 +49,13 @@ bool ReadImage(const path &img_path, Mat &gray_u8);         // CV_8UC1 (the libr
 bool ReadImageColor(const path &img_path, Mat &bgr_u8);     // CV_8UC3, BGR order as cv::imread(IMREAD_COLOR)
 bool WritePGM(const path &p, const Mat &gray_u8);
 bool WritePNG(const path &p, const Mat &img_u8);             // CV_8UC1 or CV_8UC3 (BGR), what cv::imwrite("*.png") stores
+bool WriteJPEG(const path &p, const Mat &img_u8, int quality = 95);  // baseline JPEG, CV_8UC1 or CV_8UC3 (BGR)
+// debug imagery of the last geometric iteration of a round (APD.cpp:162-314, main.cpp:191-204)
+bool ShowDepthMap(const path &depth_path, const Mat &depth, float depth_min, float depth_max);
+bool ShowNormalMap(const path &normal_path, const Mat &normal);
+bool ShowWeakImage(const path &weak_path, const Mat &weak);
+bool ShowConfidenceMap(const path &confidence_path, const Mat &confidence);
+void JetColorMap(uint8_t bgr[256][3]);  // cv::COLORMAP_JET
 bool ExportPointCloud(const path &ply_path, const std::vector<PointList> &pc, bool export_color = true);
 std::string ToFormatIndex(int index);
 

@@ -11,6 +11,7 @@
 //   * EXIF orientation (cv::imread applies it unless IMREAD_IGNORE_ORIENTATION is passed; the reference does not pass it).
 // Pinned against cv2 (libjpeg-turbo) in tests/test_host_io.py: grey and colour, 4:4:4 / 4:2:2 / 4:2:0, baseline,
 // progressive, restart markers, odd sizes.
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -638,6 +639,138 @@ bool decode_jpeg(const std::vector<uint8_t> &f, bool want_color, int &w, int &h,
         channels = 1;
     }
     apply_orientation(J.orientation, w, h, channels, pix);
+    return true;
+}
+
+}  // namespace apd
+
+// ------------------------------------------------------------------------------------------------ encoder
+// Baseline JPEG writer for the debug imagery of the drop-in (depth_k.jpg, normal_k.jpg: APD.cpp:162-230, 265-287): 8-bit,
+// 4:4:4, the Annex K quantisation tables at OpenCV's default quality 95, and one flat prefix code per class (every DC
+// category 4 bits, every AC (run, size) symbol 8 bits) declared in the DHT segments -- valid for any decoder, a little larger
+// than with tuned tables, and free of transcribed 162-entry tables.
+namespace apd {
+namespace {
+
+struct BitWriter {
+    std::vector<uint8_t> &out;
+    uint32_t acc = 0;
+    int n = 0;
+    explicit BitWriter(std::vector<uint8_t> &o) : out(o) {}
+    void put(uint32_t code, int len) {
+        acc = (acc << len) | (code & ((1u << len) - 1u));
+        n += len;
+        while (n >= 8) {
+            const uint8_t b = (uint8_t)(acc >> (n - 8));
+            out.push_back(b);
+            if (b == 0xFF) out.push_back(0);
+            n -= 8;
+        }
+    }
+    void flush() { if (n) put(0x7F, 8 - n); }
+};
+
+const uint8_t kStdLumaQ[64] = {16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57, 69, 56,
+                               14, 17, 22, 29, 51, 87, 80, 62, 18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64, 81, 104, 113, 92,
+                               49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+const uint8_t kStdChromaQ[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99, 99, 99,
+                                 47, 66, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
+                                 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
+
+// AC symbols of baseline JPEG: EOB, ZRL and (run 0..15, size 1..10); flat 8-bit codes in this order
+int ac_symbol_index(int sym) {
+    if (sym == 0x00) return 0;
+    if (sym == 0xF0) return 1;
+    return 2 + (sym >> 4) * 10 + ((sym & 15) - 1);
+}
+
+}  // namespace
+
+bool encode_jpeg(int w, int h, int channels, const uint8_t *pix /* grey or BGR */, int quality, std::vector<uint8_t> &out) {
+    if (w <= 0 || h <= 0 || (channels != 1 && channels != 3) || w > 65535 || h > 65535) return false;
+    quality = quality < 1 ? 1 : quality > 100 ? 100 : quality;
+    const int scale = quality < 50 ? 5000 / quality : 200 - 2 * quality;
+    uint8_t q[2][64];
+    for (int t = 0; t < 2; ++t)
+        for (int i = 0; i < 64; ++i) {
+            const int v = ((t ? kStdChromaQ[i] : kStdLumaQ[i]) * scale + 50) / 100;
+            q[t][i] = (uint8_t)(v < 1 ? 1 : v > 255 ? 255 : v);
+        }
+    auto be16 = [&](int v) { out.push_back((uint8_t)(v >> 8)); out.push_back((uint8_t)v); };
+    out.clear();
+    out.push_back(0xFF); out.push_back(0xD8);
+    static const uint8_t jfif[] = {0xFF, 0xE0, 0, 16, 'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0};
+    out.insert(out.end(), jfif, jfif + sizeof(jfif));
+    for (int t = 0; t < (channels == 3 ? 2 : 1); ++t) {
+        out.push_back(0xFF); out.push_back(0xDB); be16(67); out.push_back((uint8_t)t);
+        for (int i = 0; i < 64; ++i) out.push_back(q[t][kZigzag[i]]);
+    }
+    out.push_back(0xFF); out.push_back(0xC0); be16(8 + 3 * channels); out.push_back(8); be16(h); be16(w); out.push_back((uint8_t)channels);
+    for (int c = 0; c < channels; ++c) { out.push_back((uint8_t)(c + 1)); out.push_back(0x11); out.push_back((uint8_t)(c ? 1 : 0)); }
+    // DHT: DC table 0 = 12 categories with 4-bit codes 0..11; AC table 0 = 162 symbols with 8-bit codes 0..161
+    out.push_back(0xFF); out.push_back(0xC4); be16(2 + 1 + 16 + 12); out.push_back(0x00);
+    for (int l = 1; l <= 16; ++l) out.push_back((uint8_t)(l == 4 ? 12 : 0));
+    for (int i = 0; i < 12; ++i) out.push_back((uint8_t)i);
+    out.push_back(0xFF); out.push_back(0xC4); be16(2 + 1 + 16 + 162); out.push_back(0x10);
+    for (int l = 1; l <= 16; ++l) out.push_back((uint8_t)(l == 8 ? 162 : 0));
+    out.push_back(0x00); out.push_back(0xF0);
+    for (int r = 0; r < 16; ++r) for (int s = 1; s <= 10; ++s) out.push_back((uint8_t)((r << 4) | s));
+    out.push_back(0xFF); out.push_back(0xDA); be16(6 + 2 * channels); out.push_back((uint8_t)channels);
+    for (int c = 0; c < channels; ++c) { out.push_back((uint8_t)(c + 1)); out.push_back(0x00); }
+    out.push_back(0); out.push_back(63); out.push_back(0);
+
+    float ct[8][8];
+    for (int u = 0; u < 8; ++u)
+        for (int x = 0; x < 8; ++x) ct[u][x] = (float)((u == 0 ? std::sqrt(0.125) : 0.5) * std::cos((2 * x + 1) * u * 3.14159265358979323846 / 16.0));
+    BitWriter bw(out);
+    int pred[3] = {0, 0, 0};
+    for (int by = 0; by < h; by += 8)
+        for (int bx = 0; bx < w; bx += 8)
+            for (int c = 0; c < channels; ++c) {
+                float blk[64], tmp[64];
+                for (int y = 0; y < 8; ++y)
+                    for (int x = 0; x < 8; ++x) {
+                        const int sy = by + y < h ? by + y : h - 1, sx = bx + x < w ? bx + x : w - 1;
+                        const uint8_t *p = pix + ((size_t)sy * w + sx) * channels;
+                        float v;
+                        if (channels == 1) v = p[0];
+                        else {
+                            const float B = p[0], G = p[1], R = p[2];
+                            v = c == 0 ? 0.299f * R + 0.587f * G + 0.114f * B
+                                       : c == 1 ? -0.168736f * R - 0.331264f * G + 0.5f * B + 128.0f : 0.5f * R - 0.418688f * G - 0.081312f * B + 128.0f;
+                        }
+                        blk[y * 8 + x] = v - 128.0f;
+                    }
+                for (int y = 0; y < 8; ++y)
+                    for (int u = 0; u < 8; ++u) { float s = 0; for (int x = 0; x < 8; ++x) s += ct[u][x] * blk[y * 8 + x]; tmp[y * 8 + u] = s; }
+                for (int u = 0; u < 8; ++u)
+                    for (int v = 0; v < 8; ++v) { float s = 0; for (int y = 0; y < 8; ++y) s += ct[v][y] * tmp[y * 8 + u]; blk[v * 8 + u] = s; }
+                int zz[64];
+                const uint8_t *qt = q[c ? 1 : 0];
+                for (int i = 0; i < 64; ++i) zz[i] = (int)std::lrint(blk[kZigzag[i]] / qt[kZigzag[i]]);
+                auto category = [](int v) { int a = v < 0 ? -v : v, n = 0; while (a) { ++n; a >>= 1; } return n; };
+                auto bits_of = [](int v, int n) { return (uint32_t)(v < 0 ? v + (1 << n) - 1 : v); };
+                const int diff = zz[0] - pred[c];
+                pred[c] = zz[0];
+                int n = category(diff);
+                bw.put((uint32_t)n, 4);
+                if (n) bw.put(bits_of(diff, n), n);
+                int run = 0;
+                for (int i = 1; i < 64; ++i) {
+                    int v = zz[i];
+                    if (v > 1023) v = 1023;
+                    if (v < -1023) v = -1023;
+                    if (v == 0) { ++run; continue; }
+                    while (run > 15) { bw.put((uint32_t)ac_symbol_index(0xF0), 8); run -= 16; }
+                    n = category(v);
+                    bw.put((uint32_t)ac_symbol_index((run << 4) | n), 8);
+                    bw.put(bits_of(v, n), n);
+                    run = 0;
+                }
+                if (run) bw.put((uint32_t)ac_symbol_index(0x00), 8);
+            }
+    bw.flush();
+    out.push_back(0xFF); out.push_back(0xD9);
     return true;
 }
 

@@ -1,5 +1,7 @@
 // test_io.cpp -- CPU-only exerciser of the host I/O layer for tests/test_host_io.py (no GPU calls; links libapde only for symbols)
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <iostream>
 
 #include "apd_io.h"
@@ -27,6 +29,29 @@ int main(int argc, char **argv) {
         Mat g;
         if (!ReadImage(argv[2], g)) return 1;
         return WritePNG(argv[3], g) ? 0 : 1;
+    }
+    if (cmd == "jpg") {  // jpg <image> <out.jpg> [quality]: colour round trip through WriteJPEG
+        Mat c;
+        if (!ReadImageColor(argv[2], c)) return 1;
+        return WriteJPEG(argv[3], c, argc > 4 ? atoi(argv[4]) : 95) ? 0 : 1;
+    }
+    if (cmd == "grayjpg") {  // grayjpg <image> <out.jpg>
+        Mat g;
+        if (!ReadImage(argv[2], g)) return 1;
+        return WriteJPEG(argv[3], g) ? 0 : 1;
+    }
+    if (cmd == "show") {  // show <dir with depths/normals/weak/confidence.bin> <depth_min> <depth_max>: the four Show* pictures
+        const path dir = argv[2];
+        Mat depth, normal, weak, conf;
+        if (!ReadBinMat(dir / "depths.bin", depth) || !ReadBinMat(dir / "normals.bin", normal) || !ReadBinMat(dir / "weak.bin", weak) ||
+            !ReadBinMat(dir / "confidence.bin", conf)) return 1;
+        const bool ok = ShowDepthMap(dir / "depth_3.jpg", depth, (float)atof(argv[3]), (float)atof(argv[4])) && ShowNormalMap(dir / "normal_3.jpg", normal) &&
+                        ShowWeakImage(dir / "weak_3.png", weak) && ShowConfidenceMap(dir / "confidence_3.png", conf);
+        uint8_t jet[256][3];
+        JetColorMap(jet);
+        Mat j(1, 256, CV_8UC3);
+        memcpy(j.data(), jet, sizeof(jet));
+        return ok && WriteBinMat(dir / "jet.bin", j) ? 0 : 1;
     }
     if (cmd == "cam") {  // cam <cam.txt>
         Camera cam;

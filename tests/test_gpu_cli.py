@@ -52,6 +52,17 @@ def test_apd_cli_end_to_end(dense):
         import cv2
         skip = cv2.imread(str(d / "APD" / ("%08d" % v) / "skip.png"), cv2.IMREAD_UNCHANGED)  # WeakVisFilter mask, APD.cpp:1035
         assert skip is not None and skip.shape == (192, 256) and set(np.unique(skip)) <= {0, 255}
+        # show_medium_result on the last geometric iteration of the round (iteration 3): main.cpp:191-204, APD.cpp:162-314
+        r = d / "APD" / ("%08d" % v)
+        wk = cv2.imread(str(r / "weak_3.png"), cv2.IMREAD_COLOR)
+        assert np.array_equal(wk, np.array([[255, 255, 255], [0, 255, 0], [0, 0, 255]], np.uint8)[weak])
+        cf = cv2.imread(str(r / "confidence_3.png"), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(cf, ((conf.astype(int) - conf.min()) * 255 // max(int(conf.max()) - int(conf.min()), 1)).astype(np.uint8))
+        nm = cv2.imread(str(r / "normal_3.jpg"), cv2.IMREAD_COLOR)
+        want = np.clip(np.rint(normal * np.float32(127.5) + np.float32(127.5)), 0, 255)
+        assert nm.shape == (192, 256, 3) and np.abs(nm - want).mean() < 3
+        assert cv2.imread(str(r / "depth_3.jpg"), cv2.IMREAD_COLOR).shape == (192, 256, 3)
+        assert not (r / "depth_0.jpg").exists()  # photometric iterations write no pictures (main.cpp:327)
     raw = open(d / "APD" / "APD.ply", "rb").read()
     head, body = raw.split(b"end_header\n")
     n = int(head.split(b"element vertex ")[1].split(b"\n")[0])

@@ -148,3 +148,95 @@ def test_camera_pairs_ply(tool, tmp_path):
     head, body = raw.split(b"end_header\n")
     assert b"element vertex 2" in head and b"property uchar blue" in head and b"format binary_little_endian 1.0" in head
     assert len(body) == 2 * 15 and struct.unpack("<3f3B", body[:15]) == (1.5, -2.0, 3.25, 10, 20, 30)
+
+
+def _write_bin(p, a, typ):
+    with open(p, "wb") as f:
+        f.write(struct.pack("<4i", 1, a.shape[0], a.shape[1], typ))
+        f.write(np.ascontiguousarray(a).tobytes())
+
+
+def test_jpeg_writer_is_decodable_and_close(tool, tmp_path):
+    """WriteJPEG (depth_k.jpg / normal_k.jpg, APD.cpp:228,286): baseline 4:4:4 files that libjpeg decodes, as close to the
+    source as cv2's own quality-95 files"""
+    import cv2
+    rng = np.random.default_rng(5)
+    for name, (w, h) in {"a": (67, 45), "b": (64, 64), "c": (1, 1), "d": (17, 8)}.items():
+        img = _natural(w, h, rng)
+        cv2.imwrite(str(tmp_path / f"{name}.png"), img)
+        subprocess.check_call([tool, "jpg", str(tmp_path / f"{name}.png"), str(tmp_path / f"{name}.jpg")])
+        got = cv2.imread(str(tmp_path / f"{name}.jpg"), cv2.IMREAD_COLOR)
+        assert got.shape == img.shape
+        cv2.imwrite(str(tmp_path / f"{name}_cv.jpg"), img, [cv2.IMWRITE_JPEG_QUALITY, 95])
+        ref = cv2.imread(str(tmp_path / f"{name}_cv.jpg"), cv2.IMREAD_COLOR)
+        err, err_cv = np.abs(got.astype(int) - img).mean(), np.abs(ref.astype(int) - img).mean()
+        assert err <= err_cv + (0.25 if w * h > 64 else 1.0) and np.abs(got.astype(int) - img).max() <= np.abs(ref.astype(int) - img).max() + 4, (name, err, err_cv)
+        # our own decoder reads it back identically to libjpeg
+        subprocess.check_call([tool, "color", str(tmp_path / f"{name}.jpg"), str(tmp_path / f"{name}.bin")])
+        assert np.array_equal(_read_bin(tmp_path / f"{name}.bin")[0], got)
+        gray = img[..., 1].copy()
+        cv2.imwrite(str(tmp_path / f"{name}_g.png"), gray)
+        subprocess.check_call([tool, "grayjpg", str(tmp_path / f"{name}_g.png"), str(tmp_path / f"{name}_g.jpg")])
+        gg = cv2.imread(str(tmp_path / f"{name}_g.jpg"), cv2.IMREAD_UNCHANGED)
+        assert gg.shape == gray.shape and np.abs(gg.astype(int) - gray).max() <= 10
+    # hard case: white noise at quality 100 (large coefficients, long zero runs absent)
+    noise = rng.integers(0, 256, (40, 56, 3), dtype=np.uint8)
+    cv2.imwrite(str(tmp_path / "n.png"), noise)
+    subprocess.check_call([tool, "jpg", str(tmp_path / "n.png"), str(tmp_path / "n.jpg"), "100"])
+    assert np.abs(cv2.imread(str(tmp_path / "n.jpg")).astype(int) - noise).max() <= 6
+    # flat picture: every AC coefficient zero (EOB-only blocks) and 16+ zero runs
+    flat = np.full((24, 40, 3), 200, np.uint8)
+    flat[20:, 36:] = 10
+    cv2.imwrite(str(tmp_path / "f.png"), flat)
+    subprocess.check_call([tool, "jpg", str(tmp_path / "f.png"), str(tmp_path / "f.jpg")])
+    assert np.abs(cv2.imread(str(tmp_path / "f.jpg")).astype(int) - flat)[:16, :32].max() <= 1
+
+
+def test_show_pictures_follow_the_reference(tool, tmp_path):
+    """ShowDepthMap / ShowNormalMap / ShowWeakImage / ShowConfidenceMap (APD.cpp:162-314) against OpenCV's own operators"""
+    import cv2
+    rng = np.random.default_rng(9)
+    h, w = 48, 72
+    y, x = np.mgrid[0:h, 0:w]
+    depth = (4 + 0.02 * x - 0.015 * y + 0.3 * np.sin(x / 6.0)).astype(np.float32)
+    depth[rng.random((h, w)) < 0.1] = 0  # invalid pixels are excluded from the statistics
+    normal = rng.normal(size=(h, w, 3)).astype(np.float32)
+    normal /= np.linalg.norm(normal, axis=2, keepdims=True)
+    normal[depth == 0] = 0
+    weak = rng.integers(0, 3, (h, w), dtype=np.uint8)
+    conf = rng.integers(3, 200, (h, w), dtype=np.uint8)
+    _write_bin(tmp_path / "depths.bin", depth, 5)
+    _write_bin(tmp_path / "normals.bin", normal, 21)
+    _write_bin(tmp_path / "weak.bin", weak, 0)
+    _write_bin(tmp_path / "confidence.bin", conf, 0)
+    dmin, dmax = 2.0 * 0.6, 8.0 * 1.2
+    subprocess.check_call([tool, "show", str(tmp_path), repr(dmin), repr(dmax)])
+    # the colour map is cv::COLORMAP_JET entry for entry
+    jet, _ = _read_bin(tmp_path / "jet.bin")
+    assert np.array_equal(jet.reshape(256, 3), cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, 256), cv2.COLORMAP_JET).reshape(256, 3))
+    # depth: mean of column means, sigma from the mean of column variances, ramp over mean +- 2 sigma, jet (APD.cpp:164-227)
+    ok = (depth >= dmin) & (depth <= dmax)
+    cols = [c for c in range(w) if ok[:, c].any()]
+    mean = np.float32(np.mean([depth[ok[:, c], c].mean() for c in cols]))
+    sigma = np.sqrt(np.mean([((depth[ok[:, c], c] - mean) ** 2).mean() for c in cols]))
+    lo = mean - 2 * sigma
+    gray = (np.clip((depth - lo) / (4 * sigma), 0, 1) * 255).astype(np.uint8)
+    want = cv2.applyColorMap(gray, cv2.COLORMAP_JET)
+    got = cv2.imread(str(tmp_path / "depth_3.jpg"), cv2.IMREAD_COLOR)
+    cv2.imwrite(str(tmp_path / "depth_cv.jpg"), want)
+    base = np.abs(cv2.imread(str(tmp_path / "depth_cv.jpg")).astype(int) - want).mean()
+    assert got.shape == want.shape and np.abs(got.astype(int) - want).mean() <= base + 0.5
+    # normals: unit vector * 127.5 + 127.5, rounded as Mat::convertTo does
+    want_n = np.empty((h, w, 3), np.uint8)
+    cv2.convertScaleAbs(normal, want_n, 1)  # placeholder to get the array type; real values below
+    want_n = np.clip(np.rint(normal * np.float32(127.5) + np.float32(127.5)), 0, 255).astype(np.uint8)
+    got_n = cv2.imread(str(tmp_path / "normal_3.jpg"), cv2.IMREAD_COLOR)
+    cv2.imwrite(str(tmp_path / "normal_cv.jpg"), want_n)
+    base_n = np.abs(cv2.imread(str(tmp_path / "normal_cv.jpg")).astype(int) - want_n).mean()
+    assert np.abs(got_n.astype(int) - want_n).mean() <= base_n + 0.5
+    # the two PNGs are lossless: exact
+    colours = np.array([[255, 255, 255], [0, 255, 0], [0, 0, 255]], np.uint8)  # WEAK, STRONG, UNKNOWN in BGR (APD.cpp:298-308)
+    assert np.array_equal(cv2.imread(str(tmp_path / "weak_3.png"), cv2.IMREAD_COLOR), colours[weak])
+    lo_c, hi_c = int(conf.min()), int(conf.max())
+    want_c = ((conf.astype(int) - lo_c) * 255 // max(hi_c - lo_c, 1)).astype(np.uint8)
+    assert np.array_equal(cv2.imread(str(tmp_path / "confidence_3.png"), cv2.IMREAD_UNCHANGED), want_c)
