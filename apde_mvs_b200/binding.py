@@ -67,6 +67,7 @@ class Schedule(C.Structure):
     _fields_ = [
         ("rounds", C.c_int), ("geom_iterations", C.c_int), ("jacobi", C.c_int), ("use_impetus", C.c_int),
         ("geom_factor", C.c_float), ("seed", C.c_uint32), ("first_view", C.c_int), ("num_views_local", C.c_int),
+        ("use_sa", C.c_int),
     ]
 
 
@@ -90,6 +91,7 @@ class POOL:
 class FIELD:
     PLANES, COSTS, SELECTED_VIEWS, VIEW_WEIGHT, WEAK_INFO, CONFIDENCE, FIT_PLANES, WEAK_RELIABLE, NEAREST_STRONG, \
         ANCHORS, IMAGE, SRC_DEPTH = range(12)
+    RELIABLE_CURVE, SA_MASK = 12, 13
 
 
 FIRST_INIT, REFINE_INIT, REFINE_ITER = 0, 1, 2
@@ -118,6 +120,7 @@ def load_library(path=None):
     lib.apde_scene_begin.argtypes = [P, C.c_int, C.c_int, C.c_int]
     lib.apde_scene_set_view.argtypes = [P, C.c_int, P, P, C.POINTER(Camera)]
     lib.apde_scene_set_pairs.argtypes = [P, C.c_int, C.c_int, P]
+    lib.apde_view_set_sa_mask.argtypes = [P, C.c_int, P, C.c_int, C.c_int]
     lib.apde_scene_commit.argtypes = [P]
     lib.apde_view_download.argtypes = [P, C.c_int, P, P, P, P, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.apde_view_upload.argtypes = [P, C.c_int, P, P, P, P, C.c_int, C.c_int]
@@ -168,7 +171,7 @@ _FIELD_DTYPE = {
     FIELD.PLANES: (np.float32, 4), FIELD.COSTS: (np.float32, 1), FIELD.SELECTED_VIEWS: (np.uint32, 1),
     FIELD.VIEW_WEIGHT: (np.uint8, 32), FIELD.WEAK_INFO: (np.uint8, 1), FIELD.CONFIDENCE: (np.uint8, 1),
     FIELD.FIT_PLANES: (np.float32, 4), FIELD.WEAK_RELIABLE: (np.uint8, 1), FIELD.NEAREST_STRONG: (np.int16, 2),
-    FIELD.ANCHORS: (np.int16, 2 * ANCHOR_NUM), FIELD.IMAGE: (np.float32, 1),
+    FIELD.ANCHORS: (np.int16, 2 * ANCHOR_NUM), FIELD.IMAGE: (np.float32, 1), FIELD.SA_MASK: (np.uint8, 1),
 }
 
 
@@ -230,6 +233,14 @@ class Context:
             self.scene_set_view(v, scene.images[v], scene.cameras[v], scene.colors[v] if scene.colors else None)
             self.scene_set_pairs(v, scene.pairs[v])
         self.scene_commit()
+
+    def view_set_sa_mask(self, view, labels):
+        """segment-label map of a view (uint8 [h, w] of any size, as in sa_masks/<id>.bin); None removes it"""
+        if labels is None:
+            self._check(self.lib.apde_view_set_sa_mask(self._h, view, None, 0, 0))
+            return
+        a = np.ascontiguousarray(labels, np.uint8)
+        self._check(self.lib.apde_view_set_sa_mask(self._h, view, _ptr(a), a.shape[1], a.shape[0]))
 
     def view_download(self, view):
         w, h = C.c_int(), C.c_int()

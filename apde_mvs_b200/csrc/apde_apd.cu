@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(128) k_ransac_fit(const __grid_constant__ Pass
 // -------------------------------------------------------------------------------------------- K8 weak propagation
 // Black/RedPixelUpdateWeak -> CheckerboardPropagationWeak -> PlaneHypothesisRefinementWeak,
 // APD.cu:1617-1652, 1442-1615, 1008-1096
-template <bool U>
+template <bool U, bool SA>
 __device__ __forceinline__ void k_prop_weak_body(const PassK &K, int iter, int color, int tiles_x,
                                                    int ylimit) {
     extern __shared__ float smem[];
@@ -331,8 +331,10 @@ __device__ __forceinline__ void k_prop_weak_body(const PassK &K, int iter, int c
 
     RefPatch rp;
     load_ref_patch<U>(K, px, py, rp);
-    AnchorRef ar;
-    load_anchor_ref<U>(K, anc, ar);
+    typename SaTypes<SA>::Info si;
+    load_sa<SA>(K, px, py, rp, si);
+    typename SaTypes<SA>::Anchors ar;
+    load_anchor_ref_x<U, SA>(K, anc, ar, si);
     unsigned n_new = 0, n_geom = 0;
 
     unsigned flags = 0, anchor_valid = 0;
@@ -353,7 +355,7 @@ __device__ __forceinline__ void k_prop_weak_body(const PassK &K, int iter, int c
         if (ok) {
             const float3 m = plane_row(K, K.planes[pos[h]]);
 #pragma unroll 1
-            for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_new<U>(K, K.v[v], v, px, py, m, rp, ar);
+            for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_new_x<U, SA>(K, K.v[v], v, px, py, m, rp, ar, si);
             n_new += N;
         } else {
             for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = (h == 0 && v == 0) ? 2.0f : 0.0f;
@@ -400,7 +402,7 @@ __device__ __forceinline__ void k_prop_weak_body(const PassK &K, int iter, int c
         float acc = 0.0f;
         for (uint32_t mk = wmask; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            float c = ncc_new<U>(K, s_vk[v], v, px, py, m, rp, ar);
+            float c = ncc_new_x<U, SA>(K, s_vk[v], v, px, py, m, rp, ar, si);
             n_new++;
             if (use_geom) { c = c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, plane_c); n_geom++; }
             acc += (float)vw_get(w, v) * c;
@@ -446,7 +448,7 @@ __device__ __forceinline__ void k_prop_weak_body(const PassK &K, int iter, int c
             float acc = 0.0f;
             for (uint32_t mk = wmask; mk; mk &= mk - 1) {
                 const int v = __ffs(mk) - 1;
-                float c = ncc_new<U>(K, s_vk[v], v, px, py, m, rp, ar);
+                float c = ncc_new_x<U, SA>(K, s_vk[v], v, px, py, m, rp, ar, si);
                 n_new++;
                 if (use_geom) { c = c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp); n_geom++; }
                 acc += (float)vw_get(w, v) * c;
@@ -467,8 +469,14 @@ __device__ __forceinline__ void k_prop_weak_body(const PassK &K, int iter, int c
 }
 __global__ void __launch_bounds__(128) k_prop_weak(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
                                                    int ylimit) {
-    if (K.tex_unorm > 0.0f) k_prop_weak_body<true>(K, iter, color, tiles_x, ylimit);
-    else k_prop_weak_body<false>(K, iter, color, tiles_x, ylimit);
+    if (K.tex_unorm > 0.0f) k_prop_weak_body<true, false>(K, iter, color, tiles_x, ylimit);
+    else k_prop_weak_body<false, false>(K, iter, color, tiles_x, ylimit);
+}
+// the same kernel for a problem with a segment-label map (see "segment labels" in apde_device.cuh)
+__global__ void __launch_bounds__(128) k_prop_weak_sa(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
+                                                      int ylimit) {
+    if (K.tex_unorm > 0.0f) k_prop_weak_body<true, true>(K, iter, color, tiles_x, ylimit);
+    else k_prop_weak_body<false, true>(K, iter, color, tiles_x, ylimit);
 }
 
 
@@ -502,12 +510,14 @@ cudaError_t launch_stage_apd(const PassK &K, int stage, int iter, int color, cud
             static size_t configured = 0;
             if (smem > configured) {
                 cudaError_t e = cudaFuncSetAttribute(k_prop_weak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_prop_weak_sa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
                 configured = smem;
             }
             const int tiles = tiles8x * ((ylimit + 7) / 8);
             const int wpb = threads / 32;
-            k_prop_weak<<<(tiles + wpb - 1) / wpb, threads, smem, st>>>(K, iter, color, tiles8x, ylimit);
+            if (K.sa) k_prop_weak_sa<<<(tiles + wpb - 1) / wpb, threads, smem, st>>>(K, iter, color, tiles8x, ylimit);
+            else k_prop_weak<<<(tiles + wpb - 1) / wpb, threads, smem, st>>>(K, iter, color, tiles8x, ylimit);
             break;
         }
         default:

@@ -42,6 +42,8 @@ struct ViewStore {
     apde_camera cam;
     std::vector<int> src;
     uint8_t *d_gray = nullptr, *d_bgr = nullptr;
+    uint8_t *d_sa = nullptr;  // segment labels as read from sa_masks/<id>.bin (own size saw x sah), nullptr = none
+    int saw = 0, sah = 0;
     int mw = 0, mh = 0;  // size of the stored maps (0 = none yet)
     int dw = 0, dh = 0;  // size of this view's depth map in the READABLE pool d_depth_pool[cur]: equal to mw x mh, except in
                          // Jacobi mode between a view's finish and the end of the pass (the new map went to the other pool)
@@ -85,6 +87,7 @@ struct apde_context {
     // problem working set (allocated once at full resolution)
     bool ws_alloc = false;
     float4 *d_planes = nullptr, *d_fit = nullptr;
+    uint8_t *d_sa = nullptr;  // segment labels of the active problem's reference view at the working size
     float *d_costs = nullptr, *d_depthws = nullptr, *d_scratch_depth = nullptr, *d_scratch_normal = nullptr;
     uint32_t *d_sel = nullptr;
     uint4 *d_vw = nullptr;
@@ -154,6 +157,7 @@ void apde_schedule_default(apde_schedule *s) {
     s->use_impetus = 1;
     s->geom_factor = 0.2f;
     s->seed = 1;
+    s->use_sa = 1;
 }
 
 int apde_create(int device, apde_context **out) {
@@ -189,7 +193,7 @@ static void free_level(apde_context *c) {
 }
 static void free_scene(apde_context *c) {
     for (auto &v : c->views) {
-        cudaFree(v.d_gray); cudaFree(v.d_bgr);
+        cudaFree(v.d_gray); cudaFree(v.d_bgr); cudaFree(v.d_sa);
     }
     c->views.clear();
     cudaFree(c->d_normal_pool); cudaFree(c->d_weak_pool); cudaFree(c->d_conf_pool);
@@ -206,6 +210,8 @@ static void free_scene(apde_context *c) {
     }
     cudaFree(c->d_skip);
     c->d_skip = nullptr;
+    cudaFree(c->d_sa);
+    c->d_sa = nullptr;
     fusion_release_cache();
     c->sweep.release();
     c->prop.release();
@@ -283,6 +289,21 @@ int apde_scene_set_view(apde_context *c, int view, const uint8_t *gray, const ui
     v.cam.width = c->W;
     v.cam.height = c->H;
     CU(cudaStreamSynchronize(c->stream));
+    return APDE_OK;
+}
+
+int apde_view_set_sa_mask(apde_context *c, int view, const uint8_t *labels, int width, int height) {
+    if (!c || view < 0 || view >= c->V) return fail(APDE_ERR_ARG, "view_set_sa_mask: bad argument");
+    CU(cudaSetDevice(c->device));
+    ViewStore &v = c->views[view];
+    cudaFree(v.d_sa);
+    v.d_sa = nullptr; v.saw = v.sah = 0;
+    if (!labels) return APDE_OK;
+    if (width < 1 || height < 1) return fail(APDE_ERR_ARG, "view_set_sa_mask: bad size %d x %d", width, height);
+    CU(cudaMalloc(&v.d_sa, (size_t)width * height));
+    CU(cudaMemcpyAsync(v.d_sa, labels, (size_t)width * height, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    v.saw = width; v.sah = height;
     return APDE_OK;
 }
 
@@ -583,6 +604,12 @@ int apde_problem_setup(apde_context *c, int ref_view, const apde_params *params,
         CU(launch_resize_nearest(rv.d_conf, rv.mw, rv.mh, c->d_conf, w, h, 1, st));
         CU(cudaMemsetAsync(c->d_fit, 0, P * sizeof(float4), st));  // APD.cpp:771
         c->launches += 2;
+        if (c->params.use_sa && rv.d_sa) {  // APD.cpp:641-649: the file's label map, nearest-resized to the working size
+            if (!c->d_sa) CU(cudaMalloc(&c->d_sa, Pfull));
+            CU(launch_resize_nearest(rv.d_sa, rv.saw, rv.sah, c->d_sa, w, h, 1, st));
+            c->launches += 1;
+            K.sa = c->d_sa;
+        }
     } else {  // APD.cpp:656-657
         CU(launch_fill_u8(c->d_weak, APDE_STRONG, P, st));
         CU(launch_fill_u8(c->d_conf, 1, P, st));
@@ -642,7 +669,8 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
     // N x more parallelism for few pixels); for the dense strong class the fused one-thread-per-pixel kernel is faster (165 vs
     // 179 ms: no intermediate buffers, no second pass over the reference patch).  APDE_PIPELINE_STRONG=1 forces the pipeline.
     static const bool pipe_strong = [] { const char *e = getenv("APDE_PIPELINE_STRONG"); return e && e[0] == '1'; }();
-    const bool pipeline = prop_stage && !legacy_prop && !getenv("APDE_QUAD_KERNELS") && (stage == APDE_STAGE_PROP_WEAK || pipe_strong);
+    // problems with a segment-label map run the thread-per-pixel kernels (their <SA> twins, apde_device.cuh)
+    const bool pipeline = prop_stage && !legacy_prop && !c->K.sa && !getenv("APDE_QUAD_KERNELS") && (stage == APDE_STAGE_PROP_WEAK || pipe_strong);
     if (prop_stage && (c->params.use_APD || pipeline)) {
         // compacted (colour, class) pixel lists: no lane idles on the other class, and the column kernels index by list slot
         if (c->lists_dirty) { const int rc = build_lists(c); if (rc) return rc; }
@@ -676,7 +704,7 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
             return prop_half_sweep(Kq, c->prop, stage == APDE_STAGE_PROP_WEAK, Kq.list, Kq.list_count, c->h_list_counts[cls], iter, c->stream,
                                    &c->launches);
         }
-        if (!legacy && !getenv("APDE_QUAD_KERNELS")) {
+        if (!legacy && !Kq.sa && !getenv("APDE_QUAD_KERNELS")) {
             // (the sweep functions count every launch but the last one; the generic count below adds that)
             if (stage == APDE_STAGE_DEPTH_TO_WEAK) {
                 float *curve = nullptr;
@@ -832,6 +860,9 @@ static int field_ptr(apde_context *c, int field, void **ptr, size_t *bytes) {
         case APDE_FIELD_RELIABLE_CURVE:
             if (!c->capture_curve || c->curve_cap < P * 61) return fail(APDE_ERR_STATE, "no reliable curve captured (apde_problem_capture_curve)");
             *ptr = c->d_curve; *bytes = P * 61 * 4; break;
+        case APDE_FIELD_SA_MASK:
+            if (!c->K.sa) return fail(APDE_ERR_STATE, "the active problem has no segment-label map");
+            *ptr = c->d_sa; *bytes = P; break;
         default: return fail(APDE_ERR_ARG, "unknown field %d", field);
     }
     return APDE_OK;
@@ -1043,6 +1074,7 @@ int apde_schedule_pass_params(apde_context *c, const apde_schedule *s, int pass_
     apde_params_default(&p);
     p.geom_factor = s->geom_factor;
     p.use_impetus = s->use_impetus;
+    p.use_sa = s->use_sa;  // main.cpp:324: consumed only for views that have a label map
     p.max_iterations = 3;
     if (i == 0) {
         p.use_APD = 0;

@@ -49,6 +49,7 @@ struct PassK {
     uint16_t *ns_tiles;    // [ceil(H/8)][ceil(W/8)] nearest-strong pruning summary: 0 = no STRONG pixel in the 8x8 tile, else 1 + max confidence
     short2 *anchors;       // [P][9]
     const float *depth;    // [N+1][P] working-resolution depth maps, 0 = ref
+    const uint8_t *sa;     // [P] segment labels of the reference view at this level (sa_masks/*.bin, APD.cpp:641-649); nullptr = all zero
     unsigned long long *counters;
     // compacted pixel lists of the checkerboard kernels (rounds with WEAK pixels): [colour][strong | weak], see k_build_lists
     const int *list;  // nullptr: implicit 8x8-tile mapping
@@ -374,6 +375,286 @@ __device__ __forceinline__ float ncc_new(const PassK &K, const ViewK &vk, int vi
     for (int i = 0; i < ns; ++i) acc += (wts[i] / sum) * sc[i];
     acc = fminf(acc, 2.0f);
     return 0.25f * center_cost + 0.75f * acc;
+}
+
+// ------------------------------------------------------------------------------------------------ segment labels (SAM masks)
+// With a label map (sa_masks/<id>.bin, written by tools/run_SAM.py, consumed when use_sa && use_APD, APD.cpp:641-649) the
+// reference restricts the patches to the centre pixel's segment:
+//   NCC-Old (APD.cu:619-719): branch B is taken when the label AT THE PROJECTED POINT'S INDEX in the reference label map
+//     ("center = pt.y * src_camera.width + pt.x", a float expression truncated to int -- quirk, reproduced) is non-zero.  It
+//     walks the same 36 odd offsets as branch A, quadrant by quadrant in a fixed order, skips taps outside the image and
+//     leaves a quadrant at the first tap of another label.
+//   NCC-New (APD.cu:463-465, 493-497, 526-530): anchors and taps of another label than the (non-zero) centre label are dropped.
+// Which taps take part depends on the pixel only, so the participation masks and the reference-side sums are built once per
+// pixel per kernel (SaInfo / AnchorRefSa) and an evaluation walks the mask.  Kernels carry these in <.., SA = true>
+// instantiations launched only for problems with a label map; the SA = false kernels are unchanged.
+struct SaInfo {
+    unsigned long long bmask;  // NCC-Old branch B: bit t = tap t of the quadrant walk takes part
+    unsigned long long nmask;  // NCC-New centre patch: bit i*6+j (branch A order)
+    float b_mean, b_var, b_inv;
+    float n_mean, n_var, n_inv;
+    int label;
+};
+struct SaNone {};
+
+__device__ __forceinline__ constexpr int sa_b_xoff(int t) {  // APD.cu:665-666
+    const int q = t / 9, j = t % 9;
+    const int ox = (j == 0 || j == 2 || j == 3) ? 1 : (j == 1 || j == 4 || j == 7) ? 3 : 5;
+    return (q == 0 || q == 2) ? ox : -ox;
+}
+__device__ __forceinline__ constexpr int sa_b_yoff(int t) {
+    const int q = t / 9, j = t % 9;
+    const int oy = (j == 0 || j == 1 || j == 5) ? 1 : (j == 2 || j == 4 || j == 6) ? 3 : 5;
+    return (q == 0 || q == 3) ? oy : -oy;
+}
+__device__ __forceinline__ float sa_inv_count(int cnt, int full, float inv_full) {
+    return cnt == full ? inv_full : rcp_approx((float)cnt);  // 1.0f / bilateral_weight_sum under --use_fast_math
+}
+
+__device__ __forceinline__ void load_sa_info(const PassK &K, int px, int py, const RefPatch &rp, SaInfo &si) {
+    const uint8_t *sa = K.sa;
+    const int W = K.W, H = K.H;
+    const int lab = sa[py * W + px];
+    si.label = lab;
+    {
+        unsigned long long bm = 0ull;
+        float s = 0.0f, ss = 0.0f;
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            bool open = true;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const int t = q * 9 + j;
+                const int xo = sa_b_xoff(t), yo = sa_b_yoff(t);
+                const int x = px + xo, y = py + yo;
+                if (open && x >= 0 && x < W && y >= 0 && y < H) {
+                    if (sa[y * W + x] != lab) open = false;
+                    else {
+                        const float v = rp.r[((xo + 5) / 2) * 6 + (yo + 5) / 2];
+                        bm |= 1ull << t;
+                        s += v;
+                        ss = fmaf(v, v, ss);
+                        cnt++;
+                    }
+                }
+            }
+        }
+        si.bmask = bm;
+        si.b_inv = sa_inv_count(cnt, 36, 1.0f / 36.0f);
+        si.b_mean = si.b_inv * s;
+        si.b_var = fmaf(si.b_inv, ss, -__fmul_rn(si.b_mean, si.b_mean));
+    }
+    {
+        unsigned long long nm = 0ull;
+        float s = 0.0f, ss = 0.0f;
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                // the reference indexes the label map without a bounds test here (APD.cu:527); WEAK pixels are >= 6 px inside
+                const int x = clampi(px + 2 * i - 5, 0, W - 1), y = clampi(py + 2 * j - 5, 0, H - 1);
+                if (lab == 0 || sa[y * W + x] == lab) {
+                    const float v = rp.r[i * 6 + j];
+                    nm |= 1ull << (i * 6 + j);
+                    s += v;
+                    ss = fmaf(v, v, ss);
+                    cnt++;
+                }
+            }
+        }
+        si.nmask = nm;
+        si.n_inv = sa_inv_count(cnt, 36, 1.0f / 36.0f);
+        si.n_mean = si.n_inv * s;
+        si.n_var = fmaf(si.n_inv, ss, -__fmul_rn(si.n_mean, si.n_mean));
+    }
+}
+
+// masked twin of patch_ncc36: ORDER 0 = branch A order (i outer, j inner), ORDER 1 = the quadrant walk.  Sample coordinates
+// are formed exactly as in patch_ncc36, so a full mask in order 0 gives the same samples.
+template <bool U, int ORDER>
+__device__ __forceinline__ float patch_ncc36_masked(const PassK &K, const Homog &Hm, int layer, int px, int py, const RefPatch &rp,
+                                                    unsigned long long mask, float mean_r, float var_r, float inv) {
+    const float *h = Hm.h;
+    const float g0 = fmaf(0.5f, h[6], h[0]), g1 = fmaf(0.5f, h[7], h[1]), g2 = fmaf(0.5f, h[8], h[2]);
+    const float g3 = fmaf(0.5f, h[6], h[3]), g4 = fmaf(0.5f, h[7], h[4]), g5 = fmaf(0.5f, h[8], h[5]);
+    float sum_s = 0.0f, sum_ss = 0.0f, sum_rs = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 36; ++t) {
+        const int xo = ORDER == 0 ? 2 * (t / 6) - 5 : sa_b_xoff(t), yo = ORDER == 0 ? 2 * (t % 6) - 5 : sa_b_yoff(t);
+        if ((mask >> t) & 1ull) {
+            const float xi = (float)(px + xo), yj = (float)(py + yo);
+            const float bx = fmaf(g0, xi, g2), by = fmaf(g3, xi, g5), bz = fmaf(h[6], xi, h[8]);
+            const float X = fmaf(g1, yj, bx), Y = fmaf(g4, yj, by), Z = fmaf(h[7], yj, bz);
+            const float iz = rcp_approx(Z);
+            const float s = fetch<U>(K, X * iz, Y * iz, layer);
+            sum_s += s;
+            sum_ss = fmaf(s, s, sum_ss);
+            sum_rs = fmaf(rp.r[((xo + 5) / 2) * 6 + (yo + 5) / 2], s, sum_rs);
+        }
+    }
+    const float mean_s = inv * sum_s, e_rs = inv * sum_rs;
+    const float var_s = fmaf(inv, sum_ss, -__fmul_rn(mean_s, mean_s));
+    if (var_r < 1e-5f || var_s < 1e-5f) return 2.0f;
+    const float covar = fmaf(-mean_r, mean_s, e_rs);
+    return fmaxf(0.0f, fminf(2.0f, fmaf(-covar, rsqrtf(var_r * var_s), 1.0f)));
+}
+
+// ComputeBilateralNCCOld with a label map, APD.cu:596-721
+template <bool U>
+__device__ __forceinline__ float ncc_old_sa(const PassK &K, const ViewK &vk, int px, int py, float3 m, const RefPatch &rp,
+                                            const SaInfo &si) {
+    const Homog Hm = make_homography(vk, m);
+    const float *h = Hm.h;
+    const float fxp = (float)px, fyp = (float)py;
+    const float Z = __fadd_rn(__fmaf_rn(h[7], fyp, __fmul_rn(h[6], fxp)), h[8]);
+    const float iz = rcp_approx(Z);
+    const float ptx = __fmul_rn(__fadd_rn(__fmaf_rn(h[1], fyp, __fmul_rn(h[0], fxp)), h[2]), iz);
+    const float pty = __fmul_rn(__fadd_rn(__fmaf_rn(h[4], fyp, __fmul_rn(h[3], fxp)), h[5]), iz);
+    if (ptx >= (float)K.W || ptx < 0.0f || pty >= (float)K.H || pty < 0.0f) return 2.0f;
+    // "const int center = pt.y * src_camera.width + pt.x": one FFMA and a truncation; the float can round up to W*H (clamped)
+    const int c = min(__float2int_rz(__fmaf_rn(pty, (float)K.W, ptx)), K.W * K.H - 1);
+    if (K.sa[c] == 0) return patch_ncc36<U>(K, Hm, vk.layer, px, py, rp);
+    if (si.bmask == 0ull) return 2.0f;  // 0 * (1/0) = NaN everywhere: max(0, min(2, NaN)) = 2
+    return patch_ncc36_masked<U, 1>(K, Hm, vk.layer, px, py, rp, si.bmask, si.b_mean, si.b_var, si.b_inv);
+}
+
+struct AnchorRefSa : AnchorRef {
+    float inv[8];
+    unsigned short tmask[8];
+};
+
+template <bool U>
+__device__ __forceinline__ void load_anchor_ref_sa(const PassK &K, const short2 *anc, AnchorRefSa &ar, const SaInfo &si) {
+    const uint8_t *sa = K.sa;
+    const int W = K.W, H = K.H, lab = si.label;
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        const short2 a = anc[k + 1];
+        ar.a[k] = a;
+        if (a.x == -1 || a.y == -1) { ar.a[k].x = -1; continue; }
+        if (lab != 0 && sa[a.x + a.y * W] != lab) { ar.a[k].x = -1; continue; }  // APD.cu:493-497
+        float sr = 0.0f, srr = 0.0f;
+        int t = 0, cnt = 0;
+        unsigned tm = 0u;
+#pragma unroll
+        for (int i = -5; i <= 5; i += 5) {
+#pragma unroll
+            for (int j = -5; j <= 5; j += 5) {
+                const float r = fetch<U>(K, (float)(a.x + i) + 0.5f, (float)(a.y + j) + 0.5f, K.ref_layer);
+                ar.r[k * 9 + t] = r;
+                const int x = clampi(a.x + i, 0, W - 1), y = clampi(a.y + j, 0, H - 1);
+                if (lab == 0 || sa[y * W + x] == lab) {
+                    tm |= 1u << t;
+                    sr += r;
+                    srr = fmaf(r, r, srr);
+                    cnt++;
+                }
+                t++;
+            }
+        }
+        ar.tmask[k] = (unsigned short)tm;
+        ar.inv[k] = sa_inv_count(cnt, 9, 1.0f / 9.0f);
+        ar.mean[k] = ar.inv[k] * sr;
+        ar.var[k] = fmaf(ar.inv[k], srr, -__fmul_rn(ar.mean[k], ar.mean[k]));
+    }
+}
+
+template <bool U>
+__device__ __forceinline__ float patch_ncc9_masked(const PassK &K, const Homog &Hm, int layer, int ax, int ay, const float *r9,
+                                                   unsigned tmask, float mean_r, float var_r, float inv) {
+    const float *h = Hm.h;
+    float ss = 0.0f, sss = 0.0f, srs = 0.0f;
+    int t = 0;
+#pragma unroll
+    for (int i = -5; i <= 5; i += 5) {
+#pragma unroll
+        for (int j = -5; j <= 5; j += 5) {
+            if ((tmask >> t) & 1u) {
+                const float fxp = (float)(ax + i), fyp = (float)(ay + j);
+                const float Z = h[6] * fxp + h[7] * fyp + h[8];
+                const float iz = rcp_approx(Z);
+                const float X = (h[0] * fxp + h[1] * fyp + h[2]) * iz, Y = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
+                const float s = fetch<U>(K, X + 0.5f, Y + 0.5f, layer);
+                ss += s; sss = fmaf(s, s, sss); srs = fmaf(r9[t], s, srs);
+            }
+            t++;
+        }
+    }
+    const float mean_s = inv * ss, e_rs = inv * srs;
+    const float var_s = fmaf(inv, sss, -__fmul_rn(mean_s, mean_s));
+    if (var_r < 1e-5f || var_s < 1e-5f) return 2.0f;
+    const float covar = fmaf(-mean_r, mean_s, e_rs);
+    return fmaxf(0.0f, fminf(2.0f, fmaf(-covar, rsqrtf(var_r * var_s), 1.0f)));
+}
+
+// ComputeBilateralNCCNew with a label map, APD.cu:448-593
+template <bool U>
+__device__ __forceinline__ float ncc_new_sa(const PassK &K, const ViewK &vk, int view_bit, int px, int py, float3 m,
+                                            const RefPatch &rp, const AnchorRefSa &ar, const SaInfo &si) {
+    const Homog Hm = make_homography(vk, m);
+    const float *h = Hm.h;
+    const float fW = (float)K.W, fH = (float)K.H;
+    {
+        const float fxp = (float)px, fyp = (float)py;
+        const float iz = rcp_approx(h[6] * fxp + h[7] * fyp + h[8]);
+        const float ptx = (h[0] * fxp + h[1] * fyp + h[2]) * iz, pty = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
+        if (ptx >= fW || ptx < 0.0f || pty >= fH || pty < 0.0f) return 2.0f;
+    }
+    // anchor 0 = the pixel itself: no tap of its segment -> "continue" with center_cost still 0 (APD.cu:543-545)
+    const float center_cost = si.nmask == 0ull ? 0.0f
+                              : patch_ncc36_masked<U, 0>(K, Hm, vk.layer, px, py, rp, si.nmask, si.n_mean, si.n_var, si.n_inv);
+    float sc[8];
+    int ns = 0;
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        const short2 a = ar.a[k];
+        if (a.x == -1) continue;
+        const float fxp = (float)a.x, fyp = (float)a.y;
+        const float iz = rcp_approx(h[6] * fxp + h[7] * fyp + h[8]);
+        const float ax = (h[0] * fxp + h[1] * fyp + h[2]) * iz, ay = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
+        if (ax < 0.0f || ay < 0.0f || ax >= fW || ay >= fH) {
+            if ((K.sel[a.x + a.y * K.W] >> view_bit) & 1u) sc[ns++] = 2.0f;
+            continue;
+        }
+        sc[ns++] = patch_ncc9_masked<U>(K, Hm, vk.layer, a.x, a.y, &ar.r[k * 9], ar.tmask[k], ar.mean[k], ar.var[k], ar.inv[k]);
+    }
+    if (ns == 0) return center_cost;
+    float mx = -1e10f;
+    for (int i = 0; i < ns; ++i) mx = fmaxf(mx, sc[i]);
+    float sum = 0.0f, acc = 0.0f;
+    float wts[8];
+    for (int i = 0; i < ns; ++i) { wts[i] = __expf(sc[i] - mx); sum += wts[i]; }
+    for (int i = 0; i < ns; ++i) acc += (wts[i] / sum) * sc[i];
+    acc = fminf(acc, 2.0f);
+    return 0.25f * center_cost + 0.75f * acc;
+}
+
+// compile-time switch used by the kernel bodies that exist in both flavours
+template <bool SA> struct SaTypes { typedef SaNone Info; typedef AnchorRef Anchors; };
+template <> struct SaTypes<true> { typedef SaInfo Info; typedef AnchorRefSa Anchors; };
+template <bool SA>
+__device__ __forceinline__ void load_sa(const PassK &K, int px, int py, const RefPatch &rp, typename SaTypes<SA>::Info &si) {
+    if constexpr (SA) load_sa_info(K, px, py, rp, si);
+}
+template <bool U, bool SA>
+__device__ __forceinline__ float ncc_old_x(const PassK &K, const ViewK &vk, int px, int py, float3 m, const RefPatch &rp,
+                                           const typename SaTypes<SA>::Info &si) {
+    if constexpr (SA) return ncc_old_sa<U>(K, vk, px, py, m, rp, si);
+    else return ncc_old<U>(K, vk, px, py, m, rp);
+}
+template <bool U, bool SA>
+__device__ __forceinline__ void load_anchor_ref_x(const PassK &K, const short2 *anc, typename SaTypes<SA>::Anchors &ar,
+                                                  const typename SaTypes<SA>::Info &si) {
+    if constexpr (SA) load_anchor_ref_sa<U>(K, anc, ar, si);
+    else load_anchor_ref<U>(K, anc, ar);
+}
+template <bool U, bool SA>
+__device__ __forceinline__ float ncc_new_x(const PassK &K, const ViewK &vk, int view_bit, int px, int py, float3 m, const RefPatch &rp,
+                                           const typename SaTypes<SA>::Anchors &ar, const typename SaTypes<SA>::Info &si) {
+    if constexpr (SA) return ncc_new_sa<U>(K, vk, view_bit, px, py, m, rp, ar, si);
+    else return ncc_new<U>(K, vk, view_bit, px, py, m, rp, ar);
 }
 
 // ComputeGeomConsistencyCost, APD.cu:865-902, with the camera pair pre-composed:

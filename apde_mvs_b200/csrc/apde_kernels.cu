@@ -20,7 +20,7 @@ namespace apde {
 // while the same kernel is still writing them, a data race.  Here the kernel runs in two phases when use_APD is set:
 // phase 0 = every pixel that is not WEAK, phase 1 = the WEAK pixels, which then see their anchors' final masks.  This is
 // one of the serialisations the reference's race allows, and it makes the pass deterministic.  phase < 0 = all pixels.
-template <bool U>
+template <bool U, bool SA>
 __device__ __forceinline__ void k_init_body(const PassK &K, int tiles_x, int phase) {
     int px, py;
     if (!full_pixel(K, tiles_x, px, py)) return;
@@ -40,14 +40,16 @@ __device__ __forceinline__ void k_init_body(const PassK &K, int tiles_x, int pha
 
     RefPatch rp;
     load_ref_patch<U>(K, px, py, rp);
+    typename SaTypes<SA>::Info si;
+    load_sa<SA>(K, px, py, rp, si);
     const float3 m = plane_row(K, pl);
     const bool weak = K.use_apd && K.weak[center] == APDE_WEAK;
     float cv[kMaxSrc], cvc[kMaxSrc];
     int num_valid = 0;
-    AnchorRef ar;
-    if (weak) load_anchor_ref<U>(K, K.anchors + (size_t)center * APDE_ANCHOR_NUM, ar);
+    typename SaTypes<SA>::Anchors ar;
+    if (weak) load_anchor_ref_x<U, SA>(K, K.anchors + (size_t)center * APDE_ANCHOR_NUM, ar, si);
     for (int v = 0; v < K.N; ++v) {
-        const float c = weak ? ncc_new<U>(K, K.v[v], v, px, py, m, rp, ar) : ncc_old<U>(K, K.v[v], px, py, m, rp);
+        const float c = weak ? ncc_new_x<U, SA>(K, K.v[v], v, px, py, m, rp, ar, si) : ncc_old_x<U, SA>(K, K.v[v], px, py, m, rp, si);
         cv[v] = c; cvc[v] = c;
         if (c < 2.0f) num_valid++;
     }
@@ -73,8 +75,13 @@ __device__ __forceinline__ void k_init_body(const PassK &K, int tiles_x, int pha
     count_evals(K, weak ? 0 : K.N, weak ? K.N : 0, 0);
 }
 __global__ void __launch_bounds__(128) k_init(const __grid_constant__ PassK K, int tiles_x, int phase) {
-    if (K.tex_unorm > 0.0f) k_init_body<true>(K, tiles_x, phase);
-    else k_init_body<false>(K, tiles_x, phase);
+    if (K.tex_unorm > 0.0f) k_init_body<true, false>(K, tiles_x, phase);
+    else k_init_body<false, false>(K, tiles_x, phase);
+}
+// the same kernel for a problem with a segment-label map (see "segment labels" in apde_device.cuh)
+__global__ void __launch_bounds__(128) k_init_sa(const __grid_constant__ PassK K, int tiles_x, int phase) {
+    if (K.tex_unorm > 0.0f) k_init_body<true, true>(K, tiles_x, phase);
+    else k_init_body<false, true>(K, tiles_x, phase);
 }
 
 
@@ -87,7 +94,7 @@ __global__ void __launch_bounds__(128) k_init(const __grid_constant__ PassK K, i
 // phase 3: current hypothesis + 5 refinement candidates, evaluated ONLY on views with non-zero weight -- zero-weight
 //          views contribute exactly 0 to the reference's weighted sums (costs are finite by construction), so
 //          skipping them is bit-identical and removes (N - S) of every N evaluations here.
-template <bool U>
+template <bool U, bool SA>
 __device__ __forceinline__ void k_prop_strong_body(const PassK &K, int iter, int color, int tiles_x,
                                                      int ylimit) {
     extern __shared__ float smem[];
@@ -103,6 +110,8 @@ __device__ __forceinline__ void k_prop_strong_body(const PassK &K, int iter, int
 
     RefPatch rp;
     load_ref_patch<U>(K, px, py, rp);
+    typename SaTypes<SA>::Info si;
+    load_sa<SA>(K, px, py, rp, si);
     unsigned n_old = 0, n_geom = 0;
 
     int pos[8];
@@ -112,7 +121,7 @@ __device__ __forceinline__ void k_prop_strong_body(const PassK &K, int iter, int
         if ((flags >> h) & 1u) {
             const float3 m = plane_row(K, K.planes[pos[h]]);
 #pragma unroll 1
-            for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_old<U>(K, K.v[v], px, py, m, rp);
+            for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_old_x<U, SA>(K, K.v[v], px, py, m, rp, si);
             n_old += N;
         } else {
             // quirk 2: "float cost_array[8][32] = {2.0f}" leaves every entry 0 except [0][0]
@@ -168,7 +177,7 @@ __device__ __forceinline__ void k_prop_strong_body(const PassK &K, int iter, int
         float acc = 0.0f;
         for (uint32_t mk = wmask; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            float c = ncc_old<U>(K, s_vk[v], px, py, m, rp);
+            float c = ncc_old_x<U, SA>(K, s_vk[v], px, py, m, rp, si);
             n_old++;
             if (use_geom) { c = __fmaf_rn(K.geom_factor, geom_cost(K, s_vk[v], v, px, py, plane_c), c); n_geom++; }
             acc += (float)vw_get(w, v) * c;
@@ -204,7 +213,7 @@ __device__ __forceinline__ void k_prop_strong_body(const PassK &K, int iter, int
         float acc = 0.0f;
         for (uint32_t mk = wmask; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            float c = ncc_old<U>(K, s_vk[v], px, py, m, rp);
+            float c = ncc_old_x<U, SA>(K, s_vk[v], px, py, m, rp, si);
             n_old++;
             if (use_geom) { c = __fmaf_rn(K.geom_factor, geom_cost(K, s_vk[v], v, px, py, tp), c); n_geom++; }
             acc += (float)vw_get(w, v) * c;
@@ -225,8 +234,13 @@ __device__ __forceinline__ void k_prop_strong_body(const PassK &K, int iter, int
 }
 __global__ void __launch_bounds__(128) k_prop_strong_v1(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
                                                         int ylimit) {
-    if (K.tex_unorm > 0.0f) k_prop_strong_body<true>(K, iter, color, tiles_x, ylimit);
-    else k_prop_strong_body<false>(K, iter, color, tiles_x, ylimit);
+    if (K.tex_unorm > 0.0f) k_prop_strong_body<true, false>(K, iter, color, tiles_x, ylimit);
+    else k_prop_strong_body<false, false>(K, iter, color, tiles_x, ylimit);
+}
+__global__ void __launch_bounds__(128) k_prop_strong_sa(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
+                                                        int ylimit) {
+    if (K.tex_unorm > 0.0f) k_prop_strong_body<true, true>(K, iter, color, tiles_x, ylimit);
+    else k_prop_strong_body<false, true>(K, iter, color, tiles_x, ylimit);
 }
 
 // The same half-sweep with the phase-3 evaluations (current hypothesis, then the five refinement hypotheses) WARP-COMPACTED.
@@ -510,7 +524,7 @@ __global__ void __launch_bounds__(128) k_median(const __grid_constant__ PassK K,
 
 // -------------------------------------------------------------------------------------------- K11 DepthToWeak
 // APD.cu:2103-2250: 61-sample disparity sweep of the view-weighted cost -> WEAK / STRONG / UNKNOWN
-template <bool U>
+template <bool U, bool SA>
 __device__ __forceinline__ void k_depth_to_weak_body(const PassK &K, int tiles_x, float *curve) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
@@ -538,6 +552,8 @@ __device__ __forceinline__ void k_depth_to_weak_body(const PassK &K, int tiles_x
 
     RefPatch rp;
     load_ref_patch<U>(K, px, py, rp);
+    typename SaTypes<SA>::Info si;
+    load_sa<SA>(K, px, py, rp, si);
     unsigned n_old = 0, n_geom = 0;
     const float fb = K.fx * base_line;
     const float disp = fb / origin_depth;
@@ -553,7 +569,7 @@ __device__ __forceinline__ void k_depth_to_weak_body(const PassK &K, int tiles_x
         float p_cost = 0.0f;
         for (uint32_t mk = sel; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            float tc = ncc_old<U>(K, s_vk[v], px, py, m, rp);
+            float tc = ncc_old_x<U, SA>(K, s_vk[v], px, py, m, rp, si);
             n_old++;
             if (K.geom) { tc += K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp); n_geom++; }
             p_cost += tc * (float)vw_get(w, v);
@@ -585,8 +601,12 @@ __device__ __forceinline__ void k_depth_to_weak_body(const PassK &K, int tiles_x
     K.weak[center] = (var > 0.2f) ? APDE_STRONG : APDE_WEAK;
 }
 __global__ void __launch_bounds__(128) k_depth_to_weak(const __grid_constant__ PassK K, int tiles_x, float *curve) {
-    if (K.tex_unorm > 0.0f) k_depth_to_weak_body<true>(K, tiles_x, curve);
-    else k_depth_to_weak_body<false>(K, tiles_x, curve);
+    if (K.tex_unorm > 0.0f) k_depth_to_weak_body<true, false>(K, tiles_x, curve);
+    else k_depth_to_weak_body<false, false>(K, tiles_x, curve);
+}
+__global__ void __launch_bounds__(128) k_depth_to_weak_sa(const __grid_constant__ PassK K, int tiles_x, float *curve) {
+    if (K.tex_unorm > 0.0f) k_depth_to_weak_body<true, true>(K, tiles_x, curve);
+    else k_depth_to_weak_body<false, true>(K, tiles_x, curve);
 }
 
 
@@ -630,7 +650,7 @@ __global__ void __launch_bounds__(128) k_confidence(const __grid_constant__ Pass
 
 // -------------------------------------------------------------------------------------------- K13 local refine
 // LocalRefine, APD.cu:2346-2432
-template <bool U>
+template <bool U, bool SA>
 __device__ __forceinline__ void k_local_refine_body(const PassK &K, int tiles_x) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
@@ -645,6 +665,8 @@ __device__ __forceinline__ void k_local_refine_body(const PassK &K, int tiles_x)
     const uint4 w = K.vw[center];
     RefPatch rp;
     load_ref_patch<U>(K, px, py, rp);
+    typename SaTypes<SA>::Info si;
+    load_sa<SA>(K, px, py, rp, si);
     unsigned n_old = 0, n_geom = 0;
     float cost_now = 0.0f, base_line = 0.0f, weight_normal = 0.0f;
     int valid_src = 0;
@@ -654,7 +676,7 @@ __device__ __forceinline__ void k_local_refine_body(const PassK &K, int tiles_x)
         const float3 m = plane_row(K, tp);
         for (uint32_t mk = sel; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            float tc = ncc_old<U>(K, s_vk[v], px, py, m, rp);
+            float tc = ncc_old_x<U, SA>(K, s_vk[v], px, py, m, rp, si);
             n_old++;
             if (K.geom) { tc += K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp); n_geom++; }
             const float wv = (float)vw_get(w, v);
@@ -681,7 +703,7 @@ __device__ __forceinline__ void k_local_refine_body(const PassK &K, int tiles_x)
         for (uint32_t mk = sel; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
             const float wv = (float)vw_get(w, v);
-            tc += ncc_old<U>(K, s_vk[v], px, py, m, rp) * wv;
+            tc += ncc_old_x<U, SA>(K, s_vk[v], px, py, m, rp, si) * wv;
             n_old++;
             if (K.geom) { tc += K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp) * wv; n_geom++; }
         }
@@ -692,8 +714,12 @@ __device__ __forceinline__ void k_local_refine_body(const PassK &K, int tiles_x)
     count_evals(K, n_old, 0, n_geom);
 }
 __global__ void __launch_bounds__(128) k_local_refine(const __grid_constant__ PassK K, int tiles_x) {
-    if (K.tex_unorm > 0.0f) k_local_refine_body<true>(K, tiles_x);
-    else k_local_refine_body<false>(K, tiles_x);
+    if (K.tex_unorm > 0.0f) k_local_refine_body<true, false>(K, tiles_x);
+    else k_local_refine_body<false, false>(K, tiles_x);
+}
+__global__ void __launch_bounds__(128) k_local_refine_sa(const __grid_constant__ PassK K, int tiles_x) {
+    if (K.tex_unorm > 0.0f) k_local_refine_body<true, true>(K, tiles_x);
+    else k_local_refine_body<false, true>(K, tiles_x);
 }
 
 
@@ -739,7 +765,7 @@ cudaError_t launch_build_lists(const PassK &K, int *lists, int *counts, int cap,
 }
 
 // -------------------------------------------------------------------------------------------- parity hook
-template <bool U>
+template <bool U, bool SA>
 __device__ __forceinline__ void k_eval_costs_body(const PassK &K, int n, const int *__restrict__ tuples,
                                                     const float4 *__restrict__ planes, int mode, float *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -752,21 +778,28 @@ __device__ __forceinline__ void k_eval_costs_body(const PassK &K, int n, const i
     } else {
         RefPatch rp;
         load_ref_patch<U>(K, px, py, rp);
+    typename SaTypes<SA>::Info si;
+    load_sa<SA>(K, px, py, rp, si);
         const float3 m = plane_row(K, pl);
         if (mode == 0) {
-            c = ncc_old<U>(K, K.v[v], px, py, m, rp);
+            c = ncc_old_x<U, SA>(K, K.v[v], px, py, m, rp, si);
         } else {
-            AnchorRef ar;
-            load_anchor_ref<U>(K, K.anchors + (size_t)(py * K.W + px) * APDE_ANCHOR_NUM, ar);
-            c = ncc_new<U>(K, K.v[v], v, px, py, m, rp, ar);
+            typename SaTypes<SA>::Anchors ar;
+            load_anchor_ref_x<U, SA>(K, K.anchors + (size_t)(py * K.W + px) * APDE_ANCHOR_NUM, ar, si);
+            c = ncc_new_x<U, SA>(K, K.v[v], v, px, py, m, rp, ar, si);
         }
     }
     out[i] = c;
 }
 __global__ void __launch_bounds__(128) k_eval_costs(const __grid_constant__ PassK K, int n, const int *__restrict__ tuples,
                                                     const float4 *__restrict__ planes, int mode, float *__restrict__ out) {
-    if (K.tex_unorm > 0.0f) k_eval_costs_body<true>(K, n, tuples, planes, mode, out);
-    else k_eval_costs_body<false>(K, n, tuples, planes, mode, out);
+    if (K.tex_unorm > 0.0f) k_eval_costs_body<true, false>(K, n, tuples, planes, mode, out);
+    else k_eval_costs_body<false, false>(K, n, tuples, planes, mode, out);
+}
+__global__ void __launch_bounds__(128) k_eval_costs_sa(const __grid_constant__ PassK K, int n, const int *__restrict__ tuples,
+                                                       const float4 *__restrict__ planes, int mode, float *__restrict__ out) {
+    if (K.tex_unorm > 0.0f) k_eval_costs_body<true, true>(K, n, tuples, planes, mode, out);
+    else k_eval_costs_body<false, true>(K, n, tuples, planes, mode, out);
 }
 
 
@@ -789,7 +822,8 @@ static bool use_thread_kernels() {
 
 cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStream_t st, float *curve) {
     const int W = K.W, H = K.H, N = K.N;
-    if (!use_thread_kernels()) {
+    const bool sa = K.sa != nullptr;  // segment labels: the <SA = true> twins of the thread-per-pixel kernels
+    if (!use_thread_kernels() && !sa) {
         bool handled = false;
         cudaError_t e = launch_stage_quad(K, stage, iter, color, st, curve, &handled);
         if (handled || e != cudaSuccess) return e;
@@ -800,7 +834,10 @@ cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStr
     switch (stage) {
         case APDE_STAGE_INIT: {
             const int tiles = tiles8x * ((H + 3) / 4);
-            if (K.use_apd) {
+            if (sa) {  // a label map exists only in use_APD passes (APD.cpp:614, 641)
+                k_init_sa<<<(tiles + 3) / 4, 128, 0, st>>>(K, tiles8x, 0);
+                k_init_sa<<<(tiles + 3) / 4, 128, 0, st>>>(K, tiles8x, 1);
+            } else if (K.use_apd) {
                 k_init<<<(tiles + 3) / 4, 128, 0, st>>>(K, tiles8x, 0);
                 k_init<<<(tiles + 3) / 4, 128, 0, st>>>(K, tiles8x, 1);
             } else {
@@ -812,17 +849,19 @@ cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStr
             const char *v1env = getenv("APDE_STRONG_V1");  // read per launch: tests toggle it inside one process
             const bool v1 = v1env && v1env[0] == '1';
             const int tiles = tiles8x * ((ylimit + 7) / 8);  // 32 same-colour pixels per tile == worst-case list length / 32
-            if (v1) {  // per-lane refinement loop (kept for A/B measurements and as the parity twin of the compacted kernel)
+            if (v1 || sa) {  // per-lane refinement loop (kept for A/B measurements and as the parity twin of the compacted kernel)
                 const int threads = prop_block_threads(N);
                 const size_t smem = prop_smem_bytes(N, threads);
                 static size_t configured = 0;
                 if (smem > configured) {
                     cudaError_t e = cudaFuncSetAttribute(k_prop_strong_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_prop_strong_sa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     if (e != cudaSuccess) return e;
                     configured = smem;
                 }
                 const int wpb = threads / 32;
-                k_prop_strong_v1<<<(tiles + wpb - 1) / wpb, threads, smem, st>>>(K, iter, color, tiles8x, ylimit);
+                if (sa) k_prop_strong_sa<<<(tiles + wpb - 1) / wpb, threads, smem, st>>>(K, iter, color, tiles8x, ylimit);
+                else k_prop_strong_v1<<<(tiles + wpb - 1) / wpb, threads, smem, st>>>(K, iter, color, tiles8x, ylimit);
                 break;
             }
             // column floats + the warp's pair list (N shorts per thread)
@@ -852,7 +891,8 @@ cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStr
         }
         case APDE_STAGE_DEPTH_TO_WEAK: {
             const int tiles = tiles8x * ((H + 3) / 4);
-            k_depth_to_weak<<<(tiles + 3) / 4, 128, vsm, st>>>(K, tiles8x, curve);
+            if (sa) k_depth_to_weak_sa<<<(tiles + 3) / 4, 128, vsm, st>>>(K, tiles8x, curve);
+            else k_depth_to_weak<<<(tiles + 3) / 4, 128, vsm, st>>>(K, tiles8x, curve);
             break;
         }
         case APDE_STAGE_CONFIDENCE: {
@@ -862,7 +902,8 @@ cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStr
         }
         case APDE_STAGE_LOCAL_REFINE: {
             const int tiles = tiles8x * ((H + 3) / 4);
-            k_local_refine<<<(tiles + 3) / 4, 128, vsm, st>>>(K, tiles8x);
+            if (sa) k_local_refine_sa<<<(tiles + 3) / 4, 128, vsm, st>>>(K, tiles8x);
+            else k_local_refine<<<(tiles + 3) / 4, 128, vsm, st>>>(K, tiles8x);
             break;
         }
         default:
@@ -873,7 +914,8 @@ cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStr
 
 cudaError_t launch_eval_costs(const PassK &K, int n, const int *tuples, const float4 *planes, int mode, float *out,
                               cudaStream_t st) {
-    k_eval_costs<<<(n + 127) / 128, 128, 0, st>>>(K, n, tuples, planes, mode, out);
+    if (K.sa) k_eval_costs_sa<<<(n + 127) / 128, 128, 0, st>>>(K, n, tuples, planes, mode, out);
+    else k_eval_costs<<<(n + 127) / 128, 128, 0, st>>>(K, n, tuples, planes, mode, out);
     return cudaGetLastError();
 }
 

@@ -46,6 +46,15 @@ std::shared_ptr<SceneSession> SceneSession::get(const path &dense_folder, int gp
         s->cameras.push_back(cam);
         check(apde_scene_set_view(s->ctx, (int)i, gray.data(), bgr.empty() ? nullptr : bgr.data(), &cam), "apde_scene_set_view");
         s->has_color = !bgr.empty();
+        // segment labels from tools/run_SAM.py, if the folder has them (APD.cpp:507, 641-649); consumed by passes with use_sa
+        const path sa_path = dense_folder / "sa_masks" / (ToFormatIndex(p.ref_image_id) + ".bin");
+        if (std::filesystem::exists(sa_path)) {
+            Mat sa;
+            if (ReadBinMat(sa_path, sa) && sa.type() == CV_8UC1 && !sa.empty()) {
+                check(apde_view_set_sa_mask(s->ctx, (int)i, sa.data(), sa.cols, sa.rows), "apde_view_set_sa_mask");
+                s->num_sa_masks++;
+            }
+        }
     }
     for (size_t i = 0; i < s->problems.size(); ++i) {
         std::vector<int32_t> src;

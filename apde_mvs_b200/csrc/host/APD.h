@@ -69,6 +69,7 @@ public:
     int view_of(int image_id) const;
     std::vector<Camera> cameras;
     bool has_color = false;
+    int num_sa_masks = 0;  // views with a label map in <dense>/sa_masks/
 private:
     SceneSession() {}
 };

@@ -168,7 +168,7 @@ int main(int argc, char **argv) {
     std::cout << "========================== Config ==========================" << std::endl;
     std::cout << "dense_folder : " << a.dense_folder << "\ngpu_index    : " << a.gpu_index << "\ndataset      : " << a.dataset
               << "\nonly_fuse    : " << a.only_fuse << "\nno_fuse      : " << a.no_fuse << "\nmemory_cache : " << a.memory_cache
-              << "\nuse_sa       : " << a.use_sa << " (ignored: SAM masks are out of scope)\nuse_impetus  : " << a.use_impetus
+              << "\nuse_sa       : " << a.use_sa << "\nuse_impetus  : " << a.use_impetus
               << "\nweak_filter  : " << a.weak_filter << "\nflush        : " << a.flush << "\nexport_anchor: " << a.export_anchor
               << "\nexport_curve : " << a.export_curve << "\nexport_color : " << a.export_color << std::endl;
     std::cout << "============================================================" << std::endl;
@@ -190,6 +190,9 @@ int main(int argc, char **argv) {
         apde_schedule sched;
         apde_schedule_default(&sched);
         sched.use_impetus = a.use_impetus;
+        sched.use_sa = a.use_sa;  // label maps of <dense>/sa_masks/ (read by SceneSession), main.cpp:324
+        if (a.use_sa && s->num_sa_masks == 0) std::cout << "Can't find sa mask folder: " << (path(a.dense_folder) / "sa_masks") << std::endl;
+        else if (a.use_sa) std::cout << "sa masks: " << s->num_sa_masks << " of " << s->problems.size() << " views" << std::endl;
         sched.geom_factor = (a.dataset == "TaT_a" || a.dataset == "TaT_i") ? 0.05f : 0.2f;  // main.cpp:294-298
         const int npass = apde_schedule_num_passes(s->ctx, &sched);
         std::cout << "Round nums: " << npass / (1 + sched.geom_iterations) << std::endl;

@@ -84,7 +84,7 @@ typedef struct {
     int weak_radius;
     int weak_increment;
     int use_APD;
-    int use_sa; /* accepted, ignored: SAM masks are out of scope */
+    int use_sa; /* consume the reference view's segment-label map (apde_view_set_sa_mask) in use_APD passes, APD.cpp:641-649 */
     int weak_peak_radius;
     int rotate_time;
     float ransac_threshold;
@@ -107,6 +107,11 @@ const char *apde_version(void);
 int apde_scene_begin(apde_context *ctx, int num_views, int width, int height);
 /* gray: H*W bytes (what cv::imread(GRAYSCALE) yields, APD.cpp:145) ; bgr may be NULL (only fusion colours need it) */
 int apde_scene_set_view(apde_context *ctx, int view, const uint8_t *gray, const uint8_t *bgr, const apde_camera *cam);
+/* segment labels of a view: the CV_8UC1 map of <dense>/sa_masks/<id>.bin (tools/run_SAM.py:41-60; any size, 0 = no segment),
+ * replaces APD.cpp:641-649 (ReadBinMat + nearest resize to the working size, done here per problem on the device).  Consumed
+ * by passes with use_APD && use_sa: NCC-Old branch B (APD.cu:664-719) and the label tests of NCC-New (APD.cu:493-497, 526-530).
+ * labels == NULL removes the map. */
+int apde_view_set_sa_mask(apde_context *ctx, int view, const uint8_t *labels, int width, int height);
 /* neighbour list of a view = Problem::src_image_ids (main.h:104), at most APDE_MAX_IMAGES-1 entries */
 int apde_scene_set_pairs(apde_context *ctx, int view, int num_src, const int32_t *src_views);
 int apde_scene_commit(apde_context *ctx);
@@ -153,7 +158,8 @@ typedef enum {
     APDE_FIELD_ANCHORS = 9,        /* short2[P][9] */
     APDE_FIELD_IMAGE = 10,         /* float[P], working-resolution reference image (read only) */
     APDE_FIELD_SRC_DEPTH = 11,     /* float[N+1][P], working-resolution depth maps, index 0 = ref (read only) */
-    APDE_FIELD_RELIABLE_CURVE = 12 /* float[P][61], DepthToWeak's cost curve (read only; needs apde_problem_capture_curve) */
+    APDE_FIELD_RELIABLE_CURVE = 12,/* float[P][61], DepthToWeak's cost curve (read only; needs apde_problem_capture_curve) */
+    APDE_FIELD_SA_MASK = 13        /* uint8[P], the reference view's segment labels at the working size (read only; error if none) */
 } apde_field;
 
 int apde_problem_get(apde_context *ctx, int field, void *host, size_t bytes);
@@ -189,6 +195,7 @@ typedef struct {
     float geom_factor;   /* 0.2 (0.05 for TaT), main.cpp:294-298 */
     uint32_t seed;
     int first_view, num_views_local; /* this rank's shard of reference views (multi-GPU); 0,0 = all */
+    int use_sa;          /* main.cpp:324; only views that were given a label map are affected */
 } apde_schedule;
 
 void apde_schedule_default(apde_schedule *s);

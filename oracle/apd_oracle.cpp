@@ -332,7 +332,30 @@ inline void count(orc_problem *pb, int which) {
 }
 
 /* NCC of one patch around (cx, cy) with the given radius/increment (shared by Old and New).  APD.cu:622-662 */
-inline float patch_ncc(const orc_problem *pb, const float *H, int src_idx, int cx, int cy, int radius, int increment) {
+/* "1.0f / bilateral_weight_sum" is one MUFU.RCP under --use_fast_math.  For the integer tap counts 1..36 it returns the
+ * correctly rounded reciprocal except for 33 (0x3cf83e0f, one ulp below 1/33): measured on B200 with tools/probe_mufu_rcp.cu
+ * (profiles/r01_mufu_rcp_counts.txt).  Counts other than 36 and 9 only occur with a segment-label map. */
+inline float rcp_count(float n) {
+    if (n == 33.0f) {
+        const uint32_t bits = 0x3cf83e0fu;
+        float r;
+        std::memcpy(&r, &bits, 4);
+        return r;
+    }
+    return 1.0f / n;
+}
+
+inline uint8_t sa_label(const orc_problem *pb, int x, int y) {
+    /* the reference indexes sa_mask without a bounds test (APD.cu:494, 527); out-of-image taps are clamped here */
+    const int W = pb->width, Hh = pb->height;
+    x = x < 0 ? 0 : (x >= W ? W - 1 : x);
+    y = y < 0 ? 0 : (y >= Hh ? Hh - 1 : y);
+    return pb->sa_mask[x + (size_t)y * W];
+}
+
+/* filter_label >= 0: only taps of that segment label take part (NCC-New with use_sa_mask, APD.cu:526-530) */
+inline float patch_ncc(const orc_problem *pb, const float *H, int src_idx, int cx, int cy, int radius, int increment,
+                       int filter_label = -1) {
     const int W = pb->width, Hh = pb->height;
     const float *ref = pb->images[0];
     const float *src = pb->images[src_idx];
@@ -340,6 +363,7 @@ inline float patch_ncc(const orc_problem *pb, const float *H, int src_idx, int c
     for (int i = -radius; i <= radius; i += increment) {
         for (int j = -radius; j <= radius; j += increment) {
             const int rx = cx + i, ry = cy + j;
+            if (filter_label >= 0 && sa_label(pb, rx, ry) != filter_label) continue;
             const float ref_pix = tex_point(ref, W, Hh, rx, ry);
             const F2 sp = corresponding_point(H, rx, ry);
             const float src_pix = tex_linear(src, W, Hh, sp.x + 0.5f, sp.y + 0.5f, pb->tex_mode);
@@ -355,11 +379,11 @@ inline float patch_ncc(const orc_problem *pb, const float *H, int src_idx, int c
             wsum += weight;
         }
     }
-    if (wsum == 0.0f) return -1.0f; /* only reachable in NCC-New with SAM masks; never here */
+    if (wsum == 0.0f) return -1.0f; /* only reachable in NCC-New with a label map: the caller skips the patch (APD.cu:543-545) */
     /* Epilogue exactly as nvcc compiles APD.cu:644-661 for sm_100 with the reference flags (SASS of the reference build:
      * MUFU.RCP; 3x FMUL; FMUL mean^2; FFMA(inv, sum_xx, -mean^2); FFMA(-mean_r, mean_s, E_rs); FFMA(-covar, 1/sqrt, 1)).
      * MUFU.RCP(36) and MUFU.RCP(9) return the correctly rounded reciprocal (tools/probe_mufu.cu). */
-    const float inv = 1.0f / wsum;
+    const float inv = rcp_count(wsum);
     const float mean_ref = inv * sum_ref, mean_src = inv * sum_src, e_rs = inv * sum_ref_src;
     const float var_ref = std::fmaf(inv, sum_ref_ref, -(mean_ref * mean_ref));
     const float var_src = std::fmaf(inv, sum_src_src, -(mean_src * mean_src));
@@ -372,7 +396,46 @@ inline float patch_ncc(const orc_problem *pb, const float *H, int src_idx, int c
     return std::fmax(0.0f, std::fmin(2.0f, v));
 }
 
-/* APD.cu:596-663 (branch A only; sa_mask == 0) */
+/* NCC-Old branch B, APD.cu:664-719: the 36 odd offsets walked quadrant by quadrant; a tap outside the image is skipped, the
+ * first tap of another segment label ends its quadrant.  Same sums and epilogue as branch A. */
+inline float patch_ncc_quadrants(const orc_problem *pb, const float *H, int src_idx, int px, int py) {
+    static const int sign[] = {1, 1, -1, -1, 1, -1, -1, 1};
+    static const int offset[] = {1, 1, 3, 1, 1, 3, 1, 5, 3, 3, 5, 1, 5, 3, 3, 5, 5, 5};
+    const int W = pb->width, Hh = pb->height;
+    const float *ref = pb->images[0];
+    const float *src = pb->images[src_idx];
+    const uint8_t center_id = pb->sa_mask[px + (size_t)py * W];
+    float sum_ref = 0.0f, sum_ref_ref = 0.0f, sum_src = 0.0f, sum_src_src = 0.0f, sum_ref_src = 0.0f, wsum = 0.0f;
+    for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 9; ++j) {
+            const int rx = px + offset[j * 2] * sign[i * 2], ry = py + offset[j * 2 + 1] * sign[i * 2 + 1];
+            if (rx < 0 || rx >= W || ry < 0 || ry >= Hh) continue;
+            if (pb->sa_mask[rx + (size_t)ry * W] != center_id) break;
+            const float ref_pix = tex_point(ref, W, Hh, rx, ry);
+            const F2 sp = corresponding_point(H, rx, ry);
+            const float src_pix = tex_linear(src, W, Hh, sp.x + 0.5f, sp.y + 0.5f, pb->tex_mode);
+            sum_ref += ref_pix;
+            sum_ref_ref = std::fmaf(ref_pix, ref_pix, sum_ref_ref);
+            sum_src += src_pix;
+            sum_src_src = std::fmaf(src_pix, src_pix, sum_src_src);
+            sum_ref_src = std::fmaf(ref_pix, src_pix, sum_ref_src);
+            wsum += 1.0f;
+        }
+    }
+    if (wsum == 0.0f) return 2.0f; /* 1/0 = inf, 0 * inf = NaN, every comparison false, max(0, min(2, NaN)) = 2 (quirk 10) */
+    const float inv = rcp_count(wsum);
+    const float mean_ref = inv * sum_ref, mean_src = inv * sum_src, e_rs = inv * sum_ref_src;
+    const float var_ref = std::fmaf(inv, sum_ref_ref, -(mean_ref * mean_ref));
+    const float var_src = std::fmaf(inv, sum_src_src, -(mean_src * mean_src));
+    const float kMinVar = 1e-5f;
+    if (var_ref < kMinVar || var_src < kMinVar) return 2.0f;
+    const float covar = std::fmaf(-mean_ref, mean_src, e_rs);
+    const float denom = std::sqrt(var_ref * var_src);
+    const float v = std::fmaf(-covar, 1.0f / denom, 1.0f);
+    return std::fmax(0.0f, std::fmin(2.0f, v));
+}
+
+/* APD.cu:596-721 */
 float ncc_old(orc_problem *pb, I2 p, int src_idx, F4 plane) {
     count(pb, 0);
     const orc_camera &rc = pb->cameras[0];
@@ -381,6 +444,14 @@ float ncc_old(orc_problem *pb, I2 p, int src_idx, F4 plane) {
     homography(rc, sc, plane, H);
     const F2 pt = corresponding_point(H, p.x, p.y);
     if (pt.x >= sc.width || pt.x < 0.0f || pt.y >= sc.height || pt.y < 0.0f) return 2.0f;
+    if (pb->sa_mask) {
+        /* "const int center = pt.y * src_camera.width + pt.x; if (sa_mask[center] == 0)" (APD.cu:619-621): the REFERENCE
+         * view's label map indexed by the projected point, float arithmetic (one FFMA under -fmad) truncated to int */
+        long long c = (long long)std::fmaf(pt.y, (float)sc.width, pt.x);
+        const long long last = (long long)pb->width * pb->height - 1;
+        if (c > last) c = last; /* the float can round up to W*H: one past the end in the reference */
+        if (pb->sa_mask[c] != 0) return patch_ncc_quadrants(pb, H, src_idx, p.x, p.y);
+    }
     return patch_ncc(pb, H, src_idx, p.x, p.y, pb->params.strong_radius, pb->params.strong_increment);
 }
 
@@ -392,7 +463,7 @@ inline void softmax(float *c, int n) { /* APD.cu:431-446 */
     for (int i = 0; i < n; i++) c[i] /= sum;
 }
 
-/* APD.cu:448-593 (sa_mask == 0) */
+/* APD.cu:448-593 */
 float ncc_new(orc_problem *pb, I2 p, int src_idx, F4 plane) {
     count(pb, 1);
     const orc_camera &rc = pb->cameras[0];
@@ -409,9 +480,12 @@ float ncc_new(orc_problem *pb, I2 p, int src_idx, F4 plane) {
     int strong_num = 0;
     if (pb->weak_info[center] != ORC_WEAK) return cost; /* reference prints "error" and returns 0 (APD.cu:590) */
     float center_cost = 0.0f, strong_weight = 0.0f;
+    const int center_id = pb->sa_mask ? pb->sa_mask[center] : 0;
+    const bool use_sa_mask = center_id != 0; /* APD.cu:463-465 */
     for (int k = 0; k < ORC_ANCHOR_NUM; ++k) {
         const S2 a = load_s2(pb->anchors, center * ORC_ANCHOR_NUM + k);
         if (a.x == -1 || a.y == -1) continue;
+        if (use_sa_mask && pb->sa_mask[a.x + (size_t)a.y * W] != center_id) continue; /* APD.cu:493-497 */
         const F2 asp = corresponding_point(H, a.x, a.y);
         if (asp.x < 0 || asp.y < 0 || asp.x >= W || asp.y >= Hh) {
             if (k != 0) {
@@ -424,7 +498,8 @@ float ncc_new(orc_problem *pb, I2 p, int src_idx, F4 plane) {
         }
         const int radius = (k == 0 ? pb->params.strong_radius : pb->params.weak_radius);
         const int increment = (k == 0 ? pb->params.strong_increment : pb->params.weak_increment);
-        const float tc = patch_ncc(pb, H, src_idx, a.x, a.y, radius, increment);
+        const float tc = patch_ncc(pb, H, src_idx, a.x, a.y, radius, increment, use_sa_mask ? center_id : -1);
+        if (tc < 0.0f) continue; /* no tap of the centre's segment: bilateral_weight_sum == 0 (APD.cu:543-545) */
         if (k == 0) center_cost = tc;
         else { strong_costs[strong_num++] = tc; strong_weight += 1; }
     }

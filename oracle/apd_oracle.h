@@ -17,8 +17,9 @@
  *   - RNG: Philox4x32-10 counter RNG keyed by (seed, stream), counter = (pixel, site, block) instead
  *     of per-pixel XORWOW seeded by clock64() (APD.cu:916).  Whole-pass parity with the reference is
  *     therefore statistical; per-function parity is exact / 1e-4.
- *   - SAM masks are out of scope: sa_mask == 0 everywhere (APD.cpp:613), so NCC-Old branch B
- *     (APD.cu:664-719) is not restated.
+ *   - running SAM is out of scope; a label map it produced (sa_masks/<id>.bin) is consumed as the reference does:
+ *     orc_problem::sa_mask != NULL switches on NCC-Old branch B (APD.cu:664-719) and the label tests of NCC-New
+ *     (APD.cu:493-497, 526-530); NULL = all-zero labels (APD.cpp:613).
  *   - anchors are stored densely ([pixel][9]) instead of through anchors_map (APD.cpp:627-640).
  */
 #ifndef APD_ORACLE_H_
@@ -94,6 +95,7 @@ typedef struct {
     int tex_mode;             /* 0 = exact fp32 bilinear, 1 = 8-bit weight quantisation (CUDA texture unit) */
     int num_threads;          /* OpenMP threads, <=0 -> 1 */
     uint64_t counters[8];     /* [0] NCC-Old evals, [1] NCC-New evals, [2] geom evals */
+    const uint8_t *sa_mask;   /* [P] segment labels of the reference view (sa_masks/<id>.bin, APD.cpp:641-649) or NULL = all zero */
 } orc_problem;
 
 /* ---- per-hypothesis cost functions (APD.cu:334-403, 448-721, 831-902) ---- */

@@ -43,7 +43,7 @@ class OProblem(C.Structure):
                 ("view_weight", C.c_void_p), ("weak_info", C.c_void_p), ("confidence", C.c_void_p),
                 ("fit_planes", C.c_void_p), ("weak_reliable", C.c_void_p), ("nearest_strong", C.c_void_p),
                 ("anchors", C.c_void_p), ("seed", C.c_uint32), ("stream", C.c_uint32), ("tex_mode", C.c_int),
-                ("num_threads", C.c_int), ("counters", C.c_uint64 * 8)]
+                ("num_threads", C.c_int), ("counters", C.c_uint64 * 8), ("sa_mask", C.c_void_p)]
 
 
 class OFusionInput(C.Structure):
@@ -128,6 +128,13 @@ class Problem:
             setattr(pb, name, getattr(self, name).ctypes.data)
         pb.seed, pb.stream, pb.tex_mode, pb.num_threads = seed, stream, tex_mode, num_threads
         assert P > 0
+
+    def set_sa_mask(self, labels):
+        """segment labels of the reference view at the working size (uint8 [h, w]); None = all zero (APD.cpp:613, 641-649)"""
+        self.sa_mask = None if labels is None else np.ascontiguousarray(labels, np.uint8)
+        if self.sa_mask is not None:
+            assert self.sa_mask.shape == (self.h, self.w)
+        self.pb.sa_mask = None if self.sa_mask is None else self.sa_mask.ctypes.data
 
     @property
     def ptr(self):

@@ -22,6 +22,8 @@ def lib():
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_run_pass.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_double)]
+        L.ref_set_sa_mask.argtypes = [C.c_void_p, C.c_longlong]
+        L.ref_set_sa_mask.restype = None
         assert L.ref_sizeof_camera() == 120
         _lib = L
     return _lib
@@ -52,6 +54,15 @@ def _cams(cameras):
 
 def _p(a):
     return None if a is None else a.ctypes.data
+
+
+def set_sa_mask(labels):
+    """segment labels (uint8 [h, w] at the working size) for the following eval_costs / run_pass calls; None clears them"""
+    if labels is None:
+        lib().ref_set_sa_mask(None, 0)
+    else:
+        a = np.ascontiguousarray(labels, np.uint8)
+        lib().ref_set_sa_mask(a.ctypes.data, a.size)
 
 
 def eval_costs(images, cameras, params, tuples, planes, mode=0, depths=None, weak=None, selected_views=None, anchors=None):

@@ -83,6 +83,9 @@ void free_state(RefState &s) {
     cudaFree(s.sa); cudaFree(s.reliable); cudaFree(s.nearest); cudaFree(s.anchors); cudaFree(s.anchors_map); cudaFree(s.helper);
 }
 
+// segment labels for the next build_state() (ref_set_sa_mask); empty = none
+std::vector<unsigned char> g_sa_mask;
+
 // the device-side part of CudaSpaceInitialization + SetDataPassHelperInCuda (APD.cpp:687-814), from caller arrays
 void build_state(RefState &s, int w, int h, int n, const float *const *images, const float *const *depths, const Camera *cams,
                  const PatchMatchParams *params, const float *planes, const uchar *weak, const uchar *conf,
@@ -125,7 +128,8 @@ void build_state(RefState &s, int w, int h, int n, const float *const *images, c
     cudaMalloc(&s.conf, P);
     if (conf) cudaMemcpy(s.conf, conf, P, cudaMemcpyHostToDevice); else cudaMemset(s.conf, 1, P);
     cudaMalloc(&s.sa, P);
-    cudaMemset(s.sa, 0, P);  // SAM off: sa_mask_host = zeros (APD.cpp:613)
+    if (g_sa_mask.size() == P) cudaMemcpy(s.sa, g_sa_mask.data(), P, cudaMemcpyHostToDevice);  // sa_masks/<id>.bin, APD.cpp:641-649
+    else cudaMemset(s.sa, 0, P);  // SAM off: sa_mask_host = zeros (APD.cpp:613)
     cudaMalloc(&s.fit, P * sizeof(float4));
     cudaMemset(s.fit, 0, P * sizeof(float4));
     cudaMalloc(&s.reliable, P);
@@ -187,6 +191,12 @@ PatchMatchParams to_ref_params(const int *ip, const float *fp) {
 extern "C" {
 
 int ref_sizeof_camera() { return (int)sizeof(Camera); }
+
+// label map (w*h bytes at the working size) used by the following ref_eval_costs / ref_run_pass calls; n = 0 clears it
+void ref_set_sa_mask(const unsigned char *labels, long long n) {
+    if (labels && n > 0) g_sa_mask.assign(labels, labels + n);
+    else g_sa_mask.clear();
+}
 
 // images / depths: arrays of n host pointers (depths may be null).  cams: n reference Camera structs (120 B each).
 int ref_eval_costs(int w, int h, int n_images, const float *const *images, const float *const *depths, const void *cams,

@@ -4,8 +4,9 @@
     python run.py --data_dir <root> --scans scan1 scan2 --gpu_num 8 --work_num 1 [--only_fuse] [--no_fuse] ...
 
 One `apd` process per scan, pinned to a GPU slot exactly like the reference's worker table (run.py:72-82, 104-138).
-Differences: --no_sam is implied (the SAM plug-in is out of scope, tools/run_SAM.py is never imported) and --APD_path
-defaults to the in-tree build.  The image-layout helper (scripts/dataset_loader.py:54-140: first existing candidate
+Differences: running SAM is out of scope (tools/run_SAM.py is never imported): label maps already present in
+<scan>/sa_masks/ are consumed (--use_sa true) unless --no_sam is given, a scan without them runs with --use_sa false
+instead of calling the SAM runner (run.py:94-98); --APD_path defaults to the in-tree build.  The image-layout helper (scripts/dataset_loader.py:54-140: first existing candidate
 directory, symlinked to <scan>/images) is restated in resolve_images_dir().
 """
 import argparse
@@ -28,7 +29,7 @@ def parse_args(argv=None):
     p.add_argument('--only_fuse', action='store_true', default=False)
     p.add_argument('--no_fuse', action='store_true', default=False)
     p.add_argument('--memory_cache', action='store_true', default=False)
-    p.add_argument('--no_sam', action='store_true', default=True)
+    p.add_argument('--no_sam', action='store_true', default=False)
     p.add_argument('--no_impetus', action='store_true', default=False)
     p.add_argument('--no_weak_filter', action='store_true', default=False)
     p.add_argument('--no_color', action='store_true', default=False)
@@ -106,8 +107,9 @@ def dataset_tag(data_dir, scan):
 
 def build_command(args, scan_dir, scan, gpu_index):
     b = lambda v: 'true' if v else 'false'  # noqa: E731
+    use_sa = not args.no_sam and os.path.isdir(os.path.join(scan_dir, 'sa_masks'))  # run.py:94-98 without the SAM runner
     return [args.APD_path, '--dense_folder', scan_dir, '--gpu_index', str(gpu_index), '--dataset', dataset_tag(args.data_dir, scan),
-            '--only_fuse', b(args.only_fuse), '--no_fuse', b(args.no_fuse), '--use_sa', 'false', '--memory_cache', b(args.memory_cache),
+            '--only_fuse', b(args.only_fuse), '--no_fuse', b(args.no_fuse), '--use_sa', b(use_sa), '--memory_cache', b(args.memory_cache),
             '--flush', b(args.flush), '--export_anchor', b(args.export_anchor), '--export_curve', b(args.export_curve),
             '--export_color', b(not args.no_color), '--use_impetus', b(not args.no_impetus), '--weak_filter', b(not args.no_weak_filter)]
 

@@ -118,13 +118,15 @@ def test_apd_cli_jpeg_inputs_and_tat_fusion(dense, tmp_path):
     assert counts["TaT_a"] != counts["TaT_i"]  # different thresholds, different clouds
 
 
-@pytest.mark.parametrize("dataset,W,H,weak,rounds", [("General", 320, 240, 0.0, 1), ("TaT_i", 960, 720, 0.25, 2)])
-def test_cli_against_the_reference_main(tmp_path, dataset, W, H, weak, rounds):
+@pytest.mark.parametrize("dataset,W,H,weak,rounds,sa", [("General", 320, 240, 0.0, 1, False), ("TaT_i", 960, 720, 0.25, 2, False),
+                                                        ("General", 960, 720, 0.25, 2, True)])
+def test_cli_against_the_reference_main(tmp_path, dataset, W, H, weak, rounds, sa):
     """the product's `apd` against the REFERENCE's own main() (APD.cu + APD.cpp + main.cpp compiled unmodified into
     oracle/_ref/libapd_ref_full.so) on the same dense folder: same files written, final depth maps agreeing on STRONG
     pixels as well as two runs of the reference agree with each other, equal state shares, fused clouds of equal size.
     Second case: two pyramid rounds (use_APD, map hand-over between levels in the reference's own host code), weak-texture
-    blobs, and the Tanks-and-Temples settings (geom_factor 0.05, RunFusion_TAT_I)."""
+    blobs, and the Tanks-and-Temples settings (geom_factor 0.05, RunFusion_TAT_I).  Third case: segment-label maps in
+    <dense>/sa_masks/ (tools/run_SAM.py's format, half-size so that the nearest resize of APD.cpp:645-648 runs) and --use_sa true."""
     import shutil
     sys.path.insert(0, ROOT)
     from oracle import ref_main_runner as runner
@@ -141,9 +143,21 @@ def test_cli_against_the_reference_main(tmp_path, dataset, W, H, weak, rounds):
     for v in range(V):
         cv2.imwrite(str(ours / "images" / ("%08d.png" % v)), scene.colors[v])  # colour inputs: grey conversion is part of the path
 
+    if sa:
+        from test_gpu_sa_mask import make_labels
+        os.makedirs(ours / "sa_masks")
+        for v in range(V):
+            lab = make_labels(W // 2, H // 2, 30 + v, zero_share=0.2)
+            with open(ours / "sa_masks" / ("%08d.bin" % v), "wb") as f:
+                f.write(struct.pack("<4i", 1, lab.shape[0], lab.shape[1], 0))
+                f.write(lab.tobytes())
+    use_sa = "true" if sa else "false"
+
     def ref_folder(name):
         d = tmp_path / name
         shutil.copytree(ours / "cams", d / "cams")
+        if sa:
+            shutil.copytree(ours / "sa_masks", d / "sa_masks")
         shutil.copy(ours / "pair.txt", d / "pair.txt")
         os.makedirs(d / "images")
         for v in range(V):  # PPM content under the .png name the reference looks for (stub cv::imread decodes by magic)
@@ -154,7 +168,7 @@ def test_cli_against_the_reference_main(tmp_path, dataset, W, H, weak, rounds):
 
     def run_ref(d, seed):
         out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_main_runner.py"), str(seed), "--dense_folder", str(d),
-                              "--use_sa", "false", "--memory_cache", "true", "--flush", "true", "--dataset", dataset], capture_output=True, text=True)
+                              "--use_sa", use_sa, "--memory_cache", "true", "--flush", "true", "--dataset", dataset], capture_output=True, text=True)
         assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
         return out.stdout
 
@@ -162,9 +176,11 @@ def test_cli_against_the_reference_main(tmp_path, dataset, W, H, weak, rounds):
     log_a = run_ref(ra, 1111)
     run_ref(rb, 2222)
     apd = os.path.join(ROOT, "apde_mvs_b200", "_build", "apd")
-    out = subprocess.run([apd, "-d", str(ours), "--use_sa", "false", "--dataset", dataset], capture_output=True, text=True)
+    out = subprocess.run([apd, "-d", str(ours), "--use_sa", use_sa, "--dataset", dataset], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout[-1500:]
     assert "Round nums: %d" % rounds in out.stdout and "Round nums: %d" % rounds in log_a
+    if sa:
+        assert "sa masks: %d of %d views" % (V, V) in out.stdout and "resize sa mask to target size" in log_a
     agree, self_agree, dshare = [], [], []
     for v in range(V):
         m = {}
@@ -190,7 +206,7 @@ def test_cli_against_the_reference_main(tmp_path, dataset, W, H, weak, rounds):
         head = open(p, "rb").read(400)
         return int(head.split(b"element vertex ")[1].split(b"\n")[0])
     n_o, n_a, n_b = ply_count(ours / "APD" / "APD.ply"), ply_count(ra / "APD" / "APD.ply"), ply_count(rb / "APD" / "APD.ply")
-    print(dataset, "apd vs reference main(): depth within 1%% per view %s (reference vs itself %s); state-share difference %.3f; fused points "
+    print(dataset, "sa" if sa else "", "apd vs reference main(): depth within 1%% per view %s (reference vs itself %s); state-share difference %.3f; fused points "
           "ours %d, reference %d / %d" % (np.round(agree, 4), np.round(self_agree, 4), max(dshare), n_o, n_a, n_b))
     assert min(agree) >= min(0.99, min(self_agree) - 0.01)
     assert max(dshare) < 0.05

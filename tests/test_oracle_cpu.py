@@ -68,6 +68,55 @@ def test_oracle_matches_reference_ncc_new():
     assert (d <= 1e-4).mean() >= 0.97 and (d <= 1e-3).mean() >= 0.99
 
 
+GOLDEN_SA = os.path.join(ROOT, "tests", "golden", "ref_costs_sa.npz")
+
+
+def test_oracle_matches_reference_with_segment_labels():
+    """NCC-Old branch B (APD.cu:664-719) and the label tests of NCC-New (APD.cu:493-497, 526-530) as executed by the reference
+    binary on a B200 with a label map in sa_mask_cuda (tests/golden/make_ref_golden_sa.py)"""
+    z, zs = np.load(GOLDEN), np.load(GOLDEN_SA)
+    pb, _ = _golden_problem(z)
+    pb.set_sa_mask(zs["labels"])
+    got = pb.eval_costs(z["old_tuples"], z["old_planes"], 0)
+    d = _stats("NCC-Old + labels oracle vs reference", got, zs["old_costs"])
+    assert (d <= 1e-4).mean() >= 0.98 and (d <= 1e-3).mean() >= 0.995
+    assert (np.abs(zs["old_costs"] - z["old_costs"]) > 1e-3).mean() > 0.2  # the map matters on this input
+    pb, _ = _golden_problem(z, use_apd=1)
+    pb.set_sa_mask(zs["labels"])
+    pb.weak_info[...] = z["new_weak"]
+    pb.anchors[...] = z["new_anchors"]
+    pb.selected_views[...] = z["new_sel"]
+    got = pb.eval_costs(z["new_tuples"], z["new_planes"], 1)
+    d = _stats("NCC-New + labels oracle vs reference", got, zs["new_costs"])
+    assert (d <= 1e-4).mean() >= 0.97 and (d <= 1e-3).mean() >= 0.99
+    assert (np.abs(zs["new_costs"] - z["new_costs"]) > 1e-3).mean() > 0.05
+
+
+def test_oracle_segment_label_properties():
+    """size-independent properties of the label path: an all-zero map is no map; one segment covering the image leaves NCC-New
+    unchanged (same taps, same order) and turns NCC-Old into the quadrant walk over the same 36 taps (same samples, another
+    summation order: equal up to fp32 rounding on textured patches)"""
+    z = np.load(GOLDEN)
+    pb, _ = _golden_problem(z)
+    h, w = z["images"][0].shape
+    base = pb.eval_costs(z["old_tuples"], z["old_planes"], 0)
+    pb.set_sa_mask(np.zeros((h, w), np.uint8))
+    assert np.array_equal(pb.eval_costs(z["old_tuples"], z["old_planes"], 0), base)
+    pb.set_sa_mask(np.full((h, w), 7, np.uint8))
+    one = pb.eval_costs(z["old_tuples"], z["old_planes"], 0)
+    t = z["old_tuples"]
+    inner = (t[:, 0] >= 5) & (t[:, 0] < w - 5) & (t[:, 1] >= 5) & (t[:, 1] < h - 5)  # branch B skips taps outside the image
+    ok = inner & (base < 1.9)
+    assert np.abs(one - base)[ok].max() < 5e-3 and (np.abs(one - base)[ok] <= 1e-4).mean() > 0.9
+    pb, _ = _golden_problem(z, use_apd=1)
+    pb.weak_info[...] = z["new_weak"]
+    pb.anchors[...] = z["new_anchors"]
+    pb.selected_views[...] = z["new_sel"]
+    base = pb.eval_costs(z["new_tuples"], z["new_planes"], 1)
+    pb.set_sa_mask(np.full((h, w), 7, np.uint8))
+    assert np.array_equal(pb.eval_costs(z["new_tuples"], z["new_planes"], 1), base)
+
+
 def test_oracle_pass_vs_reference_pass_statistical():
     """whole photometric pass: the reference (XORWOW, seed patched) and the oracle (Philox) are different random
     processes, so parity is statistical: on textured pixels both must sit within 1 % of the ground truth"""

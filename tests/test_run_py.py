@@ -32,6 +32,11 @@ def test_dry_run_commands_layout_and_order(tmp_path):
     for l in lines:  # booleans take a value, spelled as main.cpp:9-24 expects them
         assert "--dataset ETH3D" in l and "--weak_filter false" in l and "--export_color false" in l and "--use_impetus true" in l
         assert "--use_sa false" in l and "--only_fuse false" in l
+    # label maps of tools/run_SAM.py already in the scan are consumed unless --no_sam (run.py:94-98, 113)
+    os.makedirs(os.path.join(root, "big", "sa_masks"))
+    for extra, want in (([], "--use_sa true"), (["--no_sam"], "--use_sa false")):
+        out = subprocess.run([sys.executable, RUN, "--data_dir", root, "--scans", "big", "--dry_run"] + extra, capture_output=True, text=True)
+        assert want in out.stdout, out.stdout
     # --no_image_symlink: the alternative layout is left alone and the scan cannot run
     root2 = str(tmp_path / "other")
     _mk(root2, "s", "undist/images", ["00000000.jpg"])
