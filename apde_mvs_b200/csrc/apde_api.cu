@@ -669,8 +669,7 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
     // N x more parallelism for few pixels); for the dense strong class the fused one-thread-per-pixel kernel is faster (165 vs
     // 179 ms: no intermediate buffers, no second pass over the reference patch).  APDE_PIPELINE_STRONG=1 forces the pipeline.
     static const bool pipe_strong = [] { const char *e = getenv("APDE_PIPELINE_STRONG"); return e && e[0] == '1'; }();
-    // problems with a segment-label map run the thread-per-pixel kernels (their <SA> twins, apde_device.cuh)
-    const bool pipeline = prop_stage && !legacy_prop && !c->K.sa && !getenv("APDE_QUAD_KERNELS") && (stage == APDE_STAGE_PROP_WEAK || pipe_strong);
+    const bool pipeline = prop_stage && !legacy_prop && !getenv("APDE_QUAD_KERNELS") && (stage == APDE_STAGE_PROP_WEAK || pipe_strong);
     if (prop_stage && (c->params.use_APD || pipeline)) {
         // compacted (colour, class) pixel lists: no lane idles on the other class, and the column kernels index by list slot
         if (c->lists_dirty) { const int rc = build_lists(c); if (rc) return rc; }
@@ -704,7 +703,7 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
             return prop_half_sweep(Kq, c->prop, stage == APDE_STAGE_PROP_WEAK, Kq.list, Kq.list_count, c->h_list_counts[cls], iter, c->stream,
                                    &c->launches);
         }
-        if (!legacy && !Kq.sa && !getenv("APDE_QUAD_KERNELS")) {
+        if (!legacy && !getenv("APDE_QUAD_KERNELS")) {
             // (the sweep functions count every launch but the last one; the generic count below adds that)
             if (stage == APDE_STAGE_DEPTH_TO_WEAK) {
                 float *curve = nullptr;

@@ -525,16 +525,17 @@ struct AnchorRefSa : AnchorRef {
     unsigned short tmask[8];
 };
 
-template <bool U>
-__device__ __forceinline__ void load_anchor_ref_sa(const PassK &K, const short2 *anc, AnchorRefSa &ar, const SaInfo &si) {
+// label tests on an anchor cache whose taps (r), positions (a) are filled: anchors of another segment are dropped, taps of
+// another segment leave the sums (APD.cu:493-497, 526-530); tap values come from ar.r, so the column pipeline can apply this to
+// the cache it re-loads from global memory
+__device__ __forceinline__ void anchor_ref_apply_labels(const PassK &K, AnchorRefSa &ar, const SaInfo &si) {
     const uint8_t *sa = K.sa;
     const int W = K.W, H = K.H, lab = si.label;
 #pragma unroll 1
     for (int k = 0; k < 8; ++k) {
-        const short2 a = anc[k + 1];
-        ar.a[k] = a;
-        if (a.x == -1 || a.y == -1) { ar.a[k].x = -1; continue; }
-        if (lab != 0 && sa[a.x + a.y * W] != lab) { ar.a[k].x = -1; continue; }  // APD.cu:493-497
+        const short2 a = ar.a[k];
+        if (a.x == -1) continue;
+        if (lab != 0 && sa[a.x + a.y * W] != lab) { ar.a[k].x = -1; continue; }
         float sr = 0.0f, srr = 0.0f;
         int t = 0, cnt = 0;
         unsigned tm = 0u;
@@ -542,10 +543,10 @@ __device__ __forceinline__ void load_anchor_ref_sa(const PassK &K, const short2 
         for (int i = -5; i <= 5; i += 5) {
 #pragma unroll
             for (int j = -5; j <= 5; j += 5) {
-                const float r = fetch<U>(K, (float)(a.x + i) + 0.5f, (float)(a.y + j) + 0.5f, K.ref_layer);
-                ar.r[k * 9 + t] = r;
+                // the reference indexes the label map without a bounds test (APD.cu:527); clamped here
                 const int x = clampi(a.x + i, 0, W - 1), y = clampi(a.y + j, 0, H - 1);
                 if (lab == 0 || sa[y * W + x] == lab) {
+                    const float r = ar.r[k * 9 + t];
                     tm |= 1u << t;
                     sr += r;
                     srr = fmaf(r, r, srr);
@@ -559,6 +560,12 @@ __device__ __forceinline__ void load_anchor_ref_sa(const PassK &K, const short2 
         ar.mean[k] = ar.inv[k] * sr;
         ar.var[k] = fmaf(ar.inv[k], srr, -__fmul_rn(ar.mean[k], ar.mean[k]));
     }
+}
+
+template <bool U>
+__device__ __forceinline__ void load_anchor_ref_sa(const PassK &K, const short2 *anc, AnchorRefSa &ar, const SaInfo &si) {
+    load_anchor_ref<U>(K, anc, ar);
+    anchor_ref_apply_labels(K, ar, si);
 }
 
 template <bool U>

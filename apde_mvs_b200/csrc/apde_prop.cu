@@ -111,7 +111,7 @@ __device__ __forceinline__ void load_anchor_ref_g(const PropK &B, int pix, Ancho
 }
 
 // ------------------------------------------------------------------------------------------------ P1 phase-1 columns
-template <bool WEAK, bool U>
+template <bool WEAK, bool U, bool SA>
 __device__ __forceinline__ void k_prop_eval1_body(const PassK &K, const PropK &B) {
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y;
@@ -121,8 +121,11 @@ __device__ __forceinline__ void k_prop_eval1_body(const PassK &K, const PropK &B
     const ViewK &vk = K.v[v];  // warp-uniform: served from the constant bank
     RefPatch rp;
     load_ref_patch_g(B, pix, rp);
-    AnchorRef ar;
+    typename SaTypes<SA>::Anchors ar;
     if (WEAK) load_anchor_ref_g(B, pix, ar);
+    typename SaTypes<SA>::Info si;
+    load_sa<SA>(K, px, py, rp, si);
+    if constexpr (SA) { if (WEAK) anchor_ref_apply_labels(K, ar, si); }
     const unsigned flags = B.cand_flags[pix] & 0xffu;
     unsigned n_eval = 0;
 #pragma unroll 1
@@ -131,7 +134,7 @@ __device__ __forceinline__ void k_prop_eval1_body(const PassK &K, const PropK &B
         if (h == 8 || ((flags >> h) & 1u)) {
             const float4 pl = (h == 8) ? K.planes[center] : K.planes[B.cand_pos[(size_t)h * B.cap + pix]];
             const float3 m = plane_row(K, pl);
-            c = WEAK ? ncc_new<U>(K, vk, v, px, py, m, rp, ar) : ncc_old<U>(K, vk, px, py, m, rp);
+            c = WEAK ? ncc_new_x<U, SA>(K, vk, v, px, py, m, rp, ar, si) : ncc_old_x<U, SA>(K, vk, px, py, m, rp, si);
             n_eval++;
         } else {
             c = (h == 0 && v == 0) ? 2.0f : 0.0f;  // quirk 2: "cost_array[8][32] = {2.0f}" zero-fills all but [0][0]
@@ -140,10 +143,10 @@ __device__ __forceinline__ void k_prop_eval1_body(const PassK &K, const PropK &B
     }
     count_evals(K, WEAK ? 0 : n_eval, WEAK ? n_eval : 0, 0);
 }
-template <bool WEAK>
+template <bool WEAK, bool SA>
 __global__ void __launch_bounds__(128) k_prop_eval1(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
-    if (K.tex_unorm > 0.0f) k_prop_eval1_body<WEAK, true>(K, B);
-    else k_prop_eval1_body<WEAK, false>(K, B);
+    if (K.tex_unorm > 0.0f) k_prop_eval1_body<WEAK, true, SA>(K, B);
+    else k_prop_eval1_body<WEAK, false, SA>(K, B);
 }
 
 
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(256) k_prop_scatter(const int *__restrict__ fl
 // ------------------------------------------------------------------------------------------------ P3 phase-3 columns
 // mode (weak only): 0 = all hypotheses in one launch (slot 8 duplicates slot 3 and is skipped); 1 = the fit plane only
 // (slot 0); 2 = the five random hypotheses that follow the outcome of the fit test (slots base3 .. base3 + 4)
-template <bool WEAK, bool U>
+template <bool WEAK, bool U, bool SA>
 __device__ __forceinline__ void k_prop_eval3_body(const PassK &K, const PropK &B, int mode) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
@@ -380,8 +383,11 @@ __device__ __forceinline__ void k_prop_eval3_body(const PassK &K, const PropK &B
     const ViewK &vk = s_vk[v];
     RefPatch rp;
     load_ref_patch_g(B, pix, rp);
-    AnchorRef ar;
+    typename SaTypes<SA>::Anchors ar;
     if (WEAK) load_anchor_ref_g(B, pix, ar);
+    typename SaTypes<SA>::Info si;
+    load_sa<SA>(K, px, py, rp, si);
+    if constexpr (SA) { if (WEAK) anchor_ref_apply_labels(K, ar, si); }
     const bool geom = WEAK ? (K.geom != 0) : (K.geom && K.impetus);
     int i0 = 0, nh = WEAK ? 11 : 5;
     if (WEAK && mode == 1) nh = 1;
@@ -392,17 +398,17 @@ __device__ __forceinline__ void k_prop_eval3_body(const PassK &K, const PropK &B
         if (WEAK && mode == 0 && i == 8) continue;  // (random depth, random normal): the same plane as slot 3
         const float4 tp = B.hyp[(size_t)i * cap + pix];
         const float3 m = plane_row(K, tp);
-        float c = WEAK ? ncc_new<U>(K, vk, v, px, py, m, rp, ar) : ncc_old<U>(K, vk, px, py, m, rp);
+        float c = WEAK ? ncc_new_x<U, SA>(K, vk, v, px, py, m, rp, ar, si) : ncc_old_x<U, SA>(K, vk, px, py, m, rp, si);
         n_eval++;
         if (geom) { c = c + K.geom_factor * geom_cost(K, vk, v, px, py, tp); n_geom++; }
         B.cost3[(size_t)i * nflat + col] = c;
     }
     count_evals(K, WEAK ? 0 : n_eval, WEAK ? n_eval : 0, n_geom);
 }
-template <bool WEAK>
+template <bool WEAK, bool SA>
 __global__ void __launch_bounds__(128) k_prop_eval3(const __grid_constant__ PassK K, const __grid_constant__ PropK B, int mode) {
-    if (K.tex_unorm > 0.0f) k_prop_eval3_body<WEAK, true>(K, B, mode);
-    else k_prop_eval3_body<WEAK, false>(K, B, mode);
+    if (K.tex_unorm > 0.0f) k_prop_eval3_body<WEAK, true, SA>(K, B, mode);
+    else k_prop_eval3_body<WEAK, false, SA>(K, B, mode);
 }
 
 // weak pixels, between the two refinement rounds: does the fit plane get accepted (APD.cu:1046-1052)?  The answer selects
@@ -535,7 +541,10 @@ static cudaError_t run_half_sweep(const PassK &K, PropWorkspace &ws, const int *
     const size_t vsm = sizeof(float) * views_smem_floats(N);
     if (pb == 0) return cudaSuccess;
     k_prop_candidates<WEAK><<<pb, 128, 0, st>>>(K, B);
-    k_prop_eval1<WEAK><<<dim3(pb, N), 128, 0, st>>>(K, B);
+    // problems with a segment-label map: the <SA> twins of the two evaluation kernels (labels re-read per column, the anchor
+    // cache re-masked in registers; see "segment labels" in apde_device.cuh)
+    if (K.sa) k_prop_eval1<WEAK, true><<<dim3(pb, N), 128, 0, st>>>(K, B);
+    else k_prop_eval1<WEAK, false><<<dim3(pb, N), 128, 0, st>>>(K, B);
     // flags3 of pixels beyond the list (previous, longer half-sweeps) must not create columns
     PCU(cudaMemsetAsync(ws.flags3, 0, (nflat + 1) * sizeof(int), st));
     k_prop_select<WEAK><<<pb, 128, vsm, st>>>(K, B, iter);
@@ -547,14 +556,17 @@ static cudaError_t run_half_sweep(const PassK &K, PropWorkspace &ws, const int *
     const char *one = getenv("APDE_WEAK_ONE_ROUND");  // A/B switch: all 10 distinct hypotheses in one launch
     const int one_round = (!WEAK || (one && one[0] == '1')) ? 1 : 0;
     if (one_round) {
-        k_prop_eval3<WEAK><<<cb, 128, vsm, st>>>(K, B, 0);
+        if (K.sa) k_prop_eval3<WEAK, true><<<cb, 128, vsm, st>>>(K, B, 0);
+        else k_prop_eval3<WEAK, false><<<cb, 128, vsm, st>>>(K, B, 0);
         if (launches) *launches += 8;
     } else {
         // the five random hypotheses of a weak pixel depend on whether its fit plane is accepted (APD.cu:1046-1067): evaluate
         // the fit plane, decide, then evaluate only the set that applies -- 6 deformable evaluations per column instead of 10
-        k_prop_eval3<WEAK><<<cb, 128, vsm, st>>>(K, B, 1);
+        if (K.sa) k_prop_eval3<WEAK, true><<<cb, 128, vsm, st>>>(K, B, 1);
+        else k_prop_eval3<WEAK, false><<<cb, 128, vsm, st>>>(K, B, 1);
         k_prop_fit_test<<<pb, 128, 0, st>>>(K, B);
-        k_prop_eval3<WEAK><<<cb, 128, vsm, st>>>(K, B, 2);
+        if (K.sa) k_prop_eval3<WEAK, true><<<cb, 128, vsm, st>>>(K, B, 2);
+        else k_prop_eval3<WEAK, false><<<cb, 128, vsm, st>>>(K, B, 2);
         if (launches) *launches += 10;
     }
     k_prop_final<WEAK><<<pb, 128, 0, st>>>(K, B, one_round);

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) k_sweep_scatter(const int *__restrict__ f
     if (i < nflat && flags[i]) colmap[colidx[i]] = (int)i;
 }
 
-template <bool U>
+template <bool U, bool SA>
 __device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, int y0, int rows, int Pb,
                                                        const int *__restrict__ colmap, int ncols, float *__restrict__ ncc,
                                                        float *__restrict__ geo) {
@@ -85,6 +85,8 @@ __device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, in
     base_line /= valid_src;
     RefPatch rp;
     load_ref_patch<U>(K, px, py, rp);
+    typename SaTypes<SA>::Info si;
+    load_sa<SA>(K, px, py, rp, si);
     unsigned n_old = 0, n_geom = 0;
     const float fb = K.fx * base_line;
     const float disp = fb / origin_depth;
@@ -96,7 +98,7 @@ __device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, in
         float4 tp = opl;
         tp.w = distance_to_origin(K, px, py, p_depth, tp);
         const float3 m = plane_row(K, tp);
-        ncc[(size_t)(pd + kSweepR) * ncols + col] = ncc_old<U>(K, vk, px, py, m, rp);
+        ncc[(size_t)(pd + kSweepR) * ncols + col] = ncc_old_x<U, SA>(K, vk, px, py, m, rp, si);
         n_old++;
         if (K.geom) { geo[(size_t)(pd + kSweepR) * ncols + col] = geom_cost(K, vk, v, px, py, tp); n_geom++; }
     }
@@ -104,7 +106,7 @@ __device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, in
         float4 tp = opl;
         tp.w = distance_to_origin(K, px, py, origin_depth, tp);
         const float3 m = plane_row(K, tp);
-        ncc[(size_t)kSweepN * ncols + col] = ncc_old<U>(K, vk, px, py, m, rp);
+        ncc[(size_t)kSweepN * ncols + col] = ncc_old_x<U, SA>(K, vk, px, py, m, rp, si);
         n_old++;
         if (K.geom) { geo[(size_t)kSweepN * ncols + col] = geom_cost(K, vk, v, px, py, tp); n_geom++; }
     }
@@ -113,8 +115,15 @@ __device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, in
 __global__ void __launch_bounds__(128) k_sweep_columns(const __grid_constant__ PassK K, int dtw, int y0, int rows, int Pb,
                                                        const int *__restrict__ colmap, int ncols, float *__restrict__ ncc,
                                                        float *__restrict__ geo) {
-    if (K.tex_unorm > 0.0f) k_sweep_columns_body<true>(K, dtw, y0, rows, Pb, colmap, ncols, ncc, geo);
-    else k_sweep_columns_body<false>(K, dtw, y0, rows, Pb, colmap, ncols, ncc, geo);
+    if (K.tex_unorm > 0.0f) k_sweep_columns_body<true, false>(K, dtw, y0, rows, Pb, colmap, ncols, ncc, geo);
+    else k_sweep_columns_body<false, false>(K, dtw, y0, rows, Pb, colmap, ncols, ncc, geo);
+}
+// the same kernel for a problem with a segment-label map (see "segment labels" in apde_device.cuh)
+__global__ void __launch_bounds__(128) k_sweep_columns_sa(const __grid_constant__ PassK K, int dtw, int y0, int rows, int Pb,
+                                                          const int *__restrict__ colmap, int ncols, float *__restrict__ ncc,
+                                                          float *__restrict__ geo) {
+    if (K.tex_unorm > 0.0f) k_sweep_columns_body<true, true>(K, dtw, y0, rows, Pb, colmap, ncols, ncc, geo);
+    else k_sweep_columns_body<false, true>(K, dtw, y0, rows, Pb, colmap, ncols, ncc, geo);
 }
 
 
@@ -312,7 +321,8 @@ static cudaError_t sweep_build_band(const PassK &K, SweepWorkspace &ws, int dtw,
         if ((e = ws.reserve_columns((size_t)ncols, K.geom != 0)) != cudaSuccess) return e;
         const size_t vsm = sizeof(float) * views_smem_floats(K.N);
         k_sweep_scatter<<<(unsigned)((nflat + 255) / 256), 256, 0, st>>>(ws.flags, ws.colidx, nflat, ws.colmap);
-        k_sweep_columns<<<(ncols + 127) / 128, 128, vsm, st>>>(K, dtw, y0, rows, Pb, ws.colmap, ncols, ws.ncc, ws.geo);
+        if (K.sa) k_sweep_columns_sa<<<(ncols + 127) / 128, 128, vsm, st>>>(K, dtw, y0, rows, Pb, ws.colmap, ncols, ws.ncc, ws.geo);
+        else k_sweep_columns<<<(ncols + 127) / 128, 128, vsm, st>>>(K, dtw, y0, rows, Pb, ws.colmap, ncols, ws.ncc, ws.geo);
         if (launches) *launches += 2;
     }
     return cudaGetLastError();

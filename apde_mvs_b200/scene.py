@@ -208,3 +208,20 @@ def depth_accuracy(depth, gt, rel=0.01):
     valid = gt > 0
     ok = np.abs(depth - gt) <= rel * gt
     return float((ok & valid).sum()) / max(1, int(valid.sum()))
+
+
+def make_label_map(w, h, seed, zero_share=0.25):
+    """synthetic segment-label map in the format of tools/run_SAM.py (uint8, 0 = no segment): blocky segments with ragged
+    borders, label = 1 + cell index (mod 250), a share of the cells unlabelled, a few single-pixel segments"""
+    rng = np.random.default_rng(seed)
+    gy, gx = np.mgrid[0:h, 0:w]
+    jx = (6 * np.sin(gy / 9.0 + seed)).astype(int)
+    jy = (5 * np.cos(gx / 11.0 - seed)).astype(int)
+    cell = ((gx + jx) // 23) + 13 * ((gy + jy) // 19)
+    lut = (1 + np.arange(cell.max() + 1) % 250).astype(np.uint8)
+    lut[rng.random(len(lut)) < zero_share] = 0
+    lab = lut[cell]
+    # a few single-pixel segments (a pixel whose four diagonal neighbours all differ: empty quadrant walk)
+    ys, xs = rng.integers(8, h - 8, 40), rng.integers(8, w - 8, 40)
+    lab[ys, xs] = 251
+    return lab

@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import ref_params  # noqa: E402
 from oracle import binding as orc  # noqa: E402
 from oracle import ref_binding as ref  # noqa: E402
-from test_gpu_sa_mask import make_labels  # noqa: E402
+from apde_mvs_b200.scene import make_label_map as make_labels  # noqa: E402
 
 
 def main():

@@ -144,7 +144,7 @@ def test_cli_against_the_reference_main(tmp_path, dataset, W, H, weak, rounds, s
         cv2.imwrite(str(ours / "images" / ("%08d.png" % v)), scene.colors[v])  # colour inputs: grey conversion is part of the path
 
     if sa:
-        from test_gpu_sa_mask import make_labels
+        from apde_mvs_b200.scene import make_label_map as make_labels
         os.makedirs(ours / "sa_masks")
         for v in range(V):
             lab = make_labels(W // 2, H // 2, 30 + v, zero_share=0.2)

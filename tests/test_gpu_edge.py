@@ -154,3 +154,24 @@ def test_strong_propagation_kernel_variants_identical(tmp_path):
     assert sorted(a.files) == sorted(b.files) and len(a.files) == 20
     for k in a.files:
         assert np.array_equal(a[k], b[k]), "map %s differs between the compacted and the per-lane kernel" % k
+
+
+def test_segment_label_kernel_variants_identical(tmp_path):
+    """with segment-label maps on every view, the default kernels (SA twins of the column pipeline and of the sweep columns)
+    and the thread-per-pixel SA twins (APDE_LEGACY_PROP / APDE_LEGACY_SWEEP) give bit-identical maps over a two-round
+    schedule -- and the labels change the result"""
+    import os
+    import subprocess
+    import sys
+    from helpers import ROOT
+    outs = []
+    for env_extra in ({"APDE_DUMP_SA": "1"}, {"APDE_DUMP_SA": "1", "APDE_LEGACY_PROP": "1", "APDE_LEGACY_SWEEP": "1"}, {}):
+        out = str(tmp_path / ("maps_%d.npz" % len(outs)))
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "dump_maps.py"), out, "320", "240", "5", "4", "0.25", "2"],
+                              env=dict(os.environ, **env_extra), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        outs.append(np.load(out))
+    a, b, plain = outs
+    assert sorted(a.files) == sorted(b.files) and len(a.files) == 20
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), "map %s differs between the default and the thread-per-pixel kernels under labels" % k
+    assert any(not np.array_equal(a[k], plain[k]) for k in a.files if k.startswith("w"))
