@@ -125,6 +125,40 @@ def test_c2_shape_properties(ctx):
     assert (rel < 0.01).mean() > 0.9
 
 
+def test_c3_shape_weak_texture(ctx):
+    """configs[2] shape: 1600x1200 with weak-texture blobs over ~40 % of every surface (4 of the 49 views, 3 sources): two
+    rounds by the pyramid rule (1600 -> 800 <= 800), the second with the deformable (anchor) path on the WEAK pixels"""
+    from apde_mvs_b200.binding import default_schedule
+    from apde_mvs_b200.scene import make_office_scene
+    V, N = 4, 3
+    scene = make_office_scene(1600, 1200, num_views=V, num_src=N, seed=3, arc_deg=12.0, weak=0.4)
+    ctx.load_scene(scene)
+    sched = default_schedule()
+    sched.seed = 31
+    assert ctx.num_passes(sched) == 8
+    for p in range(4):
+        ctx.run_schedule_pass(sched, p)
+    weak_round0 = np.mean([(m[2] == 0).mean() for m in _download(ctx, V)])
+    ctx.counters(reset=True)
+    t_new = 0
+    for p in range(4, 8):
+        t_new += ctx.run_schedule_pass(sched, p).evals_ncc_new
+    maps = _download(ctx, V)
+    assert maps[0][0].shape == (1200, 1600)
+    accs, shares = _strong_accuracy(maps, scene)
+    wacc, wshare = [], []
+    for v, (d, _, wk, _) in enumerate(maps):
+        gt = scene.gt_depth[v]
+        sel = _interior((wk == 0) & (gt > 0))
+        wacc.append(float(_interior(np.abs(d - gt) <= 0.01 * gt)[sel].mean()))
+        wshare.append(float(sel.mean()))
+    print("C3 shape: weak share after round 0 %.3f; final STRONG accuracy %s share %s; WEAK accuracy %s share %s; deformable evals %d" % (
+        weak_round0, np.round(accs, 4), np.round(shares, 3), np.round(wacc, 4), np.round(wshare, 3), t_new))
+    assert weak_round0 > 0.15 and t_new > 1600 * 1200 * V * 0.15 * N * 10  # the anchor path carried a real share of the work
+    assert min(accs) >= 0.97
+    assert min(wacc) >= 0.7  # weak-texture pixels get their planes through the anchors (measured 0.78-0.87 on B200, r01)
+
+
 def test_c4_shape_three_levels(ctx):
     """configs[3] shape: 1920x1056 => three pyramid levels (480x264, 960x528, 1920x1056), 4 * 3 passes per view"""
     from apde_mvs_b200.binding import default_schedule
