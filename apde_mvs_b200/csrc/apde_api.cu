@@ -88,6 +88,7 @@ struct apde_context {
     bool ws_alloc = false;
     float4 *d_planes = nullptr, *d_fit = nullptr;
     uint8_t *d_sa = nullptr;  // segment labels of the active problem's reference view at the working size
+    ListScratch list_scratch;
     float *d_costs = nullptr, *d_depthws = nullptr, *d_scratch_depth = nullptr, *d_scratch_normal = nullptr;
     uint32_t *d_sel = nullptr;
     uint4 *d_vw = nullptr;
@@ -212,6 +213,7 @@ static void free_scene(apde_context *c) {
     c->d_skip = nullptr;
     cudaFree(c->d_sa);
     c->d_sa = nullptr;
+    c->list_scratch.release();
     fusion_release_cache();
     c->sweep.release();
     c->prop.release();
@@ -648,10 +650,10 @@ int apde_problem_dims(apde_context *c, int *width, int *height, int *num_images)
 // build (twice per pass), and saves launching worst-case grids for the sparse WEAK class: the column pipeline of a weak
 // half-sweep is ~10 launches over [N][capacity] arrays, ~1 ms each time even when the frame holds no WEAK pixel at all.
 static int build_lists(apde_context *c) {
-    CU(launch_build_lists(c->K, c->d_lists, c->d_list_counts, c->list_cap, c->stream));
+    CU(launch_build_lists(c->K, c->d_lists, c->d_list_counts, c->list_cap, c->list_scratch, c->stream));
     CU(cudaMemcpyAsync(c->h_list_counts, c->d_list_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->launches++;
+    c->launches += 2;  // k_list_count + k_list_fill (the scan between them is cub's)
     c->lists_dirty = false;
     return APDE_OK;
 }
@@ -671,11 +673,21 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
     static const bool pipe_strong = [] { const char *e = getenv("APDE_PIPELINE_STRONG"); return e && e[0] == '1'; }();
     const bool pipeline = prop_stage && !legacy_prop && !getenv("APDE_QUAD_KERNELS") && (stage == APDE_STAGE_PROP_WEAK || pipe_strong);
     if (prop_stage && (c->params.use_APD || pipeline)) {
-        // compacted (colour, class) pixel lists: no lane idles on the other class, and the column kernels index by list slot
         if (c->lists_dirty) { const int rc = build_lists(c); if (rc) return rc; }
         const int cls = (color << 1) | (stage == APDE_STAGE_PROP_WEAK ? 1 : 0);
-        Kl.list = c->d_lists + (size_t)cls * c->list_cap;
-        Kl.list_count = c->d_list_counts + cls;
+        // The fused strong kernel walks the list only when enough lanes of the implicit 8x8-tile mapping would idle on WEAK
+        // pixels.  Measured on B200 (r01, 1920x1080, 10 src, ~1 % WEAK): tile mapping 1731 ms per step vs 1896 ms through the
+        // list (72.8 % vs 66.5 % of the gather peak) -- list slots are appended in atomic order, so neighbouring CTAs work on
+        // distant tiles and warps straddle tiles.  APDE_STRONG_LIST_SHARE = share of same-colour pixels below which the list
+        // is used (0 = never, 1 = always; default 0.8).
+        static const float list_share = [] { const char *e = getenv("APDE_STRONG_LIST_SHARE"); return e ? (float)atof(e) : 0.8f; }();
+        const int ylimit = std::min(c->K.H, 32 * (((c->K.H / 2) + 15) / 16));  // rows the half-sweeps cover (quirk 7, APD.cu:2676-2678)
+        const bool dense = stage == APDE_STAGE_PROP_STRONG && !pipeline &&
+                           (float)c->h_list_counts[cls] >= list_share * 0.5f * (float)c->K.W * (float)ylimit;
+        if (!dense) {
+            Kl.list = c->d_lists + (size_t)cls * c->list_cap;
+            Kl.list_count = c->d_list_counts + cls;
+        }
     }
     // WEAK-only full-frame stages (GenAnchors, RANSAC plane fit) walk the two (colour, weak) lists instead of the whole grid.
     // The lists hold rows [0, half_rows_limit): only usable when that covers the frame (quirk 7 shapes fall back).

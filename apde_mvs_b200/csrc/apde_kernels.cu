@@ -723,47 +723,6 @@ __global__ void __launch_bounds__(128) k_local_refine_sa(const __grid_constant__
 }
 
 
-// -------------------------------------------------------------------------------------------- pixel lists
-// One pass over the 8x8 tiles: every pixel the red/black kernels would visit is appended to the list of its
-// (colour, strong | weak) class.  Warp-aggregated appends keep tile-local order, so a warp of the propagation kernels
-// still works on spatially close pixels.  lists: 4 arrays of `cap` ints; counts: 4 ints (zeroed by the caller).
-// One warp scans a (64 >> shift)-row x (1 << shift)-column tile of 64 pixels; shift = 3 is the 8x8 tile of half_pixel().
-__global__ void __launch_bounds__(128) k_build_lists(const __grid_constant__ PassK K, int tiles_x, int shift, int ylimit, int *lists,
-                                                     int *counts, int cap) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
-    const int tx = tile % tiles_x, ty = tile / tiles_x;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int l = lane + 32 * half;
-        const int px = (tx << shift) + (l & ((1 << shift) - 1)), py = ty * (64 >> shift) + (l >> shift);
-        const bool in = px < K.W && py < ylimit;
-        const int center = py * K.W + px;
-        const int cls = in ? ((((px + py) & 1) << 1) | (K.weak[center] == APDE_WEAK ? 1 : 0)) : -1;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const unsigned m = __ballot_sync(0xffffffffu, cls == c);
-            if (m == 0) continue;
-            int base = 0;
-            if (lane == __ffs(m) - 1) base = atomicAdd(&counts[c], __popc(m));
-            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-            if (cls == c) lists[(size_t)c * cap + base + __popc(m & ((1u << lane) - 1))] = center;
-        }
-    }
-}
-
-cudaError_t launch_build_lists(const PassK &K, int *lists, int *counts, int cap, cudaStream_t st) {
-    const int ylimit = min(K.H, half_rows_limit(K.H));
-    static const int shift = [] { const char *e = getenv("APDE_LIST_TILE_SHIFT"); const int v = e ? atoi(e) : 3; return v < 1 || v > 6 ? 3 : v; }();
-    const int tw = 1 << shift, th = 64 >> shift;
-    const int tiles_x = (K.W + tw - 1) / tw;
-    const int tiles = tiles_x * ((ylimit + th - 1) / th);
-    cudaError_t e = cudaMemsetAsync(counts, 0, 4 * sizeof(int), st);
-    if (e != cudaSuccess) return e;
-    k_build_lists<<<(tiles + 3) / 4, 128, 0, st>>>(K, tiles_x, shift, ylimit, lists, counts, cap);
-    return cudaGetLastError();
-}
-
 // -------------------------------------------------------------------------------------------- parity hook
 template <bool U, bool SA>
 __device__ __forceinline__ void k_eval_costs_body(const PassK &K, int n, const int *__restrict__ tuples,
@@ -778,8 +737,8 @@ __device__ __forceinline__ void k_eval_costs_body(const PassK &K, int n, const i
     } else {
         RefPatch rp;
         load_ref_patch<U>(K, px, py, rp);
-    typename SaTypes<SA>::Info si;
-    load_sa<SA>(K, px, py, rp, si);
+        typename SaTypes<SA>::Info si;
+        load_sa<SA>(K, px, py, rp, si);
         const float3 m = plane_row(K, pl);
         if (mode == 0) {
             c = ncc_old_x<U, SA>(K, K.v[v], px, py, m, rp, si);

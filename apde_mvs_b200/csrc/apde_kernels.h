@@ -16,7 +16,14 @@ cudaError_t launch_eval_costs(const PassK &K, int n, const int *tuples, const fl
                               cudaStream_t st);
 int prop_block_threads(int N);
 // compacted (colour, strong | weak) pixel lists for the checkerboard kernels: lists = 4 x cap ints, counts = 4 ints
-cudaError_t launch_build_lists(const PassK &K, int *lists, int *counts, int cap, cudaStream_t st);
+// scratch of the tile-ordered list build (apde_lists.cu): per-tile class counts, their scan
+struct ListScratch {
+    int *tile_counts = nullptr, *offsets = nullptr;
+    void *scan_tmp = nullptr;
+    size_t scan_bytes = 0, cap = 0;
+    void release();
+};
+cudaError_t launch_build_lists(const PassK &K, int *lists, int *counts, int cap, ListScratch &ls, cudaStream_t st);
 
 // red/black propagation as a pipeline of balanced column kernels (apde_prop.cu)
 struct PropK {  // device view of the workspace, passed by value
