@@ -382,7 +382,7 @@ inline float patch_ncc(const orc_problem *pb, const float *H, int src_idx, int c
     if (wsum == 0.0f) return -1.0f; /* only reachable in NCC-New with a label map: the caller skips the patch (APD.cu:543-545) */
     /* Epilogue exactly as nvcc compiles APD.cu:644-661 for sm_100 with the reference flags (SASS of the reference build:
      * MUFU.RCP; 3x FMUL; FMUL mean^2; FFMA(inv, sum_xx, -mean^2); FFMA(-mean_r, mean_s, E_rs); FFMA(-covar, 1/sqrt, 1)).
-     * MUFU.RCP(36) and MUFU.RCP(9) return the correctly rounded reciprocal (tools/probe_mufu.cu). */
+     * MUFU.RCP(36) and MUFU.RCP(9) return the correctly rounded reciprocal (tools/probe_mufu_rcp.cu). */
     const float inv = rcp_count(wsum);
     const float mean_ref = inv * sum_ref, mean_src = inv * sum_src, e_rs = inv * sum_ref_src;
     const float var_ref = std::fmaf(inv, sum_ref_ref, -(mean_ref * mean_ref));
