@@ -68,7 +68,7 @@ def build_host():
         srcs = common + [os.path.join(HOST_DIR, main_src)]
         if os.path.exists(out) and all(os.path.getmtime(h) < os.path.getmtime(out) for h in hdrs + [lib]):
             continue
-        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-o", out] + srcs +
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-pthread", "-o", out] + srcs +
                               ["-L" + OUT_DIR, "-lapde", "-lz", "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64", "-lcudart",
                                "-Wl,-rpath,/usr/local/cuda/lib64"])
     return APD_BIN

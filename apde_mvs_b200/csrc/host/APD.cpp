@@ -26,32 +26,33 @@ std::shared_ptr<SceneSession> SceneSession::get(const path &dense_folder, int gp
     for (auto &p : s->problems) max_id = std::max(max_id, p.ref_image_id);
     s->id_to_view.assign(max_id + 1, -1);
     for (size_t i = 0; i < s->problems.size(); ++i) s->id_to_view[s->problems[i].ref_image_id] = (int)i;
+    // Decoding is the host cost of a scene (a 24-megapixel JPEG takes ~1.5 s for its grey and colour versions): views are read
+    // by a batch of threads (LoadViews, apd_io.cpp) and uploaded in view order; one batch of decoded views is alive at a time.
+    const size_t n_views = s->problems.size();
+    const size_t batch_size = LoadViewsBatchSize(n_views);
     bool begun = false;
-    for (size_t i = 0; i < s->problems.size(); ++i) {
-        const auto &p = s->problems[i];
-        Mat gray, bgr;
-        const path img = dense_folder / "images" / (ToFormatIndex(p.ref_image_id) + p.img_ext);
-        if (!ReadImage(img, gray)) throw std::runtime_error("Images may error, check it!");
-        ReadImageColor(img, bgr);
-        if (!begun) {
-            s->width = gray.cols; s->height = gray.rows;
-            check(apde_scene_begin(s->ctx, (int)s->problems.size(), s->width, s->height), "apde_scene_begin");
-            begun = true;
-        } else if (gray.cols != s->width || gray.rows != s->height) {
-            throw std::runtime_error("Images may error, check it!");  // CheckImages, main.cpp:104-127
-        }
-        Camera cam;
-        if (!ReadCamera(dense_folder / "cams" / (ToFormatIndex(p.ref_image_id) + "_cam.txt"), cam)) throw std::runtime_error("can not read camera of image " + ToFormatIndex(p.ref_image_id));
-        cam.width = s->width; cam.height = s->height;
-        s->cameras.push_back(cam);
-        check(apde_scene_set_view(s->ctx, (int)i, gray.data(), bgr.empty() ? nullptr : bgr.data(), &cam), "apde_scene_set_view");
-        s->has_color = !bgr.empty();
-        // segment labels from tools/run_SAM.py, if the folder has them (APD.cpp:507, 641-649); consumed by passes with use_sa
-        const path sa_path = dense_folder / "sa_masks" / (ToFormatIndex(p.ref_image_id) + ".bin");
-        if (std::filesystem::exists(sa_path)) {
-            Mat sa;
-            if (ReadBinMat(sa_path, sa) && sa.type() == CV_8UC1 && !sa.empty()) {
-                check(apde_view_set_sa_mask(s->ctx, (int)i, sa.data(), sa.cols, sa.rows), "apde_view_set_sa_mask");
+    for (size_t first = 0; first < n_views; first += batch_size) {
+        std::vector<LoadedView> batch;
+        LoadViews(dense_folder, s->problems, first, std::min(batch_size, n_views - first), batch);
+        for (size_t k = 0; k < batch.size(); ++k) {
+            const size_t i = first + k;
+            const auto &p = s->problems[i];
+            LoadedView &l = batch[k];
+            if (!l.image_ok) throw std::runtime_error("Images may error, check it!");
+            if (!begun) {
+                s->width = l.gray.cols; s->height = l.gray.rows;
+                check(apde_scene_begin(s->ctx, (int)n_views, s->width, s->height), "apde_scene_begin");
+                begun = true;
+            } else if (l.gray.cols != s->width || l.gray.rows != s->height) {
+                throw std::runtime_error("Images may error, check it!");  // CheckImages, main.cpp:104-127
+            }
+            if (!l.cam_ok) throw std::runtime_error("can not read camera of image " + ToFormatIndex(p.ref_image_id));
+            l.cam.width = s->width; l.cam.height = s->height;
+            s->cameras.push_back(l.cam);
+            check(apde_scene_set_view(s->ctx, (int)i, l.gray.data(), l.bgr.empty() ? nullptr : l.bgr.data(), &l.cam), "apde_scene_set_view");
+            s->has_color = !l.bgr.empty();
+            if (!l.sa.empty()) {
+                check(apde_view_set_sa_mask(s->ctx, (int)i, l.sa.data(), l.sa.cols, l.sa.rows), "apde_view_set_sa_mask");
                 s->num_sa_masks++;
             }
         }

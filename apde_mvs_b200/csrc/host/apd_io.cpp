@@ -8,6 +8,8 @@
 #include <iomanip>
 #include <iostream>
 #include <sstream>
+#include <thread>
+#include <algorithm>
 
 namespace apd {
 
@@ -284,6 +286,30 @@ bool GenerateSampleList(const path &dense_folder, std::vector<ProblemDesc> &prob
         problems.push_back(pr);
     }
     return true;
+}
+
+size_t LoadViewsBatchSize(size_t num_views) {
+    const size_t hw = std::max<size_t>(1, std::thread::hardware_concurrency());
+    return std::max<size_t>(1, std::min<size_t>({hw, num_views, (size_t)16}));
+}
+
+void LoadViews(const path &dense_folder, const std::vector<ProblemDesc> &problems, size_t first, size_t count, std::vector<LoadedView> &out) {
+    out.clear();
+    out.resize(count);
+    auto load_one = [&](size_t k) {
+        const ProblemDesc &p = problems[first + k];
+        LoadedView &l = out[k];
+        const path img = dense_folder / "images" / (ToFormatIndex(p.ref_image_id) + p.img_ext);
+        l.image_ok = ReadImage(img, l.gray);
+        if (l.image_ok) ReadImageColor(img, l.bgr);
+        l.cam_ok = ReadCamera(dense_folder / "cams" / (ToFormatIndex(p.ref_image_id) + "_cam.txt"), l.cam);
+        const path sa_path = dense_folder / "sa_masks" / (ToFormatIndex(p.ref_image_id) + ".bin");
+        if (std::filesystem::exists(sa_path) && !(ReadBinMat(sa_path, l.sa) && l.sa.type() == CV_8UC1 && !l.sa.empty())) l.sa = Mat();
+    };
+    if (count == 1) { load_one(0); return; }
+    std::vector<std::thread> pool;
+    for (size_t k = 0; k < count; ++k) pool.emplace_back(load_one, k);
+    for (auto &t : pool) t.join();
 }
 
 }  // namespace apd

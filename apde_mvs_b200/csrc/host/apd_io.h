@@ -68,4 +68,16 @@ struct ProblemDesc {  // main.h:102-115 (the fields the schedule needs)
 // pair.txt parser with the reference's rules: score <= 0 entries dropped, result folder APD/<id>/ created
 bool GenerateSampleList(const path &dense_folder, std::vector<ProblemDesc> &problems, std::string *err);
 
+// Everything a view brings from disk: grey and BGR image (ReadImage / ReadImageColor), camera (ReadCamera) and, when
+// <dense>/sa_masks/<id>.bin exists, its segment-label map (CV_8UC1, tools/run_SAM.py:41-60; APD.cpp:507, 641-649)
+struct LoadedView {
+    Mat gray, bgr, sa;
+    Camera cam;
+    bool image_ok = false, cam_ok = false;
+};
+// views [first, first + count) of `problems`, decoded by one thread each (the reference's ThreadPool idea, APD.cpp:1040,
+// applied to CheckImages / ReadImage, main.cpp:104-127); results in view order
+void LoadViews(const path &dense_folder, const std::vector<ProblemDesc> &problems, size_t first, size_t count, std::vector<LoadedView> &out);
+size_t LoadViewsBatchSize(size_t num_views);  // min(hardware threads, views, 16)
+
 }  // namespace apd

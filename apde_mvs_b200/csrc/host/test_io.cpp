@@ -1,4 +1,5 @@
 // test_io.cpp -- CPU-only exerciser of the host I/O layer for tests/test_host_io.py (no GPU calls; links libapde only for symbols)
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -74,6 +75,23 @@ int main(int argc, char **argv) {
         std::string err;
         if (!GenerateSampleList(argv[2], pr, &err)) { std::cout << err << std::endl; return 1; }
         for (auto &p : pr) { printf("%d %s:", p.ref_image_id, p.img_ext.c_str()); for (int s : p.src_image_ids) printf(" %d", s); printf("\n"); }
+        return 0;
+    }
+    if (cmd == "load") {  // load <dense_folder>: every view through LoadViews (threaded batches), one line of checksums per view
+        std::vector<ProblemDesc> pr;
+        std::string err;
+        if (!GenerateSampleList(argv[2], pr, &err)) { std::cout << err << std::endl; return 1; }
+        const size_t bs = LoadViewsBatchSize(pr.size());
+        for (size_t first = 0; first < pr.size(); first += bs) {
+            std::vector<LoadedView> batch;
+            LoadViews(argv[2], pr, first, std::min(bs, pr.size() - first), batch);
+            for (size_t k = 0; k < batch.size(); ++k) {
+                const LoadedView &l = batch[k];
+                auto sum = [](const Mat &m) { unsigned long long a = 0; for (size_t i = 0; i < m.buf.size(); ++i) a = a * 1315423911ull + m.buf[i]; return a; };
+                printf("%d %d %d %dx%d %llu %llu %llu %.9g %.9g\n", pr[first + k].ref_image_id, (int)l.image_ok, (int)l.cam_ok, l.gray.cols, l.gray.rows,
+                       sum(l.gray), sum(l.bgr), sum(l.sa), l.cam_ok ? l.cam.K[0] : 0.0f, l.cam_ok ? l.cam.depth_min : 0.0f);
+            }
+        }
         return 0;
     }
     if (cmd == "ply") {  // ply <out.ply>

@@ -240,3 +240,52 @@ def test_show_pictures_follow_the_reference(tool, tmp_path):
     lo_c, hi_c = int(conf.min()), int(conf.max())
     want_c = ((conf.astype(int) - lo_c) * 255 // max(hi_c - lo_c, 1)).astype(np.uint8)
     assert np.array_equal(cv2.imread(str(tmp_path / "confidence_3.png"), cv2.IMREAD_UNCHANGED), want_c)
+
+
+def test_threaded_view_loader_matches_serial_decoding(tool, tmp_path):
+    """LoadViews (the scene loader of the `apd` CLI: one decoding thread per view, batches of min(cores, views, 16)) returns,
+    in view order, exactly what ReadImage / ReadImageColor / ReadCamera / ReadBinMat give one by one -- 19 views, so that more
+    than one batch runs; JPEG and PNG inputs, a label map for some views only, one undecodable image"""
+    import cv2
+    rng = np.random.default_rng(11)
+    d = tmp_path / "scan"
+    os.makedirs(d / "images"); os.makedirs(d / "cams"); os.makedirs(d / "sa_masks")
+    V, w, h = 19, 96, 64
+    imgs, labels = [], {}
+    for v in range(V):
+        img = _natural(w, h, rng)
+        ext = ".jpg" if v % 2 else ".png"
+        if v != 7:
+            cv2.imwrite(str(d / "images" / ("%08d%s" % (v, ext))), img)
+        else:
+            open(d / "images" / ("%08d%s" % (v, ext)), "wb").write(b"not an image at all")
+        imgs.append(str(d / "images" / ("%08d%s" % (v, ext))))
+        with open(d / "cams" / ("%08d_cam.txt" % v), "w") as f:
+            f.write("extrinsic\n1 0 0 %d\n0 1 0 0\n0 0 1 0\n0 0 0 1\n\nintrinsic\n%d 0 48\n0 %d 32\n0 0 1\n\n%g 0.01 192 3.5\n" % (v, 100 + v, 100 + v, 1.5 + v))
+        if v % 3 == 0:
+            labels[v] = rng.integers(0, 9, (h // 2, w // 2), dtype=np.uint8)
+            _write_bin(d / "sa_masks" / ("%08d.bin" % v), labels[v], 0)
+    with open(d / "pair.txt", "w") as f:
+        f.write("%d\n" % V)
+        for v in range(V):
+            f.write("%d\n2 %d 1.0 %d 1.0\n" % (v, (v + 1) % V, (v + 2) % V))
+    # view 7 is not decodable: the loader reports image_ok = 0 for it (the CLI then stops with the reference's message)
+    out = subprocess.run([tool, "load", str(d)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = [l.split() for l in out.stdout.splitlines() if l and l[0].isdigit() and len(l.split()) == 9]
+    assert [int(l[0]) for l in lines] == list(range(V))  # view order kept across batches
+
+    def chk(a):
+        s = 0
+        for b in np.ascontiguousarray(a).ravel().tolist():
+            s = (s * 1315423911 + b) & 0xFFFFFFFFFFFFFFFF
+        return s
+    for v, l in enumerate(lines):
+        if v == 7:
+            assert l[1] == "0"
+            continue
+        assert l[1] == "1" and l[2] == "1" and l[3] == "%dx%d" % (w, h)
+        assert int(l[4]) == chk(cv2.imread(imgs[v], cv2.IMREAD_GRAYSCALE))
+        assert int(l[5]) == chk(cv2.imread(imgs[v], cv2.IMREAD_COLOR))
+        assert int(l[6]) == (chk(labels[v]) if v in labels else 0)
+        assert float(l[7]) == 100 + v and abs(float(l[8]) - (1.5 + v)) < 1e-6
