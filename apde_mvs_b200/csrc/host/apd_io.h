@@ -56,6 +56,19 @@ bool ShowNormalMap(const path &normal_path, const Mat &normal);
 bool ShowWeakImage(const path &weak_path, const Mat &weak);
 bool ShowConfidenceMap(const path &confidence_path, const Mat &confidence);
 void JetColorMap(uint8_t bgr[256][3]);  // cv::COLORMAP_JET
+// The four pictures of one view (main.cpp:191-204) written by worker threads while the caller goes on with the next GPU pass:
+// encoding a 1920x1080 view takes 0.5-1.2 s of one core, more than the PatchMatch pass that produced it.  At most
+// min(cores, 16) views are in flight, fewer when their maps would hold more than ~2 GB; wait() (also the destructor) joins.
+class ShowWriter {
+public:
+    ShowWriter();
+    ~ShowWriter();
+    void submit(const path &result_folder, int iteration, Mat depth, Mat normal, Mat weak, Mat confidence, float depth_min, float depth_max);
+    void wait();
+private:
+    struct Impl;
+    Impl *impl;
+};
 bool ExportPointCloud(const path &ply_path, const std::vector<PointList> &pc, bool export_color = true);
 std::string ToFormatIndex(int index);
 

@@ -2,8 +2,13 @@
 // (main.cpp:191-204, 359): depth_<it>.jpg (jet ramp over mean +- 2 sigma), normal_<it>.jpg, weak_<it>.png, confidence_<it>.png.
 // Pixel values follow the reference's arithmetic; the .jpg files are baseline JPEGs from apd_jpeg.cpp's encoder (quality 95
 // as cv::imwrite's default), so they decode to the same picture up to JPEG quantisation, not to the same bytes as libjpeg's.
+#include <algorithm>
+#include <array>
 #include <cmath>
+#include <deque>
 #include <fstream>
+#include <memory>
+#include <thread>
 
 #include "apd_io.h"
 
@@ -117,6 +122,47 @@ bool ShowWeakImage(const path &weak_path, const Mat &weak) {
         }
     }
     return WritePNG(weak_path, img);
+}
+
+// ------------------------------------------------------------------------------------------------ asynchronous writer
+struct ShowWriter::Impl {
+    std::deque<std::thread> running;  // oldest first
+    size_t max_threads = 1;
+};
+
+ShowWriter::ShowWriter() : impl(new Impl) {
+    const size_t hw = std::max<size_t>(1, std::thread::hardware_concurrency());
+    impl->max_threads = std::min<size_t>(hw, 16);
+}
+ShowWriter::~ShowWriter() {
+    wait();
+    delete impl;
+}
+void ShowWriter::wait() {
+    for (auto &t : impl->running) t.join();
+    impl->running.clear();
+}
+void ShowWriter::submit(const path &result_folder, int iteration, Mat depth, Mat normal, Mat weak, Mat confidence, float depth_min,
+                        float depth_max) {
+    const size_t bytes = depth.buf.size() + normal.buf.size() + weak.buf.size() + confidence.buf.size();
+    const size_t by_memory = std::max<size_t>(1, ((size_t)2 << 30) / std::max<size_t>(1, bytes));
+    const size_t limit = std::min(impl->max_threads, by_memory);
+    while (impl->running.size() >= limit) {  // the oldest view first: in-flight maps stay bounded
+        impl->running.front().join();
+        impl->running.pop_front();
+    }
+    auto maps = std::make_shared<std::array<Mat, 4>>();
+    (*maps)[0] = std::move(depth); (*maps)[1] = std::move(normal); (*maps)[2] = std::move(weak); (*maps)[3] = std::move(confidence);
+    impl->running.emplace_back([maps, result_folder, iteration, depth_min, depth_max]() {
+        try {  // debug imagery must never take the run down (the reference ignores the return values, main.cpp:197-203)
+            const std::string it = std::to_string(iteration);
+            ShowDepthMap(result_folder / ("depth_" + it + ".jpg"), (*maps)[0], depth_min, depth_max);
+            ShowNormalMap(result_folder / ("normal_" + it + ".jpg"), (*maps)[1]);
+            ShowWeakImage(result_folder / ("weak_" + it + ".png"), (*maps)[2]);
+            ShowConfidenceMap(result_folder / ("confidence_" + it + ".png"), (*maps)[3]);
+        } catch (...) {
+        }
+    });
 }
 
 }  // namespace apd

@@ -76,7 +76,7 @@ static void write_maps(SceneSession &s) {
 
 // problem.show_medium_result (main.cpp:191-204, 359): pictures of every view's maps after the last geometric iteration of a round.
 // Every view's maps are those of this pass once the pass has ended, so writing them here equals writing them problem by problem.
-static void write_show(SceneSession &s, int iteration) {
+static void write_show(SceneSession &s, int iteration, ShowWriter &writer) {
     if (getenv("APDE_NO_SHOW")) return;
     for (size_t i = 0; i < s.problems.size(); ++i) {
         int w = 0, h = 0;
@@ -84,13 +84,10 @@ static void write_show(SceneSession &s, int iteration) {
         if (w == 0) continue;
         Mat depth(h, w, CV_32FC1), normal(h, w, CV_32FC3), weak(h, w, CV_8UC1), conf(h, w, CV_8UC1);
         apde_view_download(s.ctx, (int)i, depth.ptr<float>(), normal.ptr<float>(), weak.data(), conf.data(), &w, &h);
-        const path dir = s.problems[i].result_folder;
-        const std::string it = std::to_string(iteration);
         const Camera &cam = s.cameras[i];
-        ShowDepthMap(dir / ("depth_" + it + ".jpg"), depth, cam.depth_min * 0.6f, cam.depth_max * 1.2f);  // APD.cpp:554-555
-        ShowNormalMap(dir / ("normal_" + it + ".jpg"), normal);
-        ShowWeakImage(dir / ("weak_" + it + ".png"), weak);
-        ShowConfidenceMap(dir / ("confidence_" + it + ".png"), conf);
+        // encoded and written by worker threads while the next round runs on the GPU; depth range as APD.cpp:554-555
+        writer.submit(s.problems[i].result_folder, iteration, std::move(depth), std::move(normal), std::move(weak), std::move(conf),
+                      cam.depth_min * 0.6f, cam.depth_max * 1.2f);
     }
 }
 
@@ -198,6 +195,7 @@ int main(int argc, char **argv) {
         std::cout << "Round nums: " << npass / (1 + sched.geom_iterations) << std::endl;
         apde_timing t;
         memset(&t, 0, sizeof(t));
+        ShowWriter show_writer;  // joins its worker threads when it goes out of scope (every return path below)
         const auto start = std::chrono::steady_clock::now();
         for (int p = 0; p < npass; ++p) {
             if (p % (1 + sched.geom_iterations) == 0)
@@ -206,12 +204,12 @@ int main(int argc, char **argv) {
             const double before = t.patchmatch_ms;
             if (p == npass - 1 && (a.export_anchor || a.export_curve)) {  // is_last_iteration, main.cpp:335
                 if (!run_pass_with_exports(*s, sched, p, a.export_anchor, a.export_curve)) { std::cout << "Error: " << apde_last_error() << std::endl; return EXIT_FAILURE; }
-                write_show(*s, p);
+                write_show(*s, p, show_writer);
                 continue;
             }
             if (apde_run_schedule_pass(s->ctx, &sched, p, &t)) { std::cout << "Error: " << apde_last_error() << std::endl; return EXIT_FAILURE; }
             printf("RunPatchMatch time: %d ms (all %zu views)\n", (int)(t.patchmatch_ms - before), s->problems.size());
-            if (p % (1 + sched.geom_iterations) == sched.geom_iterations) write_show(*s, p);
+            if (p % (1 + sched.geom_iterations) == sched.geom_iterations) write_show(*s, p, show_writer);
         }
         const auto end = std::chrono::steady_clock::now();
         std::cout << "Cost time: " << std::chrono::duration_cast<std::chrono::milliseconds>(end - start).count() << " ms" << std::endl;

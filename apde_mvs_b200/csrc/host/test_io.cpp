@@ -54,6 +54,28 @@ int main(int argc, char **argv) {
         memcpy(j.data(), jet, sizeof(jet));
         return ok && WriteBinMat(dir / "jet.bin", j) ? 0 : 1;
     }
+    if (cmd == "showasync") {  // showasync <dir with the four .bin maps> <n> <dmin> <dmax>: n views through ShowWriter into <dir>/<k>/
+        const path dir = argv[2];
+        Mat depth, normal, weak, conf;
+        if (!ReadBinMat(dir / "depths.bin", depth) || !ReadBinMat(dir / "normals.bin", normal) || !ReadBinMat(dir / "weak.bin", weak) ||
+            !ReadBinMat(dir / "confidence.bin", conf)) return 1;
+        const int n = atoi(argv[3]);
+        {
+            ShowWriter writer;
+            for (int k = 0; k < n; ++k) {
+                std::filesystem::create_directories(dir / std::to_string(k));
+                Mat d = depth;
+                for (size_t i = 0; i < d.buf.size() / 4; ++i) d.ptr<float>()[i] += 0.01f * k;  // another picture per view
+                writer.submit(dir / std::to_string(k), 3, d, normal, weak, conf, (float)atof(argv[4]), (float)atof(argv[5]));
+            }
+        }  // the destructor joins
+        for (int k = 0; k < n; ++k) {  // the same pictures, one by one
+            Mat d = depth;
+            for (size_t i = 0; i < d.buf.size() / 4; ++i) d.ptr<float>()[i] += 0.01f * k;
+            if (!ShowDepthMap(dir / std::to_string(k) / "depth_sync.jpg", d, (float)atof(argv[4]), (float)atof(argv[5]))) return 1;
+        }
+        return 0;
+    }
     if (cmd == "cam") {  // cam <cam.txt>
         Camera cam;
         if (!ReadCamera(argv[2], cam)) return 1;

@@ -289,3 +289,28 @@ def test_threaded_view_loader_matches_serial_decoding(tool, tmp_path):
         assert int(l[5]) == chk(cv2.imread(imgs[v], cv2.IMREAD_COLOR))
         assert int(l[6]) == (chk(labels[v]) if v in labels else 0)
         assert float(l[7]) == 100 + v and abs(float(l[8]) - (1.5 + v)) < 1e-6
+
+
+def test_show_writer_threads_write_the_same_pictures(tool, tmp_path):
+    """ShowWriter (the CLI's asynchronous Show*: worker threads encode while the next round runs): 20 views, more than the
+    thread limit, every view's four files complete when the writer is destroyed and identical to the one-by-one result"""
+    rng = np.random.default_rng(3)
+    h, w = 40, 56
+    y, x = np.mgrid[0:h, 0:w]
+    depth = (4 + 0.02 * x - 0.015 * y).astype(np.float32)
+    normal = rng.normal(size=(h, w, 3)).astype(np.float32)
+    normal /= np.linalg.norm(normal, axis=2, keepdims=True)
+    _write_bin(tmp_path / "depths.bin", depth, 5)
+    _write_bin(tmp_path / "normals.bin", normal, 21)
+    _write_bin(tmp_path / "weak.bin", rng.integers(0, 3, (h, w), dtype=np.uint8), 0)
+    _write_bin(tmp_path / "confidence.bin", rng.integers(3, 200, (h, w), dtype=np.uint8), 0)
+    n = 20
+    subprocess.check_call([tool, "showasync", str(tmp_path), str(n), "1.2", "9.6"])
+    first = None
+    for k in range(n):
+        d = tmp_path / str(k)
+        for name in ("depth_3.jpg", "normal_3.jpg", "weak_3.png", "confidence_3.png"):
+            assert (d / name).exists() and os.path.getsize(d / name) > 100, (k, name)
+        assert open(d / "depth_3.jpg", "rb").read() == open(d / "depth_sync.jpg", "rb").read()
+        first = first or open(d / "normal_3.jpg", "rb").read()
+        assert open(d / "normal_3.jpg", "rb").read() == first
