@@ -296,6 +296,34 @@ def test_c_abi_exports_every_declared_symbol(apde_lib):
     assert C.sizeof(Params) == 72
 
 
+def test_header_is_plain_c_and_struct_sizes_match_the_binding(apde_lib, tmp_path):
+    """include/apde.h is the drop-in boundary: it must compile as C (no C++ types across it), link against libapde.so from a C
+    program, and the ctypes mirrors in apde_mvs_b200/binding.py must have the compiler's struct sizes"""
+    from apde_mvs_b200.binding import Camera, Params, Schedule, Timing, lib_path
+    src = tmp_path / "abi.c"
+    src.write_text('''#include <stdio.h>
+#include "apde.h"
+int main(void) {
+    apde_params p;
+    apde_schedule s;
+    apde_params_default(&p);
+    apde_schedule_default(&s);
+    printf("%zu %zu %zu %zu %d %d %d %s\\n", sizeof(apde_camera), sizeof(apde_params), sizeof(apde_schedule), sizeof(apde_timing),
+           p.top_k, s.geom_iterations, s.use_sa, apde_version());
+    return apde_view_set_sa_mask(0, 0, 0, 0, 0) == 0;  /* null context: an error code, not a crash */
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(lib_path())
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L" + libdir, "-lapde", "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    f = out.stdout.split()
+    assert [int(x) for x in f[:4]] == [C.sizeof(Camera), C.sizeof(Params), C.sizeof(Schedule), C.sizeof(Timing)]
+    assert f[4:7] == ["4", "3", "1"] and "sm_100a" in out.stdout
+
+
 def test_no_cpu_fallback(apde_lib):
     """without a CUDA device the product fails loudly instead of computing on the host"""
     from apde_mvs_b200.binding import ApdeError, Context
