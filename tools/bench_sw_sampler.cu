@@ -9,6 +9,8 @@
 //           (profiles/r01_texture_filter_model.md: A, B = 1.8 fixed-point fractions, W11 = (A*B + 128) >> 8, ...)
 //   SMEM16  the same with (texel, right neighbour) pairs stored as 16-bit words: 2 loads per sample
 //   HYBRID  taps with even index through TEX, odd taps through SMEM16 (both pipes busy)
+//   SMEM16F / HYBRIDF  (added after the first measurement) the software filter with ~half the instructions (fixed-point
+//           coordinate from one F2I per axis, DP4A over packed texels and weights); HYBRIDF sends one tap in four through it
 // and reports Gsamples/s per variant plus the number of samples whose value differs from TEX (must be 0: the software filter is
 // the pinned model of the texture unit).  The accumulation per sample (sum, sum of squares, product with a reference value) is
 // the NCC's, so the instruction mix around the sample is the real one.
@@ -25,7 +27,7 @@
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
 constexpr int kHyp = 61, kTaps = 6;       // 61 hypotheses, 6 x 6 taps
-enum Mode { TEX = 0, SMEM8 = 1, SMEM16 = 2, HYBRID = 3 };
+enum Mode { TEX = 0, SMEM8 = 1, SMEM16 = 2, HYBRID = 3, SMEM16F = 4, HYBRIDF = 5 };
 
 struct Warp {  // x' = (h0 x + h1 y + h2 + k b0) / (h6 x + h7 y + h8 + k b2), y' alike: a homography whose translation moves with k
     float h[9];
@@ -69,6 +71,22 @@ __device__ __forceinline__ float sample_smem(const void *win, int x0, int y0, in
     return (float)(W00 * t00 + W10 * t10 + W01 * t01 + W11 * t11) * (1.0f / 256.0f);
 }
 
+// the same filter with fewer instructions (CPU-checked against the pinned model on 60 000 probes incl. bucket edges):
+//   one FFMA + one F2I.FLOOR per axis gives the 24.8 fixed-point coordinate fx = floor((x - 0.5) * 256 + 0.5); i = fx >> 8, A = fx & 255
+//   (the model's A = 256 case becomes (i + 1, 0): the same four-weight sum);
+//   the (texel, right neighbour) pairs of the two rows form one 32-bit word and the four weights another: one DP4A, plus
+//   t00 * 256 in the single case W00 == 256 (A == B == 0), whose low byte is 0
+__device__ __forceinline__ float sample_smem_fast(const unsigned short *s, int x0, int y0, int pitch, float x, float y) {
+    const int fx = __float2int_rd(fmaf(x, 256.0f, -127.5f)), fy = __float2int_rd(fmaf(y, 256.0f, -127.5f));
+    const int A = fx & 255, B = fy & 255;
+    const int p = ((fy >> 8) - y0) * pitch + ((fx >> 8) - x0);
+    const unsigned tex4 = __byte_perm((unsigned)s[p], (unsigned)s[p + pitch], 0x5410);  // t00 | t10 << 8 | t01 << 16 | t11 << 24
+    const int W11 = (A * B + 128) >> 8, W10 = A - W11, W01 = B - W11, W00 = 256 - A - B + W11;
+    const unsigned w4 = (unsigned)(W00 & 255) | ((unsigned)W10 << 8) | ((unsigned)W01 << 16) | ((unsigned)W11 << 24);
+    const unsigned sum = __dp4a(tex4, w4, (unsigned)((W00 >> 8) * ((tex4 & 255u) << 8)));
+    return (float)sum * (1.0f / 256.0f);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(128) k_sweep(cudaTextureObject_t tex, const uint8_t *__restrict__ lin, int W, int H, int layer, Warp w,
                                                float *__restrict__ out, int *__restrict__ fallback, int win_bytes) {
@@ -97,7 +115,7 @@ __global__ void __launch_bounds__(128) k_sweep(cudaTextureObject_t tex, const ui
         x0 = box[0] - 1; y0 = box[1] - 1;  // one texel of slack for rounding at the box edge
         const int ww = box[2] - x0 + 2, wh = box[3] - y0 + 2;
         pitch = (ww + 3) & ~3;
-        const int elem = (MODE == SMEM8) ? 1 : 2;
+        const int elem = (MODE == SMEM8) ? 1 : 2;  // every other software mode stores pairs
         staged = (long long)pitch * wh * elem <= win_bytes && ww > 0 && wh > 0;
         if (staged) {
             for (int idx = threadIdx.x; idx < pitch * wh; idx += blockDim.x) {
@@ -123,8 +141,11 @@ __global__ void __launch_bounds__(128) k_sweep(cudaTextureObject_t tex, const ui
                 float X, Y;
                 project(w, (float)(px + 2 * i - 5), (float)(py + 2 * j - 5), (float)k, X, Y);
                 float s;
-                const bool soft = staged && (MODE == SMEM8 || MODE == SMEM16 || (MODE == HYBRID && ((i * kTaps + j) & 1)));
+                // HYBRID: every other tap in software; HYBRIDF: one tap in four (the share at which issue and filter slots balance on paper)
+                const bool soft = staged && (MODE == SMEM8 || MODE == SMEM16 || MODE == SMEM16F || (MODE == HYBRID && ((i * kTaps + j) & 1)) ||
+                                             (MODE == HYBRIDF && ((i * kTaps + j) & 3) == 3));
                 if (MODE == TEX || !soft) s = sample_tex(tex, X, Y, layer);
+                else if (MODE == SMEM16F || MODE == HYBRIDF) s = sample_smem_fast((const unsigned short *)smem, x0, y0, pitch, X, Y);
                 else s = (MODE == SMEM8) ? sample_smem<false>(smem, x0, y0, pitch, X, Y) : sample_smem<true>(smem, x0, y0, pitch, X, Y);
                 s1 += s;
                 s2 = fmaf(s, s, s2);
@@ -213,12 +234,12 @@ int main(int argc, char **argv) {
 
     // a mild homography: 3 % scale, 1.5 degree shear, weak perspective; hypothesis step ~ 0.9 px in x, 0.05 px in y
     Warp w = {{1.03f, 0.02f, 3.7f, -0.015f, 0.98f, -2.3f, 1.0e-5f, -0.8e-5f, 1.0f}, {0.9f, 0.05f, 1.0e-4f}};
-    std::vector<float *> outs(4);
+    std::vector<float *> outs(6);
     for (auto &o : outs) CK(cudaMalloc(&o, (size_t)L * W * H * sizeof(float)));
     const double samples = (double)L * W * H * kHyp * kTaps * kTaps;
-    const char *names[4] = {"TEX", "SMEM8", "SMEM16", "HYBRID"};
-    float ms[4];
-    int fb[4] = {0, 0, 0, 0};
+    const char *names[6] = {"TEX", "SMEM8", "SMEM16", "HYBRID", "SMEM16F", "HYBRIDF"};
+    float ms[6];
+    int fb[6] = {0, 0, 0, 0, 0, 0};
     ms[0] = run<TEX>(tex, lin, W, H, L, w, outs[0], d_int, 0);
     ms[1] = run<SMEM8>(tex, lin, W, H, L, w, outs[1], d_int, kMaxWin);
     CK(cudaMemcpy(&fb[1], d_int, sizeof(int), cudaMemcpyDeviceToHost));
@@ -226,9 +247,13 @@ int main(int argc, char **argv) {
     CK(cudaMemcpy(&fb[2], d_int, sizeof(int), cudaMemcpyDeviceToHost));
     ms[3] = run<HYBRID>(tex, lin, W, H, L, w, outs[3], d_int, kMaxWin);
     CK(cudaMemcpy(&fb[3], d_int, sizeof(int), cudaMemcpyDeviceToHost));
+    ms[4] = run<SMEM16F>(tex, lin, W, H, L, w, outs[4], d_int, kMaxWin);
+    CK(cudaMemcpy(&fb[4], d_int, sizeof(int), cudaMemcpyDeviceToHost));
+    ms[5] = run<HYBRIDF>(tex, lin, W, H, L, w, outs[5], d_int, kMaxWin);
+    CK(cudaMemcpy(&fb[5], d_int, sizeof(int), cudaMemcpyDeviceToHost));
     std::vector<float> ref((size_t)L * W * H), got(ref.size());
     CK(cudaMemcpy(ref.data(), outs[0], ref.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    for (int m = 0; m < 4; ++m) {
+    for (int m = 0; m < 6; ++m) {
         size_t diff = 0;
         if (m) {
             CK(cudaMemcpy(got.data(), outs[m], got.size() * sizeof(float), cudaMemcpyDeviceToHost));
