@@ -122,6 +122,7 @@ def test_ncc_old_with_labels(ctx, office_sa):
             (dr <= 1e-4).mean(), dr.max(), (dro <= 1e-4).mean()))
         assert (dr <= 1e-4).mean() >= 0.97 and (dr <= 1e-3).mean() >= 0.995
         assert (dro <= 1e-4).mean() >= 0.97
+    ctx.view_set_sa_mask(2, None)
 
 
 def test_apd_stages_with_labels(ctx, office_sa):
