@@ -139,6 +139,8 @@ def load_library(path=None):
     lib.apde_run_schedule.argtypes = [P, C.POINTER(Schedule), C.POINTER(Timing)]
     lib.apde_run_schedule_pass.argtypes = [P, C.POINTER(Schedule), C.c_int, C.POINTER(Timing)]
     lib.apde_schedule_num_passes.argtypes = [P, C.POINTER(Schedule)]
+    lib.apde_schedule_pass_params.argtypes = [P, C.POINTER(Schedule), C.c_int, C.POINTER(Params), C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
+    lib.apde_problem_capture_curve.argtypes = [P, C.c_int]
     lib.apde_get_counters.argtypes = [P, C.POINTER(C.c_uint64), C.c_int]
     lib.apde_set_profiling.argtypes = [P, C.c_int]
     lib.apde_set_sweep_budget_mb.argtypes = [P, C.c_size_t]
@@ -172,6 +174,7 @@ _FIELD_DTYPE = {
     FIELD.VIEW_WEIGHT: (np.uint8, 32), FIELD.WEAK_INFO: (np.uint8, 1), FIELD.CONFIDENCE: (np.uint8, 1),
     FIELD.FIT_PLANES: (np.float32, 4), FIELD.WEAK_RELIABLE: (np.uint8, 1), FIELD.NEAREST_STRONG: (np.int16, 2),
     FIELD.ANCHORS: (np.int16, 2 * ANCHOR_NUM), FIELD.IMAGE: (np.float32, 1), FIELD.SA_MASK: (np.uint8, 1),
+    FIELD.RELIABLE_CURVE: (np.float32, 61),
 }
 
 
@@ -333,6 +336,16 @@ class Context:
         return out
 
     # ---- schedule
+    def schedule_pass_params(self, sched, pass_index):
+        """(Params, scale_size, seed) that pass `pass_index` of the schedule uses for every view (main.cpp:309-365)"""
+        p, scale, seed = Params(), C.c_int(), C.c_uint32()
+        self._check(self.lib.apde_schedule_pass_params(self._h, C.byref(sched), pass_index, C.byref(p), C.byref(scale), C.byref(seed)))
+        return p, scale.value, seed.value
+
+    def capture_curve(self, on=True):
+        """keep DepthToWeak's 61-sample cost curve of the following problems (FIELD.RELIABLE_CURVE)"""
+        self._check(self.lib.apde_problem_capture_curve(self._h, 1 if on else 0))
+
     def num_passes(self, sched):
         n = self.lib.apde_schedule_num_passes(self._h, C.byref(sched))
         if n < 0:

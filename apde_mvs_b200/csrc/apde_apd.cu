@@ -353,7 +353,7 @@ __device__ __forceinline__ void k_prop_weak_body(const PassK &K, int iter, int c
             if (K.weak[ap] == APDE_STRONG) { ok = true; pos[h] = ap; flags |= 1u << h; }
         }
         if (ok) {
-            const float3 m = plane_row(K, K.planes[pos[h]]);
+            const PlaneM m = plane_row(K, K.planes[pos[h]]);
 #pragma unroll 1
             for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_new_x<U, SA>(K, K.v[v], v, px, py, m, rp, ar, si);
             n_new += N;
@@ -398,7 +398,7 @@ __device__ __forceinline__ void k_prop_weak_body(const PassK &K, int iter, int c
     float4 plane_now = plane_c;
     float cost_now;
     {
-        const float3 m = plane_row(K, plane_c);
+        const PlaneM m = plane_row(K, plane_c);
         float acc = 0.0f;
         for (uint32_t mk = wmask; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
@@ -444,7 +444,7 @@ __device__ __forceinline__ void k_prop_weak_body(const PassK &K, int iter, int c
                 const float d = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : base_d);
                 tp.w = distance_to_origin(K, px, py, d, tp);
             }
-            const float3 m = plane_row(K, tp);
+            const PlaneM m = plane_row(K, tp);
             float acc = 0.0f;
             for (uint32_t mk = wmask; mk; mk &= mk - 1) {
                 const int v = __ffs(mk) - 1;

@@ -478,59 +478,31 @@ int apde_view_upload(apde_context *c, int view, const float *depth, const float 
 }
 
 // ------------------------------------------------------------------------------------------------ problem
-static void mat3_mul(const double *A, const double *B, double *C) {
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-        double s = 0;
-        for (int k = 0; k < 3; ++k) s += A[3 * i + k] * B[3 * k + j];
-        C[3 * i + j] = s;
-    }
+// a0*b0 + a1*b1 + a2*b2 as the reference build contracts it on the device (FMUL of the middle product, FFMA of the first,
+// FFMA of the last; see dot3_ref in apde_device.cuh).  IEEE fp32 multiply / fused multiply-add on the host give the same
+// bits as the GPU's FMUL / FFMA (the operands here are far from the denormal range, so .FTZ does not matter).
+static inline float dot3_ref_host(float a0, float b0, float a1, float b1, float a2, float b2) {
+    volatile float mid = a1 * b1;  // volatile: the product must be rounded to fp32 on its own (no host-side contraction)
+    return fmaf(a2, b2, fmaf(a0, b0, mid));
 }
 
-// camera-pair constants (double precision on the host).  Zero-skew pinhole K as the reference assumes (APD.cu:375-393).
+// Camera-pair part of ComputeHomography (APD.cu:336-362), computed once per (reference, source) pair instead of once per
+// evaluation, in the reference's own fp32 operation order so that every bit of R_rel and t_rel agrees with what the
+// reference's kernels compute on the fly:  C = -(R^T t);  R_rel = R_s R_r^T;  t_rel = R_s (C_r - C_s).
 static void make_view_k(const apde_camera &rc, const apde_camera &sc, int layer, ViewK &vk) {
-    double Rr[9], Rs[9], Kr[9], Ks[9], Kri[9], Ksi[9];
-    for (int i = 0; i < 9; ++i) { Rr[i] = rc.R[i]; Rs[i] = sc.R[i]; Kr[i] = rc.K[i]; Ks[i] = sc.K[i]; }
-    auto kinv = [](const double *K, double *Ki) {
-        const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
-        Ki[0] = 1.0 / fx; Ki[1] = 0; Ki[2] = -cx / fx;
-        Ki[3] = 0; Ki[4] = 1.0 / fy; Ki[5] = -cy / fy;
-        Ki[6] = 0; Ki[7] = 0; Ki[8] = 1.0;
-    };
-    auto kfwd = [](const double *K, double *Kf) {  // what ComputeHomography applies for the source: fx, fy, cx, cy, K[8]
-        Kf[0] = K[0]; Kf[1] = 0; Kf[2] = K[2];
-        Kf[3] = 0; Kf[4] = K[4]; Kf[5] = K[5];
-        Kf[6] = 0; Kf[7] = 0; Kf[8] = K[8];
-    };
-    double Krf[9], Ksf[9];
-    kfwd(Kr, Krf); kfwd(Ks, Ksf);
-    kinv(Kr, Kri); kinv(Ks, Ksi);
-    double Cr[3], Cs[3];
+    float Sr[3], Ss[3];  // -C of both cameras
     for (int j = 0; j < 3; ++j) {
-        Cr[j] = -(Rr[0 + j] * rc.t[0] + Rr[3 + j] * rc.t[1] + Rr[6 + j] * rc.t[2]);
-        Cs[j] = -(Rs[0 + j] * sc.t[0] + Rs[3 + j] * sc.t[1] + Rs[6 + j] * sc.t[2]);
+        Sr[j] = dot3_ref_host(rc.R[0 + j], rc.t[0], rc.R[3 + j], rc.t[1], rc.R[6 + j], rc.t[2]);
+        Ss[j] = dot3_ref_host(sc.R[0 + j], sc.t[0], sc.R[3 + j], sc.t[1], sc.R[6 + j], sc.t[2]);
     }
-    double RrT[9], RsT[9];
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { RrT[3 * i + j] = Rr[3 * j + i]; RsT[3 * i + j] = Rs[3 * j + i]; }
-    double Rrel[9], RrelT[9];
-    mat3_mul(Rs, RrT, Rrel);   // R_s R_r^T
-    mat3_mul(Rr, RsT, RrelT);  // R_r R_s^T
-    double dC[3] = {Cr[0] - Cs[0], Cr[1] - Cs[1], Cr[2] - Cs[2]};
-    double trel[3], treli[3];
-    for (int i = 0; i < 3; ++i) {
-        trel[i] = Rs[3 * i] * dC[0] + Rs[3 * i + 1] * dC[1] + Rs[3 * i + 2] * dC[2];
-        treli[i] = -(Rr[3 * i] * dC[0] + Rr[3 * i + 1] * dC[1] + Rr[3 * i + 2] * dC[2]);
-    }
-    double T[9], A[9], Ai[9];
-    mat3_mul(Ksf, Rrel, T); mat3_mul(T, Kri, A);
-    mat3_mul(Krf, RrelT, T); mat3_mul(T, Ksi, Ai);
-    for (int i = 0; i < 9; ++i) { vk.A[i] = (float)A[i]; vk.Ai[i] = (float)Ai[i]; }
-    for (int i = 0; i < 3; ++i) {
-        vk.b[i] = (float)(Ksf[3 * i] * trel[0] + Ksf[3 * i + 1] * trel[1] + Ksf[3 * i + 2] * trel[2]);
-        vk.bi[i] = (float)(Krf[3 * i] * treli[0] + Krf[3 * i + 1] * treli[1] + Krf[3 * i + 2] * treli[2]);
-    }
-    // baseline from the float camera centres as DepthToWeak computes it (APD.cu:2142-2147)
-    const float d0 = rc.c[0] - sc.c[0], d1 = rc.c[1] - sc.c[1], d2 = rc.c[2] - sc.c[2];
-    vk.baseline = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            vk.Rrel[3 * i + j] = dot3_ref_host(sc.R[3 * i], rc.R[3 * j], sc.R[3 * i + 1], rc.R[3 * j + 1], sc.R[3 * i + 2], rc.R[3 * j + 2]);
+    // C_rel = ref_C - src_C = (-Sr) - (-Ss) = Ss - Sr (exact either way)
+    const float c0 = Ss[0] - Sr[0], c1 = Ss[1] - Sr[1], c2 = Ss[2] - Sr[2];
+    for (int i = 0; i < 3; ++i) vk.trel[i] = dot3_ref_host(sc.R[3 * i], c0, sc.R[3 * i + 1], c1, sc.R[3 * i + 2], c2);
+    for (int i = 0; i < 9; ++i) { vk.K[i] = sc.K[i]; vk.R[i] = sc.R[i]; }
+    for (int i = 0; i < 3; ++i) { vk.t[i] = sc.t[i]; vk.c[i] = sc.c[i]; }
     vk.layer = layer;
 }
 
@@ -578,7 +550,8 @@ int apde_problem_setup(apde_context *c, int ref_view, const apde_params *params,
     K.depth_min = c->params.depth_min; K.depth_max = c->params.depth_max;
     K.geom_factor = c->params.geom_factor; K.ransac_threshold = c->params.ransac_threshold;
     K.fx = c->cams[0].K[0]; K.fy = c->cams[0].K[4]; K.cx = c->cams[0].K[2]; K.cy = c->cams[0].K[5];
-    for (int i = 0; i < 9; ++i) K.R[i] = c->cams[0].R[i];
+    for (int i = 0; i < 9; ++i) { K.R[i] = c->cams[0].R[i]; K.Kr[i] = c->cams[0].K[i]; }
+    for (int i = 0; i < 3; ++i) { K.t[i] = c->cams[0].t[i]; K.c[i] = c->cams[0].c[i]; }
     K.ref_layer = ref_view;
     K.seed = seed;
     K.stream = (uint32_t)ref_view;
@@ -671,7 +644,7 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
     // N x more parallelism for few pixels); for the dense strong class the fused one-thread-per-pixel kernel is faster (165 vs
     // 179 ms: no intermediate buffers, no second pass over the reference patch).  APDE_PIPELINE_STRONG=1 forces the pipeline.
     static const bool pipe_strong = [] { const char *e = getenv("APDE_PIPELINE_STRONG"); return e && e[0] == '1'; }();
-    const bool pipeline = prop_stage && !legacy_prop && !getenv("APDE_QUAD_KERNELS") && (stage == APDE_STAGE_PROP_WEAK || pipe_strong);
+    const bool pipeline = prop_stage && !legacy_prop && (stage == APDE_STAGE_PROP_WEAK || pipe_strong);
     if (prop_stage && (c->params.use_APD || pipeline)) {
         if (c->lists_dirty) { const int rc = build_lists(c); if (rc) return rc; }
         const int cls = (color << 1) | (stage == APDE_STAGE_PROP_WEAK ? 1 : 0);
@@ -692,7 +665,7 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
     // WEAK-only full-frame stages (GenAnchors, RANSAC plane fit) walk the two (colour, weak) lists instead of the whole grid.
     // The lists hold rows [0, half_rows_limit): only usable when that covers the frame (quirk 7 shapes fall back).
     const bool weak_lists = (stage == APDE_STAGE_GEN_ANCHORS || stage == APDE_STAGE_RANSAC_FIT) && c->params.use_APD &&
-                            !getenv("APDE_QUAD_KERNELS") && !getenv("APDE_NO_WEAK_LISTS") && 32 * (((c->K.H / 2) + 15) / 16) >= c->K.H;
+                            !getenv("APDE_NO_WEAK_LISTS") && 32 * (((c->K.H / 2) + 15) / 16) >= c->K.H;
     if (weak_lists && c->lists_dirty) { const int rc = build_lists(c); if (rc) return rc; }
     auto run_stage = [&](const PassK &Kq) -> cudaError_t {
         static const bool legacy = [] { const char *e = getenv("APDE_LEGACY_SWEEP"); return e && e[0] == '1'; }();
@@ -715,7 +688,7 @@ int apde_problem_stage(apde_context *c, int stage, int iter, int color) {
             return prop_half_sweep(Kq, c->prop, stage == APDE_STAGE_PROP_WEAK, Kq.list, Kq.list_count, c->h_list_counts[cls], iter, c->stream,
                                    &c->launches);
         }
-        if (!legacy && !getenv("APDE_QUAD_KERNELS")) {
+        if (!legacy) {
             // (the sweep functions count every launch but the last one; the generic count below adds that)
             if (stage == APDE_STAGE_DEPTH_TO_WEAK) {
                 float *curve = nullptr;

@@ -2,9 +2,17 @@
 //
 // Design: one thread per pixel; the 36 reference-patch texels and their sums are loaded ONCE per
 // pixel per kernel and stay in registers (the reference re-fetches them through the texture unit for every
-// evaluation, APD.cu:632); the camera-pair part of the homography is precomputed on the host per (ref, src) pair
-// (the reference recomputes it per evaluation, APD.cu:336-362), so that H = A - b m^T costs 9 FMAs; source texels
-// are gathered through ONE layered texture object (linear filter, clamp) holding every view of the pyramid level.
+// evaluation, APD.cu:632); the camera-pair part of the homography (R_rel, t_rel) is computed once per (ref, src) pair
+// (the reference recomputes it per evaluation, APD.cu:336-362); source texels are gathered through ONE layered texture
+// object (linear filter, clamp) holding every view of the pyramid level.
+//
+// ARITHMETIC CONTRACT.  Every floating-point operation that feeds a sample coordinate, a cost or a depth follows the
+// reference BUILD (nvcc -O3 --use_fast_math, CMakeLists.txt:26) operation for operation: the same association, the same
+// FMUL / FFMA / FADD split the compiler chose there (read from the SASS of the reference build, recorded in
+// profiles/r02_reference_sass_arithmetic.md), MUFU.RCP / MUFU.SQRT where the reference build has them.  All of it is
+// written with explicit intrinsics so that no inlining context can re-associate or re-contract it.  The reason: sample
+// coordinates land on the texture unit's 1/256 weight grid, a 1-ulp difference in the homography flips buckets and moves a
+// cost by ~1e-4; with the reference's own operation order the costs agree bit for bit.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -16,23 +24,23 @@ namespace apde {
 constexpr int kMaxSrc = APDE_MAX_IMAGES - 1;
 constexpr int kPatch = 36;  // (2*5/2+1)^2 samples: strong_radius 5, strong_increment 2 (main.h:87-88)
 
-// per (reference, source) pair constants, precomputed in double on the host
+// per (reference, source) pair constants
 struct ViewK {
-    float A[9];   // K_s R_rel K_r^-1                (homography:  H = A - b m^T,  m = n^T K_r^-1 / w)
-    float b[3];   // K_s t_rel,  t_rel = R_s (C_r - C_s)
-    float Ai[9];  // K_r R_rel^T K_s^-1              (backward reprojection)
-    float bi[3];  // K_r R_r (C_s - C_r)
-    float baseline;
-    int layer;    // layer of this source view in the level's texture
-    int pad_[2];  // 112 bytes: 16-byte aligned rows in shared memory
+    float Rrel[9];  // R_s R_r^T            fp32, in the reference's operation order (APD.cu:348-356; host twin: pair_terms())
+    float trel[3];  // R_s (C_r - C_s)      (APD.cu:338-343, 357-362)
+    float K[9], R[9], t[3], c[3];  // the source camera at this level: the geometric cost and the confidence count go
+                                   // through world coordinates exactly as the reference does (APD.cu:831-863)
+    int layer;      // layer of this source view in the level's texture
+    int pad_[2];    // 160 bytes: 16-byte aligned rows in shared memory
 };
 
 struct PassK {
     int W, H, N;  // N = number of source views
     int state, geom, impetus, use_apd, top_k, weak_peak_radius, rotate_time, max_iterations;
     float depth_min, depth_max, geom_factor, ransac_threshold;
-    float fx, fy, cx, cy;  // reference intrinsics at this level
+    float fx, fy, cx, cy;  // reference intrinsics at this level (= Kr[0], Kr[4], Kr[2], Kr[5])
     float R[9];            // reference rotation
+    float Kr[9], t[3], c[3];  // the rest of the reference camera (world route of the geometric cost)
     int ref_layer;
     uint32_t seed, stream;
     cudaTextureObject_t tex;  // layered images of the level (linear filter, clamp, unnormalised coordinates)
@@ -103,17 +111,31 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
-// reference-camera plane helpers (APD.cu:190-240), zero-skew pinhole
-// (explicit intrinsics, see plane_row: the same plane must give the same depth in every kernel it is inlined into)
-__device__ __forceinline__ float depth_from_plane(const PassK &K, float4 pl, int px, int py) {
-    const float a = __fmul_rn(__fsub_rn((float)px, K.cx), pl.x);
-    const float b = __fmul_rn(__fdividef(K.fx, K.fy), __fsub_rn((float)py, K.cy));
-    const float den = __fmaf_rn(K.fx, pl.z, __fmaf_rn(b, pl.y, a));
-    return __fdividef(__fmul_rn(-pl.w, K.fx), den);
+// single MUFU.SQRT (what sqrt() / sqrtf() compile to under --use_fast_math on sm_100)
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
+// a0*b0 + a1*b1 + a2*b2 as the reference build contracts every such sum: FMUL on the MIDDLE product, FFMA of the first,
+// FFMA of the last (APD.cu:338-362, 841-843, 856-862, 222)
+__device__ __forceinline__ float dot3_ref(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return __fmaf_rn(a2, b2, __fmaf_rn(a0, b0, __fmul_rn(a1, b1)));
+}
+
+// reference-camera plane helpers (APD.cu:190-240), zero-skew pinhole; operation order of the reference build
+// ComputeDepthfromPlaneHypothesis, APD.cu:237-240:
+//   -w*K0 / ((x-K2)*nx + (K0/K4)*(y-K5)*ny + K0*nz)  ==  (w * -K0) * RCP(FFMA(K0, nz, FFMA(x-K2, nx, ((K0*RCP(K4))*(y-K5))*ny)))
+__device__ __forceinline__ float depth_from_plane(const PassK &K, float4 pl, int px, int py) {
+    const float ty = __fmul_rn(__fmul_rn(__fmul_rn(K.fx, rcp_approx(K.fy)), __fsub_rn((float)py, K.cy)), pl.y);
+    const float den = __fmaf_rn(K.fx, pl.z, __fmaf_rn(__fsub_rn((float)px, K.cx), pl.x, ty));
+    return __fmul_rn(__fmul_rn(pl.w, -K.fx), rcp_approx(den));
+}
+// GetDistance2Origin + Get3DPoint, APD.cu:190-195, 218-223:  X0 = (depth*(x-K2))*RCP(K0), X1 = (depth*(y-K5))*RCP(K4)
 __device__ __forceinline__ float distance_to_origin(const PassK &K, int px, int py, float depth, float4 n) {
-    const float X0 = depth * (px - K.cx) / K.fx, X1 = depth * (py - K.cy) / K.fy;
-    return -(n.x * X0 + n.y * X1 + n.z * depth);
+    const float X0 = __fmul_rn(__fmul_rn(depth, __fsub_rn((float)px, K.cx)), rcp_approx(K.fx));
+    const float X1 = __fmul_rn(__fmul_rn(depth, __fsub_rn((float)py, K.cy)), rcp_approx(K.fy));
+    return -dot3_ref(X0, n.x, X1, n.y, depth, n.z);
 }
 __device__ __forceinline__ float3 view_direction(const PassK &K, int px, int py, float depth) {
     const float X0 = depth * (px - K.cx) / K.fx, X1 = depth * (py - K.cy) / K.fy, X2 = depth;
@@ -125,12 +147,12 @@ __device__ __forceinline__ void normalize3(float4 &v) {
     v.x *= inv; v.y *= inv; v.z *= inv;
 }
 __device__ __forceinline__ float4 normal_to_world(const PassK &K, float4 p) {  // TransformNormal APD.cu:405
-    return make_float4(K.R[0] * p.x + K.R[3] * p.y + K.R[6] * p.z, K.R[1] * p.x + K.R[4] * p.y + K.R[7] * p.z,
-                       K.R[2] * p.x + K.R[5] * p.y + K.R[8] * p.z, p.w);
+    return make_float4(dot3_ref(K.R[0], p.x, K.R[3], p.y, K.R[6], p.z), dot3_ref(K.R[1], p.x, K.R[4], p.y, K.R[7], p.z),
+                       dot3_ref(K.R[2], p.x, K.R[5], p.y, K.R[8], p.z), p.w);
 }
 __device__ __forceinline__ float4 normal_to_refcam(const PassK &K, float4 p) {  // TransformNormal2RefCam APD.cu:415
-    return make_float4(K.R[0] * p.x + K.R[1] * p.y + K.R[2] * p.z, K.R[3] * p.x + K.R[4] * p.y + K.R[5] * p.z,
-                       K.R[6] * p.x + K.R[7] * p.y + K.R[8] * p.z, p.w);
+    return make_float4(dot3_ref(K.R[0], p.x, K.R[1], p.y, K.R[2], p.z), dot3_ref(K.R[3], p.x, K.R[4], p.y, K.R[5], p.z),
+                       dot3_ref(K.R[6], p.x, K.R[7], p.y, K.R[8], p.z), p.w);
 }
 
 __device__ __forceinline__ float4 random_normal(const PassK &K, int px, int py, Rng &rng, float depth) {  // APD.cu:242
@@ -204,29 +226,97 @@ __device__ __forceinline__ void load_ref_patch(const PassK &K, int px, int py, R
     }
     // epilogue arithmetic exactly as the reference build's SASS: mean = inv * sum; var = FFMA(inv, sum_xx, -(mean * mean))
     const float inv = 1.0f / 36.0f;
-    rp.mean = inv * s;
-    rp.var = fmaf(inv, ss, -__fmul_rn(rp.mean, rp.mean));
+    rp.mean = __fmul_rn(inv, s);
+    rp.var = __fmaf_rn(inv, ss, -__fmul_rn(rp.mean, rp.mean));
 }
 
-// m = n^T K_r^-1 / w : the hypothesis-dependent row vector of H = A - b m^T
-// Explicit intrinsics: every kernel that evaluates a hypothesis must produce the SAME row vector from the same plane, whatever
-// the compiler would contract around an inlined copy (a 1-ulp difference moves sample coordinates across the texture unit's
-// 1/256 weight buckets and shows up as 1e-4-level cost differences between kernel variants).
-__device__ __forceinline__ float3 plane_row(const PassK &K, float4 pl) {
-    const float iw = rcp_approx(pl.w);
-    const float mx = __fdividef(pl.x, K.fx), my = __fdividef(pl.y, K.fy);
-    const float mz = __fmaf_rn(-my, K.cy, __fmaf_rn(-mx, K.cx, pl.z));
-    return make_float3(__fmul_rn(mx, iw), __fmul_rn(my, iw), __fmul_rn(mz, iw));
+// The hypothesis-dependent part of ComputeHomography: the camera-frame normal and MUFU.RCP(w) ("x / w" under
+// --use_fast_math).  Shared by every source view of the hypothesis.
+struct PlaneM { float nx, ny, nz, rw; };
+__device__ __forceinline__ PlaneM plane_row(const PassK &, float4 pl) {
+    PlaneM m;
+    m.nx = pl.x; m.ny = pl.y; m.nz = pl.z; m.rw = rcp_approx(pl.w);
+    return m;
 }
 
 struct Homog { float h[9]; };
 
-__device__ __forceinline__ Homog make_homography(const ViewK &vk, float3 m) {
+// ComputeHomography, APD.cu:364-393, operation for operation as the reference build executes it:
+//   H_i   = FFMA(-(n_c * t_rel[r]), RCP(w), R_rel[i])                                     (:364-372)
+//   tmp0  = H0 * RCP(K0)   tmp1 = H1 * RCP(K4)                                            (:375-376)
+//   tmp2  = H2 + FFMA(H0 * -K2, RCP(K0), -((H1 * K5) * RCP(K4)))                          (:377)
+//   H'0   = FFMA(Ks0, tmp0, Ks2 * tmp6) ...  H'3 = FFMA(Ks4, tmp3, Ks5 * tmp6) ...  H'6 = Ks8 * tmp6   (:385-393)
+// (K = reference intrinsics, Ks = source intrinsics; R_rel, t_rel come per camera pair from pair_terms())
+__device__ __forceinline__ Homog make_homography(const PassK &K, const ViewK &vk, const PlaneM &m) {
+    const float rK0 = rcp_approx(K.fx), rK4 = rcp_approx(K.fy);
+    float t[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float tr = vk.trel[r];
+        const float H0 = __fmaf_rn(-__fmul_rn(m.nx, tr), m.rw, vk.Rrel[3 * r + 0]);
+        const float H1 = __fmaf_rn(-__fmul_rn(m.ny, tr), m.rw, vk.Rrel[3 * r + 1]);
+        const float H2 = __fmaf_rn(-__fmul_rn(m.nz, tr), m.rw, vk.Rrel[3 * r + 2]);
+        t[3 * r + 0] = __fmul_rn(H0, rK0);
+        t[3 * r + 1] = __fmul_rn(H1, rK4);
+        t[3 * r + 2] = __fadd_rn(H2, __fmaf_rn(__fmul_rn(H0, -K.cx), rK0, -__fmul_rn(__fmul_rn(H1, K.cy), rK4)));
+    }
+    const float ks0 = vk.K[0], ks2 = vk.K[2], ks4 = vk.K[4], ks5 = vk.K[5], ks8 = vk.K[8];
     Homog Hm;
-    Hm.h[0] = fmaf(-vk.b[0], m.x, vk.A[0]); Hm.h[1] = fmaf(-vk.b[0], m.y, vk.A[1]); Hm.h[2] = fmaf(-vk.b[0], m.z, vk.A[2]);
-    Hm.h[3] = fmaf(-vk.b[1], m.x, vk.A[3]); Hm.h[4] = fmaf(-vk.b[1], m.y, vk.A[4]); Hm.h[5] = fmaf(-vk.b[1], m.z, vk.A[5]);
-    Hm.h[6] = fmaf(-vk.b[2], m.x, vk.A[6]); Hm.h[7] = fmaf(-vk.b[2], m.y, vk.A[7]); Hm.h[8] = fmaf(-vk.b[2], m.z, vk.A[8]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        Hm.h[c] = __fmaf_rn(ks0, t[c], __fmul_rn(ks2, t[6 + c]));
+        Hm.h[3 + c] = __fmaf_rn(ks4, t[3 + c], __fmul_rn(ks5, t[6 + c]));
+        Hm.h[6 + c] = __fmul_rn(ks8, t[6 + c]);
+    }
     return Hm;
+}
+
+// ComputeCorrespondingPoint of a single point (APD.cu:396-403) as the reference build contracts it OUTSIDE the patch loops:
+//   X = H2 + FFMA(H0, x, H1 * y)  (same for Y, Z);  pt = (X * RCP(Z), Y * RCP(Z))
+__device__ __forceinline__ void project_point(const float *h, float x, float y, float &ptx, float &pty) {
+    const float X = __fadd_rn(h[2], __fmaf_rn(h[0], x, __fmul_rn(h[1], y)));
+    const float Y = __fadd_rn(h[5], __fmaf_rn(h[3], x, __fmul_rn(h[4], y)));
+    const float Z = __fadd_rn(h[8], __fmaf_rn(h[6], x, __fmul_rn(h[7], y)));
+    const float iz = rcp_approx(Z);
+    ptx = __fmul_rn(X, iz);
+    pty = __fmul_rn(Y, iz);
+}
+// ... and the texture coordinate of that point, "pt + 0.5f" contracted with the division: FFMA(X, RCP(Z), 0.5)
+// (the quadrant walk of NCC-Old branch B, APD.cu:687-689)
+__device__ __forceinline__ void sample_coord_point(const float *h, float x, float y, float &u, float &v) {
+    const float X = __fadd_rn(h[2], __fmaf_rn(h[0], x, __fmul_rn(h[1], y)));
+    const float Y = __fadd_rn(h[5], __fmaf_rn(h[3], x, __fmul_rn(h[4], y)));
+    const float Z = __fadd_rn(h[8], __fmaf_rn(h[6], x, __fmul_rn(h[7], y)));
+    const float iz = rcp_approx(Z);
+    u = __fmaf_rn(X, iz, 0.5f);
+    v = __fmaf_rn(Y, iz, 0.5f);
+}
+// Inside the patch loops (i outer over x, j inner over y; APD.cu:629-634, 523-533) the reference build hoists the x
+// products out of the inner loop, which changes the contraction:  X = H2 + FFMA(H1, y, H0 * x);  u = FFMA(X, RCP(Z), 0.5)
+struct RowX { float x0, x3, x6; };
+__device__ __forceinline__ RowX sample_row(const float *h, float x) {
+    RowX r;
+    r.x0 = __fmul_rn(h[0], x); r.x3 = __fmul_rn(h[3], x); r.x6 = __fmul_rn(h[6], x);
+    return r;
+}
+__device__ __forceinline__ void sample_coord_loop(const float *h, const RowX &r, float y, float &u, float &v) {
+    const float X = __fadd_rn(h[2], __fmaf_rn(h[1], y, r.x0));
+    const float Y = __fadd_rn(h[5], __fmaf_rn(h[4], y, r.x3));
+    const float Z = __fadd_rn(h[8], __fmaf_rn(h[7], y, r.x6));
+    const float iz = rcp_approx(Z);
+    u = __fmaf_rn(X, iz, 0.5f);
+    v = __fmaf_rn(Y, iz, 0.5f);
+}
+
+// NCC from the five sums, APD.cu:644-662 as built: means = inv * sums; var = FFMA(inv, sum_xx, -(mean * mean));
+// covar = FFMA(-mean_r, mean_s, inv * sum_rs); cost = max(0, min(2, FFMA(-covar, RCP(SQRT(var_r * var_s)), 1)))
+__device__ __forceinline__ float ncc_epilogue(float inv, float mean_r, float var_r, float sum_s, float sum_ss, float sum_rs) {
+    const float mean_s = __fmul_rn(inv, sum_s), e_rs = __fmul_rn(inv, sum_rs);
+    const float var_s = __fmaf_rn(inv, sum_ss, -__fmul_rn(mean_s, mean_s));
+    if (var_r < 1e-5f || var_s < 1e-5f) return 2.0f;
+    const float covar = __fmaf_rn(-mean_r, mean_s, e_rs);
+    const float c = __fmaf_rn(-covar, rcp_approx(sqrt_approx(__fmul_rn(var_r, var_s))), 1.0f);
+    return fmaxf(0.0f, fminf(c, 2.0f));
 }
 
 // NCC of the warped 6x6 patch against the register-resident reference patch.  APD.cu:622-662.
@@ -234,43 +324,29 @@ template <bool U>
 __device__ __forceinline__ float patch_ncc36(const PassK &K, const Homog &Hm, int layer, int px, int py,
                                              const RefPatch &rp) {
     const float *h = Hm.h;
-    // fold the +0.5 texel-centre offset into the numerators: (X + 0.5 Z) / Z
-    const float g0 = fmaf(0.5f, h[6], h[0]), g1 = fmaf(0.5f, h[7], h[1]), g2 = fmaf(0.5f, h[8], h[2]);
-    const float g3 = fmaf(0.5f, h[6], h[3]), g4 = fmaf(0.5f, h[7], h[4]), g5 = fmaf(0.5f, h[8], h[5]);
     float sum_s = 0.0f, sum_ss = 0.0f, sum_rs = 0.0f;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-        const float xi = (float)(px + 2 * i - 5);
-        const float bx = fmaf(g0, xi, g2), by = fmaf(g3, xi, g5), bz = fmaf(h[6], xi, h[8]);
+        const RowX row = sample_row(h, (float)(px + 2 * i - 5));
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            const float yj = (float)(py + 2 * j - 5);
-            const float X = fmaf(g1, yj, bx), Y = fmaf(g4, yj, by), Z = fmaf(h[7], yj, bz);
-            const float iz = rcp_approx(Z);
-            const float s = fetch<U>(K, X * iz, Y * iz, layer);
-            sum_s += s;
-            sum_ss = fmaf(s, s, sum_ss);
-            sum_rs = fmaf(rp.r[i * 6 + j], s, sum_rs);
+            float u, v;
+            sample_coord_loop(h, row, (float)(py + 2 * j - 5), u, v);
+            const float s = fetch<U>(K, u, v, layer);
+            sum_s = __fadd_rn(sum_s, s);
+            sum_ss = __fmaf_rn(s, s, sum_ss);
+            sum_rs = __fmaf_rn(rp.r[i * 6 + j], s, sum_rs);
         }
     }
-    const float inv = 1.0f / 36.0f;
-    const float mean_s = inv * sum_s, e_rs = inv * sum_rs;
-    const float var_s = fmaf(inv, sum_ss, -__fmul_rn(mean_s, mean_s));
-    if (rp.var < 1e-5f || var_s < 1e-5f) return 2.0f;
-    const float covar = fmaf(-rp.mean, mean_s, e_rs);
-    return fmaxf(0.0f, fminf(2.0f, fmaf(-covar, rsqrtf(rp.var * var_s), 1.0f)));
+    return ncc_epilogue(1.0f / 36.0f, rp.mean, rp.var, sum_s, sum_ss, sum_rs);
 }
 
 // ComputeBilateralNCCOld, APD.cu:596-663 (branch A).  Only the patch centre is bounds-checked (quirk 8).
 template <bool U>
-__device__ __forceinline__ float ncc_old(const PassK &K, const ViewK &vk, int px, int py, float3 m, const RefPatch &rp) {
-    const Homog Hm = make_homography(vk, m);
-    const float *h = Hm.h;
-    const float fxp = (float)px, fyp = (float)py;
-    const float Z = __fadd_rn(__fmaf_rn(h[7], fyp, __fmul_rn(h[6], fxp)), h[8]);
-    const float iz = rcp_approx(Z);
-    const float ptx = __fmul_rn(__fadd_rn(__fmaf_rn(h[1], fyp, __fmul_rn(h[0], fxp)), h[2]), iz);
-    const float pty = __fmul_rn(__fadd_rn(__fmaf_rn(h[4], fyp, __fmul_rn(h[3], fxp)), h[5]), iz);
+__device__ __forceinline__ float ncc_old(const PassK &K, const ViewK &vk, int px, int py, const PlaneM &m, const RefPatch &rp) {
+    const Homog Hm = make_homography(K, vk, m);
+    float ptx, pty;
+    project_point(Hm.h, (float)px, (float)py, ptx, pty);
     if (ptx >= (float)K.W || ptx < 0.0f || pty >= (float)K.H || pty < 0.0f) return 2.0f;
     return patch_ncc36<U>(K, Hm, vk.layer, px, py, rp);
 }
@@ -299,13 +375,13 @@ __device__ __forceinline__ void load_anchor_ref(const PassK &K, const short2 *an
             for (int j = -5; j <= 5; j += 5) {
                 const float r = fetch<U>(K, (float)(a.x + i) + 0.5f, (float)(a.y + j) + 0.5f, K.ref_layer);
                 ar.r[k * 9 + t++] = r;
-                sr += r;
-                srr = fmaf(r, r, srr);
+                sr = __fadd_rn(sr, r);
+                srr = __fmaf_rn(r, r, srr);
             }
         }
         const float inv = 1.0f / 9.0f;
-        ar.mean[k] = inv * sr;
-        ar.var[k] = fmaf(inv, srr, -__fmul_rn(ar.mean[k], ar.mean[k]));
+        ar.mean[k] = __fmul_rn(inv, sr);
+        ar.var[k] = __fmaf_rn(inv, srr, -__fmul_rn(ar.mean[k], ar.mean[k]));
     }
 }
 
@@ -318,35 +394,45 @@ __device__ __forceinline__ float patch_ncc9(const PassK &K, const Homog &Hm, int
     int t = 0;
 #pragma unroll
     for (int i = -5; i <= 5; i += 5) {
+        const RowX row = sample_row(h, (float)(ax + i));
 #pragma unroll
         for (int j = -5; j <= 5; j += 5) {
-            const float fxp = (float)(ax + i), fyp = (float)(ay + j);
-            const float Z = h[6] * fxp + h[7] * fyp + h[8];
-            const float iz = rcp_approx(Z);
-            const float X = (h[0] * fxp + h[1] * fyp + h[2]) * iz, Y = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
-            const float s = fetch<U>(K, X + 0.5f, Y + 0.5f, layer);
-            ss += s; sss = fmaf(s, s, sss); srs = fmaf(r9[t++], s, srs);
+            float u, v;
+            sample_coord_loop(h, row, (float)(ay + j), u, v);
+            const float s = fetch<U>(K, u, v, layer);
+            ss = __fadd_rn(ss, s); sss = __fmaf_rn(s, s, sss); srs = __fmaf_rn(r9[t++], s, srs);
         }
     }
-    const float inv = 1.0f / 9.0f;
-    const float mean_s = inv * ss, e_rs = inv * srs;
-    const float var_s = fmaf(inv, sss, -__fmul_rn(mean_s, mean_s));
-    if (var_r < 1e-5f || var_s < 1e-5f) return 2.0f;
-    const float covar = fmaf(-mean_r, mean_s, e_rs);
-    return fmaxf(0.0f, fminf(2.0f, fmaf(-covar, rsqrtf(var_r * var_s), 1.0f)));
+    return ncc_epilogue(1.0f / 9.0f, mean_r, var_r, ss, sss, srs);
+}
+
+// Softmax-weighted mean of the anchor costs + the focal mix with the centre cost, APD.cu:431-446, 572-587 as built:
+//   e_i = EX2((c_i - max) * log2e); w_i = e_i * RCP(sum e); strong = FFMA chain of w_i * c_i; MIN(strong, 2);
+//   "0.25 * center + 0.75 * strong" is evaluated in double and rounded once: DFMA(center, 0.25, strong * 0.75) ->
+//   in float that is FFMA(0.75, strong, 0.25 * center) (0.25 * center is exact, the FFMA rounds the exact sum once)
+__device__ __forceinline__ float focal_mix(float center_cost, const float *sc, int ns) {
+    if (ns == 0) return center_cost;
+    float mx = -1e10f;
+    for (int i = 0; i < ns; ++i) if (sc[i] > mx) mx = sc[i];
+    float sum = 0.0f, acc = 0.0f;
+    float wts[8];
+    for (int i = 0; i < ns; ++i) { wts[i] = __expf(__fsub_rn(sc[i], mx)); sum = __fadd_rn(sum, wts[i]); }
+    const float rs = rcp_approx(sum);
+    for (int i = 0; i < ns; ++i) acc = __fmaf_rn(__fmul_rn(wts[i], rs), sc[i], acc);
+    acc = acc > 2.0f ? 2.0f : acc;
+    return __fmaf_rn(0.75f, acc, __fmul_rn(0.25f, center_cost));
 }
 
 // ComputeBilateralNCCNew, APD.cu:448-593 (sa_mask == 0): centre patch + focal-weighted anchor patches.
 template <bool U>
-__device__ __forceinline__ float ncc_new(const PassK &K, const ViewK &vk, int view_bit, int px, int py, float3 m,
+__device__ __forceinline__ float ncc_new(const PassK &K, const ViewK &vk, int view_bit, int px, int py, const PlaneM &m,
                                          const RefPatch &rp, const AnchorRef &ar) {
-    const Homog Hm = make_homography(vk, m);
+    const Homog Hm = make_homography(K, vk, m);
     const float *h = Hm.h;
     const float fW = (float)K.W, fH = (float)K.H;
     {
-        const float fxp = (float)px, fyp = (float)py;
-        const float iz = rcp_approx(h[6] * fxp + h[7] * fyp + h[8]);
-        const float ptx = (h[0] * fxp + h[1] * fyp + h[2]) * iz, pty = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
+        float ptx, pty;
+        project_point(h, (float)px, (float)py, ptx, pty);
         if (ptx >= fW || ptx < 0.0f || pty >= fH || pty < 0.0f) return 2.0f;
     }
     // anchor 0 is the pixel itself (APD.cu:1887): its bounds test repeats the centre test above
@@ -357,24 +443,15 @@ __device__ __forceinline__ float ncc_new(const PassK &K, const ViewK &vk, int vi
     for (int k = 0; k < 8; ++k) {
         const short2 a = ar.a[k];
         if (a.x == -1) continue;
-        const float fxp = (float)a.x, fyp = (float)a.y;
-        const float iz = rcp_approx(h[6] * fxp + h[7] * fyp + h[8]);
-        const float ax = (h[0] * fxp + h[1] * fyp + h[2]) * iz, ay = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
+        float ax, ay;
+        project_point(h, (float)a.x, (float)a.y, ax, ay);
         if (ax < 0.0f || ay < 0.0f || ax >= fW || ay >= fH) {
             if ((K.sel[a.x + a.y * K.W] >> view_bit) & 1u) sc[ns++] = 2.0f;
             continue;
         }
         sc[ns++] = patch_ncc9<U>(K, Hm, vk.layer, a.x, a.y, &ar.r[k * 9], ar.mean[k], ar.var[k]);
     }
-    if (ns == 0) return center_cost;
-    float mx = -1e10f;
-    for (int i = 0; i < ns; ++i) mx = fmaxf(mx, sc[i]);
-    float sum = 0.0f, acc = 0.0f;
-    float wts[8];
-    for (int i = 0; i < ns; ++i) { wts[i] = __expf(sc[i] - mx); sum += wts[i]; }
-    for (int i = 0; i < ns; ++i) acc += (wts[i] / sum) * sc[i];
-    acc = fminf(acc, 2.0f);
-    return 0.25f * center_cost + 0.75f * acc;
+    return focal_mix(center_cost, sc, ns);
 }
 
 // ------------------------------------------------------------------------------------------------ segment labels (SAM masks)
@@ -433,8 +510,8 @@ __device__ __forceinline__ void load_sa_info(const PassK &K, int px, int py, con
                     else {
                         const float v = rp.r[((xo + 5) / 2) * 6 + (yo + 5) / 2];
                         bm |= 1ull << t;
-                        s += v;
-                        ss = fmaf(v, v, ss);
+                        s = __fadd_rn(s, v);
+                        ss = __fmaf_rn(v, v, ss);
                         cnt++;
                     }
                 }
@@ -442,8 +519,8 @@ __device__ __forceinline__ void load_sa_info(const PassK &K, int px, int py, con
         }
         si.bmask = bm;
         si.b_inv = sa_inv_count(cnt, 36, 1.0f / 36.0f);
-        si.b_mean = si.b_inv * s;
-        si.b_var = fmaf(si.b_inv, ss, -__fmul_rn(si.b_mean, si.b_mean));
+        si.b_mean = __fmul_rn(si.b_inv, s);
+        si.b_var = __fmaf_rn(si.b_inv, ss, -__fmul_rn(si.b_mean, si.b_mean));
     }
     {
         unsigned long long nm = 0ull;
@@ -458,64 +535,55 @@ __device__ __forceinline__ void load_sa_info(const PassK &K, int px, int py, con
                 if (lab == 0 || sa[y * W + x] == lab) {
                     const float v = rp.r[i * 6 + j];
                     nm |= 1ull << (i * 6 + j);
-                    s += v;
-                    ss = fmaf(v, v, ss);
+                    s = __fadd_rn(s, v);
+                    ss = __fmaf_rn(v, v, ss);
                     cnt++;
                 }
             }
         }
         si.nmask = nm;
         si.n_inv = sa_inv_count(cnt, 36, 1.0f / 36.0f);
-        si.n_mean = si.n_inv * s;
-        si.n_var = fmaf(si.n_inv, ss, -__fmul_rn(si.n_mean, si.n_mean));
+        si.n_mean = __fmul_rn(si.n_inv, s);
+        si.n_var = __fmaf_rn(si.n_inv, ss, -__fmul_rn(si.n_mean, si.n_mean));
     }
 }
 
-// masked twin of patch_ncc36: ORDER 0 = branch A order (i outer, j inner), ORDER 1 = the quadrant walk.  Sample coordinates
-// are formed exactly as in patch_ncc36, so a full mask in order 0 gives the same samples.
+// masked twin of patch_ncc36: ORDER 0 = branch A order (i outer, j inner: the loops of APD.cu:523-533 with their hoisted
+// x products), ORDER 1 = the quadrant walk of APD.cu:665-698 (single points).  A full mask in order 0 gives patch_ncc36.
 template <bool U, int ORDER>
 __device__ __forceinline__ float patch_ncc36_masked(const PassK &K, const Homog &Hm, int layer, int px, int py, const RefPatch &rp,
                                                     unsigned long long mask, float mean_r, float var_r, float inv) {
     const float *h = Hm.h;
-    const float g0 = fmaf(0.5f, h[6], h[0]), g1 = fmaf(0.5f, h[7], h[1]), g2 = fmaf(0.5f, h[8], h[2]);
-    const float g3 = fmaf(0.5f, h[6], h[3]), g4 = fmaf(0.5f, h[7], h[4]), g5 = fmaf(0.5f, h[8], h[5]);
     float sum_s = 0.0f, sum_ss = 0.0f, sum_rs = 0.0f;
 #pragma unroll
     for (int t = 0; t < 36; ++t) {
         const int xo = ORDER == 0 ? 2 * (t / 6) - 5 : sa_b_xoff(t), yo = ORDER == 0 ? 2 * (t % 6) - 5 : sa_b_yoff(t);
         if ((mask >> t) & 1ull) {
-            const float xi = (float)(px + xo), yj = (float)(py + yo);
-            const float bx = fmaf(g0, xi, g2), by = fmaf(g3, xi, g5), bz = fmaf(h[6], xi, h[8]);
-            const float X = fmaf(g1, yj, bx), Y = fmaf(g4, yj, by), Z = fmaf(h[7], yj, bz);
-            const float iz = rcp_approx(Z);
-            const float s = fetch<U>(K, X * iz, Y * iz, layer);
-            sum_s += s;
-            sum_ss = fmaf(s, s, sum_ss);
-            sum_rs = fmaf(rp.r[((xo + 5) / 2) * 6 + (yo + 5) / 2], s, sum_rs);
+            float u, v;
+            if (ORDER == 0) sample_coord_loop(h, sample_row(h, (float)(px + xo)), (float)(py + yo), u, v);
+            else sample_coord_point(h, (float)(px + xo), (float)(py + yo), u, v);
+            const float s = fetch<U>(K, u, v, layer);
+            sum_s = __fadd_rn(sum_s, s);
+            sum_ss = __fmaf_rn(s, s, sum_ss);
+            sum_rs = __fmaf_rn(rp.r[((xo + 5) / 2) * 6 + (yo + 5) / 2], s, sum_rs);
         }
     }
-    const float mean_s = inv * sum_s, e_rs = inv * sum_rs;
-    const float var_s = fmaf(inv, sum_ss, -__fmul_rn(mean_s, mean_s));
-    if (var_r < 1e-5f || var_s < 1e-5f) return 2.0f;
-    const float covar = fmaf(-mean_r, mean_s, e_rs);
-    return fmaxf(0.0f, fminf(2.0f, fmaf(-covar, rsqrtf(var_r * var_s), 1.0f)));
+    return ncc_epilogue(inv, mean_r, var_r, sum_s, sum_ss, sum_rs);
 }
 
 // ComputeBilateralNCCOld with a label map, APD.cu:596-721
 template <bool U>
-__device__ __forceinline__ float ncc_old_sa(const PassK &K, const ViewK &vk, int px, int py, float3 m, const RefPatch &rp,
+__device__ __forceinline__ float ncc_old_sa(const PassK &K, const ViewK &vk, int px, int py, const PlaneM &m, const RefPatch &rp,
                                             const SaInfo &si) {
-    const Homog Hm = make_homography(vk, m);
-    const float *h = Hm.h;
-    const float fxp = (float)px, fyp = (float)py;
-    const float Z = __fadd_rn(__fmaf_rn(h[7], fyp, __fmul_rn(h[6], fxp)), h[8]);
-    const float iz = rcp_approx(Z);
-    const float ptx = __fmul_rn(__fadd_rn(__fmaf_rn(h[1], fyp, __fmul_rn(h[0], fxp)), h[2]), iz);
-    const float pty = __fmul_rn(__fadd_rn(__fmaf_rn(h[4], fyp, __fmul_rn(h[3], fxp)), h[5]), iz);
+    const Homog Hm = make_homography(K, vk, m);
+    float ptx, pty;
+    project_point(Hm.h, (float)px, (float)py, ptx, pty);
     if (ptx >= (float)K.W || ptx < 0.0f || pty >= (float)K.H || pty < 0.0f) return 2.0f;
-    // "const int center = pt.y * src_camera.width + pt.x": one FFMA and a truncation; the float can round up to W*H (clamped)
-    const int c = min(__float2int_rz(__fmaf_rn(pty, (float)K.W, ptx)), K.W * K.H - 1);
-    if (K.sa[c] == 0) return patch_ncc36<U>(K, Hm, vk.layer, px, py, rp);
+    // "const int center = pt.y * src_camera.width + pt.x": one FFMA of the FLOAT coordinates and a truncation.  For points in
+    // the last source row the index runs past the map (up to W - 1 elements): the reference reads whatever follows its
+    // cudaMalloc'ed buffer there (undefined).  Defined here as label 0 -> branch A (what the reference golden vectors show).
+    const int c = __float2int_rz(__fmaf_rn(pty, (float)K.W, ptx));
+    if (c >= K.W * K.H || K.sa[c] == 0) return patch_ncc36<U>(K, Hm, vk.layer, px, py, rp);
     if (si.bmask == 0ull) return 2.0f;  // 0 * (1/0) = NaN everywhere: max(0, min(2, NaN)) = 2
     return patch_ncc36_masked<U, 1>(K, Hm, vk.layer, px, py, rp, si.bmask, si.b_mean, si.b_var, si.b_inv);
 }
@@ -548,8 +616,8 @@ __device__ __forceinline__ void anchor_ref_apply_labels(const PassK &K, AnchorRe
                 if (lab == 0 || sa[y * W + x] == lab) {
                     const float r = ar.r[k * 9 + t];
                     tm |= 1u << t;
-                    sr += r;
-                    srr = fmaf(r, r, srr);
+                    sr = __fadd_rn(sr, r);
+                    srr = __fmaf_rn(r, r, srr);
                     cnt++;
                 }
                 t++;
@@ -557,8 +625,8 @@ __device__ __forceinline__ void anchor_ref_apply_labels(const PassK &K, AnchorRe
         }
         ar.tmask[k] = (unsigned short)tm;
         ar.inv[k] = sa_inv_count(cnt, 9, 1.0f / 9.0f);
-        ar.mean[k] = ar.inv[k] * sr;
-        ar.var[k] = fmaf(ar.inv[k], srr, -__fmul_rn(ar.mean[k], ar.mean[k]));
+        ar.mean[k] = __fmul_rn(ar.inv[k], sr);
+        ar.var[k] = __fmaf_rn(ar.inv[k], srr, -__fmul_rn(ar.mean[k], ar.mean[k]));
     }
 }
 
@@ -576,37 +644,31 @@ __device__ __forceinline__ float patch_ncc9_masked(const PassK &K, const Homog &
     int t = 0;
 #pragma unroll
     for (int i = -5; i <= 5; i += 5) {
+        const RowX row = sample_row(h, (float)(ax + i));
 #pragma unroll
         for (int j = -5; j <= 5; j += 5) {
             if ((tmask >> t) & 1u) {
-                const float fxp = (float)(ax + i), fyp = (float)(ay + j);
-                const float Z = h[6] * fxp + h[7] * fyp + h[8];
-                const float iz = rcp_approx(Z);
-                const float X = (h[0] * fxp + h[1] * fyp + h[2]) * iz, Y = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
-                const float s = fetch<U>(K, X + 0.5f, Y + 0.5f, layer);
-                ss += s; sss = fmaf(s, s, sss); srs = fmaf(r9[t], s, srs);
+                float u, v;
+                sample_coord_loop(h, row, (float)(ay + j), u, v);
+                const float s = fetch<U>(K, u, v, layer);
+                ss = __fadd_rn(ss, s); sss = __fmaf_rn(s, s, sss); srs = __fmaf_rn(r9[t], s, srs);
             }
             t++;
         }
     }
-    const float mean_s = inv * ss, e_rs = inv * srs;
-    const float var_s = fmaf(inv, sss, -__fmul_rn(mean_s, mean_s));
-    if (var_r < 1e-5f || var_s < 1e-5f) return 2.0f;
-    const float covar = fmaf(-mean_r, mean_s, e_rs);
-    return fmaxf(0.0f, fminf(2.0f, fmaf(-covar, rsqrtf(var_r * var_s), 1.0f)));
+    return ncc_epilogue(inv, mean_r, var_r, ss, sss, srs);
 }
 
 // ComputeBilateralNCCNew with a label map, APD.cu:448-593
 template <bool U>
-__device__ __forceinline__ float ncc_new_sa(const PassK &K, const ViewK &vk, int view_bit, int px, int py, float3 m,
+__device__ __forceinline__ float ncc_new_sa(const PassK &K, const ViewK &vk, int view_bit, int px, int py, const PlaneM &m,
                                             const RefPatch &rp, const AnchorRefSa &ar, const SaInfo &si) {
-    const Homog Hm = make_homography(vk, m);
+    const Homog Hm = make_homography(K, vk, m);
     const float *h = Hm.h;
     const float fW = (float)K.W, fH = (float)K.H;
     {
-        const float fxp = (float)px, fyp = (float)py;
-        const float iz = rcp_approx(h[6] * fxp + h[7] * fyp + h[8]);
-        const float ptx = (h[0] * fxp + h[1] * fyp + h[2]) * iz, pty = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
+        float ptx, pty;
+        project_point(h, (float)px, (float)py, ptx, pty);
         if (ptx >= fW || ptx < 0.0f || pty >= fH || pty < 0.0f) return 2.0f;
     }
     // anchor 0 = the pixel itself: no tap of its segment -> "continue" with center_cost still 0 (APD.cu:543-545)
@@ -618,24 +680,15 @@ __device__ __forceinline__ float ncc_new_sa(const PassK &K, const ViewK &vk, int
     for (int k = 0; k < 8; ++k) {
         const short2 a = ar.a[k];
         if (a.x == -1) continue;
-        const float fxp = (float)a.x, fyp = (float)a.y;
-        const float iz = rcp_approx(h[6] * fxp + h[7] * fyp + h[8]);
-        const float ax = (h[0] * fxp + h[1] * fyp + h[2]) * iz, ay = (h[3] * fxp + h[4] * fyp + h[5]) * iz;
+        float ax, ay;
+        project_point(h, (float)a.x, (float)a.y, ax, ay);
         if (ax < 0.0f || ay < 0.0f || ax >= fW || ay >= fH) {
             if ((K.sel[a.x + a.y * K.W] >> view_bit) & 1u) sc[ns++] = 2.0f;
             continue;
         }
         sc[ns++] = patch_ncc9_masked<U>(K, Hm, vk.layer, a.x, a.y, &ar.r[k * 9], ar.tmask[k], ar.mean[k], ar.var[k], ar.inv[k]);
     }
-    if (ns == 0) return center_cost;
-    float mx = -1e10f;
-    for (int i = 0; i < ns; ++i) mx = fmaxf(mx, sc[i]);
-    float sum = 0.0f, acc = 0.0f;
-    float wts[8];
-    for (int i = 0; i < ns; ++i) { wts[i] = __expf(sc[i] - mx); sum += wts[i]; }
-    for (int i = 0; i < ns; ++i) acc += (wts[i] / sum) * sc[i];
-    acc = fminf(acc, 2.0f);
-    return 0.25f * center_cost + 0.75f * acc;
+    return focal_mix(center_cost, sc, ns);
 }
 
 // compile-time switch used by the kernel bodies that exist in both flavours
@@ -646,7 +699,7 @@ __device__ __forceinline__ void load_sa(const PassK &K, int px, int py, const Re
     if constexpr (SA) load_sa_info(K, px, py, rp, si);
 }
 template <bool U, bool SA>
-__device__ __forceinline__ float ncc_old_x(const PassK &K, const ViewK &vk, int px, int py, float3 m, const RefPatch &rp,
+__device__ __forceinline__ float ncc_old_x(const PassK &K, const ViewK &vk, int px, int py, const PlaneM &m, const RefPatch &rp,
                                            const typename SaTypes<SA>::Info &si) {
     if constexpr (SA) return ncc_old_sa<U>(K, vk, px, py, m, rp, si);
     else return ncc_old<U>(K, vk, px, py, m, rp);
@@ -658,35 +711,79 @@ __device__ __forceinline__ void load_anchor_ref_x(const PassK &K, const short2 *
     else load_anchor_ref<U>(K, anc, ar);
 }
 template <bool U, bool SA>
-__device__ __forceinline__ float ncc_new_x(const PassK &K, const ViewK &vk, int view_bit, int px, int py, float3 m, const RefPatch &rp,
+__device__ __forceinline__ float ncc_new_x(const PassK &K, const ViewK &vk, int view_bit, int px, int py, const PlaneM &m, const RefPatch &rp,
                                            const typename SaTypes<SA>::Anchors &ar, const typename SaTypes<SA>::Info &si) {
     if constexpr (SA) return ncc_new_sa<U>(K, vk, view_bit, px, py, m, rp, ar, si);
     else return ncc_new<U>(K, vk, view_bit, px, py, m, rp, ar);
 }
 
-// ComputeGeomConsistencyCost, APD.cu:865-902, with the camera pair pre-composed:
-//   forward:  x_s ~ depth * A p~ + b ;  backward:  x_r ~ d_s * Ai s~ + bi
+// ------------------------------------------------------------------------------------------------ world route (APD.cu:831-863)
+// Get3DPointonWorld_cu as built:  X = ((x - K2) * depth) * RCP(K0), Y = ((y - K5) * depth) * RCP(K4), Z = depth;
+// world = R^T (X, Y, Z) + c with every row a dot3_ref
+__device__ __forceinline__ float3 point_to_world(const float *Kc, const float *R, const float *c, float x, float y, float depth) {
+    const float X = __fmul_rn(__fmul_rn(__fsub_rn(x, Kc[2]), depth), rcp_approx(Kc[0]));
+    const float Y = __fmul_rn(__fmul_rn(__fsub_rn(y, Kc[5]), depth), rcp_approx(Kc[4]));
+    return make_float3(__fadd_rn(dot3_ref(R[0], X, R[3], Y, R[6], depth), c[0]),
+                       __fadd_rn(dot3_ref(R[1], X, R[4], Y, R[7], depth), c[1]),
+                       __fadd_rn(dot3_ref(R[2], X, R[5], Y, R[8], depth), c[2]));
+}
+// ProjectonCamera_cu as built:  tmp = R P + t (dot3_ref + FADD);  depth = dot3_ref(K6.., tmp);  point = dot3_ref(K0.., tmp) * RCP(depth).
+// Returns the two numerators and RCP(depth) so that callers can contract as the reference build does.
+struct Proj { float nx, ny, d, rd; };
+__device__ __forceinline__ Proj project_to_camera(const float *Kc, const float *R, const float *t, float3 P) {
+    const float tx = __fadd_rn(dot3_ref(R[0], P.x, R[1], P.y, R[2], P.z), t[0]);
+    const float ty = __fadd_rn(dot3_ref(R[3], P.x, R[4], P.y, R[5], P.z), t[1]);
+    const float tz = __fadd_rn(dot3_ref(R[6], P.x, R[7], P.y, R[8], P.z), t[2]);
+    Proj q;
+    q.d = dot3_ref(Kc[6], tx, Kc[7], ty, Kc[8], tz);
+    q.rd = rcp_approx(q.d);
+    q.nx = dot3_ref(Kc[0], tx, Kc[1], ty, Kc[2], tz);
+    q.ny = dot3_ref(Kc[3], tx, Kc[4], ty, Kc[5], tz);
+    return q;
+}
+// depth-map texel under a projected point: "tex2D(depth_image, (int)x + 0.5f, (int)y + 0.5f)" through a clamped linear
+// texture == the texel at the clamped truncation (cvt.rzi saturates, NaN -> 0)
+__device__ __forceinline__ float source_depth(const PassK &K, int v, float sx, float sy) {
+    const int ix = clampi(__float2int_rz(sx), 0, K.W - 1), iy = clampi(__float2int_rz(sy), 0, K.H - 1);
+    return K.depth[(size_t)(v + 1) * K.W * K.H + (size_t)iy * K.W + ix];
+}
+
+// ComputeGeomConsistencyCost, APD.cu:865-902: forward through world coordinates into the source view, the source depth
+// texel, back into the reference view; diff = FFMA(-numerator, RCP(depth), p); cost = min(3, SQRT(FFMA(dc, dc, dr * dr)))
 __device__ __forceinline__ float geom_cost(const PassK &K, const ViewK &vk, int v /* 0-based source */, int px, int py,
                                            float4 plane) {
     const float depth = depth_from_plane(K, plane, px, py);
     const float fxp = (float)px, fyp = (float)py;
-    // explicit intrinsics throughout: the truncation below turns a 1-ulp difference into another depth texel
-    const float qx = __fadd_rn(__fmaf_rn(vk.A[1], fyp, __fmul_rn(vk.A[0], fxp)), vk.A[2]);
-    const float qy = __fadd_rn(__fmaf_rn(vk.A[4], fyp, __fmul_rn(vk.A[3], fxp)), vk.A[5]);
-    const float qz = __fadd_rn(__fmaf_rn(vk.A[7], fyp, __fmul_rn(vk.A[6], fxp)), vk.A[8]);
-    const float Z = __fmaf_rn(depth, qz, vk.b[2]);
-    const float sx = __fdividef(__fmaf_rn(depth, qx, vk.b[0]), Z), sy = __fdividef(__fmaf_rn(depth, qy, vk.b[1]), Z);
-    // "(int)src_pt.x + 0.5f" through a clamped texture == clamped truncation (cvt.rzi saturates, NaN -> 0)
-    const int ix = clampi(__float2int_rz(sx), 0, K.W - 1), iy = clampi(__float2int_rz(sy), 0, K.H - 1);
-    const float sd = K.depth[(size_t)(v + 1) * K.W * K.H + (size_t)iy * K.W + ix];
+    const float3 Pw = point_to_world(K.Kr, K.R, K.c, fxp, fyp, depth);
+    const Proj s = project_to_camera(vk.K, vk.R, vk.t, Pw);
+    const float sx = __fmul_rn(s.nx, s.rd), sy = __fmul_rn(s.ny, s.rd);
+    const float sd = source_depth(K, v, sx, sy);
     if (sd == 0.0f) return 3.0f;
-    const float rx = __fadd_rn(__fmaf_rn(vk.Ai[1], sy, __fmul_rn(vk.Ai[0], sx)), vk.Ai[2]);
-    const float ry = __fadd_rn(__fmaf_rn(vk.Ai[4], sy, __fmul_rn(vk.Ai[3], sx)), vk.Ai[5]);
-    const float rz = __fadd_rn(__fmaf_rn(vk.Ai[7], sy, __fmul_rn(vk.Ai[6], sx)), vk.Ai[8]);
-    const float Zr = __fmaf_rn(sd, rz, vk.bi[2]);
-    const float bx = __fdividef(__fmaf_rn(sd, rx, vk.bi[0]), Zr), by = __fdividef(__fmaf_rn(sd, ry, vk.bi[1]), Zr);
-    const float dc = __fsub_rn(fxp, bx), dr = __fsub_rn(fyp, by);
-    return fminf(3.0f, sqrtf(__fmaf_rn(dr, dr, __fmul_rn(dc, dc))));
+    const float3 Ps = point_to_world(vk.K, vk.R, vk.c, sx, sy, sd);
+    const Proj b = project_to_camera(K.Kr, K.R, K.t, Ps);
+    const float dc = __fmaf_rn(-b.nx, b.rd, fxp), dr = __fmaf_rn(-b.ny, b.rd, fyp);
+    return fminf(sqrt_approx(__fmaf_rn(dc, dc, __fmul_rn(dr, dr))), 3.0f);
+}
+
+// baseline of a source view as DepthToWeak / LocalRefine compute it (APD.cu:2142-2147): float differences of the camera
+// centres, FFMA(d2, d2, FFMA(d0, d0, d1 * d1)), MUFU.SQRT
+__device__ __forceinline__ float view_baseline(const PassK &K, const ViewK &vk) {
+    const float d0 = __fsub_rn(K.c[0], vk.c[0]), d1 = __fsub_rn(K.c[1], vk.c[1]), d2 = __fsub_rn(K.c[2], vk.c[2]);
+    return sqrt_approx(dot3_ref(d0, d0, d1, d1, d2, d2));
+}
+
+// The disparity sweep of DepthToWeak / LocalRefine (APD.cu:2155-2165, 2399-2407) as built:
+//   base_line = sum * RCP(float(valid_src));  fb = base_line * K0;  disp = fb * RCP(origin_depth);
+//   p_depth(pd) = fb * RCP(disp + float(pd))
+struct SweepDepths {
+    float fb, disp;
+    __device__ __forceinline__ float depth(int pd) const { return __fmul_rn(fb, rcp_approx(__fadd_rn(disp, (float)pd))); }
+};
+__device__ __forceinline__ SweepDepths sweep_depths(const PassK &K, float base_sum, int valid_src, float origin_depth) {
+    SweepDepths s;
+    s.fb = __fmul_rn(__fmul_rn(rcp_approx((float)valid_src), base_sum), K.fx);
+    s.disp = __fmul_rn(s.fb, rcp_approx(origin_depth));
+    return s;
 }
 
 // packed view weights: 4 bits per view in a uint4

@@ -42,7 +42,7 @@ __device__ __forceinline__ void k_init_body(const PassK &K, int tiles_x, int pha
     load_ref_patch<U>(K, px, py, rp);
     typename SaTypes<SA>::Info si;
     load_sa<SA>(K, px, py, rp, si);
-    const float3 m = plane_row(K, pl);
+    const PlaneM m = plane_row(K, pl);
     const bool weak = K.use_apd && K.weak[center] == APDE_WEAK;
     float cv[kMaxSrc], cvc[kMaxSrc];
     int num_valid = 0;
@@ -65,10 +65,10 @@ __device__ __forceinline__ void k_init_body(const PassK &K, int tiles_x, int pha
     const int top_k = min(num_valid, K.top_k);
     if (top_k > 0) {
         float acc = 0.0f;
-        for (int i = 0; i < top_k; ++i) acc += cv[i];
+        for (int i = 0; i < top_k; ++i) acc = __fadd_rn(acc, cv[i]);
         const float thr = cv[top_k - 1];
         for (int i = 0; i < K.N; ++i) if (cvc[i] <= thr) sel |= (1u << i);
-        cost = acc / top_k;
+        cost = __fmul_rn(rcp_approx((float)top_k), acc);  // "cost / top_k" as built: MUFU.RCP(float(top_k)) * cost
     }
     K.sel[center] = sel;
     K.costs[center] = cost;
@@ -119,7 +119,7 @@ __device__ __forceinline__ void k_prop_strong_body(const PassK &K, int iter, int
 #pragma unroll 1
     for (int h = 0; h < 8; ++h) {
         if ((flags >> h) & 1u) {
-            const float3 m = plane_row(K, K.planes[pos[h]]);
+            const PlaneM m = plane_row(K, K.planes[pos[h]]);
 #pragma unroll 1
             for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_old_x<U, SA>(K, K.v[v], px, py, m, rp, si);
             n_old += N;
@@ -173,7 +173,7 @@ __device__ __forceinline__ void k_prop_strong_body(const PassK &K, int iter, int
 
     // current hypothesis on the selected views
     {
-        const float3 m = plane_row(K, plane_c);
+        const PlaneM m = plane_row(K, plane_c);
         float acc = 0.0f;
         for (uint32_t mk = wmask; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
@@ -209,7 +209,7 @@ __device__ __forceinline__ void k_prop_strong_body(const PassK &K, int iter, int
         float4 tp = (i == 0 || i == 4) ? base_n : (i == 3 ? cand_n[1] : cand_n[0]);
         const float d = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : base_d);
         tp.w = distance_to_origin(K, px, py, d, tp);
-        const float3 m = plane_row(K, tp);
+        const PlaneM m = plane_row(K, tp);
         float acc = 0.0f;
         for (uint32_t mk = wmask; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
@@ -295,7 +295,7 @@ __device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int i
 #pragma unroll 1
         for (int h = 0; h < 8; ++h) {
             if ((flags >> h) & 1u) {
-                const float3 m = plane_row(K, K.planes[pos[h]]);
+                const PlaneM m = plane_row(K, K.planes[pos[h]]);
 #pragma unroll 1
                 for (int v = 0; v < N; ++v) sc[(h * N + v) * stride] = ncc_old<U>(K, K.v[v], px, py, m, rp);
                 n_old += N;
@@ -380,7 +380,7 @@ __device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int i
                 for (int i = 0; i < nh; ++i) {
                     const float4 tp = make_float4(scol[(kStrongPlaneSlot + 4 * i + 0) * stride], scol[(kStrongPlaneSlot + 4 * i + 1) * stride],
                                                   scol[(kStrongPlaneSlot + 4 * i + 2) * stride], scol[(kStrongPlaneSlot + 4 * i + 3) * stride]);
-                    const float3 m = plane_row(K, tp);
+                    const PlaneM m = plane_row(K, tp);
                     float c = ncc_old<U>(K, vk, spx, spy, m, rp);
                     n_old++;
                     if (use_geom) { c = __fmaf_rn(K.geom_factor, geom_cost(K, vk, v, spx, spy, tp), c); n_geom++; }
@@ -543,38 +543,37 @@ __device__ __forceinline__ void k_depth_to_weak_body(const PassK &K, int tiles_x
     int valid_src = 0;
     for (uint32_t mk = sel; mk; mk &= mk - 1) {
         const int v = __ffs(mk) - 1;
-        weight_normal += (float)vw_get(w, v);
-        base_line += s_vk[v].baseline;
+        weight_normal = __fadd_rn(weight_normal, (float)vw_get(w, v));
+        base_line = __fadd_rn(base_line, view_baseline(K, s_vk[v]));
         valid_src++;
     }
     if (valid_src == 0) { K.weak[center] = APDE_UNKNOWN; return; }
-    base_line /= valid_src;
+    const SweepDepths sd = sweep_depths(K, base_line, valid_src, origin_depth);
 
     RefPatch rp;
     load_ref_patch<U>(K, px, py, rp);
     typename SaTypes<SA>::Info si;
     load_sa<SA>(K, px, py, rp, si);
     unsigned n_old = 0, n_geom = 0;
-    const float fb = K.fx * base_line;
-    const float disp = fb / origin_depth;
     const int radius = 30, n = 61;
+    const float rwn = rcp_approx(weight_normal);
     float pc[61];
 #pragma unroll 1
     for (int pd = -radius; pd <= radius; ++pd) {
-        const float p_depth = fb / (disp + pd);
+        const float p_depth = sd.depth(pd);
         if (p_depth < K.depth_min || p_depth > K.depth_max) { pc[pd + radius] = 2.0f; continue; }
         float4 tp = opl;
         tp.w = distance_to_origin(K, px, py, p_depth, tp);
-        const float3 m = plane_row(K, tp);
+        const PlaneM m = plane_row(K, tp);
         float p_cost = 0.0f;
         for (uint32_t mk = sel; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
             float tc = ncc_old_x<U, SA>(K, s_vk[v], px, py, m, rp, si);
             n_old++;
-            if (K.geom) { tc += K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp); n_geom++; }
-            p_cost += tc * (float)vw_get(w, v);
+            if (K.geom) { tc = __fmaf_rn(K.geom_factor, geom_cost(K, s_vk[v], v, px, py, tp), tc); n_geom++; }
+            p_cost = __fmaf_rn((float)vw_get(w, v), tc, p_cost);  // APD.cu:2179-2181 as built
         }
-        p_cost /= weight_normal;
+        p_cost = __fmul_rn(p_cost, rwn);
         pc[pd + radius] = (2.0f > p_cost) ? p_cost : 2.0f;  // OpenCV MIN(2.0f, p_cost): NaN -> 2
     }
     count_evals(K, n_old, 0, n_geom);
@@ -623,27 +622,21 @@ __global__ void __launch_bounds__(128) k_confidence(const __grid_constant__ Pass
     const float ref_depth = K.planes[center].w;
     if (ref_depth <= 0.0f) { K.weak[center] = APDE_UNKNOWN; return; }
     const float fxp = (float)px, fyp = (float)py;
+    const float3 Pw = point_to_world(K.Kr, K.R, K.c, fxp, fyp, ref_depth);
     int nc = 1;
     for (uint32_t mk = sel; mk; mk &= mk - 1) {
         const int v = __ffs(mk) - 1;
         const ViewK &vk = s_vk[v];
-        const float qx = vk.A[0] * fxp + vk.A[1] * fyp + vk.A[2];
-        const float qy = vk.A[3] * fxp + vk.A[4] * fyp + vk.A[5];
-        const float qz = vk.A[6] * fxp + vk.A[7] * fyp + vk.A[8];
-        const float Z = fmaf(ref_depth, qz, vk.b[2]);
-        const float sx = fmaf(ref_depth, qx, vk.b[0]) / Z, sy = fmaf(ref_depth, qy, vk.b[1]) / Z;
-        const int ix = clampi(__float2int_rz(sx), 0, K.W - 1), iy = clampi(__float2int_rz(sy), 0, K.H - 1);
-        const float sd = K.depth[(size_t)(v + 1) * K.W * K.H + (size_t)iy * K.W + ix];
+        const Proj s = project_to_camera(vk.K, vk.R, vk.t, Pw);
+        const float sx = __fmul_rn(s.nx, s.rd), sy = __fmul_rn(s.ny, s.rd);
+        const float sd = source_depth(K, v, sx, sy);
         if (sd <= 0.0f) continue;
         nc += 1;
-        const float rx = vk.Ai[0] * sx + vk.Ai[1] * sy + vk.Ai[2];
-        const float ry = vk.Ai[3] * sx + vk.Ai[4] * sy + vk.Ai[5];
-        const float rz = vk.Ai[6] * sx + vk.Ai[7] * sy + vk.Ai[8];
-        const float Zr = fmaf(sd, rz, vk.bi[2]);
-        const float bx = fmaf(sd, rx, vk.bi[0]) / Zr, by = fmaf(sd, ry, vk.bi[1]) / Zr;
-        const float dc = fxp - bx, dr = fyp - by;
-        if (sqrtf(dc * dc + dr * dr) <= 2.0f) nc += 2;
-        if (fabsf(ref_depth - Zr) / ref_depth <= 0.02f) nc += 2;
+        const float3 Ps = point_to_world(vk.K, vk.R, vk.c, sx, sy, sd);
+        const Proj b = project_to_camera(K.Kr, K.R, K.t, Ps);
+        const float dc = __fmaf_rn(-b.nx, b.rd, fxp), dr = __fmaf_rn(-b.ny, b.rd, fyp);
+        if (sqrt_approx(__fmaf_rn(dc, dc, __fmul_rn(dr, dr))) <= 2.0f) nc += 2;
+        if (__fmul_rn(fabsf(__fsub_rn(ref_depth, b.d)), rcp_approx(ref_depth)) <= 0.02f) nc += 2;
     }
     K.conf[center] = (uint8_t)min(nc, 255);
 }
@@ -673,44 +666,43 @@ __device__ __forceinline__ void k_local_refine_body(const PassK &K, int tiles_x)
     {
         float4 tp = opl;
         tp.w = distance_to_origin(K, px, py, origin_depth, tp);
-        const float3 m = plane_row(K, tp);
+        const PlaneM m = plane_row(K, tp);
         for (uint32_t mk = sel; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
             float tc = ncc_old_x<U, SA>(K, s_vk[v], px, py, m, rp, si);
             n_old++;
-            if (K.geom) { tc += K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp); n_geom++; }
+            if (K.geom) { tc = __fmaf_rn(K.geom_factor, geom_cost(K, s_vk[v], v, px, py, tp), tc); n_geom++; }
             const float wv = (float)vw_get(w, v);
-            cost_now += tc * wv;
-            weight_normal += wv;
-            base_line += s_vk[v].baseline;
+            cost_now = __fmaf_rn(wv, tc, cost_now);  // APD.cu:2380-2383 as built
+            weight_normal = __fadd_rn(weight_normal, wv);
+            base_line = __fadd_rn(base_line, view_baseline(K, s_vk[v]));
             valid_src++;
         }
     }
     if (weight_normal == 0.0f) { count_evals(K, n_old, 0, n_geom); return; }
-    cost_now /= weight_normal;
-    base_line /= valid_src;
-    const float fb = K.fx * base_line;
-    const float disp = fb / origin_depth;
+    const float rwn = rcp_approx(weight_normal);
+    const SweepDepths sd = sweep_depths(K, base_line, valid_src, origin_depth);
     float min_cost = 2.0f, best_depth = origin_depth;
 #pragma unroll 1
     for (int pd = -5; pd <= 5; ++pd) {
-        const float p_depth = fb / (disp + pd);
+        const float p_depth = sd.depth(pd);
         if (p_depth < K.depth_min || p_depth > K.depth_max) continue;
         float4 tp = opl;
         tp.w = distance_to_origin(K, px, py, p_depth, tp);
-        const float3 m = plane_row(K, tp);
+        const PlaneM m = plane_row(K, tp);
         float tc = 0.0f;
         for (uint32_t mk = sel; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
             const float wv = (float)vw_get(w, v);
-            tc += ncc_old_x<U, SA>(K, s_vk[v], px, py, m, rp, si) * wv;
+            tc = __fmaf_rn(wv, ncc_old_x<U, SA>(K, s_vk[v], px, py, m, rp, si), tc);  // APD.cu:2417-2419 as built
             n_old++;
-            if (K.geom) { tc += K.geom_factor * geom_cost(K, s_vk[v], v, px, py, tp) * wv; n_geom++; }
+            if (K.geom) { tc = __fmaf_rn(wv, __fmul_rn(K.geom_factor, geom_cost(K, s_vk[v], v, px, py, tp)), tc); n_geom++; }
         }
-        tc /= weight_normal;
+        tc = __fmul_rn(tc, rwn);
         if (tc < min_cost) { min_cost = tc; best_depth = p_depth; }
     }
-    if ((double)(cost_now - min_cost) > 0.1) K.planes[center].w = best_depth;
+    // "cost_now /= weight_normal; ... cost_now - min_cost > 0.1" is one FFMA in the reference build, compared in double
+    if ((double)__fmaf_rn(rwn, cost_now, -min_cost) > 0.1) K.planes[center].w = best_depth;
     count_evals(K, n_old, 0, n_geom);
 }
 __global__ void __launch_bounds__(128) k_local_refine(const __grid_constant__ PassK K, int tiles_x) {
@@ -739,7 +731,7 @@ __device__ __forceinline__ void k_eval_costs_body(const PassK &K, int n, const i
         load_ref_patch<U>(K, px, py, rp);
         typename SaTypes<SA>::Info si;
         load_sa<SA>(K, px, py, rp, si);
-        const float3 m = plane_row(K, pl);
+        const PlaneM m = plane_row(K, pl);
         if (mode == 0) {
             c = ncc_old_x<U, SA>(K, K.v[v], px, py, m, rp, si);
         } else {
@@ -770,23 +762,9 @@ int prop_block_threads(int N) {
     return 32;
 }
 
-// APDE_QUAD_KERNELS=1 selects the experimental quad-cooperative kernels (apde_quad.cu).  Measured on B200 (r01): they
-// hold the texture rate under scattered hypotheses but need 2.7x the issue slots per evaluation (exact-order shuffle
-// chain), and lose to the thread-per-evaluation kernels of this file on the real, mostly coherent workload.
-static bool use_thread_kernels() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("APDE_QUAD_KERNELS"); v = (e && e[0] == '1') ? 0 : 1; }
-    return v == 1;
-}
-
 cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStream_t st, float *curve) {
     const int W = K.W, H = K.H, N = K.N;
     const bool sa = K.sa != nullptr;  // segment labels: the <SA = true> twins of the thread-per-pixel kernels
-    if (!use_thread_kernels() && !sa) {
-        bool handled = false;
-        cudaError_t e = launch_stage_quad(K, stage, iter, color, st, curve, &handled);
-        if (handled || e != cudaSuccess) return e;
-    }
     const int ylimit = min(H, half_rows_limit(H));
     const int tiles8x = (W + 7) / 8;
     const size_t vsm = sizeof(float) * views_smem_floats(N);

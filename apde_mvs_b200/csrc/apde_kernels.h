@@ -8,8 +8,6 @@ namespace apde {
 
 // run one kernel of the pass (stage ids of include/apde.h).  curve: optional [P][61] export of DepthToWeak.
 cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStream_t st, float *curve);
-// quad-cooperative versions of the heavy stages (apde_quad.cu); *handled = false when the stage has none
-cudaError_t launch_stage_quad(const PassK &K, int stage, int iter, int color, cudaStream_t st, float *curve, bool *handled);
 // weak-texture (APD) stages: nearest strong, anchors, RANSAC fit, deformable propagation
 cudaError_t launch_stage_apd(const PassK &K, int stage, int iter, int color, cudaStream_t st);
 cudaError_t launch_eval_costs(const PassK &K, int n, const int *tuples, const float4 *planes, int mode, float *out,

@@ -133,7 +133,7 @@ __device__ __forceinline__ void k_prop_eval1_body(const PassK &K, const PropK &B
         float c;
         if (h == 8 || ((flags >> h) & 1u)) {
             const float4 pl = (h == 8) ? K.planes[center] : K.planes[B.cand_pos[(size_t)h * B.cap + pix]];
-            const float3 m = plane_row(K, pl);
+            const PlaneM m = plane_row(K, pl);
             c = WEAK ? ncc_new_x<U, SA>(K, vk, v, px, py, m, rp, ar, si) : ncc_old_x<U, SA>(K, vk, px, py, m, rp, si);
             n_eval++;
         } else {
@@ -397,7 +397,7 @@ __device__ __forceinline__ void k_prop_eval3_body(const PassK &K, const PropK &B
     for (int i = i0; i < nh; ++i) {
         if (WEAK && mode == 0 && i == 8) continue;  // (random depth, random normal): the same plane as slot 3
         const float4 tp = B.hyp[(size_t)i * cap + pix];
-        const float3 m = plane_row(K, tp);
+        const PlaneM m = plane_row(K, tp);
         float c = WEAK ? ncc_new_x<U, SA>(K, vk, v, px, py, m, rp, ar, si) : ncc_old_x<U, SA>(K, vk, px, py, m, rp, si);
         n_eval++;
         if (geom) { c = c + K.geom_factor * geom_cost(K, vk, v, px, py, tp); n_geom++; }

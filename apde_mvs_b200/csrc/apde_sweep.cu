@@ -81,23 +81,21 @@ __device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, in
     const uint32_t sel = K.sel[center];
     float base_line = 0.0f;
     int valid_src = 0;
-    for (uint32_t mk = sel; mk; mk &= mk - 1) { base_line += s_vk[__ffs(mk) - 1].baseline; valid_src++; }
-    base_line /= valid_src;
+    for (uint32_t mk = sel; mk; mk &= mk - 1) { base_line = __fadd_rn(base_line, view_baseline(K, s_vk[__ffs(mk) - 1])); valid_src++; }
+    const SweepDepths sd = sweep_depths(K, base_line, valid_src, origin_depth);
     RefPatch rp;
     load_ref_patch<U>(K, px, py, rp);
     typename SaTypes<SA>::Info si;
     load_sa<SA>(K, px, py, rp, si);
     unsigned n_old = 0, n_geom = 0;
-    const float fb = K.fx * base_line;
-    const float disp = fb / origin_depth;
     const int r = (cls == 2) ? kSweepR : 5;
 #pragma unroll 1
     for (int pd = -r; pd <= r; ++pd) {
-        const float p_depth = fb / (disp + pd);
+        const float p_depth = sd.depth(pd);
         if (p_depth < K.depth_min || p_depth > K.depth_max) continue;
         float4 tp = opl;
         tp.w = distance_to_origin(K, px, py, p_depth, tp);
-        const float3 m = plane_row(K, tp);
+        const PlaneM m = plane_row(K, tp);
         ncc[(size_t)(pd + kSweepR) * ncols + col] = ncc_old_x<U, SA>(K, vk, px, py, m, rp, si);
         n_old++;
         if (K.geom) { geo[(size_t)(pd + kSweepR) * ncols + col] = geom_cost(K, vk, v, px, py, tp); n_geom++; }
@@ -105,7 +103,7 @@ __device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, in
     {
         float4 tp = opl;
         tp.w = distance_to_origin(K, px, py, origin_depth, tp);
-        const float3 m = plane_row(K, tp);
+        const PlaneM m = plane_row(K, tp);
         ncc[(size_t)kSweepN * ncols + col] = ncc_old_x<U, SA>(K, vk, px, py, m, rp, si);
         n_old++;
         if (K.geom) { geo[(size_t)kSweepN * ncols + col] = geom_cost(K, vk, v, px, py, tp); n_geom++; }
@@ -146,28 +144,27 @@ __global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ 
     int valid_src = 0;
     for (uint32_t mk = sel; mk; mk &= mk - 1) {
         const int v = __ffs(mk) - 1;
-        weight_normal += (float)vw_get(w, v);
-        base_line += s_vk[v].baseline;
+        weight_normal = __fadd_rn(weight_normal, (float)vw_get(w, v));
+        base_line = __fadd_rn(base_line, view_baseline(K, s_vk[v]));
         valid_src++;
     }
-    base_line /= valid_src;
-    const float fb = K.fx * base_line;
-    const float disp = fb / origin_depth;
+    const SweepDepths sd = sweep_depths(K, base_line, valid_src, origin_depth);
+    const float rwn = rcp_approx(weight_normal);
     const int radius = kSweepR, n = kSweepN;
     float pc[kSweepN];
 #pragma unroll 1
     for (int pd = -radius; pd <= radius; ++pd) {
-        const float p_depth = fb / (disp + pd);
+        const float p_depth = sd.depth(pd);
         if (p_depth < K.depth_min || p_depth > K.depth_max) { pc[pd + radius] = 2.0f; continue; }
         float p_cost = 0.0f;
         for (uint32_t mk = sel; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
             const size_t o = (size_t)(pd + radius) * ncols + colidx[(size_t)v * Pb + loc];
             float tc = ncc[o];
-            if (K.geom) tc += K.geom_factor * geo[o];
-            p_cost += tc * (float)vw_get(w, v);
+            if (K.geom) tc = __fmaf_rn(K.geom_factor, geo[o], tc);
+            p_cost = __fmaf_rn((float)vw_get(w, v), tc, p_cost);  // APD.cu:2179-2181 as built
         }
-        p_cost /= weight_normal;
+        p_cost = __fmul_rn(p_cost, rwn);
         pc[pd + radius] = (2.0f > p_cost) ? p_cost : 2.0f;  // OpenCV MIN(2.0f, p_cost): NaN -> 2
     }
     if (curve) for (int i = 0; i < n; ++i) curve[(size_t)idx * n + i] = pc[i];
@@ -211,35 +208,34 @@ __global__ void __launch_bounds__(128) k_sweep_refine(const __grid_constant__ Pa
         const int v = __ffs(mk) - 1;
         const size_t o = (size_t)kSweepN * ncols + colidx[(size_t)v * Pb + loc];
         float tc = ncc[o];
-        if (K.geom) tc += K.geom_factor * geo[o];
+        if (K.geom) tc = __fmaf_rn(K.geom_factor, geo[o], tc);
         const float wv = (float)vw_get(w, v);
-        cost_now += tc * wv;
-        weight_normal += wv;
-        base_line += s_vk[v].baseline;
+        cost_now = __fmaf_rn(wv, tc, cost_now);  // APD.cu:2380-2383 as built
+        weight_normal = __fadd_rn(weight_normal, wv);
+        base_line = __fadd_rn(base_line, view_baseline(K, s_vk[v]));
         valid_src++;
     }
     if (weight_normal == 0.0f) return;
-    cost_now /= weight_normal;
-    base_line /= valid_src;
-    const float fb = K.fx * base_line;
-    const float disp = fb / origin_depth;
+    const float rwn = rcp_approx(weight_normal);
+    const SweepDepths sd = sweep_depths(K, base_line, valid_src, origin_depth);
     float min_cost = 2.0f, best_depth = origin_depth;
 #pragma unroll 1
     for (int pd = -5; pd <= 5; ++pd) {
-        const float p_depth = fb / (disp + pd);
+        const float p_depth = sd.depth(pd);
         if (p_depth < K.depth_min || p_depth > K.depth_max) continue;
         float tc = 0.0f;
         for (uint32_t mk = sel; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
             const size_t o = (size_t)(pd + kSweepR) * ncols + colidx[(size_t)v * Pb + loc];
             const float wv = (float)vw_get(w, v);
-            tc += ncc[o] * wv;
-            if (K.geom) tc += K.geom_factor * geo[o] * wv;
+            tc = __fmaf_rn(wv, ncc[o], tc);  // APD.cu:2417-2419 as built
+            if (K.geom) tc = __fmaf_rn(wv, __fmul_rn(K.geom_factor, geo[o]), tc);
         }
-        tc /= weight_normal;
+        tc = __fmul_rn(tc, rwn);
         if (tc < min_cost) { min_cost = tc; best_depth = p_depth; }
     }
-    if ((double)(cost_now - min_cost) > 0.1) K.planes[idx].w = best_depth;
+    // "cost_now /= weight_normal; ... cost_now - min_cost > 0.1" is one FFMA in the reference build, compared in double
+    if ((double)__fmaf_rn(rwn, cost_now, -min_cost) > 0.1) K.planes[idx].w = best_depth;
 }
 
 // ------------------------------------------------------------------------------------------------ host side

@@ -4,6 +4,15 @@
  * Plain fp32 restatement of the reference algorithm, one function per reference function, each citing the
  * reference file:line it follows.  Compiled with -ffp-contract=off so every operation rounds like the
  * source says.  Nothing in the product (apde_mvs_b200/) links, imports or executes this file.
+ *
+ * ARITHMETIC.  The reference is built with nvcc -O3 --use_fast_math (CMakeLists.txt:26): the compiler contracts
+ * multiply-adds into FFMA and turns every division / sqrt into MUFU.RCP / MUFU.SQRT.  Which product of "a*b + c*d + e*f"
+ * is rounded on its own decides sample coordinates at the 1-ulp level, and those land on the texture unit's 1/256 weight
+ * grid -- so the restatement follows the reference BUILD operation for operation (pattern read from the SASS of
+ * oracle/_ref/libapd_ref.so, profiles/r02_reference_sass_arithmetic.md): std::fmaf where the build has an FFMA, a separately
+ * rounded product where it has an FMUL.  The only approximation left: MUFU.RCP / MUFU.SQRT / MUFU.EX2 are hardware tables
+ * (<= 1 ulp off the correctly rounded value); the oracle uses the correctly rounded 1/x, sqrt, exp2 instead (mufu_rcp,
+ * mufu_sqrt, mufu_ex2 below).  That residual is what the golden-vector tests bound.
  */
 #include "apd_oracle.h"
 
@@ -144,6 +153,17 @@ inline int find_min_cost_index(const float *costs, int n) { /* APD.cu:60-71, tie
 
 inline int is_set(uint32_t v, int n) { return (v >> n) & 1u; }
 
+/* hardware special-function units of the reference build, approximated by the correctly rounded value (<= 1 ulp) */
+inline float mufu_rcp(float x) { return 1.0f / x; }
+inline float mufu_sqrt(float x) { return std::sqrt(x); }
+inline float mufu_ex2(float x) { return std::exp2(x); }
+/* a0*b0 + a1*b1 + a2*b2 as the reference build contracts every such sum: FMUL of the MIDDLE product, FFMA of the first,
+ * FFMA of the last (APD.cu:338-362, 408-422, 841-843, 856-862, 222) */
+inline float dot3_ref(float a0, float b0, float a1, float b1, float a2, float b2) {
+    const float mid = a1 * b1;
+    return std::fmaf(a2, b2, std::fmaf(a0, b0, mid));
+}
+
 inline void normalize3(F4 *v) { /* APD.cu:157-164 (rsqrtf) */
     const float n2 = v->x * v->x + v->y * v->y + v->z * v->z;
     const float inv = 1.0f / std::sqrt(n2);
@@ -165,8 +185,8 @@ inline void pdf_to_cdf(float *probs, int n) { /* APD.cu:174-188 */
 }
 
 inline void get_3d_point(const orc_camera &cam, float px, float py, float depth, float *X) { /* APD.cu:190-202 */
-    X[0] = depth * (px - cam.K[2]) / cam.K[0];
-    X[1] = depth * (py - cam.K[5]) / cam.K[4];
+    X[0] = (depth * (px - cam.K[2])) * mufu_rcp(cam.K[0]); /* as built: FMUL, FMUL by MUFU.RCP(K0) */
+    X[1] = (depth * (py - cam.K[5])) * mufu_rcp(cam.K[4]);
     X[2] = depth;
 }
 
@@ -180,12 +200,14 @@ inline F4 view_direction(const orc_camera &cam, I2 p, float depth) { /* APD.cu:2
 inline float distance_to_origin(const orc_camera &cam, I2 p, float depth, F4 n) { /* APD.cu:218-223 */
     float X[3];
     get_3d_point(cam, (float)p.x, (float)p.y, depth, X);
-    return -(n.x * X[0] + n.y * X[1] + n.z * X[2]);
+    return -dot3_ref(X[0], n.x, X[1], n.y, X[2], n.z);
 }
 
 inline float depth_from_plane(const orc_camera &cam, F4 pl, I2 p) { /* APD.cu:237-240 */
-    return -pl.w * cam.K[0] /
-           ((p.x - cam.K[2]) * pl.x + (cam.K[0] / cam.K[4]) * (p.y - cam.K[5]) * pl.y + cam.K[0] * pl.z);
+    /* as built: (w * -K0) * RCP(FFMA(K0, nz, FFMA(x - K2, nx, ((K0 * RCP(K4)) * (y - K5)) * ny))) */
+    const float ty = ((cam.K[0] * mufu_rcp(cam.K[4])) * ((float)p.y - cam.K[5])) * pl.y;
+    const float den = std::fmaf(cam.K[0], pl.z, std::fmaf((float)p.x - cam.K[2], pl.x, ty));
+    return (pl.w * -cam.K[0]) * mufu_rcp(den);
 }
 
 inline F4 random_normal(const orc_camera &cam, I2 p, Rng &rng, float depth) { /* APD.cu:242-268 */
@@ -240,85 +262,91 @@ inline F4 random_plane(const orc_camera &cam, I2 p, Rng &rng, float dmin, float 
 
 inline F4 normal_to_world(const orc_camera &cam, F4 pl) { /* TransformNormal APD.cu:405-413 */
     F4 r;
-    r.x = cam.R[0] * pl.x + cam.R[3] * pl.y + cam.R[6] * pl.z;
-    r.y = cam.R[1] * pl.x + cam.R[4] * pl.y + cam.R[7] * pl.z;
-    r.z = cam.R[2] * pl.x + cam.R[5] * pl.y + cam.R[8] * pl.z;
+    r.x = dot3_ref(cam.R[0], pl.x, cam.R[3], pl.y, cam.R[6], pl.z);
+    r.y = dot3_ref(cam.R[1], pl.x, cam.R[4], pl.y, cam.R[7], pl.z);
+    r.z = dot3_ref(cam.R[2], pl.x, cam.R[5], pl.y, cam.R[8], pl.z);
     r.w = pl.w;
     return r;
 }
 
 inline F4 normal_to_refcam(const orc_camera &cam, F4 pl) { /* TransformNormal2RefCam APD.cu:415-423 */
     F4 r;
-    r.x = cam.R[0] * pl.x + cam.R[1] * pl.y + cam.R[2] * pl.z;
-    r.y = cam.R[3] * pl.x + cam.R[4] * pl.y + cam.R[5] * pl.z;
-    r.z = cam.R[6] * pl.x + cam.R[7] * pl.y + cam.R[8] * pl.z;
+    r.x = dot3_ref(cam.R[0], pl.x, cam.R[1], pl.y, cam.R[2], pl.z);
+    r.y = dot3_ref(cam.R[3], pl.x, cam.R[4], pl.y, cam.R[5], pl.z);
+    r.z = dot3_ref(cam.R[6], pl.x, cam.R[7], pl.y, cam.R[8], pl.z);
     r.w = pl.w;
     return r;
 }
 
-/* APD.cu:334-394 */
+/* APD.cu:334-394, as built (see the header): every three-term sum is a dot3_ref; C_rel = ref_C - src_C;
+ *   H_i  = FFMA(-(t_rel[r] * n_c), RCP(w), R_rel[i]);  tmp0 = H0 * RCP(K0);  tmp1 = H1 * RCP(K4);
+ *   tmp2 = H2 + FFMA(H0 * -K2, RCP(K0), -((H1 * K5) * RCP(K4)));  H'0 = FFMA(Ks0, tmp0, Ks2 * tmp6) ...  H'6 = Ks8 * tmp6 */
 void homography(const orc_camera &rc, const orc_camera &sc, F4 pl, float *H) {
-    float ref_C[3], src_C[3];
-    ref_C[0] = -(rc.R[0] * rc.t[0] + rc.R[3] * rc.t[1] + rc.R[6] * rc.t[2]);
-    ref_C[1] = -(rc.R[1] * rc.t[0] + rc.R[4] * rc.t[1] + rc.R[7] * rc.t[2]);
-    ref_C[2] = -(rc.R[2] * rc.t[0] + rc.R[5] * rc.t[1] + rc.R[8] * rc.t[2]);
-    src_C[0] = -(sc.R[0] * sc.t[0] + sc.R[3] * sc.t[1] + sc.R[6] * sc.t[2]);
-    src_C[1] = -(sc.R[1] * sc.t[0] + sc.R[4] * sc.t[1] + sc.R[7] * sc.t[2]);
-    src_C[2] = -(sc.R[2] * sc.t[0] + sc.R[5] * sc.t[1] + sc.R[8] * sc.t[2]);
+    float Sr[3], Ss[3]; /* -ref_C, -src_C */
+    for (int j = 0; j < 3; ++j) {
+        Sr[j] = dot3_ref(rc.R[0 + j], rc.t[0], rc.R[3 + j], rc.t[1], rc.R[6 + j], rc.t[2]);
+        Ss[j] = dot3_ref(sc.R[0 + j], sc.t[0], sc.R[3 + j], sc.t[1], sc.R[6 + j], sc.t[2]);
+    }
     float Rr[9], Cr[3], tr[3];
-    Rr[0] = sc.R[0] * rc.R[0] + sc.R[1] * rc.R[1] + sc.R[2] * rc.R[2];
-    Rr[1] = sc.R[0] * rc.R[3] + sc.R[1] * rc.R[4] + sc.R[2] * rc.R[5];
-    Rr[2] = sc.R[0] * rc.R[6] + sc.R[1] * rc.R[7] + sc.R[2] * rc.R[8];
-    Rr[3] = sc.R[3] * rc.R[0] + sc.R[4] * rc.R[1] + sc.R[5] * rc.R[2];
-    Rr[4] = sc.R[3] * rc.R[3] + sc.R[4] * rc.R[4] + sc.R[5] * rc.R[5];
-    Rr[5] = sc.R[3] * rc.R[6] + sc.R[4] * rc.R[7] + sc.R[5] * rc.R[8];
-    Rr[6] = sc.R[6] * rc.R[0] + sc.R[7] * rc.R[1] + sc.R[8] * rc.R[2];
-    Rr[7] = sc.R[6] * rc.R[3] + sc.R[7] * rc.R[4] + sc.R[8] * rc.R[5];
-    Rr[8] = sc.R[6] * rc.R[6] + sc.R[7] * rc.R[7] + sc.R[8] * rc.R[8];
-    Cr[0] = ref_C[0] - src_C[0];
-    Cr[1] = ref_C[1] - src_C[1];
-    Cr[2] = ref_C[2] - src_C[2];
-    tr[0] = sc.R[0] * Cr[0] + sc.R[1] * Cr[1] + sc.R[2] * Cr[2];
-    tr[1] = sc.R[3] * Cr[0] + sc.R[4] * Cr[1] + sc.R[5] * Cr[2];
-    tr[2] = sc.R[6] * Cr[0] + sc.R[7] * Cr[1] + sc.R[8] * Cr[2];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            Rr[3 * i + j] = dot3_ref(sc.R[3 * i], rc.R[3 * j], sc.R[3 * i + 1], rc.R[3 * j + 1], sc.R[3 * i + 2], rc.R[3 * j + 2]);
+    for (int j = 0; j < 3; ++j) Cr[j] = Ss[j] - Sr[j]; /* (-Sr) - (-Ss) */
+    for (int i = 0; i < 3; ++i) tr[i] = dot3_ref(sc.R[3 * i], Cr[0], sc.R[3 * i + 1], Cr[1], sc.R[3 * i + 2], Cr[2]);
 
-    H[0] = Rr[0] - tr[0] * pl.x / pl.w;
-    H[1] = Rr[1] - tr[0] * pl.y / pl.w;
-    H[2] = Rr[2] - tr[0] * pl.z / pl.w;
-    H[3] = Rr[3] - tr[1] * pl.x / pl.w;
-    H[4] = Rr[4] - tr[1] * pl.y / pl.w;
-    H[5] = Rr[5] - tr[1] * pl.z / pl.w;
-    H[6] = Rr[6] - tr[2] * pl.x / pl.w;
-    H[7] = Rr[7] - tr[2] * pl.y / pl.w;
-    H[8] = Rr[8] - tr[2] * pl.z / pl.w;
-
+    const float rw = mufu_rcp(pl.w), rK0 = mufu_rcp(rc.K[0]), rK4 = mufu_rcp(rc.K[4]);
     float tmp[9];
-    tmp[0] = H[0] / rc.K[0];
-    tmp[1] = H[1] / rc.K[4];
-    tmp[2] = -H[0] * rc.K[2] / rc.K[0] - H[1] * rc.K[5] / rc.K[4] + H[2];
-    tmp[3] = H[3] / rc.K[0];
-    tmp[4] = H[4] / rc.K[4];
-    tmp[5] = -H[3] * rc.K[2] / rc.K[0] - H[4] * rc.K[5] / rc.K[4] + H[5];
-    tmp[6] = H[6] / rc.K[0];
-    tmp[7] = H[7] / rc.K[4];
-    tmp[8] = -H[6] * rc.K[2] / rc.K[0] - H[7] * rc.K[5] / rc.K[4] + H[8];
-
-    H[0] = sc.K[0] * tmp[0] + sc.K[2] * tmp[6];
-    H[1] = sc.K[0] * tmp[1] + sc.K[2] * tmp[7];
-    H[2] = sc.K[0] * tmp[2] + sc.K[2] * tmp[8];
-    H[3] = sc.K[4] * tmp[3] + sc.K[5] * tmp[6];
-    H[4] = sc.K[4] * tmp[4] + sc.K[5] * tmp[7];
-    H[5] = sc.K[4] * tmp[5] + sc.K[5] * tmp[8];
-    H[6] = sc.K[8] * tmp[6];
-    H[7] = sc.K[8] * tmp[7];
-    H[8] = sc.K[8] * tmp[8];
+    for (int r = 0; r < 3; ++r) {
+        const float q0 = pl.x * tr[r], q1 = pl.y * tr[r], q2 = pl.z * tr[r];
+        const float H0 = std::fmaf(-q0, rw, Rr[3 * r + 0]);
+        const float H1 = std::fmaf(-q1, rw, Rr[3 * r + 1]);
+        const float H2 = std::fmaf(-q2, rw, Rr[3 * r + 2]);
+        tmp[3 * r + 0] = H0 * rK0;
+        tmp[3 * r + 1] = H1 * rK4;
+        const float a = H0 * -rc.K[2];
+        const float b = (H1 * rc.K[5]) * rK4;
+        tmp[3 * r + 2] = H2 + std::fmaf(a, rK0, -b);
+    }
+    for (int c = 0; c < 3; ++c) {
+        const float m0 = sc.K[2] * tmp[6 + c], m1 = sc.K[5] * tmp[6 + c];
+        H[c] = std::fmaf(sc.K[0], tmp[c], m0);
+        H[3 + c] = std::fmaf(sc.K[4], tmp[3 + c], m1);
+        H[6 + c] = sc.K[8] * tmp[6 + c];
+    }
 }
 
-inline F2 corresponding_point(const float *H, int px, int py) { /* APD.cu:396-403 */
-    const float x = H[0] * px + H[1] * py + H[2];
-    const float y = H[3] * px + H[4] * py + H[5];
-    const float z = H[6] * px + H[7] * py + H[8];
-    return F2{x / z, y / z};
+/* ComputeCorrespondingPoint of a single point, APD.cu:396-403, as built outside the patch loops:
+ *   X = H2 + FFMA(H0, x, H1 * y) (same for Y, Z);  pt = (X * RCP(Z), Y * RCP(Z)) */
+inline void project_xyz(const float *H, int px, int py, float &X, float &Y, float &Z) {
+    const float x = (float)px, y = (float)py;
+    const float m0 = H[1] * y, m1 = H[4] * y, m2 = H[7] * y;
+    X = H[2] + std::fmaf(H[0], x, m0);
+    Y = H[5] + std::fmaf(H[3], x, m1);
+    Z = H[8] + std::fmaf(H[6], x, m2);
+}
+inline F2 corresponding_point(const float *H, int px, int py) {
+    float X, Y, Z;
+    project_xyz(H, px, py, X, Y, Z);
+    const float rz = mufu_rcp(Z);
+    return F2{X * rz, Y * rz};
+}
+/* texture coordinate of a single point: "pt + 0.5f" is contracted with the division, FFMA(X, RCP(Z), 0.5) (APD.cu:687-689) */
+inline F2 sample_coord_point(const float *H, int px, int py) {
+    float X, Y, Z;
+    project_xyz(H, px, py, X, Y, Z);
+    const float rz = mufu_rcp(Z);
+    return F2{std::fmaf(X, rz, 0.5f), std::fmaf(Y, rz, 0.5f)};
+}
+/* inside the patch loops (i outer over x, j inner over y; APD.cu:629-634, 523-533) the build hoists the x products out of
+ * the inner loop, which changes the contraction:  X = H2 + FFMA(H1, y, H0 * x);  u = FFMA(X, RCP(Z), 0.5) */
+inline F2 sample_coord_loop(const float *H, int px, int py) {
+    const float x = (float)px, y = (float)py;
+    const float x0 = H[0] * x, x3 = H[3] * x, x6 = H[6] * x;
+    const float X = H[2] + std::fmaf(H[1], y, x0);
+    const float Y = H[5] + std::fmaf(H[4], y, x3);
+    const float Z = H[8] + std::fmaf(H[7], y, x6);
+    const float rz = mufu_rcp(Z);
+    return F2{std::fmaf(X, rz, 0.5f), std::fmaf(Y, rz, 0.5f)};
 }
 
 inline F4 load4(const float *p, size_t i) { return F4{p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]}; }
@@ -365,8 +393,8 @@ inline float patch_ncc(const orc_problem *pb, const float *H, int src_idx, int c
             const int rx = cx + i, ry = cy + j;
             if (filter_label >= 0 && sa_label(pb, rx, ry) != filter_label) continue;
             const float ref_pix = tex_point(ref, W, Hh, rx, ry);
-            const F2 sp = corresponding_point(H, rx, ry);
-            const float src_pix = tex_linear(src, W, Hh, sp.x + 0.5f, sp.y + 0.5f, pb->tex_mode);
+            const F2 sp = sample_coord_loop(H, rx, ry);
+            const float src_pix = tex_linear(src, W, Hh, sp.x, sp.y, pb->tex_mode);
             const float weight = 1.0f; /* quirk 1: "bilateral" weight == 1 (APD.cu:534,635) */
             /* nvcc (-fmad=true, the reference's build) folds weight == 1 and contracts every "sum += a * b" into one
              * FMA.  This matters: on weak texture var = E[x^2] - E[x]^2 is a difference of two ~16384 numbers whose
@@ -390,9 +418,9 @@ inline float patch_ncc(const orc_problem *pb, const float *H, int src_idx, int c
     const float kMinVar = 1e-5f;
     if (var_ref < kMinVar || var_src < kMinVar) return 2.0f;
     const float covar = std::fmaf(-mean_ref, mean_src, e_rs);
-    const float denom = std::sqrt(var_ref * var_src);
+    const float denom = mufu_sqrt(var_ref * var_src);
     /* max(0, min(2, v)) with CUDA fminf/fmaxf NaN semantics (quirk 10): NaN -> 2 */
-    const float v = std::fmaf(-covar, 1.0f / denom, 1.0f);
+    const float v = std::fmaf(-covar, mufu_rcp(denom), 1.0f);
     return std::fmax(0.0f, std::fmin(2.0f, v));
 }
 
@@ -412,8 +440,8 @@ inline float patch_ncc_quadrants(const orc_problem *pb, const float *H, int src_
             if (rx < 0 || rx >= W || ry < 0 || ry >= Hh) continue;
             if (pb->sa_mask[rx + (size_t)ry * W] != center_id) break;
             const float ref_pix = tex_point(ref, W, Hh, rx, ry);
-            const F2 sp = corresponding_point(H, rx, ry);
-            const float src_pix = tex_linear(src, W, Hh, sp.x + 0.5f, sp.y + 0.5f, pb->tex_mode);
+            const F2 sp = sample_coord_point(H, rx, ry);
+            const float src_pix = tex_linear(src, W, Hh, sp.x, sp.y, pb->tex_mode);
             sum_ref += ref_pix;
             sum_ref_ref = std::fmaf(ref_pix, ref_pix, sum_ref_ref);
             sum_src += src_pix;
@@ -430,8 +458,8 @@ inline float patch_ncc_quadrants(const orc_problem *pb, const float *H, int src_
     const float kMinVar = 1e-5f;
     if (var_ref < kMinVar || var_src < kMinVar) return 2.0f;
     const float covar = std::fmaf(-mean_ref, mean_src, e_rs);
-    const float denom = std::sqrt(var_ref * var_src);
-    const float v = std::fmaf(-covar, 1.0f / denom, 1.0f);
+    const float denom = mufu_sqrt(var_ref * var_src);
+    const float v = std::fmaf(-covar, mufu_rcp(denom), 1.0f);
     return std::fmax(0.0f, std::fmin(2.0f, v));
 }
 
@@ -447,20 +475,22 @@ float ncc_old(orc_problem *pb, I2 p, int src_idx, F4 plane) {
     if (pb->sa_mask) {
         /* "const int center = pt.y * src_camera.width + pt.x; if (sa_mask[center] == 0)" (APD.cu:619-621): the REFERENCE
          * view's label map indexed by the projected point, float arithmetic (one FFMA under -fmad) truncated to int */
-        long long c = (long long)std::fmaf(pt.y, (float)sc.width, pt.x);
-        const long long last = (long long)pb->width * pb->height - 1;
-        if (c > last) c = last; /* the float can round up to W*H: one past the end in the reference */
-        if (pb->sa_mask[c] != 0) return patch_ncc_quadrants(pb, H, src_idx, p.x, p.y);
+        const long long c = (long long)std::fmaf(pt.y, (float)sc.width, pt.x);
+        /* for points in the last source row the index of FLOAT coordinates runs past the map (up to W - 1 elements): the
+         * reference reads past its buffer there (undefined); defined here as label 0 -> branch A, which is what the reference
+         * binary returned for every such tuple of tests/golden/ref_costs_sa.npz */
+        if (c < (long long)pb->width * pb->height && pb->sa_mask[c] != 0) return patch_ncc_quadrants(pb, H, src_idx, p.x, p.y);
     }
     return patch_ncc(pb, H, src_idx, p.x, p.y, pb->params.strong_radius, pb->params.strong_increment);
 }
 
-inline void softmax(float *c, int n) { /* APD.cu:431-446 */
+inline void softmax(float *c, int n) { /* APD.cu:431-446; exp(x) = EX2(x * log2e), "/ sum" = "* RCP(sum)" as built */
     float mx = -1e10f;
     for (int i = 0; i < n; i++) if (c[i] > mx) mx = c[i];
     float sum = 0.0f;
-    for (int i = 0; i < n; i++) { c[i] = std::exp(c[i] - mx); sum += c[i]; }
-    for (int i = 0; i < n; i++) c[i] /= sum;
+    for (int i = 0; i < n; i++) { c[i] = mufu_ex2((c[i] - mx) * 1.4426950216293334961f); sum += c[i]; }
+    const float rs = mufu_rcp(sum);
+    for (int i = 0; i < n; i++) c[i] *= rs;
 }
 
 /* APD.cu:448-593 */
@@ -510,7 +540,7 @@ float ncc_new(orc_problem *pb, I2 p, int src_idx, F4 plane) {
         for (int i = 0; i < strong_num; ++i) wts[i] = strong_costs[i];
         softmax(wts, strong_num);
         float strong_cost = 0.0f;
-        for (int i = 0; i < strong_num; ++i) strong_cost += wts[i] * strong_costs[i];
+        for (int i = 0; i < strong_num; ++i) strong_cost = std::fmaf(wts[i], strong_costs[i], strong_cost);
         strong_cost = ORC_MIN(strong_cost, cost_max);
         cost = (float)(0.25 * (double)center_cost + 0.75 * (double)strong_cost); /* double literals, APD.cu:586 */
     }
@@ -519,26 +549,34 @@ float ncc_new(orc_problem *pb, I2 p, int src_idx, F4 plane) {
 
 inline F3 point_on_world(float x, float y, float depth, const orc_camera &cam) { /* APD.cu:831-851 */
     F3 X, T;
-    X.x = depth * (x - cam.K[2]) / cam.K[0];
-    X.y = depth * (y - cam.K[5]) / cam.K[4];
+    X.x = ((x - cam.K[2]) * depth) * mufu_rcp(cam.K[0]); /* as built */
+    X.y = ((y - cam.K[5]) * depth) * mufu_rcp(cam.K[4]);
     X.z = depth;
-    T.x = cam.R[0] * X.x + cam.R[3] * X.y + cam.R[6] * X.z;
-    T.y = cam.R[1] * X.x + cam.R[4] * X.y + cam.R[7] * X.z;
-    T.z = cam.R[2] * X.x + cam.R[5] * X.y + cam.R[8] * X.z;
+    T.x = dot3_ref(cam.R[0], X.x, cam.R[3], X.y, cam.R[6], X.z);
+    T.y = dot3_ref(cam.R[1], X.x, cam.R[4], X.y, cam.R[7], X.z);
+    T.z = dot3_ref(cam.R[2], X.x, cam.R[5], X.y, cam.R[8], X.z);
     X.x = T.x + cam.c[0];
     X.y = T.y + cam.c[1];
     X.z = T.z + cam.c[2];
     return X;
 }
 
-inline void project_on_camera(F3 P, const orc_camera &cam, F2 &pt, float &depth) { /* APD.cu:853-863 */
+/* APD.cu:853-863 as built; num = the two numerators, rdepth = RCP(depth) (callers contract "p - num / depth" into one FFMA) */
+inline void project_on_camera_parts(F3 P, const orc_camera &cam, F2 &num, float &depth, float &rdepth) {
     F3 t;
-    t.x = cam.R[0] * P.x + cam.R[1] * P.y + cam.R[2] * P.z + cam.t[0];
-    t.y = cam.R[3] * P.x + cam.R[4] * P.y + cam.R[5] * P.z + cam.t[1];
-    t.z = cam.R[6] * P.x + cam.R[7] * P.y + cam.R[8] * P.z + cam.t[2];
-    depth = cam.K[6] * t.x + cam.K[7] * t.y + cam.K[8] * t.z;
-    pt.x = (cam.K[0] * t.x + cam.K[1] * t.y + cam.K[2] * t.z) / depth;
-    pt.y = (cam.K[3] * t.x + cam.K[4] * t.y + cam.K[5] * t.z) / depth;
+    t.x = dot3_ref(cam.R[0], P.x, cam.R[1], P.y, cam.R[2], P.z) + cam.t[0];
+    t.y = dot3_ref(cam.R[3], P.x, cam.R[4], P.y, cam.R[5], P.z) + cam.t[1];
+    t.z = dot3_ref(cam.R[6], P.x, cam.R[7], P.y, cam.R[8], P.z) + cam.t[2];
+    depth = dot3_ref(cam.K[6], t.x, cam.K[7], t.y, cam.K[8], t.z);
+    rdepth = mufu_rcp(depth);
+    num.x = dot3_ref(cam.K[0], t.x, cam.K[1], t.y, cam.K[2], t.z);
+    num.y = dot3_ref(cam.K[3], t.x, cam.K[4], t.y, cam.K[5], t.z);
+}
+inline void project_on_camera(F3 P, const orc_camera &cam, F2 &pt, float &depth) {
+    F2 num; float rd;
+    project_on_camera_parts(P, cam, num, depth, rd);
+    pt.x = num.x * rd;
+    pt.y = num.y * rd;
 }
 
 /* nearest-texel depth fetch "(int)x + 0.5f" through a clamped linear texture (APD.cu:885, 2319) */
@@ -561,10 +599,12 @@ float geom_cost(orc_problem *pb, I2 p, int src_idx, F4 plane) {
     const float src_depth = depth_fetch(pb, src_idx, sp);
     if (src_depth == 0.0f) return max_cost;
     const F3 s3 = point_on_world(sp.x, sp.y, src_depth, sc);
-    F2 bp; float rd;
-    project_on_camera(s3, rc, bp, rd);
-    const float dc = p.x - bp.x, dr = p.y - bp.y;
-    const float cc = std::sqrt(dc * dc + dr * dr);
+    F2 bn; float rd, rrd;
+    project_on_camera_parts(s3, rc, bn, rd, rrd);
+    /* as built: diff = FFMA(-num, RCP(depth), p); cost = min(3, SQRT(FFMA(dc, dc, dr * dr))) */
+    const float dc = std::fmaf(-bn.x, rrd, (float)p.x), dr = std::fmaf(-bn.y, rrd, (float)p.y);
+    const float drr = dr * dr;
+    const float cc = mufu_sqrt(std::fmaf(dc, dc, drr));
     return std::fmin(max_cost, cc);
 }
 
@@ -999,8 +1039,7 @@ void median_pixel(orc_problem *pb, I2 p) {
 
 inline float baseline_len(const orc_camera &a, const orc_camera &b) { /* APD.cu:2142-2147 */
     const float d0 = a.c[0] - b.c[0], d1 = a.c[1] - b.c[1], d2 = a.c[2] - b.c[2];
-    const float t = d0 * d0 + d1 * d1 + d2 * d2;
-    return std::sqrt(t);
+    return mufu_sqrt(dot3_ref(d0, d0, d1, d1, d2, d2)); /* as built: FFMA(d2, d2, FFMA(d0, d0, d1 * d1)), MUFU.SQRT */
 }
 
 bool point_in_triangle(S2 A, S2 B, S2 C, I2 P) { /* APD.cu:122-143 */
@@ -1193,12 +1232,15 @@ void orc_depth_to_weak(orc_problem *pb, float *curve) {
             valid_src++;
         }
         if (valid_src == 0) { pb->weak_info[center] = ORC_UNKNOWN; continue; }
-        base_line /= valid_src;
-        const float disp = cams[0].K[0] * base_line / origin_depth;
+        /* as built (APD.cu:2155-2165): base_line * RCP(valid); fb = base_line * K0; disp = fb * RCP(depth); p_depth = fb * RCP(disp + pd) */
+        base_line = mufu_rcp((float)valid_src) * base_line;
+        const float fb = base_line * cams[0].K[0];
+        const float disp = fb * mufu_rcp(origin_depth);
+        const float rwn = mufu_rcp(weight_normal);
         const int radius = 30, n = 2 * radius + 1;
         float pc[61];
         for (int pd = -radius; pd <= radius; ++pd) {
-            const float p_depth = cams[0].K[0] * base_line / (disp + pd);
+            const float p_depth = fb * mufu_rcp(disp + (float)pd);
             if (p_depth < prm.depth_min || p_depth > prm.depth_max) { pc[pd + radius] = 2.0f; continue; }
             F4 tp = opl;
             tp.w = distance_to_origin(cams[0], pt, p_depth, tp);
@@ -1207,11 +1249,11 @@ void orc_depth_to_weak(orc_problem *pb, float *curve) {
                 float tc = 0.0f;
                 if (is_set(sel, s - 1)) {
                     tc += ncc_old(pb, pt, s, tp);
-                    if (prm.geom_consistency) tc += prm.geom_factor * geom_cost(pb, pt, s, tp);
-                    p_cost += (tc * vw[s - 1]);
+                    if (prm.geom_consistency) tc = std::fmaf(prm.geom_factor, geom_cost(pb, pt, s, tp), tc); /* FFMA as built */
+                    p_cost = std::fmaf((float)vw[s - 1], tc, p_cost);
                 }
             }
-            p_cost /= weight_normal;
+            p_cost = p_cost * rwn;
             pc[pd + radius] = ORC_MIN(2.0f, p_cost);
         }
         if (curve) for (int i = 0; i < n; ++i) curve[center * n + i] = pc[i];
@@ -1256,12 +1298,13 @@ void orc_confidence(orc_problem *pb) {
             if (src_depth <= 0.0f) continue;
             nc += 1;
             const F3 s3 = point_on_world(sp.x, sp.y, src_depth, sc);
-            F2 bp; float rd;
-            project_on_camera(s3, rc, bp, rd);
-            const float dc = x - bp.x, dr = y - bp.y;
-            const float pd = std::sqrt(dc * dc + dr * dr);
+            F2 bn; float rd, rrd;
+            project_on_camera_parts(s3, rc, bn, rd, rrd);
+            const float dc = std::fmaf(-bn.x, rrd, (float)x), dr = std::fmaf(-bn.y, rrd, (float)y); /* as built */
+            const float drr = dr * dr;
+            const float pd = mufu_sqrt(std::fmaf(dc, dc, drr));
             if (pd <= 2.0f) nc += 2;
-            const float rdd = std::fabs(ref_depth - rd) / ref_depth;
+            const float rdd = std::fabs(ref_depth - rd) * mufu_rcp(ref_depth);
             if (rdd <= 0.02f) nc += 2;
         }
         if (nc > 255) nc = 255;
@@ -1289,32 +1332,34 @@ void orc_local_refine(orc_problem *pb) {
             F4 tp = opl;
             tp.w = distance_to_origin(cams[0], pt, origin_depth, tp);
             float tc = ncc_old(pb, pt, s, tp);
-            if (prm.geom_consistency) tc += prm.geom_factor * geom_cost(pb, pt, s, tp);
-            cost_now += (tc * vw[s - 1]);
+            if (prm.geom_consistency) tc = std::fmaf(prm.geom_factor, geom_cost(pb, pt, s, tp), tc); /* FFMA as built */
+            cost_now = std::fmaf((float)vw[s - 1], tc, cost_now);
             weight_normal += vw[s - 1];
             base_line += baseline_len(cams[0], cams[s]);
             valid_src++;
         }
         if (weight_normal == 0 || valid_src == 0) continue;
-        cost_now /= weight_normal;
-        base_line /= valid_src;
-        const float disp = cams[0].K[0] * base_line / origin_depth;
+        const float rwn = mufu_rcp(weight_normal);
+        base_line = mufu_rcp((float)valid_src) * base_line; /* as built, APD.cu:2399-2407 */
+        const float fb = base_line * cams[0].K[0];
+        const float disp = fb * mufu_rcp(origin_depth);
         const int radius = 5;
         float min_cost = 2.0f, best_depth = origin_depth;
         for (int pd = -radius; pd <= radius; ++pd) {
-            const float p_depth = cams[0].K[0] * base_line / (disp + pd);
+            const float p_depth = fb * mufu_rcp(disp + (float)pd);
             if (p_depth < prm.depth_min || p_depth > prm.depth_max) continue;
             F4 tp = opl;
             tp.w = distance_to_origin(cams[0], pt, p_depth, tp);
             float tc = 0.0f;
             for (int s = 1; s < prm.num_images; ++s) if (is_set(sel, s - 1)) {
-                tc += (ncc_old(pb, pt, s, tp) * vw[s - 1]);
-                if (prm.geom_consistency) tc += (prm.geom_factor * geom_cost(pb, pt, s, tp) * vw[s - 1]);
+                tc = std::fmaf((float)vw[s - 1], ncc_old(pb, pt, s, tp), tc); /* FFMA as built, APD.cu:2417-2419 */
+                if (prm.geom_consistency) { const float g = prm.geom_factor * geom_cost(pb, pt, s, tp); tc = std::fmaf((float)vw[s - 1], g, tc); }
             }
-            tc /= weight_normal;
+            tc = tc * rwn;
             if (tc < min_cost) { min_cost = tc; best_depth = p_depth; }
         }
-        if ((double)(cost_now - min_cost) > 0.1) pb->planes[4 * center + 3] = best_depth;
+        /* "cost_now /= weight_normal; ... cost_now - min_cost > 0.1" is ONE FFMA in the reference build, compared in double */
+        if ((double)std::fmaf(rwn, cost_now, -min_cost) > 0.1) pb->planes[4 * center + 3] = best_depth;
     }
 }
 
@@ -1559,6 +1604,16 @@ void orc_run_pass(orc_problem *pb) {
  * fusion (APD.cpp:844-910, 962-1227)
  * ============================================================================================== */
 namespace {
+/* ProjectCamera of the HOST code, APD.cpp:891-900: plain IEEE fp32, no contraction (g++ build of the reference) */
+void f_project_on_camera(F3 P, const orc_camera &cam, F2 &pt, float &depth) {
+    F3 t;
+    t.x = cam.R[0] * P.x + cam.R[1] * P.y + cam.R[2] * P.z + cam.t[0];
+    t.y = cam.R[3] * P.x + cam.R[4] * P.y + cam.R[5] * P.z + cam.t[1];
+    t.z = cam.R[6] * P.x + cam.R[7] * P.y + cam.R[8] * P.z + cam.t[2];
+    depth = cam.K[6] * t.x + cam.K[7] * t.y + cam.K[8] * t.z;
+    pt.x = (cam.K[0] * t.x + cam.K[1] * t.y + cam.K[2] * t.z) / depth;
+    pt.y = (cam.K[3] * t.x + cam.K[4] * t.y + cam.K[5] * t.z) / depth;
+}
 F3 f_point_on_world(int x, int y, float depth, const orc_camera &cam) { /* APD.cpp:866-889 */
     F3 X, T;
     X.x = depth * (x - cam.K[2]) / cam.K[0];
@@ -1616,7 +1671,7 @@ void orc_weak_vis_filter(const orc_fusion_input *in, uint8_t *skip) {
                 ang = (float)((double)(ang * 180.0f) / kPiD);
                 if (ang > 80.0f) continue;
                 F2 pt; float pd;
-                project_on_camera(X, sc, pt, pd);
+                f_project_on_camera(X, sc, pt, pd);
                 if (pd <= 0.0f) continue;
                 const int sr = (int)(pt.y + 0.5f), scn = (int)(pt.x + 0.5f);
                 if (scn >= 0 && scn < W && sr >= 0 && sr < H) {
@@ -1659,7 +1714,7 @@ int64_t orc_fuse(const orc_fusion_input *in, const uint8_t *skip, float *pts, fl
             for (int j = 0; j < num_ngb; ++j) {
                 const int s = in->src_ids[nb0 + j];
                 F2 pt; float pd;
-                project_on_camera(X, in->cameras[s], pt, pd);
+                f_project_on_camera(X, in->cameras[s], pt, pd);
                 const int sr = (int)(pt.y + 0.5f), sc = (int)(pt.x + 0.5f);
                 if (sc >= 0 && sc < W && sr >= 0 && sr < H) {
                     const size_t spx = (size_t)sr * W + sc;
@@ -1669,7 +1724,7 @@ int64_t orc_fuse(const orc_fusion_input *in, const uint8_t *skip, float *pts, fl
                     const float *sn = &in->normals[(s * P + spx) * 3];
                     const F3 tX = f_point_on_world(sc, sr, sd, in->cameras[s]);
                     F2 tp;
-                    project_on_camera(tX, in->cameras[ref], tp, pd);
+                    f_project_on_camera(tX, in->cameras[ref], tp, pd);
                     const float re = (float)std::sqrt(std::pow((double)(c - tp.x), 2) + std::pow((double)(r - tp.y), 2));
                     const float rdd = std::fabs(pd - ref_depth) / ref_depth;
                     const float ang = f_angle(rn, sn);
@@ -1736,7 +1791,7 @@ extern "C" int64_t orc_fuse_tat(const orc_fusion_input *in, const uint8_t *skip,
             for (int j = 0; j < num_ngb; ++j) {
                 const int s = in->src_ids[nb0 + j];
                 F2 pt; float pd;
-                project_on_camera(X, in->cameras[s], pt, pd);
+                f_project_on_camera(X, in->cameras[s], pt, pd);
                 const int sr = (int)(pt.y + 0.5f), sc = (int)(pt.x + 0.5f);
                 if (sc >= 0 && sc < W && sr >= 0 && sr < H) {
                     const size_t spx = (size_t)sr * W + sc;
@@ -1746,7 +1801,7 @@ extern "C" int64_t orc_fuse_tat(const orc_fusion_input *in, const uint8_t *skip,
                     const float *sn = &in->normals[(s * P + spx) * 3];
                     const F3 tX = f_point_on_world(sc, sr, sd, in->cameras[s]);
                     F2 tp;
-                    project_on_camera(tX, in->cameras[ref], tp, pd);
+                    f_project_on_camera(tX, in->cameras[ref], tp, pd);
                     diff[j].dist = (float)std::sqrt(std::pow((double)(c - tp.x), 2) + std::pow((double)(r - tp.y), 2));
                     diff[j].depth = std::fabs(pd - ref_depth) / ref_depth;
                     diff[j].angle = f_angle(rn, sn);

@@ -22,6 +22,7 @@ def lib():
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_run_pass.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_double)]
+        L.ref_run_stages.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 14 + [C.c_int, C.c_void_p, C.c_void_p]
         L.ref_set_sa_mask.argtypes = [C.c_void_p, C.c_longlong]
         L.ref_set_sa_mask.restype = None
         assert L.ref_sizeof_camera() == 120
@@ -104,3 +105,43 @@ def run_pass(images, cameras, params, planes=None, weak=None, conf=None, depths=
     if rc != 0:
         raise RuntimeError("ref_run_pass failed: %d" % rc)
     return planes, weak, conf, ms.value
+
+
+STAGES = {"nearest_strong": 0, "neighbour_update": 1, "init": 2, "depth_normal": 3, "median_black": 4, "median_red": 5,
+          "depth_to_weak": 6, "confidence": 7, "local_refine": 8}
+
+
+def run_stages(images, cameras, params, stages, state, depths=None, anchors=None, want_curve=False):
+    """Launch the reference's own RNG-free kernels (names of STAGES, in order) on `state` = dict with any of planes [h,w,4],
+    costs [h,w], selected_views [h,w] u32, view_weight [h,w,32] u8, weak_info / confidence / weak_reliable [h,w] u8,
+    nearest_strong [h,w,2] i16.  Returns a dict of the same arrays after the kernels (+ "curve" [h,w,61])."""
+    h, w = images[0].shape
+    n = len(images)
+    pi, keep_i = _ptr_array(images)
+    pd, keep_d = _ptr_array(depths)
+    ip, fp = _params(params)
+    ip[1] = n
+    spec = (("planes", np.float32, (h, w, 4)), ("costs", np.float32, (h, w)), ("selected_views", np.uint32, (h, w)),
+            ("view_weight", np.uint8, (h, w, 32)), ("weak_info", np.uint8, (h, w)), ("confidence", np.uint8, (h, w)),
+            ("weak_reliable", np.uint8, (h, w)), ("nearest_strong", np.int16, (h, w, 2)))
+    out = {}
+    for name, dt, shape in spec:
+        if name in state and state[name] is not None:
+            out[name] = np.ascontiguousarray(state[name], dt).reshape(shape).copy()
+        elif name == "planes":
+            out[name] = np.zeros(shape, dt)
+        else:
+            out[name] = None
+    anc = None if anchors is None else np.ascontiguousarray(anchors, np.int16)
+    st = np.array([STAGES[s] for s in stages], np.int32)
+    curve = np.zeros((h, w, 61), np.float32) if want_curve else None
+    cams = _cams(cameras)
+    rc = lib().ref_run_stages(w, h, n, C.cast(pi, C.c_void_p), C.cast(pd, C.c_void_p) if pd else None, C.cast(cams, C.c_void_p),
+                              _p(ip), _p(fp), _p(out["planes"]), _p(out["costs"]), _p(out["selected_views"]), _p(out["view_weight"]),
+                              _p(out["weak_info"]), _p(out["confidence"]), _p(out["weak_reliable"]), _p(out["nearest_strong"]), _p(anc),
+                              len(st), _p(st), _p(curve))
+    if rc != 0:
+        raise RuntimeError("ref_run_stages failed: %d" % rc)
+    if want_curve:
+        out["curve"] = curve
+    return out

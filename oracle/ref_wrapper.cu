@@ -8,6 +8,11 @@
 //   * ref_run_pass   : builds the reference APD object's device state from caller arrays and runs the reference's own
 //                      APD::RunPatchMatch() -- the GPU baseline of bench.py --impl reference and of the whole-pass
 //                      parity test.
+//   * ref_run_stages : launches the reference's own RNG-FREE kernels (FindNearestStrongPoint, NeigbourUpdate,
+//                      RandomInitialization in a REFINE state, GetDepthandNormal, Black/RedPixelFilterStrong, DepthToWeak,
+//                      ConfidenceCompute, LocalRefine) on injected device state with the launch geometry of
+//                      APD::RunPatchMatch (APD.cu:2664-2683) and returns the state -- the bit-for-bit pin of the
+//                      product's stage kernels.
 // The only deviation from the reference binary: clock64() in InitRandomStates (APD.cu:916) reads a settable seed so that
 // runs are repeatable (SURVEY.md 7.1 step 0 allows exactly this patch; it is done with a macro, not an edit).
 // The output lives in oracle/_ref/ (git-ignored) and only runs on the GPU box.
@@ -127,9 +132,13 @@ void build_state(RefState &s, int w, int h, int n, const float *const *images, c
     if (weak) cudaMemcpy(s.weak, weak, P, cudaMemcpyHostToDevice); else cudaMemset(s.weak, STRONG, P);
     cudaMalloc(&s.conf, P);
     if (conf) cudaMemcpy(s.conf, conf, P, cudaMemcpyHostToDevice); else cudaMemset(s.conf, 1, P);
-    cudaMalloc(&s.sa, P);
+    // ComputeBilateralNCCOld indexes sa_mask with "pt.y * width + pt.x" of FLOAT coordinates (APD.cu:619-621): for points in the
+    // last source row the index runs up to width - 1 elements past the map.  The reference reads whatever follows its buffer
+    // there; this harness makes that read defined by following the map with zeros (= "no segment", branch A).
+    cudaMalloc(&s.sa, P + (size_t)w + 64);
+    cudaMemset(s.sa, 0, P + (size_t)w + 64);
     if (g_sa_mask.size() == P) cudaMemcpy(s.sa, g_sa_mask.data(), P, cudaMemcpyHostToDevice);  // sa_masks/<id>.bin, APD.cpp:641-649
-    else cudaMemset(s.sa, 0, P);  // SAM off: sa_mask_host = zeros (APD.cpp:613)
+    // else SAM off: sa_mask_host = zeros (APD.cpp:613)
     cudaMalloc(&s.fit, P * sizeof(float4));
     cudaMemset(s.fit, 0, P * sizeof(float4));
     cudaMalloc(&s.reliable, P);
@@ -257,6 +266,63 @@ int ref_run_pass(int w, int h, int n_images, const float *const *images, const f
     if (weak) memcpy(weak, apd.weak_info_host.ptr<uchar>(0), P);
     if (conf && (prm.geom_consistency || prm.use_APD)) memcpy(conf, apd.confidence_host.ptr<uchar>(0), P);
     free_state(s);
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
+// The reference's own kernels, one at a time, on caller-supplied state (all arrays in / out, host pointers, any may be null
+// except planes):  planes float4[P], costs float[P], sel uint32[P], vw uchar[P][32], weak / conf / reliable uchar[P],
+// nearest short2[P].  stages: 0 FindNearestStrongPoint, 1 NeigbourUpdate, 2 RandomInitialization (params.state must not be
+// FIRST_INIT: that branch draws random planes), 3 GetDepthandNormal, 4 BlackPixelFilterStrong, 5 RedPixelFilterStrong,
+// 6 DepthToWeak, 7 ConfidenceCompute, 8 LocalRefine.  curve: float[P][61] out (DepthToWeak's reliable curve) or null.
+int ref_run_stages(int w, int h, int n_images, const float *const *images, const float *const *depths, const void *cams,
+                   const int *iparams, const float *fparams, float *planes, float *costs, unsigned *sel, unsigned char *vw,
+                   unsigned char *weak, unsigned char *conf, unsigned char *reliable, short *nearest, const short *anchors_dense,
+                   int n_stages, const int *stages, float *curve) {
+    const size_t P = (size_t)w * h;
+    PatchMatchParams prm = to_ref_params(iparams, fparams);
+    RefState s;
+    build_state(s, w, h, n_images, images, depths, (const Camera *)cams, &prm, planes, weak, conf, anchors_dense);
+    if (costs) cudaMemcpy(s.costs, costs, P * sizeof(float), cudaMemcpyHostToDevice);
+    if (sel) cudaMemcpy(s.sel, sel, P * sizeof(unsigned), cudaMemcpyHostToDevice);
+    if (vw) cudaMemcpy(s.vw, vw, P * MAX_IMAGES, cudaMemcpyHostToDevice);
+    if (reliable) cudaMemcpy(s.reliable, reliable, P, cudaMemcpyHostToDevice);
+    if (nearest) cudaMemcpy(s.nearest, nearest, P * sizeof(short2), cudaMemcpyHostToDevice);
+    float *d_curve = nullptr;
+    if (curve) { cudaMalloc(&d_curve, P * RELIABLE_CURVE_SAMPLE_NUM * sizeof(float)); cudaMemset(d_curve, 0, P * RELIABLE_CURVE_SAMPLE_NUM * sizeof(float)); }
+    // launch geometry of APD::RunPatchMatch, APD.cu:2664-2683
+    const int BLOCK_W = 32, BLOCK_H = BLOCK_W / 2;
+    const dim3 grid_full((w + 15) / 16, (h + 15) / 16, 1), block_full(16, 16, 1);
+    const dim3 grid_half((w + BLOCK_W - 1) / BLOCK_W, ((h / 2) + BLOCK_H - 1) / BLOCK_H, 1), block_half(BLOCK_W, BLOCK_H, 1);
+    int bad = 0;
+    for (int i = 0; i < n_stages; ++i) {
+        switch (stages[i]) {
+            case 0: FindNearestStrongPoint<<<grid_full, block_full>>>(s.helper); break;
+            case 1: NeigbourUpdate<<<grid_full, block_full>>>(s.helper); break;
+            case 2:
+                if (prm.state == FIRST_INIT) { bad = 1; break; }
+                RandomInitialization<<<grid_full, block_full>>>(s.helper);
+                break;
+            case 3: GetDepthandNormal<<<grid_full, block_full>>>(s.helper); break;
+            case 4: BlackPixelFilterStrong<<<grid_half, block_half>>>(s.helper); break;
+            case 5: RedPixelFilterStrong<<<grid_half, block_half>>>(s.helper); break;
+            case 6: DepthToWeak<<<grid_full, block_full>>>(s.helper, d_curve); break;
+            case 7: ConfidenceCompute<<<grid_full, block_full>>>(s.helper); break;
+            case 8: LocalRefine<<<grid_full, block_full>>>(s.helper); break;
+            default: bad = 1;
+        }
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(planes, s.planes, P * sizeof(float4), cudaMemcpyDeviceToHost);
+    if (costs) cudaMemcpy(costs, s.costs, P * sizeof(float), cudaMemcpyDeviceToHost);
+    if (sel) cudaMemcpy(sel, s.sel, P * sizeof(unsigned), cudaMemcpyDeviceToHost);
+    if (vw) cudaMemcpy(vw, s.vw, P * MAX_IMAGES, cudaMemcpyDeviceToHost);
+    if (weak) cudaMemcpy(weak, s.weak, P, cudaMemcpyDeviceToHost);
+    if (conf) cudaMemcpy(conf, s.conf, P, cudaMemcpyDeviceToHost);
+    if (reliable) cudaMemcpy(reliable, s.reliable, P, cudaMemcpyDeviceToHost);
+    if (nearest) cudaMemcpy(nearest, s.nearest, P * sizeof(short2), cudaMemcpyDeviceToHost);
+    if (curve) { cudaMemcpy(curve, d_curve, P * RELIABLE_CURVE_SAMPLE_NUM * sizeof(float), cudaMemcpyDeviceToHost); cudaFree(d_curve); }
+    free_state(s);
+    if (bad) return -1000;
     return e == cudaSuccess ? 0 : -(int)e;
 }
 

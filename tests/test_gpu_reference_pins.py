@@ -1,0 +1,306 @@
+"""Product vs the REFERENCE BINARY, bit for bit (oracle/_ref/libapd_ref.so = /root/reference/APD.cu compiled unmodified).
+
+North star: per-hypothesis costs within 1e-4 absolute of the reference's formulation on identical inputs; integer / indexing
+work bit-exact.  The product's arithmetic follows the reference BUILD operation for operation (apde_device.cuh, "ARITHMETIC
+CONTRACT"), so the bar here is stricter than the north star's:
+
+  * costs (NCC-Old, NCC-New, geometric): 100 % of tuples within 1e-4, and bit-equal on all but a measured handful;
+  * the committed golden vectors of the reference (tests/golden/ref_costs*.npz) likewise;
+  * the RNG-free reference kernels (RandomInitialization in a REFINE state = ComputeMultiViewInitialCostandSelectedViews,
+    GetDepthandNormal, Black/RedPixelFilterStrong, DepthToWeak, ConfidenceCompute, LocalRefine, FindNearestStrongPoint,
+    NeigbourUpdate) launched on the SAME injected state as the product's stages: integer outputs np.array_equal, depths and
+    costs bit-equal.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, pull_state, push_state, ref_params, to_apde_params
+
+pytestmark = pytest.mark.gpu
+SEED = 4711
+
+
+def _ref():
+    from oracle import ref_binding as ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libapd_ref.so not built (needs /root/reference at build time)")
+    return ref
+
+
+def _inputs(ctx):
+    """working-resolution inputs of the active product problem, as the reference wrapper takes them"""
+    from apde_mvs_b200.binding import FIELD
+    w, h, n = ctx.problem_dims()
+    cams, prm = ctx.problem_cameras()
+    imgs = [ctx.problem_image(i) for i in range(n)]
+    depths = None
+    if prm.geom_consistency or prm.use_APD:
+        d = ctx.problem_get(FIELD.SRC_DEPTH)
+        depths = [d[i] for i in range(n)]
+    return imgs, [cams[i] for i in range(n)], prm, depths
+
+
+def _report(name, got, want):
+    d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    eq = (got == want) | (np.isnan(got) & np.isnan(want))
+    print("%s: n=%d  bit-equal %.6f  max |d| %.3g  frac<=1e-4 %.6f" % (name, got.size, eq.mean(), np.nanmax(d), (d <= 1e-4).mean()))
+    return d, eq
+
+
+@pytest.fixture(scope="module")
+def office_state(ctx):
+    """6 views 256x192, 4 sources, 35 % weak-texture blobs, two pyramid rounds: state after round 0 + the photometric pass and
+    one geometric pass of round 1 (use_APD on, WEAK pixels present, depth / confidence maps of every view)"""
+    from apde_mvs_b200.binding import default_schedule
+    from apde_mvs_b200.scene import make_office_scene
+    scene = make_office_scene(256, 192, num_views=6, num_src=4, seed=3, weak=0.35, with_color=True)
+    ctx.load_scene(scene)
+    sched = default_schedule()
+    sched.rounds, sched.seed = 2, 5
+    for pidx in range(0, 6):
+        ctx.run_schedule_pass(sched, pidx)
+    return scene, sched
+
+
+def _setup_geometric(ctx, sched, view=1, use_apd=1, pass_index=6):
+    p, _, _ = ctx.schedule_pass_params(sched, pass_index)
+    p.use_APD = use_apd
+    ctx.problem_setup(view, p, 1, SEED)
+    return p
+
+
+def test_costs_bit_equal_to_the_reference_binary(ctx, office_state):
+    """ComputeBilateralNCCOld / New, ComputeGeomConsistencyCost on identical (pixel, view, plane) tuples: product == reference"""
+    ref = _ref()
+    from apde_mvs_b200.binding import STAGE
+    scene, sched = office_state
+    _setup_geometric(ctx, sched)
+    ctx.problem_stage(STAGE.NEAREST_STRONG)
+    ctx.problem_stage(STAGE.GEN_ANCHORS)
+    ctx.problem_stage(STAGE.INIT)
+    st = pull_state(ctx)
+    imgs, cams, prm, depths = _inputs(ctx)
+    w, h, n = ctx.problem_dims()
+    rng = np.random.default_rng(11)
+    N = 30000
+    xs, ys, vs = rng.integers(0, w, N), rng.integers(0, h, N), rng.integers(1, n, N)
+    planes = st["planes"][ys, xs].copy()
+    k = N // 2  # half near the current estimate, half perturbed so that costs cover [0, 2]
+    planes[:k, 3] *= rng.uniform(0.9, 1.1, k).astype(np.float32)
+    planes[:k, :2] += rng.normal(0, 0.1, (k, 2)).astype(np.float32)
+    tuples = np.stack([xs, ys, vs], 1).astype(np.int32)
+    for mode, name in ((0, "NCC-Old"), (2, "geometric")):
+        got = ctx.eval_costs(tuples, planes, mode)
+        want = ref.eval_costs(imgs, cams, prm, tuples, planes, mode, depths=depths)
+        d, eq = _report("%s product vs reference binary" % name, got, want)
+        assert (d <= 1e-4).all(), "costs beyond 1e-4: %s" % (tuples[d > 1e-4][:10],)
+        assert eq.mean() >= 0.9999
+        assert len(np.unique(np.round(got, 3))) > 100  # not a degenerate comparison
+    # deformable NCC on the WEAK pixels, with their anchors and the anchors' selected views
+    wy, wx = np.nonzero(st["weak_info"] == 0)
+    assert len(wx) > 500
+    pick = rng.choice(len(wx), min(12000, len(wx)), replace=False)
+    t2 = np.stack([wx[pick], wy[pick], rng.integers(1, n, len(pick))], 1).astype(np.int32)
+    pl2 = st["planes"][wy[pick], wx[pick]].copy()
+    pl2[: len(pick) // 2, 3] *= rng.uniform(0.95, 1.05, len(pick) // 2).astype(np.float32)
+    got = ctx.eval_costs(t2, pl2, 1)
+    want = ref.eval_costs(imgs, cams, prm, t2, pl2, 1, depths=depths, weak=st["weak_info"], selected_views=st["selected_views"],
+                          anchors=st["anchors"])
+    d, eq = _report("NCC-New product vs reference binary", got, want)
+    assert (d <= 1e-4).all()
+    assert eq.mean() >= 0.9999
+    ctx.problem_finish()
+
+
+def _golden_scene(ctx):
+    """the scene tests/golden/make_ref_golden.py used: the product gets it through its own loader"""
+    from apde_mvs_b200.scene import make_office_scene
+    scene = make_office_scene(128, 96, num_views=5, num_src=4, seed=9, weak=0.3)
+    ctx.load_scene(scene)
+    return scene
+
+
+def test_product_matches_the_committed_reference_vectors(ctx):
+    """the golden (pixel, view, plane) -> cost vectors of the reference binary (tests/golden/ref_costs.npz): 100 % within 1e-4"""
+    from apde_mvs_b200.binding import FIELD
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ref_costs.npz"))
+    scene = _golden_scene(ctx)
+    V = len(scene.images)
+    for v in range(V):  # geometric cost: the golden run used the ground-truth depth maps as source depths
+        ctx.view_upload(v, depth=scene.gt_depth[v].astype(np.float32), normal=np.zeros(scene.gt_depth[v].shape + (3,), np.float32),
+                        weak=np.ones(scene.gt_depth[v].shape, np.uint8), conf=np.ones(scene.gt_depth[v].shape, np.uint8))
+    p = to_apde_params(ref_params(geom=1))
+    ctx.problem_setup(2, p, 1, SEED)
+    assert np.array_equal(np.stack([ctx.problem_image(i) for i in range(5)]), z["images"])
+    got = ctx.eval_costs(z["old_tuples"], z["old_planes"], 0)
+    d, eq = _report("golden NCC-Old", got, z["old_costs"])
+    assert (d <= 1e-4).all() and eq.mean() >= 0.9999
+    got = ctx.eval_costs(z["old_tuples"], z["old_planes"], 2)
+    d, eq = _report("golden geometric", got, z["geom_costs"])
+    assert (d <= 1e-4).all() and eq.mean() >= 0.9999
+    ctx.problem_finish()
+    # NCC-New: weak map, anchors and selected views of the golden run
+    ctx.view_upload(2, weak=z["new_weak"], conf=np.ones_like(z["new_weak"]))
+    p = to_apde_params(ref_params(use_apd=1))
+    ctx.problem_setup(2, p, 1, SEED)
+    ctx.problem_set(FIELD.ANCHORS, z["new_anchors"])
+    ctx.problem_set(FIELD.SELECTED_VIEWS, z["new_sel"])
+    got = ctx.eval_costs(z["new_tuples"], z["new_planes"], 1)
+    d, eq = _report("golden NCC-New", got, z["new_costs"])
+    assert (d <= 1e-4).all() and eq.mean() >= 0.9999
+    # ... and with a segment-label map (NCC-Old branch B, label tests of NCC-New)
+    zs = np.load(os.path.join(ROOT, "tests", "golden", "ref_costs_sa.npz"))
+    ctx.problem_finish()
+    ctx.view_set_sa_mask(2, zs["labels"])
+    ctx.problem_setup(2, p, 1, SEED)
+    ctx.problem_set(FIELD.ANCHORS, z["new_anchors"])
+    ctx.problem_set(FIELD.SELECTED_VIEWS, z["new_sel"])
+    got = ctx.eval_costs(z["new_tuples"], z["new_planes"], 1)
+    d, eq = _report("golden NCC-New + labels", got, zs["new_costs"])
+    assert (d <= 1e-4).all() and eq.mean() >= 0.9999
+    got = ctx.eval_costs(z["old_tuples"], z["old_planes"], 0)
+    d, eq = _report("golden NCC-Old + labels", got, zs["old_costs"])
+    assert (d <= 1e-4).all() and eq.mean() >= 0.9999
+    ctx.problem_finish()
+    ctx.view_set_sa_mask(2, None)
+
+
+def _ref_state(st):
+    return {k: st[k] for k in ("planes", "costs", "selected_views", "view_weight", "weak_info", "confidence", "weak_reliable",
+                                "nearest_strong")}
+
+
+def test_rng_free_kernels_equal_the_reference_kernels(ctx, office_state):
+    """every reference kernel that draws no random number, launched on the product's own state: outputs must be EQUAL"""
+    ref = _ref()
+    from apde_mvs_b200.binding import FIELD, STAGE
+    scene, sched = office_state
+    for use_apd in (0, 1):
+        prm0 = _setup_geometric(ctx, sched, view=1, use_apd=use_apd)
+        imgs, cams, prm, depths = _inputs(ctx)
+        tag = "use_APD=%d" % use_apd
+        if use_apd:
+            # K2 FindNearestStrongPoint: 201x201 brute force in the reference, ring search with tile pruning here
+            ctx.problem_stage(STAGE.NEAREST_STRONG)
+            st = pull_state(ctx)
+            r = ref.run_stages(imgs, cams, prm, ["nearest_strong"], _ref_state(st), depths=depths)
+            assert np.array_equal(st["nearest_strong"], r["nearest_strong"]), tag
+            ctx.problem_stage(STAGE.GEN_ANCHORS)  # (GenAnchors draws random numbers; NeigbourUpdate is fused into it)
+            st = pull_state(ctx)
+            # K4 NeigbourUpdate on the product's reliable flags: unreliable WEAK pixels become UNKNOWN -- already applied by the
+            # fused kernel, so the reference kernel must leave the product's map unchanged
+            r = ref.run_stages(imgs, cams, prm, ["neighbour_update"], _ref_state(st), depths=depths)
+            assert np.array_equal(st["weak_info"], r["weak_info"]), tag
+        # K5 RandomInitialization in a REFINE state == TransformNormal2RefCam + GetDistance2Origin +
+        # ComputeMultiViewInitialCostandSelectedViews: planes, costs and the top-k view masks
+        st0 = pull_state(ctx)
+        ctx.problem_stage(STAGE.INIT)
+        st = pull_state(ctx)
+        r = ref.run_stages(imgs, cams, prm, ["init"], _ref_state(st0), depths=depths, anchors=st0["anchors"] if use_apd else None)
+        strong = st0["weak_info"] != 0 if use_apd else np.ones(st0["weak_info"].shape, bool)
+        _, eqp = _report("%s init planes" % tag, st["planes"], r["planes"])
+        assert eqp.all(), tag
+        d, eq = _report("%s init costs (NCC-Old pixels)" % tag, st["costs"][strong], r["costs"][strong])
+        assert eq.all(), tag
+        assert np.array_equal(st["selected_views"][strong], r["selected_views"][strong]), tag
+        if use_apd and (~strong).any():
+            # WEAK pixels: the deformable cost reads selected_views of its anchors while the reference's kernel is still writing
+            # them (a data race, DESIGN.md "Determinism"); the product's two-phase order is one of the allowed outcomes
+            d, eq = _report("%s init costs (NCC-New pixels, racy in the reference)" % tag, st["costs"][~strong], r["costs"][~strong])
+            assert (d <= 1e-4).mean() >= 0.999
+        # three propagation iterations of the product give a realistic state for the tail kernels
+        for it in range(3):
+            ctx.problem_stage(STAGE.PROP_STRONG, it, 0)
+            ctx.problem_stage(STAGE.PROP_STRONG, it, 1)
+            if use_apd:
+                ctx.problem_stage(STAGE.RANSAC_FIT, it)
+                ctx.problem_stage(STAGE.PROP_WEAK, it, 0)
+                ctx.problem_stage(STAGE.PROP_WEAK, it, 1)
+        # K9 GetDepthandNormal
+        st0 = pull_state(ctx)
+        ctx.problem_stage(STAGE.DEPTH_NORMAL)
+        st = pull_state(ctx)
+        r = ref.run_stages(imgs, cams, prm, ["depth_normal"], _ref_state(st0), depths=depths)
+        _, eq = _report("%s GetDepthandNormal" % tag, st["planes"], r["planes"])
+        assert eq.all(), tag
+        # K10 Black/RedPixelFilterStrong
+        st0 = st
+        ctx.problem_stage(STAGE.MEDIAN, 0, 0)
+        ctx.problem_stage(STAGE.MEDIAN, 0, 1)
+        st = pull_state(ctx)
+        r = ref.run_stages(imgs, cams, prm, ["median_black", "median_red"], _ref_state(st0), depths=depths)
+        _, eq = _report("%s median filter" % tag, st["planes"], r["planes"])
+        assert eq.all(), tag
+        # K11 DepthToWeak: 61 x S cost evaluations per pixel -> PixelState, plus the cost curve itself
+        st0 = st
+        ctx.capture_curve(True)
+        ctx.problem_stage(STAGE.DEPTH_TO_WEAK)
+        st = pull_state(ctx)
+        curve = ctx.problem_get(FIELD.RELIABLE_CURVE)
+        ctx.capture_curve(False)
+        r = ref.run_stages(imgs, cams, prm, ["depth_to_weak"], _ref_state(st0), depths=depths, want_curve=True)
+        swept = (r["curve"] != 0).any(axis=2)
+        _, eqc = _report("%s DepthToWeak cost curve (%d swept px x 61)" % (tag, swept.sum()), curve.reshape(r["curve"].shape)[swept], r["curve"][swept])
+        print("%s DepthToWeak states: equal %.6f  product %s reference %s" % (
+            tag, (st["weak_info"] == r["weak_info"]).mean(), np.bincount(st["weak_info"].ravel(), minlength=3),
+            np.bincount(r["weak_info"].ravel(), minlength=3)))
+        assert eqc.all(), tag
+        assert np.array_equal(st["weak_info"], r["weak_info"]), tag
+        # K12 ConfidenceCompute
+        st0 = st
+        ctx.problem_stage(STAGE.CONFIDENCE)
+        st = pull_state(ctx)
+        r = ref.run_stages(imgs, cams, prm, ["confidence"], _ref_state(st0), depths=depths)
+        print("%s confidence equal %.6f" % (tag, (st["confidence"] == r["confidence"]).mean()))
+        assert np.array_equal(st["confidence"], r["confidence"]), tag
+        assert np.array_equal(st["weak_info"], r["weak_info"]), tag
+        # K13 LocalRefine
+        st0 = st
+        ctx.problem_stage(STAGE.LOCAL_REFINE)
+        st = pull_state(ctx)
+        r = ref.run_stages(imgs, cams, prm, ["local_refine"], _ref_state(st0), depths=depths)
+        changed = (st0["planes"][..., 3] != r["planes"][..., 3])
+        _, eq = _report("%s LocalRefine (%d depths moved by the reference)" % (tag, changed.sum()), st["planes"], r["planes"])
+        assert eq.all(), tag
+        ctx.problem_finish()
+
+
+def test_view_selection_masks_bit_exact_on_identical_costs(ctx, office_state):
+    """the mask logic of ComputeMultiViewInitialCostandSelectedViews (sort, top-k, threshold with <=, APD.cu:754-770) isolated
+    from any cost noise: the product's init kernel, the reference's init kernel and a numpy restatement of the rule on the
+    PRODUCT'S OWN per-view costs must give the same uint32 masks and the same mean cost"""
+    ref = _ref()
+    from apde_mvs_b200.binding import STAGE
+    scene, sched = office_state
+    _setup_geometric(ctx, sched, view=3, use_apd=0)
+    imgs, cams, prm, depths = _inputs(ctx)
+    st0 = pull_state(ctx)
+    ctx.problem_stage(STAGE.INIT)
+    st = pull_state(ctx)
+    w, h, n = ctx.problem_dims()
+    N = n - 1
+    ys, xs = np.mgrid[0:h, 0:w]
+    planes = st["planes"].reshape(-1, 4)
+    cv = np.stack([ctx.eval_costs(np.stack([xs.ravel(), ys.ravel(), np.full(h * w, v + 1)], 1).astype(np.int32), planes, 0)
+                   for v in range(N)], 1)  # [P, N] per-view costs of the product
+    srt = np.sort(cv, axis=1)
+    valid = (cv < 2.0).sum(1)
+    top_k = np.minimum(valid, prm.top_k)
+    thr = np.take_along_axis(srt, np.maximum(top_k - 1, 0)[:, None], 1)[:, 0]
+    mask = ((cv <= thr[:, None]) * (1 << np.arange(N))[None, :]).sum(1).astype(np.uint32)
+    mask[top_k == 0] = 0
+    acc = np.zeros(h * w, np.float32)
+    for i in range(4):  # "cost += cost_vector[i]" in ascending order, fp32
+        acc = np.where(i < top_k, (acc + srt[:, min(i, N - 1)]).astype(np.float32), acc)
+    # "cost / top_k" is MUFU.RCP(float(top_k)) * cost in the reference build; RCP(1..4) is correctly rounded
+    rk = (np.float32(1.0) / np.maximum(top_k, 1).astype(np.float32)).astype(np.float32)
+    cost = np.where(top_k > 0, (rk * acc).astype(np.float32), np.float32(2.0))
+    assert np.array_equal(st["selected_views"].ravel(), mask)
+    assert np.array_equal(st["costs"].ravel(), cost)
+    r = ref.run_stages(imgs, cams, prm, ["init"], _ref_state(st0), depths=depths)
+    assert np.array_equal(st["selected_views"], r["selected_views"])
+    assert np.array_equal(st["costs"], r["costs"])
+    ctx.problem_finish()

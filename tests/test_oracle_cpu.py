@@ -38,8 +38,11 @@ def test_oracle_matches_reference_ncc_old():
     pb, _ = _golden_problem(z)
     got = pb.eval_costs(z["old_tuples"], z["old_planes"], 0)
     d = _stats("NCC-Old oracle vs reference", got, z["old_costs"])
-    assert (d <= 1e-4).mean() >= 0.98 and (d <= 1e-3).mean() >= 0.995
-    assert ((got == 2.0) == (z["old_costs"] == 2.0)).mean() >= 0.995
+    # measured: 99.90 % within 1e-4, max 5.4e-4, p99 1e-5.  The oracle follows the reference build's operation order; what is
+    # left is MUFU.RCP (<= 1 ulp off the correctly rounded reciprocal the oracle uses) moving a sample across a 1/256 weight
+    # bucket.  The product, which has the same MUFU unit, matches these vectors bit for bit (tests/test_gpu_reference_pins.py).
+    assert (d <= 1e-4).mean() >= 0.998 and (d <= 1e-3).all()
+    assert ((got == 2.0) == (z["old_costs"] == 2.0)).all()
     # the texture unit's weight quantisation is part of the reference's formulation: exact bilinear must fit worse
     pb.pb.tex_mode = 0
     d0 = np.abs(pb.eval_costs(z["old_tuples"], z["old_planes"], 0) - z["old_costs"])
@@ -52,8 +55,8 @@ def test_oracle_matches_reference_geom_cost():
     pb, _ = _golden_problem(z)
     got = pb.eval_costs(z["old_tuples"], z["old_planes"], 2)
     d = _stats("geom oracle vs reference", got, z["geom_costs"])
-    assert (d <= 1e-3).mean() >= 0.99  # a truncated texel index may flip at a pixel boundary
-    assert ((got == 3.0) == (z["geom_costs"] == 3.0)).mean() >= 0.995
+    assert (d <= 1e-4).all()  # measured: max 4.1e-5 (MUFU.RCP / MUFU.SQRT vs correctly rounded)
+    assert ((got == 3.0) == (z["geom_costs"] == 3.0)).all()
 
 
 def test_oracle_matches_reference_ncc_new():
@@ -65,7 +68,7 @@ def test_oracle_matches_reference_ncc_new():
     pb.selected_views[...] = z["new_sel"]
     got = pb.eval_costs(z["new_tuples"], z["new_planes"], 1)
     d = _stats("NCC-New oracle vs reference", got, z["new_costs"])
-    assert (d <= 1e-4).mean() >= 0.97 and (d <= 1e-3).mean() >= 0.99
+    assert (d <= 1e-4).mean() >= 0.995 and (d <= 1e-3).all()  # measured: 99.65 % within 1e-4, max 5.0e-4
 
 
 GOLDEN_SA = os.path.join(ROOT, "tests", "golden", "ref_costs_sa.npz")
@@ -79,7 +82,7 @@ def test_oracle_matches_reference_with_segment_labels():
     pb.set_sa_mask(zs["labels"])
     got = pb.eval_costs(z["old_tuples"], z["old_planes"], 0)
     d = _stats("NCC-Old + labels oracle vs reference", got, zs["old_costs"])
-    assert (d <= 1e-4).mean() >= 0.98 and (d <= 1e-3).mean() >= 0.995
+    assert (d <= 1e-4).mean() >= 0.997 and (d <= 1e-3).all()  # measured: 99.87 % within 1e-4, max 8.8e-4
     assert (np.abs(zs["old_costs"] - z["old_costs"]) > 1e-3).mean() > 0.2  # the map matters on this input
     pb, _ = _golden_problem(z, use_apd=1)
     pb.set_sa_mask(zs["labels"])
@@ -88,7 +91,7 @@ def test_oracle_matches_reference_with_segment_labels():
     pb.selected_views[...] = z["new_sel"]
     got = pb.eval_costs(z["new_tuples"], z["new_planes"], 1)
     d = _stats("NCC-New + labels oracle vs reference", got, zs["new_costs"])
-    assert (d <= 1e-4).mean() >= 0.97 and (d <= 1e-3).mean() >= 0.99
+    assert (d <= 1e-4).mean() >= 0.996 and (d <= 1e-3).all()  # measured: 99.77 % within 1e-4, max 3.2e-4
     assert (np.abs(zs["new_costs"] - z["new_costs"]) > 1e-3).mean() > 0.05
 
 
