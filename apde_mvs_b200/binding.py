@@ -7,6 +7,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 MAX_IMAGES = 32
 ANCHOR_NUM = 9
+COMM_ID_BYTES = 128
 
 
 def lib_path():
@@ -75,7 +76,8 @@ class Timing(C.Structure):
     _fields_ = [
         ("patchmatch_ms", C.c_double), ("device_ms", C.c_double), ("total_ms", C.c_double),
         ("evals_ncc_old", C.c_uint64), ("evals_ncc_new", C.c_uint64), ("evals_geom", C.c_uint64),
-        ("kernel_launches", C.c_uint64), ("passes", C.c_int),
+        ("kernel_launches", C.c_uint64), ("passes", C.c_int), ("pad_", C.c_int),
+        ("exchange_ms", C.c_double), ("exchange_bytes", C.c_uint64),
     ]
 
 
@@ -153,6 +155,13 @@ def load_library(path=None):
     lib.apde_weak_vis_filter_range.argtypes = [P, C.c_int, C.c_int, P]
     lib.apde_map_pool.argtypes = [P, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.apde_views_mark_maps.argtypes = [P, C.c_int, C.c_int]
+    lib.apde_comm_create_id.argtypes = [P]
+    lib.apde_comm_init.argtypes = [P, P, C.c_int, C.c_int]
+    lib.apde_comm_block_of.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.apde_comm_info.argtypes = [P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.apde_exchange.argtypes = [P, C.c_int]
+    lib.apde_fuse_collective.argtypes = [P, C.c_int, C.c_int, P, P, C.c_int64, C.POINTER(C.c_int64)]
+    lib.apde_comm_destroy.argtypes = [P]
     _lib = lib
     return lib
 
@@ -409,6 +418,46 @@ class Context:
 
     def views_mark_maps(self, width, height):
         self._check(self.lib.apde_views_mark_maps(self._h, width, height))
+
+    # ---- multi-GPU jobs (apde_comm_*): NCCL inside the library, the caller only hands the 128-byte id around
+    @staticmethod
+    def comm_create_id():
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        lib = load_library()
+        if lib.apde_comm_create_id(C.cast(buf, C.c_void_p)) != 0:
+            raise ApdeError("apde_comm_create_id: %s" % lib.apde_last_error().decode())
+        return bytes(buf)
+
+    def comm_init(self, comm_id, rank, world):
+        assert len(comm_id) == COMM_ID_BYTES
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(comm_id)
+        self._check(self.lib.apde_comm_init(self._h, C.cast(buf, C.c_void_p), rank, world))
+
+    def comm_info(self):
+        """(rank, world, first_view, num_views) of this context in its job (a lone context is rank 0 of 1)"""
+        r, w, f, n = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.apde_comm_info(self._h, C.byref(r), C.byref(w), C.byref(f), C.byref(n)))
+        return r.value, w.value, f.value, n.value
+
+    def exchange(self, which):
+        self._check(self.lib.apde_exchange(self._h, which))
+
+    def fuse_collective(self, use_weak_filter=True, variant=0):
+        """collective RunFusion over the maps of all ranks: (xyz, bgr) on rank 0, (None, None) elsewhere"""
+        rank = self.comm_info()[0]
+        n = C.c_int64()
+        flt = 1 if use_weak_filter else 0
+        if rank != 0:
+            self._check(self.lib.apde_fuse_collective(self._h, variant, flt, None, None, 0, C.byref(n)))
+            # ranks other than 0 join the second (filling) call of rank 0 below: its gathers are collective as well
+            self._check(self.lib.apde_fuse_collective(self._h, variant, flt, None, None, 0, C.byref(n)))
+            return None, None
+        self._check(self.lib.apde_fuse_collective(self._h, variant, flt, None, None, 0, C.byref(n)))
+        xyz = np.zeros((n.value, 3), np.float32)
+        bgr = np.zeros((n.value, 3), np.float32)
+        n2 = C.c_int64()
+        self._check(self.lib.apde_fuse_collective(self._h, variant, flt, _ptr(xyz), _ptr(bgr), n.value, C.byref(n2)))
+        return xyz[:n2.value], bgr[:n2.value]
 
     def fuse(self, use_weak_filter=True, max_points=None, variant=0):
         """variant 0 = RunFusion, 1 = RunFusion_TAT_I, 2 = RunFusion_TAT_A (main.cpp:277-283)"""

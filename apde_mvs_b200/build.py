@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libapde.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["apde_api.cu", "apde_kernels.cu", "apde_apd.cu", "apde_sweep.cu", "apde_prop.cu", "apde_maps.cu", "apde_lists.cu", "apde_fusion.cu", "apde_microbench.cu"]
+SOURCES = ["apde_api.cu", "apde_comm.cu", "apde_kernels.cu", "apde_apd.cu", "apde_sweep.cu", "apde_prop.cu", "apde_maps.cu", "apde_lists.cu", "apde_fusion.cu", "apde_microbench.cu"]
 # the fusion kernels restate HOST code of the reference (IEEE arithmetic, no FMA contraction): no fast-math there
 PRECISE = {"apde_fusion.cu": ["-fmad=false"]}
 FAST = ["--use_fast_math"]
@@ -50,7 +50,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if procs or not os.path.exists(LIB):
-        subprocess.check_call([NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs + ["-lcudart"])
+        subprocess.check_call([NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs + ["-lcudart", "-ldl"])
     return LIB
 
 

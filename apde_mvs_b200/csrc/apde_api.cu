@@ -14,118 +14,17 @@
 #include <string>
 #include <vector>
 
-#include "../../include/apde.h"
-#include "apde_kernels.h"
+#include "apde_context.h"
 #include "apde_fusion.h"
 
-using namespace apde;
-
-static const int kStages = 11;
-static const int kCounterWords = (kStages + 1) * 4;
-static thread_local std::string g_err;
-static int fail(int code, const char *fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
-    va_end(ap);
-    g_err = buf;
-    return code;
+std::string &apde_error_slot() {
+    static thread_local std::string e;
+    return e;
 }
-#define CU(call)                                                                                           \
-    do {                                                                                                   \
-        cudaError_t e_ = (call);                                                                           \
-        if (e_ != cudaSuccess) return fail(APDE_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
-    } while (0)
-
-struct ViewStore {
-    apde_camera cam;
-    std::vector<int> src;
-    uint8_t *d_gray = nullptr, *d_bgr = nullptr;
-    uint8_t *d_sa = nullptr;  // segment labels as read from sa_masks/<id>.bin (own size saw x sah), nullptr = none
-    int saw = 0, sah = 0;
-    int mw = 0, mh = 0;  // size of the stored maps (0 = none yet)
-    int dw = 0, dh = 0;  // size of this view's depth map in the READABLE pool d_depth_pool[cur]: equal to mw x mh, except in
-                         // Jacobi mode between a view's finish and the end of the pass (the new map went to the other pool)
-    float *d_normal = nullptr;
-    uint8_t *d_weak = nullptr, *d_conf = nullptr;
-    bool has_conf = false;
-};
-
-struct apde_context {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int V = 0, W = 0, H = 0;
-    bool committed = false;
-    std::vector<ViewStore> views;
-    float *d_depth_pool[2] = {nullptr, nullptr};  // [V][W*H] ; [1] only allocated in Jacobi mode
-    // normal / weak / confidence maps of all views, contiguous per field so that a multi-GPU job can all-gather them in
-    // place before fusion (apde_map_pool); ViewStore::d_normal / d_weak / d_conf point into these
-    float *d_normal_pool = nullptr;               // [V][W*H*3]
-    uint8_t *d_weak_pool = nullptr, *d_conf_pool = nullptr;  // [V][W*H]
-    int cur = 0;
-    // pyramid level (one alive at a time)
-    // pyramid levels: built on first use, kept for the whole scene (images are immutable after commit)
-    struct Level {
-        int scale = 0, w = 0, h = 0;
-        cudaArray_t arr = nullptr;
-        cudaTextureObject_t tex = 0;
-        float *lin = nullptr;  // [V][h*w]
-        void *half = nullptr;  // [V][h*w] __half staging when the texture is stored as fp16
-        bool fp16 = false;
-        bool u8 = false;       // 8-bit UNORM texels (scale 1 only: the images are 8-bit integers)
-        bool u16 = false;      // 16-bit UNORM texels holding 4 x value (power-of-two scales of divisible sizes: 2x2 means)
-        bool stale = true;     // contents must be re-derived from the views' images
-    };
-    std::vector<Level> levels;
-    int level_scale = 0, lw = 0, lh = 0;  // the level of the current problem
-    float level_unorm = 0.0f, level_inv = 1.0f;
-    cudaArray_t level_arr = nullptr;
-    cudaTextureObject_t level_tex = 0;
-    float *d_level_lin = nullptr;  // [V][lh*lw]
-    // problem working set (allocated once at full resolution)
-    bool ws_alloc = false;
-    float4 *d_planes = nullptr, *d_fit = nullptr;
-    uint8_t *d_sa = nullptr;  // segment labels of the active problem's reference view at the working size
-    ListScratch list_scratch;
-    float *d_costs = nullptr, *d_depthws = nullptr, *d_scratch_depth = nullptr, *d_scratch_normal = nullptr;
-    uint32_t *d_sel = nullptr;
-    uint4 *d_vw = nullptr;
-    uint8_t *d_weak = nullptr, *d_conf = nullptr, *d_reliable = nullptr;
-    short2 *d_nearest = nullptr, *d_anchors = nullptr;
-    uint16_t *d_ns_tiles = nullptr;
-    float *d_curve = nullptr;   // [P][61] DepthToWeak cost curves while capture_curve is on
-    size_t curve_cap = 0;
-    bool capture_curve = false;
-    int *d_lists = nullptr, *d_list_counts = nullptr;  // compacted checkerboard pixel lists (4 x list_cap)
-    int list_cap = 0;
-    int h_list_counts[4] = {0, 0, 0, 0};  // host copy of the list lengths: sizes (or skips) the list-driven launches
-    bool lists_dirty = true;
-    unsigned long long *d_counters = nullptr;  // [kStages + 1][4]: per-stage NCC-Old / NCC-New / geom evaluation counts
-    uint64_t launches = 0;
-    // per-stage profiling (CUDA events on the launching stream)
-    bool profiling = false;
-    std::vector<cudaEvent_t> ev_pool, pm_events;
-    std::vector<int> ev_stage;
-    double stage_ms[16] = {0};
-    uint64_t stage_launches[16] = {0};
-    // current problem
-    bool problem_active = false;
-    int ref_view = -1;
-    bool jacobi_write = false;
-    apde_params params;
-    std::vector<apde_camera> cams;
-    PassK K;
-    SweepWorkspace sweep;  // DepthToWeak / LocalRefine column costs
-    PropWorkspace prop;    // propagation pipeline buffers
-    // fusion state
-    uint8_t *d_skip = nullptr;
-};
 
 extern "C" {
 
-const char *apde_last_error(void) { return g_err.c_str(); }
+const char *apde_last_error(void) { return apde_error_slot().c_str(); }
 const char *apde_version(void) { return "apde-b200 0.1 sm_100a"; }
 
 void apde_params_default(apde_params *p) {  // main.h:80-100
@@ -225,6 +124,7 @@ void apde_destroy(apde_context *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    apde_comm_destroy(c);
     free_scene(c);
     cudaFree(c->d_counters);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -1090,8 +990,13 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
     const int per_round = 1 + s->geom_iterations;
     if (pass_index < 0 || pass_index >= rounds * per_round) return fail(APDE_ERR_ARG, "run_schedule_pass: pass %d out of range", pass_index);
     const int i = pass_index / per_round, j = pass_index % per_round - 1;  // j = -1: photometric pass
+    (void)i; (void)j;
+    int rc_tmp = 0;
     const size_t Pfull = (size_t)c->W * c->H;
-    if (s->jacobi && !c->d_depth_pool[1]) {
+    // a multi-GPU job (apde_comm_init): this rank's block of views, Jacobi order, depth maps exchanged view by view
+    const bool job = apde_comm_attached(c);
+    const bool jacobi = s->jacobi != 0 || job;
+    if (jacobi && !c->d_depth_pool[1]) {
         CU(cudaMalloc(&c->d_depth_pool[1], (size_t)c->V * Pfull * sizeof(float)));
         CU(cudaMemsetAsync(c->d_depth_pool[1], 0, (size_t)c->V * Pfull * sizeof(float), c->stream));
     }
@@ -1102,8 +1007,15 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
         const int prc = apde_schedule_pass_params(c, s, pass_index, &p, &scale, &seed);
         if (prc) return prc;
     }
-    const int first = (s->num_views_local > 0) ? s->first_view : 0;
-    const int count = (s->num_views_local > 0) ? s->num_views_local : c->V;
+    int first = (s->num_views_local > 0) ? s->first_view : 0;
+    int count = (s->num_views_local > 0) ? s->num_views_local : c->V;
+    int longest = count;  // views in the largest block of the job: every rank takes part in that many exchange rounds
+    if (job) {
+        if (s->num_views_local > 0) return fail(APDE_ERR_ARG, "run_schedule_pass: a multi-GPU job deals the views out itself (num_views_local must be 0)");
+        int rk = 0, wd = 1;
+        if ((rc_tmp = apde_comm_info(c, &rk, &wd, &first, &count))) return rc_tmp;
+        longest = (c->V + wd - 1) / wd;
+    }
     if (first < 0 || first + count > c->V) return fail(APDE_ERR_ARG, "run_schedule_pass: bad shard [%d, %d)", first, first + count);
 
     // APDE_PROFILE_PASS=<pass>[:<occurrence>]: bracket that pass with cudaProfilerStart/Stop, for
@@ -1123,18 +1035,26 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
     CU(cudaEventCreate(&evp0));
     CU(cudaEventCreate(&evp1));
     CU(cudaEventRecord(evp0, c->stream));
-    while ((int)c->pm_events.size() < 2 * count) {
+    while ((int)c->pm_events.size() < 2 * std::max(count, 1)) {
         cudaEvent_t ev;
         CU(cudaEventCreate(&ev));
         c->pm_events.push_back(ev);
     }
-    for (int v = first; v < first + count; ++v) {
-        if ((rc = apde_problem_setup(c, v, &p, scale, seed))) return rc;
-        CU(cudaEventRecord(c->pm_events[2 * (v - first)], c->stream));
-        if ((rc = apde_problem_run(c))) return rc;
-        CU(cudaEventRecord(c->pm_events[2 * (v - first) + 1], c->stream));
-        if ((rc = problem_finish_impl(c, s->jacobi != 0))) return rc;  // no host sync: the host runs ahead of the stream
+    double exposed_ms = 0.0;
+    uint64_t received = 0;
+    for (int k = 0; k < longest; ++k) {
+        if (k < count) {
+            const int v = first + k;
+            if ((rc = apde_problem_setup(c, v, &p, scale, seed))) return rc;
+            CU(cudaEventRecord(c->pm_events[2 * k], c->stream));
+            if ((rc = apde_problem_run(c))) return rc;
+            CU(cudaEventRecord(c->pm_events[2 * k + 1], c->stream));
+            if ((rc = problem_finish_impl(c, jacobi))) return rc;  // no host sync: the host runs ahead of the stream
+        }
+        // the k-th views of all ranks travel while the (k + 1)-th are computed
+        if (job && (rc = apde_comm_share_depth_row(c, k, c->cur ^ 1, c->lw, c->lh))) return rc;
     }
+    if (job && (rc = apde_comm_join(c, &exposed_ms, &received))) return rc;  // the compute stream waits for the last rows
     CU(cudaEventRecord(evp1, c->stream));
     CU(cudaEventSynchronize(evp1));
     for (int k = 0; k < count; ++k) {
@@ -1142,15 +1062,22 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
         CU(cudaEventElapsedTime(&ms, c->pm_events[2 * k], c->pm_events[2 * k + 1]));
         pm_ms += ms;
     }
-    if (s->jacobi) {
+    if (jacobi) {
         // views outside this rank's shard keep their previous depth until the host-side exchange overwrites them
-        if (count < c->V) {
+        // (a job's exchange has already put the new rows there)
+        if (count < c->V && !job) {
             for (int v = 0; v < c->V; ++v) {
                 if (v >= first && v < first + count) continue;
                 CU(cudaMemcpyAsync(c->d_depth_pool[c->cur ^ 1] + (size_t)v * Pfull, c->d_depth_pool[c->cur] + (size_t)v * Pfull,
                                    Pfull * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
                 // the host-side exchange fills these at the pass resolution before the next pass reads them
                 c->views[v].mw = c->lw; c->views[v].mh = c->lh;
+            }
+        }
+        if (job) {
+            for (int v = 0; v < c->V; ++v) {
+                if (v >= first && v < first + count) continue;
+                c->views[v].mw = c->lw; c->views[v].mh = c->lh;  // the received maps are at the pass resolution
             }
         }
         c->cur ^= 1;
@@ -1173,6 +1100,8 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
         out->evals_geom += c1[2] - c0[2];
         out->kernel_launches += c1[3] - c0[3];
         out->passes += 1;
+        out->exchange_ms += exposed_ms;
+        out->exchange_bytes += received;
     }
     return APDE_OK;
 }

@@ -17,11 +17,22 @@ std::shared_ptr<SceneSession> SceneSession::get(const path &dense_folder, int gp
     const std::string key = std::filesystem::weakly_canonical(dense_folder).string();
     auto it = g_sessions.find(key);
     if (it != g_sessions.end()) return it->second;
+    return get_job(dense_folder, {gpu_index});
+}
+
+std::shared_ptr<SceneSession> SceneSession::get_job(const path &dense_folder, const std::vector<int> &gpus) {
+    const std::string key = std::filesystem::weakly_canonical(dense_folder).string();
+    if (gpus.empty()) throw std::runtime_error("no GPU given");
     std::shared_ptr<SceneSession> s(new SceneSession());
     std::string err;
     if (!GenerateSampleList(dense_folder, s->problems, &err)) throw std::runtime_error(err);
     if (s->problems.empty()) throw std::runtime_error("no problems in " + (dense_folder / "pair.txt").string());
-    check(apde_create(gpu_index, &s->ctx), "apde_create");
+    for (int g : gpus) {
+        apde_context *c = nullptr;
+        check(apde_create(g, &c), "apde_create");
+        s->ctxs.push_back(c);
+    }
+    s->ctx = s->ctxs[0];
     int max_id = 0;
     for (auto &p : s->problems) max_id = std::max(max_id, p.ref_image_id);
     s->id_to_view.assign(max_id + 1, -1);
@@ -41,7 +52,7 @@ std::shared_ptr<SceneSession> SceneSession::get(const path &dense_folder, int gp
             if (!l.image_ok) throw std::runtime_error("Images may error, check it!");
             if (!begun) {
                 s->width = l.gray.cols; s->height = l.gray.rows;
-                check(apde_scene_begin(s->ctx, (int)n_views, s->width, s->height), "apde_scene_begin");
+                for (apde_context *c : s->ctxs) check(apde_scene_begin(c, (int)n_views, s->width, s->height), "apde_scene_begin");
                 begun = true;
             } else if (l.gray.cols != s->width || l.gray.rows != s->height) {
                 throw std::runtime_error("Images may error, check it!");  // CheckImages, main.cpp:104-127
@@ -49,12 +60,12 @@ std::shared_ptr<SceneSession> SceneSession::get(const path &dense_folder, int gp
             if (!l.cam_ok) throw std::runtime_error("can not read camera of image " + ToFormatIndex(p.ref_image_id));
             l.cam.width = s->width; l.cam.height = s->height;
             s->cameras.push_back(l.cam);
-            check(apde_scene_set_view(s->ctx, (int)i, l.gray.data(), l.bgr.empty() ? nullptr : l.bgr.data(), &l.cam), "apde_scene_set_view");
-            s->has_color = !l.bgr.empty();
-            if (!l.sa.empty()) {
-                check(apde_view_set_sa_mask(s->ctx, (int)i, l.sa.data(), l.sa.cols, l.sa.rows), "apde_view_set_sa_mask");
-                s->num_sa_masks++;
+            for (apde_context *c : s->ctxs) {  // every GPU of a job holds the whole scene
+                check(apde_scene_set_view(c, (int)i, l.gray.data(), l.bgr.empty() ? nullptr : l.bgr.data(), &l.cam), "apde_scene_set_view");
+                if (!l.sa.empty()) check(apde_view_set_sa_mask(c, (int)i, l.sa.data(), l.sa.cols, l.sa.rows), "apde_view_set_sa_mask");
             }
+            s->has_color = !l.bgr.empty();
+            if (!l.sa.empty()) s->num_sa_masks++;
         }
     }
     for (size_t i = 0; i < s->problems.size(); ++i) {
@@ -64,15 +75,17 @@ std::shared_ptr<SceneSession> SceneSession::get(const path &dense_folder, int gp
             if (v < 0) throw std::runtime_error("pair.txt names image " + std::to_string(id) + " that is not a reference view");
             src.push_back(v);
         }
-        check(apde_scene_set_pairs(s->ctx, (int)i, (int)src.size(), src.data()), "apde_scene_set_pairs");
+        for (apde_context *c : s->ctxs) check(apde_scene_set_pairs(c, (int)i, (int)src.size(), src.data()), "apde_scene_set_pairs");
     }
-    check(apde_scene_commit(s->ctx), "apde_scene_commit");
+    for (apde_context *c : s->ctxs) check(apde_scene_commit(c), "apde_scene_commit");
     g_sessions[key] = s;
     return s;
 }
 
 void SceneSession::release_all() { g_sessions.clear(); }
-SceneSession::~SceneSession() { if (ctx) apde_destroy(ctx); }
+SceneSession::~SceneSession() {
+    for (apde_context *c : ctxs) apde_destroy(c);
+}
 int SceneSession::view_of(int image_id) const { return (image_id >= 0 && image_id < (int)id_to_view.size()) ? id_to_view[image_id] : -1; }
 
 APD::APD(const Problem &problem_) : problem(problem_) {
@@ -165,6 +178,44 @@ static void run_fusion_variant(int variant, const path &dense_folder, const std:
     }
     ExportPointCloud(dense_folder / "APD" / name, pc, export_color && s->has_color);
     std::cout << "Fused " << pc.size() << " points" << std::endl;
+}
+
+void RunFusionJob(SceneSession &s, int rank, int variant, const std::string &name, bool weak_filter, bool export_color) {
+    apde_context *c = s.ctxs.at((size_t)rank);
+    int first = 0, count = 0;
+    check(apde_comm_info(c, nullptr, nullptr, &first, &count), "apde_comm_info");
+    // normals, states and confidences of every view on every rank (depth maps already are: exchanged pass by pass)
+    for (int which : {APDE_POOL_NORMAL, APDE_POOL_WEAK, APDE_POOL_CONFIDENCE}) check(apde_exchange(c, which), "apde_exchange");
+    int mw = 0, mh = 0;
+    check(apde_view_download(c, count > 0 ? first : 0, nullptr, nullptr, nullptr, nullptr, &mw, &mh), "apde_view_download(dims)");
+    if (count == 0) { mw = s.width; mh = s.height; }
+    check(apde_views_mark_maps(c, mw, mh), "apde_views_mark_maps");
+    int filter_mode = 0;
+    if (weak_filter) {  // the rank's own views: WeakVisFilter's work items (APD.cpp:1040-1047), skip.png by their owner (APD.cpp:1026-1036)
+        const size_t P = (size_t)mw * mh;
+        std::vector<uint8_t> skip(P * (size_t)std::max(count, 1));
+        check(apde_weak_vis_filter_range(c, first, count, skip.data()), "apde_weak_vis_filter_range");
+        for (int k = 0; k < count; ++k) {
+            Mat img(mh, mw, CV_8UC1);
+            for (size_t i = 0; i < P; ++i) img.data()[i] = skip[(size_t)k * P + i] == 1 ? 255 : 0;
+            WritePNG(s.problems[(size_t)(first + k)].result_folder / "skip.png", img);
+        }
+        check(apde_exchange(c, APDE_POOL_SKIP), "apde_exchange(skip)");
+        filter_mode = APDE_WEAK_FILTER_KEEP;
+    }
+    if (rank != 0) return;
+    // the greedy claim order runs over all views through masks[] (APD.cpp:1149,1176,1209): one rank, over the gathered maps
+    int64_t n = 0, n2 = 0;
+    check(apde_fuse_variant(c, variant, filter_mode, nullptr, nullptr, 0, &n), "apde_fuse(count)");
+    std::vector<float> xyz((size_t)n * 3), bgr((size_t)n * 3);
+    check(apde_fuse_variant(c, variant, filter_mode, xyz.data(), bgr.data(), n, &n2), "apde_fuse");
+    std::vector<PointList> pc((size_t)std::min(n, n2));
+    for (size_t i = 0; i < pc.size(); ++i) {
+        pc[i].coord = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        pc[i].color = {bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2]};
+    }
+    ExportPointCloud(s.problems[0].dense_folder / "APD" / name, pc, export_color && s.has_color);
+    std::cout << ("Fused " + std::to_string(pc.size()) + " points\n") << std::flush;
 }
 
 void RunFusion(const path &dense_folder, const std::vector<Problem> &, const std::string &name, bool weak_filter, bool export_color) {

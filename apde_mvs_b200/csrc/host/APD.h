@@ -60,9 +60,13 @@ struct float4_ { float x, y, z, w; };
 class SceneSession {
 public:
     static std::shared_ptr<SceneSession> get(const path &dense_folder, int gpu_index = 0);
+    // a multi-GPU job over one scene (`apd --gpus N`): one context per listed GPU, every context holds the whole scene (views
+    // are decoded once and uploaded to each); the contexts are connected with apde_comm_init by the threads that drive them
+    static std::shared_ptr<SceneSession> get_job(const path &dense_folder, const std::vector<int> &gpus);
     static void release_all();
     ~SceneSession();
-    apde_context *ctx = nullptr;
+    apde_context *ctx = nullptr;        // == ctxs[0]
+    std::vector<apde_context *> ctxs;   // one per GPU of the job (size 1 without --gpus)
     std::vector<ProblemDesc> problems;
     std::vector<int> id_to_view;  // image id -> view index (-1: unknown)
     int width = 0, height = 0;
@@ -111,5 +115,8 @@ void RunFusion_TAT_I(const path &dense_folder, const std::vector<Problem> &probl
                      bool weak_filter = true, bool export_color = true);
 void RunFusion_TAT_A(const path &dense_folder, const std::vector<Problem> &problems, const std::string &name = "APD.ply",
                      bool weak_filter = true, bool export_color = true);
+// The fusion of a multi-GPU job, called by EVERY rank's thread with its own context: WeakVisFilter of the rank's own views
+// (skip.png written by their owner), the gathers and, on rank 0, the greedy fusion and the PLY.  variant = enum apde_fuse_kind.
+void RunFusionJob(SceneSession &s, int rank, int variant, const std::string &name, bool weak_filter, bool export_color);
 
 }  // namespace apd

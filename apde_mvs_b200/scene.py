@@ -132,12 +132,33 @@ class Scene:
                 f.write("%d\n%d %s\n" % (i, len(src), " ".join("%d 1.0" % s for s in src)))
 
 
+def _render_job(job):
+    facets, K, R, t, W, H = job
+    with np.errstate(all="ignore"):
+        return render_view(facets, K, R, t, W, H)
+
+
+def render_views(facets, K, poses, width, height, which=None, workers=0):
+    """(gray, depth) of the views `which` (default all), rendered by a pool of processes when there is more than one big view
+    (ray casting + 5-octave value noise is ~4 s of one core per 1080p view)"""
+    which = list(range(len(poses))) if which is None else list(which)
+    jobs = [(facets, K, poses[i][0], poses[i][1], width, height) for i in which]
+    workers = workers or min(len(jobs), os.cpu_count() or 1, 16)
+    if workers <= 1 or len(jobs) < 2 or width * height < 256 * 256:
+        return [_render_job(j) for j in jobs]
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(workers) as pool:
+        return pool.map(_render_job, jobs, chunksize=1)
+
+
 def _finish(scene, facets, K, poses, num_src, depth_range, with_color=False, prerendered=None):
     W, H = scene.width, scene.height
     scene.K = K
     centers = []
+    if prerendered is None:
+        prerendered = render_views(facets, K, poses, W, H)
     for i, (R, t) in enumerate(poses):
-        gray, depth = prerendered[i] if prerendered is not None else render_view(facets, K, R, t, W, H)
+        gray, depth = prerendered[i]
         scene.images.append(gray)
         scene.gt_depth.append(depth)
         scene.Rs.append(R)
@@ -186,20 +207,30 @@ def _room_facets(seed, weak=0.0):
     return fac
 
 
-def make_office_scene(width=1550, height=1030, num_views=26, num_src=10, seed=2, weak=0.0, arc_deg=60.0, with_color=False,
-                      prerendered=None):
-    """C2 / C3 / C4 / C5 shaped: floor + two walls + three boxes, cameras on an arc looking at the room centre.
-    weak > 0 adds weak-texture blobs (amplitude <= 1 grey level) covering roughly that fraction of every surface."""
+def office_setup(width, height, num_views, seed=2, weak=0.0, arc_deg=60.0, rings=1):
+    """facets, K and camera poses of the office scene: `rings` arcs of `num_views` cameras each, one above the other
+    (0.3 m apart, closer than neighbours on an arc), views numbered ring by ring -- the nearest-camera source lists of a
+    view then reach into the neighbouring rings, which a multi-GPU job hands to other ranks"""
     f = 0.85 * width
     K = np.array([[f, 0, width / 2.0], [0, f, height / 2.0], [0, 0, 1.0]])
     facets = _room_facets(seed, weak)
     target = np.array([0.0, 0.3, 5.5])
     poses = []
     radius = 5.5
-    for i in range(num_views):
-        a = np.deg2rad(-arc_deg / 2 + arc_deg * i / max(1, num_views - 1))
-        eye = target + radius * np.array([np.sin(a), -0.25 + 0.1 * np.sin(3 * a), -np.cos(a)])
-        poses.append(look_at(eye, target))
+    for g in range(rings):
+        lift = 0.3 * (g - (rings - 1) / 2.0)
+        for i in range(num_views):
+            a = np.deg2rad(-arc_deg / 2 + arc_deg * i / max(1, num_views - 1))
+            eye = target + radius * np.array([np.sin(a), -0.25 + 0.1 * np.sin(3 * a), -np.cos(a)]) + np.array([0.0, lift, 0.0])
+            poses.append(look_at(eye, target))
+    return facets, K, poses
+
+
+def make_office_scene(width=1550, height=1030, num_views=26, num_src=10, seed=2, weak=0.0, arc_deg=60.0, with_color=False,
+                      prerendered=None, rings=1):
+    """C2 / C3 / C4 / C5 shaped: floor + two walls + three boxes, cameras on an arc (or `rings` arcs) looking at the room
+    centre.  weak > 0 adds weak-texture blobs (amplitude <= 1 grey level) covering roughly that fraction of every surface."""
+    facets, K, poses = office_setup(width, height, num_views, seed, weak, arc_deg, rings)
     return _finish(Scene(width, height), facets, K, poses, num_src, (2.0, 12.0), with_color, prerendered)
 
 

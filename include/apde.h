@@ -22,6 +22,8 @@
  *                                                                                        APD.cu:448-721, 865-902
  *   apde_weak_vis_filter / apde_fuse    <- WeakVisFilter, RunFusion                      APD.cpp:962-1227
  *   apde_fuse_variant                   <- RunFusion_TAT_I / RunFusion_TAT_A             APD.cpp:1229-1608
+ *   apde_comm_* / apde_exchange / apde_fuse_collective
+ *                                       <- (none: the reference is single-GPU per scan, run.py:127-153)
  *   apde_get_counters                   <- (none; the reference only prints wall-clock, main.cpp:157-161)
  *   apde_last_error                     <- CudaSafeCall / CudaCheckError                 APD.cpp:417-450
  *
@@ -212,6 +214,9 @@ typedef struct {
     uint64_t evals_ncc_old, evals_ncc_new, evals_geom;
     uint64_t kernel_launches;
     int passes;
+    int pad_;
+    double exchange_ms;       /* multi-GPU: device time the compute stream waited for the depth-map exchange (the exposed part) */
+    uint64_t exchange_bytes;  /* multi-GPU: depth-map bytes this rank received */
 } apde_timing;
 
 int apde_run_schedule(apde_context *ctx, const apde_schedule *s, apde_timing *out);
@@ -240,6 +245,35 @@ int apde_microbench_pattern(apde_context *ctx, int mode, float spread, double *t
 /* device pointer + byte size of the replicated depth-map pool ([V][P] float at the current map size) so that a
  * host-side collective (NCCL all-gather between passes) can exchange shards in place */
 int apde_depth_pool(apde_context *ctx, void **dev_ptr, size_t *bytes, size_t *bytes_per_view);
+
+/* ---------------------------------------------------------------- multi-GPU jobs (no counterpart in the reference,
+ * which runs one process per GPU on disjoint scans, run.py:127-153)
+ *
+ * One context per GPU, every context holds the whole scene (images, cameras, pairs).  Reference views are dealt out in
+ * contiguous blocks; within a pass every rank runs its own block, and each finished depth map is broadcast to the other
+ * ranks over NCCL (NVLink / NVSwitch) while the next view of the block is being computed -- the maps a view reads from its
+ * neighbours are those of the PREVIOUS pass (Jacobi order; main.cpp:309,336 is Gauss-Seidel through the file cache).
+ * The contexts may live in one process (one host thread per context: `apd --gpus N`) or in one process per GPU (torchrun,
+ * mpirun): rank 0 makes an id with apde_comm_create_id, the job hands its 128 bytes to every rank, every rank calls
+ * apde_comm_init.  After that
+ *   apde_run_schedule / apde_run_schedule_pass   run this rank's block and exchange the depth maps (collective calls);
+ *   apde_exchange                                all-gathers the rows of one map pool (before fusion);
+ *   apde_fuse_collective                         sharded WeakVisFilter + gathers + the greedy fusion on rank 0.
+ * NCCL is loaded at run time (dlopen of libnccl.so.2) by apde_comm_create_id / apde_comm_init only: a single-GPU user needs none. */
+#define APDE_COMM_ID_BYTES 128
+int apde_comm_create_id(uint8_t id[APDE_COMM_ID_BYTES]);
+int apde_comm_init(apde_context *ctx, const uint8_t id[APDE_COMM_ID_BYTES], int rank, int world);
+/* how a job deals V views out: contiguous blocks, the first V % world ranks hold one view more (pure function, no GPU) */
+int apde_comm_block_of(int num_views, int world, int rank, int *first_view, int *count);
+/* rank, world and this rank's block [first_view, first_view + num_views) of the committed scene (any pointer may be NULL) */
+int apde_comm_info(apde_context *ctx, int *rank, int *world, int *first_view, int *num_views);
+/* collective: the rows of pool `which` (enum apde_pool) that belong to each rank's own views reach every rank, in place */
+int apde_exchange(apde_context *ctx, int which);
+/* collective: RunFusion / _TAT_I / _TAT_A over the maps of all ranks.  WeakVisFilter is sharded by reference view, the map and
+ * skip pools are all-gathered, rank 0 runs the greedy fusion and receives the points; the other ranks get *num_points = 0. */
+int apde_fuse_collective(apde_context *ctx, int variant, int use_weak_filter, float *xyz, float *bgr, int64_t max_points,
+                         int64_t *num_points);
+int apde_comm_destroy(apde_context *ctx);
 
 /* ---------------------------------------------------------------- fusion (APD.cpp:962-1227) */
 /* skip_weaks: uint8[V][P] out (host) or NULL to keep it on the device only */

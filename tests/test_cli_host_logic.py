@@ -148,3 +148,38 @@ def test_cli_two_rounds_write_pictures_per_round(mock_apd, tmp_path):
         assert [n for n in names if n.startswith("depth_")] == ["depth_3.jpg", "depth_7.jpg"]
         assert [n for n in names if n.startswith("confidence_")] == ["confidence_3.png", "confidence_7.png"]
         assert np.array_equal(_read_bin(r / "depths.bin"), _mock_maps(v, 832, 48, 8)[0])
+
+
+def test_cli_job_over_two_gpus_against_the_test_double(mock_apd, tmp_path):
+    """`apd --gpus 2`: one scene, two contexts, two host threads.  Both contexts get the whole scene (decoded once), both join
+    the job with the same id, every rank runs all passes as collective calls, each rank writes the maps / skip.png of ITS block
+    of views, the maps are gathered before fusion and rank 0 alone writes the cloud."""
+    rng = np.random.default_rng(6)
+    V, w, h = 7, 64, 48  # 7 views over 2 ranks: blocks of 4 and 3
+    d = tmp_path / "scan"
+    _make_folder(d, V, w, h, rng, labels_for={1})
+    out = subprocess.run([mock_apd, "-d", str(d), "--gpus", "2", "--gpu_index", "3", "--dataset", "TaT_i"], capture_output=True, text=True,
+                         env=dict(os.environ, APDE_NO_SHOW="1"))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    log = out.stdout.splitlines()
+    assert "MOCK create 0 device 3" in log and "MOCK create 1 device 4" in log
+    assert len([l for l in log if l.startswith("MOCK view")]) == V and len([l for l in log if l.startswith("MOCK ctx1+ view")]) == V
+    assert "MOCK comm_init ctx 0 rank 0 of 2" in log and "MOCK comm_init ctx 1 rank 1 of 2" in log
+    for r in (0, 1):
+        assert [l for l in log if l.startswith("MOCK rank %d of 2 pass" % r)] == ["MOCK rank %d of 2 pass %d" % (r, p) for p in range(4)]
+        ex = [l for l in log if l.startswith("MOCK rank %d exchange" % r)]
+        assert ex == ["MOCK rank %d exchange %d" % (r, k) for k in (1, 2, 3, 4)]  # normal, weak, confidence; skip after the filter
+        assert "MOCK rank %d mark %dx%d" % (r, w, h) in log
+    assert "There are 7 problems needed to be processed! (2 GPUs)" in log and "All done" in log
+    for v in range(V):
+        r = d / "APD" / ("%08d" % v)
+        depth, weak, conf = _mock_maps(v, w, h, 4)
+        assert np.array_equal(_read_bin(r / "depths.bin"), depth) and np.array_equal(_read_bin(r / "weak.bin"), weak)
+        import cv2
+        skip = cv2.imread(str(r / "skip.png"), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(skip.ravel(), np.where((np.arange(w * h) + v) % 7 == 0, 255, 0).astype(np.uint8))
+    head = open(d / "APD" / "APD.ply", "rb").read(300)
+    assert b"element vertex 6" in head  # RunFusion_TAT_I (variant 1) on rank 0 only
+    # the exports that step through a pass view by view are single-GPU
+    out2 = subprocess.run([mock_apd, "-d", str(d), "--gpus", "2", "--export_anchor", "true"], capture_output=True, text=True)
+    assert out2.returncode != 0 and "without --gpus" in out2.stdout

@@ -199,18 +199,19 @@ def test_rng_free_kernels_equal_the_reference_kernels(ctx, office_state):
         st0 = pull_state(ctx)
         ctx.problem_stage(STAGE.INIT)
         st = pull_state(ctx)
-        r = ref.run_stages(imgs, cams, prm, ["init"], _ref_state(st0), depths=depths, anchors=st0["anchors"] if use_apd else None)
-        strong = st0["weak_info"] != 0 if use_apd else np.ones(st0["weak_info"].shape, bool)
+        # With use_APD the deformable cost of a WEAK pixel reads selected_views of its anchors while the reference's kernel is
+        # still writing them (a data race, DESIGN.md "Determinism").  Anchors are STRONG pixels, whose masks depend on nothing
+        # else, so handing the reference kernel the FINAL masks as its input state makes every interleaving read the same
+        # values -- the serialisation the product implements with its two-phase launch.
+        rs0 = _ref_state(st0)
+        rs0["selected_views"] = st["selected_views"]
+        r = ref.run_stages(imgs, cams, prm, ["init"], rs0, depths=depths, anchors=st0["anchors"] if use_apd else None)
         _, eqp = _report("%s init planes" % tag, st["planes"], r["planes"])
         assert eqp.all(), tag
-        d, eq = _report("%s init costs (NCC-Old pixels)" % tag, st["costs"][strong], r["costs"][strong])
+        d, eq = _report("%s init costs (%d WEAK pixels with the deformable cost)" % (tag, (st0["weak_info"] == 0).sum() if use_apd else 0),
+                        st["costs"], r["costs"])
         assert eq.all(), tag
-        assert np.array_equal(st["selected_views"][strong], r["selected_views"][strong]), tag
-        if use_apd and (~strong).any():
-            # WEAK pixels: the deformable cost reads selected_views of its anchors while the reference's kernel is still writing
-            # them (a data race, DESIGN.md "Determinism"); the product's two-phase order is one of the allowed outcomes
-            d, eq = _report("%s init costs (NCC-New pixels, racy in the reference)" % tag, st["costs"][~strong], r["costs"][~strong])
-            assert (d <= 1e-4).mean() >= 0.999
+        assert np.array_equal(st["selected_views"], r["selected_views"]), tag
         # three propagation iterations of the product give a realistic state for the tail kernels
         for it in range(3):
             ctx.problem_stage(STAGE.PROP_STRONG, it, 0)

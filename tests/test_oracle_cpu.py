@@ -360,105 +360,56 @@ def test_view_sharding_partition():
             assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
 
 
-def _gloo_worker(rank, world, port, V, q):
-    import torch
+def _gloo_job_worker(rank, world, port, V, q):
+    """host logic of a multi-GPU job on CPU (gloo, world_size 2): the rendezvous hands the SAME 128-byte id to every rank, every
+    rank joins with its own rank / world, the schedule and the fusion are issued as collective calls in the same order"""
     import torch.distributed as dist
-    from apde_mvs_b200.sharding import exchange_depth_maps, shard
+    from apde_mvs_b200.binding import COMM_ID_BYTES, Schedule
+    from apde_mvs_b200.distributed import Job
+    from apde_mvs_b200.sharding import shard
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    P = 64
-    pool = torch.zeros(V, P)
-    first, count = shard(V, world, rank)
-    for v in range(first, first + count):
-        pool[v] = v + 1.0  # "fresh depth maps" of the owned views
-    exchange_depth_maps(dist, pool, V, world)
-    ok = bool(torch.equal(pool, (torch.arange(V, dtype=torch.float32) + 1)[:, None].expand(V, P)))
-    q.put((rank, ok))
-    dist.destroy_process_group()
 
+    class FakeCtx:  # stands in for binding.Context: records what the launcher-side logic asks of the library
+        made = 0
 
-@pytest.mark.parametrize("V", [8, 7])
-def test_depth_map_exchange_gloo_world2(V):
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29600 + V
-    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, V, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=120) for _ in procs]
-    for p in procs:
-        p.join(60)
-    assert all(ok for _, ok in res), res
-
-
-def _gloo_fusion_worker(rank, world, port, V, q):
-    """DistributedScene host logic on CPU tensors: a fake context whose 'kernels' write recognisable values"""
-    import torch
-    import torch.distributed as dist
-    from apde_mvs_b200.binding import POOL
-    from apde_mvs_b200.distributed import DistributedScene
-    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    P = 48
-
-    class FakeCtx:
         def __init__(self):
-            self.V = V
-            self.pools = {POOL.DEPTH: torch.zeros(V, P), POOL.NORMAL: torch.zeros(V, 3 * P), POOL.WEAK: torch.zeros(V, P, dtype=torch.uint8),
-                          POOL.CONFIDENCE: torch.zeros(V, P, dtype=torch.uint8), POOL.SKIP: torch.zeros(V, P, dtype=torch.uint8)}
             self.log = []
+
+        @staticmethod
+        def comm_create_id():
+            FakeCtx.made += 1
+            return bytes((7 * i + 3) % 256 for i in range(COMM_ID_BYTES))
+
+        def comm_init(self, comm_id, r, w):
+            self.log.append(("init", bytes(comm_id), r, w))
+
+        def comm_info(self):
+            f, c = shard(V, world, rank)
+            return rank, world, f, c
 
         def num_passes(self, sched):
             return 3
 
         def run_schedule_pass(self, sched, p, t):
-            assert sched.jacobi == 1
-            for v in range(sched.first_view, sched.first_view + sched.num_views_local):
-                # a pass may only read depth maps of the PREVIOUS pass from other views: they must all be there
-                if p > 0:
-                    assert torch.all(self.pools[POOL.DEPTH][:, 0] == torch.arange(V) + 100.0 * (p - 1) + 1), (p, self.pools[POOL.DEPTH][:, 0])
-            for v in range(sched.first_view, sched.first_view + sched.num_views_local):
-                self.pools[POOL.DEPTH][v] = v + 100.0 * p + 1
-                self.pools[POOL.NORMAL][v] = -(v + 1.0)
-                self.pools[POOL.WEAK][v] = v + 1
-                self.pools[POOL.CONFIDENCE][v] = 2 * v + 1
+            assert sched.num_views_local == 0  # the library deals the views out itself
             self.log.append("pass%d" % p)
 
-        def view_dims(self, v):
-            return (8, 6)
+        def fuse_collective(self, weak_filter, variant=0):
+            self.log.append("fuse%d%d" % (int(weak_filter), variant))
+            return ("xyz", "bgr") if rank == 0 else (None, None)
 
-        def views_mark_maps(self, w, h):
-            self.log.append("mark%dx%d" % (w, h))
-
-        def weak_vis_filter_range(self, first, count):
-            # needs every view's maps
-            assert torch.all(self.pools[POOL.WEAK][:, 0] == torch.arange(V, dtype=torch.uint8) + 1)
-            for v in range(first, first + count):
-                self.pools[POOL.SKIP][v] = 10 + v
-            self.log.append("filter%d+%d" % (first, count))
-
-        def fuse(self, use_weak_filter, variant=0):
-            assert use_weak_filter == 2  # keep the gathered skip maps
-            assert torch.all(self.pools[POOL.SKIP][:, 0] == torch.arange(V, dtype=torch.uint8) + 10)
-            assert torch.all(self.pools[POOL.NORMAL][:, 0] == -(torch.arange(V) + 1.0))
-            assert torch.all(self.pools[POOL.CONFIDENCE][:, 0] == 2 * torch.arange(V, dtype=torch.uint8) + 1)
-            self.log.append("fuse")
-            return "xyz", "bgr"
-
-    class CpuScene(DistributedScene):
-        def pool_tensor(self, which):
-            return self.ctx.pools[which]
-
-    from apde_mvs_b200.binding import Schedule
-    ctx = FakeCtx()
-    ds = CpuScene(ctx, dist, "cpu")
+    ok = True
     try:
-        ds.run_schedule(Schedule())
-        xyz, bgr = ds.fuse(True)
-        ok = (xyz == "xyz") if rank == 0 else (xyz is None)
-        ok = ok and ctx.log[:3] == ["pass0", "pass1", "pass2"] and ctx.log[3] == "mark8x6" and ctx.log[4].startswith("filter")
-        ok = ok and (("fuse" in ctx.log) == (rank == 0))
+        ctx = FakeCtx()
+        job = Job(ctx, dist)
+        job.run_schedule(Schedule())
+        xyz, _ = job.fuse(True, variant=1)
+        want_id = bytes((7 * i + 3) % 256 for i in range(COMM_ID_BYTES))
+        ok = ctx.log[0] == ("init", want_id, rank, world) and ctx.log[1:] == ["pass0", "pass1", "pass2", "fuse11"]
+        ok = ok and FakeCtx.made == (1 if rank == 0 else 0)  # only rank 0 creates the id
+        ok = ok and (job.first, job.count) == shard(V, world, rank)
+        ok = ok and ((xyz == "xyz") if rank == 0 else (xyz is None))
     except AssertionError as e:  # report instead of hanging the peer
         ok = False
         print("rank %d: %r" % (rank, e))
@@ -467,16 +418,32 @@ def _gloo_fusion_worker(rank, world, port, V, q):
 
 
 @pytest.mark.parametrize("V", [6, 5])
-def test_distributed_fusion_host_logic_gloo_world2(V):
-    """per-pass depth exchange, then normal/weak/confidence gather, sharded WeakVisFilter, skip gather, rank-0 fusion"""
+def test_multi_gpu_job_host_logic_gloo_world2(V):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29650 + V
-    procs = [ctx.Process(target=_gloo_fusion_worker, args=(r, 2, port, V, q)) for r in range(2)]
+    procs = [ctx.Process(target=_gloo_job_worker, args=(r, 2, port, V, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
     for p in procs:
         p.join(60)
     assert all(ok for _, ok in res), res
+
+
+def test_view_blocks_of_the_library_match_the_host_mirror(apde_lib):
+    """apde_comm_block_of (what the NCCL exchange inside libapde uses) == sharding.shard, and the blocks tile [0, V)"""
+    from apde_mvs_b200.sharding import shard
+    for V in (0, 1, 5, 7, 26, 88, 300):
+        for world in (1, 2, 3, 4, 8):
+            nxt = 0
+            for rank in range(world):
+                f, c = C.c_int(), C.c_int()
+                assert apde_lib.apde_comm_block_of(V, world, rank, C.byref(f), C.byref(c)) == 0
+                assert (f.value, c.value) == shard(V, world, rank)
+                assert f.value == nxt
+                nxt += c.value
+            assert nxt == V
+    f, c = C.c_int(), C.c_int()
+    assert apde_lib.apde_comm_block_of(4, 2, 2, C.byref(f), C.byref(c)) != 0  # rank out of range
