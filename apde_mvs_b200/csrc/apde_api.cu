@@ -147,6 +147,9 @@ int apde_scene_begin(apde_context *c, int num_views, int width, int height) {
         for (auto &v : c->views) {
             v.mw = v.mh = v.dw = v.dh = 0; v.has_conf = false; v.src.clear();
             CU(cudaMemsetAsync(v.d_conf, 0, (size_t)c->W * c->H, c->stream));
+            // nothing of the previous scene may leak into this one: label maps and colour images are per scene
+            cudaFree(v.d_sa); v.d_sa = nullptr; v.saw = v.sah = 0;
+            cudaFree(v.d_bgr); v.d_bgr = nullptr;
         }
         for (auto &L : c->levels) L.stale = true;
         c->level_scale = 0;
@@ -162,7 +165,9 @@ int apde_scene_begin(apde_context *c, int num_views, int width, int height) {
     CU(cudaMalloc(&c->d_normal_pool, (size_t)num_views * P * 3 * sizeof(float)));
     CU(cudaMalloc(&c->d_weak_pool, (size_t)num_views * P));
     CU(cudaMalloc(&c->d_conf_pool, (size_t)num_views * P));
-    CU(cudaMemset(c->d_conf_pool, 0, (size_t)num_views * P));  // no confidence map exists before the first geometric / APD pass (main.cpp:187-190)
+    // no confidence map exists before the first geometric / APD pass (main.cpp:187-190).  Everything is ordered on c->stream: it is
+    // a non-blocking stream, which the legacy default stream does not synchronise with
+    CU(cudaMemsetAsync(c->d_conf_pool, 0, (size_t)num_views * P, c->stream));
     for (int i = 0; i < num_views; ++i) {
         ViewStore &v = c->views[i];
         CU(cudaMalloc(&v.d_gray, P));
@@ -186,7 +191,14 @@ int apde_scene_set_view(apde_context *c, int view, const uint8_t *gray, const ui
     if (bgr) {
         if (!v.d_bgr) CU(cudaMalloc(&v.d_bgr, P * 3));
         CU(cudaMemcpyAsync(v.d_bgr, bgr, P * 3, cudaMemcpyHostToDevice, c->stream));
+    } else if (v.d_bgr) {  // a view without colours must not keep an earlier image's
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(v.d_bgr);
+        v.d_bgr = nullptr;
     }
+    // the pyramid levels derived from the previous image of this view are stale (images may be replaced on a committed scene)
+    for (auto &L : c->levels) L.stale = true;
+    c->level_scale = 0;
     v.cam = *cam;
     v.cam.width = c->W;
     v.cam.height = c->H;
@@ -352,11 +364,11 @@ int apde_view_download(apde_context *c, int view, float *depth, float *normal, u
     if (height) *height = v.mh;
     const size_t P = (size_t)v.mw * v.mh, Pfull = (size_t)c->W * c->H;
     if (P == 0) return APDE_OK;
+    if (depth) CU(cudaMemcpyAsync(depth, c->d_depth_pool[c->cur] + (size_t)view * Pfull, P * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (normal) CU(cudaMemcpyAsync(normal, v.d_normal, P * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (weak) CU(cudaMemcpyAsync(weak, v.d_weak, P, cudaMemcpyDeviceToHost, c->stream));
+    if (conf) CU(cudaMemcpyAsync(conf, v.d_conf, P, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (depth) CU(cudaMemcpy(depth, c->d_depth_pool[c->cur] + (size_t)view * Pfull, P * sizeof(float), cudaMemcpyDeviceToHost));
-    if (normal) CU(cudaMemcpy(normal, v.d_normal, P * 3 * sizeof(float), cudaMemcpyDeviceToHost));
-    if (weak) CU(cudaMemcpy(weak, v.d_weak, P, cudaMemcpyDeviceToHost));
-    if (conf) CU(cudaMemcpy(conf, v.d_conf, P, cudaMemcpyDeviceToHost));
     return APDE_OK;
 }
 
@@ -367,11 +379,13 @@ int apde_view_upload(apde_context *c, int view, const float *depth, const float 
     CU(cudaSetDevice(c->device));
     ViewStore &v = c->views[view];
     const size_t P = (size_t)width * height, Pfull = (size_t)c->W * c->H;
+    // on c->stream (non-blocking: a legacy-stream copy from pageable memory is not ordered against it), then synchronised so that
+    // the caller's buffers may be re-used at once
+    if (depth) CU(cudaMemcpyAsync(c->d_depth_pool[c->cur] + (size_t)view * Pfull, depth, P * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (normal) CU(cudaMemcpyAsync(v.d_normal, normal, P * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (weak) CU(cudaMemcpyAsync(v.d_weak, weak, P, cudaMemcpyHostToDevice, c->stream));
+    if (conf) { CU(cudaMemcpyAsync(v.d_conf, conf, P, cudaMemcpyHostToDevice, c->stream)); v.has_conf = true; }
     CU(cudaStreamSynchronize(c->stream));
-    if (depth) CU(cudaMemcpy(c->d_depth_pool[c->cur] + (size_t)view * Pfull, depth, P * sizeof(float), cudaMemcpyHostToDevice));
-    if (normal) CU(cudaMemcpy(v.d_normal, normal, P * 3 * sizeof(float), cudaMemcpyHostToDevice));
-    if (weak) CU(cudaMemcpy(v.d_weak, weak, P, cudaMemcpyHostToDevice));
-    if (conf) { CU(cudaMemcpy(v.d_conf, conf, P, cudaMemcpyHostToDevice)); v.has_conf = true; }
     v.mw = width; v.mh = height;
     if (depth) { v.dw = width; v.dh = height; }
     return APDE_OK;

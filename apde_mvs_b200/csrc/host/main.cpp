@@ -18,6 +18,7 @@ struct Args {
     int gpu_index = 0;
     int gpus = 1;               // extension: one scene over this many GPUs (gpu_index, gpu_index + 1, ...), NCCL between them
     std::vector<int> gpu_list;  // extension: ... or over exactly these devices
+    bool jacobi = false;        // extension: every view reads the PREVIOUS pass's maps of its neighbours (what a multi-GPU job does)
     bool only_fuse = false, no_fuse = false, memory_cache = true, use_sa = true, use_impetus = true, weak_filter = true, flush = false,
          export_anchor = false, export_curve = false, export_color = true;
 };
@@ -27,7 +28,9 @@ static void usage() {
                  "  -D [ --dataset ] arg (=DTU)  DTU, ETH3D, TaT_a, TaT_i, General\n  -f [ --only_fuse ] arg (=0)\n  -F [ --no_fuse ] arg (=0)\n"
                  "  -m [ --memory_cache ] arg (=1)\n  -s [ --use_sa ] arg (=1)\n  -i [ --use_impetus ] arg (=1)\n  -w [ --weak_filter ] arg (=1)\n"
                  "  --flush arg (=0)\n  -n [ --export_anchor ] arg (=0)\n  -r [ --export_curve ] arg (=0)\n  -c [ --export_color ] arg (=1)\n  -h [ --help ]\n"
-                 "  --gpus arg (=1)            one scene over N GPUs (gpu_index .. gpu_index + N - 1)\n  --gpu_list arg             ... or over the listed devices, e.g. 0,2,3\n";
+                 "  --gpus arg (=1)            one scene over N GPUs (gpu_index .. gpu_index + N - 1)\n  --gpu_list arg             ... or over the listed devices, e.g. 0,2,3\n"
+                 "  --view_order arg (=reference)  reference: a view sees the maps its neighbours finished earlier in the same pass (main.cpp:309,336);\n"
+                 "                             jacobi: only those of the previous pass (always so with --gpus > 1)\n";
 }
 static bool to_bool(const std::string &v) { return v == "1" || v == "true" || v == "True" || v == "yes" || v == "on"; }
 
@@ -50,6 +53,7 @@ static Args parse(int argc, char **argv) {
         else if (k == "--gpu_index") a.gpu_index = atoi(v.c_str());
         else if (k == "--dataset") a.dataset = v;
         else if (k == "--gpus") a.gpus = atoi(v.c_str());
+        else if (k == "--view_order") a.jacobi = (v == "jacobi");
         else if (k == "--gpu_list") {
             std::stringstream ss(v);
             std::string tok;
@@ -285,6 +289,7 @@ int main(int argc, char **argv) {
         apde_schedule sched;
         apde_schedule_default(&sched);
         sched.use_impetus = a.use_impetus;
+        sched.jacobi = a.jacobi ? 1 : 0;
         sched.use_sa = a.use_sa;  // label maps of <dense>/sa_masks/ (read by SceneSession), main.cpp:324
         if (a.use_sa && s->num_sa_masks == 0) std::cout << "Can't find sa mask folder: " << (path(a.dense_folder) / "sa_masks") << std::endl;
         else if (a.use_sa) std::cout << "sa masks: " << s->num_sa_masks << " of " << s->problems.size() << " views" << std::endl;
