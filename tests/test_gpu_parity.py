@@ -1,10 +1,13 @@
 """GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on identical inputs.
 
 Tolerances (BASELINE.json north_star): integer / indexing work bit-exact; per-hypothesis costs within 1e-4 absolute;
-depth maps >= 99 % of pixels within 1 % relative depth.  Cost parity is stated as a distribution because source
-coordinates land on the texture unit's 1/256-texel weight grid: a 1-ulp difference in the fp32 homography moves a few
-of the 36 samples to the neighbouring weight bucket (the reference, recompiled with a different FMA contraction,
-shows the same spread; see DESIGN.md "noise floor").
+depth maps >= 99 % of pixels within 1 % relative depth.
+
+Product and oracle both follow the reference build's operation order (profiles/r02_reference_sass_arithmetic.md).  The
+product equals the REFERENCE BINARY bit for bit (tests/test_gpu_reference_pins.py).  Against the CPU oracle one difference is
+left: the GPU's MUFU.RCP / MUFU.SQRT are table look-ups within 1 ulp of the correctly rounded values the oracle uses, and a
+1-ulp coordinate difference occasionally moves a sample to the neighbouring 1/256 weight bucket of the texture unit.  The
+bars below sit just under what was measured on B200 in round 2 (gpurun_out/r02_gputests_s.log -> profiles/).
 """
 import numpy as np
 import pytest
@@ -70,8 +73,8 @@ def test_ncc_old_cost_parity(loaded, plane_scene):
     want = pb.eval_costs(tuples, planes, 0)
     d = np.abs(got - want)
     _report("ncc_old vs oracle(8-bit weights)", d)
-    assert (d <= 1e-4).mean() >= 0.99
-    assert d.max() <= 5e-3
+    assert (d <= 1e-4).mean() >= 0.999  # measured 0.99950, max 3.1e-4
+    assert d.max() <= 1e-3
     # the exact-fp32 bilinear model must be clearly worse: the texture unit quantises its weights
     pb0 = oracle_from_ctx(ctx, SEED, 2, tex_mode=0)
     d0 = np.abs(got - pb0.eval_costs(tuples, planes, 0))
@@ -95,10 +98,10 @@ def test_ncc_old_edge_cases(loaded):
     planes[:, 3] = rng.uniform(0.5, 9.0, 200)  # fronto-parallel planes from very near to far
     tuples = np.stack([xs, ys, vs], 1)
     got, want = ctx.eval_costs(tuples, planes, 0), pb.eval_costs(tuples, planes, 0)
-    assert ((got == 2.0) == (want == 2.0)).mean() >= 0.99
+    assert ((got == 2.0) == (want == 2.0)).mean() >= 0.995
     d = np.abs(got - want)
     _report("edge cases", d)
-    assert (d <= 1e-4).mean() >= 0.97
+    assert (d <= 1e-4).mean() >= 0.995  # measured 1.0, max 9.8e-5
 
 
 def test_init_stage_parity(loaded):
@@ -115,13 +118,13 @@ def test_init_stage_parity(loaded):
     assert np.quantile(rel, 0.999) < 1e-4
     d = np.abs(st["costs"] - pb.costs)
     _report("init costs", d)
-    assert (d <= 1e-3).mean() >= 0.99
+    assert (d <= 1e-4).mean() >= 0.998 and (d <= 1e-3).mean() >= 0.9995  # measured 0.99878 within 1e-4
     same = (st["selected_views"] == pb.selected_views).mean()
     print("selected views identical: %.5f" % same)
-    assert same >= 0.98
+    assert same >= 0.9995  # measured 1.0 (a mask can flip where two costs differ by an ulp of MUFU.RCP)
 
 
-def _compare_after_stage(ctx, pb, cam, min_same=0.97):
+def _compare_after_stage(ctx, pb, cam, min_same=0.9995):
     st = pull_state(ctx)
     dg = plane_depth(st["planes"], cam)
     do = plane_depth(pb.planes, cam)
@@ -146,7 +149,7 @@ def test_propagation_stage_parity(loaded):
     for color in (0, 1):
         ctx.problem_stage(STAGE.PROP_STRONG, 0, color)
         pb.stage("propagate_strong", 0, color)
-        st = _compare_after_stage(ctx, pb, cams[0], 0.97)
+        st = _compare_after_stage(ctx, pb, cams[0], 0.9995)  # measured 1.0
         # untouched colour must be bit-identical (in-place red/black update)
         h, w = pb.costs.shape
         gy, gx = np.mgrid[0:h, 0:w]
@@ -185,7 +188,7 @@ def test_tail_stages_parity(loaded):
     same = (st["weak_info"] == pb.weak_info).mean()
     print("DepthToWeak states identical: %.5f  hist gpu %s oracle %s" % (
         same, np.bincount(st["weak_info"].ravel(), minlength=3), np.bincount(pb.weak_info.ravel(), minlength=3)))
-    assert same >= 0.985
+    assert same >= 0.9995  # measured 0.99997 (2 of 76 800 pixels)
     push_state(ctx, pb, ("weak_info",))
     ctx.problem_stage(STAGE.LOCAL_REFINE)
     pb.stage("local_refine")
@@ -193,7 +196,7 @@ def test_tail_stages_parity(loaded):
     with np.errstate(all="ignore"):
         rel = np.abs(st["planes"][..., 3] - pb.planes[..., 3]) / np.abs(pb.planes[..., 3])
     print("LocalRefine depth within 1e-4: %.5f" % (rel <= 1e-4).mean())
-    assert (rel <= 1e-4).mean() >= 0.99
+    assert (rel <= 1e-4).mean() >= 0.9995  # measured 1.0
 
 
 def test_full_pass_depth_accuracy(loaded, plane_scene):

@@ -76,14 +76,14 @@ def test_geometric_pass_stage_parity(ctx, office):
     got, want = ctx.eval_costs(tuples, planes, 2), pb.eval_costs(tuples, planes, 2)
     d = np.abs(got - want)
     print("geom cost: max %.3g p99 %.3g frac<=1e-3 %.5f" % (d.max(), np.quantile(d, 0.99), (d <= 1e-3).mean()))
-    assert (d <= 1e-3).mean() >= 0.99  # a truncated source texel index can flip at a pixel boundary (APD.cu:885)
+    assert (d <= 1e-4).all()  # measured max 4.4e-5 (MUFU.RCP / MUFU.SQRT vs the oracle's correctly rounded values)
     push_state(ctx, pb, ("planes", "costs", "selected_views"))
     for color in (0, 1):
         ctx.problem_stage(STAGE.PROP_STRONG, 0, color)
         pb.stage("propagate_strong", 0, color)
         frac, _ = _depth_agreement(ctx, pb, cams[0])
         print("geom propagation colour %d: depth within 1%% of oracle %.5f" % (color, frac))
-        assert frac >= 0.97
+        assert frac >= 0.9995  # measured 0.99992 / 1.0
         push_state(ctx, pb, ("planes", "costs", "selected_views", "view_weight"))
     ctx.problem_stage(STAGE.DEPTH_NORMAL)
     pb.stage("depth_normal")
@@ -93,13 +93,13 @@ def test_geometric_pass_stage_parity(ctx, office):
     st = pull_state(ctx)
     same = (st["confidence"] == pb.confidence).mean()
     print("confidence identical: %.5f" % same)
-    assert same >= 0.995
+    assert same >= 0.9999  # measured 1.0
     ctx.problem_stage(STAGE.DEPTH_TO_WEAK)
     pb.stage("depth_to_weak", None)
     st = pull_state(ctx)
     same = (st["weak_info"] == pb.weak_info).mean()
     print("DepthToWeak (geom) identical: %.5f" % same)
-    assert same >= 0.98
+    assert same >= 0.9995  # measured 1.0
     ctx.problem_finish()
 
 
@@ -140,7 +140,7 @@ def test_apd_stage_parity(ctx, office):
     same_state = (st["weak_info"] == pb.weak_info).mean()
     print("anchors: reliable flags equal %.5f, anchor sets equal %.5f (same order %.5f), states equal %.5f" % (
         same_rel, same_anchor, same_order, same_state))
-    assert same_rel >= 0.99 and same_anchor >= 0.97 and same_state >= 0.995
+    assert same_rel >= 0.9995 and same_anchor >= 0.995 and same_state >= 0.9999  # measured 1.0 / 0.99876 / 1.0
     push_state(ctx, pb, ("weak_info", "weak_reliable", "anchors"))
     cams, _ = ctx.problem_cameras()
     ctx.problem_stage(STAGE.INIT)
@@ -149,7 +149,7 @@ def test_apd_stage_parity(ctx, office):
     d = np.abs(st["costs"] - pb.costs)
     wk = pb.weak_info == 0
     print("init (NCC-New on %d weak px): |dcost|<=1e-3 weak %.5f all %.5f" % (wk.sum(), (d[wk] <= 1e-3).mean(), (d <= 1e-3).mean()))
-    assert (d[wk] <= 1e-3).mean() >= 0.97
+    assert (d[wk] <= 1e-3).mean() >= 0.998  # measured 0.99915
     # deformable cost parity on the weak pixels themselves
     ys, xs = np.nonzero(wk)
     rng = np.random.default_rng(5)
@@ -160,7 +160,9 @@ def test_apd_stage_parity(ctx, office):
     got, want = ctx.eval_costs(tuples, planes, 1), pb.eval_costs(tuples, planes, 1)
     dd = np.abs(got - want)
     print("ncc_new: max %.3g p99 %.3g frac<=1e-4 %.5f" % (dd.max(), np.quantile(dd, 0.99), (dd <= 1e-4).mean()))
-    assert (dd <= 1e-4).mean() >= 0.97 and (dd <= 1e-3).mean() >= 0.99
+    # measured 0.99816 within 1e-4; the maximum (0.25) is an anchor whose projection sits on the image border: in or out decides
+    # whether a cost of 2 joins the softmax (APD.cu:500-511), and one ulp of MUFU.RCP decides that
+    assert (dd <= 1e-4).mean() >= 0.997 and (dd <= 1e-3).mean() >= 0.998
     push_state(ctx, pb, ("planes", "costs", "selected_views"))
     for color in (0, 1):
         ctx.problem_stage(STAGE.PROP_STRONG, 0, color)
@@ -171,14 +173,14 @@ def test_apd_stage_parity(ctx, office):
     st = pull_state(ctx)
     close = np.isclose(st["fit_planes"], pb.fit_planes, rtol=1e-3, atol=1e-4).all(axis=2)
     print("fit planes equal: %.5f (weak only %.5f)" % (close.mean(), close[wk].mean()))
-    assert close[wk].mean() >= 0.97
+    assert close[wk].mean() >= 0.9995  # measured 1.0
     push_state(ctx, pb, ("fit_planes",))
     for color in (0, 1):
         ctx.problem_stage(STAGE.PROP_WEAK, 0, color)
         pb.stage("propagate_weak", 0, color)
         frac, _ = _depth_agreement(ctx, pb, cams[0], wk)
         print("weak propagation colour %d: weak-pixel depth within 1%% of oracle %.5f" % (color, frac))
-        assert frac >= 0.95
+        assert frac >= 0.999  # measured 1.0 / 0.99986
         push_state(ctx, pb, ("planes", "costs", "selected_views", "view_weight"))
     ctx.problem_finish()
 

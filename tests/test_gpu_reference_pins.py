@@ -208,10 +208,13 @@ def test_rng_free_kernels_equal_the_reference_kernels(ctx, office_state):
         r = ref.run_stages(imgs, cams, prm, ["init"], rs0, depths=depths, anchors=st0["anchors"] if use_apd else None)
         _, eqp = _report("%s init planes" % tag, st["planes"], r["planes"])
         assert eqp.all(), tag
-        d, eq = _report("%s init costs (%d WEAK pixels with the deformable cost)" % (tag, (st0["weak_info"] == 0).sum() if use_apd else 0),
-                        st["costs"], r["costs"])
-        assert eq.all(), tag
-        assert np.array_equal(st["selected_views"], r["selected_views"]), tag
+        racy = (st0["weak_info"] == 0) if use_apd else np.zeros(st0["weak_info"].shape, bool)
+        d, eq = _report("%s init costs (%d WEAK pixels with the deformable cost)" % (tag, racy.sum()), st["costs"], r["costs"])
+        assert eq[~racy].all(), tag
+        assert np.array_equal(st["selected_views"][~racy], r["selected_views"][~racy]), tag
+        # ... except that the reference kernel zeroes a mask before it rebuilds it (APD.cu:755): a WEAK pixel that reads an
+        # anchor's mask inside that window sees 0.  Observed on 0 or 2 of 3514 WEAK pixels, run to run.
+        assert eq[racy].mean() >= 0.998 if racy.any() else True, tag
         # three propagation iterations of the product give a realistic state for the tail kernels
         for it in range(3):
             ctx.problem_stage(STAGE.PROP_STRONG, it, 0)

@@ -114,14 +114,14 @@ def test_ncc_old_with_labels(ctx, office_sa):
     print("ncc_old + labels vs oracle: max %.3g p99 %.3g frac<=1e-4 %.5f; the map changes %.3f of the costs" % (
         d.max(), np.quantile(d, 0.99), (d <= 1e-4).mean(), changed.mean()))
     assert changed.mean() > 0.2
-    assert (d <= 1e-4).mean() >= 0.97 and (d <= 1e-3).mean() >= 0.995
+    assert (d <= 1e-4).mean() >= 0.997 and (d <= 1e-3).mean() >= 0.998  # measured 0.99770: oracle = correctly rounded MUFU
     rc = _ref_costs(ctx, pb, lab, tuples, planes, 0)
     if rc is not None:
         dr, dro = np.abs(got - rc), np.abs(want - rc)
         print("  vs the reference's device function: ours frac<=1e-4 %.5f (max %.3g); oracle frac<=1e-4 %.5f" % (
             (dr <= 1e-4).mean(), dr.max(), (dro <= 1e-4).mean()))
-        assert (dr <= 1e-4).mean() >= 0.97 and (dr <= 1e-3).mean() >= 0.995
-        assert (dro <= 1e-4).mean() >= 0.97
+        assert np.array_equal(got, rc)  # the product equals the reference's own ComputeBilateralNCCOld bit for bit
+        assert (dro <= 1e-4).mean() >= 0.997
     ctx.view_set_sa_mask(2, None)
 
 
@@ -153,7 +153,7 @@ def test_apd_stages_with_labels(ctx, office_sa):
     print("init with labels (%d weak px): |dcost|<=1e-3 weak %.5f all %.5f; masks equal %.5f" % (
         wk.sum(), (d[wk] <= 1e-3).mean(), (d <= 1e-3).mean(), (st["selected_views"] == pb.selected_views).mean()))
     assert wk.sum() > 500
-    assert (d[wk] <= 1e-3).mean() >= 0.97 and (d <= 1e-3).mean() >= 0.98
+    assert (d[wk] <= 1e-3).mean() >= 0.999 and (d <= 1e-3).mean() >= 0.999  # measured 0.99972 / 0.99969
     push_state(ctx, pb, ("planes", "costs", "selected_views"))
     # deformable cost on the weak pixels
     ys, xs = np.nonzero(wk)
@@ -171,12 +171,12 @@ def test_apd_stages_with_labels(ctx, office_sa):
     print("ncc_new + labels: max %.3g p99 %.3g frac<=1e-4 %.5f; the map changes %.3f of the costs" % (
         dd.max(), np.quantile(dd, 0.99), (dd <= 1e-4).mean(), (np.abs(want - plain) > 1e-3).mean()))
     assert (np.abs(want - plain) > 1e-3).mean() > 0.05
-    assert (dd <= 1e-4).mean() >= 0.97 and (dd <= 1e-3).mean() >= 0.99
+    assert (dd <= 1e-4).mean() >= 0.998 and (dd <= 1e-3).mean() >= 0.998  # measured 0.99859
     rc = _ref_costs(ctx, pb, keep, tuples, planes, 1)
     if rc is not None:
         dr = np.abs(got - rc)
         print("  vs the reference's device function: frac<=1e-4 %.5f max %.3g" % ((dr <= 1e-4).mean(), dr.max()))
-        assert (dr <= 1e-4).mean() >= 0.97 and (dr <= 1e-3).mean() >= 0.99
+        assert np.array_equal(got, rc)  # bit for bit the reference's own ComputeBilateralNCCNew
 
     def depth_agreement(sel):
         s = pull_state(ctx)
@@ -190,7 +190,7 @@ def test_apd_stages_with_labels(ctx, office_sa):
         pb.stage("propagate_strong", 0, color)
         frac = depth_agreement(~wk)
         print("strong propagation colour %d: depth within 1%% of oracle %.5f" % (color, frac))
-        assert frac >= 0.96
+        assert frac >= 0.9995  # measured 1.0
         push_state(ctx, pb, ("planes", "costs", "selected_views", "view_weight"))
     ctx.problem_stage(STAGE.RANSAC_FIT, 0)
     pb.stage("ransac_fit", 0)
@@ -200,7 +200,7 @@ def test_apd_stages_with_labels(ctx, office_sa):
         pb.stage("propagate_weak", 0, color)
         frac = depth_agreement(wk)
         print("weak propagation colour %d: weak-pixel depth within 1%% of oracle %.5f" % (color, frac))
-        assert frac >= 0.95
+        assert frac >= 0.999  # measured 1.0
         push_state(ctx, pb, ("planes", "costs", "selected_views", "view_weight"))
     ctx.problem_stage(STAGE.DEPTH_NORMAL)
     pb.stage("depth_normal")
@@ -211,7 +211,7 @@ def test_apd_stages_with_labels(ctx, office_sa):
     same = (st["weak_info"] == pb.weak_info).mean()
     print("DepthToWeak with labels: states identical %.5f  hist gpu %s oracle %s" % (
         same, np.bincount(st["weak_info"].ravel(), minlength=3), np.bincount(pb.weak_info.ravel(), minlength=3)))
-    assert same >= 0.98
+    assert same >= 0.9995  # measured 0.99996
     push_state(ctx, pb, ("weak_info",))
     ctx.problem_stage(STAGE.LOCAL_REFINE)
     pb.stage("local_refine")
@@ -219,7 +219,7 @@ def test_apd_stages_with_labels(ctx, office_sa):
     with np.errstate(all="ignore"):
         rel = np.abs(st["planes"][..., 3] - pb.planes[..., 3]) / np.abs(pb.planes[..., 3])
     print("LocalRefine with labels: depth within 1e-4: %.5f" % (rel <= 1e-4).mean())
-    assert (rel <= 1e-4).mean() >= 0.99
+    assert (rel <= 1e-4).mean() >= 0.9995  # measured 1.0
     ctx.problem_finish()
     ctx.view_set_sa_mask(1, None)
 
