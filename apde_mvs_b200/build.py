@@ -27,6 +27,25 @@ def _newer(src, dst):
     return not os.path.exists(dst) or os.path.getmtime(src) > os.path.getmtime(dst)
 
 
+def build_variant(name, defines):
+    """an experimental build of the same ABI with extra -D flags, into ab/<name>/libapde.so (A/B runs: APDE_LIB=...)"""
+    out = os.path.join(HERE, "..", "ab", name)
+    os.makedirs(out, exist_ok=True)
+    procs, objs = [], []
+    for s in SOURCES:
+        obj = os.path.join(out, s.replace(".cu", ".o"))
+        objs.append(obj)
+        procs.append(subprocess.Popen([NVCC] + [f for f in FLAGS if f not in ("-Xptxas", "-v")] + PRECISE.get(s, FAST) + ["-D" + d for d in defines] +
+                                      ["-c", os.path.join(CSRC, s), "-o", obj], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE))
+    for p in procs:
+        _, err = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(err.decode()[-3000:])
+    lib = os.path.join(out, "libapde.so")
+    subprocess.check_call([NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-o", lib] + objs + ["-lcudart", "-ldl"])
+    return lib
+
+
 def build(force=False, verbose=False):
     os.makedirs(OUT_DIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]

@@ -514,7 +514,8 @@ cudaError_t launch_stage_apd(const PassK &K, int stage, int iter, int color, cud
                 if (e != cudaSuccess) return e;
                 configured = smem;
             }
-            const int tiles = tiles8x * ((ylimit + 7) / 8);
+            const int tiles = half_tiles(K, ylimit);
+            const int tiles8x = half_tiles_x(K);
             const int wpb = threads / 32;
             if (K.sa) k_prop_weak_sa<<<(tiles + wpb - 1) / wpb, threads, smem, st>>>(K, iter, color, tiles8x, ylimit);
             else k_prop_weak<<<(tiles + wpb - 1) / wpb, threads, smem, st>>>(K, iter, color, tiles8x, ylimit);

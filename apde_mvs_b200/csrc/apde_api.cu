@@ -470,6 +470,10 @@ int apde_problem_setup(apde_context *c, int ref_view, const apde_params *params,
     K.seed = seed;
     K.stream = (uint32_t)ref_view;
     K.tex = c->level_tex;
+    {  // experiment knob: shape of the implicit checkerboard tiles (3 = 8x8 default ... 6 = 64x1)
+        static const int ts = [] { const char *e = getenv("APDE_TILE_SHIFT"); const int v = e ? atoi(e) : 3; return (v >= 2 && v <= 6) ? v : 3; }();
+        K.tile_shift = ts;
+    }
     K.tex_unorm = c->level_unorm;
     K.tex_inv = c->level_inv;
     K.planes = c->d_planes; K.costs = c->d_costs; K.sel = c->d_sel; K.vw = c->d_vw; K.weak = c->d_weak; K.conf = c->d_conf;

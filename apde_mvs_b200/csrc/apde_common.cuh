@@ -8,14 +8,22 @@
 namespace apde {
 
 // -------------------------------------------------------------------------------------------- pixel mappings
-// checkerboard kernels: one warp = the 32 pixels of one colour inside an 8x8 tile (compact texture footprint).
+// checkerboard kernels: one warp = the 32 pixels of one colour inside a tile of 64 pixels, (1 << tile_shift) wide: 8x8 by
+// default (compact texture footprint), 16x4 / 32x2 / 64x1 as experiment knobs (APDE_TILE_SHIFT)
 __device__ __forceinline__ bool half_pixel(const PassK &K, int color, int tiles_x, int ylimit, int &px, int &py) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
-    py = ty * 8 + (lane >> 2);
-    px = tx * 8 + 2 * (lane & 3) + ((py + color) & 1);
+    const int sh = K.tile_shift;
+    py = ty * (64 >> sh) + (lane >> (sh - 1));
+    px = (tx << sh) + 2 * (lane & ((1 << (sh - 1)) - 1)) + ((py + color) & 1);
     return px < K.W && py < ylimit;
+}
+// grid of the implicit checkerboard mapping
+__host__ __device__ inline int half_tiles_x(const PassK &K) { return (K.W + (1 << K.tile_shift) - 1) >> K.tile_shift; }
+__host__ __device__ inline int half_tiles(const PassK &K, int ylimit) {
+    const int th = 64 >> K.tile_shift;
+    return half_tiles_x(K) * ((ylimit + th - 1) / th);
 }
 // checkerboard kernels in rounds that have WEAK pixels: threads walk a compacted pixel list (no idle lanes on the
 // other class); without a list the implicit tile mapping above is used

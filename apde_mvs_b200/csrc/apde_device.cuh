@@ -44,6 +44,7 @@ struct PassK {
     int ref_layer;
     uint32_t seed, stream;
     cudaTextureObject_t tex;  // layered images of the level (linear filter, clamp, unnormalised coordinates)
+    int tile_shift;           // implicit checkerboard mapping: a warp = the 32 same-colour pixels of a (1 << tile_shift) x (64 >> tile_shift) tile
     float tex_unorm, tex_inv; // 0: float32 texels.  > 0: integer texels read as normalised float; sample = rint(t * tex_unorm) * tex_inv
     float4 *planes;
     float *costs;

@@ -785,7 +785,8 @@ cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStr
         case APDE_STAGE_PROP_STRONG: {
             const char *v1env = getenv("APDE_STRONG_V1");  // read per launch: tests toggle it inside one process
             const bool v1 = v1env && v1env[0] == '1';
-            const int tiles = tiles8x * ((ylimit + 7) / 8);  // 32 same-colour pixels per tile == worst-case list length / 32
+            const int tiles = half_tiles(K, ylimit);  // 32 same-colour pixels per tile == worst-case list length / 32
+            const int tiles8x = half_tiles_x(K);
             if (v1 || sa) {  // per-lane refinement loop (kept for A/B measurements and as the parity twin of the compacted kernel)
                 const int threads = prop_block_threads(N);
                 const size_t smem = prop_smem_bytes(N, threads);
@@ -822,8 +823,8 @@ cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStr
             k_depth_normal<<<(W * H + 255) / 256, 256, 0, st>>>(K);
             break;
         case APDE_STAGE_MEDIAN: {
-            const int tiles = tiles8x * ((ylimit + 7) / 8);
-            k_median<<<(tiles + 3) / 4, 128, 0, st>>>(K, color, tiles8x, ylimit);
+            const int tiles = half_tiles(K, ylimit);
+            k_median<<<(tiles + 3) / 4, 128, 0, st>>>(K, color, half_tiles_x(K), ylimit);
             break;
         }
         case APDE_STAGE_DEPTH_TO_WEAK: {
