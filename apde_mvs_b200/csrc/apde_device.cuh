@@ -325,6 +325,9 @@ template <bool U>
 __device__ __forceinline__ float patch_ncc36(const PassK &K, const Homog &Hm, int layer, int px, int py,
                                              const RefPatch &rp) {
     const float *h = Hm.h;
+    // "if (var_ref < kMinVar || var_src < kMinVar) cost = cost_max" (APD.cu:655): a texture-less reference patch decides the
+    // cost on its own, whatever the 36 source samples are
+    if (rp.var < 1e-5f) return 2.0f;
     float sum_s = 0.0f, sum_ss = 0.0f, sum_rs = 0.0f;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -391,6 +394,7 @@ template <bool U>
 __device__ __forceinline__ float patch_ncc9(const PassK &K, const Homog &Hm, int layer, int ax, int ay, const float *r9,
                                             float mean_r, float var_r) {
     const float *h = Hm.h;
+    if (var_r < 1e-5f) return 2.0f;  // decided by the reference side alone (APD.cu:556)
     float ss = 0.0f, sss = 0.0f, srs = 0.0f;
     int t = 0;
 #pragma unroll
@@ -555,6 +559,7 @@ template <bool U, int ORDER>
 __device__ __forceinline__ float patch_ncc36_masked(const PassK &K, const Homog &Hm, int layer, int px, int py, const RefPatch &rp,
                                                     unsigned long long mask, float mean_r, float var_r, float inv) {
     const float *h = Hm.h;
+    if (var_r < 1e-5f) return 2.0f;  // decided by the reference side alone
     float sum_s = 0.0f, sum_ss = 0.0f, sum_rs = 0.0f;
 #pragma unroll
     for (int t = 0; t < 36; ++t) {
@@ -641,6 +646,7 @@ template <bool U>
 __device__ __forceinline__ float patch_ncc9_masked(const PassK &K, const Homog &Hm, int layer, int ax, int ay, const float *r9,
                                                    unsigned tmask, float mean_r, float var_r, float inv) {
     const float *h = Hm.h;
+    if (var_r < 1e-5f) return 2.0f;  // decided by the reference side alone
     float ss = 0.0f, sss = 0.0f, srs = 0.0f;
     int t = 0;
 #pragma unroll
