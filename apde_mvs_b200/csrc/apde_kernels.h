@@ -42,6 +42,12 @@ struct PropK {  // device view of the workspace, passed by value
     uint8_t *base3;       // [cap] weak pixels: first refinement slot after the fit-plane test (1 or 6)
     int *flags3, *colidx3, *colmap3;  // (pixel, selected view) columns: flags [N][cap], their prefix sum, column -> flat
     float *cost3;         // [11][N * cap]
+    // weak pixels, anchor-sorted pipeline: the (pixel slot, anchor slot) pairs of the half-sweep ordered by the 8x8 image tile
+    // their anchor lies in, so that a warp gathers anchor patches that are neighbours in the image
+    unsigned *akey_in, *akey;  // [8 * cap] tile number of the anchor (0xffffffff: empty slot), unsorted / sorted
+    int *aitem_in, *aitem;     // [8 * cap] pix * 8 + k, unsorted / sorted
+    float *acost1;             // [9][8][N][cap]   anchor costs of the phase-1 hypotheses (< 0: the anchor does not take part)
+    float *acost3;             // [5][8][N * cap]  anchor costs of the refinement hypotheses, by column
 };
 struct PropWorkspace {
     int cap = 0, views = 0;
@@ -54,7 +60,14 @@ struct PropWorkspace {
     uint8_t *nh = nullptr, *base3 = nullptr;
     void *scan_tmp = nullptr;
     size_t scan_bytes = 0;
+    // anchor-sorted weak pipeline (allocated on first use, sized by the weak lists actually seen)
+    unsigned *akey_in = nullptr, *akey = nullptr;
+    int *aitem_in = nullptr, *aitem = nullptr;
+    float *acost1 = nullptr, *acost3 = nullptr;
+    void *sort_tmp = nullptr;
+    size_t sort_bytes = 0, aitem_cap = 0, acost_cap = 0;
     cudaError_t reserve(int cap, int N);
+    cudaError_t reserve_anchor_pipeline(size_t stride, int N);
     void release();
 };
 cudaError_t prop_half_sweep(const PassK &K, PropWorkspace &ws, bool weak, const int *list, const int *count, int max_pixels, int iter,

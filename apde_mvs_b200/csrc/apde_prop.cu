@@ -81,6 +81,11 @@ __device__ __forceinline__ void k_prop_candidates_body(const PassK &K, const Pro
             B.anchorref[(size_t)(72 + k) * B.cap + pix] = ar.mean[k];
             B.anchorref[(size_t)(80 + k) * B.cap + pix] = ar.var[k];
             B.anchor_xy[(size_t)k * B.cap + pix] = ((int)ar.a[k].x & 0xffff) | ((int)ar.a[k].y << 16);
+            if (B.akey_in) {  // anchor-sorted pipeline: key = 8x8 tile of the anchor in row-major tile order
+                const bool on = ar.a[k].x != -1;
+                B.akey_in[(size_t)pix * 8 + k] = on ? (unsigned)((ar.a[k].y >> 3) * ((K.W + 7) >> 3) + (ar.a[k].x >> 3)) : 0xffffffffu;
+                B.aitem_in[(size_t)pix * 8 + k] = pix * 8 + k;
+            }
         }
     }
 }
@@ -479,6 +484,247 @@ __global__ void __launch_bounds__(128) k_prop_final(const __grid_constant__ Pass
     }
 }
 
+// ------------------------------------------------------------------------------------------------ weak pixels: anchor-sorted pipeline
+// The deformable cost of a WEAK pixel (ComputeBilateralNCCNew, APD.cu:448-593) is one 6x6 centre patch plus up to eight 3x3
+// anchor patches, and the anchors are STRONG pixels up to hundreds of pixels away in eight directions.  With one thread per
+// (pixel, view) column the 32 lanes of a warp gather 32 unrelated anchor patches per texture instruction: measured r01 / r02,
+// ~30 % of the gather rate on the anchors' samples, which are two thirds of all samples.  Neighbouring WEAK pixels share
+// anchors (the nearest STRONG pixels around their blob), so here a half-sweep
+//   * sorts its (pixel, anchor slot) pairs by the 8x8 image tile the anchor lies in (once per half-sweep, P0),
+//   * evaluates the CENTRE patches per (pixel, view) as before               -> centre cost, or "centre outside the image",
+//   * evaluates the ANCHOR patches per sorted (pixel, anchor) pair and view  -> one cost per (hypothesis, anchor, view, pixel),
+//   * and combines them per (pixel, view) in anchor-slot order with the reference's softmax mix.
+// Every cost is computed by the same device functions on the same operands as in ncc_new(), and combined in the same order:
+// the maps are bit-identical to the column kernels above (tools/ab_r02_weak.sh).
+constexpr float kAnchorAbsent = -1.0f;  // the anchor does not take part (outside the source image and not selected there)
+constexpr float kCentreOutside = -1.0f; // the pixel itself projects outside the source image: the cost is 2 whatever the anchors
+
+template <bool U>
+__device__ __forceinline__ float weak_centre_cost(const PassK &K, const ViewK &vk, int px, int py, const PlaneM &m, const RefPatch &rp) {
+    const Homog Hm = make_homography(K, vk, m);
+    float ptx, pty;
+    project_point(Hm.h, (float)px, (float)py, ptx, pty);
+    if (ptx >= (float)K.W || ptx < 0.0f || pty >= (float)K.H || pty < 0.0f) return kCentreOutside;
+    return patch_ncc36<U>(K, Hm, vk.layer, px, py, rp);
+}
+// one anchor of one hypothesis: APD.cu:499-512 (projection test, selected-view rule) and :514-563 (the 3x3 patch)
+template <bool U>
+__device__ __forceinline__ float weak_anchor_cost(const PassK &K, const ViewK &vk, int view_bit, short2 a, const PlaneM &m, const float *r9,
+                                                  float mean_r, float var_r) {
+    const Homog Hm = make_homography(K, vk, m);
+    float ax, ay;
+    project_point(Hm.h, (float)a.x, (float)a.y, ax, ay);
+    if (ax < 0.0f || ay < 0.0f || ax >= (float)K.W || ay >= (float)K.H)
+        return ((K.sel[a.x + a.y * K.W] >> view_bit) & 1u) ? 2.0f : kAnchorAbsent;
+    return patch_ncc9<U>(K, Hm, vk.layer, a.x, a.y, r9, mean_r, var_r);
+}
+__device__ __forceinline__ float weak_mix(float centre, const float *ac /* [8] costs by anchor slot */, const int *xy /* [8] */) {
+    if (centre < 0.0f) return 2.0f;
+    float sc[8];
+    int ns = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if ((short)(xy[k] & 0xffff) == -1) continue;
+        const float c = ac[k];
+        if (c < 0.0f) continue;
+        sc[ns++] = c;
+    }
+    return focal_mix(centre, sc, ns);
+}
+
+// phase 1, centre patches: thread = (pixel, view), the nine hypotheses in turn
+template <bool U>
+__device__ __forceinline__ void k_weak_center1_body(const PassK &K, const PropK &B) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    int px, py, center;
+    if (!prop_pixel(K, B, pix, px, py, center)) return;
+    const int N = K.N;
+    const ViewK &vk = K.v[v];
+    RefPatch rp;
+    load_ref_patch_g(B, pix, rp);
+    const unsigned flags = B.cand_flags[pix] & 0xffu;
+    unsigned n_eval = 0;
+#pragma unroll 1
+    for (int h = 0; h < kH1; ++h) {
+        float c;
+        if (h == 8 || ((flags >> h) & 1u)) {
+            const float4 pl = (h == 8) ? K.planes[center] : K.planes[B.cand_pos[(size_t)h * B.cap + pix]];
+            c = weak_centre_cost<U>(K, vk, px, py, plane_row(K, pl), rp);
+            n_eval++;
+        } else {
+            c = (h == 0 && v == 0) ? 2.0f : 0.0f;  // quirk 2 (see k_prop_eval1)
+        }
+        B.cost1[((size_t)h * N + v) * B.cap + pix] = c;
+    }
+    count_evals(K, 0, n_eval, 0);
+}
+__global__ void __launch_bounds__(128) k_weak_center1(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
+    if (K.tex_unorm > 0.0f) k_weak_center1_body<true>(K, B);
+    else k_weak_center1_body<false>(K, B);
+}
+
+// reference side of one anchor patch, gathered through the texture unit (neighbouring threads hold neighbouring anchors):
+// the texels, sums and statistics of load_anchor_ref()
+template <bool U>
+__device__ __forceinline__ void anchor_ref9(const PassK &K, short2 a, float *r9, float &mean_r, float &var_r) {
+    float sr = 0.0f, srr = 0.0f;
+    int t = 0;
+#pragma unroll
+    for (int i = -5; i <= 5; i += 5) {
+#pragma unroll
+        for (int j = -5; j <= 5; j += 5) {
+            const float r = fetch<U>(K, (float)(a.x + i) + 0.5f, (float)(a.y + j) + 0.5f, K.ref_layer);
+            r9[t++] = r;
+            sr = __fadd_rn(sr, r);
+            srr = __fmaf_rn(r, r, srr);
+        }
+    }
+    const float inv = 1.0f / 9.0f;
+    mean_r = __fmul_rn(inv, sr);
+    var_r = __fmaf_rn(inv, srr, -__fmul_rn(mean_r, mean_r));
+}
+
+// phase 1, anchor patches: thread = (sorted (pixel, anchor) pair, view)
+template <bool U>
+__device__ __forceinline__ void k_weak_anchor1_body(const PassK &K, const PropK &B, int nitems) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nitems || B.akey[idx] == 0xffffffffu) return;
+    const int v = blockIdx.y, N = K.N;
+    const int item = B.aitem[idx], pix = item >> 3, k = item & 7;
+    if (pix >= *B.count) return;
+    const int center = B.list[pix];
+    const int xy = B.anchor_xy[(size_t)k * B.cap + pix];
+    const short2 a = make_short2((short)(xy & 0xffff), (short)(xy >> 16));
+    const ViewK &vk = K.v[v];
+    float r9[9], mean_r, var_r;
+    anchor_ref9<U>(K, a, r9, mean_r, var_r);
+    const unsigned flags = B.cand_flags[pix] & 0xffu;
+#pragma unroll 1
+    for (int h = 0; h < kH1; ++h) {
+        if (!(h == 8 || ((flags >> h) & 1u))) continue;
+        const float4 pl = (h == 8) ? K.planes[center] : K.planes[B.cand_pos[(size_t)h * B.cap + pix]];
+        B.acost1[(((size_t)h * 8 + k) * N + v) * B.cap + pix] = weak_anchor_cost<U>(K, vk, v, a, plane_row(K, pl), r9, mean_r, var_r);
+    }
+}
+__global__ void __launch_bounds__(128) k_weak_anchor1(const __grid_constant__ PassK K, const __grid_constant__ PropK B, int nitems) {
+    if (K.tex_unorm > 0.0f) k_weak_anchor1_body<true>(K, B, nitems);
+    else k_weak_anchor1_body<false>(K, B, nitems);
+}
+
+// phase 1, combination: thread = (pixel, view)
+__global__ void __launch_bounds__(128) k_weak_combine1(const __grid_constant__ PassK K, const __grid_constant__ PropK B) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y, N = K.N;
+    if (pix >= *B.count) return;
+    const unsigned flags = B.cand_flags[pix] & 0xffu;
+    int xy[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xy[k] = B.anchor_xy[(size_t)k * B.cap + pix];
+#pragma unroll 1
+    for (int h = 0; h < kH1; ++h) {
+        if (!(h == 8 || ((flags >> h) & 1u))) continue;
+        float ac[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ac[k] = ((short)(xy[k] & 0xffff) == -1) ? kAnchorAbsent : B.acost1[(((size_t)h * 8 + k) * N + v) * B.cap + pix];
+        float *dst = &B.cost1[((size_t)h * N + v) * B.cap + pix];
+        *dst = weak_mix(*dst, ac, xy);
+    }
+}
+
+// refinement hypotheses of the weak pixels by column: slots [i0, i0 + nh) of B.hyp; mode 1 = the fit plane (slot 0),
+// mode 2 = the five random hypotheses that follow the outcome of the fit test (slots base3 .. base3 + 4)
+__device__ __forceinline__ void weak_slots(const PropK &B, int pix, int mode, int &i0, int &nh) {
+    i0 = 0; nh = 1;
+    if (mode == 2) { i0 = B.base3[pix]; nh = 5; }
+}
+
+template <bool U>
+__device__ __forceinline__ void k_weak_center3_body(const PassK &K, const PropK &B, int mode) {
+    extern __shared__ float smem[];
+    const ViewK *s_vk = stage_views(K, smem);
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t cap = B.cap, nflat = (size_t)K.N * cap;
+    if (col >= B.colidx3[nflat]) return;
+    const int flat = B.colmap3[col];
+    const int v = flat / (int)cap, pix = flat % (int)cap;
+    const int center = B.list[pix];
+    const int px = center % K.W, py = center / K.W;
+    RefPatch rp;
+    load_ref_patch_g(B, pix, rp);
+    int i0, nh;
+    weak_slots(B, pix, mode, i0, nh);
+    unsigned n_eval = 0;
+#pragma unroll 1
+    for (int i = i0; i < i0 + nh; ++i) {
+        const float4 tp = B.hyp[(size_t)i * cap + pix];
+        B.cost3[(size_t)i * nflat + col] = weak_centre_cost<U>(K, s_vk[v], px, py, plane_row(K, tp), rp);
+        n_eval++;
+    }
+    count_evals(K, 0, n_eval, 0);
+}
+__global__ void __launch_bounds__(128) k_weak_center3(const __grid_constant__ PassK K, const __grid_constant__ PropK B, int mode) {
+    if (K.tex_unorm > 0.0f) k_weak_center3_body<true>(K, B, mode);
+    else k_weak_center3_body<false>(K, B, mode);
+}
+
+template <bool U>
+__device__ __forceinline__ void k_weak_anchor3_body(const PassK &K, const PropK &B, int nitems, int mode) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nitems || B.akey[idx] == 0xffffffffu) return;
+    const int v = blockIdx.y;
+    const size_t cap = B.cap, nflat = (size_t)K.N * cap;
+    const int item = B.aitem[idx], pix = item >> 3, k = item & 7;
+    if (pix >= *B.count || !B.flags3[(size_t)v * cap + pix]) return;  // only the views this pixel selected have a column
+    const int col = B.colidx3[(size_t)v * cap + pix];
+    const int xy = B.anchor_xy[(size_t)k * cap + pix];
+    const short2 a = make_short2((short)(xy & 0xffff), (short)(xy >> 16));
+    const ViewK &vk = K.v[v];
+    float r9[9], mean_r, var_r;
+    anchor_ref9<U>(K, a, r9, mean_r, var_r);
+    int i0, nh;
+    weak_slots(B, pix, mode, i0, nh);
+#pragma unroll 1
+    for (int ii = 0; ii < nh; ++ii) {
+        const float4 tp = B.hyp[(size_t)(i0 + ii) * cap + pix];
+        B.acost3[((size_t)ii * 8 + k) * nflat + col] = weak_anchor_cost<U>(K, vk, v, a, plane_row(K, tp), r9, mean_r, var_r);
+    }
+}
+__global__ void __launch_bounds__(128) k_weak_anchor3(const __grid_constant__ PassK K, const __grid_constant__ PropK B, int nitems, int mode) {
+    if (K.tex_unorm > 0.0f) k_weak_anchor3_body<true>(K, B, nitems, mode);
+    else k_weak_anchor3_body<false>(K, B, nitems, mode);
+}
+
+__global__ void __launch_bounds__(128) k_weak_combine3(const __grid_constant__ PassK K, const __grid_constant__ PropK B, int mode) {
+    extern __shared__ float smem[];
+    const ViewK *s_vk = stage_views(K, smem);
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t cap = B.cap, nflat = (size_t)K.N * cap;
+    if (col >= B.colidx3[nflat]) return;
+    const int flat = B.colmap3[col];
+    const int v = flat / (int)cap, pix = flat % (int)cap;
+    const int center = B.list[pix];
+    const int px = center % K.W, py = center / K.W;
+    int xy[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xy[k] = B.anchor_xy[(size_t)k * cap + pix];
+    int i0, nh;
+    weak_slots(B, pix, mode, i0, nh);
+    const bool geom = K.geom != 0;  // weak pixels carry the geometric term whenever geom_consistency (quirk 4)
+    unsigned n_geom = 0;
+#pragma unroll 1
+    for (int ii = 0; ii < nh; ++ii) {
+        float ac[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ac[k] = ((short)(xy[k] & 0xffff) == -1) ? kAnchorAbsent : B.acost3[((size_t)ii * 8 + k) * nflat + col];
+        float *dst = &B.cost3[(size_t)(i0 + ii) * nflat + col];
+        float c = weak_mix(*dst, ac, xy);
+        if (geom) { c = c + K.geom_factor * geom_cost(K, s_vk[v], v, px, py, B.hyp[(size_t)(i0 + ii) * cap + pix]); n_geom++; }
+        *dst = c;
+    }
+    count_evals(K, 0, 0, n_geom);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 #define PCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
 
@@ -510,7 +756,37 @@ cudaError_t PropWorkspace::reserve(int cap_, int N) {
     PCU(cudaMemset(flags3, 0, (nflat + 1) * sizeof(int)));
     return cudaSuccess;
 }
+// anchor-sorted weak pipeline: buffers sized by the row stride of the half-sweep (the weak list length), grow-only
+cudaError_t PropWorkspace::reserve_anchor_pipeline(size_t stride, int N) {
+    const size_t items = stride * 8;
+    if (items > aitem_cap) {
+        cudaFree(akey_in); cudaFree(akey); cudaFree(aitem_in); cudaFree(aitem); cudaFree(sort_tmp);
+        akey_in = akey = nullptr; aitem_in = aitem = nullptr; sort_tmp = nullptr; aitem_cap = 0;
+        const size_t cap2 = items + items / 4;
+        PCU(cudaMalloc(&akey_in, cap2 * sizeof(unsigned)));
+        PCU(cudaMalloc(&akey, cap2 * sizeof(unsigned)));
+        PCU(cudaMalloc(&aitem_in, cap2 * sizeof(int)));
+        PCU(cudaMalloc(&aitem, cap2 * sizeof(int)));
+        sort_bytes = 0;
+        PCU(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, akey_in, akey, aitem_in, aitem, (int)cap2));
+        PCU(cudaMalloc(&sort_tmp, sort_bytes));
+        aitem_cap = cap2;
+    }
+    const size_t need = (size_t)(kH1 + 5) * 8 * N * stride;  // acost1 [9][8][N][stride] + acost3 [5][8][N * stride]
+    if (need > acost_cap) {
+        cudaFree(acost1);
+        acost1 = acost3 = nullptr; acost_cap = 0;
+        const size_t cap2 = need + need / 4;
+        PCU(cudaMalloc(&acost1, cap2 * sizeof(float)));
+        acost_cap = cap2;
+    }
+    acost3 = acost1 + (size_t)kH1 * 8 * N * stride;
+    return cudaSuccess;
+}
+
 void PropWorkspace::release() {
+    cudaFree(akey_in); cudaFree(akey); cudaFree(aitem_in); cudaFree(aitem); cudaFree(sort_tmp); cudaFree(acost1);
+    akey_in = akey = nullptr; aitem_in = aitem = nullptr; sort_tmp = nullptr; acost1 = acost3 = nullptr; aitem_cap = acost_cap = 0;
     cudaFree(cand_pos); cudaFree(cand_flags); cudaFree(cost1); cudaFree(plane_now); cudaFree(depth_now); cudaFree(cost_now);
     cudaFree(cost_written); cudaFree(wnorm); cudaFree(wmask); cudaFree(nh); cudaFree(hyp); cudaFree(flags3); cudaFree(colidx3);
     cudaFree(colmap3); cudaFree(cost3); cudaFree(scan_tmp); cudaFree(refpatch); cudaFree(anchorref); cudaFree(anchor_xy); cudaFree(base3);
@@ -536,14 +812,37 @@ static cudaError_t run_half_sweep(const PassK &K, PropWorkspace &ws, const int *
     }
     B.anchorref = ws.anchorref; B.anchor_xy = ws.anchor_xy; B.base3 = ws.base3;
     const int N = K.N;
+    // weak pixels without a label map: the anchor-sorted pipeline (APDE_WEAK_COLUMNS=1 keeps the column kernels: A/B and parity
+    // twin).  Its anchor costs take (9 + 5) x 8 x N floats per weak pixel; beyond 8 GB the column kernels run instead.
+    B.akey_in = B.akey = nullptr; B.aitem_in = B.aitem = nullptr; B.acost1 = B.acost3 = nullptr;
+    bool sorted = false;
+    if (WEAK && !K.sa) {
+        const char *e = getenv("APDE_WEAK_COLUMNS");
+        const size_t bytes = (size_t)(kH1 + 5) * 8 * N * B.cap * sizeof(float);
+        if (!(e && e[0] == '1') && bytes <= ((size_t)8 << 30)) {
+            PCU(ws.reserve_anchor_pipeline((size_t)B.cap, N));
+            B.akey_in = ws.akey_in; B.akey = ws.akey; B.aitem_in = ws.aitem_in; B.aitem = ws.aitem; B.acost1 = ws.acost1; B.acost3 = ws.acost3;
+            sorted = true;
+        }
+    }
+    const int nitems = max_pixels * 8;
+    const unsigned ib = (unsigned)((nitems + 127) / 128);
     const size_t nflat = (size_t)N * B.cap;
     const unsigned pb = (unsigned)((max_pixels + 127) / 128);
     const size_t vsm = sizeof(float) * views_smem_floats(N);
     if (pb == 0) return cudaSuccess;
+    if (sorted) PCU(cudaMemsetAsync(ws.akey_in, 0xff, (size_t)nitems * sizeof(unsigned), st));  // slots past the list end sort last
     k_prop_candidates<WEAK><<<pb, 128, 0, st>>>(K, B);
+    if (sorted) {
+        PCU(cub::DeviceRadixSort::SortPairs(ws.sort_tmp, ws.sort_bytes, ws.akey_in, ws.akey, ws.aitem_in, ws.aitem, nitems, 0, 32, st));
+        k_weak_center1<<<dim3(pb, N), 128, 0, st>>>(K, B);
+        k_weak_anchor1<<<dim3(ib, N), 128, 0, st>>>(K, B, nitems);
+        k_weak_combine1<<<dim3(pb, N), 128, 0, st>>>(K, B);
+        if (launches) *launches += 3;
+    }
     // problems with a segment-label map: the <SA> twins of the two evaluation kernels (labels re-read per column, the anchor
     // cache re-masked in registers; see "segment labels" in apde_device.cuh)
-    if (K.sa) k_prop_eval1<WEAK, true><<<dim3(pb, N), 128, 0, st>>>(K, B);
+    else if (K.sa) k_prop_eval1<WEAK, true><<<dim3(pb, N), 128, 0, st>>>(K, B);
     else k_prop_eval1<WEAK, false><<<dim3(pb, N), 128, 0, st>>>(K, B);
     // flags3 of pixels beyond the list (previous, longer half-sweeps) must not create columns
     PCU(cudaMemsetAsync(ws.flags3, 0, (nflat + 1) * sizeof(int), st));
@@ -562,11 +861,21 @@ static cudaError_t run_half_sweep(const PassK &K, PropWorkspace &ws, const int *
     } else {
         // the five random hypotheses of a weak pixel depend on whether its fit plane is accepted (APD.cu:1046-1067): evaluate
         // the fit plane, decide, then evaluate only the set that applies -- 6 deformable evaluations per column instead of 10
-        if (K.sa) k_prop_eval3<WEAK, true><<<cb, 128, vsm, st>>>(K, B, 1);
-        else k_prop_eval3<WEAK, false><<<cb, 128, vsm, st>>>(K, B, 1);
+        auto eval3 = [&](int mode) {
+            if (sorted) {
+                k_weak_center3<<<cb, 128, vsm, st>>>(K, B, mode);
+                k_weak_anchor3<<<dim3(ib, N), 128, 0, st>>>(K, B, nitems, mode);
+                k_weak_combine3<<<cb, 128, vsm, st>>>(K, B, mode);
+                if (launches) *launches += 2;
+            } else if (K.sa) {
+                k_prop_eval3<WEAK, true><<<cb, 128, vsm, st>>>(K, B, mode);
+            } else {
+                k_prop_eval3<WEAK, false><<<cb, 128, vsm, st>>>(K, B, mode);
+            }
+        };
+        eval3(1);
         k_prop_fit_test<<<pb, 128, 0, st>>>(K, B);
-        if (K.sa) k_prop_eval3<WEAK, true><<<cb, 128, vsm, st>>>(K, B, 2);
-        else k_prop_eval3<WEAK, false><<<cb, 128, vsm, st>>>(K, B, 2);
+        eval3(2);
         if (launches) *launches += 10;
     }
     k_prop_final<WEAK><<<pb, 128, 0, st>>>(K, B, one_round);

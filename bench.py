@@ -469,13 +469,13 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import ref_binding as ref
-    from oracle.ref_schedule import compute_round_num, run_reference_schedule
+    from oracle.ref_schedule import compute_round_num, run_reference_schedule, sample_views
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libapd_ref.so not built (needs /root/reference at build time)"}))
         return
     scene = build_scene(args, 1)
     V = len(scene.images)
-    nviews = min(args.ref_views, V) if args.ref_views > 0 else V
+    nviews = len(sample_views(V, args.ref_views))
     W, H = scene.width, scene.height
     rounds = args.rounds if args.rounds > 0 else compute_round_num(W, H)
 
@@ -499,7 +499,7 @@ def run_reference(args, rank, world):
         "data": "synthetic",
         "config": {"workload": "%s: same scene and schedule as the default arm; the reference's APD.cu rebuilt for sm_100 (reference flags) "
                                "run on the GPU; %d of %d reference views timed per step" % (args.config, nviews, V),
-                   "views_total": V, "passes_per_view": rounds * (1 + args.geom_iters)},
+                   "views_total": V, "views_timed": sample_views(V, args.ref_views), "passes_per_view": rounds * (1 + args.geom_iters)},
         "cpu_baseline": {"value": value, "unit": "ref-views/s", "kind": "reference", "cores": 1,
                          "sample": "%d of %d reference views through all %d passes per step (plus the first photometric pass of every view); "
                                    "sum of the reference's own 'RunPatchMatch time' (main.cpp:157-161)" % (nviews, V, rounds * (1 + args.geom_iters))},

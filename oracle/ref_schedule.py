@@ -33,12 +33,20 @@ def compute_round_num(width, height):
     return rounds
 
 
+def sample_views(V, nviews):
+    """`nviews` reference views spread evenly over the scene (the middle of each of nviews equal blocks); all views for 0"""
+    if nviews <= 0 or nviews >= V:
+        return list(range(V))
+    return sorted({min(V - 1, int((i + 0.5) * V / nviews)) for i in range(nviews)})
+
+
 def run_reference_schedule(scene, rounds=0, geom_iters=3, nviews=0, seed_base=0, camera_type=None, geom_factor=0.2):
     """returns (maps, patchmatch_ms): maps[v] = dict(depth, normal, weak, conf) after the last pass; patchmatch_ms = sum of
-    the reference's own 'RunPatchMatch time' over the timed views (the first `nviews`; 0 = all)."""
+    the reference's own 'RunPatchMatch time' over the timed views (`nviews` views spread over the scene, sample_views; 0 = all).
+    Every view runs the first photometric pass (the later passes of the timed views read those depth maps)."""
     import cv2
     V = len(scene.images)
-    nviews = nviews if nviews > 0 else V
+    timed = set(sample_views(V, nviews))
     W, H = scene.width, scene.height
     rounds = rounds if rounds > 0 else compute_round_num(W, H)
     fimgs = [im.astype(np.float32) for im in scene.images]
@@ -61,7 +69,9 @@ def run_reference_schedule(scene, rounds=0, geom_iters=3, nviews=0, seed_base=0,
                 p.state, p.geom_consistency, p.weak_peak_radius = (0 if i == 0 else 1), 0, 6
             else:
                 p.state, p.geom_consistency, p.weak_peak_radius = 2, 1, max(4 - 2 * j, 2)
-            for v in range(nviews if (i, j) != (0, -1) else V):  # every view needs a depth map after the first pass
+            for v in range(V):
+                if (i, j) != (0, -1) and v not in timed:  # every view needs a depth map after the first pass
+                    continue
                 ids = [v] + list(scene.pairs[v])
                 cams = []
                 for k in ids:
@@ -86,7 +96,7 @@ def run_reference_schedule(scene, rounds=0, geom_iters=3, nviews=0, seed_base=0,
                     weak, conf = rs(maps[v]["weak"]), rs(maps[v]["conf"])
                 pl, wk, cf, ms = ref.run_pass([lv_imgs[k] for k in ids], cams, p, planes, weak, conf, depths,
                                               seed=seed_base + 1000 * it + v)
-                if v < nviews:
+                if v in timed:
                     pm_ms += ms
                 depth = pl[..., 3].copy()
                 bad = (depth < p.depth_min) | (depth > p.depth_max)

@@ -175,3 +175,24 @@ def test_segment_label_kernel_variants_identical(tmp_path):
     for k in a.files:
         assert np.array_equal(a[k], b[k]), "map %s differs between the default and the thread-per-pixel kernels under labels" % k
     assert any(not np.array_equal(a[k], plain[k]) for k in a.files if k.startswith("w"))
+
+
+def test_weak_propagation_pipelines_identical(tmp_path):
+    """weak pixels: the anchor-sorted pipeline (default: anchor patches gathered by sorted (pixel, anchor) pairs, centre patches
+    and the softmax mix in separate kernels), the (pixel, view) column kernels (APDE_WEAK_COLUMNS=1) and the thread-per-pixel
+    kernel (APDE_LEGACY_PROP=1) give bit-identical maps over a two-round schedule with 30 % weak texture"""
+    import os
+    import subprocess
+    import sys
+    from helpers import ROOT
+    outs = []
+    for env_extra in ({}, {"APDE_WEAK_COLUMNS": "1"}, {"APDE_LEGACY_PROP": "1"}):
+        out = str(tmp_path / ("maps_%d.npz" % len(outs)))
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "dump_maps.py"), out, "400", "300", "5", "4", "0.3", "2"],
+                              env=dict(os.environ, **env_extra), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        outs.append(np.load(out))
+    a, b, c = outs
+    assert len(a.files) == 20 and (a["w0"] == 0).mean() > 0.05  # there are WEAK pixels
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), "map %s differs between the anchor-sorted pipeline and the column kernels" % k
+        assert np.array_equal(a[k], c[k]), "map %s differs between the anchor-sorted pipeline and the thread-per-pixel kernel" % k
