@@ -143,6 +143,7 @@ def load_library(path=None):
     lib.apde_schedule_num_passes.argtypes = [P, C.POINTER(Schedule)]
     lib.apde_schedule_pass_params.argtypes = [P, C.POINTER(Schedule), C.c_int, C.POINTER(Params), C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
     lib.apde_problem_capture_curve.argtypes = [P, C.c_int]
+    lib.apde_fuse_take_points.argtypes = [P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int64)]
     lib.apde_get_counters.argtypes = [P, C.POINTER(C.c_uint64), C.c_int]
     lib.apde_set_profiling.argtypes = [P, C.c_int]
     lib.apde_set_sweep_budget_mb.argtypes = [P, C.c_size_t]
@@ -447,24 +448,26 @@ class Context:
         rank = self.comm_info()[0]
         n = C.c_int64()
         flt = 1 if use_weak_filter else 0
-        if rank != 0:
-            self._check(self.lib.apde_fuse_collective(self._h, variant, flt, None, None, 0, C.byref(n)))
-            # ranks other than 0 join the second (filling) call of rank 0 below: its gathers are collective as well
-            self._check(self.lib.apde_fuse_collective(self._h, variant, flt, None, None, 0, C.byref(n)))
-            return None, None
+        # one collective call; rank 0's context keeps the cloud until take_points copies it out
         self._check(self.lib.apde_fuse_collective(self._h, variant, flt, None, None, 0, C.byref(n)))
-        xyz = np.zeros((n.value, 3), np.float32)
-        bgr = np.zeros((n.value, 3), np.float32)
+        if rank != 0:
+            return None, None
+        return self._take_points(n.value)
+
+    def _take_points(self, n):
+        xyz = np.zeros((n, 3), np.float32)
+        bgr = np.zeros((n, 3), np.float32)
         n2 = C.c_int64()
-        self._check(self.lib.apde_fuse_collective(self._h, variant, flt, _ptr(xyz), _ptr(bgr), n.value, C.byref(n2)))
-        return xyz[:n2.value], bgr[:n2.value]
+        self._check(self.lib.apde_fuse_take_points(self._h, _ptr(xyz), _ptr(bgr), n, C.byref(n2)))
+        assert n2.value == n
+        return xyz, bgr
 
     def fuse(self, use_weak_filter=True, max_points=None, variant=0):
         """variant 0 = RunFusion, 1 = RunFusion_TAT_I, 2 = RunFusion_TAT_A (main.cpp:277-283)"""
         n = C.c_int64()
-        if max_points is None:
+        if max_points is None:  # fusion runs once: count (the context keeps the cloud), then take
             self._check(self.lib.apde_fuse_variant(self._h, variant, int(use_weak_filter), None, None, 0, C.byref(n)))
-            max_points = n.value
+            return self._take_points(n.value)
         xyz = np.zeros((max_points, 3), np.float32)
         bgr = np.zeros((max_points, 3), np.float32)
         self._check(self.lib.apde_fuse_variant(self._h, variant, int(use_weak_filter), _ptr(xyz), _ptr(bgr), max_points,

@@ -110,6 +110,9 @@ static void free_scene(apde_context *c) {
     }
     cudaFree(c->d_skip);
     c->d_skip = nullptr;
+    std::vector<float>().swap(c->fused.xyz);
+    std::vector<float>().swap(c->fused.bgr);
+    c->fused.valid = false;
     cudaFree(c->d_sa);
     c->d_sa = nullptr;
     c->list_scratch.release();
@@ -1236,11 +1239,29 @@ int apde_fuse_variant(apde_context *c, int variant, int use_weak_filter, float *
         CU(cudaMemsetAsync(c->d_skip, 0, (size_t)c->V * P, c->stream));
     }
     uint64_t launches = 0;
+    // a count-only call keeps the cloud on the host side of the context, so that a caller who sizes its buffers from the count
+    // (apde_fuse_take_points) does not run the fusion a second time
+    c->fused.xyz.clear(); c->fused.bgr.clear(); c->fused.valid = false;
+    FusedPoints *keep = (!xyz && !bgr) ? &c->fused : nullptr;
     cudaError_t e = variant == APDE_FUSE_DEFAULT
-                        ? fusion_run(fv, mw, mh, c->d_skip, xyz, bgr, max_points, num_points, c->stream, &launches)
-                        : fusion_run_tat(fv, mw, mh, variant, c->d_skip, xyz, bgr, max_points, num_points, c->stream, &launches);
+                        ? fusion_run(fv, mw, mh, c->d_skip, xyz, bgr, max_points, num_points, c->stream, &launches, keep)
+                        : fusion_run_tat(fv, mw, mh, variant, c->d_skip, xyz, bgr, max_points, num_points, c->stream, &launches, keep);
     c->launches += launches;
-    if (e != cudaSuccess) return fail(APDE_ERR_CUDA, "fusion: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) { c->fused.xyz.clear(); c->fused.bgr.clear(); return fail(APDE_ERR_CUDA, "fusion: %s", cudaGetErrorString(e)); }
+    if (keep) keep->valid = true;
+    return APDE_OK;
+}
+
+int apde_fuse_take_points(apde_context *c, float *xyz, float *bgr, int64_t max_points, int64_t *num_points) {
+    if (!c || !num_points) return fail(APDE_ERR_ARG, "fuse_take_points: null argument");
+    if (!c->fused.valid) return fail(APDE_ERR_STATE, "fuse_take_points: no cloud kept (call apde_fuse / apde_fuse_variant / apde_fuse_collective with xyz = bgr = NULL first)");
+    const int64_t n = (int64_t)(c->fused.xyz.size() / 3), k = std::max<int64_t>(0, std::min(n, max_points));
+    if (xyz && k) memcpy(xyz, c->fused.xyz.data(), (size_t)k * 3 * sizeof(float));
+    if (bgr && k) memcpy(bgr, c->fused.bgr.data(), (size_t)k * 3 * sizeof(float));
+    *num_points = n;
+    std::vector<float>().swap(c->fused.xyz);
+    std::vector<float>().swap(c->fused.bgr);
+    c->fused.valid = false;
     return APDE_OK;
 }
 

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/apde.h"
+#include "apde_fusion.h"
 #include "apde_kernels.h"
 
 using namespace apde;  // internal header of the host-side translation units
@@ -116,6 +117,7 @@ struct apde_context {
     PropWorkspace prop;    // propagation pipeline buffers
     // fusion state
     uint8_t *d_skip = nullptr;
+    FusedPoints fused;  // cloud of the last count-only fusion call, until apde_fuse_take_points
     // multi-GPU job (apde_comm.cu): NCCL communicator of the job, this rank's block of views, the exchange stream
     struct Comm *comm = nullptr;
 };

@@ -285,10 +285,26 @@ cudaError_t fusion_weak_vis_filter(const std::vector<FusionView> &views, int w, 
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+// the points of one reference view leave the device: into the caller's buffers (as far as they reach) and / or appended to `keep`
+static cudaError_t deliver_points(const float *d_xyz, const float *d_bgr, int64_t n, int64_t total, float *xyz, float *bgr,
+                                  int64_t max_points, FusedPoints *keep) {
+    const int64_t room = std::max<int64_t>(0, std::min<int64_t>(n, max_points - total));
+    cudaError_t e = cudaSuccess;
+    if (room > 0 && xyz && (e = cudaMemcpy(xyz + 3 * total, d_xyz, (size_t)room * 3 * sizeof(float), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+    if (room > 0 && bgr && (e = cudaMemcpy(bgr + 3 * total, d_bgr, (size_t)room * 3 * sizeof(float), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+    if (keep && n > 0) {
+        keep->xyz.resize((size_t)(total + n) * 3);
+        keep->bgr.resize((size_t)(total + n) * 3);
+        if ((e = cudaMemcpy(keep->xyz.data() + 3 * total, d_xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+        if ((e = cudaMemcpy(keep->bgr.data() + 3 * total, d_bgr, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+    }
+    return e;
+}
+
 #define FCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = e_; goto done; } } while (0)
 
 cudaError_t fusion_run(const std::vector<FusionView> &views, int w, int h, const uint8_t *skip, float *xyz, float *bgr,
-                       int64_t max_points, int64_t *num_points, cudaStream_t st, uint64_t *launches) {
+                       int64_t max_points, int64_t *num_points, cudaStream_t st, uint64_t *launches, FusedPoints *keep) {
     const int V = (int)views.size(), P = w * h;
     cudaError_t err = cudaSuccess;
     FCam *d_cams = nullptr;
@@ -359,9 +375,7 @@ cudaError_t fusion_run(const std::vector<FusionView> &views, int w, int h, const
         FCU(cudaMemcpyAsync(&last_flag, d_flags + P - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         FCU(cudaStreamSynchronize(st));
         const int64_t n = (int64_t)last_off + last_flag;
-        const int64_t room = std::max<int64_t>(0, std::min<int64_t>(n, max_points - total));
-        if (room > 0 && xyz) FCU(cudaMemcpy(xyz + 3 * total, d_xyz, (size_t)room * 3 * sizeof(float), cudaMemcpyDeviceToHost));
-        if (room > 0 && bgr) FCU(cudaMemcpy(bgr + 3 * total, d_bgr, (size_t)room * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        FCU(deliver_points(d_xyz, d_bgr, n, total, xyz, bgr, max_points, keep));
         total += n;
     }
     *num_points = total;
@@ -495,7 +509,7 @@ __global__ void __launch_bounds__(128) k_tat_emit(const FCam *__restrict__ cams,
 }
 
 cudaError_t fusion_run_tat(const std::vector<FusionView> &views, int w, int h, int variant, const uint8_t *skip, float *xyz,
-                           float *bgr, int64_t max_points, int64_t *num_points, cudaStream_t st, uint64_t *launches) {
+                           float *bgr, int64_t max_points, int64_t *num_points, cudaStream_t st, uint64_t *launches, FusedPoints *keep) {
     const int V = (int)views.size(), P = w * h;
     cudaError_t err = cudaSuccess;
     FCam *d_cams = nullptr;
@@ -544,9 +558,7 @@ cudaError_t fusion_run_tat(const std::vector<FusionView> &views, int w, int h, i
         FCU(cudaMemcpyAsync(&last_flag, d_flags + P - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         FCU(cudaStreamSynchronize(st));
         const int64_t n = (int64_t)last_off + last_flag;
-        const int64_t room = std::max<int64_t>(0, std::min<int64_t>(n, max_points - total));
-        if (room > 0 && xyz) FCU(cudaMemcpy(xyz + 3 * total, d_xyz, (size_t)room * 3 * sizeof(float), cudaMemcpyDeviceToHost));
-        if (room > 0 && bgr) FCU(cudaMemcpy(bgr + 3 * total, d_bgr, (size_t)room * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        FCU(deliver_points(d_xyz, d_bgr, n, total, xyz, bgr, max_points, keep));
         total += n;
     }
     *num_points = total;

@@ -167,10 +167,11 @@ static void run_fusion_variant(int variant, const path &dense_folder, const std:
         }
         filter_mode = APDE_WEAK_FILTER_KEEP;
     }
-    check(apde_fuse_variant(s->ctx, variant, filter_mode, nullptr, nullptr, 0, &n), "apde_fuse(count)");
+    // one fusion: the count-only call keeps the cloud in the context, apde_fuse_take_points hands it over
+    check(apde_fuse_variant(s->ctx, variant, filter_mode, nullptr, nullptr, 0, &n), "apde_fuse");
     std::vector<float> xyz((size_t)n * 3), bgr((size_t)n * 3);
     int64_t n2 = 0;
-    check(apde_fuse_variant(s->ctx, variant, filter_mode, xyz.data(), bgr.data(), n, &n2), "apde_fuse");
+    check(apde_fuse_take_points(s->ctx, xyz.data(), bgr.data(), n, &n2), "apde_fuse_take_points");
     std::vector<PointList> pc((size_t)std::min(n, n2));
     for (size_t i = 0; i < pc.size(); ++i) {
         pc[i].coord = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
@@ -206,9 +207,9 @@ void RunFusionJob(SceneSession &s, int rank, int variant, const std::string &nam
     if (rank != 0) return;
     // the greedy claim order runs over all views through masks[] (APD.cpp:1149,1176,1209): one rank, over the gathered maps
     int64_t n = 0, n2 = 0;
-    check(apde_fuse_variant(c, variant, filter_mode, nullptr, nullptr, 0, &n), "apde_fuse(count)");
+    check(apde_fuse_variant(c, variant, filter_mode, nullptr, nullptr, 0, &n), "apde_fuse");
     std::vector<float> xyz((size_t)n * 3), bgr((size_t)n * 3);
-    check(apde_fuse_variant(c, variant, filter_mode, xyz.data(), bgr.data(), n, &n2), "apde_fuse");
+    check(apde_fuse_take_points(c, xyz.data(), bgr.data(), n, &n2), "apde_fuse_take_points");
     std::vector<PointList> pc((size_t)std::min(n, n2));
     for (size_t i = 0; i < pc.size(); ++i) {
         pc[i].coord = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};

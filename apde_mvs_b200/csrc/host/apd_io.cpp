@@ -28,6 +28,16 @@ bool ReadBinMat(const path &mat_path, Mat &mat) {
     int32_t version, rows, cols, type;
     in.read((char *)&version, 4); in.read((char *)&rows, 4); in.read((char *)&cols, 4); in.read((char *)&type, 4);
     if (!in || version != 1) { std::cout << "Version error: " << mat_path << std::endl; return false; }
+    // the header is untrusted input: a type the writer can produce (the four of WriteBinMat's callers, main.cpp:180-204 and
+    // APD.cu:2615-2661), and a payload that is really in the file -- before any allocation is sized from it
+    if (type != CV_8UC1 && type != CV_32SC1 && type != CV_32FC1 && type != CV_32FC3) { std::cout << "Type error: " << mat_path << std::endl; return false; }
+    if (rows < 0 || cols < 0 || rows > (1 << 16) || cols > (1 << 16)) { std::cout << "Size error: " << mat_path << std::endl; return false; }
+    const std::streampos body = in.tellg();
+    in.seekg(0, std::ios::end);
+    const std::streamoff have = in.tellg() - body;
+    in.seekg(body);
+    Mat probe(0, 0, type);
+    if ((std::streamoff)((size_t)rows * cols * probe.elem_size()) > have) { std::cout << "Size error: " << mat_path << " is truncated" << std::endl; return false; }
     mat.create(rows, cols, type);
     in.read((char *)mat.data(), (std::streamsize)mat.buf.size());
     return (bool)in;

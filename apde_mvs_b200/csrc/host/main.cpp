@@ -173,6 +173,14 @@ static bool read_maps(SceneSession &s) {  // --only_fuse: depth maps come from a
         Mat depth, normal, weak, conf;
         if (!ReadBinMat(dir / "depths.bin", depth) || !ReadBinMat(dir / "normals.bin", normal) || !ReadBinMat(dir / "weak.bin", weak) ||
             !ReadBinMat(dir / "confidence.bin", conf)) return false;
+        // the checks of RunFusion's loader (APD.cpp:1106-1119), plus the element types and the image bound the upload relies on;
+        // the reference skips such a view and fuses the rest -- here the maps of all views sit in one pool, so the run stops
+        auto bad = [&](const char *what) { std::cout << "Error: " << what << " (" << dir.string() << ")" << std::endl; return false; };
+        if (depth.type() != CV_32FC1 || normal.type() != CV_32FC3 || weak.type() != CV_8UC1 || conf.type() != CV_8UC1) return bad("unexpected element type in the maps of a previous run");
+        if (normal.cols != depth.cols || normal.rows != depth.rows) return bad("normal size is not equal to depth size");
+        if (weak.cols != depth.cols || weak.rows != depth.rows) return bad("weak size is not equal to depth size");
+        if (conf.cols != depth.cols || conf.rows != depth.rows) return bad("confidence size is not equal to depth size");
+        if (depth.cols < 1 || depth.rows < 1 || depth.cols > s.width || depth.rows > s.height) return bad("depth map is empty or larger than the image");
         if (apde_view_upload(s.ctx, (int)i, depth.ptr<float>(), normal.ptr<float>(), weak.data(), conf.data(), depth.cols, depth.rows)) return false;
     }
     return true;
@@ -261,6 +269,8 @@ static int run_job(const Args &a) {
 
 int main(int argc, char **argv) {
     Args a = parse(argc, argv);
+    // every return path below frees the contexts while the CUDA runtime is still up (not at static-destruction time)
+    struct Release { ~Release() { SceneSession::release_all(); } } release_on_exit;
     if (a.only_fuse) a.memory_cache = false;
     if (a.no_fuse) a.flush = true;
     std::cout << "========================== Config ==========================" << std::endl;

@@ -304,6 +304,11 @@ int apde_views_mark_maps(apde_context *ctx, int width, int height);
 enum apde_fuse_kind { APDE_FUSE_DEFAULT = 0, APDE_FUSE_TAT_I = 1, APDE_FUSE_TAT_A = 2 };
 int apde_fuse_variant(apde_context *ctx, int variant, int use_weak_filter, float *xyz, float *bgr, int64_t max_points,
                       int64_t *num_points);
+/* A fusion call with xyz = bgr = NULL counts the points AND keeps the cloud in host memory of the context; this call copies it
+ * out (up to max_points points; *num_points = size of the kept cloud) and releases it, so that a caller who sizes its buffers
+ * from the count runs the fusion once.  APDE_ERR_STATE when no cloud is kept (after a scene change, a fusion call with
+ * buffers, or a previous take).  After apde_fuse_collective only rank 0 holds a cloud. */
+int apde_fuse_take_points(apde_context *ctx, float *xyz, float *bgr, int64_t max_points, int64_t *num_points);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,7 @@ struct apde_context {
     int *src_count;
     int rank, world;  /* multi-GPU job: 0 of 1 until apde_comm_init */
     int id;           /* creation order: tells the contexts of a job apart in the log */
+    int kept_variant, kept_filter, kept;  /* cloud kept by a count-only fusion call */
 };
 static int g_created = 0;
 
@@ -139,13 +140,24 @@ int apde_weak_vis_filter_range(apde_context *c, int first_view, int num_views, u
 }
 int apde_comm_destroy(apde_context *c) { (void)c; return 0; }
 
+static void mock_points(int variant, int use_weak_filter, float *xyz, float *bgr, int64_t n, int64_t max_points) {
+    for (int64_t i = 0; i < n && i < max_points; ++i)
+        for (int k = 0; k < 3; ++k) { xyz[3 * i + k] = (float)(i + 0.25 * k); bgr[3 * i + k] = (float)(10 * i + k + use_weak_filter); }
+}
 int apde_fuse_variant(apde_context *c, int variant, int use_weak_filter, float *xyz, float *bgr, int64_t max_points, int64_t *num_points) {
     const int64_t n = 5 + variant;
-    (void)c;
-    if (xyz && bgr)
-        for (int64_t i = 0; i < n && i < max_points; ++i)
-            for (int k = 0; k < 3; ++k) { xyz[3 * i + k] = (float)(i + 0.25 * k); bgr[3 * i + k] = (float)(10 * i + k + use_weak_filter); }
+    printf("MOCK fusion run variant %d\n", variant);  /* the host side must run the fusion ONCE per cloud */
+    c->kept = 0;
+    if (xyz && bgr) mock_points(variant, use_weak_filter, xyz, bgr, n, max_points);
+    else { c->kept = 1; c->kept_variant = variant; c->kept_filter = use_weak_filter; }
     *num_points = n;
+    return 0;
+}
+int apde_fuse_take_points(apde_context *c, float *xyz, float *bgr, int64_t max_points, int64_t *num_points) {
+    if (!c->kept) return -1;
+    mock_points(c->kept_variant, c->kept_filter, xyz, bgr, 5 + c->kept_variant, max_points);
+    *num_points = 5 + c->kept_variant;
+    c->kept = 0;
     return 0;
 }
 int apde_fuse(apde_context *c, int use_weak_filter, float *xyz, float *bgr, int64_t max_points, int64_t *num_points) {

@@ -116,10 +116,12 @@ def test_cli_host_flow_against_the_test_double(mock_apd, tmp_path):
     assert b"element vertex 5" in head and len(body) == 5 * 15
     pts = np.frombuffer(body, np.dtype([("p", "<f4", 3), ("c", "u1", 3)]))
     assert np.allclose(pts["p"][2], [2.0, 2.25, 2.5]) and list(pts["c"][2]) == [22, 23, 24]  # use_weak_filter = KEEP (2) after the filter ran
+    assert log.count("MOCK fusion run") == 1  # count + take: the cloud is fused once, not once to count and once to fill
     # ---- --only_fuse re-reads the maps; TaT switches: geom_factor 0.05 and the other fusion variants
     out2 = subprocess.run([mock_apd, "-d", str(d), "--only_fuse", "true", "--dataset", "TaT_a"], capture_output=True, text=True)
     assert out2.returncode == 0 and "MOCK upload 18 %dx%d d00 %.6g" % (w, h, _mock_maps(18, w, h, 4)[0][0, 0]) in out2.stdout
     assert "MOCK pass" not in out2.stdout and b"element vertex 7" in open(d / "APD" / "APD.ply", "rb").read(300)
+    assert out2.stdout.count("MOCK fusion run variant 2") == 1
     for f in ("depth_3.jpg", "weak_3.png"):
         os.remove(d / "APD" / "00000000" / f)
     os.remove(d / "APD" / "APD.ply")
@@ -127,6 +129,18 @@ def test_cli_host_flow_against_the_test_double(mock_apd, tmp_path):
                           env=dict(os.environ, APDE_NO_SHOW="1"))
     assert out3.returncode == 0 and "MOCK pass 3 use_sa 0 geom_factor 0.05" in out3.stdout and "Skip fusion, all done!" in out3.stdout
     assert not (d / "APD" / "APD.ply").exists() and not (d / "APD" / "00000000" / "depth_3.jpg").exists()
+    # ---- --only_fuse validates the maps it is about to upload (APD.cpp:1106-1119 checks sizes; types and truncation as well here)
+    import struct
+    victim = d / "APD" / "00000003" / "weak.bin"
+    good = open(victim, "rb").read()
+    for bad_bytes, msg in ((struct.pack("<4i", 1, h, w - 1, 0) + bytes(h * (w - 1)), "weak size is not equal to depth size"),
+                           (struct.pack("<4i", 1, h, w, 5) + bytes(4 * h * w), "unexpected element type"),
+                           (struct.pack("<4i", 1, 1 << 15, 1 << 15, 0) + bytes(16), "is truncated"),
+                           (struct.pack("<4i", 1, -4, w, 0), "Size error")):
+        open(victim, "wb").write(bad_bytes)
+        bad = subprocess.run([mock_apd, "-d", str(d), "--only_fuse", "true"], capture_output=True, text=True)
+        assert bad.returncode != 0 and msg in bad.stdout and "MOCK fusion run" not in bad.stdout, (msg, bad.stdout[-400:])
+    open(victim, "wb").write(good)
     # ---- errors: an undecodable image stops the run with the reference's message (main.cpp:104-127)
     open(imgs[5], "wb").write(b"garbage")
     out4 = subprocess.run([mock_apd, "-d", str(d)], capture_output=True, text=True)
