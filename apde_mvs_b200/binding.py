@@ -143,7 +143,7 @@ def load_library(path=None):
     lib.apde_schedule_num_passes.argtypes = [P, C.POINTER(Schedule)]
     lib.apde_schedule_pass_params.argtypes = [P, C.POINTER(Schedule), C.c_int, C.POINTER(Params), C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
     lib.apde_problem_capture_curve.argtypes = [P, C.c_int]
-    lib.apde_fuse_take_points.argtypes = [P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int64)]
+    lib.apde_fuse_take_points.argtypes = [P, P, P, C.c_int64, C.POINTER(C.c_int64)]
     lib.apde_get_counters.argtypes = [P, C.POINTER(C.c_uint64), C.c_int]
     lib.apde_set_profiling.argtypes = [P, C.c_int]
     lib.apde_set_sweep_budget_mb.argtypes = [P, C.c_size_t]

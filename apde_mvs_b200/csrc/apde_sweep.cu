@@ -151,36 +151,53 @@ __global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ 
     const SweepDepths sd = sweep_depths(K, base_line, valid_src, origin_depth);
     const float rwn = rcp_approx(weight_normal);
     const int radius = kSweepR, n = kSweepN;
+    // The reference sums, per depth step, over the selected views in ascending order.  Here the views are the OUTER loop and
+    // the 61 steps are unrolled: every pc[i] still receives its FFMAs in ascending view order (bit-identical), but the 61
+    // (+61) loads of a view are independent and in flight together, and pc[] lives in registers (static indices only below).
     float pc[kSweepN];
-#pragma unroll 1
-    for (int pd = -radius; pd <= radius; ++pd) {
-        const float p_depth = sd.depth(pd);
-        if (p_depth < K.depth_min || p_depth > K.depth_max) { pc[pd + radius] = 2.0f; continue; }
-        float p_cost = 0.0f;
-        for (uint32_t mk = sel; mk; mk &= mk - 1) {
-            const int v = __ffs(mk) - 1;
-            const size_t o = (size_t)(pd + radius) * ncols + colidx[(size_t)v * Pb + loc];
-            float tc = ncc[o];
-            if (K.geom) tc = __fmaf_rn(K.geom_factor, geo[o], tc);
-            p_cost = __fmaf_rn((float)vw_get(w, v), tc, p_cost);  // APD.cu:2179-2181 as built
+#pragma unroll
+    for (int i = 0; i < kSweepN; ++i) pc[i] = 0.0f;
+    for (uint32_t mk = sel; mk; mk &= mk - 1) {
+        const int v = __ffs(mk) - 1;
+        const size_t c0 = (size_t)colidx[(size_t)v * Pb + loc];
+        const float wv = (float)vw_get(w, v);
+        if (K.geom) {
+#pragma unroll
+            for (int i = 0; i < kSweepN; ++i) {
+                const size_t o = (size_t)i * ncols + c0;
+                pc[i] = __fmaf_rn(wv, __fmaf_rn(K.geom_factor, geo[o], ncc[o]), pc[i]);  // APD.cu:2179-2181 as built
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kSweepN; ++i) pc[i] = __fmaf_rn(wv, ncc[(size_t)i * ncols + c0], pc[i]);
         }
-        p_cost = __fmul_rn(p_cost, rwn);
-        pc[pd + radius] = (2.0f > p_cost) ? p_cost : 2.0f;  // OpenCV MIN(2.0f, p_cost): NaN -> 2
     }
-    if (curve) for (int i = 0; i < n; ++i) curve[(size_t)idx * n + i] = pc[i];
+#pragma unroll
+    for (int i = 0; i < kSweepN; ++i) {
+        const float p_depth = sd.depth(i - radius);
+        // (steps outside the depth range were never evaluated: their slots hold stale values, replaced here)
+        const float p_cost = __fmul_rn(pc[i], rwn);
+        pc[i] = (p_depth < K.depth_min || p_depth > K.depth_max) ? 2.0f : ((2.0f > p_cost) ? p_cost : 2.0f);  // OpenCV MIN(2.0f, p_cost): NaN -> 2
+    }
+    if (curve) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) curve[(size_t)idx * n + i] = pc[i];
+    }
     unsigned long long peaks = 0ull;
     int peak_count = 0, min_peak = 0;
-    float min_cost = 2.0f;
+    float min_cost = 2.0f, cost_at_min_peak = pc[0];  // pc[min_peak] without a dynamic index
+#pragma unroll
     for (int i = 2; i < n - 2; ++i) {
         if (pc[i - 1] > pc[i] && pc[i + 1] > pc[i]) {
             peaks |= 1ull << i;
             peak_count++;
-            if (pc[i] < min_cost) { min_peak = i; min_cost = pc[i]; }
+            if (pc[i] < min_cost) { min_peak = i; min_cost = pc[i]; cost_at_min_peak = pc[i]; }
         }
     }
-    if (abs(min_peak - radius) > K.weak_peak_radius || pc[min_peak] > 0.5f) { K.weak[idx] = APDE_WEAK; return; }
-    if (peak_count == 1) { K.weak[idx] = (pc[min_peak] <= 0.15f) ? APDE_STRONG : APDE_WEAK; return; }
+    if (abs(min_peak - radius) > K.weak_peak_radius || cost_at_min_peak > 0.5f) { K.weak[idx] = APDE_WEAK; return; }
+    if (peak_count == 1) { K.weak[idx] = (cost_at_min_peak <= 0.15f) ? APDE_STRONG : APDE_WEAK; return; }
     float var = 0.0f;
+#pragma unroll
     for (int i = 2; i < n - 2; ++i)
         if (((peaks >> i) & 1ull) && i != min_peak) { const float d = pc[i] - min_cost; var += d * d; }
     var = sqrtf(var);
