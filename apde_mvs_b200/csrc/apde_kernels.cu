@@ -359,8 +359,13 @@ __device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int i
     }
     __syncwarp();
     const int pxy = (px << 16) | py;
-    // every pair evaluates the nh planes parked in plane slots 0 .. nh-1 of its owner's column and leaves the costs in cost slot [i][v]
-    auto evaluate_pairs = [&](int nh) {
+    // Two rounds over ONE instance of the evaluation code (the kernel's instruction footprint, not its arithmetic, is what a
+    // second inlined copy would cost): round 0 = the current hypothesis, round 1 = the five refinement hypotheses.  In each
+    // round every pair evaluates the nh planes parked in plane slots 0 .. nh-1 of its owner's column and leaves the costs in
+    // cost slot [i][v]; the owner lane then consumes them.
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+        const int nh = round ? 5 : 1;
 #pragma unroll 1
         for (int base = 0; base < total; base += 32) {
             const bool has = base + lane < total;
@@ -389,76 +394,71 @@ __device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int i
             }
         }
         __syncwarp();
-    };
-
-    // ---- the current hypothesis on the selected views
-    evaluate_pairs(1);
-    if (active) {
-        float acc = 0.0f;
-        for (uint32_t mk = wmask; mk; mk &= mk - 1) {
-            const int v = __ffs(mk) - 1;
-            acc += (float)vw_get(w, v) * sc[(kStrongCostSlot + v) * stride];
-        }
-        cost_now = acc / wnorm;
-        cost_written = cost_now;
-        plane_now = plane_c;
-        depth_now = depth_from_plane(K, plane_c, px, py);
-        if (cand_center >= 0) {
-            const float4 cand = K.planes[cand_center];
-            const float db = depth_from_plane(K, cand, px, py);
-            if (db >= dmin && db <= dmax && fc_min < cost_now) {
-                depth_now = db; plane_now = cand; cost_now = fc_min;
-                K.sel[center] = wmask;
-            }
-        }
-        // PlaneHypothesisRefinementStrong: all five candidates are built from the state BEFORE the loop (APD.cu:968-980)
-        const float depth_rand = rng.uniform() * (dmax - dmin) + dmin;
-        float4 cand_n[2];
-        cand_n[0] = random_normal(K, px, py, rng, depth_now);
-        const float lo = (1.0f - 0.02f) * depth_now, hi = (1.0f + 0.02f) * depth_now;
-        const float depth_pert = rng.uniform() * (hi - lo) + lo;  // the do-while can never repeat (quirk 6)
-        cand_n[1] = perturbed_normal(K, px, py, plane_now, rng, (float)(0.02 * 3.14159265358979323846));
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            float4 tp = (i == 0 || i == 4) ? plane_now : (i == 3 ? cand_n[1] : cand_n[0]);
-            const float d = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : depth_now);
-            tp.w = distance_to_origin(K, px, py, d, tp);
-            sc[(kStrongPlaneSlot + 4 * i + 0) * stride] = tp.x;
-            sc[(kStrongPlaneSlot + 4 * i + 1) * stride] = tp.y;
-            sc[(kStrongPlaneSlot + 4 * i + 2) * stride] = tp.z;
-            sc[(kStrongPlaneSlot + 4 * i + 3) * stride] = tp.w;
-        }
-    }
-    __syncwarp();
-
-    // ---- the five refinement hypotheses
-    evaluate_pairs(5);
-    if (active) {
-#pragma unroll 1
-        for (int i = 0; i < 5; ++i) {
-            const float4 tp = make_float4(sc[(kStrongPlaneSlot + 4 * i + 0) * stride], sc[(kStrongPlaneSlot + 4 * i + 1) * stride],
-                                          sc[(kStrongPlaneSlot + 4 * i + 2) * stride], sc[(kStrongPlaneSlot + 4 * i + 3) * stride]);
+        if (active && round == 0) {
+            // ---- the current hypothesis on the selected views
             float acc = 0.0f;
             for (uint32_t mk = wmask; mk; mk &= mk - 1) {
                 const int v = __ffs(mk) - 1;
-                acc += (float)vw_get(w, v) * sc[(kStrongCostSlot + i * N + v) * stride];
+                acc += (float)vw_get(w, v) * sc[(kStrongCostSlot + v) * stride];
             }
-            const float tc = acc / wnorm;
-            const float db = depth_from_plane(K, tp, px, py);
-            if (db >= dmin && db <= dmax && tc < cost_now) { depth_now = db; plane_now = tp; cost_now = tc; }
+            cost_now = acc / wnorm;
+            cost_written = cost_now;
+            plane_now = plane_c;
+            depth_now = depth_from_plane(K, plane_c, px, py);
+            if (cand_center >= 0) {
+                const float4 cand = K.planes[cand_center];
+                const float db = depth_from_plane(K, cand, px, py);
+                if (db >= dmin && db <= dmax && fc_min < cost_now) {
+                    depth_now = db; plane_now = cand; cost_now = fc_min;
+                    K.sel[center] = wmask;
+                }
+            }
+            // PlaneHypothesisRefinementStrong: all five candidates are built from the state BEFORE the loop (APD.cu:968-980)
+            const float depth_rand = rng.uniform() * (dmax - dmin) + dmin;
+            float4 cand_n[2];
+            cand_n[0] = random_normal(K, px, py, rng, depth_now);
+            const float lo = (1.0f - 0.02f) * depth_now, hi = (1.0f + 0.02f) * depth_now;
+            const float depth_pert = rng.uniform() * (hi - lo) + lo;  // the do-while can never repeat (quirk 6)
+            cand_n[1] = perturbed_normal(K, px, py, plane_now, rng, (float)(0.02 * 3.14159265358979323846));
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                float4 tp = (i == 0 || i == 4) ? plane_now : (i == 3 ? cand_n[1] : cand_n[0]);
+                const float d = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : depth_now);
+                tp.w = distance_to_origin(K, px, py, d, tp);
+                sc[(kStrongPlaneSlot + 4 * i + 0) * stride] = tp.x;
+                sc[(kStrongPlaneSlot + 4 * i + 1) * stride] = tp.y;
+                sc[(kStrongPlaneSlot + 4 * i + 2) * stride] = tp.z;
+                sc[(kStrongPlaneSlot + 4 * i + 3) * stride] = tp.w;
+            }
+        } else if (active) {
+            // ---- the five refinement hypotheses
+#pragma unroll 1
+            for (int i = 0; i < 5; ++i) {
+                const float4 tp = make_float4(sc[(kStrongPlaneSlot + 4 * i + 0) * stride], sc[(kStrongPlaneSlot + 4 * i + 1) * stride],
+                                              sc[(kStrongPlaneSlot + 4 * i + 2) * stride], sc[(kStrongPlaneSlot + 4 * i + 3) * stride]);
+                float acc = 0.0f;
+                for (uint32_t mk = wmask; mk; mk &= mk - 1) {
+                    const int v = __ffs(mk) - 1;
+                    acc += (float)vw_get(w, v) * sc[(kStrongCostSlot + i * N + v) * stride];
+                }
+                const float tc = acc / wnorm;
+                const float db = depth_from_plane(K, tp, px, py);
+                if (db >= dmin && db <= dmax && tc < cost_now) { depth_now = db; plane_now = tp; cost_now = tc; }
+            }
+            if (K.state == APDE_REFINE_INIT) {
+                // costs[center] was overwritten with the recomputed current cost before this test (quirk 5)
+                if ((double)cost_now < (double)cost_written - 0.1) { K.costs[center] = cost_now; K.planes[center] = plane_now; }
+                else K.costs[center] = cost_written;
+            } else {
+                K.costs[center] = cost_now;
+                K.planes[center] = plane_now;
+            }
         }
-        if (K.state == APDE_REFINE_INIT) {
-            // costs[center] was overwritten with the recomputed current cost before this test (quirk 5)
-            if ((double)cost_now < (double)cost_written - 0.1) { K.costs[center] = cost_now; K.planes[center] = plane_now; }
-            else K.costs[center] = cost_written;
-        } else {
-            K.costs[center] = cost_now;
-            K.planes[center] = plane_now;
-        }
+        __syncwarp();
     }
     count_evals(K, n_old, 0, n_geom);
 }
-__global__ void __launch_bounds__(128) k_prop_strong(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
+__global__ void __launch_bounds__(128, 3) k_prop_strong(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
                                                      int ylimit) {
     if (K.tex_unorm > 0.0f) k_prop_strong_compact_body<true>(K, iter, color, tiles_x, ylimit);
     else k_prop_strong_compact_body<false>(K, iter, color, tiles_x, ylimit);
