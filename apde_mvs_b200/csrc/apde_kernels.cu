@@ -256,8 +256,11 @@ __global__ void __launch_bounds__(128) k_prop_strong_sa(const __grid_constant__ 
 //
 // per-thread shared-memory column (slot * blockDim + thread):  phase 1-2: [8N] candidate costs, [N] view priors
 //                                                              phase 3  : [38] ref patch, [20] 5 planes, [5N] costs
-constexpr int kStrongRefSlot = 0, kStrongPlaneSlot = kPatch + 2, kStrongCostSlot = kPatch + 2 + 20;
-__host__ __device__ inline int strong_column_floats(int N) { return max(9 * N, kStrongCostSlot + 5 * N); }
+//   with 8-bit texels (U) the reference patch is 36 integers 0..255: parked as 9 packed words, so a column is 9N floats again
+//   (N = 10: 90 instead of 108: 28 KB more L1 for the texture path at 3 resident blocks per SM)
+constexpr int kStrongRefSlot = 0;
+__host__ __device__ constexpr int strong_ref_words(bool U) { return (U ? kPatch / 4 : kPatch) + 2; }
+__host__ __device__ inline int strong_column_floats(int N, bool U) { return max(9 * N, strong_ref_words(U) + 20 + 5 * N); }
 
 template <bool U>
 __device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int iter, int color, int tiles_x, int ylimit) {
@@ -269,7 +272,8 @@ __device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int i
     float *col0 = smem + views_smem_floats(N);                 // columns of all threads
     float *sc = col0 + threadIdx.x;                            // this thread's column
     float *sp = sc + 8 * N * stride;
-    unsigned short *items = reinterpret_cast<unsigned short *>(col0 + (size_t)strong_column_floats(N) * stride) + (size_t)warp * 32 * N;
+    constexpr int kStrongPlaneSlot = strong_ref_words(U), kStrongCostSlot = strong_ref_words(U) + 20;
+    unsigned short *items = reinterpret_cast<unsigned short *>(col0 + (size_t)strong_column_floats(N, U) * stride) + (size_t)warp * 32 * N;
 
     int px = 0, py = 0;
     bool active = half_pixel_or_list(K, color, tiles_x, ylimit, px, py);
@@ -339,10 +343,19 @@ __device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int i
 
         plane_c = K.planes[center];
         // park the reference patch and the current plane in this thread's column (the phase-1 costs are dead now)
+        if (U) {
 #pragma unroll
-        for (int k = 0; k < kPatch; ++k) sc[(kStrongRefSlot + k) * stride] = rp.r[k];
-        sc[(kStrongRefSlot + kPatch) * stride] = rp.mean;
-        sc[(kStrongRefSlot + kPatch + 1) * stride] = rp.var;
+            for (int k = 0; k < kPatch / 4; ++k) {
+                const unsigned word = (unsigned)rp.r[4 * k] | ((unsigned)rp.r[4 * k + 1] << 8) | ((unsigned)rp.r[4 * k + 2] << 16) |
+                                      ((unsigned)rp.r[4 * k + 3] << 24);
+                sc[(kStrongRefSlot + k) * stride] = __uint_as_float(word);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPatch; ++k) sc[(kStrongRefSlot + k) * stride] = rp.r[k];
+        }
+        sc[(kStrongPlaneSlot - 2) * stride] = rp.mean;
+        sc[(kStrongPlaneSlot - 1) * stride] = rp.var;
         sc[(kStrongPlaneSlot + 0) * stride] = plane_c.x;
         sc[(kStrongPlaneSlot + 1) * stride] = plane_c.y;
         sc[(kStrongPlaneSlot + 2) * stride] = plane_c.z;
@@ -376,10 +389,21 @@ __device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int i
                 const int spx = sxy >> 16, spy = sxy & 0xffff;
                 float *scol = col0 + (warp * 32 + src);
                 RefPatch rp;
+                if (U) {
 #pragma unroll
-                for (int k = 0; k < kPatch; ++k) rp.r[k] = scol[(kStrongRefSlot + k) * stride];
-                rp.mean = scol[(kStrongRefSlot + kPatch) * stride];
-                rp.var = scol[(kStrongRefSlot + kPatch + 1) * stride];
+                    for (int k = 0; k < kPatch / 4; ++k) {
+                        const unsigned word = __float_as_uint(scol[(kStrongRefSlot + k) * stride]);
+                        rp.r[4 * k] = (float)(word & 255u);
+                        rp.r[4 * k + 1] = (float)((word >> 8) & 255u);
+                        rp.r[4 * k + 2] = (float)((word >> 16) & 255u);
+                        rp.r[4 * k + 3] = (float)(word >> 24);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kPatch; ++k) rp.r[k] = scol[(kStrongRefSlot + k) * stride];
+                }
+                rp.mean = scol[(kStrongPlaneSlot - 2) * stride];
+                rp.var = scol[(kStrongPlaneSlot - 1) * stride];
                 const ViewK &vk = s_vk[v];
 #pragma unroll 1
                 for (int i = 0; i < nh; ++i) {
@@ -458,6 +482,8 @@ __device__ __forceinline__ void k_prop_strong_compact_body(const PassK &K, int i
     }
     count_evals(K, n_old, 0, n_geom);
 }
+// 3 resident blocks per SM.  Measured on B200 (r02, 1920x1080): a 4th block (128 registers, 96 B of stack, 200 KB of shared
+// memory per SM) leaves the texture path ~56 KB of L1 and costs 33 % (strong propagation 1852 -> 2456 ms per step)
 __global__ void __launch_bounds__(128, 3) k_prop_strong(const __grid_constant__ PassK K, int iter, int color, int tiles_x,
                                                      int ylimit) {
     if (K.tex_unorm > 0.0f) k_prop_strong_compact_body<true>(K, iter, color, tiles_x, ylimit);
@@ -803,7 +829,8 @@ cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStr
                 break;
             }
             // column floats + the warp's pair list (N shorts per thread)
-            auto bytes = [&](int threads) { return sizeof(float) * ((size_t)views_smem_floats(N) + (size_t)(strong_column_floats(N) + (N + 1) / 2) * threads); };
+            const bool u8 = K.tex_unorm > 0.0f;
+            auto bytes = [&](int threads) { return sizeof(float) * ((size_t)views_smem_floats(N) + (size_t)(strong_column_floats(N, u8) + (N + 1) / 2) * threads); };
             const int threads = bytes(128) <= 72 * 1024 ? 128 : (bytes(64) <= 100 * 1024 ? 64 : 32);
             const size_t smem = bytes(threads);
             static size_t configured = 0;
