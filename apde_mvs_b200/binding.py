@@ -144,6 +144,7 @@ def load_library(path=None):
     lib.apde_schedule_pass_params.argtypes = [P, C.POINTER(Schedule), C.c_int, C.POINTER(Params), C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
     lib.apde_problem_capture_curve.argtypes = [P, C.c_int]
     lib.apde_fuse_take_points.argtypes = [P, P, P, C.c_int64, C.POINTER(C.c_int64)]
+    lib.apde_get_anchor_evals.argtypes = [P, C.POINTER(C.c_uint64)]
     lib.apde_get_counters.argtypes = [P, C.POINTER(C.c_uint64), C.c_int]
     lib.apde_set_profiling.argtypes = [P, C.c_int]
     lib.apde_set_sweep_budget_mb.argtypes = [P, C.c_size_t]
@@ -376,6 +377,12 @@ class Context:
         out = (C.c_uint64 * 4)()
         self._check(self.lib.apde_get_counters(self._h, out, 1 if reset else 0))
         return [int(x) for x in out]
+
+    def anchor_evals(self):
+        """3x3 anchor patches sampled by the weak propagation since the last counter reset (9 samples each)"""
+        out = C.c_uint64(0)
+        self._check(self.lib.apde_get_anchor_evals(self._h, C.byref(out)))
+        return int(out.value)
 
     def set_sweep_budget_mb(self, mb):
         self._check(self.lib.apde_set_sweep_budget_mb(self._h, C.c_size_t(mb)))

@@ -945,6 +945,17 @@ int apde_get_counters(apde_context *c, uint64_t out[4], int reset) {
     return APDE_OK;
 }
 
+int apde_get_anchor_evals(apde_context *c, uint64_t *anchor_patches) {
+    if (!c || !anchor_patches) return fail(APDE_ERR_ARG, "get_anchor_evals: null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    unsigned long long h[kCounterWords];
+    CU(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    *anchor_patches = 0;
+    for (int s = 0; s <= kStages; ++s) *anchor_patches += h[4 * s + 3];
+    return APDE_OK;
+}
+
 int apde_depth_pool(apde_context *c, void **dev_ptr, size_t *bytes, size_t *bytes_per_view) {
     if (!c || !c->d_depth_pool[0]) return fail(APDE_ERR_STATE, "depth_pool: no scene");
     const size_t Pfull = (size_t)c->W * c->H;

@@ -803,13 +803,17 @@ __device__ __forceinline__ void vw_inc(uint4 &w, int v) {
     if (v < 8) w.x += inc; else if (v < 16) w.y += inc; else if (v < 24) w.z += inc; else w.w += inc;
 }
 
-__device__ __forceinline__ void count_evals(const PassK &K, unsigned n_old, unsigned n_new, unsigned n_geom) {
+// counters[0..2] = NCC-Old, NCC-New (centre patches), geometric evaluations; counters[3] = 3x3 anchor patches SAMPLED by the
+// anchor-sorted weak pipeline (9 samples each; the real sample count of the deformable cost: 36 * [1] + 9 * [3])
+__device__ __forceinline__ void count_evals(const PassK &K, unsigned n_old, unsigned n_new, unsigned n_geom, unsigned n_anchor = 0) {
     const unsigned m = __activemask();
     const unsigned a = __reduce_add_sync(m, n_old), b = __reduce_add_sync(m, n_new), c = __reduce_add_sync(m, n_geom);
+    const unsigned d = __reduce_add_sync(m, n_anchor);
     if ((int)(threadIdx.x & 31u) == __ffs(m) - 1) {
         if (a) atomicAdd(&K.counters[0], (unsigned long long)a);
         if (b) atomicAdd(&K.counters[1], (unsigned long long)b);
         if (c) atomicAdd(&K.counters[2], (unsigned long long)c);
+        if (d) atomicAdd(&K.counters[3], (unsigned long long)d);
     }
 }
 

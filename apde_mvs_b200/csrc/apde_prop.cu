@@ -510,12 +510,13 @@ __device__ __forceinline__ float weak_centre_cost(const PassK &K, const ViewK &v
 // one anchor of one hypothesis: APD.cu:499-512 (projection test, selected-view rule) and :514-563 (the 3x3 patch)
 template <bool U>
 __device__ __forceinline__ float weak_anchor_cost(const PassK &K, const ViewK &vk, int view_bit, short2 a, const PlaneM &m, const float *r9,
-                                                  float mean_r, float var_r) {
+                                                  float mean_r, float var_r, unsigned &n_sampled) {
     const Homog Hm = make_homography(K, vk, m);
     float ax, ay;
     project_point(Hm.h, (float)a.x, (float)a.y, ax, ay);
     if (ax < 0.0f || ay < 0.0f || ax >= (float)K.W || ay >= (float)K.H)
         return ((K.sel[a.x + a.y * K.W] >> view_bit) & 1u) ? 2.0f : kAnchorAbsent;
+    n_sampled += var_r >= 1e-5f;  // (a texture-less anchor patch decides its cost before any source sample, see patch_ncc9)
     return patch_ncc9<U>(K, Hm, vk.layer, a.x, a.y, r9, mean_r, var_r);
 }
 __device__ __forceinline__ float weak_mix(float centre, const float *ac /* [8] costs by anchor slot */, const int *xy /* [8] */) {
@@ -600,12 +601,14 @@ __device__ __forceinline__ void k_weak_anchor1_body(const PassK &K, const PropK 
     float r9[9], mean_r, var_r;
     anchor_ref9<U>(K, a, r9, mean_r, var_r);
     const unsigned flags = B.cand_flags[pix] & 0xffu;
+    unsigned n_anchor = 0;
 #pragma unroll 1
     for (int h = 0; h < kH1; ++h) {
         if (!(h == 8 || ((flags >> h) & 1u))) continue;
         const float4 pl = (h == 8) ? K.planes[center] : K.planes[B.cand_pos[(size_t)h * B.cap + pix]];
-        B.acost1[(((size_t)h * 8 + k) * N + v) * B.cap + pix] = weak_anchor_cost<U>(K, vk, v, a, plane_row(K, pl), r9, mean_r, var_r);
+        B.acost1[(((size_t)h * 8 + k) * N + v) * B.cap + pix] = weak_anchor_cost<U>(K, vk, v, a, plane_row(K, pl), r9, mean_r, var_r, n_anchor);
     }
+    count_evals(K, 0, 0, 0, n_anchor);
 }
 __global__ void __launch_bounds__(128) k_weak_anchor1(const __grid_constant__ PassK K, const __grid_constant__ PropK B, int nitems) {
     if (K.tex_unorm > 0.0f) k_weak_anchor1_body<true>(K, B, nitems);
@@ -684,11 +687,13 @@ __device__ __forceinline__ void k_weak_anchor3_body(const PassK &K, const PropK 
     anchor_ref9<U>(K, a, r9, mean_r, var_r);
     int i0, nh;
     weak_slots(B, pix, mode, i0, nh);
+    unsigned n_anchor = 0;
 #pragma unroll 1
     for (int ii = 0; ii < nh; ++ii) {
         const float4 tp = B.hyp[(size_t)(i0 + ii) * cap + pix];
-        B.acost3[((size_t)ii * 8 + k) * nflat + col] = weak_anchor_cost<U>(K, vk, v, a, plane_row(K, tp), r9, mean_r, var_r);
+        B.acost3[((size_t)ii * 8 + k) * nflat + col] = weak_anchor_cost<U>(K, vk, v, a, plane_row(K, tp), r9, mean_r, var_r, n_anchor);
     }
+    count_evals(K, 0, 0, 0, n_anchor);
 }
 __global__ void __launch_bounds__(128) k_weak_anchor3(const __grid_constant__ PassK K, const __grid_constant__ PropK B, int nitems, int mode) {
     if (K.tex_unorm > 0.0f) k_weak_anchor3_body<true>(K, B, nitems, mode);

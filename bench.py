@@ -38,8 +38,8 @@ SAMPLES_PER_EVAL = 36.0
 SAMPLES_PER_ANCHOR = 9.0  # NCC-New: 36 + 9 per valid anchor (APD.cu:521-533)
 # dram__bytes_read.sum + dram__bytes_write.sum per full-resolution launch at the headline workload, from `ncu --set full`
 # captures (profiles/): the dominant kernels are bound by the texture units, not by HBM.
-NCU_TRAFFIC = {"prop_strong": (2.6e8, "k_prop_strong", "profiles/r01_ncu_full_prop_strong_compacted.md"),
-               "depth_to_weak": (3.55e9, "k_sweep_columns", "profiles/r01_ncu_1080p_raw_summary.txt")}
+NCU_TRAFFIC = {"prop_strong": (2.16e8, "k_prop_strong", "profiles/r02_ncu_top_kernels.md"),
+               "depth_to_weak": (6.85e9, "k_sweep_columns", "profiles/r02_ncu_top_kernels.md")}
 STAGE_NAMES = ["nearest_strong", "gen_anchors", "init", "prop_strong", "ransac_fit", "prop_weak", "depth_normal", "median",
                "depth_to_weak", "confidence", "local_refine"]
 CONFIGS = {  # width, height, views per GPU, source views, rounds (0 = ComputeRoundNum), weak-texture share
@@ -262,6 +262,7 @@ def run_ours(args, rank, world, local_rank):
     ctx.set_profiling(False)
     st_ms, st_launch, st_evals = ctx.stage_stats()
     cnt = ctx.counters()
+    anchor_patches = ctx.anchor_evals()
     # device time of the steps: CUDA events on the launching stream around every pass, including the wait for the exchange
     dev_s = tm.device_ms * 1e-3
     # ---- timed region 2: end to end from host buffers
@@ -321,6 +322,11 @@ def run_ours(args, rank, world, local_rank):
     }
     i_pw = STAGE_NAMES.index("prop_weak")
     if st_launch[i_pw] and st_ms[i_pw] > 0:
+        # the deformable cost's real sample count on this rank: 36 per centre patch + 9 per anchor patch actually sampled (counted
+        # on the device by the anchor-sorted pipeline); the weak stage is the only one with deformable evaluations after init
+        roofline["prop_weak_tex_frac_counted_anchors"] = float(
+            (st_evals[i_pw, 0] * SAMPLES_PER_EVAL + st_evals[i_pw, 1] * SAMPLES_PER_EVAL + anchor_patches * SAMPLES_PER_ANCHOR) / (st_ms[i_pw] * 1e-3) / 1e9 / tex_peak)
+        roofline["anchor_patches_per_deformable_eval"] = float(anchor_patches / max(1.0, float(st_evals[i_pw, 1])))
         roofline["prop_weak_tex_frac_with_8_anchors"] = float(
             (st_evals[i_pw, 0] * SAMPLES_PER_EVAL + st_evals[i_pw, 1] * (SAMPLES_PER_EVAL + 8 * SAMPLES_PER_ANCHOR)) / (st_ms[i_pw] * 1e-3) / 1e9 / tex_peak)
     per_arc, arcs = scene_layout(args, world)

@@ -227,6 +227,9 @@ int apde_schedule_num_passes(apde_context *ctx, const apde_schedule *s);
 /* cumulative device counters since the last reset: [0] NCC-Old evals, [1] NCC-New evals, [2] geom evals,
  * [3] kernel launches */
 int apde_get_counters(apde_context *ctx, uint64_t out[4], int reset);
+/* 3x3 anchor patches (9 samples each) sampled by the weak propagation since the last counter reset: with out[1] above the real
+ * sample count of the deformable cost, 36 * out[1] + 9 * anchor_patches (APD.cu:514-563) */
+int apde_get_anchor_evals(apde_context *ctx, uint64_t *anchor_patches);
 
 /* per-kernel profile of the pass: when enabled, every stage launch is bracketed by CUDA events on the launching stream.
  * ms[11], launches[11], evals[11][3] are indexed by apde_stage. */
