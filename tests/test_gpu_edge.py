@@ -109,6 +109,18 @@ def test_fusion_variants_on_uploaded_maps_with_holes():
             assert len(xyz_g) == len(xyz_o)
             assert np.allclose(xyz_g, xyz_o, rtol=1e-5, atol=1e-5)
             assert np.abs(bgr_g - bgr_o).max() <= 1e-3
+    # the cloud of a count-only call is handed over once (apde_fuse_take_points); the direct call with buffers gives the same
+    # points, truncates at max_points, and leaves nothing to take
+    from apde_mvs_b200.binding import ApdeError
+    xyz_a, bgr_a = ctx.fuse(True, variant=0)
+    with pytest.raises(ApdeError):
+        ctx._take_points(len(xyz_a))
+    xyz_b, bgr_b = ctx.fuse(True, max_points=len(xyz_a), variant=0)
+    assert np.array_equal(xyz_a, xyz_b) and np.array_equal(bgr_a, bgr_b)
+    xyz_c, _ = ctx.fuse(True, max_points=100, variant=0)
+    assert len(xyz_c) == 100 and np.array_equal(xyz_c, xyz_a[:100])
+    with pytest.raises(ApdeError):
+        ctx._take_points(10)
     ctx.close()
 
 
