@@ -162,15 +162,34 @@ __global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ 
         if (!((sel >> v) & 1u)) continue;
         const size_t c0 = (size_t)colidx[(size_t)v * Pb + loc];
         const float wv = (float)vw_get(w, v);
+        // loads in batches of kBatch steps (2 x kBatch independent loads in flight per thread), then the FFMAs of the batch
+        constexpr int kBatch = 16;
         if (K.geom) {
 #pragma unroll
-            for (int i = 0; i < kSweepN; ++i) {
-                const size_t o = (size_t)i * ncols + c0;
-                pc[i] = __fmaf_rn(wv, __fmaf_rn(K.geom_factor, geo[o], ncc[o]), pc[i]);  // APD.cu:2179-2181 as built
+            for (int b = 0; b < kSweepN; b += kBatch) {
+                float tn[kBatch], tg[kBatch];
+#pragma unroll
+                for (int i = 0; i < kBatch; ++i)
+                    if (b + i < kSweepN) {
+                        const size_t o = (size_t)(b + i) * ncols + c0;
+                        tn[i] = __ldg(ncc + o);
+                        tg[i] = __ldg(geo + o);
+                    }
+#pragma unroll
+                for (int i = 0; i < kBatch; ++i)
+                    if (b + i < kSweepN) pc[b + i] = __fmaf_rn(wv, __fmaf_rn(K.geom_factor, tg[i], tn[i]), pc[b + i]);  // APD.cu:2179-2181 as built
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < kSweepN; ++i) pc[i] = __fmaf_rn(wv, ncc[(size_t)i * ncols + c0], pc[i]);
+            for (int b = 0; b < kSweepN; b += 2 * kBatch) {
+                float tn[2 * kBatch];
+#pragma unroll
+                for (int i = 0; i < 2 * kBatch; ++i)
+                    if (b + i < kSweepN) tn[i] = __ldg(ncc + (size_t)(b + i) * ncols + c0);
+#pragma unroll
+                for (int i = 0; i < 2 * kBatch; ++i)
+                    if (b + i < kSweepN) pc[b + i] = __fmaf_rn(wv, tn[i], pc[b + i]);
+            }
         }
     }
 #pragma unroll
