@@ -1063,9 +1063,13 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
     if (rc) return rc;
     const auto t0 = std::chrono::steady_clock::now();
     double pm_ms = 0.0;
-    cudaEvent_t evp0, evp1;
-    CU(cudaEventCreate(&evp0));
-    CU(cudaEventCreate(&evp1));
+    struct PassEvents {  // destroyed on every return path
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~PassEvents() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } pass_events;
+    CU(cudaEventCreate(&pass_events.a));
+    CU(cudaEventCreate(&pass_events.b));
+    const cudaEvent_t evp0 = pass_events.a, evp1 = pass_events.b;
     CU(cudaEventRecord(evp0, c->stream));
     while ((int)c->pm_events.size() < 2 * std::max(count, 1)) {
         cudaEvent_t ev;
@@ -1074,6 +1078,7 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
     }
     double exposed_ms = 0.0;
     uint64_t received = 0;
+    const int pass_w = (int)std::round(c->W * (1.0f / (float)scale)), pass_h = (int)std::round(c->H * (1.0f / (float)scale));
     for (int k = 0; k < longest; ++k) {
         if (k < count) {
             const int v = first + k;
@@ -1083,8 +1088,9 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
             CU(cudaEventRecord(c->pm_events[2 * k + 1], c->stream));
             if ((rc = problem_finish_impl(c, jacobi))) return rc;  // no host sync: the host runs ahead of the stream
         }
-        // the k-th views of all ranks travel while the (k + 1)-th are computed
-        if (job && (rc = apde_comm_share_depth_row(c, k, c->cur ^ 1, c->lw, c->lh))) return rc;
+        // the k-th views of all ranks travel while the (k + 1)-th are computed.  The row size is the pass's level size, derived
+        // from the scale as ensure_level does -- a rank that holds no view in this job (more ranks than views) never set one up
+        if (job && (rc = apde_comm_share_depth_row(c, k, c->cur ^ 1, pass_w, pass_h))) return rc;
     }
     if (job && (rc = apde_comm_join(c, &exposed_ms, &received))) return rc;  // the compute stream waits for the last rows
     CU(cudaEventRecord(evp1, c->stream));
@@ -1109,7 +1115,7 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
         if (job) {
             for (int v = 0; v < c->V; ++v) {
                 if (v >= first && v < first + count) continue;
-                c->views[v].mw = c->lw; c->views[v].mh = c->lh;  // the received maps are at the pass resolution
+                c->views[v].mw = pass_w; c->views[v].mh = pass_h;  // the received maps are at the pass resolution
             }
         }
         c->cur ^= 1;
@@ -1119,7 +1125,6 @@ int apde_run_schedule_pass(apde_context *c, const apde_schedule *s, int pass_ind
     if (prof_now) cudaProfilerStop();
     float dev_ms = 0.0f;
     CU(cudaEventElapsedTime(&dev_ms, evp0, evp1));
-    cudaEventDestroy(evp0); cudaEventDestroy(evp1);
     const auto t1 = std::chrono::steady_clock::now();
     if (out) {
         uint64_t c1[4];

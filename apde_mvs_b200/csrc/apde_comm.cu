@@ -144,15 +144,26 @@ int apde_comm_init(apde_context *c, const uint8_t id[APDE_COMM_ID_BYTES], int ra
     CU(cudaSetDevice(c->device));
     Comm *m = new Comm();
     m->rank = rank; m->world = world;
+    auto drop = [&](int rc) {  // a half-built job must not leak its stream / events / communicator
+        if (m->comm) api.CommDestroy(m->comm);
+        if (m->ev_ready) cudaEventDestroy(m->ev_ready);
+        if (m->ev_done) cudaEventDestroy(m->ev_done);
+        if (m->ev_w0) cudaEventDestroy(m->ev_w0);
+        if (m->ev_w1) cudaEventDestroy(m->ev_w1);
+        if (m->stream) cudaStreamDestroy(m->stream);
+        delete m;
+        return rc;
+    };
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&m->ev_w0);
+    if (e == cudaSuccess) e = cudaEventCreate(&m->ev_w1);
+    if (e != cudaSuccess) return drop(fail(APDE_ERR_CUDA, "comm_init: %s", cudaGetErrorString(e)));
     ncclUniqueId u;
     memcpy(&u, id, APDE_COMM_ID_BYTES);
     ncclResult_t r = api.CommInitRank(&m->comm, world, u, rank);
-    if (r != ncclSuccess) { delete m; return fail(APDE_ERR_CUDA, "ncclCommInitRank(rank %d of %d): %s", rank, world, api.GetErrorString(r)); }
-    CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&m->ev_ready, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
-    CU(cudaEventCreate(&m->ev_w0));
-    CU(cudaEventCreate(&m->ev_w1));
+    if (r != ncclSuccess) { m->comm = nullptr; return drop(fail(APDE_ERR_CUDA, "ncclCommInitRank(rank %d of %d): %s", rank, world, api.GetErrorString(r))); }
     c->comm = m;
     return APDE_OK;
 }

@@ -27,6 +27,19 @@ def test_sharded_schedule_and_fusion_match_single_gpu(world, apde_lib):
     assert r.returncode == 0 and "DIST_FUSION_CHECK PASS" in r.stdout
 
 
+def test_more_ranks_than_views(apde_lib):
+    """3 views over 4 GPUs: one rank holds no view, takes part in every exchange round and in the collective fusion, and the job
+    still equals the single-GPU Jacobi run bit for bit"""
+    if _gpus() < 4:
+        pytest.skip("needs 4 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
+           "--master-port", "29719", os.path.join(ROOT, "tools", "dist_fusion_check.py")]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600, env=dict(os.environ, APDE_CHECK_VIEWS="3"))
+    print(r.stdout[-3000:])
+    print(r.stderr[-2000:])
+    assert r.returncode == 0 and "DIST_FUSION_CHECK PASS" in r.stdout
+
+
 def _read_all(folder, V):
     out = {}
     for v in range(V):

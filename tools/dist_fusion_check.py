@@ -15,6 +15,9 @@ from apde_mvs_b200.scene import make_office_scene
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 dist.init_process_group("gloo")
 W, H, V, N = 480, 360, 7, 4  # 7 views over 2 or 4 ranks: ragged shards
+if os.environ.get("APDE_CHECK_VIEWS"):  # e.g. 3 views over 4 ranks: one rank holds no view and only receives
+    V = int(os.environ["APDE_CHECK_VIEWS"])
+    N = min(N, V - 1)
 scene = make_office_scene(W, H, num_views=V, num_src=N, seed=6, weak=0.2, with_color=True)
 ctx = Context(local)
 ctx.load_scene(scene)
