@@ -80,7 +80,8 @@ struct SweepWorkspace {
     size_t map_cap = 0;
     void *scan_tmp = nullptr;
     size_t scan_bytes = 0, flag_cap = 0, col_cap = 0, geo_cap = 0;
-    float *ncc = nullptr, *geo = nullptr;      // [62][ncols] column costs (slot 61 = the current depth)
+    float *ncc = nullptr;                      // [62][ncols] column costs (slot 61 = the current depth); geometric passes: FFMA(geom_factor, geom, ncc)
+    float *geo = nullptr;                      // geometric passes: [22][ncols] = raw NCC [11] and raw geometric cost [11] of the LocalRefine steps
     int ncols = 0;
     int y0 = 0, rows = 0, Pb = 0;              // the band of rows the stored columns cover; Pb = slots (8x4 tiles, padded)
     size_t budget_mb = 0;                      // column storage budget (0 = APDE_SWEEP_BUDGET_MB or 48 GB)

@@ -19,7 +19,8 @@
 
 namespace apde {
 
-constexpr int kSweepR = 30, kSweepN = 61, kSlots = 62;  // slot 61 = the hypothesis at the current depth (LocalRefine's cost_now)
+constexpr int kSweepR = 30, kSweepN = 61, kSlots = 62;
+constexpr int kRefineR = 5, kRefineN = 11, kRefineSlots = 2 * kRefineN;  // LocalRefine's own steps: raw NCC [11] then raw geometric cost [11]  // slot 61 = the hypothesis at the current depth (LocalRefine's cost_now)
 
 // class of a pixel for the sweep: 0 = none, 1 = LocalRefine only (+-5), 2 = DepthToWeak + LocalRefine (+-30)
 __device__ __forceinline__ int sweep_class(const PassK &K, int px, int py, int center, bool dtw) {
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(256) k_sweep_scatter(const int *__restrict__ f
 template <bool U, bool SA>
 __device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, int y0, int rows, int Pb,
                                                        const int *__restrict__ colmap, int ncols, float *__restrict__ ncc,
-                                                       float *__restrict__ geo) {
+                                                       float *__restrict__ lr) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,9 +101,23 @@ __device__ __forceinline__ void k_sweep_columns_body(const PassK &K, int dtw, in
         tp.w = distance_to_origin(K, px, py, p_depth, tp);
         const PlaneM m = plane_row(K, tp);
         const size_t o = (size_t)(current ? kSweepN : pd + kSweepR) * ncols + col;
-        ncc[o] = ncc_old_x<U, SA>(K, vk, px, py, m, rp, si);
+        const float cn = ncc_old_x<U, SA>(K, vk, px, py, m, rp, si);
         n_old++;
-        if (K.geom) { geo[o] = geom_cost(K, vk, v, px, py, tp); n_geom++; }
+        if (K.geom) {
+            // geometric passes store what the consumers add up: the combined cost FFMA(geom_factor, geom, ncc) of every step
+            // (DepthToWeak's curve, LocalRefine's cost_now, APD.cu:2179-2181, 2380-2383) and, for the 11 steps LocalRefine
+            // sweeps, the two terms on their own (it weights them separately, APD.cu:2417-2419): 62 + 22 floats per column
+            // instead of 124
+            const float cg = geom_cost(K, vk, v, px, py, tp);
+            n_geom++;
+            ncc[o] = __fmaf_rn(K.geom_factor, cg, cn);
+            if (!current && pd >= -kRefineR && pd <= kRefineR) {
+                lr[(size_t)(pd + kRefineR) * ncols + col] = cn;
+                lr[(size_t)(kRefineN + pd + kRefineR) * ncols + col] = cg;
+            }
+        } else {
+            ncc[o] = cn;
+        }
     }
     count_evals(K, n_old, 0, n_geom);
 }
@@ -126,8 +141,7 @@ __global__ void __launch_bounds__(128) k_sweep_columns_sa(const __grid_constant_
 // DepthToWeak decision logic, APD.cu:2157-2249
 __global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ PassK K, int y0, int rows, int Pb,
                                                         const int *__restrict__ colidx, int ncols,
-                                                        const float *__restrict__ ncc, const float *__restrict__ geo,
-                                                        float *curve) {
+                                                        const float *__restrict__ ncc, float *curve) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
     const int loc = blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,34 +176,18 @@ __global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ 
         if (!((sel >> v) & 1u)) continue;
         const size_t c0 = (size_t)colidx[(size_t)v * Pb + loc];
         const float wv = (float)vw_get(w, v);
-        // loads in batches of kBatch steps (2 x kBatch independent loads in flight per thread), then the FFMAs of the batch
-        constexpr int kBatch = 16;
-        if (K.geom) {
+        // loads in batches of kBatch steps (independent loads in flight), then the FFMAs of the batch
+        // (in geometric passes a slot already holds FFMA(geom_factor, geom, ncc), APD.cu:2179-2181 as built)
+        constexpr int kBatch = 32;
 #pragma unroll
-            for (int b = 0; b < kSweepN; b += kBatch) {
-                float tn[kBatch], tg[kBatch];
+        for (int b = 0; b < kSweepN; b += kBatch) {
+            float tn[kBatch];
 #pragma unroll
-                for (int i = 0; i < kBatch; ++i)
-                    if (b + i < kSweepN) {
-                        const size_t o = (size_t)(b + i) * ncols + c0;
-                        tn[i] = __ldg(ncc + o);
-                        tg[i] = __ldg(geo + o);
-                    }
+            for (int i = 0; i < kBatch; ++i)
+                if (b + i < kSweepN) tn[i] = __ldg(ncc + (size_t)(b + i) * ncols + c0);
 #pragma unroll
-                for (int i = 0; i < kBatch; ++i)
-                    if (b + i < kSweepN) pc[b + i] = __fmaf_rn(wv, __fmaf_rn(K.geom_factor, tg[i], tn[i]), pc[b + i]);  // APD.cu:2179-2181 as built
-            }
-        } else {
-#pragma unroll
-            for (int b = 0; b < kSweepN; b += 2 * kBatch) {
-                float tn[2 * kBatch];
-#pragma unroll
-                for (int i = 0; i < 2 * kBatch; ++i)
-                    if (b + i < kSweepN) tn[i] = __ldg(ncc + (size_t)(b + i) * ncols + c0);
-#pragma unroll
-                for (int i = 0; i < 2 * kBatch; ++i)
-                    if (b + i < kSweepN) pc[b + i] = __fmaf_rn(wv, tn[i], pc[b + i]);
-            }
+            for (int i = 0; i < kBatch; ++i)
+                if (b + i < kSweepN) pc[b + i] = __fmaf_rn(wv, tn[i], pc[b + i]);
         }
     }
 #pragma unroll
@@ -228,7 +226,7 @@ __global__ void __launch_bounds__(128) k_sweep_classify(const __grid_constant__ 
 // LocalRefine decision logic, APD.cu:2368-2431
 __global__ void __launch_bounds__(128) k_sweep_refine(const __grid_constant__ PassK K, int y0, int rows, int Pb,
                                                       const int *__restrict__ colidx, int ncols,
-                                                      const float *__restrict__ ncc, const float *__restrict__ geo) {
+                                                      const float *__restrict__ ncc, const float *__restrict__ lr) {
     extern __shared__ float smem[];
     const ViewK *s_vk = stage_views(K, smem);
     const int loc = blockIdx.x * blockDim.x + threadIdx.x;
@@ -244,8 +242,7 @@ __global__ void __launch_bounds__(128) k_sweep_refine(const __grid_constant__ Pa
     for (uint32_t mk = sel; mk; mk &= mk - 1) {
         const int v = __ffs(mk) - 1;
         const size_t o = (size_t)kSweepN * ncols + colidx[(size_t)v * Pb + loc];
-        float tc = ncc[o];
-        if (K.geom) tc = __fmaf_rn(K.geom_factor, geo[o], tc);
+        const float tc = ncc[o];  // geometric passes: already FFMA(geom_factor, geom, ncc)
         const float wv = (float)vw_get(w, v);
         cost_now = __fmaf_rn(wv, tc, cost_now);  // APD.cu:2380-2383 as built
         weight_normal = __fadd_rn(weight_normal, wv);
@@ -263,10 +260,14 @@ __global__ void __launch_bounds__(128) k_sweep_refine(const __grid_constant__ Pa
         float tc = 0.0f;
         for (uint32_t mk = sel; mk; mk &= mk - 1) {
             const int v = __ffs(mk) - 1;
-            const size_t o = (size_t)(pd + kSweepR) * ncols + colidx[(size_t)v * Pb + loc];
+            const size_t c0 = (size_t)colidx[(size_t)v * Pb + loc];
             const float wv = (float)vw_get(w, v);
-            tc = __fmaf_rn(wv, ncc[o], tc);  // APD.cu:2417-2419 as built
-            if (K.geom) tc = __fmaf_rn(wv, __fmul_rn(K.geom_factor, geo[o]), tc);
+            if (K.geom) {  // the two terms on their own (see k_sweep_columns)
+                tc = __fmaf_rn(wv, lr[(size_t)(pd + kRefineR) * ncols + c0], tc);  // APD.cu:2417-2419 as built
+                tc = __fmaf_rn(wv, __fmul_rn(K.geom_factor, lr[(size_t)(kRefineN + pd + kRefineR) * ncols + c0]), tc);
+            } else {
+                tc = __fmaf_rn(wv, ncc[(size_t)(pd + kSweepR) * ncols + c0], tc);
+            }
         }
         tc = __fmul_rn(tc, rwn);
         if (tc < min_cost) { min_cost = tc; best_depth = p_depth; }
@@ -306,11 +307,14 @@ cudaError_t SweepWorkspace::reserve_columns(size_t ncols_, bool geom) {
         if (e != cudaSuccess) return e;
         col_cap = cap;
     }
-    if (geom && geo_cap < col_cap) {
+    const size_t need_lr = ncols_ * kRefineSlots;
+    if (geom && geo_cap < need_lr) {
         cudaFree(geo);
-        cudaError_t e = cudaMalloc(&geo, col_cap * sizeof(float));
+        geo = nullptr; geo_cap = 0;
+        const size_t cap = need_lr + need_lr / 8;
+        cudaError_t e = cudaMalloc(&geo, cap * sizeof(float));
         if (e != cudaSuccess) return e;
-        geo_cap = col_cap;
+        geo_cap = cap;
     }
     return cudaSuccess;
 }
@@ -321,8 +325,8 @@ void SweepWorkspace::release() {
 }
 
 // Rows per band so that the WORST-CASE column storage of a band (every view selected at every pixel) stays under the
-// budget: N * Pb * 62 floats (* 2 with the geometric term).  1920x1080 x 10 views fits one band (10.3 GB); 6048x4032 x 10
-// views would need 121 GB in one piece and is processed in 3 bands.  APDE_SWEEP_BUDGET_MB overrides the 48 GB default.
+// budget: N * Pb * 62 floats (84 with the geometric term).  1920x1080 x 10 views fits one band (7.0 GB); 6048x4032 x 10
+// views would need 82 GB in one piece and is processed in 2 bands.  APDE_SWEEP_BUDGET_MB overrides the 48 GB default.
 static int band_rows(const PassK &K, const SweepWorkspace &ws) {
     static const size_t env_mb = [] {
         const char *e = getenv("APDE_SWEEP_BUDGET_MB");
@@ -330,7 +334,7 @@ static int band_rows(const PassK &K, const SweepWorkspace &ws) {
     }();
     const size_t mb = ws.budget_mb ? ws.budget_mb : (env_mb ? env_mb : (size_t)49152);
     const size_t budget = mb << 20;
-    const size_t per_row = (size_t)K.N * K.W * kSlots * sizeof(float) * (K.geom ? 2 : 1);
+    const size_t per_row = (size_t)K.N * K.W * (kSlots + (K.geom ? kRefineSlots : 0)) * sizeof(float);
     const size_t rows = budget / (per_row ? per_row : 1);
     return (int)std::max<size_t>(1, std::min<size_t>(rows, (size_t)K.H));
 }
@@ -363,7 +367,7 @@ static cudaError_t sweep_build_band(const PassK &K, SweepWorkspace &ws, int dtw,
 static cudaError_t sweep_classify_band(const PassK &K, SweepWorkspace &ws, float *curve, cudaStream_t st) {
     if (ws.ncols == 0) return cudaSuccess;
     k_sweep_classify<<<(ws.Pb + 127) / 128, 128, sizeof(float) * views_smem_floats(K.N), st>>>(K, ws.y0, ws.rows, ws.Pb, ws.colidx, ws.ncols, ws.ncc,
-                                                                                              ws.geo, curve);
+                                                                                              curve);
     return cudaGetLastError();
 }
 static cudaError_t sweep_refine_band(const PassK &K, SweepWorkspace &ws, cudaStream_t st) {
