@@ -25,6 +25,9 @@ def parse_args(argv=None):
     p.add_argument('--resume', action='store_true', default=False)
     p.add_argument('--gpu_num', type=int, default=1)
     p.add_argument('--work_num', type=int, default=1)
+    p.add_argument('--gpus_per_scan', type=int, default=1,
+                   help='extension: one scan over this many GPUs (apd --gpus N: views dealt out in blocks, depth maps exchanged over '
+                        'NCCL); --gpu_num GPUs then make gpu_num // gpus_per_scan slots')
     p.add_argument('--scans', type=str, nargs='+', default=[])
     p.add_argument('--only_fuse', action='store_true', default=False)
     p.add_argument('--no_fuse', action='store_true', default=False)
@@ -108,10 +111,13 @@ def dataset_tag(data_dir, scan):
 def build_command(args, scan_dir, scan, gpu_index):
     b = lambda v: 'true' if v else 'false'  # noqa: E731
     use_sa = not args.no_sam and os.path.isdir(os.path.join(scan_dir, 'sa_masks'))  # run.py:94-98 without the SAM runner
-    return [args.APD_path, '--dense_folder', scan_dir, '--gpu_index', str(gpu_index), '--dataset', dataset_tag(args.data_dir, scan),
-            '--only_fuse', b(args.only_fuse), '--no_fuse', b(args.no_fuse), '--use_sa', b(use_sa), '--memory_cache', b(args.memory_cache),
-            '--flush', b(args.flush), '--export_anchor', b(args.export_anchor), '--export_curve', b(args.export_curve),
-            '--export_color', b(not args.no_color), '--use_impetus', b(not args.no_impetus), '--weak_filter', b(not args.no_weak_filter)]
+    cmd = [args.APD_path, '--dense_folder', scan_dir, '--gpu_index', str(gpu_index), '--dataset', dataset_tag(args.data_dir, scan),
+           '--only_fuse', b(args.only_fuse), '--no_fuse', b(args.no_fuse), '--use_sa', b(use_sa), '--memory_cache', b(args.memory_cache),
+           '--flush', b(args.flush), '--export_anchor', b(args.export_anchor), '--export_curve', b(args.export_curve),
+           '--export_color', b(not args.no_color), '--use_impetus', b(not args.no_impetus), '--weak_filter', b(not args.no_weak_filter)]
+    if args.gpus_per_scan > 1:  # the slot's GPUs: gpu_index .. gpu_index + gpus_per_scan - 1
+        cmd += ['--gpus', str(args.gpus_per_scan), '--gpu_list', ','.join(str(gpu_index + g) for g in range(args.gpus_per_scan))]
+    return cmd
 
 
 def _init(pp, ll, aa):
@@ -137,7 +143,7 @@ def worker(scan):
                 pos_index = j
                 break
     try:
-        gpu_index = pos_index // args.work_num
+        gpu_index = (pos_index // args.work_num) * args.gpus_per_scan
         apd_dir = os.path.join(scan_dir, 'APD')
         os.makedirs(apd_dir, exist_ok=True)
         if args.resume and os.path.exists(os.path.join(apd_dir, 'APD.ply')):
@@ -189,7 +195,10 @@ def main(argv=None):
         return 0
     counted.sort(key=lambda x: -x[0])
     scans = [s for _, s in counted]
-    total = a.gpu_num * a.work_num
+    if a.gpus_per_scan < 1 or a.gpu_num % a.gpus_per_scan:
+        print('--gpu_num must be a multiple of --gpus_per_scan')
+        return 1
+    total = (a.gpu_num // a.gpus_per_scan) * a.work_num
     positions = mp.Array('i', [0] * total)
     lock = mp.Lock()
     with mp.Pool(total, initializer=_init, initargs=(positions, lock, a)) as pool:

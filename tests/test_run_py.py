@@ -44,6 +44,25 @@ def test_dry_run_commands_layout_and_order(tmp_path):
     assert not os.path.exists(os.path.join(root2, "s", "images")) and "--dense_folder" not in out.stdout
 
 
+def test_gpus_per_scan_slots(tmp_path):
+    """--gpus_per_scan N: gpu_num // N slots, every command names its slot's devices for `apd --gpus N`"""
+    root = str(tmp_path / "scenes")
+    for k in range(3):
+        _mk(root, "scan%d" % k, "images", ["%08d.png" % i for i in range(3 - k)])
+    out = subprocess.run([sys.executable, RUN, "--data_dir", root, "--dry_run", "--gpu_num", "8", "--gpus_per_scan", "4"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = [l for l in out.stdout.splitlines() if "--dense_folder" in l]
+    assert len(lines) == 3
+    lists = sorted(l.split("--gpu_list ")[1].split()[0] for l in lines)
+    assert set(lists) <= {"0,1,2,3", "4,5,6,7"} and all("--gpus 4" in l for l in lines)
+    for l in lines:
+        assert "--gpu_index %s " % l.split("--gpu_list ")[1].split(",")[0] in l
+    bad = subprocess.run([sys.executable, RUN, "--data_dir", root, "--dry_run", "--gpu_num", "6", "--gpus_per_scan", "4"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "multiple of" in bad.stdout
+    one = subprocess.run([sys.executable, RUN, "--data_dir", root, "--dry_run", "--gpu_num", "2"], capture_output=True, text=True)
+    assert "--gpus" not in one.stdout.replace("--gpus_per_scan", "")
+
+
 def test_dataset_tags_and_reservation():
     sys.path.insert(0, ROOT)
     import importlib
