@@ -507,12 +507,13 @@ cudaError_t launch_stage_apd(const PassK &K, int stage, int iter, int color, cud
             const int ylimit = min(H, half_rows_limit(H));
             const int threads = prop_block_threads(N);
             const size_t smem = sizeof(float) * ((size_t)views_smem_floats(N) + (size_t)9 * N * threads);
-            static size_t configured = 0;
-            if (smem > configured) {
+            static SmemOptIn configured;
+            int dev = 0;
+            if (configured.needed(smem, &dev)) {
                 cudaError_t e = cudaFuncSetAttribute(k_prop_weak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(k_prop_weak_sa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
-                configured = smem;
+                configured.done(smem, dev);
             }
             const int tiles = half_tiles(K, ylimit);
             const int tiles8x = half_tiles_x(K);

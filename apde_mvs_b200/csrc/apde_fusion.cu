@@ -18,6 +18,7 @@
 #include <climits>
 
 #include <map>
+#include <mutex>
 
 namespace apde {
 
@@ -25,11 +26,13 @@ namespace apde {
 // kernels.  Blocks are therefore recycled through a small exact-size pool (per device), emptied by fusion_release_cache().
 static std::multimap<std::pair<int, size_t>, void *> g_pool;
 static std::map<void *, std::pair<int, size_t>> g_live;
+static std::mutex g_pool_mutex;  // the contexts of a multi-GPU job (a host thread each) filter their views concurrently
 template <typename T>
 static cudaError_t pool_malloc(T **p, size_t bytes) {
     int dev = 0;
     cudaGetDevice(&dev);
     const auto key = std::make_pair(dev, bytes);
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
     auto it = g_pool.find(key);
     if (it != g_pool.end()) {
         *p = static_cast<T *>(it->second);
@@ -44,12 +47,14 @@ static cudaError_t pool_malloc(T **p, size_t bytes) {
 }
 static void pool_free(void *p) {
     if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
     auto it = g_live.find(p);
     if (it == g_live.end()) { cudaFree(p); return; }
     g_pool.emplace(it->second, p);
     g_live.erase(it);
 }
 void fusion_release_cache() {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
     for (auto &kv : g_pool) cudaFree(kv.second);
     g_pool.clear();
 }

@@ -816,12 +816,13 @@ cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStr
             if (v1 || sa) {  // per-lane refinement loop (kept for A/B measurements and as the parity twin of the compacted kernel)
                 const int threads = prop_block_threads(N);
                 const size_t smem = prop_smem_bytes(N, threads);
-                static size_t configured = 0;
-                if (smem > configured) {
+                static SmemOptIn configured;
+                int dev = 0;
+                if (configured.needed(smem, &dev)) {
                     cudaError_t e = cudaFuncSetAttribute(k_prop_strong_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_prop_strong_sa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     if (e != cudaSuccess) return e;
-                    configured = smem;
+                    configured.done(smem, dev);
                 }
                 const int wpb = threads / 32;
                 if (sa) k_prop_strong_sa<<<(tiles + wpb - 1) / wpb, threads, smem, st>>>(K, iter, color, tiles8x, ylimit);
@@ -833,11 +834,12 @@ cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStr
             auto bytes = [&](int threads) { return sizeof(float) * ((size_t)views_smem_floats(N) + (size_t)(strong_column_floats(N, u8) + (N + 1) / 2) * threads); };
             const int threads = bytes(128) <= 72 * 1024 ? 128 : (bytes(64) <= 100 * 1024 ? 64 : 32);
             const size_t smem = bytes(threads);
-            static size_t configured = 0;
-            if (smem > configured) {
+            static SmemOptIn configured;
+            int dev = 0;
+            if (configured.needed(smem, &dev)) {
                 cudaError_t e = cudaFuncSetAttribute(k_prop_strong, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
-                configured = smem;
+                configured.done(smem, dev);
                 // experiment knob: shared-memory carve-out in per cent (less shared memory = fewer resident CTAs, more L1/TEX cache)
                 if (const char *co = getenv("APDE_STRONG_CARVEOUT"))
                     cudaFuncSetAttribute(k_prop_strong, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));

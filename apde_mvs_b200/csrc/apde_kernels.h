@@ -2,9 +2,25 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "apde_device.cuh"
 
 namespace apde {
+
+// High-water mark, PER DEVICE, of the dynamic shared memory a kernel has been opted in to (cudaFuncSetAttribute acts on the
+// current device's instance of the function, and the contexts of a multi-GPU job -- one host thread per GPU -- share the process).
+struct SmemOptIn {
+    std::atomic<size_t> mark[64];
+    SmemOptIn() { for (auto &m : mark) m.store(0); }
+    // true: the caller must (re)configure its kernels for `smem` on the current device, then call done(smem)
+    bool needed(size_t smem, int *dev) const {
+        cudaGetDevice(dev);
+        return smem > mark[*dev & 63].load(std::memory_order_acquire);
+    }
+    void done(size_t smem, int dev) { mark[dev & 63].store(smem, std::memory_order_release); }
+};
+
 
 // run one kernel of the pass (stage ids of include/apde.h).  curve: optional [P][61] export of DepthToWeak.
 cudaError_t launch_stage(const PassK &K, int stage, int iter, int color, cudaStream_t st, float *curve);

@@ -61,8 +61,8 @@ def test_apd_cli_job_equals_single_gpu_jacobi(world, tmp_path, apde_lib):
     from apde_mvs_b200 import build as b
     from apde_mvs_b200.scene import make_office_scene
     apd = b.build_host()
-    V = 7  # ragged blocks
-    scene = make_office_scene(480, 360, num_views=V, num_src=4, seed=6, weak=0.2, with_color=True)
+    V = 11  # ragged blocks; 10 source views: the strong propagation needs its opt-in to > 48 KB of shared memory on EVERY device
+    scene = make_office_scene(480, 360, num_views=V, num_src=10, seed=6, weak=0.2, with_color=True)
     one, many = str(tmp_path / "one"), str(tmp_path / "many")
     scene.write_dense_folder(one)
     shutil.copytree(one, many)
