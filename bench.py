@@ -356,7 +356,7 @@ def run_ours(args, rank, world, local_rank):
                            "source_reads_crossing_ranks": int(cross_total), "source_reads_total": int(V * args.src),
                            "collective": "ncclBroadcast per finished view (grouped over the ranks) on a second stream, overlapped with the next view",
                            "job_check": job_check}
-    if not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:  # rank 0 at N = 1 only
         out["cpu_baseline"] = cpu_baseline(args, scene, evals_total / args.steps / V)
     if world == 1 and not args.no_fusion:
         out["fusion"] = fusion_report(args, ctx, scene, cpu=not args.no_cpu_baseline)
